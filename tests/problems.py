@@ -1,0 +1,71 @@
+"""Spec dicts (the plain-data problem format shared by the oracle and the product compiler)
+built straight from the synthetic ingredients -- independent of the product's API classes, so
+``tests/test_compile.py`` can check that ``bayesbay_b200._compile`` emits the same thing."""
+import numpy as np
+
+from bayesbay_b200 import synthetic
+
+
+def _prior(p):
+    p = dict(p)
+    kind = p.pop("kind", "uniform")
+    if kind == "uniform":
+        a, b = p["vmin"], p["vmax"]
+    elif kind == "gaussian":
+        a, b = p["mean"], p["std"]
+    else:
+        a, b = p["mean"], p["scale"]
+    return dict(name=p["name"], kind=kind, a=float(a), b=float(b), perturb_std=float(p["perturb_std"]),
+                perturb_std_birth=float(p.get("perturb_std_birth") or p["perturb_std"]))
+
+
+def _target(ing, forward):
+    t = ing["target"]
+    return dict(name=t["name"], dobs=np.asarray(ing["d_obs"], dtype=np.float64), hierarchical=True,
+                std_min=float(t["std_min"]), std_max=float(t["std_max"]), std_perturb_std=float(t["std_perturb_std"]),
+                cov_inv=None, forward=forward)
+
+
+def spec_from_ingredients(ing):
+    kind = ing["kind"]
+    if kind in ("tomography_2d", "partition_1d"):
+        v = ing["voronoi"]
+        ndim = 2 if kind == "tomography_2d" else 1
+        kmin, kmax = v["n_dimensions_min"], v["n_dimensions_max"]
+        space = dict(
+            name=v["name"], kind="voronoi2d" if ndim == 2 else "voronoi1d", ndim=ndim, trans_d=True,
+            kmin=kmin, kmax=kmax, kinit_max=int((kmax - kmin) * 0.3 + kmin),
+            vmin=[float(x) for x in np.atleast_1d(v["vmin"])], vmax=[float(x) for x in np.atleast_1d(v["vmax"])],
+            site_std=[float(v["perturb_std"])] * ndim, birth_from=v["birth_from"],
+            params=[_prior(ing["prior"])], weights=dict(birth=1, death=1, values=3, sites=1),
+        )
+        if ndim == 2:
+            fwd = dict(kind="ray2d", space=0, param=0, transform="reciprocal", indptr=ing["indptr"],
+                       indices=ing["indices"], data=ing["data"], points=ing["points"])
+        else:
+            fwd = dict(kind="lookup1d", space=0, param=0, x=ing["x"])
+    elif kind == "polyfit":
+        space = dict(name=ing["space"]["name"], kind="plain", ndim=0, trans_d=False, kmin=1, kmax=1, kinit_max=1,
+                     vmin=[], vmax=[], site_std=[], birth_from="prior", params=[_prior(p) for p in ing["priors"]],
+                     weights=dict(birth=0, death=0, values=3, sites=0))
+        fwd = dict(kind="linear", space=0, params=[0, 1, 2, 3], G=ing["G"])
+    else:
+        raise ValueError(kind)
+    return dict(spaces=[space], targets=[_target(ing, fwd)])
+
+
+def tomo_small():
+    return synthetic.tomography_2d(nx=12, ny=10, n_sources_per_side=3, n_receivers=5, kmin=4, kmax=20)
+
+
+def partition_small(birth_from="prior"):
+    return synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from=birth_from)
+
+
+REPLAYS = {
+    "tomo_small": tomo_small,
+    "partition_1d": partition_small,
+    "partition_1d_nb": lambda: partition_small("neighbour"),
+    "polyfit": synthetic.polyfit,
+    "polyfit_nb": lambda: synthetic.polyfit(all_gaussian=False),
+}
