@@ -1,0 +1,315 @@
+"""Device engine: owns the HBM buffers (torch tensors, buffer management only) and drives the
+CUDA kernels of ``libbbb200.so`` through its C ABI.
+
+State layout: every per-chain array is structure-of-arrays with
+the chain index fastest and cells padded to ``n_dimensions_max`` --
+``sites [2][ndim][K][C]``, ``values [2][P][K][C]``, ``k [2][C]`` per parameter space (two slots:
+current / proposed, selected per chain by ``sel[C]``), ``cell_idx [2][G][C]`` (uint8 when
+K <= 256) per ray target, and ``[C]`` scalars (sigma, phi = sum of squared residuals,
+temperature, iteration, counters).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_PRIOR_KIND = {"uniform": L.PRIOR_UNIFORM, "gaussian": L.PRIOR_GAUSSIAN, "laplace": L.PRIOR_LAPLACE}
+_SPACE_KIND = {"plain": L.SPACE_PLAIN, "voronoi1d": L.SPACE_VORONOI1D, "voronoi2d": L.SPACE_VORONOI2D}
+_FWD_KIND = {"ray2d": L.FWD_RAY2D, "lookup1d": L.FWD_LOOKUP1D, "linear": L.FWD_LINEAR}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One engine per (process, device).  ``spec`` is the plain-data problem description emitted by
+    :func:`bayesbay_b200._compile.compile_problem`."""
+
+    def __init__(self, spec: dict, n_chains: int, device="cuda:0", seed: int = 0, chain_id0: int = 0,
+                 tape: Optional[np.ndarray] = None):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("bayesbay_b200 needs a CUDA device (no CPU fallback)")
+        self.spec = spec
+        self.device = torch.device(device)
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.C = int(n_chains)
+        self.seed = int(seed)
+        self.chain_id0 = int(chain_id0)
+        self._keep: List[torch.Tensor] = []  # device constants borrowed by the C side
+        self._handle = C.c_void_p()
+        self._cspec = self._build_spec()
+        L.check(self.lib.bbb_engine_create(C.byref(self._cspec), self.dev_index, C.byref(self._handle)))
+        self._alloc(tape)
+        L.check(self.lib.bbb_engine_bind_buffers(self._handle, C.byref(self._cbuf)))
+
+    # ------------------------------------------------------------------ spec / buffers
+    def _const(self, arr, dtype):
+        t = torch.as_tensor(np.ascontiguousarray(arr, dtype=dtype)).to(self.device)
+        self._keep.append(t)
+        return t
+
+    def _build_spec(self) -> L.ProblemSpec:
+        spec = self.spec
+        ps = L.ProblemSpec()
+        if len(spec["spaces"]) > L.MAX_SPACES or len(spec["targets"]) > L.MAX_TARGETS:
+            raise ValueError("too many parameter spaces / targets for the device engine")
+        ps.n_spaces = len(spec["spaces"])
+        ps.n_targets = len(spec["targets"])
+        ps.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        for i, sp in enumerate(spec["spaces"]):
+            s = ps.spaces[i]
+            s.kind = _SPACE_KIND[sp["kind"]]
+            s.ndim = sp["ndim"]
+            s.trans_d = int(bool(sp["trans_d"]))
+            s.kmin, s.kmax, s.kinit_max = sp["kmin"], sp["kmax"], sp["kinit_max"]
+            s.birth_from = L.BIRTH_FROM_NEIGHBOUR if sp["birth_from"] == "neighbour" else L.BIRTH_FROM_PRIOR
+            if len(sp["params"]) > L.MAX_PARAMS:
+                raise ValueError(f"parameter space {sp['name']!r}: more than {L.MAX_PARAMS} parameters")
+            s.n_params = len(sp["params"])
+            for d in range(sp["ndim"]):
+                s.vmin[d], s.vmax[d], s.site_std[d] = sp["vmin"][d], sp["vmax"][d], sp["site_std"][d]
+            w = sp["weights"]
+            s.w_birth, s.w_death, s.w_values, s.w_sites = w["birth"], w["death"], w["values"], w["sites"]
+            for j, p in enumerate(sp["params"]):
+                s.prior_kind[j] = _PRIOR_KIND[p["kind"]]
+                s.prior_a[j], s.prior_b[j] = p["a"], p["b"]
+                s.perturb_std[j], s.perturb_std_birth[j] = p["perturb_std"], p["perturb_std_birth"]
+        for i, tg in enumerate(spec["targets"]):
+            t = ps.targets[i]
+            dobs = self._const(tg["dobs"], np.float64)
+            t.n_data = dobs.numel()
+            t.dobs = dobs.data_ptr()
+            if tg["hierarchical"]:
+                t.cov_kind = L.COV_HIERARCHICAL
+                t.std_min, t.std_max, t.std_perturb_std = tg["std_min"], tg["std_max"], tg["std_perturb_std"]
+            elif np.isscalar(tg["cov_inv"]):
+                t.cov_kind = L.COV_SCALAR
+                t.cov_scalar = float(tg["cov_inv"])
+            else:
+                cov = np.asarray(tg["cov_inv"], dtype=np.float64)
+                if cov.ndim != 1 or cov.size != t.n_data:
+                    raise ValueError("only scalar or per-datum (1-D) inverse covariances run on the device")
+                t.cov_kind = L.COV_VECTOR
+                t.cov_vec = self._const(cov, np.float64).data_ptr()
+            f = tg["forward"]
+            t.fwd_kind = _FWD_KIND[f["kind"]]
+            t.space = f["space"]
+            if f["kind"] == "ray2d":
+                t.param = f["param"]
+                t.transform = L.TRANSFORM_RECIPROCAL if f.get("transform", "reciprocal") == "reciprocal" else L.TRANSFORM_IDENTITY
+                pts = np.asarray(f["points"], dtype=np.float64)
+                t.n_points = pts.shape[0]
+                t.nnz = int(np.asarray(f["indices"]).size)
+                if np.asarray(f["indptr"]).size != t.n_data + 1:
+                    raise ValueError("ray matrix rows do not match the number of data")
+                if t.nnz and int(np.max(f["indices"])) >= t.n_points:
+                    raise ValueError("ray matrix column index outside the query grid")
+                t.indptr = self._const(f["indptr"], np.int32).data_ptr()
+                t.indices = self._const(f["indices"], np.int32).data_ptr()
+                t.data = self._const(f["data"], np.float64).data_ptr()
+                t.points_x = self._const(pts[:, 0], np.float64).data_ptr()
+                t.points_y = self._const(pts[:, 1], np.float64).data_ptr()
+            elif f["kind"] == "lookup1d":
+                t.param = f["param"]
+                x = np.asarray(f["x"], dtype=np.float64)
+                if x.size != t.n_data:
+                    raise ValueError("lookup positions do not match the number of data")
+                t.x = self._const(x, np.float64).data_ptr()
+            else:
+                G = np.asarray(f["G"], dtype=np.float64)
+                K = spec["spaces"][f["space"]]["kmax"]
+                if G.shape != (t.n_data, len(f["params"]) * K):
+                    raise ValueError(f"linear operator shape {G.shape} != ({t.n_data}, {len(f['params']) * K})")
+                t.n_lin_params = len(f["params"])
+                for q, p in enumerate(f["params"]):
+                    t.lin_params[q] = p
+                t.G = self._const(G, np.float64).data_ptr()
+        return ps
+
+    def _alloc(self, tape):
+        Cn, dev = self.C, self.device
+        f64, i32, i64, u8 = torch.float64, torch.int32, torch.int64, torch.uint8
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+        b = L.Buffers()
+        b.n_chains, b.chain_id0 = Cn, self.chain_id0
+        self.sites, self.values, self.k, self.sel = [], [], [], []
+        for i, sp in enumerate(self.spec["spaces"]):
+            K, nd, P = sp["kmax"], sp["ndim"], len(sp["params"])
+            self.sites.append(z((2, nd, K, Cn), f64) if nd else None)
+            self.values.append(z((2, P, K, Cn), f64) if P else None)
+            self.k.append(z((2, Cn), i32))
+            self.sel.append(z((Cn,), u8))
+            b.sites[i], b.values[i] = _ptr(self.sites[i]), _ptr(self.values[i])
+            b.k[i], b.sel[i] = _ptr(self.k[i]), _ptr(self.sel[i])
+        self.sigma, self.phi, self.cell_idx, self.idx_sel, self.partial = [], [], [], [], []
+        for i, tg in enumerate(self.spec["targets"]):
+            self.sigma.append(torch.ones((2, Cn), dtype=f64, device=dev) if tg["hierarchical"] else None)
+            self.phi.append(z((2, Cn), f64))
+            if tg["forward"]["kind"] == "ray2d":
+                K = self.spec["spaces"][tg["forward"]["space"]]["kmax"]
+                G = int(np.asarray(tg["forward"]["points"]).shape[0])
+                tiles = int(self.lib.bbb_ray_tiles(int(np.asarray(tg["dobs"]).size)))
+                self.cell_idx.append(z((2, G, Cn), u8 if K <= 256 else torch.int16))
+                self.idx_sel.append(z((Cn,), u8))
+                self.partial.append(z((tiles, Cn), f64))
+            else:
+                self.cell_idx.append(None)
+                self.idx_sel.append(None)
+                self.partial.append(None)
+            b.sigma[i], b.phi[i] = _ptr(self.sigma[i]), _ptr(self.phi[i])
+            b.cell_idx[i], b.idx_sel[i], b.partial[i] = _ptr(self.cell_idx[i]), _ptr(self.idx_sel[i]), _ptr(self.partial[i])
+        nm = 4 * len(self.spec["spaces"]) + 1
+        self.temperature = torch.ones((Cn,), dtype=f64, device=dev)
+        self.iteration = z((Cn,), i64)
+        self.move = z((Cn,), i32)
+        self.edit = z((2, Cn), i32)
+        self.log_prob_ratio = z((Cn,), f64)
+        self.log_like_ratio = z((Cn,), f64)
+        self.accepted = z((Cn,), i32)
+        self.n_proposed = z((nm, Cn), i64)
+        self.n_accepted = z((nm, Cn), i64)
+        self.draw_cursor = z((Cn,), i64)
+        b.temperature, b.iteration = _ptr(self.temperature), _ptr(self.iteration)
+        b.move, b.edit = _ptr(self.move), _ptr(self.edit)
+        b.log_prob_ratio, b.log_like_ratio, b.accepted = _ptr(self.log_prob_ratio), _ptr(self.log_like_ratio), _ptr(self.accepted)
+        b.n_proposed, b.n_accepted = _ptr(self.n_proposed), _ptr(self.n_accepted)
+        b.tape_cursor = _ptr(self.draw_cursor)
+        self.tape = None
+        if tape is not None:
+            tape = np.ascontiguousarray(tape, dtype=np.float64)
+            if tape.ndim != 2 or tape.shape[0] != Cn:
+                raise ValueError("tape must be [n_chains][length]")
+            self.tape = torch.as_tensor(tape).to(dev)
+            b.tape, b.tape_stride = _ptr(self.tape), tape.shape[1]
+        self._cbuf = b
+
+    # ------------------------------------------------------------------ driving
+    @property
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def init_states(self):
+        L.check(self.lib.bbb_engine_init_states(self._handle, self._stream))
+
+    def refresh(self):
+        L.check(self.lib.bbb_engine_refresh(self._handle, self._stream))
+
+    def step(self, n_steps: int = 1):
+        L.check(self.lib.bbb_engine_step(self._handle, int(n_steps), self._stream))
+
+    def gather_space(self, s: int):
+        sp = self.spec["spaces"][s]
+        K, nd, P = sp["kmax"], sp["ndim"], len(sp["params"])
+        k = torch.empty((self.C,), dtype=torch.int32, device=self.device)
+        sites = torch.empty((nd, K, self.C), dtype=torch.float64, device=self.device) if nd else None
+        vals = torch.empty((P, K, self.C), dtype=torch.float64, device=self.device) if P else None
+        L.check(self.lib.bbb_engine_gather_space(self._handle, s, _ptr(k), _ptr(sites), _ptr(vals), self._stream))
+        return k, sites, vals
+
+    def dpred(self, t: int) -> torch.Tensor:
+        R = int(np.asarray(self.spec["targets"][t]["dobs"]).size)
+        out = torch.empty((R, self.C), dtype=torch.float64, device=self.device)
+        L.check(self.lib.bbb_engine_dpred(self._handle, t, _ptr(out), self._stream))
+        return out
+
+    def misfit_logdet(self):
+        m = torch.empty((self.C,), dtype=torch.float64, device=self.device)
+        ld = torch.empty((self.C,), dtype=torch.float64, device=self.device)
+        L.check(self.lib.bbb_engine_misfit_logdet(self._handle, _ptr(m), _ptr(ld), self._stream))
+        return m, ld
+
+    def current_cell_idx(self, t: int) -> torch.Tensor:
+        """[G][C] nearest-site index of the current states of ray target ``t``."""
+        sel = self.idx_sel[t].long()
+        idx = self.cell_idx[t]
+        return torch.where(sel[None, :] == 0, idx[0], idx[1])
+
+    # ------------------------------------------------------------------ host <-> device state
+    def load_states(self, states: List[dict], temperatures=None):
+        """Write starting states.  ``states[c]`` = ``{"spaces": [{"k", "sites", "values": [..]}],
+        "sigma": [..]}`` (numpy).  Resets slots and re-evaluates the forward of every chain."""
+        if len(states) != self.C:
+            raise ValueError(f"expected {self.C} starting states, got {len(states)}")
+        for s, sp in enumerate(self.spec["spaces"]):
+            K, nd, P = sp["kmax"], sp["ndim"], len(sp["params"])
+            k = np.array([st["spaces"][s]["k"] for st in states], dtype=np.int32)
+            if (k < sp["kmin"]).any() or (k > sp["kmax"]).any():
+                raise ValueError(f"starting state: n_dimensions outside [{sp['kmin']}, {sp['kmax']}]")
+            if nd:
+                sites = np.zeros((nd, K, self.C))
+                for c, st in enumerate(states):
+                    sites[:, : k[c], c] = np.asarray(st["spaces"][s]["sites"], dtype=np.float64).reshape(k[c], nd).T
+                self.sites[s][0].copy_(torch.as_tensor(sites))
+            if P:
+                vals = np.zeros((P, K, self.C))
+                for c, st in enumerate(states):
+                    for p in range(P):
+                        vals[p, : k[c], c] = st["spaces"][s]["values"][p]
+                self.values[s][0].copy_(torch.as_tensor(vals))
+            self.k[s].copy_(torch.as_tensor(np.stack((k, k))))
+            self.sel[s].zero_()
+        for t, tg in enumerate(self.spec["targets"]):
+            if tg["hierarchical"]:
+                sg = np.array([st["sigma"][t] for st in states], dtype=np.float64)
+                self.sigma[t].copy_(torch.as_tensor(np.stack((sg, sg))))
+            if self.idx_sel[t] is not None:
+                self.idx_sel[t].zero_()
+        if temperatures is not None:
+            self.temperature.copy_(torch.as_tensor(np.asarray(temperatures, dtype=np.float64)))
+        self.refresh()
+
+    def fetch_states(self) -> List[dict]:
+        """Current state of every chain as host dicts (inverse of :meth:`load_states`)."""
+        out = [dict(spaces=[], sigma=[]) for _ in range(self.C)]
+        for s, sp in enumerate(self.spec["spaces"]):
+            k, sites, vals = self.gather_space(s)
+            k = k.cpu().numpy()
+            sites = None if sites is None else sites.cpu().numpy()
+            vals = None if vals is None else vals.cpu().numpy()
+            for c in range(self.C):
+                kc = int(k[c])
+                st = dict(k=kc, sites=None, values=[])
+                if sites is not None:
+                    a = sites[:, :kc, c].T.copy()
+                    st["sites"] = a[:, 0] if sp["ndim"] == 1 else a
+                if vals is not None:
+                    st["values"] = [vals[p, :kc, c].copy() for p in range(vals.shape[0])]
+                out[c]["spaces"].append(st)
+        for t, tg in enumerate(self.spec["targets"]):
+            sg = self.sigma[t][0].cpu().numpy() if tg["hierarchical"] else None
+            for c in range(self.C):
+                out[c]["sigma"].append(None if sg is None else float(sg[c]))
+        return out
+
+    def close(self):
+        if self._handle:
+            self.lib.bbb_engine_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pt_swap(gathered: torch.Tensor, seed: int, round_: int, id0: int, n_local: int,
+            tape: Optional[torch.Tensor] = None):
+    """Run one parallel-tempering swap round on ``gathered`` [n_total][3] (misfit, logdet, T).
+    Returns ``(local temperatures [n_local], number of accepted swaps)``."""
+    lib = L.load()
+    n_total = gathered.shape[0]
+    assert gathered.is_contiguous() and gathered.dtype == torch.float64
+    t_out = torch.empty((n_local,), dtype=torch.float64, device=gathered.device)
+    n_acc = torch.zeros((1,), dtype=torch.int32, device=gathered.device)
+    stream = C.c_void_p(torch.cuda.current_stream(gathered.device).cuda_stream)
+    L.check(lib.bbb_pt_swap(_ptr(gathered), n_total, seed & 0xFFFFFFFFFFFFFFFF, int(round_), int(id0), int(n_local),
+                            _ptr(t_out), _ptr(n_acc), _ptr(tape), stream))
+    return t_out, n_acc

@@ -1,0 +1,403 @@
+// extern "C" boundary of libbbb200.so (see include/bbb200.h).  Host-side only: validates the spec,
+// keeps a device copy of (spec, buffers) and enqueues kernels on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "kernels.h"
+
+using namespace bbb;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(int err, const char *what) {
+    return fail(BBB_ERR_CUDA, "%s: CUDA error %d (%s)", what, err, cudaGetErrorString((cudaError_t)err));
+}
+#define CU(expr)                                               \
+    do {                                                       \
+        int _e = (int)(expr);                                  \
+        if (_e != 0) return cuda_fail(_e, #expr);              \
+    } while (0)
+
+struct bbb_engine {
+    EngineParams host;
+    EngineParams *dev;
+    int device;
+    bool bound;
+    bool has_ray;
+};
+
+extern "C" {
+
+int bbb_abi_version(void) { return BBB_ABI_VERSION; }
+const char *bbb_last_error(void) { return g_err; }
+int64_t bbb_ray_tiles(int64_t n_data) { return (n_data + RAY_TILE - 1) / RAY_TILE; }
+
+static int validate_spec(const bbb_problem_spec *P) {
+    if (P->n_spaces < 1 || P->n_spaces > BBB_MAX_SPACES) return fail(BBB_ERR_INVALID, "n_spaces out of range");
+    if (P->n_targets < 1 || P->n_targets > BBB_MAX_TARGETS) return fail(BBB_ERR_INVALID, "n_targets out of range");
+    for (int s = 0; s < P->n_spaces; ++s) {
+        const bbb_space_spec &S = P->spaces[s];
+        if (S.kind < BBB_SPACE_PLAIN || S.kind > BBB_SPACE_VORONOI2D) return fail(BBB_ERR_INVALID, "space %d: bad kind", s);
+        const int want_ndim = S.kind == BBB_SPACE_PLAIN ? 0 : (S.kind == BBB_SPACE_VORONOI1D ? 1 : 2);
+        if (S.ndim != want_ndim) return fail(BBB_ERR_INVALID, "space %d: ndim %d does not match kind", s, S.ndim);
+        if (S.kmin < 1 || S.kmax < S.kmin) return fail(BBB_ERR_INVALID, "space %d: need 1 <= kmin <= kmax", s);
+        if (S.kmax > 65535) return fail(BBB_ERR_UNSUPPORTED, "space %d: kmax > 65535", s);
+        if (!S.trans_d && S.kmin != S.kmax) return fail(BBB_ERR_INVALID, "space %d: fixed dimension needs kmin == kmax", s);
+        if (S.trans_d && (S.kinit_max < S.kmin || S.kinit_max > S.kmax))
+            return fail(BBB_ERR_INVALID, "space %d: kinit_max outside [kmin, kmax]", s);
+        if (S.n_params < 0 || S.n_params > BBB_MAX_PARAMS) return fail(BBB_ERR_INVALID, "space %d: n_params", s);
+        if (S.w_birth < 0 || S.w_death < 0 || S.w_values < 0 || S.w_sites < 0 ||
+            S.w_birth + S.w_death + S.w_values + S.w_sites <= 0)
+            return fail(BBB_ERR_INVALID, "space %d: move weights", s);
+        if (!S.trans_d && (S.w_birth > 0 || S.w_death > 0)) return fail(BBB_ERR_INVALID, "space %d: birth/death on a fixed space", s);
+        if (S.kind == BBB_SPACE_PLAIN && S.w_sites > 0) return fail(BBB_ERR_INVALID, "space %d: site move on a plain space", s);
+        if (S.n_params == 0 && S.w_values > 0) return fail(BBB_ERR_INVALID, "space %d: value move without parameters", s);
+        for (int d = 0; d < S.ndim; ++d)
+            if (!(S.vmin[d] < S.vmax[d]) || !(S.site_std[d] > 0)) return fail(BBB_ERR_INVALID, "space %d: site domain / perturb_std", s);
+        for (int p = 0; p < S.n_params; ++p) {
+            if (S.prior_kind[p] < BBB_PRIOR_UNIFORM || S.prior_kind[p] > BBB_PRIOR_LAPLACE)
+                return fail(BBB_ERR_INVALID, "space %d param %d: prior kind", s, p);
+            if (S.prior_kind[p] == BBB_PRIOR_UNIFORM ? !(S.prior_a[p] < S.prior_b[p]) : !(S.prior_b[p] > 0))
+                return fail(BBB_ERR_INVALID, "space %d param %d: prior hyper-parameters", s, p);
+            if (!(S.perturb_std[p] > 0) || !(S.perturb_std_birth[p] > 0))
+                return fail(BBB_ERR_INVALID, "space %d param %d: perturb_std", s, p);
+        }
+    }
+    for (int t = 0; t < P->n_targets; ++t) {
+        const bbb_target_spec &T = P->targets[t];
+        if (T.n_data < 1 || T.dobs == nullptr) return fail(BBB_ERR_INVALID, "target %d: no data", t);
+        if (T.space < 0 || T.space >= P->n_spaces) return fail(BBB_ERR_INVALID, "target %d: space index", t);
+        const bbb_space_spec &S = P->spaces[T.space];
+        if (T.cov_kind == BBB_COV_HIERARCHICAL) {
+            if (!(T.std_min >= 0) || !(T.std_max >= T.std_min) || !(T.std_perturb_std > 0))
+                return fail(BBB_ERR_INVALID, "target %d: noise std range", t);
+        } else if (T.cov_kind == BBB_COV_VECTOR) {
+            if (T.cov_vec == nullptr) return fail(BBB_ERR_INVALID, "target %d: cov_vec is NULL", t);
+        } else if (T.cov_kind != BBB_COV_SCALAR) {
+            return fail(BBB_ERR_INVALID, "target %d: cov_kind", t);
+        }
+        if (T.fwd_kind == BBB_FWD_RAY2D) {
+            if (S.kind != BBB_SPACE_VORONOI2D) return fail(BBB_ERR_INVALID, "target %d: ray2d forward needs a Voronoi2D space", t);
+            if (T.param < 0 || T.param >= S.n_params) return fail(BBB_ERR_INVALID, "target %d: param index", t);
+            if (T.n_points < 1 || !T.indptr || !T.indices || !T.data || !T.points_x || !T.points_y)
+                return fail(BBB_ERR_INVALID, "target %d: ray2d arrays", t);
+        } else if (T.fwd_kind == BBB_FWD_LOOKUP1D) {
+            if (S.kind != BBB_SPACE_VORONOI1D) return fail(BBB_ERR_INVALID, "target %d: lookup1d forward needs a Voronoi1D space", t);
+            if (T.param < 0 || T.param >= S.n_params || !T.x) return fail(BBB_ERR_INVALID, "target %d: lookup1d arrays", t);
+        } else if (T.fwd_kind == BBB_FWD_LINEAR) {
+            if (S.trans_d) return fail(BBB_ERR_INVALID, "target %d: linear forward needs a fixed-dimension space", t);
+            if (T.n_lin_params < 1 || T.n_lin_params > BBB_MAX_LINEAR_PARAMS || !T.G)
+                return fail(BBB_ERR_INVALID, "target %d: linear arrays", t);
+            for (int q = 0; q < T.n_lin_params; ++q)
+                if (T.lin_params[q] < 0 || T.lin_params[q] >= S.n_params) return fail(BBB_ERR_INVALID, "target %d: lin_params", t);
+        } else {
+            return fail(BBB_ERR_INVALID, "target %d: fwd_kind", t);
+        }
+    }
+    return BBB_OK;
+}
+
+int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out) {
+    if (!spec || !out) return fail(BBB_ERR_INVALID, "NULL argument");
+    int rc = validate_spec(spec);
+    if (rc != BBB_OK) return rc;
+    CU(cudaSetDevice(device));
+    bbb_engine *e = new (std::nothrow) bbb_engine();
+    if (!e) return fail(BBB_ERR_INVALID, "out of host memory");
+    memset(&e->host, 0, sizeof(e->host));
+    e->host.spec = *spec;
+    e->device = device;
+    e->bound = false;
+    e->has_ray = false;
+    for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
+    int err = (int)cudaMalloc(&e->dev, sizeof(EngineParams));
+    if (err != 0) {
+        delete e;
+        return cuda_fail(err, "cudaMalloc(EngineParams)");
+    }
+    *out = e;
+    return BBB_OK;
+}
+
+int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
+    if (!e || !b) return fail(BBB_ERR_INVALID, "NULL argument");
+    const bbb_problem_spec &P = e->host.spec;
+    if (b->n_chains < 1) return fail(BBB_ERR_SHAPE, "n_chains < 1");
+    for (int s = 0; s < P.n_spaces; ++s) {
+        if (!b->k[s] || !b->sel[s]) return fail(BBB_ERR_SHAPE, "space %d: k/sel buffer missing", s);
+        if (P.spaces[s].ndim > 0 && !b->sites[s]) return fail(BBB_ERR_SHAPE, "space %d: sites buffer missing", s);
+        if (P.spaces[s].n_params > 0 && !b->values[s]) return fail(BBB_ERR_SHAPE, "space %d: values buffer missing", s);
+    }
+    for (int t = 0; t < P.n_targets; ++t) {
+        if (!b->phi[t]) return fail(BBB_ERR_SHAPE, "target %d: phi buffer missing", t);
+        if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL && !b->sigma[t]) return fail(BBB_ERR_SHAPE, "target %d: sigma buffer missing", t);
+        if (P.targets[t].fwd_kind == BBB_FWD_RAY2D && (!b->cell_idx[t] || !b->idx_sel[t] || !b->partial[t]))
+            return fail(BBB_ERR_SHAPE, "target %d: cell_idx/idx_sel/partial buffer missing", t);
+    }
+    if (!b->temperature || !b->iteration || !b->move || !b->edit || !b->log_prob_ratio || !b->log_like_ratio ||
+        !b->accepted || !b->n_proposed || !b->n_accepted || !b->tape_cursor)
+        return fail(BBB_ERR_SHAPE, "a per-chain scalar buffer is missing");
+    if (b->tape && b->tape_stride < 1) return fail(BBB_ERR_SHAPE, "tape_stride < 1");
+    e->host.buf = *b;
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpy(e->dev, &e->host, sizeof(EngineParams), cudaMemcpyHostToDevice));
+    e->bound = true;
+    return BBB_OK;
+}
+
+void bbb_engine_destroy(bbb_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaFree(e->dev);
+    delete e;
+}
+
+static int idx_bytes_of(const bbb_problem_spec &P, int t) { return P.spaces[P.targets[t].space].kmax <= 256 ? 1 : 2; }
+
+static int run_raster(bbb_engine *e, int t, bool proposal, cudaStream_t st) {
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_buffers &B = e->host.buf;
+    const bbb_target_spec &T = P.targets[t];
+    const bbb_space_spec &S = P.spaces[T.space];
+    RasterArgs a;
+    a.sites = B.sites[T.space];
+    a.k = B.k[T.space];
+    a.K = S.kmax;
+    a.C = B.n_chains;
+    a.sel = B.sel[T.space];
+    a.idx_sel = B.idx_sel[t];
+    a.slot_xor = proposal ? 1 : 0;
+    a.move = proposal ? B.move : nullptr;
+    a.lpr = B.log_prob_ratio;
+    a.n_spaces = P.n_spaces;
+    a.space = T.space;
+    a.px = T.points_x;
+    a.py = T.points_y;
+    a.G = T.n_points;
+    a.idx = B.cell_idx[t];
+    a.idx_bytes = idx_bytes_of(P, t);
+    a.points_per_block = raster_points_per_block(a.G, a.C);
+    return launch_raster2d(a, st);
+}
+
+static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool write_partial, cudaStream_t st) {
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_buffers &B = e->host.buf;
+    const bbb_target_spec &T = P.targets[t];
+    const bbb_space_spec &S = P.spaces[T.space];
+    SpmmArgs a;
+    a.idx = B.cell_idx[t];
+    a.idx_bytes = idx_bytes_of(P, t);
+    a.idx_sel = B.idx_sel[t];
+    a.values = B.values[T.space];
+    a.k = B.k[T.space];
+    a.sel = B.sel[T.space];
+    a.slot_xor = proposal ? 1 : 0;
+    a.n_params = S.n_params;
+    a.param = T.param;
+    a.K = S.kmax;
+    a.C = B.n_chains;
+    a.G = T.n_points;
+    a.R = T.n_data;
+    a.indptr = T.indptr;
+    a.indices = T.indices;
+    a.data = T.data;
+    a.transform = T.transform;
+    a.dobs = T.dobs;
+    a.w = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec : nullptr;
+    a.move = proposal ? B.move : nullptr;
+    a.lpr = B.log_prob_ratio;
+    a.n_spaces = P.n_spaces;
+    a.space = T.space;
+    a.dpred = dpred;
+    a.partial = write_partial ? B.partial[t] : nullptr;
+    return launch_ray_spmm(a, st);
+}
+
+#define NEED_BOUND(e)                                                                  \
+    do {                                                                               \
+        if (!(e)) return fail(BBB_ERR_INVALID, "NULL engine");                         \
+        if (!(e)->bound) return fail(BBB_ERR_SHAPE, "bbb_engine_bind_buffers not called"); \
+        CU(cudaSetDevice((e)->device));                                                \
+    } while (0)
+
+int bbb_engine_refresh(bbb_engine *e, void *stream) {
+    NEED_BOUND(e);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bbb_problem_spec &P = e->host.spec;
+    for (int t = 0; t < P.n_targets; ++t) {
+        if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
+        CU(run_raster(e, t, false, st));
+        CU(run_spmm(e, t, false, nullptr, true, st));
+    }
+    CU(launch_refresh_finish(e->dev, e->host.buf.n_chains, st));
+    return BBB_OK;
+}
+
+int bbb_engine_init_states(bbb_engine *e, void *stream) {
+    NEED_BOUND(e);
+    CU(launch_init_states(e->dev, e->host.buf.n_chains, (cudaStream_t)stream));
+    return bbb_engine_refresh(e, stream);
+}
+
+int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
+    NEED_BOUND(e);
+    if (n_steps < 0) return fail(BBB_ERR_INVALID, "n_steps < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bbb_problem_spec &P = e->host.spec;
+    const long long C = e->host.buf.n_chains;
+    if (!e->has_ray) {
+        if (n_steps > 0) CU(launch_fused_steps(e->dev, C, n_steps, st));
+        return BBB_OK;
+    }
+    for (int64_t it = 0; it < n_steps; ++it) {
+        CU(launch_propose(e->dev, C, st));
+        for (int t = 0; t < P.n_targets; ++t) {
+            if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
+            CU(run_raster(e, t, true, st));
+            CU(run_spmm(e, t, true, nullptr, true, st));
+        }
+        CU(launch_finish(e->dev, C, st));
+    }
+    return BBB_OK;
+}
+
+int bbb_engine_gather_space(bbb_engine *e, int space, int32_t *k_out, double *sites_out, double *values_out,
+                            void *stream) {
+    NEED_BOUND(e);
+    if (space < 0 || space >= e->host.spec.n_spaces) return fail(BBB_ERR_INVALID, "space index");
+    if (!k_out) return fail(BBB_ERR_INVALID, "k_out is NULL");
+    CU(launch_gather_space(e->dev, e->host.buf.n_chains, space, e->host.spec.spaces[space].kmax, k_out, sites_out,
+                           values_out, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream) {
+    NEED_BOUND(e);
+    if (target < 0 || target >= e->host.spec.n_targets || !dpred_out) return fail(BBB_ERR_INVALID, "target index / NULL output");
+    if (e->host.spec.targets[target].fwd_kind == BBB_FWD_RAY2D)
+        CU(run_spmm(e, target, false, dpred_out, false, (cudaStream_t)stream));
+    else
+        CU(launch_small_dpred(e->dev, e->host.buf.n_chains, target, dpred_out, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_engine_misfit_logdet(bbb_engine *e, double *misfit_out, double *logdet_out, void *stream) {
+    NEED_BOUND(e);
+    if (!misfit_out || !logdet_out) return fail(BBB_ERR_INVALID, "NULL output");
+    CU(launch_misfit_logdet(e->dev, e->host.buf.n_chains, misfit_out, logdet_out, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_pt_swap(double *gathered, int64_t n_total, uint64_t seed, int64_t round, int64_t id0, int64_t n_local,
+                double *temperature_out, int32_t *n_accepted_out, const double *tape, void *stream) {
+    if (!gathered || !temperature_out) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (n_total < 2) return fail(BBB_ERR_INVALID, "parallel tempering needs at least 2 chains");
+    if (id0 < 0 || n_local < 0 || id0 + n_local > n_total) return fail(BBB_ERR_INVALID, "local chain range");
+    CU(launch_pt_swap(gathered, n_total, seed, round, id0, n_local, temperature_out, n_accepted_out, tape,
+                      (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+// ---- stand-alone kernels ------------------------------------------------------------------------
+int bbb_raster2d(const double *sites, const int32_t *k, int32_t K, int64_t C, const double *points_x,
+                 const double *points_y, int32_t G, void *idx_out, void *stream) {
+    if (!sites || !k || !points_x || !points_y || !idx_out) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (K < 1 || K > 65535 || C < 1 || G < 1) return fail(BBB_ERR_INVALID, "bad sizes");
+    RasterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sites = sites;
+    a.k = k;
+    a.K = K;
+    a.C = C;
+    a.px = points_x;
+    a.py = points_y;
+    a.G = G;
+    a.idx = idx_out;
+    a.idx_bytes = K <= 256 ? 1 : 2;
+    a.points_per_block = raster_points_per_block(G, C);
+    CU(launch_raster2d(a, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_raster1d(const double *sites, const double *values, const int32_t *k, int32_t K, int64_t C, const double *x,
+                 int32_t R, int32_t *idx_out, double *field_out, void *stream) {
+    if (!sites || !k || !x) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (field_out && !values) return fail(BBB_ERR_INVALID, "field requested without values");
+    if (K < 1 || C < 1 || R < 1) return fail(BBB_ERR_INVALID, "bad sizes");
+    CU(launch_raster1d(sites, values, k, K, C, x, R, idx_out, field_out, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_ray_forward(const void *idx, const double *values, const int32_t *k, int32_t K, int64_t C, int32_t G,
+                    int32_t R, const int32_t *indptr, const int32_t *indices, const double *data, int32_t transform,
+                    const double *dobs, const double *w, double *dpred_out, double *phi_out, double *partial_scratch,
+                    void *stream) {
+    if (!idx || !values || !k || !indptr || !indices || !data || !dobs) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (phi_out && !partial_scratch) return fail(BBB_ERR_INVALID, "phi requested without partial scratch");
+    if (K < 1 || K > 65535 || C < 1 || G < 1 || R < 1) return fail(BBB_ERR_INVALID, "bad sizes");
+    SpmmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.idx = idx;
+    a.idx_bytes = K <= 256 ? 1 : 2;
+    a.values = values;
+    a.k = k;
+    a.n_params = 1;
+    a.param = 0;
+    a.K = K;
+    a.C = C;
+    a.G = G;
+    a.R = R;
+    a.indptr = indptr;
+    a.indices = indices;
+    a.data = data;
+    a.transform = transform;
+    a.dobs = dobs;
+    a.w = w;
+    a.dpred = dpred_out;
+    a.partial = phi_out ? partial_scratch : nullptr;
+    CU(launch_ray_spmm(a, (cudaStream_t)stream));
+    if (phi_out) CU(launch_phi_from_partial(partial_scratch, (R + RAY_TILE - 1) / RAY_TILE, C, phi_out, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_dense_forward(const double *G, const double *m, int32_t R, int32_t M, int64_t C, double *dpred_out,
+                      void *stream) {
+    if (!G || !m || !dpred_out) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (R < 1 || M < 1 || C < 1) return fail(BBB_ERR_INVALID, "bad sizes");
+    CU(launch_dense_forward(G, m, R, M, C, dpred_out, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_loglike(const double *dpred, const double *dobs, const double *sigma, int32_t R, int64_t C, double *misfit_out,
+                double *logdet_out, void *stream) {
+    if (!dpred || !dobs || !sigma || !misfit_out || !logdet_out) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (R < 1 || C < 1) return fail(BBB_ERR_INVALID, "bad sizes");
+    CU(launch_loglike(dpred, dobs, sigma, R, C, misfit_out, logdet_out, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_logprior(const bbb_space_spec *space, const double *values, const int32_t *k, int64_t C, double *log_prior_out,
+                 void *stream) {
+    if (!space || !values || !k || !log_prior_out) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (space->n_params < 1 || space->n_params > BBB_MAX_PARAMS || C < 1) return fail(BBB_ERR_INVALID, "bad sizes");
+    CU(launch_logprior(*space, values, k, C, log_prior_out, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_philox_kat(const uint32_t *counter, const uint32_t *key, uint32_t *out) {
+    if (!counter || !key || !out) return fail(BBB_ERR_INVALID, "NULL argument");
+    philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1], out);
+    return BBB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// Shared device-side helpers: SoA views over the caller-owned buffers, prior formulas.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/bbb200.h"
+#include "rng.cuh"
+
+namespace bbb {
+
+constexpr double LOG_TWO_PI_HALF = 0.91893853320467274178;  // 0.5*log(2*pi)
+constexpr double SQRT_TWO_PI = 2.50662827463100050242;
+constexpr int RAY_TILE = 64;       // rays per SpMM block (partial-misfit granularity)
+constexpr int CHAIN_TILE = 32;     // chains per warp-lane tile
+
+struct EngineParams {
+    bbb_problem_spec spec;
+    bbb_buffers buf;
+};
+
+// ---- slot-addressed views (arrays are [2][...][K][C], chain fastest) -------------------------
+__device__ __forceinline__ double &site_ref(const bbb_buffers &B, const bbb_space_spec &S, int s,
+                                            int slot, int d, int j, long long c) {
+    return B.sites[s][(((long long)slot * S.ndim + d) * S.kmax + j) * B.n_chains + c];
+}
+__device__ __forceinline__ double &value_ref(const bbb_buffers &B, const bbb_space_spec &S, int s,
+                                             int slot, int p, int j, long long c) {
+    return B.values[s][(((long long)slot * S.n_params + p) * S.kmax + j) * B.n_chains + c];
+}
+__device__ __forceinline__ int32_t &k_ref(const bbb_buffers &B, int s, int slot, long long c) {
+    return B.k[s][(long long)slot * B.n_chains + c];
+}
+
+// ---- priors (prior/_prior.py: Uniform :400-481, Gaussian :599-682, Laplace :800-881) ----------
+__device__ __forceinline__ double prior_log_pdf(int kind, double a, double b, double v) {
+    if (kind == BBB_PRIOR_UNIFORM) return (a <= v && v <= b) ? -log(b - a) : -INFINITY;
+    if (kind == BBB_PRIOR_GAUSSIAN) {
+        const double z = (v - a) / b;
+        return -LOG_TWO_PI_HALF - log(b) - 0.5 * (z * z);
+    }
+    return -0.69314718055994530942 - log(b) - fabs(v - a) / b;
+}
+__device__ __forceinline__ double prior_value_ratio(int kind, double a, double b, double old_v,
+                                                    double new_v) {
+    if (kind == BBB_PRIOR_UNIFORM) return (a <= new_v && new_v <= b) ? 0.0 : -INFINITY;
+    if (kind == BBB_PRIOR_GAUSSIAN) return (old_v - new_v) * (old_v + new_v - 2.0 * a) / (2.0 * (b * b));
+    return (fabs(old_v - a) - fabs(new_v - a)) / b;
+}
+__device__ __forceinline__ double prior_sample(int kind, double a, double b, Rng &rng) {
+    if (kind == BBB_PRIOR_UNIFORM) return rng.uniform(a, b);
+    if (kind == BBB_PRIOR_GAUSSIAN) return rng.normal(a, b);
+    return rng.laplace(a, b);
+}
+
+__device__ __forceinline__ int n_move_types(const bbb_problem_spec &P) { return 4 * P.n_spaces + 1; }
+
+}  // namespace bbb

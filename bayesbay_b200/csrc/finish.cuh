@@ -1,0 +1,157 @@
+// F3/F4 per-chain forwards, L1/L2 likelihood ratio and the Metropolis-Hastings decision (P0).
+#pragma once
+#include "common.cuh"
+
+namespace bbb {
+
+__device__ __forceinline__ double data_weight(const bbb_target_spec &T, int r) {
+    return (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r] : 1.0;
+}
+
+// 1-D nearest-nuclei cell of xp: interpolate_nearest_1d + nearest_neighbour_1d
+// (_utils_1d.pyx:87-114): xp <= x[0] -> 0, xp >= x[k-1] -> k-1, else the first i with
+// x[i] <= xp <= x[i+1], tie -> upper.  `hint` is a monotone sweep pointer (data sorted ascending);
+// `at(j)` returns site j of the chain.
+template <typename At>
+__device__ __forceinline__ int cell_1d_at(At at, int k, double xp, int &hint) {
+    if (xp <= at(0)) return 0;
+    if (xp >= at(k - 1)) return k - 1;
+    int i = hint;
+    if (i > k - 2 || at(i) > xp) i = 0;  // data not ascending: restart the sweep
+    while (i < k - 2 && at(i + 1) < xp) ++i;
+    hint = i;
+    const double x0 = at(i);
+    const double x1 = at(i + 1);
+    return (fabs(x0 - xp) < fabs(x1 - xp)) ? i : i + 1;
+}
+__device__ __forceinline__ int cell_1d(const bbb_buffers &B, const bbb_space_spec &S, int s, int slot,
+                                       long long c, int k, double xp, int &hint) {
+    return cell_1d_at([&](int j) { return site_ref(B, S, s, slot, 0, j, c); }, k, xp, hint);
+}
+
+// phi = sum_r w_r (d_pred[r] - d_obs[r])^2 of a thread-evaluated target; optionally stores d_pred
+// (stride C) and the cell index (lookup1d, stride C).
+__device__ inline double small_target_phi(const bbb_problem_spec &P, const bbb_buffers &B, int t, int slot,
+                                          long long c, double *dpred_out, int32_t *idx_out) {
+    const bbb_target_spec &T = P.targets[t];
+    const int s = T.space;
+    const bbb_space_spec &S = P.spaces[s];
+    const long long C = B.n_chains;
+    double phi = 0.0;
+    if (T.fwd_kind == BBB_FWD_LOOKUP1D) {
+        // Voronoi1D.interpolate_tessellation(..., 'nuclei') (discretization/_voronoi.py:705-732)
+        const int k = k_ref(B, s, slot, c);
+        int hint = 0;
+        for (int r = 0; r < T.n_data; ++r) {
+            const int i = cell_1d(B, S, s, slot, c, k, T.x[r], hint);
+            const double d = value_ref(B, S, s, slot, T.param, i, c);
+            if (dpred_out) dpred_out[(long long)r * C + c] = d;
+            if (idx_out) idx_out[(long long)r * C + c] = i;
+            const double res = d - T.dobs[r];
+            phi += data_weight(T, r) * (res * res);
+        }
+    } else if (T.fwd_kind == BBB_FWD_LINEAR) {
+        // fwd_operator @ m (02_hierarchical_polyfit.ipynb cell 12)
+        const int K = S.kmax;
+        const int M = T.n_lin_params * K;
+        for (int r = 0; r < T.n_data; ++r) {
+            double d = 0.0;
+            for (int q = 0; q < T.n_lin_params; ++q)
+                for (int j = 0; j < K; ++j)
+                    d += T.G[(long long)r * M + q * K + j] * value_ref(B, S, s, slot, T.lin_params[q], j, c);
+            if (dpred_out) dpred_out[(long long)r * C + c] = d;
+            const double res = d - T.dobs[r];
+            phi += data_weight(T, r) * (res * res);
+        }
+    }
+    return phi;
+}
+
+__device__ __forceinline__ double ray_partial_sum(const bbb_buffers &B, const bbb_target_spec &T, int t, long long c) {
+    const int n_tiles = (T.n_data + RAY_TILE - 1) / RAY_TILE;
+    double phi = 0.0;
+    for (int i = 0; i < n_tiles; ++i) phi += B.partial[t][(long long)i * B.n_chains + c];
+    return phi;
+}
+
+// Target.inverse_covariance_times_vector / log_determinant_covariance (likelihood/_target.py:136-208)
+__device__ __forceinline__ void misfit_logdet_terms(const bbb_target_spec &T, double phi, double sigma,
+                                                    double &misfit, double &logdet) {
+    if (T.cov_kind == BBB_COV_HIERARCHICAL) {
+        misfit = (1.0 / (sigma * sigma)) * phi;
+        logdet = (2.0 * T.n_data) * log(sigma);
+    } else if (T.cov_kind == BBB_COV_SCALAR) {
+        misfit = T.cov_scalar * phi;
+        logdet = 0.0;
+    } else {
+        misfit = phi;
+        logdet = 0.0;
+    }
+}
+
+// True when the current proposal of chain c requires target t's forward to be re-evaluated.
+__device__ __forceinline__ bool target_touched(const bbb_problem_spec &P, int move, double lpr, int t) {
+    if (isinf(lpr)) return false;                 // forward skipped, _markov_chain.py:222-223
+    if (move == 4 * P.n_spaces) return false;     // noise move: d_pred unchanged (quirk Q1)
+    return P.targets[t].space == (move >> 2);
+}
+__device__ __forceinline__ bool move_is_geometry(int move) {
+    const int inner = move & 3;
+    return inner != BBB_MOVE_VALUES;
+}
+
+// Likelihood ratio, MH decision, commit, statistics: _next_iteration (_markov_chain.py:222-243)
+__device__ inline void finish_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, Rng &rng) {
+    const long long C = B.n_chains;
+    const int move = B.move[c];
+    const double lpr = B.log_prob_ratio[c];
+    const bool noise = (move == 4 * P.n_spaces);
+    const int s = move >> 2;
+    double llr = 0.0;
+    if (!isinf(lpr)) {
+        double old_m = 0.0, new_m = 0.0, old_ld = 0.0, new_ld = 0.0;
+        for (int t = 0; t < P.n_targets; ++t) {
+            const bbb_target_spec &T = P.targets[t];
+            const bool hier = (T.cov_kind == BBB_COV_HIERARCHICAL);
+            const double phi_old = B.phi[t][c];
+            double phi_new = phi_old;
+            if (!noise && T.space == s) {
+                if (T.fwd_kind == BBB_FWD_RAY2D) phi_new = ray_partial_sum(B, T, t, c);
+                else phi_new = small_target_phi(P, B, t, B.sel[s][c] ^ 1, c, nullptr, nullptr);
+                B.phi[t][C + c] = phi_new;
+            }
+            const double sig_old = hier ? B.sigma[t][c] : 1.0;
+            const double sig_new = (hier && noise) ? B.sigma[t][C + c] : sig_old;
+            double m0, l0, m1, l1;
+            misfit_logdet_terms(T, phi_old, sig_old, m0, l0);
+            misfit_logdet_terms(T, phi_new, sig_new, m1, l1);
+            old_m += m0; new_m += m1;
+            if (hier) { old_ld += l0; new_ld += l1; }
+        }
+        // _log_likelihood_ratio_from_targets (likelihood/_log_likelihood.py:245-251), then / T (:243)
+        llr = (old_ld - new_ld + old_m - new_m) / 2.0 / B.temperature[c];
+    }
+    const double log_u = log(rng.unit());
+    const bool accepted = (lpr + llr) > log_u;  // NaN compares false -> rejected
+    if (accepted) {
+        if (noise) {
+            for (int t = 0; t < P.n_targets; ++t)
+                if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL) B.sigma[t][c] = B.sigma[t][C + c];
+        } else {
+            B.sel[s][c] ^= 1;
+            for (int t = 0; t < P.n_targets; ++t) {
+                const bbb_target_spec &T = P.targets[t];
+                if (T.space != s) continue;
+                B.phi[t][c] = B.phi[t][C + c];
+                if (T.fwd_kind == BBB_FWD_RAY2D && move_is_geometry(move)) B.idx_sel[t][c] ^= 1;
+            }
+        }
+    }
+    B.log_like_ratio[c] = llr;
+    B.accepted[c] = accepted ? 1 : 0;
+    B.n_proposed[(long long)move * C + c] += 1;
+    B.n_accepted[(long long)move * C + c] += accepted ? 1 : 0;
+    B.iteration[c] += 1;
+}
+
+}  // namespace bbb

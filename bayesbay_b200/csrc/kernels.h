@@ -1,0 +1,80 @@
+// Internal launch interface between the C ABI (abi.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace bbb {
+
+// Arguments of the 2-D rasterisation kernel.  `move == nullptr` means "all chains, current slots";
+// otherwise only chains whose proposal changed the geometry of `space` are rasterised, reading the
+// proposed slot (sel ^ 1) and writing the proposed index slot (idx_sel ^ 1).
+struct RasterArgs {
+    const double *sites;      // [slots][2][K][C]
+    const int32_t *k;         // [slots][C]
+    int K;
+    long long C;
+    const uint8_t *sel;       // [C] or nullptr (slot 0)
+    const uint8_t *idx_sel;   // [C] or nullptr (slot 0)
+    int slot_xor;             // 1: proposed slots, 0: current slots
+    const int32_t *move;      // [C] or nullptr
+    const double *lpr;        // [C]
+    int n_spaces, space;
+    const double *px, *py;    // [G]
+    int G;
+    void *idx;                // [slots][G][C]
+    int idx_bytes;            // 1 or 2
+    int points_per_block;
+};
+
+struct SpmmArgs {
+    const void *idx;          // [slots][G][C]
+    int idx_bytes;
+    const uint8_t *idx_sel;   // [C] or nullptr
+    const double *values;     // [slots][n_params][K][C]
+    const int32_t *k;         // [slots][C]
+    const uint8_t *sel;       // [C] or nullptr
+    int slot_xor;
+    int n_params, param, K;
+    long long C;
+    int G, R;
+    const int32_t *indptr, *indices;
+    const double *data;
+    int transform;
+    const double *dobs;
+    const double *w;          // [R] or nullptr
+    const int32_t *move;      // [C] or nullptr (all chains)
+    const double *lpr;
+    int n_spaces, space;
+    double *dpred;            // [R][C] or nullptr
+    double *partial;          // [ray_tiles][C] or nullptr
+};
+
+int raster_points_per_block(int G, long long C);
+int launch_raster2d(const RasterArgs &a, cudaStream_t stream);
+int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream);
+
+// step_kernels.cu
+int launch_propose(const EngineParams *dev_params, long long C, cudaStream_t stream);
+int launch_finish(const EngineParams *dev_params, long long C, cudaStream_t stream);
+int launch_fused_steps(const EngineParams *dev_params, long long C, long long n_steps, cudaStream_t stream);
+int launch_init_states(const EngineParams *dev_params, long long C, cudaStream_t stream);
+int launch_refresh_finish(const EngineParams *dev_params, long long C, cudaStream_t stream);
+int launch_gather_space(const EngineParams *dev_params, long long C, int space, int kmax, int32_t *k_out,
+                        double *sites_out, double *values_out, cudaStream_t stream);
+int launch_small_dpred(const EngineParams *dev_params, long long C, int target, double *dpred_out,
+                       cudaStream_t stream);
+int launch_misfit_logdet(const EngineParams *dev_params, long long C, double *misfit_out,
+                         double *logdet_out, cudaStream_t stream);
+int launch_pt_swap(const double *gathered, long long n_total, uint64_t seed, long long round, long long id0,
+                   long long n_local, double *temperature_out, int32_t *n_accepted_out, const double *tape,
+                   cudaStream_t stream);
+int launch_raster1d(const double *sites, const double *values, const int32_t *k, int K, long long C,
+                    const double *x, int R, int32_t *idx_out, double *field_out, cudaStream_t stream);
+int launch_dense_forward(const double *G, const double *m, int R, int M, long long C, double *dpred_out,
+                         cudaStream_t stream);
+int launch_loglike(const double *dpred, const double *dobs, const double *sigma, int R, long long C,
+                   double *misfit_out, double *logdet_out, cudaStream_t stream);
+int launch_logprior(const bbb_space_spec &space, const double *values, const int32_t *k, long long C,
+                    double *out, cudaStream_t stream);
+int launch_phi_from_partial(const double *partial, int n_tiles, long long C, double *phi_out, cudaStream_t stream);
+
+}  // namespace bbb

@@ -1,0 +1,245 @@
+// P0-P7: move choice and proposal for one chain (one thread per chain, lanes = chains).
+//
+// Every reference move (perturbations/*.py, discretization/_voronoi.py, parameterization/
+// _parameter_space.py) is reduced to one "edit script" on the padded cell arrays:
+//     remove cell `rm` (or none), insert a cell (site, values) at output position `ins` (or none)
+// so the O(K) part -- writing the proposed slot -- is one loop that every lane of a warp runs in
+// lock step, whatever move each chain drew:
+//     value move      rm = ins = idx, same site, new values
+//     site move 2-D   rm = ins = idx, new site, same values
+//     site move 1-D   rm = idx, ins = sorted position of the new site (Voronoi1D.perturb_value
+//                     re-sorts with argsort, discretization/_voronoi.py:573-591)
+//     birth 2-D       ins = k (np.vstack/np.append, _voronoi.py:330-337)          quirk Q10
+//     birth 1-D       ins = bisect_left(sites, new) (_voronoi.py:601-609)
+//     birth plain     ins = randint(0, k) (parameterization/_parameter_space.py:197-275)
+//     death           rm = randint(0, k-1) (np.delete, _voronoi.py:376-385)
+#pragma once
+#include "common.cuh"
+
+namespace bbb {
+
+constexpr int MAX_RESAMPLE = 100000;  // the reference loops forever; see DESIGN.md
+
+struct Edit {
+    int rm, ins;
+    double site[2];
+    double vals[BBB_MAX_PARAMS];
+    double lpr;
+    bool write;
+};
+
+// nearest_neighbour_1d (_utils_1d.pyx:102-114) over the cells of `slot`, optionally skipping `skip`
+__device__ inline int nearest_1d(const bbb_buffers &B, const bbb_space_spec &S, int s, int slot,
+                                 long long c, int k, int skip, double xp) {
+    auto at = [&](int j) { return site_ref(B, S, s, slot, 0, j + (skip >= 0 && j >= skip ? 1 : 0), c); };
+    const int n = k - (skip >= 0 ? 1 : 0);
+    if (n == 1 || xp < at(0)) return 0;
+    for (int i = 0; i < n - 1; ++i) {
+        const double x0 = at(i), x1 = at(i + 1);
+        if (x0 <= xp && xp <= x1) return (fabs(x0 - xp) < fabs(x1 - xp)) ? i : i + 1;
+    }
+    return n - 1;
+}
+
+// Voronoi.nearest_neighbour (discretization/_voronoi.py:462-465): argmin of the Euclidean distance,
+// lowest index on ties; squared distance with separately rounded products (no FMA).
+__device__ inline int nearest_2d(const bbb_buffers &B, const bbb_space_spec &S, int s, int slot,
+                                 long long c, int k, int skip, double px, double py) {
+    double best = INFINITY;
+    int bi = 0, out = 0;
+    for (int j = 0; j < k; ++j) {
+        if (j == skip) continue;
+        const double dx = site_ref(B, S, s, slot, 0, j, c) - px;
+        const double dy = site_ref(B, S, s, slot, 1, j, c) - py;
+        const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (d < best) { best = d; bi = out; }
+        ++out;
+    }
+    return bi;  // index among the remaining cells
+}
+
+__device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, Rng &rng) {
+    // ---- outer choice: _markov_chain.py:208-210 ------------------------------------------------
+    double w[BBB_MAX_SPACES + 1];
+    int n_outer = 0;
+    for (int s = 0; s < P.n_spaces; ++s) {
+        const bbb_space_spec &S = P.spaces[s];
+        w[n_outer++] = S.w_birth + S.w_death + S.w_values + S.w_sites;
+    }
+    bool any_hier = false;
+    for (int t = 0; t < P.n_targets; ++t) any_hier |= (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL);
+    if (any_hier) w[n_outer++] = 1.0;
+    const int i_outer = rng.choice(w, n_outer);
+
+    if (i_outer >= P.n_spaces) {
+        // ---- P7 NoisePerturbation.perturb (perturbations/_data_noise.py:21-77) ------------------
+        for (int t = 0; t < P.n_targets; ++t) {
+            const bbb_target_spec &T = P.targets[t];
+            if (T.cov_kind != BBB_COV_HIERARCHICAL) continue;
+            const double old_v = B.sigma[t][c];
+            double new_v = old_v;
+            for (int it = 0; it < MAX_RESAMPLE; ++it) {
+                const double cand = old_v + rng.normal(0.0, T.std_perturb_std);
+                if (cand < T.std_min || cand > T.std_max) continue;
+                new_v = cand;
+                break;
+            }
+            B.sigma[t][B.n_chains + c] = new_v;
+        }
+        B.move[c] = 4 * P.n_spaces;
+        B.edit[c] = -1;
+        B.edit[B.n_chains + c] = -1;
+        B.log_prob_ratio[c] = 0.0;
+        return;
+    }
+
+    // ---- inner choice: ParamSpacePerturbation.perturb_param_space_state (_param_space.py:79-92)
+    const int s = i_outer;
+    const bbb_space_spec &S = P.spaces[s];
+    double wi[4];
+    int kinds[4];
+    int n_inner = 0;
+    if (S.w_birth > 0) { wi[n_inner] = S.w_birth; kinds[n_inner++] = BBB_MOVE_BIRTH; }
+    if (S.w_death > 0) { wi[n_inner] = S.w_death; kinds[n_inner++] = BBB_MOVE_DEATH; }
+    if (S.w_values > 0) { wi[n_inner] = S.w_values; kinds[n_inner++] = BBB_MOVE_VALUES; }
+    if (S.w_sites > 0) { wi[n_inner] = S.w_sites; kinds[n_inner++] = BBB_MOVE_SITES; }
+    const int inner = kinds[rng.choice(wi, n_inner)];
+
+    const int cur = B.sel[s][c];
+    const int prop = cur ^ 1;
+    const int k = k_ref(B, s, cur, c);
+    Edit e;
+    e.rm = -1;
+    e.ins = -1;
+    e.lpr = 0.0;
+    e.write = true;
+    e.site[0] = e.site[1] = 0.0;
+
+    if (inner == BBB_MOVE_VALUES) {
+        // P2 ParamPerturbation.perturb_param_space_state (perturbations/_param_values.py:60-84)
+        const int idx = rng.randint(0, k - 1);
+        e.rm = e.ins = idx;
+        for (int d = 0; d < S.ndim; ++d) e.site[d] = site_ref(B, S, s, cur, d, idx, c);
+        for (int p = 0; p < S.n_params; ++p) {
+            const double old_v = value_ref(B, S, s, cur, p, idx, c);
+            const double new_v = old_v + rng.normal(0.0, S.perturb_std[p]);
+            e.lpr += prior_value_ratio(S.prior_kind[p], S.prior_a[p], S.prior_b[p], old_v, new_v);
+            e.vals[p] = new_v;
+        }
+    } else if (inner == BBB_MOVE_SITES) {
+        // P3 Voronoi.perturb_value + _perturb_site (_voronoi.py:171-232; 1-D :566-591)
+        const int idx = rng.randint(0, k - 1);
+        e.rm = idx;
+        for (int p = 0; p < S.n_params; ++p) e.vals[p] = value_ref(B, S, s, cur, p, idx, c);
+        double old_site[2] = {0.0, 0.0};
+        for (int d = 0; d < S.ndim; ++d) old_site[d] = e.site[d] = site_ref(B, S, s, cur, d, idx, c);
+        for (int it = 0; it < MAX_RESAMPLE; ++it) {
+            double cand[2];
+            bool ok = true;
+            for (int d = 0; d < S.ndim; ++d) {
+                cand[d] = old_site[d] + rng.normal(0.0, S.site_std[d]);
+                ok &= (cand[d] >= S.vmin[d]) && (cand[d] <= S.vmax[d]);
+            }
+            if (ok) {
+                for (int d = 0; d < S.ndim; ++d) e.site[d] = cand[d];
+                break;
+            }
+        }
+        if (S.ndim == 1) {
+            int pos = 0;
+            for (int j = 0; j < k; ++j)
+                if (j != idx && site_ref(B, S, s, cur, 0, j, c) < e.site[0]) ++pos;
+            e.ins = pos;
+        } else {
+            e.ins = idx;
+        }
+    } else if (inner == BBB_MOVE_BIRTH) {
+        // P4/P6 Voronoi.birth (_voronoi.py:234-339, 1-D :593-611) / ParameterSpace.birth
+        if (k == S.kmax) {
+            e.lpr = -INFINITY;
+            e.write = false;
+        } else if (S.kind == BBB_SPACE_PLAIN) {
+            e.ins = rng.randint(0, k);
+            for (int p = 0; p < S.n_params; ++p)
+                e.vals[p] = prior_sample(S.prior_kind[p], S.prior_a[p], S.prior_b[p], rng);
+        } else {
+            for (int d = 0; d < S.ndim; ++d) e.site[d] = rng.uniform(S.vmin[d], S.vmax[d]);
+            if (S.birth_from == BBB_BIRTH_FROM_PRIOR) {
+                // _initialize_params_from_prior (discretization/_discretization.py:299-321)
+                for (int p = 0; p < S.n_params; ++p)
+                    e.vals[p] = prior_sample(S.prior_kind[p], S.prior_a[p], S.prior_b[p], rng);
+            } else {
+                // _initialize_params_from_neighbour (discretization/_discretization.py:323-375)
+                const int i_near = (S.ndim == 1) ? nearest_1d(B, S, s, cur, c, k, -1, e.site[0])
+                                                 : nearest_2d(B, S, s, cur, c, k, -1, e.site[0], e.site[1]);
+                for (int p = 0; p < S.n_params; ++p) {
+                    const double theta = S.perturb_std_birth[p];
+                    const double old_v = value_ref(B, S, s, cur, p, i_near, c);
+                    const double new_v = old_v + rng.normal(0.0, theta);
+                    e.vals[p] = new_v;
+                    const double diff = new_v - old_v;
+                    e.lpr += prior_log_pdf(S.prior_kind[p], S.prior_a[p], S.prior_b[p], new_v) +
+                             (log(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta)));
+                }
+            }
+            if (S.ndim == 1) {
+                int pos = 0;  // bisect_left
+                for (int j = 0; j < k; ++j)
+                    if (site_ref(B, S, s, cur, 0, j, c) < e.site[0]) ++pos;
+                e.ins = pos;
+            } else {
+                e.ins = k;
+            }
+        }
+    } else {
+        // P5/P6 Voronoi.death (_voronoi.py:341-385, 1-D :613-625) / ParameterSpace.death
+        if (k == S.kmin) {
+            e.lpr = -INFINITY;
+            e.write = false;
+        } else {
+            e.rm = rng.randint(0, k - 1);
+            if (S.kind != BBB_SPACE_PLAIN && S.birth_from == BBB_BIRTH_FROM_NEIGHBOUR) {
+                // _log_prob_death_parameters (discretization/_discretization.py:435-465)
+                double pos[2] = {0.0, 0.0};
+                for (int d = 0; d < S.ndim; ++d) pos[d] = site_ref(B, S, s, cur, d, e.rm, c);
+                int i_near = (S.ndim == 1) ? nearest_1d(B, S, s, cur, c, k, e.rm, pos[0])
+                                           : nearest_2d(B, S, s, cur, c, k, e.rm, pos[0], pos[1]);
+                i_near += (i_near >= e.rm) ? 1 : 0;  // back to indices of the current state
+                for (int p = 0; p < S.n_params; ++p) {
+                    const double theta = S.perturb_std_birth[p];
+                    const double gone = value_ref(B, S, s, cur, p, e.rm, c);
+                    const double near_v = value_ref(B, S, s, cur, p, i_near, c);
+                    const double diff = gone - near_v;
+                    e.lpr -= prior_log_pdf(S.prior_kind[p], S.prior_a[p], S.prior_b[p], gone);
+                    e.lpr -= log(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta));
+                }
+            }
+        }
+    }
+
+    // ---- write the proposed slot: one lock-step loop for every move kind -----------------------
+    if (e.write) {
+        const int k_new = k - (e.rm >= 0 ? 1 : 0) + (e.ins >= 0 ? 1 : 0);
+        int src = 0;
+        for (int jo = 0; jo < k_new; ++jo) {
+            if (jo == e.ins) {
+                for (int d = 0; d < S.ndim; ++d) site_ref(B, S, s, prop, d, jo, c) = e.site[d];
+                for (int p = 0; p < S.n_params; ++p) value_ref(B, S, s, prop, p, jo, c) = e.vals[p];
+            } else {
+                if (src == e.rm) ++src;
+                for (int d = 0; d < S.ndim; ++d)
+                    site_ref(B, S, s, prop, d, jo, c) = site_ref(B, S, s, cur, d, src, c);
+                for (int p = 0; p < S.n_params; ++p)
+                    value_ref(B, S, s, prop, p, jo, c) = value_ref(B, S, s, cur, p, src, c);
+                ++src;
+            }
+        }
+        k_ref(B, s, prop, c) = k_new;
+    }
+    B.move[c] = 4 * s + inner;
+    B.edit[c] = e.rm;
+    B.edit[B.n_chains + c] = e.ins;
+    B.log_prob_ratio[c] = e.lpr;
+}
+
+}  // namespace bbb

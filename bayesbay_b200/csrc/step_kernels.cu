@@ -1,0 +1,384 @@
+// Chain-step kernels: proposal (P0-P7), accept/commit, fused many-steps-per-launch loop for
+// thread-evaluable forwards, initialisation (I1), result gathering (O1), parallel-tempering swap
+// round (T1) and the small stand-alone parity kernels (F3, F4, L1-L3).
+#include "finish.cuh"
+#include "kernels.h"
+#include "propose.cuh"
+
+namespace bbb {
+
+constexpr int STEP_THREADS = 64;  // 2 warps per block: spreads C = 1024 chains over 16 SMs' worth of blocks
+
+__device__ __forceinline__ void rng_begin(Rng &rng, const EngineParams &ep, long long c, uint32_t tag,
+                                          bool continue_step) {
+    const bbb_buffers &B = ep.buf;
+    if (B.tape != nullptr) {
+        rng.init_tape(B.tape + c * B.tape_stride, B.tape_cursor[c]);
+    } else {
+        rng.init_philox(ep.spec.seed, (uint64_t)(B.chain_id0 + c), (uint64_t)B.iteration[c], tag);
+        if (continue_step) rng.n = (uint32_t)B.tape_cursor[c];
+    }
+}
+__device__ __forceinline__ void rng_end(const Rng &rng, const EngineParams &ep, long long c) {
+    const bbb_buffers &B = ep.buf;
+    B.tape_cursor[c] = (B.tape != nullptr) ? rng.cursor : (long long)rng.n;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) k_propose(const EngineParams *epp) {
+    const EngineParams &ep = *epp;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ep.buf.n_chains) return;
+    Rng rng;
+    rng_begin(rng, ep, c, STREAM_STEP, false);
+    propose_chain(ep.spec, ep.buf, c, rng);
+    rng_end(rng, ep, c);
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) k_finish(const EngineParams *epp) {
+    const EngineParams &ep = *epp;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ep.buf.n_chains) return;
+    Rng rng;
+    rng_begin(rng, ep, c, STREAM_STEP, true);
+    finish_chain(ep.spec, ep.buf, c, rng);
+    rng_end(rng, ep, c);
+}
+
+// All forwards thread-evaluable (lookup1d / linear): the whole step is one thread's work and there
+// is no cross-chain dependency, so n_steps iterations run inside ONE launch (the 1-D and polyfit
+// configurations are launch-latency bound otherwise).
+__global__ void __launch_bounds__(STEP_THREADS) k_fused_steps(const EngineParams *epp, long long n_steps) {
+    const EngineParams &ep = *epp;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ep.buf.n_chains) return;
+    for (long long it = 0; it < n_steps; ++it) {
+        Rng rng;
+        rng_begin(rng, ep, c, STREAM_STEP, false);
+        propose_chain(ep.spec, ep.buf, c, rng);
+        finish_chain(ep.spec, ep.buf, c, rng);
+        rng_end(rng, ep, c);
+    }
+}
+
+// I1: Voronoi._initialize (_voronoi.py:151-169; 1-D :551-564), ParameterSpace._initialize
+// (_parameter_space.py:146-160), Prior.initialize (_prior.py:396-398,:577-597), Target.initialize
+// (_target.py:115-134).  Draw order: k, sites, each parameter's k values, then sigma per target.
+__global__ void __launch_bounds__(STEP_THREADS) k_init_states(const EngineParams *epp) {
+    const EngineParams &ep = *epp;
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B.n_chains) return;
+    Rng rng;
+    rng_begin(rng, ep, c, STREAM_INIT, false);
+    for (int s = 0; s < P.n_spaces; ++s) {
+        const bbb_space_spec &S = P.spaces[s];
+        const int k = S.trans_d ? rng.randint(S.kmin, S.kinit_max) : S.kmin;
+        for (int j = 0; j < k; ++j)
+            for (int d = 0; d < S.ndim; ++d) site_ref(B, S, s, 0, d, j, c) = rng.uniform(S.vmin[d], S.vmax[d]);
+        if (S.ndim == 1) {  // np.sort
+            for (int j = 1; j < k; ++j) {
+                const double v = site_ref(B, S, s, 0, 0, j, c);
+                int i = j - 1;
+                while (i >= 0 && site_ref(B, S, s, 0, 0, i, c) > v) {
+                    site_ref(B, S, s, 0, 0, i + 1, c) = site_ref(B, S, s, 0, 0, i, c);
+                    --i;
+                }
+                site_ref(B, S, s, 0, 0, i + 1, c) = v;
+            }
+        }
+        for (int p = 0; p < S.n_params; ++p)
+            for (int j = 0; j < k; ++j)
+                value_ref(B, S, s, 0, p, j, c) = prior_sample(S.prior_kind[p], S.prior_a[p], S.prior_b[p], rng);
+        k_ref(B, s, 0, c) = k;
+        k_ref(B, s, 1, c) = k;
+        B.sel[s][c] = 0;
+    }
+    for (int t = 0; t < P.n_targets; ++t) {
+        const bbb_target_spec &T = P.targets[t];
+        if (T.cov_kind == BBB_COV_HIERARCHICAL) {
+            const double sg = rng.uniform(T.std_min, T.std_max);
+            B.sigma[t][c] = sg;
+            B.sigma[t][B.n_chains + c] = sg;
+        }
+        if (T.fwd_kind == BBB_FWD_RAY2D) B.idx_sel[t][c] = 0;
+    }
+    rng_end(rng, ep, c);
+}
+
+// phi of the CURRENT state for every target (ray targets: sum of the partials a CURRENT-mode SpMM
+// just wrote).
+__global__ void __launch_bounds__(STEP_THREADS) k_refresh_finish(const EngineParams *epp) {
+    const EngineParams &ep = *epp;
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B.n_chains) return;
+    for (int t = 0; t < P.n_targets; ++t) {
+        const bbb_target_spec &T = P.targets[t];
+        double phi;
+        if (T.fwd_kind == BBB_FWD_RAY2D) phi = ray_partial_sum(B, T, t, c);
+        else phi = small_target_phi(P, B, t, B.sel[T.space][c], c, nullptr, nullptr);
+        B.phi[t][c] = phi;
+        B.phi[t][B.n_chains + c] = phi;
+    }
+}
+
+// O1: compact the current slot of one space, [..][K][C] (blockIdx.y = cell j)
+__global__ void k_gather_space(const EngineParams *epp, int s, int32_t *k_out, double *sites_out,
+                               double *values_out) {
+    const EngineParams &ep = *epp;
+    const bbb_space_spec &S = ep.spec.spaces[s];
+    const bbb_buffers &B = ep.buf;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B.n_chains) return;
+    const int j = blockIdx.y;
+    const int slot = B.sel[s][c];
+    if (j == 0) k_out[c] = k_ref(B, s, slot, c);
+    for (int d = 0; d < S.ndim; ++d)
+        sites_out[((long long)d * S.kmax + j) * B.n_chains + c] = site_ref(B, S, s, slot, d, j, c);
+    for (int p = 0; p < S.n_params; ++p)
+        values_out[((long long)p * S.kmax + j) * B.n_chains + c] = value_ref(B, S, s, slot, p, j, c);
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) k_small_dpred(const EngineParams *epp, int t, double *dpred_out) {
+    const EngineParams &ep = *epp;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ep.buf.n_chains) return;
+    small_target_phi(ep.spec, ep.buf, t, ep.buf.sel[ep.spec.targets[t].space][c], c, dpred_out, nullptr);
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) k_misfit_logdet(const EngineParams *epp, double *misfit_out,
+                                                                double *logdet_out) {
+    const EngineParams &ep = *epp;
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B.n_chains) return;
+    double m = 0.0, ld = 0.0;
+    for (int t = 0; t < P.n_targets; ++t) {
+        const bbb_target_spec &T = P.targets[t];
+        const bool hier = (T.cov_kind == BBB_COV_HIERARCHICAL);
+        double mt, lt;
+        misfit_logdet_terms(T, B.phi[t][c], hier ? B.sigma[t][c] : 1.0, mt, lt);
+        m += mt;
+        if (hier) ld += lt;
+    }
+    misfit_out[c] = m;
+    logdet_out[c] = ld;
+}
+
+// ------------------------------------------------------------------------------------------------
+// T1: ParallelTempering.on_end_advance_chain (samplers/_samplers.py:334-342).  n_total sequential
+// random-pair attempts; the pair, log u and the temperature-free part of the ratio of 32 attempts
+// are computed in parallel by the lanes of one warp, then applied in order (temperatures live in
+// shared memory when they fit).  Quirk Q2 (ratio already divided by T1) is reproduced.
+// ------------------------------------------------------------------------------------------------
+constexpr int SWAP_THREADS = 256;
+constexpr int SWAP_SMEM_MAX = 24576;  // temperatures held in shared memory up to this many chains
+
+__global__ void __launch_bounds__(SWAP_THREADS) k_pt_swap(double *gathered, long long n_total, uint64_t seed,
+                                                          long long round, long long id0, long long n_local,
+                                                          double *temperature_out, int32_t *n_accepted_out,
+                                                          const double *tape, int use_smem) {
+    extern __shared__ double temps_smem[];
+    double *temps = use_smem ? temps_smem : nullptr;
+    if (use_smem) {
+        for (long long i = threadIdx.x; i < n_total; i += blockDim.x) temps[i] = gathered[3 * i + 2];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int n_acc = 0;
+        for (long long base = 0; base < n_total; base += 32) {
+            const long long i = base + lane;
+            int a = 0, b = 0;
+            double log_u = 0.0, core = 0.0;
+            if (i < n_total) {
+                Rng rng;
+                if (tape != nullptr) {
+                    rng.init_tape(tape, 3 * i);
+                } else {
+                    rng.init_philox(seed, 0, (uint64_t)round, STREAM_SWAP);
+                    rng.n = (uint32_t)(3 * i);
+                }
+                const int n = (int)n_total;
+                a = min((int)(rng.u() * (double)n), n - 1);
+                b = min((int)(rng.u() * (double)(n - 1)), n - 2);
+                if (b >= a) ++b;
+                log_u = log(rng.unit());
+                core = (gathered[3 * (long long)a + 1] - gathered[3 * (long long)b + 1] +
+                        gathered[3 * (long long)a + 0] - gathered[3 * (long long)b + 0]) / 2.0;
+            }
+            const int cnt = (int)min(32LL, n_total - base);
+            for (int q = 0; q < cnt; ++q) {
+                const int qa = __shfl_sync(0xffffffffu, a, q);
+                const int qb = __shfl_sync(0xffffffffu, b, q);
+                const double qlu = __shfl_sync(0xffffffffu, log_u, q);
+                const double qcore = __shfl_sync(0xffffffffu, core, q);
+                const double t1 = use_smem ? temps[qa] : gathered[3 * (long long)qa + 2];
+                const double t2 = use_smem ? temps[qb] : gathered[3 * (long long)qb + 2];
+                const double llr = qcore / t1;
+                const double prob = (1.0 / t1 - 1.0 / t2) * llr;
+                const bool swap = prob > qlu;
+                __syncwarp();
+                if (swap && lane == 0) {
+                    if (use_smem) { temps[qa] = t2; temps[qb] = t1; }
+                    else { gathered[3 * (long long)qa + 2] = t2; gathered[3 * (long long)qb + 2] = t1; }
+                }
+                if (!use_smem) __threadfence_block();
+                __syncwarp();
+                n_acc += swap ? 1 : 0;
+            }
+        }
+        if (lane == 0 && n_accepted_out != nullptr) *n_accepted_out = n_acc;
+    }
+    __syncthreads();
+    if (use_smem) {
+        for (long long i = threadIdx.x; i < n_total; i += blockDim.x) gathered[3 * i + 2] = temps[i];
+    }
+    for (long long i = threadIdx.x; i < n_local; i += blockDim.x)
+        temperature_out[i] = use_smem ? temps[id0 + i] : gathered[3 * (id0 + i) + 2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone parity kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_raster1d(const double *sites, const double *values, const int32_t *k, int K, long long C,
+                           const double *x, int R, int32_t *idx_out, double *field_out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int kc = k[c];
+    int hint = 0;
+    auto at = [&](int j) { return sites[(long long)j * C + c]; };
+    for (int r = 0; r < R; ++r) {
+        const int i = cell_1d_at(at, kc, x[r], hint);
+        if (idx_out) idx_out[(long long)r * C + c] = i;
+        if (field_out) field_out[(long long)r * C + c] = values[(long long)i * C + c];
+    }
+}
+
+__global__ void k_dense_forward(const double *G, const double *m, int R, int M, long long C, double *dpred) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= C) return;
+    double d = 0.0;
+    for (int q = 0; q < M; ++q) d += G[(long long)r * M + q] * m[(long long)q * C + c];
+    dpred[(long long)r * C + c] = d;
+}
+
+__global__ void k_loglike(const double *dpred, const double *dobs, const double *sigma, int R, long long C,
+                          double *misfit, double *logdet) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double phi = 0.0;
+    for (int r = 0; r < R; ++r) {
+        const double res = dpred[(long long)r * C + c] - dobs[r];
+        phi += res * res;
+    }
+    const double sg = sigma[c];
+    misfit[c] = (1.0 / (sg * sg)) * phi;
+    logdet[c] = (2.0 * R) * log(sg);
+}
+
+__global__ void k_logprior(bbb_space_spec S, const double *values, const int32_t *k, long long C, double *out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double tot = 0.0;
+    const int kc = k[c];
+    for (int p = 0; p < S.n_params; ++p) {
+        double sub = 0.0;
+        for (int j = 0; j < kc; ++j)
+            sub += prior_log_pdf(S.prior_kind[p], S.prior_a[p], S.prior_b[p],
+                                 values[((long long)p * S.kmax + j) * C + c]);
+        tot += sub;
+    }
+    out[c] = tot;
+}
+
+__global__ void k_phi_from_partial(const double *partial, int n_tiles, long long C, double *phi) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = 0; i < n_tiles; ++i) s += partial[(long long)i * C + c];
+    phi[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline int blocks_for(long long C, int threads) { return (int)((C + threads - 1) / threads); }
+
+int launch_propose(const EngineParams *p, long long C, cudaStream_t st) {
+    k_propose<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_finish(const EngineParams *p, long long C, cudaStream_t st) {
+    k_finish<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_fused_steps(const EngineParams *p, long long C, long long n_steps, cudaStream_t st) {
+    k_fused_steps<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p, n_steps);
+    return (int)cudaGetLastError();
+}
+int launch_init_states(const EngineParams *p, long long C, cudaStream_t st) {
+    k_init_states<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_refresh_finish(const EngineParams *p, long long C, cudaStream_t st) {
+    k_refresh_finish<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_gather_space(const EngineParams *p, long long C, int space, int kmax, int32_t *k_out,
+                          double *sites_out, double *values_out, cudaStream_t st) {
+    dim3 grid(blocks_for(C, 128), kmax);
+    k_gather_space<<<grid, 128, 0, st>>>(p, space, k_out, sites_out, values_out);
+    return (int)cudaGetLastError();
+}
+int launch_small_dpred(const EngineParams *p, long long C, int target, double *dpred_out, cudaStream_t st) {
+    k_small_dpred<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p, target, dpred_out);
+    return (int)cudaGetLastError();
+}
+int launch_misfit_logdet(const EngineParams *p, long long C, double *misfit_out, double *logdet_out,
+                         cudaStream_t st) {
+    k_misfit_logdet<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p, misfit_out, logdet_out);
+    return (int)cudaGetLastError();
+}
+int launch_pt_swap(const double *gathered, long long n_total, uint64_t seed, long long round, long long id0,
+                   long long n_local, double *temperature_out, int32_t *n_accepted_out, const double *tape,
+                   cudaStream_t st) {
+    const int use_smem = n_total <= SWAP_SMEM_MAX;
+    const size_t smem = use_smem ? (size_t)n_total * sizeof(double) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(k_pt_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+    }
+    k_pt_swap<<<1, SWAP_THREADS, smem, st>>>(const_cast<double *>(gathered), n_total, seed, round, id0, n_local,
+                                             temperature_out, n_accepted_out, tape, use_smem);
+    return (int)cudaGetLastError();
+}
+int launch_raster1d(const double *sites, const double *values, const int32_t *k, int K, long long C,
+                    const double *x, int R, int32_t *idx_out, double *field_out, cudaStream_t st) {
+    k_raster1d<<<blocks_for(C, 64), 64, 0, st>>>(sites, values, k, K, C, x, R, idx_out, field_out);
+    return (int)cudaGetLastError();
+}
+int launch_dense_forward(const double *G, const double *m, int R, int M, long long C, double *dpred_out,
+                         cudaStream_t st) {
+    dim3 grid(blocks_for(C, 128), R);
+    k_dense_forward<<<grid, 128, 0, st>>>(G, m, R, M, C, dpred_out);
+    return (int)cudaGetLastError();
+}
+int launch_loglike(const double *dpred, const double *dobs, const double *sigma, int R, long long C,
+                   double *misfit_out, double *logdet_out, cudaStream_t st) {
+    k_loglike<<<blocks_for(C, 128), 128, 0, st>>>(dpred, dobs, sigma, R, C, misfit_out, logdet_out);
+    return (int)cudaGetLastError();
+}
+int launch_logprior(const bbb_space_spec &space, const double *values, const int32_t *k, long long C, double *out,
+                    cudaStream_t st) {
+    k_logprior<<<blocks_for(C, 128), 128, 0, st>>>(space, values, k, C, out);
+    return (int)cudaGetLastError();
+}
+int launch_phi_from_partial(const double *partial, int n_tiles, long long C, double *phi_out, cudaStream_t st) {
+    k_phi_from_partial<<<blocks_for(C, 128), 128, 0, st>>>(partial, n_tiles, C, phi_out);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace bbb

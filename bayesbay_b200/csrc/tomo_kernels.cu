@@ -1,0 +1,197 @@
+// F1 (2-D Voronoi nearest-site rasterisation) and F2 (straight-ray forward as a CSR ray-matrix
+// SpMM with chains as the dense, coalesced dimension, fused with the Gaussian misfit reduction).
+//
+// Layout: every per-chain array is [..][C] with the chain index fastest, so a warp = 32 chains
+// reads/writes one contiguous 32 B (uint8), 128 B (int32) or 256 B (fp64) segment per access.
+#include "kernels.h"
+
+namespace bbb {
+
+// ------------------------------------------------------------------------------------------------
+// F1: brute-force nearest site.  One lane = one chain, one warp = 32 chains x a strip of grid
+// points; the 32 chains' site rows come from L1/L2 as coalesced 256 B segments.  Squared distance
+// dx*dx + dy*dy with separately rounded products and sum (no FMA contraction) and strict '<' so
+// the lowest index wins ties: identical to numpy argmin / scipy KDTree.query on the same sites.
+// ------------------------------------------------------------------------------------------------
+constexpr int RASTER_POINTS_PER_LANE = 4;
+constexpr int RASTER_WARPS = 8;
+
+template <typename IdxT>
+__global__ void __launch_bounds__(RASTER_WARPS * 32)
+k_raster2d(RasterArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * CHAIN_TILE + lane;
+    const bool in_range = c < a.C;
+    bool active = in_range;
+    int sslot = 0, islot = 0;
+    if (in_range) {
+        if (a.move != nullptr) {
+            const int mv = a.move[c];
+            active = !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space &&
+                     (mv & 3) != BBB_MOVE_VALUES;
+        }
+        if (a.sel != nullptr) sslot = a.sel[c] ^ a.slot_xor;
+        if (a.idx_sel != nullptr) islot = a.idx_sel[c] ^ a.slot_xor;
+    }
+    if (!__syncthreads_or(active ? 1 : 0)) return;
+    const int k = active ? a.k[(long long)sslot * a.C + c] : 0;
+    int kmax = k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    const double *sx = a.sites + ((long long)sslot * 2 + 0) * a.K * a.C + (in_range ? c : 0);
+    const double *sy = a.sites + ((long long)sslot * 2 + 1) * a.K * a.C + (in_range ? c : 0);
+    IdxT *out = reinterpret_cast<IdxT *>(a.idx) + (long long)islot * a.G * a.C + (in_range ? c : 0);
+
+    const int g_begin = blockIdx.y * a.points_per_block;
+    const int g_end = min(a.G, g_begin + a.points_per_block);
+    for (int g0 = g_begin + warp * RASTER_POINTS_PER_LANE; g0 < g_end; g0 += RASTER_WARPS * RASTER_POINTS_PER_LANE) {
+        double gx[RASTER_POINTS_PER_LANE], gy[RASTER_POINTS_PER_LANE], best[RASTER_POINTS_PER_LANE];
+        int bi[RASTER_POINTS_PER_LANE];
+#pragma unroll
+        for (int q = 0; q < RASTER_POINTS_PER_LANE; ++q) {
+            const int g = min(g0 + q, a.G - 1);
+            gx[q] = a.px[g];
+            gy[q] = a.py[g];
+            best[q] = INFINITY;
+            bi[q] = 0;
+        }
+        for (int j = 0; j < kmax; ++j) {
+            if (j < k) {
+                const double x = sx[(long long)j * a.C];
+                const double y = sy[(long long)j * a.C];
+#pragma unroll
+                for (int q = 0; q < RASTER_POINTS_PER_LANE; ++q) {
+                    const double dx = x - gx[q];
+                    const double dy = y - gy[q];
+                    const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    if (d < best[q]) { best[q] = d; bi[q] = j; }
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < RASTER_POINTS_PER_LANE; ++q)
+                if (g0 + q < g_end) out[(long long)(g0 + q) * a.C] = (IdxT)bi[q];
+        }
+    }
+}
+
+int launch_raster2d(const RasterArgs &a, cudaStream_t stream) {
+    const int chain_tiles = (int)((a.C + CHAIN_TILE - 1) / CHAIN_TILE);
+    // enough blocks for >= ~4 waves of 148 SMs, each block at least 64 points
+    int ppb = a.points_per_block;
+    dim3 grid(chain_tiles, (a.G + ppb - 1) / ppb);
+    if (a.idx_bytes == 1) k_raster2d<uint8_t><<<grid, RASTER_WARPS * 32, 0, stream>>>(a);
+    else k_raster2d<uint16_t><<<grid, RASTER_WARPS * 32, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int raster_points_per_block(int G, long long C) {
+    const long long chain_tiles = (C + CHAIN_TILE - 1) / CHAIN_TILE;
+    const long long target_blocks = 148LL * 8;
+    long long per_tile = (target_blocks + chain_tiles - 1) / chain_tiles;
+    if (per_tile < 1) per_tile = 1;
+    long long ppb = (G + per_tile - 1) / per_tile;
+    const int quantum = RASTER_WARPS * RASTER_POINTS_PER_LANE;
+    ppb = ((ppb + quantum - 1) / quantum) * quantum;
+    if (ppb < quantum) ppb = quantum;
+    return (int)ppb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F2: d_pred[r][c] = sum_j data[j] * f(value[cell_idx[indices[j]][c]][c]);  phi[c] = sum_r w_r res^2.
+// Block = 32 chains (lanes) x RAY_TILE rays (8 warps take rays round-robin).  The 32 chains'
+// (transformed) cell values are staged once per block in shared memory as table[j][lane]
+// (conflict-free: a lane only ever touches its own bank pair), so per non-zero a warp issues one
+// coalesced 32 B / 64 B index gather, one LDS and one DFMA; the CSR entry is a warp-uniform load.
+// The per-block misfit is written to partial[tile][c] and summed in tile order by the accept
+// stage, which keeps the result bit-reproducible run to run (no atomics).
+// ------------------------------------------------------------------------------------------------
+constexpr int SPMM_WARPS = 8;
+
+template <typename IdxT>
+__global__ void __launch_bounds__(SPMM_WARPS * 32)
+k_ray_spmm(SpmmArgs a) {
+    extern __shared__ double table[];  // [K_block][32]
+    __shared__ double red[SPMM_WARPS][32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * CHAIN_TILE + lane;
+    const bool in_range = c < a.C;
+    bool active = in_range;
+    int vslot = 0, islot = 0;
+    if (in_range) {
+        bool geom = false;
+        if (a.move != nullptr) {
+            const int mv = a.move[c];
+            active = !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space;
+            geom = (mv & 3) != BBB_MOVE_VALUES;
+        }
+        if (a.sel != nullptr) vslot = a.sel[c] ^ a.slot_xor;
+        if (a.idx_sel != nullptr) islot = a.idx_sel[c] ^ ((a.move != nullptr) ? (geom ? 1 : 0) : 0);
+    }
+    if (!__syncthreads_or(active ? 1 : 0)) return;
+    const int k = active ? a.k[(long long)vslot * a.C + c] : 0;
+    int kmax = k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    const double *vals = a.values + ((long long)vslot * a.n_params + a.param) * a.K * a.C + (in_range ? c : 0);
+    for (int j = warp; j < kmax; j += SPMM_WARPS) {
+        double v = (j < k) ? vals[(long long)j * a.C] : 1.0;
+        if (a.transform == BBB_TRANSFORM_RECIPROCAL) v = 1.0 / v;
+        table[j * 32 + lane] = v;
+    }
+    __syncthreads();
+    const IdxT *idx = reinterpret_cast<const IdxT *>(a.idx) + (long long)islot * a.G * a.C + (in_range ? c : 0);
+    const int r_begin = blockIdx.y * RAY_TILE;
+    const int r_end = min(a.R, r_begin + RAY_TILE);
+    double ssq = 0.0;
+    for (int r = r_begin + warp; r < r_end; r += SPMM_WARPS) {
+        const int j0 = a.indptr[r];
+        const int j1 = a.indptr[r + 1];
+        double acc = 0.0;
+        if (active) {
+            for (int jj = j0; jj < j1; ++jj) {
+                const int col = a.indices[jj];
+                const double v = a.data[jj];
+                const int cell = (int)idx[(long long)col * a.C];
+                acc += v * table[cell * 32 + lane];
+            }
+            if (a.dpred != nullptr) a.dpred[(long long)r * a.C + c] = acc;
+            const double res = acc - a.dobs[r];
+            const double w = (a.w != nullptr) ? a.w[r] : 1.0;
+            ssq += w * (res * res);
+        }
+    }
+    red[warp][lane] = ssq;
+    __syncthreads();
+    if (warp == 0 && active && a.partial != nullptr) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < SPMM_WARPS; ++w) tot += red[w][lane];
+        a.partial[(long long)blockIdx.y * a.C + c] = tot;
+    }
+}
+
+int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream) {
+    const int chain_tiles = (int)((a.C + CHAIN_TILE - 1) / CHAIN_TILE);
+    const int ray_tiles = (a.R + RAY_TILE - 1) / RAY_TILE;
+    dim3 grid(chain_tiles, ray_tiles);
+    const size_t smem = (size_t)a.K * 32 * sizeof(double);
+    cudaError_t err = cudaSuccess;
+    if (a.idx_bytes == 1) {
+        if (smem > 48 * 1024)
+            err = cudaFuncSetAttribute(k_ray_spmm<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        k_ray_spmm<uint8_t><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
+    } else {
+        if (smem > 48 * 1024)
+            err = cudaFuncSetAttribute(k_ray_spmm<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        k_ray_spmm<uint16_t><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace bbb

@@ -1,0 +1,227 @@
+/*
+ * bbb200.h -- C ABI of libbbb200.so, the B200-native batched reversible-jump MCMC engine.
+ *
+ * This is the drop-in boundary for ONE path of BayesBay 0.3.11 (reference paths relative to
+ * /root/reference): the chain pool + chain step that `Sampler.advance_chain`
+ * (src/bayesbay/samplers/_samplers.py:191-239) farms out to one OS process per chain, i.e.
+ * `BaseMarkovChain.advance_chain/_next_iteration` (src/bayesbay/_markov_chain.py:204-297) and
+ * everything it calls (perturbations/, discretization/, prior/, likelihood/, _utils_1d.pyx).
+ * A `Sampler` subclass whose `run()` calls these entry points instead of `advance_chain` is a
+ * plug-in of the reference's own extension seam (`Sampler.run` is abstract,
+ * samplers/_samplers.py:152-162; used by `BaseBayesianInversion.run`, _bayes_inversion.py:236-249).
+ *
+ * Conventions
+ *   - plain C types only; every pointer named "device" is a CUDA device pointer owned by the
+ *     caller (PyTorch allocates, this library never frees caller memory);
+ *   - every entry returns 0 on success or a negative bbb_status; bbb_last_error() gives the
+ *     message (thread-local);
+ *   - all launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*);
+ *   - chains are the fastest-varying (coalesced) dimension of every per-chain array: an array
+ *     documented as [A][B][C] is row-major with C = n_chains innermost.
+ */
+#ifndef BBB200_H
+#define BBB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBB_ABI_VERSION 1
+
+#define BBB_MAX_SPACES 4
+#define BBB_MAX_PARAMS 8
+#define BBB_MAX_TARGETS 4
+#define BBB_MAX_LINEAR_PARAMS 16
+
+typedef enum {
+    BBB_OK = 0,
+    BBB_ERR_INVALID = -1,   /* invalid spec / argument */
+    BBB_ERR_SHAPE = -2,     /* buffer shape / missing buffer */
+    BBB_ERR_CUDA = -3,      /* a CUDA runtime call failed (message carries the CUDA error) */
+    BBB_ERR_UNSUPPORTED = -4
+} bbb_status;
+
+/* parameter-space kinds: ParameterSpace (parameterization/_parameter_space.py), Voronoi1D,
+ * Voronoi2D (discretization/_voronoi.py:471, :1283) */
+enum { BBB_SPACE_PLAIN = 0, BBB_SPACE_VORONOI1D = 1, BBB_SPACE_VORONOI2D = 2 };
+/* prior kinds: UniformPrior(a=vmin,b=vmax), GaussianPrior(a=mean,b=std), LaplacePrior(a=mean,b=scale)
+ * (prior/_prior.py:300, :484, :685) */
+enum { BBB_PRIOR_UNIFORM = 0, BBB_PRIOR_GAUSSIAN = 1, BBB_PRIOR_LAPLACE = 2 };
+enum { BBB_BIRTH_FROM_PRIOR = 0, BBB_BIRTH_FROM_NEIGHBOUR = 1 };
+/* forward operators (the user forward functions of the tutorials) */
+enum { BBB_FWD_RAY2D = 0, BBB_FWD_LOOKUP1D = 1, BBB_FWD_LINEAR = 2 };
+enum { BBB_TRANSFORM_IDENTITY = 0, BBB_TRANSFORM_RECIPROCAL = 1 };
+/* data covariance: hierarchical sigma (Target(std_min,...)), fixed scalar / vector inverse covariance
+ * (likelihood/_target.py:136-170) */
+enum { BBB_COV_HIERARCHICAL = 0, BBB_COV_SCALAR = 1, BBB_COV_VECTOR = 2 };
+/* inner move kinds; move id = 4 * space + kind, noise move id = 4 * n_spaces */
+enum { BBB_MOVE_BIRTH = 0, BBB_MOVE_DEATH = 1, BBB_MOVE_VALUES = 2, BBB_MOVE_SITES = 3 };
+
+typedef struct {
+    int32_t kind;            /* BBB_SPACE_* */
+    int32_t ndim;            /* 0, 1, 2 */
+    int32_t trans_d;
+    int32_t kmin, kmax;      /* kmax is also the pad K of the SoA arrays */
+    int32_t kinit_max;       /* int((kmax-kmin)*init_range + kmin), discretization/_voronoi.py:159 */
+    int32_t birth_from;      /* BBB_BIRTH_FROM_* */
+    int32_t n_params;
+    double vmin[2], vmax[2], site_std[2];
+    double w_birth, w_death, w_values, w_sites; /* inner weights 1,1,3,1 (0 = move absent) */
+    int32_t prior_kind[BBB_MAX_PARAMS];
+    double prior_a[BBB_MAX_PARAMS], prior_b[BBB_MAX_PARAMS];
+    double perturb_std[BBB_MAX_PARAMS], perturb_std_birth[BBB_MAX_PARAMS];
+} bbb_space_spec;
+
+typedef struct {
+    int32_t n_data;
+    int32_t cov_kind;        /* BBB_COV_* */
+    double std_min, std_max, std_perturb_std;
+    double cov_scalar;
+    const double *dobs;      /* device [n_data] */
+    const double *cov_vec;   /* device [n_data] or NULL */
+    int32_t fwd_kind;        /* BBB_FWD_* */
+    int32_t space;           /* parameter space the forward reads */
+    int32_t param;           /* ray2d / lookup1d: parameter index inside the space */
+    int32_t transform;       /* ray2d: BBB_TRANSFORM_* applied to the cell value */
+    /* ray2d: CSR ray matrix shared by all chains + query points of the rasterisation */
+    int32_t n_points;
+    int64_t nnz;
+    const int32_t *indptr;   /* device [n_data + 1] */
+    const int32_t *indices;  /* device [nnz] */
+    const double *data;      /* device [nnz] */
+    const double *points_x;  /* device [n_points] */
+    const double *points_y;  /* device [n_points] */
+    /* lookup1d: data positions */
+    const double *x;         /* device [n_data] */
+    /* linear: d_pred = G @ concat(values[p] for p in lin_params), each of length kmax (fixed k) */
+    int32_t n_lin_params;
+    int32_t lin_params[BBB_MAX_LINEAR_PARAMS];
+    const double *G;         /* device [n_data][n_lin_params * kmax] row-major */
+} bbb_target_spec;
+
+typedef struct {
+    int32_t n_spaces, n_targets;
+    bbb_space_spec spaces[BBB_MAX_SPACES];
+    bbb_target_spec targets[BBB_MAX_TARGETS];
+    uint64_t seed;           /* Philox key */
+} bbb_problem_spec;
+
+/* Device buffers of one engine (all owned by the caller).  "slot" arrays are double-buffered:
+ * sel[s][c] names the slot holding chain c's CURRENT state of space s, the other slot receives
+ * the proposal; accepting a proposal flips the bit (no copy). */
+typedef struct {
+    int64_t n_chains;        /* chains resident on this device */
+    int64_t chain_id0;       /* global id of local chain 0 (Philox counter word) */
+    /* per parameter space */
+    double *sites[BBB_MAX_SPACES];    /* [2][ndim][K][C] */
+    double *values[BBB_MAX_SPACES];   /* [2][n_params][K][C] */
+    int32_t *k[BBB_MAX_SPACES];       /* [2][C] */
+    uint8_t *sel[BBB_MAX_SPACES];     /* [C] */
+    /* per target */
+    double *sigma[BBB_MAX_TARGETS];   /* [2][C]  (0 = current, 1 = proposed) hierarchical only */
+    double *phi[BBB_MAX_TARGETS];     /* [2][C]  sum_i w_i r_i^2 with sigma factored out */
+    void *cell_idx[BBB_MAX_TARGETS];  /* ray2d: [2][G][C] uint8 (K <= 256) or uint16 */
+    uint8_t *idx_sel[BBB_MAX_TARGETS];/* ray2d: [C] */
+    double *partial[BBB_MAX_TARGETS]; /* ray2d: [n_ray_tiles][C], n_ray_tiles = bbb_ray_tiles(n_data) */
+    /* chain scalars */
+    double *temperature;     /* [C] */
+    int64_t *iteration;      /* [C] iterations done (Philox counter) */
+    /* last proposal / decision (inputs of the accept stage, outputs for step-replay parity) */
+    int32_t *move;           /* [C] move id */
+    int32_t *edit;           /* [2][C] (remove index or -1, insert index or -1) */
+    double *log_prob_ratio;  /* [C] */
+    double *log_like_ratio;  /* [C] */
+    int32_t *accepted;       /* [C] */
+    /* statistics: _save_statistics (src/bayesbay/_markov_chain.py:136-157) */
+    int64_t *n_proposed;     /* [4*n_spaces+1][C] */
+    int64_t *n_accepted;     /* [4*n_spaces+1][C] */
+    /* optional recorded uniforms (step-replay parity); NULL selects Philox */
+    const double *tape;      /* [C][tape_stride] */
+    int64_t tape_stride;
+    int64_t *tape_cursor;    /* [C] */
+} bbb_buffers;
+
+typedef struct bbb_engine bbb_engine;
+
+int bbb_abi_version(void);
+const char *bbb_last_error(void);
+/* number of ray tiles the partial-misfit buffer must hold for a ray target with n_data rays */
+int64_t bbb_ray_tiles(int64_t n_data);
+
+/* Engine life cycle.  Replaces the chain pool `Sampler.advance_chain`
+ * (samplers/_samplers.py:191-239).  The spec is copied; device pointers inside it are borrowed. */
+int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out);
+int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *buffers);
+void bbb_engine_destroy(bbb_engine *e);
+
+/* Draw starting states on the device: `MarkovChain._init_starting_state`
+ * (src/bayesbay/_markov_chain.py:364-395) -> Voronoi._initialize / ParameterSpace._initialize /
+ * Prior.initialize / Target.initialize.  Also evaluates the forward of every chain. */
+int bbb_engine_init_states(bbb_engine *e, void *stream);
+/* Re-evaluate rasterisation, forward and misfit of the CURRENT states (after the caller wrote
+ * starting states, temperatures, ... into the bound buffers). */
+int bbb_engine_refresh(bbb_engine *e, void *stream);
+/* Advance every chain n_steps iterations: `BaseMarkovChain.advance_chain`
+ * (src/bayesbay/_markov_chain.py:249-297) for all chains at once. */
+int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream);
+/* Compact the CURRENT state of every chain into caller arrays (`_save_state`,
+ * src/bayesbay/_markov_chain.py:115-134): k [C] int32, sites [ndim][K][C], values [P][K][C]. */
+int bbb_engine_gather_space(bbb_engine *e, int space, int32_t *k_out, double *sites_out,
+                            double *values_out, void *stream);
+/* d_pred of the CURRENT states of one target, [n_data][C] (the "{target}.dpred" cache entry,
+ * likelihood/_log_likelihood.py:311-320). */
+int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream);
+/* Per-chain totals over targets with each chain's own sigma: misfit and log|C_e|
+ * (`LogLikelihood._get_misfit_and_det`, likelihood/_log_likelihood.py:308-332), both [C]. */
+int bbb_engine_misfit_logdet(bbb_engine *e, double *misfit_out, double *logdet_out, void *stream);
+
+/* Parallel-tempering swap round: `ParallelTempering.on_end_advance_chain`
+ * (samplers/_samplers.py:334-342).  `gathered` is [n_total][3] (misfit, logdet, T) for ALL chains
+ * of the job in global chain order (all-gathered by the caller over NCCL); every rank runs the
+ * same n_total sequential attempts from the shared Philox key (seed, round) and writes the new
+ * temperatures of its own chains [id0, id0 + n_local) to temperature_out [n_local]; the temperature
+ * column of `gathered` is updated in place.
+ * If `tape` is not NULL the uniforms come from it (3 per attempt). */
+int bbb_pt_swap(double *gathered, int64_t n_total, uint64_t seed, int64_t round,
+                int64_t id0, int64_t n_local, double *temperature_out, int32_t *n_accepted_out,
+                const double *tape, void *stream);
+
+/* ---- stand-alone kernels (parity entry points; the engine uses the same device code) ---- */
+/* F1: nearest Voronoi site of every query point for every chain.
+ * Voronoi2D.interpolate_tessellation (discretization/_voronoi.py:1429-1454) = KDTree.query.
+ * sites [2][K][C], k [C], points [G] -> idx [G][C] (uint8 if K <= 256 else uint16). */
+int bbb_raster2d(const double *sites, const int32_t *k, int32_t K, int64_t C, const double *points_x,
+                 const double *points_y, int32_t G, void *idx_out, void *stream);
+/* F1/F4: 1-D nearest-nuclei lookup, interpolate_nearest_1d (_utils_1d.pyx:87-114,171-192).
+ * sites [K][C] sorted, values [K][C], x [R] -> idx [R][C] int32 and field [R][C]. */
+int bbb_raster1d(const double *sites, const double *values, const int32_t *k, int32_t K, int64_t C,
+                 const double *x, int32_t R, int32_t *idx_out, double *field_out, void *stream);
+/* F2: straight-ray forward, d_pred[r][c] = sum_j data[j] * f(values[idx[indices[j]][c]][c])
+ * (31_sw_tomography.ipynb cell 12: jacobian @ (1 / vel[nearest])).  Writes d_pred [R][C] if not
+ * NULL and phi[c] = sum_r w_r (d_pred - dobs)^2 if not NULL (w = NULL means 1). */
+int bbb_ray_forward(const void *idx, const double *values, const int32_t *k, int32_t K, int64_t C,
+                    int32_t G, int32_t R, const int32_t *indptr, const int32_t *indices,
+                    const double *data, int32_t transform, const double *dobs, const double *w,
+                    double *dpred_out, double *phi_out, double *partial_scratch, void *stream);
+/* F3: dense linear forward d_pred = G @ m, m [M][C] -> d_pred [R][C] (02_hierarchical_polyfit.ipynb
+ * cell 12). */
+int bbb_dense_forward(const double *G, const double *m, int32_t R, int32_t M, int64_t C,
+                      double *dpred_out, void *stream);
+/* L1/L2: Gaussian misfit, log-determinant and (tempered) log-likelihood ratio
+ * (likelihood/_log_likelihood.py:204-251,308-332; likelihood/_target.py:136-208), uncorrelated
+ * hierarchical noise: dpred [R][C], sigma [C] -> misfit [C], logdet [C]. */
+int bbb_loglike(const double *dpred, const double *dobs, const double *sigma, int32_t R, int64_t C,
+                double *misfit_out, double *logdet_out, void *stream);
+/* L3: ParameterSpace.log_prior (parameterization/_parameter_space.py:189-195): values [P][K][C],
+ * k [C] -> log_prior [C]. */
+int bbb_logprior(const bbb_space_spec *space, const double *values, const int32_t *k, int64_t C,
+                 double *log_prior_out, void *stream);
+/* Philox4x32-10 known-answer check: fills out[4] (host) for counter[4], key[2]. */
+int bbb_philox_kat(const uint32_t *counter, const uint32_t *key, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBB200_H */

@@ -1,0 +1,180 @@
+"""Engine-level parity (through the C ABI): the CUDA chain step against
+(a) tape-driven runs of the UNMODIFIED reference (tests/golden/replay_*.npz) and
+(b) the oracle driven by the same Philox streams, plus parallel-tempering swap rounds."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import chain as OC  # noqa: E402
+from oracle import rng as OR  # noqa: E402
+from tests import problems  # noqa: E402
+
+
+def _engine(spec, n_chains, **kw):
+    from bayesbay_b200._engine import Engine
+
+    assert torch.cuda.is_available()
+    return Engine(spec, n_chains, **kw)
+
+
+def _check_states(states, g, t, spec, rtol=1e-12):
+    sp = spec["spaces"][0]
+    for c, st in enumerate(states):
+        k = int(g["k"][c, t])
+        ss = st["spaces"][0]
+        assert ss["k"] == k, (c, t)
+        if sp["ndim"] == 2:
+            np.testing.assert_allclose(ss["sites"], g["sites"][c, t, :k, :], rtol=rtol, atol=1e-15)
+        elif sp["ndim"] == 1:
+            np.testing.assert_allclose(ss["sites"], g["sites"][c, t, :k, 0], rtol=rtol, atol=1e-15)
+        for j in range(len(sp["params"])):
+            np.testing.assert_allclose(ss["values"][j], g["values"][c, t, j, :k], rtol=rtol, atol=1e-15)
+        np.testing.assert_allclose(st["sigma"][0], g["sigma"][c, t], rtol=rtol)
+
+
+@pytest.mark.parametrize("name", list(problems.REPLAYS))
+def test_step_replay_against_reference(name, golden_dir):
+    """Every chain consumes the tape the reference consumed: initial state, move choice, prior/proposal
+    ratio, log-likelihood ratio, accept bit, resulting state and tape position must all agree."""
+    g = np.load(os.path.join(golden_dir, f"replay_{name}.npz"))
+    spec = problems.spec_from_ingredients(problems.REPLAYS[name]())
+    n_chains, n_steps = g["lpr"].shape
+    eng = _engine(spec, n_chains, tape=g["tape"])
+    eng.init_states()
+    assert np.array_equal(eng.draw_cursor.cpu().numpy(), g["cursor"][:, 0])
+    _check_states(eng.fetch_states(), g, 0, spec)
+    for t in range(n_steps):
+        eng.step(1)
+        move = eng.move.cpu().numpy()
+        lpr = eng.log_prob_ratio.cpu().numpy()
+        llr = eng.log_like_ratio.cpu().numpy()
+        acc = eng.accepted.cpu().numpy()
+        assert np.array_equal(move, g["move"][:, t]), t
+        assert np.array_equal(eng.draw_cursor.cpu().numpy(), g["cursor"][:, t + 1]), t
+        ref_lpr = g["lpr"][:, t]
+        inf = np.isinf(ref_lpr)
+        assert np.array_equal(np.isinf(lpr), inf)
+        np.testing.assert_allclose(lpr[~inf], ref_lpr[~inf], rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(llr[~inf], g["llr"][:, t][~inf], rtol=1e-9, atol=1e-9)
+        assert np.array_equal(acc, g["accepted"][:, t]), t
+        _check_states(eng.fetch_states(), g, t + 1, spec)
+    # statistics accumulate like _save_statistics
+    prop = eng.n_proposed.cpu().numpy()
+    accd = eng.n_accepted.cpu().numpy()
+    for c in range(n_chains):
+        assert np.array_equal(prop[:, c], np.bincount(g["move"][c], minlength=5))
+        assert np.array_equal(accd[:, c], np.bincount(g["move"][c], weights=g["accepted"][c], minlength=5))
+    assert (eng.iteration.cpu().numpy() == n_steps).all()
+
+
+def _oracle_state(st):
+    sp = st["spaces"][0]
+    return OC.ChainState([OC.SpaceState(sp["k"], None if sp["sites"] is None else np.array(sp["sites"]),
+                                        [np.array(v) for v in sp["values"]])], list(st["sigma"]), 1.0, [None])
+
+
+@pytest.mark.parametrize("name,n_chains,n_steps", [("tomo_small", 96, 40), ("partition_1d", 70, 60),
+                                                   ("partition_1d_nb", 33, 60), ("polyfit", 64, 50)])
+def test_philox_steps_against_oracle(name, n_chains, n_steps):
+    """Counter-based streams: device and oracle draw the same Philox4x32-10 uniforms, so whole
+    trajectories must agree (until a 1-ulp difference flips a decision, which the test tolerates
+    only by comparing chains that are still in step)."""
+    spec = problems.spec_from_ingredients(problems.REPLAYS[name]())
+    seed, id0 = 1234567890123, 1000
+    eng = _engine(spec, n_chains, seed=seed, chain_id0=id0)
+    eng.init_states()
+    dev0 = eng.fetch_states()
+    states = []
+    for c in range(n_chains):
+        st = OC.init_state(spec, OR.PhiloxStream(seed, id0 + c, 0, OR.STREAM_INIT))
+        states.append(st)
+        d = _oracle_state(dev0[c])
+        assert d.spaces[0].k == st.spaces[0].k
+        if st.spaces[0].sites is not None:
+            np.testing.assert_allclose(d.spaces[0].sites, st.spaces[0].sites, rtol=1e-14)
+        for a, b in zip(d.spaces[0].values, st.spaces[0].values):
+            np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(d.sigma[0], st.sigma[0], rtol=1e-14)
+    in_step = np.ones(n_chains, bool)
+    for t in range(n_steps):
+        eng.step(1)
+        move = eng.move.cpu().numpy()
+        lpr = eng.log_prob_ratio.cpu().numpy()
+        llr = eng.log_like_ratio.cpu().numpy()
+        acc = eng.accepted.cpu().numpy()
+        for c in range(n_chains):
+            if not in_step[c]:
+                continue
+            states[c], info = OC.step(spec, states[c], OR.PhiloxStream(seed, id0 + c, t))
+            assert info["move"] == move[c], (c, t)
+            if math.isinf(info["log_prob_ratio"]):
+                assert lpr[c] == info["log_prob_ratio"]
+            else:
+                np.testing.assert_allclose(lpr[c], info["log_prob_ratio"], rtol=1e-10, atol=1e-11)
+                np.testing.assert_allclose(llr[c], info["log_like_ratio"], rtol=1e-8, atol=1e-8)
+            if bool(acc[c]) != info["accepted"]:
+                in_step[c] = False  # decision on a knife edge; stop following this chain
+    assert in_step.mean() > 0.95
+    final = eng.fetch_states()
+    for c in np.flatnonzero(in_step):
+        d = _oracle_state(final[c])
+        assert d.spaces[0].k == states[c].spaces[0].k
+        for a, b in zip(d.spaces[0].values, states[c].spaces[0].values):
+            np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12)
+    # cached misfit equals a fresh evaluation of the final states (no drift in the double-buffering)
+    mis, ld = eng.misfit_logdet()
+    eng.refresh()
+    mis2, ld2 = eng.misfit_logdet()
+    np.testing.assert_allclose(mis.cpu().numpy(), mis2.cpu().numpy(), rtol=1e-13)
+    np.testing.assert_allclose(ld.cpu().numpy(), ld2.cpu().numpy(), rtol=1e-13)
+    for c in np.flatnonzero(in_step)[:8]:
+        m, l_ = OC.misfit_and_logdet(spec, states[c])
+        np.testing.assert_allclose(mis[c].item(), m, rtol=1e-10)
+        np.testing.assert_allclose(ld[c].item(), l_, rtol=1e-12)
+
+
+def test_dpred_and_cell_index_of_current_states():
+    spec = problems.spec_from_ingredients(problems.tomo_small())
+    eng = _engine(spec, 40, seed=7)
+    eng.init_states()
+    eng.step(25)
+    states = eng.fetch_states()
+    dp = eng.dpred(0).cpu().numpy()
+    idx = eng.current_cell_idx(0).cpu().numpy()
+    fwd = spec["targets"][0]["forward"]
+    from oracle import kernels as OK
+
+    for c in range(40):
+        ss = states[c]["spaces"][0]
+        ref, ridx = OK.tomography_forward(fwd, ss["sites"], ss["values"][0])
+        assert np.array_equal(idx[:, c], ridx), c
+        np.testing.assert_allclose(dp[:, c], ref, rtol=1e-12)
+
+
+def test_pt_swap_golden_and_oracle(golden_dir):
+    from bayesbay_b200._engine import pt_swap
+
+    g = np.load(os.path.join(golden_dir, "pt_swap.npz"))
+    for r in range(g["misfit"].shape[0]):
+        gathered = torch.as_tensor(np.stack((g["misfit"][r], g["logdet"][r], g["t_before"][r]), axis=1).copy()).cuda()
+        tape = torch.as_tensor(g["tape"][int(g["cursor0"][r]): int(g["cursor1"][r])].copy()).cuda()
+        t_out, n_acc = pt_swap(gathered, 0, 0, 0, 6, tape=tape)
+        assert np.array_equal(t_out.cpu().numpy(), g["t_after"][r])
+        assert np.array_equal(gathered.cpu().numpy()[:, 2], g["t_after"][r])
+    # Philox mode against the oracle, sharded output, many chains
+    rng = np.random.default_rng(0)
+    for n in (2, 7, 64, 1000, 8192):
+        mis = rng.uniform(50, 150, n)
+        ld = rng.uniform(-20, 20, n)
+        temps = OC.pt_ladder(n, 5.0, 0.4) if n > 2 else np.array([1.0, 5.0])
+        ref, n_ref = OC.pt_swap_round(mis, ld, list(temps), OR.PhiloxStream(99, 0, 3, OR.STREAM_SWAP))
+        gathered = torch.as_tensor(np.stack((mis, ld, temps), axis=1).copy()).cuda()
+        id0, nl = n // 4, n - n // 4 - n // 3
+        t_out, n_acc = pt_swap(gathered, 99, 3, id0, nl)
+        assert np.array_equal(t_out.cpu().numpy(), np.array(ref)[id0: id0 + nl]), n
+        assert int(n_acc.item()) == n_ref
