@@ -31,8 +31,16 @@ def kg(golden_dir):
     return np.load(os.path.join(golden_dir, "kernels.npz"))
 
 
+_KEEP = []  # device inputs must outlive the asynchronous launches that read them
+
+
 def dev(a, dtype=None):
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).cuda()
+    t = torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).cuda()
+    _KEEP.append(t)
+    if len(_KEEP) > 256:
+        torch.cuda.synchronize()
+        del _KEEP[:128]
+    return t
 
 
 def ptr(t):
