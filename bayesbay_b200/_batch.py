@@ -1,0 +1,334 @@
+"""Host-side runtime of a batch of chains: owns one :class:`Engine`, converts between the
+reference's per-chain objects (``State``, ``saved_states``, ``statistics``) and the device SoA
+buffers, and implements the batched ``advance_chain``.
+
+This replaces the reference's chain pool -- ``Sampler.advance_chain``'s
+``joblib.Parallel(n_jobs=len(chains), backend="loky")`` over pickled ``MarkovChain`` objects
+(src/bayesbay/samplers/_samplers.py:191-239) -- by launches on one CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import os
+from collections import defaultdict
+from typing import List, Optional
+
+import numpy as np
+
+from . import _compile
+from ._state import DataNoiseState, ParameterSpaceState, State
+
+_seed_counter = itertools.count()
+_base_seed: Optional[int] = None
+
+
+def seed(value: Optional[int]):
+    """Set the base seed of the Philox streams used by engines created afterwards (``None`` = draw
+    from OS entropy, the default -- the reference's chains are unseeded too)."""
+    global _base_seed, _seed_counter
+    _base_seed = value
+    _seed_counter = itertools.count()
+
+
+def next_seed() -> int:
+    n = next(_seed_counter)
+    if _base_seed is None:
+        return int.from_bytes(os.urandom(8), "little")
+    return (int(_base_seed) * 0x9E3779B97F4A7C15 + n * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+# --------------------------------------------------------------------------- #
+# state conversion
+# --------------------------------------------------------------------------- #
+def state_to_host_dict(spec: dict, state: State) -> dict:
+    spaces = []
+    for sp in spec["spaces"]:
+        ps = state[sp["name"]]
+        if ps is None:
+            raise ValueError(f"starting state has no parameter space {sp['name']!r}")
+        k = int(ps.n_dimensions)
+        sites = ps["discretization"] if sp["ndim"] else None
+        if sp["ndim"] and sites is None:
+            raise ValueError(f"starting state of {sp['name']!r} has no 'discretization'")
+        values = []
+        for p in sp["params"]:
+            v = ps[p["name"]]
+            if v is None or len(v) != k:
+                raise ValueError(f"starting state: parameter {sp['name']}.{p['name']} should have {k} values")
+            values.append(np.asarray(v, dtype=np.float64))
+        if sp["ndim"] == 1:
+            sites = np.asarray(sites, dtype=np.float64).reshape(k)
+            if np.any(np.diff(sites) < 0):
+                raise ValueError("Voronoi1D starting sites must be sorted")
+        elif sp["ndim"] == 2:
+            sites = np.asarray(sites, dtype=np.float64).reshape(k, 2)
+        spaces.append(dict(k=k, sites=sites, values=values))
+    sigma = []
+    for t in spec["targets"]:
+        if t["hierarchical"]:
+            noise = state[t["name"]]
+            if noise is None:
+                raise ValueError(f"starting state has no data-noise entry for target {t['name']!r}")
+            sigma.append(float(noise.std))
+        else:
+            sigma.append(None)
+    return dict(spaces=spaces, sigma=sigma)
+
+
+def host_dict_to_state(spec: dict, d: dict, temperature=1.0, state_cls=State, ps_cls=ParameterSpaceState,
+                       noise_cls=DataNoiseState) -> State:
+    pv = {}
+    for sp, ss in zip(spec["spaces"], d["spaces"]):
+        vals = {}
+        if sp["ndim"]:
+            vals["discretization"] = ss["sites"]
+        for p, v in zip(sp["params"], ss["values"]):
+            vals[p["name"]] = v
+        pv[sp["name"]] = ps_cls(int(ss["k"]), vals)
+    for t, sg in zip(spec["targets"], d["sigma"]):
+        if t["hierarchical"]:
+            pv[t["name"]] = noise_cls(std=sg, correlation=None)
+    return state_cls(pv, temperature=float(temperature))
+
+
+# --------------------------------------------------------------------------- #
+# the batch
+# --------------------------------------------------------------------------- #
+class ChainBatch:
+    """All chains of one inversion resident on one GPU."""
+
+    def __init__(self, spec: dict, n_chains: int, device=None, seed=None, chain_id0: int = 0,
+                 starting_states: Optional[List[State]] = None, save_dpred: bool = True):
+        import torch
+
+        from ._engine import Engine
+
+        if device is None:
+            device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+        self.spec = spec
+        self.n_chains = int(n_chains)
+        self.chain_id0 = int(chain_id0)
+        self.save_dpred = save_dpred
+        self.seed = next_seed() if seed is None else int(seed)
+        self.engine = Engine(spec, self.n_chains, device=device, seed=self.seed, chain_id0=chain_id0)
+        self.names = _compile.perturbation_names(spec)
+        self.iteration = 0
+        self.saved: List[dict] = []  # one entry per save point: host arrays + mask of chains saved
+        self._torch = torch
+        if starting_states is None:
+            self.engine.init_states()
+        else:
+            self.engine.load_states([state_to_host_dict(spec, s) for s in starting_states])
+
+    # ---- temperatures ----------------------------------------------------
+    def set_temperatures(self, temps):
+        t = self._torch.as_tensor(np.asarray(temps, dtype=np.float64))
+        self.engine.temperature.copy_(t)
+
+    def temperatures(self) -> np.ndarray:
+        return self.engine.temperature.cpu().numpy()
+
+    # ---- advancing -------------------------------------------------------
+    def advance(self, n_iterations: int, burnin_iterations: int = 0, save_every: int = 100):
+        """``BaseMarkovChain.advance_chain`` for all chains (src/bayesbay/_markov_chain.py:249-297):
+        iteration ``i`` (1-based, global) is saved iff ``i > burnin`` and ``(i - burnin) % save_every == 0``
+        and the chain's temperature is 1 (``_next_iteration`` :241-242)."""
+        done = 0
+        while done < n_iterations:
+            i_next = self.iteration + 1
+            if i_next <= burnin_iterations:
+                to_save = burnin_iterations + save_every - i_next
+            else:
+                r = (i_next - burnin_iterations) % save_every
+                to_save = 0 if r == 0 else save_every - r
+            n = min(n_iterations - done, to_save + 1)
+            self.engine.step(n)
+            self.iteration += n
+            done += n
+            if n == to_save + 1:
+                self._save()
+
+    def _save(self):
+        eng = self.engine
+        temps = eng.temperature.cpu().numpy()
+        mask = temps == 1.0
+        if not mask.any():
+            return
+        entry = dict(mask=mask, spaces=[], sigma=[], dpred=[])
+        for s in range(len(self.spec["spaces"])):
+            k, sites, vals = eng.gather_space(s)
+            entry["spaces"].append((k.cpu().numpy(), None if sites is None else sites.cpu().numpy(),
+                                    None if vals is None else vals.cpu().numpy()))
+        for t, tg in enumerate(self.spec["targets"]):
+            entry["sigma"].append(eng.sigma[t][0].cpu().numpy() if tg["hierarchical"] else None)
+            entry["dpred"].append(eng.dpred(t).cpu().numpy() if self.save_dpred else None)
+        self.saved.append(entry)
+
+    # ---- results in the reference's shapes -------------------------------
+    def saved_states_of(self, c: int, start: int = 0):
+        """``chain.saved_states`` (src/bayesbay/_markov_chain.py:115-134): ``defaultdict(list)`` keyed
+        ``"{ps}.n_dimensions"`` (trans-d only), ``"{ps}.discretization"``, ``"{ps}.{param}"``,
+        ``"{target}.std"``, ``"{target}.dpred"``."""
+        out = defaultdict(list)
+        for entry in self.saved[start:]:
+            if not entry["mask"][c]:
+                continue
+            for sp, (k, sites, vals) in zip(self.spec["spaces"], entry["spaces"]):
+                kc = int(k[c])
+                if sp["trans_d"]:
+                    out[f"{sp['name']}.n_dimensions"].append(kc)
+                if sp["ndim"] == 1:
+                    out[f"{sp['name']}.discretization"].append(sites[0, :kc, c].copy())
+                elif sp["ndim"] == 2:
+                    out[f"{sp['name']}.discretization"].append(sites[:, :kc, c].T.copy())
+                for j, p in enumerate(sp["params"]):
+                    out[f"{sp['name']}.{p['name']}"].append(vals[j, :kc, c].copy())
+            for tg, sg in zip(self.spec["targets"], entry["sigma"]):
+                if sg is not None:
+                    out[f"{tg['name']}.std"].append(float(sg[c]))
+            for tg, dp in zip(self.spec["targets"], entry["dpred"]):
+                if dp is not None:
+                    out[f"{tg['name']}.dpred"].append(dp[:, c].copy())
+        return out
+
+    def statistics(self):
+        """Per-chain statistics dictionaries in the reference's shape (``_init_statistics`` /
+        ``_save_statistics``, src/bayesbay/_markov_chain.py:106-157)."""
+        prop = self.engine.n_proposed.cpu().numpy()
+        acc = self.engine.n_accepted.cpu().numpy()
+        out = []
+        for c in range(self.n_chains):
+            n_prop = defaultdict(lambda: defaultdict(float))
+            n_acc = defaultdict(lambda: defaultdict(float))
+            for m, nm in enumerate(self.names):
+                if nm is None or prop[m, c] == 0:
+                    continue
+                outer, inner = nm
+                if inner is None:
+                    n_prop[outer] = int(prop[m, c])
+                    n_acc[outer] = int(acc[m, c])
+                else:
+                    n_prop[outer][inner] += float(prop[m, c])
+                    n_acc[outer][inner] += float(acc[m, c])
+            out.append({
+                "n_proposed_models": n_prop,
+                "n_accepted_models": n_acc,
+                "n_proposed_models_total": int(prop[:, c].sum()),
+                "n_accepted_models_total": int(acc[:, c].sum()),
+                "exceptions": defaultdict(int),
+            })
+        return out
+
+    def current_states(self, **classes) -> List[State]:
+        temps = self.temperatures()
+        states = [host_dict_to_state(self.spec, d, temps[c], **classes) for c, d in enumerate(self.engine.fetch_states())]
+        return states
+
+    def misfit_logdet_T(self):
+        """[C][3] (misfit, logdet, T) of the current states: the only data a PT swap round needs."""
+        m, ld = self.engine.misfit_logdet()
+        return self._torch.stack((m, ld, self.engine.temperature), dim=1).contiguous()
+
+
+# --------------------------------------------------------------------------- #
+# small device utilities behind the descriptor API
+# --------------------------------------------------------------------------- #
+def _cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bayesbay_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def sample_space_states(space, n: int) -> List[ParameterSpaceState]:
+    """Starting states of one parameter space drawn by the device initialisation kernel."""
+    from .parameterization import Parameterization
+
+    spec = _compile.compile_problem(Parameterization(space))
+    batch = ChainBatch(spec, n, save_dpred=False)
+    return [s[space.name] for s in batch.current_states()]
+
+
+def device_log_prior(space, ps_states: List[ParameterSpaceState]) -> List[float]:
+    """``ParameterSpace.log_prior`` through ``bbb_logprior``."""
+    torch = _cuda()
+    from . import _lib as L
+    from ._engine import _PRIOR_KIND
+
+    sp = _compile.compile_space(space)
+    P, K, Cn = len(sp["params"]), sp["kmax"], len(ps_states)
+    if P == 0:
+        return [0.0] * Cn
+    cs = L.SpaceSpec()
+    cs.n_params, cs.kmax = P, K
+    for j, p in enumerate(sp["params"]):
+        cs.prior_kind[j], cs.prior_a[j], cs.prior_b[j] = _PRIOR_KIND[p["kind"]], p["a"], p["b"]
+    vals = np.zeros((P, K, Cn))
+    k = np.zeros(Cn, np.int32)
+    for c, st in enumerate(ps_states):
+        k[c] = st.n_dimensions
+        if k[c] > K:
+            raise ValueError("state has more dimensions than n_dimensions_max")
+        for j, p in enumerate(sp["params"]):
+            vals[j, : k[c], c] = st[p["name"]]
+    dv, dk = torch.as_tensor(vals).cuda(), torch.as_tensor(k).cuda()
+    out = torch.empty(Cn, dtype=torch.float64, device="cuda")
+    lib = L.load()
+    L.check(lib.bbb_logprior(C.byref(cs), C.c_void_p(dv.data_ptr()), C.c_void_p(dk.data_ptr()), Cn,
+                             C.c_void_p(out.data_ptr()), None))
+    return [float(x) for x in out.cpu().numpy()]
+
+
+def device_interpolate_2d(samples_sites, samples_values, interp_positions, as_tensor=False):
+    """Batched ``Voronoi2D.interpolate_tessellation``: every sample is one "chain" of ``bbb_raster2d``."""
+    torch = _cuda()
+    from . import _lib as L
+
+    pts = np.ascontiguousarray(interp_positions, dtype=np.float64)
+    n = len(samples_sites)
+    K = max(int(np.asarray(s).shape[0]) for s in samples_sites)
+    sites = np.zeros((2, K, n))
+    vals = np.zeros((K, n))
+    k = np.zeros(n, np.int32)
+    for c, (s, v) in enumerate(zip(samples_sites, samples_values)):
+        s = np.asarray(s, dtype=np.float64)
+        k[c] = s.shape[0]
+        sites[:, : k[c], c] = s.T
+        vals[: k[c], c] = v
+    G = pts.shape[0]
+    ds, dk = torch.as_tensor(sites).cuda(), torch.as_tensor(k).cuda()
+    px, py = torch.as_tensor(pts[:, 0].copy()).cuda(), torch.as_tensor(pts[:, 1].copy()).cuda()
+    idx = torch.empty((G, n), dtype=torch.uint8 if K <= 256 else torch.int16, device="cuda")
+    lib = L.load()
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    L.check(lib.bbb_raster2d(p(ds), p(dk), K, n, p(px), p(py), G, p(idx), None))
+    idx = idx.long()
+    if K > 256:
+        idx = idx & 0xFFFF
+    fields = torch.gather(torch.as_tensor(vals).cuda(), 0, idx).T.contiguous()  # [n][G]
+    return fields if as_tensor else fields.cpu().numpy()
+
+
+def device_interpolate_1d(samples_sites, samples_values, interp_positions):
+    """Batched ``Voronoi1D.interpolate_tessellation(..., 'nuclei')`` through ``bbb_raster1d``."""
+    torch = _cuda()
+    from . import _lib as L
+
+    x = np.ascontiguousarray(np.atleast_1d(interp_positions), dtype=np.float64)
+    n = len(samples_sites)
+    K = max(int(np.asarray(s).size) for s in samples_sites)
+    sites = np.zeros((K, n))
+    vals = np.zeros((K, n))
+    k = np.zeros(n, np.int32)
+    for c, (s, v) in enumerate(zip(samples_sites, samples_values)):
+        k[c] = np.asarray(s).size
+        sites[: k[c], c] = s
+        vals[: k[c], c] = v
+    ds, dv, dk, dx = (torch.as_tensor(a).cuda() for a in (sites, vals, k, x))
+    field = torch.empty((x.size, n), dtype=torch.float64, device="cuda")
+    lib = L.load()
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    L.check(lib.bbb_raster1d(p(ds), p(dv), p(dk), K, n, p(dx), x.size, None, p(field), None))
+    return field.T.cpu().numpy()

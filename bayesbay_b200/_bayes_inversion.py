@@ -1,0 +1,199 @@
+"""``BayesianInversion`` facade (reference src/bayesbay/_bayes_inversion.py) on the CUDA engine.
+
+Same constructor and ``run`` / ``get_results`` signatures.  ``run`` does exactly what the reference
+does with a sampler (``_bayes_inversion.py:236-249``): ``sampler.initialize(chains)``; set
+``sampler.parallel_config``; ``self._chains = sampler.run(...)``.  The chains live on the device from
+construction on (starting states are drawn by the initialisation kernel, or taken from
+``walkers_starting_states``).
+
+Multi-GPU: under ``torchrun`` (``torch.distributed`` initialised, one rank per GPU) ``n_chains`` is the
+job-wide number of chains and each rank owns a contiguous shard; the only cross-rank traffic is the
+parallel-tempering all-gather of three doubles per chain.
+"""
+from __future__ import annotations
+
+import os
+from collections import defaultdict
+from typing import Dict, List, Union
+
+from . import _compile
+from ._batch import ChainBatch
+from ._markov_chain import BaseMarkovChain, MarkovChain
+from ._state import State
+from .likelihood import LogLikelihood
+from .parameterization import Parameterization
+from .samplers import Sampler, VanillaSampler
+
+__all__ = ["BaseBayesianInversion", "BayesianInversion"]
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover
+        return None
+    return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
+
+
+class BaseBayesianInversion:
+    """Low-level interface of the reference (``_bayes_inversion.py:22-398``), which takes arbitrary
+    Python perturbation / likelihood callables.  Those cannot run inside CUDA kernels and there is no
+    CPU fallback, so constructing it directly raises; :class:`BayesianInversion` is the supported entry
+    point and inherits ``run`` / ``get_results`` from here."""
+
+    def __init__(self, walkers_starting_states=None, perturbation_funcs=None, perturbation_weights=None,
+                 log_like_ratio_func=None, log_like_func=None, n_chains: int = 10, save_dpred: bool = True):
+        raise TypeError(
+            "BaseBayesianInversion drives user-defined Python perturbation and likelihood callables, which cannot "
+            "run on the device (no CPU fallback). Describe the problem with Parameterization + LogLikelihood and use "
+            "BayesianInversion.")
+
+    @property
+    def chains(self) -> List[BaseMarkovChain]:
+        return self._chains
+
+    def run(self, sampler: Sampler = None, n_iterations: int = 1000, burnin_iterations: int = 0, save_every: int = 100,
+            verbose: bool = True, print_every: int = 100, parallel_config: dict = None):
+        """Run the inversion (reference ``_bayes_inversion.py:198-249``).  ``parallel_config`` is kept for
+        signature compatibility; joblib keys (``n_jobs``, ``backend``) are ignored."""
+        if sampler is None:
+            sampler = VanillaSampler()
+        sampler.initialize(self.chains)
+        _parallel_config = {"n_jobs": len(self.chains), "backend": "cuda"}
+        if parallel_config is not None:
+            _parallel_config.update(parallel_config)
+        sampler.parallel_config = _parallel_config
+        self._chains = sampler.run(n_iterations=n_iterations, burnin_iterations=burnin_iterations,
+                                   save_every=save_every, verbose=verbose, print_every=print_every)
+        self._sync_chains()
+
+    def get_results(self, keys: Union[str, List[str]] = None, concatenate_chains: bool = True):
+        """Saved samples of this rank's chains (reference ``_bayes_inversion.py:251-326``)."""
+        return self.get_results_from_chains(self.chains, keys, concatenate_chains)
+
+    @staticmethod
+    def get_results_from_chains(chains, keys=None, concatenate_chains=True) -> Dict[str, list]:
+        if not isinstance(chains, list):
+            chains = [chains]
+        if not all(isinstance(c, BaseMarkovChain) for c in chains):
+            raise TypeError("`chains` should be a list of Markov chains (i.e. instances of BaseMarkovChain or MarkovChain)")
+        if chains and getattr(chains[0], "_batch_owner", None) is not None:
+            chains[0]._batch_owner._sync_chains()
+        if isinstance(keys, str):
+            keys = [keys]
+        results = defaultdict(list)
+        for chain in chains:
+            for key, saved_values in chain.saved_states.items():
+                if keys is None or key in keys:
+                    if concatenate_chains and isinstance(saved_values, list):
+                        results[key].extend(saved_values)
+                    else:
+                        results[key].append(saved_values)
+        return dict(results)
+
+
+class BayesianInversion(BaseBayesianInversion):
+    """``BayesianInversion(parameterization, log_likelihood, n_chains=10, walkers_starting_states=None,
+    save_dpred=True)`` -- reference ``_bayes_inversion.py:329-488``.
+
+    Extra keyword-only arguments (all optional): ``device`` (default ``cuda:$LOCAL_RANK``) and ``seed``
+    (Philox key; default from :func:`bayesbay_b200.seed` or OS entropy)."""
+
+    def __init__(self, parameterization: Parameterization, log_likelihood: LogLikelihood, n_chains: int = 10,
+                 walkers_starting_states: List[State] = None, save_dpred: bool = True, *, device=None, seed=None):
+        if not isinstance(log_likelihood, LogLikelihood):
+            raise TypeError("`log_likelihood` should be an instance of `bayesbay.likelihood.LogLikelihood`")
+        if walkers_starting_states is not None and n_chains != len(walkers_starting_states):
+            raise ValueError(
+                f"Length of `walkers_starting_states` ({len(walkers_starting_states)})"
+                f" does not match `n_chains` ({n_chains}).")
+        self.parameterization = parameterization
+        self.log_likelihood = log_likelihood
+        self.n_chains = n_chains
+        self.save_dpred = save_dpred
+        self.walkers_starting_states = walkers_starting_states
+        self.perturbation_funcs = parameterization.perturbation_funcs + log_likelihood.perturbation_funcs
+        self.perturbation_weights = parameterization.perturbation_weights + log_likelihood.perturbation_weights
+        self.spec = _compile.compile_problem(parameterization, log_likelihood)
+        # chain sharding over ranks (one process per GPU)
+        dist = _dist()
+        self.world_size = dist.get_world_size() if dist else 1
+        self.rank = dist.get_rank() if dist else 0
+        if n_chains % self.world_size:
+            raise ValueError(f"n_chains ({n_chains}) must be divisible by the number of ranks ({self.world_size})")
+        self.n_chains_global = n_chains
+        n_local = n_chains // self.world_size
+        self.chain_id0 = self.rank * n_local
+        if seed is None:
+            from ._batch import next_seed
+
+            seed = next_seed()
+        if dist:
+            import torch
+
+            t = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64,
+                             device=device or f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}")
+            dist.broadcast(t, src=0)
+            seed = int(t.item())
+        starts = None
+        if walkers_starting_states is not None:
+            starts = walkers_starting_states[self.chain_id0: self.chain_id0 + n_local]
+        self.batch = ChainBatch(self.spec, n_local, device=device, seed=seed, chain_id0=self.chain_id0,
+                                starting_states=starts, save_dpred=save_dpred)
+        self.batch.seed_global = seed
+        self._chains = []
+        for c in range(n_local):
+            ch = MarkovChain(id=self.chain_id0 + c, batch=self.batch, index=c, parameterization=parameterization,
+                             log_likelihood=log_likelihood, perturbation_funcs=self.perturbation_funcs,
+                             perturbation_weights=self.perturbation_weights, save_dpred=save_dpred)
+            ch._batch_owner = self
+            self._chains.append(ch)
+        self._dirty = True
+        self._n_saved_synced = 0
+        self.log_likelihood.add_targets_observer(self)
+
+    # ---- device <-> chain views -------------------------------------------
+    def _mark_dirty(self):
+        self._dirty = True
+        for ch in self._chains:
+            ch._current_state = None
+
+    def _sync_chains(self, states: bool = True):
+        """Refresh the per-chain views (statistics, saved states, current state, temperature)."""
+        if not self._dirty and (not states or self._chains[0]._current_state is not None):
+            return
+        stats = self.batch.statistics()
+        temps = self.batch.temperatures()
+        cur = self.batch.current_states() if states else None
+        start = self._n_saved_synced
+        for c, ch in enumerate(self._chains):
+            ch._statistics = stats[c]
+            ch._temperature = float(temps[c])
+            for key, vals in self.batch.saved_states_of(c, start).items():
+                ch._saved_states[key].extend(vals)
+            if cur is not None:
+                ch._current_state = cur[c]
+        self._n_saved_synced = len(self.batch.saved)
+        if states:
+            self._dirty = False
+
+    def all_gather(self, local):
+        """[C_local][3] -> [C_total][3] in global chain order (NCCL all-gather over NVLink when sharded)."""
+        dist = _dist()
+        if dist is None:
+            return local.clone()
+        import torch
+
+        out = torch.empty((local.shape[0] * self.world_size, local.shape[1]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+
+    def update_log_likelihood_targets(self, targets):
+        raise TypeError("targets cannot be added after the chains were placed on the device; build a new inversion")
+
+    def set_perturbation_funcs(self, perturbation_funcs, perturbation_weights=None):
+        raise TypeError("custom perturbation lists are not supported by the device engine")
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(parameterization={self.parameterization}, "
+                f"log_likelihood={self.log_likelihood}, n_chains={self.n_chains}, save_dpred={self.save_dpred})")

@@ -1,0 +1,178 @@
+"""Compile API objects into the flat problem description ("spec dict") the device engine runs.
+
+Duck-typed on attribute names the reference classes share with this package (``_n_dimensions_min``,
+``parameters``, ``birth_from``, ``vmin`` ...), so the same function also accepts a
+``Parameterization`` / ``LogLikelihood`` built with the unmodified reference -- that is what lets a
+batched sampler plug into the reference's own ``BayesianInversion.run(sampler=...)`` seam
+(INTEGRATION.md)."""
+from __future__ import annotations
+
+from numbers import Number
+
+import numpy as np
+
+from .exceptions import DeviceUnsupported
+
+MAX_SPACES, MAX_PARAMS, MAX_TARGETS = 4, 8, 4
+
+
+def _cls(obj):
+    return type(obj).__name__
+
+
+def _scalar(x, what):
+    if x is None or not np.isscalar(x) or not isinstance(x, Number):
+        raise DeviceUnsupported(f"{what} must be a scalar (position-dependent hyper-parameters are not on the device yet)")
+    return float(x)
+
+
+def compile_prior(p) -> dict:
+    name = _cls(p)
+    if getattr(p, "position", None) is not None:
+        raise DeviceUnsupported(f"prior {p.name!r}: position-dependent priors are not on the device yet")
+    std = _scalar(p.perturb_std, f"{p.name}.perturb_std")
+    std_birth = getattr(p, "perturb_std_birth", None)
+    std_birth = std if std_birth is None else _scalar(std_birth, f"{p.name}.perturb_std_birth")
+    if name in ("UniformPrior", "UniformParameter"):
+        kind, a, b = "uniform", _scalar(p.vmin, "vmin"), _scalar(p.vmax, "vmax")
+    elif name in ("GaussianPrior", "GaussianParameter"):
+        kind, a, b = "gaussian", _scalar(p.mean, "mean"), _scalar(p.std, "std")
+    elif name == "LaplacePrior":
+        kind, a, b = "laplace", _scalar(p.mean, "mean"), _scalar(p.scale, "scale")
+    else:
+        raise DeviceUnsupported(
+            f"prior {p.name!r} of type {name}: only Uniform/Gaussian/LaplacePrior run on the device "
+            "(user callables cannot run in a CUDA kernel and there is no CPU fallback)")
+    return dict(name=p.name, kind=kind, a=a, b=b, perturb_std=std, perturb_std_birth=std_birth)
+
+
+def compile_space(ps) -> dict:
+    name = _cls(ps)
+    params = list(ps.parameters.values())
+    for p in params:
+        if hasattr(p, "parameters"):
+            raise DeviceUnsupported(f"parameter space {ps.name!r}: nested parameter spaces are not supported on the device")
+    if len(params) > MAX_PARAMS:
+        raise DeviceUnsupported(f"parameter space {ps.name!r}: more than {MAX_PARAMS} parameters")
+    trans_d = bool(ps.trans_d)
+    kmin, kmax = int(ps._n_dimensions_min), int(ps._n_dimensions_max)
+    init_range = ps._n_dimensions_init_range
+    kinit_max = int((kmax - kmin) * init_range + kmin) if trans_d else kmin
+    kinit_max = min(max(kinit_max, kmin), kmax)
+    spec = dict(name=ps.name, trans_d=trans_d, kmin=kmin, kmax=kmax, kinit_max=kinit_max,
+                params=[compile_prior(p) for p in params])
+    if name in ("Voronoi1D", "Voronoi2D"):
+        ndim = 1 if name == "Voronoi1D" else 2
+        if getattr(ps, "polygon", None) is not None:
+            raise DeviceUnsupported("polygon domains are not supported on the device")
+        vmin = np.atleast_1d(np.asarray(ps.vmin, dtype=float))
+        vmax = np.atleast_1d(np.asarray(ps.vmax, dtype=float))
+        std = np.atleast_1d(np.asarray(ps.perturb_std, dtype=float))
+        if std.size == 1:
+            std = np.repeat(std, ndim)
+        if vmin.size != ndim or vmax.size != ndim or std.size != ndim:
+            raise ValueError(f"{ps.name}: vmin/vmax/perturb_std should have {ndim} entries")
+        if ps.birth_from not in ("prior", "neighbour"):
+            raise ValueError("birth_from should be 'prior' or 'neighbour'")
+        spec.update(kind="voronoi1d" if ndim == 1 else "voronoi2d", ndim=ndim, vmin=[float(v) for v in vmin],
+                    vmax=[float(v) for v in vmax], site_std=[float(v) for v in std], birth_from=ps.birth_from,
+                    weights=dict(birth=1 if trans_d else 0, death=1 if trans_d else 0, values=3 if params else 0, sites=1))
+    elif name == "ParameterSpace":
+        spec.update(kind="plain", ndim=0, vmin=[], vmax=[], site_std=[], birth_from="prior",
+                    weights=dict(birth=1 if trans_d else 0, death=1 if trans_d else 0, values=3 if params else 0, sites=0))
+        if not trans_d and not params:
+            raise DeviceUnsupported(f"parameter space {ps.name!r} has nothing to perturb")
+    else:
+        raise DeviceUnsupported(f"parameter space type {name} is not supported on the device")
+    return spec
+
+
+def compile_target(tgt, fwd, space_index: dict, spaces: list) -> dict:
+    if getattr(tgt, "noise_is_correlated", False):
+        raise DeviceUnsupported(f"target {tgt.name!r}: correlated noise is not on the device yet (SURVEY.md 8f rank 3)")
+    dobs = np.ascontiguousarray(tgt.dobs, dtype=np.float64).ravel()
+    cov = getattr(tgt, "covariance_mat_inv", None)
+    spec = dict(name=tgt.name, dobs=dobs, hierarchical=cov is None,
+                std_min=float(tgt.std_min), std_max=float(tgt.std_max), std_perturb_std=float(tgt.std_perturb_std),
+                cov_inv=None)
+    if cov is not None:
+        if np.isscalar(cov):
+            spec["cov_inv"] = float(cov)
+        else:
+            cov = np.asarray(cov, dtype=np.float64)
+            if cov.ndim != 1 or cov.size != dobs.size:
+                raise DeviceUnsupported(f"target {tgt.name!r}: only scalar or per-datum inverse covariances are on the device")
+            spec["cov_inv"] = cov
+    kind = getattr(fwd, "kind", None)
+    if kind not in ("ray2d", "lookup1d", "linear"):
+        raise TypeError(
+            f"forward function of target {tgt.name!r} is {fwd!r}: the device engine only runs the forward operators "
+            "of bayesbay_b200.forward (RayTomographyForward, NearestLookup1D, LinearForward). Arbitrary Python "
+            "callables cannot run in a CUDA kernel and there is no CPU fallback.")
+    if fwd.param_space_name not in space_index:
+        raise ValueError(f"forward of target {tgt.name!r} reads unknown parameter space {fwd.param_space_name!r}")
+    s = space_index[fwd.param_space_name]
+    sp = spaces[s]
+    pnames = [p["name"] for p in sp["params"]]
+    if fwd.n_data != dobs.size:
+        raise ValueError(f"forward of target {tgt.name!r} predicts {fwd.n_data} data but dobs has {dobs.size}")
+    if kind == "ray2d":
+        if sp["kind"] != "voronoi2d":
+            raise ValueError("RayTomographyForward needs a Voronoi2D parameter space")
+        spec["forward"] = dict(kind="ray2d", space=s, param=pnames.index(fwd.param_name), transform=fwd.transform,
+                               indptr=fwd.indptr, indices=fwd.indices, data=fwd.data, points=fwd.grid_points)
+    elif kind == "lookup1d":
+        if sp["kind"] != "voronoi1d":
+            raise ValueError("NearestLookup1D needs a Voronoi1D parameter space")
+        spec["forward"] = dict(kind="lookup1d", space=s, param=pnames.index(fwd.param_name), x=fwd.x)
+    else:
+        if sp["trans_d"]:
+            raise ValueError("LinearForward needs a fixed-dimension parameter space")
+        params = [pnames.index(n) for n in fwd.param_names]
+        if fwd.G.shape[1] != len(params) * sp["kmax"]:
+            raise ValueError(f"LinearForward: G has {fwd.G.shape[1]} columns, expected {len(params) * sp['kmax']}")
+        spec["forward"] = dict(kind="linear", space=s, params=params, G=fwd.G)
+    return spec
+
+
+def compile_problem(parameterization, log_likelihood=None) -> dict:
+    """``Parameterization`` (+ ``LogLikelihood``) -> spec dict.  Raises ``TypeError`` /
+    ``DeviceUnsupported`` for anything the device cannot run (there is no CPU fallback)."""
+    spaces = [compile_space(ps) for ps in parameterization.parameter_spaces.values()]
+    if len(spaces) > MAX_SPACES:
+        raise DeviceUnsupported(f"more than {MAX_SPACES} parameter spaces")
+    index = {sp["name"]: i for i, sp in enumerate(spaces)}
+    targets = []
+    if log_likelihood is not None:
+        if getattr(log_likelihood, "log_like_func", None) or getattr(log_likelihood, "log_like_ratio_func", None):
+            raise TypeError("user log-likelihood callables cannot run on the device; use targets + forward operators")
+        tg = list(log_likelihood.targets)
+        fw = list(log_likelihood.fwd_functions)
+        if len(tg) != len(fw):
+            raise ValueError("the number of targets and forward functions must be equal")
+        if len(tg) > MAX_TARGETS:
+            raise DeviceUnsupported(f"more than {MAX_TARGETS} targets")
+        for t, f in zip(tg, fw):
+            f = getattr(f, "func", f)  # the reference wraps callables in _FunctionWrapper(func, args, kwargs)
+            targets.append(compile_target(t, f, index, spaces))
+    return dict(spaces=spaces, targets=targets)
+
+
+def perturbation_names(spec: dict):
+    """Statistics keys in device move-id order: ``[(outer_name, inner_name | None)] * (4*n_spaces+1)``
+    (None where the move does not exist), following the ``__name__`` rules of perturbations/*.py."""
+    out = []
+    for sp in spec["spaces"]:
+        outer = f"ParamSpacePerturbation(param_space_name={sp['name']})"
+        pn = [f"{sp['name']}.{p['name']}" for p in sp["params"]]
+        names = {
+            "birth": f"BirthPerturbation({sp['name']})",
+            "death": f"DeathPerturbation({sp['name']})",
+            "values": f"ParamPerturbation({str(pn) if len(pn) != 1 else pn[0]})",
+            "sites": f"ParamPerturbation({sp['name']}.discretization)",
+        }
+        for kind in ("birth", "death", "values", "sites"):
+            out.append((outer, names[kind]) if sp["weights"][kind] > 0 else None)
+    hier = [t["name"] for t in spec["targets"] if t["hierarchical"]]
+    out.append((f"NoisePerturbation({str(hier) if len(hier) > 1 else hier[0]})", None) if hier else None)
+    return out

@@ -204,6 +204,11 @@ class Engine:
     def step(self, n_steps: int = 1):
         L.check(self.lib.bbb_engine_step(self._handle, int(n_steps), self._stream))
 
+    def set_annealing(self, temperature_start, cooling_rate, cooling_iterations, burnin_iterations):
+        torch.cuda.synchronize(self.device)
+        L.check(self.lib.bbb_engine_set_annealing(self._handle, float(temperature_start), float(cooling_rate),
+                                                  int(cooling_iterations), int(burnin_iterations)))
+
     def gather_space(self, s: int):
         sp = self.spec["spaces"][s]
         K, nd, P = sp["kmax"], sp["ndim"], len(sp["params"])

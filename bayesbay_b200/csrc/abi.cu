@@ -43,7 +43,7 @@ int64_t bbb_ray_tiles(int64_t n_data) { return (n_data + RAY_TILE - 1) / RAY_TIL
 
 static int validate_spec(const bbb_problem_spec *P) {
     if (P->n_spaces < 1 || P->n_spaces > BBB_MAX_SPACES) return fail(BBB_ERR_INVALID, "n_spaces out of range");
-    if (P->n_targets < 1 || P->n_targets > BBB_MAX_TARGETS) return fail(BBB_ERR_INVALID, "n_targets out of range");
+    if (P->n_targets < 0 || P->n_targets > BBB_MAX_TARGETS) return fail(BBB_ERR_INVALID, "n_targets out of range");
     for (int s = 0; s < P->n_spaces; ++s) {
         const bbb_space_spec &S = P->spaces[s];
         if (S.kind < BBB_SPACE_PLAIN || S.kind > BBB_SPACE_VORONOI2D) return fail(BBB_ERR_INVALID, "space %d: bad kind", s);
@@ -268,6 +268,20 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
         }
         CU(launch_finish(e->dev, C, st));
     }
+    return BBB_OK;
+}
+
+int bbb_engine_set_annealing(bbb_engine *e, double temperature_start, double cooling_rate, int64_t cooling_iterations,
+                             int64_t burnin_iterations) {
+    NEED_BOUND(e);
+    if (temperature_start < 0 || cooling_iterations < 0 || burnin_iterations < 0) return fail(BBB_ERR_INVALID, "negative annealing parameter");
+    e->host.anneal.enabled = temperature_start > 0 ? 1 : 0;
+    e->host.anneal.t0 = temperature_start;
+    e->host.anneal.rate = cooling_rate;
+    e->host.anneal.cooling_iterations = cooling_iterations;
+    e->host.anneal.burnin_iterations = burnin_iterations;
+    CU(cudaMemcpyAsync(&e->dev->anneal, &e->host.anneal, sizeof(Annealing), cudaMemcpyHostToDevice, 0));
+    CU(cudaStreamSynchronize(0));
     return BBB_OK;
 }
 

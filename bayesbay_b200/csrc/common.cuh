@@ -14,10 +14,26 @@ constexpr double SQRT_TWO_PI = 2.50662827463100050242;
 constexpr int RAY_TILE = 64;       // rays per SpMM block (partial-misfit granularity)
 constexpr int CHAIN_TILE = 32;     // chains per warp-lane tile
 
+// SimulatedAnnealing.on_begin_iteration (samplers/_samplers.py:402-414): temperature of iteration `it`
+struct Annealing {
+    int enabled;
+    double t0, rate;
+    long long cooling_iterations, burnin_iterations;
+};
+
 struct EngineParams {
     bbb_problem_spec spec;
     bbb_buffers buf;
+    Annealing anneal;
 };
+
+__device__ __forceinline__ double annealing_temperature(const Annealing &a, long long it) {
+    if (it < a.burnin_iterations && it < a.cooling_iterations) {
+        const double t = a.t0 * exp(-a.rate * (double)it);
+        return t > 1.0 ? t : 1.0;  // guard against rounding below 1
+    }
+    return 1.0;
+}
 
 // ---- slot-addressed views (arrays are [2][...][K][C], chain fastest) -------------------------
 __device__ __forceinline__ double &site_ref(const bbb_buffers &B, const bbb_space_spec &S, int s,

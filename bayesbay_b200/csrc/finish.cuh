@@ -101,8 +101,11 @@ __device__ __forceinline__ bool move_is_geometry(int move) {
 }
 
 // Likelihood ratio, MH decision, commit, statistics: _next_iteration (_markov_chain.py:222-243)
-__device__ inline void finish_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, Rng &rng) {
+__device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rng) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
+    if (ep.anneal.enabled) B.temperature[c] = annealing_temperature(ep.anneal, B.iteration[c]);
     const int move = B.move[c];
     const double lpr = B.log_prob_ratio[c];
     const bool noise = (move == 4 * P.n_spaces);

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_finish(const EngineParams *epp
     if (c >= ep.buf.n_chains) return;
     Rng rng;
     rng_begin(rng, ep, c, STREAM_STEP, true);
-    finish_chain(ep.spec, ep.buf, c, rng);
+    finish_chain(ep, c, rng);
     rng_end(rng, ep, c);
 }
 
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_fused_steps(const EngineParams
         Rng rng;
         rng_begin(rng, ep, c, STREAM_STEP, false);
         propose_chain(ep.spec, ep.buf, c, rng);
-        finish_chain(ep.spec, ep.buf, c, rng);
+        finish_chain(ep, c, rng);
         rng_end(rng, ep, c);
     }
 }

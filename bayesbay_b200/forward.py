@@ -1,0 +1,112 @@
+"""Device-native forward operators ("second seam").
+
+The reference's ``LogLikelihood(targets, fwd_functions)`` takes arbitrary Python callables
+``state -> d_pred`` (src/bayesbay/likelihood/_log_likelihood.py:67-78).  A Python callable cannot
+run inside a CUDA kernel and this package has no CPU fallback, so the forward functions of the
+tutorials are provided as operator *descriptors* that carry the arrays the engine uploads:
+
+* :class:`RayTomographyForward` -- ``jacobian @ (1 / vel[nearest_site(grid_points)])``
+  (docs/source/tutorials/31_sw_tomography.ipynb cell 12, tests/21_test_voronoi_2d.py:57-68);
+* :class:`NearestLookup1D` -- ``Voronoi1D.interpolate_tessellation(sites, values, x, 'nuclei')``
+  (discretization/_voronoi.py:705-732; the lookup of 42_transd_partition_mod.ipynb cell 11);
+* :class:`LinearForward` -- ``G @ m`` (02_hierarchical_polyfit.ipynb cell 12).
+
+They are listed where the reference lists forward callables.  Calling one on the host raises: the
+numpy adapters that turn a descriptor into a callable for the *unmodified reference* live in
+``oracle/reference_adapters.py`` (test infrastructure).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["ForwardOperator", "RayTomographyForward", "NearestLookup1D", "LinearForward"]
+
+
+class ForwardOperator:
+    kind = None
+
+    def __call__(self, state):
+        raise TypeError(
+            f"{type(self).__name__} is evaluated inside the CUDA engine; it has no host implementation "
+            "(see oracle/reference_adapters.py for running it inside the unmodified reference)")
+
+    @property
+    def __name__(self):
+        return type(self).__name__
+
+
+class RayTomographyForward(ForwardOperator):
+    """Straight-ray travel times through a 2-D Voronoi field.
+
+    Parameters
+    ----------
+    jacobian : scipy.sparse matrix or ``(indptr, indices, data)``
+        ray matrix, rows = rays, columns = ``grid_points`` (shared by all chains)
+    grid_points : (G, 2) array
+        query points of the nearest-site rasterisation
+    param_space_name, param_name : str
+        the Voronoi2D space and the parameter holding the cell values
+    transform : {"reciprocal", "identity"}
+        ``"reciprocal"`` multiplies the ray matrix with ``1 / value`` (velocity -> slowness)
+    """
+
+    kind = "ray2d"
+
+    def __init__(self, jacobian, grid_points, param_space_name="voronoi", param_name="vel", transform="reciprocal"):
+        if isinstance(jacobian, (tuple, list)):
+            indptr, indices, data = jacobian
+        else:
+            csr = jacobian.tocsr()
+            csr.sort_indices()
+            indptr, indices, data = csr.indptr, csr.indices, csr.data
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(data, dtype=np.float64)
+        self.grid_points = np.ascontiguousarray(grid_points, dtype=np.float64)
+        if self.grid_points.ndim != 2 or self.grid_points.shape[1] != 2:
+            raise ValueError("grid_points should have shape (G, 2)")
+        if transform not in ("reciprocal", "identity"):
+            raise ValueError("transform should be 'reciprocal' or 'identity'")
+        if self.indices.size and (self.indices.min() < 0 or self.indices.max() >= self.grid_points.shape[0]):
+            raise ValueError("jacobian column index outside grid_points")
+        if self.indptr[0] != 0 or self.indptr[-1] != self.indices.size or self.data.size != self.indices.size:
+            raise ValueError("inconsistent CSR arrays")
+        self.param_space_name = param_space_name
+        self.param_name = param_name
+        self.transform = transform
+
+    @property
+    def n_data(self):
+        return self.indptr.size - 1
+
+
+class NearestLookup1D(ForwardOperator):
+    """``d_pred[i] = values[nearest_site(x[i])]`` on a Voronoi1D space."""
+
+    kind = "lookup1d"
+
+    def __init__(self, x, param_space_name, param_name):
+        self.x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        self.param_space_name = param_space_name
+        self.param_name = param_name
+
+    @property
+    def n_data(self):
+        return self.x.size
+
+
+class LinearForward(ForwardOperator):
+    """``d_pred = G @ concatenate([state[ps][p] for p in param_names])`` on a fixed-dimension space."""
+
+    kind = "linear"
+
+    def __init__(self, G, param_space_name, param_names):
+        self.G = np.ascontiguousarray(G, dtype=np.float64)
+        if self.G.ndim != 2:
+            raise ValueError("G should be a 2-D array")
+        self.param_space_name = param_space_name
+        self.param_names = list(param_names)
+
+    @property
+    def n_data(self):
+        return self.G.shape[0]

@@ -140,7 +140,7 @@ typedef struct {
     /* optional recorded uniforms (step-replay parity); NULL selects Philox */
     const double *tape;      /* [C][tape_stride] */
     int64_t tape_stride;
-    int64_t *tape_cursor;    /* [C] */
+    int64_t *tape_cursor;    /* [C] tape position (tape mode) / draws consumed in the step (Philox mode) */
 } bbb_buffers;
 
 typedef struct bbb_engine bbb_engine;
@@ -166,6 +166,12 @@ int bbb_engine_refresh(bbb_engine *e, void *stream);
 /* Advance every chain n_steps iterations: `BaseMarkovChain.advance_chain`
  * (src/bayesbay/_markov_chain.py:249-297) for all chains at once. */
 int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream);
+/* Simulated-annealing schedule `SimulatedAnnealing.on_begin_iteration` (samplers/_samplers.py:402-414):
+ * while enabled (temperature_start > 0) every chain's temperature of iteration `it` is
+ * max(1, temperature_start * exp(-cooling_rate * it)) for it < min(cooling_iterations, burnin_iterations)
+ * and 1 afterwards.  temperature_start == 0 disables the schedule.  Synchronises the device. */
+int bbb_engine_set_annealing(bbb_engine *e, double temperature_start, double cooling_rate,
+                             int64_t cooling_iterations, int64_t burnin_iterations);
 /* Compact the CURRENT state of every chain into caller arrays (`_save_state`,
  * src/bayesbay/_markov_chain.py:115-134): k [C] int32, sites [ndim][K][C], values [P][K][C]. */
 int bbb_engine_gather_space(bbb_engine *e, int space, int32_t *k_out, double *sites_out,

@@ -1,0 +1,313 @@
+"""The reference-facing API (same names / call sequence as bayesbay) on the CUDA engine:
+result shapes, statistics dictionaries, samplers, and Monte-Carlo-level agreement with long runs of the
+unmodified reference (tests/golden/stats_*.npz)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import bayesbay_b200 as bb  # noqa: E402
+from bayesbay_b200 import synthetic  # noqa: E402
+from bayesbay_b200.forward import LinearForward, NearestLookup1D, RayTomographyForward  # noqa: E402
+from tests import problems  # noqa: E402
+
+
+def device_forward(ing):
+    if ing["kind"] == "tomography_2d":
+        return RayTomographyForward((ing["indptr"], ing["indices"], ing["data"]), ing["points"], "voronoi", "vel")
+    if ing["kind"] == "partition_1d":
+        return NearestLookup1D(ing["x"], "voronoi", "y")
+    return LinearForward(ing["G"], "my_param_space", ["m0", "m1", "m2", "m3"])
+
+
+def make_inversion(ing, n_chains, seed=0, **kw):
+    par, ll = synthetic.build_problem(ing, bb, device_forward)
+    return bb.BayesianInversion(par, ll, n_chains=n_chains, seed=seed, **kw)
+
+
+def test_results_and_statistics_shapes():
+    """Usage exactly as tests/21_test_voronoi_2d.py:115-126 / the tomography notebook."""
+    ing = problems.tomo_small()
+    inv = make_inversion(ing, 6, seed=3)
+    inv.run(sampler=None, n_iterations=300, burnin_iterations=100, save_every=50, verbose=False)
+    res = inv.get_results()
+    assert set(res) == {"voronoi.n_dimensions", "voronoi.discretization", "voronoi.vel", "d_obs.std", "d_obs.dpred"}
+    n_saved = 6 * (300 - 100) // 50
+    assert all(len(v) == n_saved for v in res.values())
+    for k, sites, vel, dp in zip(res["voronoi.n_dimensions"], res["voronoi.discretization"], res["voronoi.vel"],
+                                 res["d_obs.dpred"]):
+        assert isinstance(k, int) and sites.shape == (k, 2) and vel.shape == (k,) and dp.shape == ing["d_obs"].shape
+        assert 4 <= k <= 20 and (vel >= 2).all() and (vel <= 4).all() and (np.abs(sites) <= 1).all()
+    assert all(isinstance(s, float) and 0 <= s <= 0.01 for s in res["d_obs.std"])
+    per_chain = inv.get_results(concatenate_chains=False)
+    assert len(per_chain["d_obs.std"]) == 6 and len(per_chain["d_obs.std"][0]) == n_saved // 6
+    assert list(inv.get_results(keys="d_obs.std")) == ["d_obs.std"]
+    ch = inv.chains[0]
+    st = ch.statistics
+    assert st["n_proposed_models_total"] == 300 == ch.ith_iteration
+    outer = "ParamSpacePerturbation(param_space_name=voronoi)"
+    assert set(st["n_proposed_models"]) <= {outer, "NoisePerturbation(d_obs)"}
+    assert set(st["n_proposed_models"][outer]) <= {"BirthPerturbation(voronoi)", "DeathPerturbation(voronoi)",
+                                                   "ParamPerturbation(voronoi.vel)",
+                                                   "ParamPerturbation(voronoi.discretization)"}
+    tot = sum(st["n_proposed_models"][outer].values()) + st["n_proposed_models"].get("NoisePerturbation(d_obs)", 0)
+    assert tot == 300
+    assert 0 < st["n_accepted_models_total"] < 300
+    cs = ch.current_state
+    assert isinstance(cs, bb.State) and cs["voronoi"].n_dimensions == len(cs["voronoi"]["vel"])
+    assert isinstance(cs["d_obs"], bb.DataNoiseState) and cs.temperature == 1.0
+    ch.print_statistics()
+    # run() may be called again and continues (reference: ith_iteration = n_proposed_models_total)
+    inv.run(n_iterations=100, burnin_iterations=0, save_every=50, verbose=False)
+    assert inv.chains[0].ith_iteration == 400
+    assert len(inv.get_results()["d_obs.std"]) == n_saved + 6 * 2
+
+
+def test_save_dpred_false_and_fixed_dimension_keys():
+    inv = make_inversion(synthetic.polyfit(), 5, seed=1, save_dpred=False)
+    inv.run(n_iterations=200, burnin_iterations=0, save_every=20, verbose=False)
+    res = inv.get_results()
+    # fixed-dimension spaces do not save n_dimensions (_markov_chain.py:118-127)
+    assert set(res) == {"my_param_space.m0", "my_param_space.m1", "my_param_space.m2", "my_param_space.m3", "my_data.std"}
+    assert len(res["my_data.std"]) == 5 * 10 and res["my_param_space.m0"][0].shape == (1,)
+    name = "ParamPerturbation(['my_param_space.m0', 'my_param_space.m1', 'my_param_space.m2', 'my_param_space.m3'])"
+    st = inv.chains[2].statistics
+    assert name in st["n_proposed_models"]["ParamSpacePerturbation(param_space_name=my_param_space)"]
+
+
+def test_walkers_starting_states_round_trip():
+    ing = problems.tomo_small()
+    inv0 = make_inversion(ing, 4, seed=11)
+    states = [ch.current_state for ch in inv0.chains]
+    par, ll = synthetic.build_problem(ing, bb, device_forward)
+    inv = bb.BayesianInversion(par, ll, n_chains=4, walkers_starting_states=states, seed=5)
+    for a, b in zip(states, (ch.current_state for ch in inv.chains)):
+        assert a["voronoi"] == b["voronoi"] and a["d_obs"].std == b["d_obs"].std
+    m0, _ = inv0.batch.engine.misfit_logdet()
+    m1, _ = inv.batch.engine.misfit_logdet()
+    assert torch.equal(m0, m1)
+    with pytest.raises(ValueError):
+        bb.BayesianInversion(par, ll, n_chains=3, walkers_starting_states=states)
+    bad = states[0].copy()
+    bad["voronoi"].param_values["vel"] = bad["voronoi"]["vel"][:-1]
+    with pytest.raises(ValueError):
+        bb.BayesianInversion(par, ll, n_chains=4, walkers_starting_states=[bad] + states[1:])
+
+
+def _rates(proposed, accepted):
+    """mean acceptance rate over chains and its standard error (between-chain spread)."""
+    r = accepted / np.maximum(proposed, 1)
+    return r.mean(0), r.std(0, ddof=1) / math.sqrt(r.shape[0])
+
+
+STAT_CASES = {
+    # name: (ingredients, iterations, burnin) -- same lengths as tests/golden/make_golden.py
+    "partition_1d": (synthetic.partition_1d, 60000, 10000),
+    "polyfit": (synthetic.polyfit, 40000, 5000),
+    "polyfit_nb": (lambda: synthetic.polyfit(all_gaussian=False), 40000, 5000),
+    "tomo_small": (problems.tomo_small, 30000, 5000),
+}
+
+
+@pytest.mark.parametrize("name", list(STAT_CASES))
+def test_full_run_statistics_match_reference(name, golden_dir):
+    """Acceptance rate per move type, mean dimension, mean noise level and posterior-mean predicted data of
+    long runs agree with the unmodified reference within Monte-Carlo error (5 sigma of the between-chain
+    standard errors; the reference fixture has 8 chains, the device runs 64)."""
+    g = np.load(os.path.join(golden_dir, f"stats_{name}.npz"))
+    mk, n_it, burnin = STAT_CASES[name]
+    ing = mk()
+    inv = make_inversion(ing, 64, seed=20240 + len(name))
+    inv.run(n_iterations=n_it, burnin_iterations=burnin, save_every=10, verbose=False)
+    ref_rate, ref_se = _rates(g["proposed"], g["accepted"])
+    names = [str(n) for n in g["names"]]
+    prop = np.zeros((64, len(names)))
+    acc = np.zeros((64, len(names)))
+    for c, ch in enumerate(inv.chains):
+        flat_p, flat_a = {}, {}
+        for key, v in ch.statistics["n_proposed_models"].items():
+            if isinstance(v, dict):
+                for k2 in v:
+                    flat_p[k2], flat_a[k2] = v[k2], ch.statistics["n_accepted_models"][key][k2]
+            else:
+                flat_p[key], flat_a[key] = v, ch.statistics["n_accepted_models"][key]
+        assert set(flat_p) == set(names)
+        prop[c] = [flat_p[n] for n in names]
+        acc[c] = [flat_a[n] for n in names]
+    # proposal shares follow the weights (1:1:3:1 inside the space, 6:1 or 3:1 against the noise move)
+    share_ref = g["proposed"].sum(0) / g["proposed"].sum()
+    share = prop.sum(0) / prop.sum()
+    np.testing.assert_allclose(share, share_ref, atol=0.004)
+    rate, se = _rates(prop, acc)
+    z = np.abs(rate - ref_rate) / np.sqrt(se ** 2 + ref_se ** 2 + 1e-8)
+    assert (z < 5).all(), dict(zip(names, zip(rate.round(4), ref_rate.round(4), z.round(1))))
+    res = inv.get_results(concatenate_chains=False)
+    tname = ing["target"]["name"]
+
+    def chain_means(values, n_chains):
+        return np.array([np.mean(v) for v in values]), n_chains
+
+    sig = np.array([np.mean(v) for v in res[f"{tname}.std"]])
+    ref_sig = g["sigma"].reshape(8, -1).mean(1)
+    z = abs(sig.mean() - ref_sig.mean()) / math.sqrt(sig.var(ddof=1) / 64 + ref_sig.var(ddof=1) / 8)
+    assert z < 5, ("sigma", sig.mean(), ref_sig.mean(), z)
+    if "k" in g.files:
+        ps = "voronoi"
+        kk = np.array([np.mean(v) for v in res[f"{ps}.n_dimensions"]])
+        ref_k = g["k"].reshape(8, -1).mean(1)
+        z = abs(kk.mean() - ref_k.mean()) / math.sqrt(kk.var(ddof=1) / 64 + ref_k.var(ddof=1) / 8)
+        assert z < 5, ("k", kk.mean(), ref_k.mean(), z)
+    dp = np.mean([np.mean(v, axis=0) for v in res[f"{tname}.dpred"]], axis=0)
+    scale = np.abs(g["dpred_mean"]).max()
+    assert np.abs(dp - g["dpred_mean"]).max() < 0.05 * scale
+
+
+def test_published_acceptance_rates_partition_model():
+    """42_transd_partition_mod.ipynb cell 15 reports 29.47 % overall acceptance with
+    birth/death 6.7 %, noise 22.95 %, site 14.7 %, value 51.75 % (different noise realisation: loose bounds)."""
+    inv = make_inversion(synthetic.partition_1d(), 128, seed=4242)
+    inv.run(n_iterations=50000, burnin_iterations=0, save_every=100000, verbose=False)
+    p = np.zeros(5)
+    a = np.zeros(5)
+    for ch in inv.chains:
+        st = ch.statistics
+        inner_p = st["n_proposed_models"]["ParamSpacePerturbation(param_space_name=voronoi)"]
+        inner_a = st["n_accepted_models"]["ParamSpacePerturbation(param_space_name=voronoi)"]
+        for i, key in enumerate(("BirthPerturbation(voronoi)", "DeathPerturbation(voronoi)",
+                                 "ParamPerturbation(voronoi.y)", "ParamPerturbation(voronoi.discretization)")):
+            p[i] += inner_p[key]
+            a[i] += inner_a[key]
+        p[4] += st["n_proposed_models"]["NoisePerturbation(d_obs)"]
+        a[4] += st["n_accepted_models"]["NoisePerturbation(d_obs)"]
+    rate = a / p
+    overall = a.sum() / p.sum()
+    assert abs(overall - 0.2947) < 0.03
+    np.testing.assert_allclose(rate, [0.0671, 0.0670, 0.5175, 0.1470, 0.2295], atol=0.035)
+    np.testing.assert_allclose(p / p.sum(), [1 / 7, 1 / 7, 3 / 7, 1 / 7, 1 / 7], atol=0.003)
+
+
+def test_parallel_tempering_sampler(golden_dir):
+    ing = synthetic.polyfit()
+    inv = make_inversion(ing, 6, seed=8)
+    sampler = bb.samplers.ParallelTempering(temperature_max=5, chains_with_unit_temperature=0.4, swap_every=50)
+    inv.run(sampler=sampler, n_iterations=400, burnin_iterations=100, save_every=10, verbose=False)
+    ladder = np.load(os.path.join(golden_dir, "pt_swap.npz"))["ladder"]
+    temps = np.array([ch.temperature for ch in inv.chains])
+    np.testing.assert_allclose(np.sort(temps), np.sort(ladder), rtol=1e-15)  # temperatures are permuted, never changed
+    assert all(ch.ith_iteration == 400 for ch in inv.chains)
+    assert sampler._round == 400 // 50 + 1  # quirk Q3: one extra zero-length window + swap round
+    # quirk Q3: effective burn-in is min(burnin, swap_every); only T == 1 chains save (quirk Q6)
+    n_saved = [len(ch.saved_states["my_data.std"]) for ch in inv.chains]
+    assert max(n_saved) <= (400 - 50) // 10 and sum(n_saved) > 0
+    with pytest.raises(ValueError):
+        inv1 = make_inversion(ing, 1, seed=8)
+        inv1.run(sampler=bb.samplers.ParallelTempering(), n_iterations=10, verbose=False)
+    # explicit ladder extension
+    inv2 = make_inversion(ing, 8, seed=9)
+    lad = np.repeat(np.geomspace(1, 5, 4), 2)
+    inv2.run(sampler=bb.samplers.ParallelTempering(swap_every=20, temperatures=lad), n_iterations=100, verbose=False)
+    np.testing.assert_allclose(np.sort([ch.temperature for ch in inv2.chains]), lad, rtol=1e-15)
+
+
+def test_tempered_chains_accept_more():
+    ing = synthetic.partition_1d()
+    par, ll = synthetic.build_problem(ing, bb, device_forward)
+    inv = bb.BayesianInversion(par, ll, n_chains=64, seed=2)
+    inv.batch.set_temperatures(np.repeat([1.0, 20.0], 32))
+    inv.run(n_iterations=5000, verbose=False)
+    acc = np.array([ch.statistics["n_accepted_models_total"] for ch in inv.chains])
+    assert acc[32:].mean() > 1.3 * acc[:32].mean()
+
+
+def test_simulated_annealing_schedule():
+    ing = synthetic.polyfit()
+    inv = make_inversion(ing, 4, seed=1)
+    sa = bb.samplers.SimulatedAnnealing(temperature_start=10, cooling_fraction=0.8)
+    sa.initialize(inv.chains)
+    assert all(ch.temperature == 10 for ch in inv.chains)
+    burnin = 100
+    sa.burnin_iterations = burnin
+    cooling_iterations = int(round(0.8 * burnin))
+    rate = math.log(10) / cooling_iterations
+    eng = inv.batch.engine
+    eng.set_annealing(10, rate, cooling_iterations, burnin)
+    for it in (0, 1, 37, 79, 80, 99, 100, 150):
+        eng.iteration.fill_(it)
+        eng.step(1)
+        want = max(1.0, 10 * math.exp(-rate * it)) if it < cooling_iterations else 1.0
+        np.testing.assert_allclose(eng.temperature.cpu().numpy(), want, rtol=1e-14)
+    inv = make_inversion(ing, 4, seed=1)
+    inv.run(sampler=bb.samplers.SimulatedAnnealing(10, 0.8), n_iterations=300, burnin_iterations=100, save_every=10,
+            verbose=False)
+    assert all(ch.temperature == 1.0 for ch in inv.chains)
+    assert len(inv.get_results()["my_data.std"]) == 4 * 20
+
+
+def test_prior_recovery_without_data():
+    """The reference's tests/00-15 run chains on a flat likelihood and eyeball that the prior is recovered;
+    here: no targets at all, then chi-square on the dimension histogram and moments of sites / values."""
+    y = bb.prior.GaussianPrior("y", mean=3.0, std=2.0, perturb_std=1.0)
+    u = bb.prior.UniformPrior("u", vmin=-1.0, vmax=5.0, perturb_std=1.5)
+    vor = bb.discretization.Voronoi1D("v", vmin=0, vmax=10, perturb_std=2.0, n_dimensions_min=1, n_dimensions_max=8,
+                                      parameters=[y, u], birth_from="prior")
+    spec = bb._compile.compile_problem(bb.parameterization.Parameterization(vor))
+    from bayesbay_b200._batch import ChainBatch
+
+    batch = ChainBatch(spec, 512, seed=77, save_dpred=False)
+    batch.advance(4000, burnin_iterations=1000, save_every=50)
+    ks, sites, ys, us = [], [], [], []
+    for c in range(512):
+        s = batch.saved_states_of(c)
+        ks += s["v.n_dimensions"]
+        sites += [x for a in s["v.discretization"] for x in a]
+        ys += [x for a in s["v.y"] for x in a]
+        us += [x for a in s["v.u"] for x in a]
+    hist = np.bincount(ks, minlength=9)[1:]
+    expected = len(ks) / 8
+    assert np.abs(hist - expected).max() < 0.08 * expected, hist  # uniform prior on k in [1, 8]
+    sites, ys, us = map(np.array, (sites, ys, us))
+    assert abs(sites.mean() - 5.0) < 0.1 and abs(sites.std() - 10 / math.sqrt(12)) < 0.1
+    assert abs(ys.mean() - 3.0) < 0.06 and abs(ys.std() - 2.0) < 0.06
+    assert abs(us.mean() - 2.0) < 0.06 and abs(us.std() - 6 / math.sqrt(12)) < 0.06 and us.min() >= -1 and us.max() <= 5
+    # sites stay sorted
+    s0 = batch.saved_states_of(0)["v.discretization"]
+    assert all((np.diff(a) >= 0).all() for a in s0)
+
+
+def test_host_api_device_utilities(golden_dir):
+    kg = np.load(os.path.join(golden_dir, "kernels.npz"))
+    # tests/20_test_param_space_log_prior.py:16-30 through the CUDA log-prior kernel
+    uni = bb.prior.UniformPrior("uniform", vmin=-1, vmax=1, perturb_std=0.1)
+    gau = bb.prior.GaussianPrior("gaussian", mean=0, std=1, perturb_std=0.1)
+    ps = bb.parameterization.ParameterSpace("ps", n_dimensions=1, parameters=[uni, gau])
+    st = bb.ParameterSpaceState(1, {"uniform": np.array([0.0]), "gaussian": np.array([0.0])})
+    assert ps.log_prior(st) == pytest.approx(math.log(1 / 2) + math.log(1 / math.sqrt(2 * math.pi)), rel=1e-15)
+    # quickstart values, tests/22_log_like_func.py:24-31
+    m = bb.prior.UniformPrior("m", 5, 15, 0.4)
+    assert [math.exp(m.log_prior(v)) for v in (5, 10, 20)] == pytest.approx([0.1, 0.1, 0.0])
+    # Voronoi2D.interpolate_tessellation == KD-tree of the reference
+    pts = kg["r2_points"]
+    for i in range(len(kg["r2_ks"])):
+        sites, vals = kg[f"r2_sites_{i}"], kg[f"r2_vals_{i}"]
+        out = bb.discretization.Voronoi2D.interpolate_tessellation(sites, vals, pts)
+        assert np.array_equal(out, vals[kg[f"r2_idx_{i}"]])
+    stats = bb.discretization.Voronoi2D.get_tessellation_statistics(
+        [kg[f"r2_sites_{i}"] for i in range(5)], [kg[f"r2_vals_{i}"] for i in range(5)], pts)
+    fields = np.stack([kg[f"r2_vals_{i}"][kg[f"r2_idx_{i}"]] for i in range(5)])
+    np.testing.assert_allclose(stats["mean"], fields.mean(0), rtol=1e-13)
+    np.testing.assert_allclose(stats["median"], np.median(fields, 0), rtol=1e-13)
+    np.testing.assert_allclose(stats["std"], fields.std(0), rtol=1e-12)
+    np.testing.assert_allclose(stats["percentiles"], np.percentile(fields, (10, 90), axis=0), rtol=1e-12)
+    # Voronoi1D
+    out = bb.discretization.Voronoi1D.interpolate_tessellation(kg["r1_sites_2"], kg["r1_vals_2"], kg["r1_x"])
+    assert np.array_equal(out, kg["r1_field_2"])
+    # initialize() draws valid states on the device
+    vor = bb.discretization.Voronoi2D("voronoi", vmin=[-1, -1], vmax=[1, 1], perturb_std=0.05, n_dimensions_min=10,
+                                      n_dimensions_max=200, parameters=[bb.prior.UniformPrior("vel", 2, 4, 0.1)])
+    s = bb.parameterization.Parameterization(vor).initialize()
+    k = s["voronoi"].n_dimensions
+    assert 10 <= k <= int((200 - 10) * 0.3 + 10) and s["voronoi"]["discretization"].shape == (k, 2)
