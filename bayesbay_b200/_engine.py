@@ -204,6 +204,10 @@ class Engine:
     def step(self, n_steps: int = 1):
         L.check(self.lib.bbb_engine_step(self._handle, int(n_steps), self._stream))
 
+    def stage(self, stage: int):
+        """One stage of one step (0 propose, 1 raster, 2 ray forward + misfit, 3 accept)."""
+        L.check(self.lib.bbb_engine_stage(self._handle, int(stage), self._stream))
+
     def set_annealing(self, temperature_start, cooling_rate, cooling_iterations, burnin_iterations):
         torch.cuda.synchronize(self.device)
         L.check(self.lib.bbb_engine_set_annealing(self._handle, float(temperature_start), float(cooling_rate),

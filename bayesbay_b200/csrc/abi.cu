@@ -271,6 +271,28 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
     return BBB_OK;
 }
 
+int bbb_engine_stage(bbb_engine *e, int stage, void *stream) {
+    NEED_BOUND(e);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bbb_problem_spec &P = e->host.spec;
+    const long long C = e->host.buf.n_chains;
+    if (!e->has_ray) return fail(BBB_ERR_UNSUPPORTED, "staged stepping needs a ray target (other problems run the fused kernel)");
+    switch (stage) {
+        case 0: CU(launch_propose(e->dev, C, st)); break;
+        case 1:
+            for (int t = 0; t < P.n_targets; ++t)
+                if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) CU(run_raster(e, t, true, st));
+            break;
+        case 2:
+            for (int t = 0; t < P.n_targets; ++t)
+                if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) CU(run_spmm(e, t, true, nullptr, true, st));
+            break;
+        case 3: CU(launch_finish(e->dev, C, st)); break;
+        default: return fail(BBB_ERR_INVALID, "stage must be 0..3");
+    }
+    return BBB_OK;
+}
+
 int bbb_engine_set_annealing(bbb_engine *e, double temperature_start, double cooling_rate, int64_t cooling_iterations,
                              int64_t burnin_iterations) {
     NEED_BOUND(e);

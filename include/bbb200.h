@@ -166,6 +166,10 @@ int bbb_engine_refresh(bbb_engine *e, void *stream);
 /* Advance every chain n_steps iterations: `BaseMarkovChain.advance_chain`
  * (src/bayesbay/_markov_chain.py:249-297) for all chains at once. */
 int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream);
+/* One stage of one step, for per-kernel timing and profiling: 0 proposal, 1 rasterisation of the
+ * proposed geometry, 2 ray forward + misfit, 3 likelihood ratio / accept / commit.  Calling stages
+ * 0,1,2,3 in order is exactly one iteration of bbb_engine_step (ray-tomography problems only). */
+int bbb_engine_stage(bbb_engine *e, int stage, void *stream);
 /* Simulated-annealing schedule `SimulatedAnnealing.on_begin_iteration` (samplers/_samplers.py:402-414):
  * while enabled (temperature_start > 0) every chain's temperature of iteration `it` is
  * max(1, temperature_start * exp(-cooling_rate * it)) for it < min(cooling_iterations, burnin_iterations)

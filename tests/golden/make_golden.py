@@ -512,6 +512,8 @@ ps_name = list(par.parameter_spaces)[0]
 if ps_name + '.n_dimensions' in res:
     out['k'] = np.array(res[ps_name + '.n_dimensions'])
 out['dpred_mean'] = np.mean(res[tname + '.dpred'], axis=0)
+per_chain = inv.get_results(concatenate_chains=False)
+out['dpred_mean_chain'] = np.array([np.mean(v, axis=0) for v in per_chain[tname + '.dpred']])
 for pname in par.parameter_spaces[ps_name].parameters:
     vals = res[ps_name + '.' + pname]
     out['mean_' + pname] = np.array([np.mean(v) for v in vals])

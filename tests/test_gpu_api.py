@@ -148,9 +148,6 @@ def test_full_run_statistics_match_reference(name, golden_dir):
     res = inv.get_results(concatenate_chains=False)
     tname = ing["target"]["name"]
 
-    def chain_means(values, n_chains):
-        return np.array([np.mean(v) for v in values]), n_chains
-
     sig = np.array([np.mean(v) for v in res[f"{tname}.std"]])
     ref_sig = g["sigma"].reshape(8, -1).mean(1)
     z = abs(sig.mean() - ref_sig.mean()) / math.sqrt(sig.var(ddof=1) / 64 + ref_sig.var(ddof=1) / 8)
@@ -161,9 +158,12 @@ def test_full_run_statistics_match_reference(name, golden_dir):
         ref_k = g["k"].reshape(8, -1).mean(1)
         z = abs(kk.mean() - ref_k.mean()) / math.sqrt(kk.var(ddof=1) / 64 + ref_k.var(ddof=1) / 8)
         assert z < 5, ("k", kk.mean(), ref_k.mean(), z)
-    dp = np.mean([np.mean(v, axis=0) for v in res[f"{tname}.dpred"]], axis=0)
-    scale = np.abs(g["dpred_mean"]).max()
-    assert np.abs(dp - g["dpred_mean"]).max() < 0.05 * scale
+    # posterior-mean predicted data, per datum, against the between-chain standard errors of both sides
+    dpc = np.array([np.mean(v, axis=0) for v in res[f"{tname}.dpred"]])  # [64][R]
+    ref_dpc = g["dpred_mean_chain"]  # [8][R]
+    se2 = dpc.var(0, ddof=1) / 64 + ref_dpc.var(0, ddof=1) / 8
+    z = np.abs(dpc.mean(0) - ref_dpc.mean(0)) / np.sqrt(se2 + 1e-300)
+    assert z.max() < 6, ("dpred", z.max(), int(z.argmax()))
 
 
 def test_published_acceptance_rates_partition_model():
