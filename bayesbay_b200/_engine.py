@@ -170,6 +170,8 @@ class Engine:
         self.iteration = z((Cn,), i64)
         self.move = z((Cn,), i32)
         self.edit = z((2, Cn), i32)
+        self.edit_site = z((2, Cn), f64)
+        self.edit_vals = z((L.MAX_PARAMS, Cn), f64)
         self.log_prob_ratio = z((Cn,), f64)
         self.log_like_ratio = z((Cn,), f64)
         self.accepted = z((Cn,), i32)
@@ -178,6 +180,7 @@ class Engine:
         self.draw_cursor = z((Cn,), i64)
         b.temperature, b.iteration = _ptr(self.temperature), _ptr(self.iteration)
         b.move, b.edit = _ptr(self.move), _ptr(self.edit)
+        b.edit_site, b.edit_vals = _ptr(self.edit_site), _ptr(self.edit_vals)
         b.log_prob_ratio, b.log_like_ratio, b.accepted = _ptr(self.log_prob_ratio), _ptr(self.log_like_ratio), _ptr(self.accepted)
         b.n_proposed, b.n_accepted = _ptr(self.n_proposed), _ptr(self.n_accepted)
         b.tape_cursor = _ptr(self.draw_cursor)

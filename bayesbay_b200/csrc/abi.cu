@@ -2,6 +2,7 @@
 // keeps a device copy of (spec, buffers) and enqueues kernels on the caller's stream.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -33,6 +34,7 @@ struct bbb_engine {
     int device;
     bool bound;
     bool has_ray;
+    bool brute_force;  // BBB_BRUTE_FORCE_RASTER=1: re-rasterise every proposal from scratch (reference behaviour)
 };
 
 extern "C" {
@@ -118,6 +120,10 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
     e->device = device;
     e->bound = false;
     e->has_ray = false;
+    {
+        const char *bf = getenv("BBB_BRUTE_FORCE_RASTER");
+        e->brute_force = bf != nullptr && bf[0] == '1';
+    }
     for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
     int err = (int)cudaMalloc(&e->dev, sizeof(EngineParams));
     if (err != 0) {
@@ -143,7 +149,7 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
         if (P.targets[t].fwd_kind == BBB_FWD_RAY2D && (!b->cell_idx[t] || !b->idx_sel[t] || !b->partial[t]))
             return fail(BBB_ERR_SHAPE, "target %d: cell_idx/idx_sel/partial buffer missing", t);
     }
-    if (!b->temperature || !b->iteration || !b->move || !b->edit || !b->log_prob_ratio || !b->log_like_ratio ||
+    if (!b->temperature || !b->iteration || !b->move || !b->edit || !b->edit_site || !b->edit_vals || !b->log_prob_ratio || !b->log_like_ratio ||
         !b->accepted || !b->n_proposed || !b->n_accepted || !b->tape_cursor)
         return fail(BBB_ERR_SHAPE, "a per-chain scalar buffer is missing");
     if (b->tape && b->tape_stride < 1) return fail(BBB_ERR_SHAPE, "tape_stride < 1");
@@ -178,6 +184,8 @@ static int run_raster(bbb_engine *e, int t, bool proposal, cudaStream_t st) {
     a.slot_xor = proposal ? 1 : 0;
     a.move = proposal ? B.move : nullptr;
     a.lpr = B.log_prob_ratio;
+    a.edit = B.edit;
+    a.edit_site = B.edit_site;
     a.n_spaces = P.n_spaces;
     a.space = T.space;
     a.px = T.points_x;
@@ -186,7 +194,16 @@ static int run_raster(bbb_engine *e, int t, bool proposal, cudaStream_t st) {
     a.idx = B.cell_idx[t];
     a.idx_bytes = idx_bytes_of(P, t);
     a.points_per_block = raster_points_per_block(a.G, a.C);
-    return launch_raster2d(a, st);
+    return (proposal && !e->brute_force) ? launch_raster2d_inc(a, st) : launch_raster2d(a, st);
+}
+
+// proposal + parallel write of the proposed slots
+static int run_propose(bbb_engine *e, cudaStream_t st) {
+    const bbb_problem_spec &P = e->host.spec;
+    const long long C = e->host.buf.n_chains;
+    int rc = launch_propose(e->dev, C, st);
+    for (int s = 0; s < P.n_spaces && rc == 0; ++s) rc = launch_apply_edit(e->dev, C, s, P.spaces[s].kmax, st);
+    return rc;
 }
 
 static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool write_partial, cudaStream_t st) {
@@ -260,7 +277,7 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
         return BBB_OK;
     }
     for (int64_t it = 0; it < n_steps; ++it) {
-        CU(launch_propose(e->dev, C, st));
+        CU(run_propose(e, st));
         for (int t = 0; t < P.n_targets; ++t) {
             if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
             CU(run_raster(e, t, true, st));
@@ -278,7 +295,7 @@ int bbb_engine_stage(bbb_engine *e, int stage, void *stream) {
     const long long C = e->host.buf.n_chains;
     if (!e->has_ray) return fail(BBB_ERR_UNSUPPORTED, "staged stepping needs a ray target (other problems run the fused kernel)");
     switch (stage) {
-        case 0: CU(launch_propose(e->dev, C, st)); break;
+        case 0: CU(run_propose(e, st)); break;
         case 1:
             for (int t = 0; t < P.n_targets; ++t)
                 if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) CU(run_raster(e, t, true, st));

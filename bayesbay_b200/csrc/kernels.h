@@ -17,6 +17,8 @@ struct RasterArgs {
     int slot_xor;             // 1: proposed slots, 0: current slots
     const int32_t *move;      // [C] or nullptr
     const double *lpr;        // [C]
+    const int32_t *edit;      // [2][C] (rm, ins)            -- incremental kernel only
+    const double *edit_site;  // [2][C] inserted site        -- incremental kernel only
     int n_spaces, space;
     const double *px, *py;    // [G]
     int G;
@@ -50,6 +52,8 @@ struct SpmmArgs {
 
 int raster_points_per_block(int G, long long C);
 int launch_raster2d(const RasterArgs &a, cudaStream_t stream);
+int launch_raster2d_inc(const RasterArgs &a, cudaStream_t stream);
+int launch_apply_edit(const EngineParams *dev_params, long long C, int space, int kmax, cudaStream_t stream);
 int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream);
 
 // step_kernels.cu

@@ -58,7 +58,8 @@ __device__ inline int nearest_2d(const bbb_buffers &B, const bbb_space_spec &S, 
     return bi;  // index among the remaining cells
 }
 
-__device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, Rng &rng) {
+__device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, Rng &rng,
+                                     bool apply_now) {
     // ---- outer choice: _markov_chain.py:208-210 ------------------------------------------------
     double w[BBB_MAX_SPACES + 1];
     int n_outer = 0;
@@ -217,24 +218,33 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         }
     }
 
-    // ---- write the proposed slot: one lock-step loop for every move kind -----------------------
-    if (e.write) {
-        const int k_new = k - (e.rm >= 0 ? 1 : 0) + (e.ins >= 0 ? 1 : 0);
+    // ---- write the proposed slot ------------------------------------------------------------------
+    // The edit (rm, ins, new cell) is published for k_apply_edit, which writes the proposed slot with one
+    // thread per (cell, chain); the fused small-problem kernel applies it here, one lock-step loop for
+    // every move kind.
+    for (int d = 0; d < S.ndim; ++d) B.edit_site[(long long)d * B.n_chains + c] = e.site[d];
+    for (int p = 0; p < S.n_params; ++p) B.edit_vals[(long long)p * B.n_chains + c] = e.vals[p];
+    const int k_new = e.write ? k - (e.rm >= 0 ? 1 : 0) + (e.ins >= 0 ? 1 : 0) : k;
+    k_ref(B, s, prop, c) = k_new;
+    if (e.write && apply_now) {
+        const int ndim = S.ndim, n_params = S.n_params;
+        const long long C = B.n_chains, KC = (long long)S.kmax * C;
+        const double *__restrict__ s_cur = B.sites[s] + (long long)cur * ndim * KC + c;
+        double *__restrict__ s_new = B.sites[s] + (long long)prop * ndim * KC + c;
+        const double *__restrict__ v_cur = B.values[s] + (long long)cur * n_params * KC + c;
+        double *__restrict__ v_new = B.values[s] + (long long)prop * n_params * KC + c;
         int src = 0;
         for (int jo = 0; jo < k_new; ++jo) {
             if (jo == e.ins) {
-                for (int d = 0; d < S.ndim; ++d) site_ref(B, S, s, prop, d, jo, c) = e.site[d];
-                for (int p = 0; p < S.n_params; ++p) value_ref(B, S, s, prop, p, jo, c) = e.vals[p];
+                for (int d = 0; d < ndim; ++d) s_new[d * KC + (long long)jo * C] = e.site[d];
+                for (int p = 0; p < n_params; ++p) v_new[p * KC + (long long)jo * C] = e.vals[p];
             } else {
                 if (src == e.rm) ++src;
-                for (int d = 0; d < S.ndim; ++d)
-                    site_ref(B, S, s, prop, d, jo, c) = site_ref(B, S, s, cur, d, src, c);
-                for (int p = 0; p < S.n_params; ++p)
-                    value_ref(B, S, s, prop, p, jo, c) = value_ref(B, S, s, cur, p, src, c);
+                for (int d = 0; d < ndim; ++d) s_new[d * KC + (long long)jo * C] = s_cur[d * KC + (long long)src * C];
+                for (int p = 0; p < n_params; ++p) v_new[p * KC + (long long)jo * C] = v_cur[p * KC + (long long)src * C];
                 ++src;
             }
         }
-        k_ref(B, s, prop, c) = k_new;
     }
     B.move[c] = 4 * s + inner;
     B.edit[c] = e.rm;

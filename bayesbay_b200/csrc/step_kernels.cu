@@ -30,8 +30,41 @@ __global__ void __launch_bounds__(STEP_THREADS) k_propose(const EngineParams *ep
     if (c >= ep.buf.n_chains) return;
     Rng rng;
     rng_begin(rng, ep, c, STREAM_STEP, false);
-    propose_chain(ep.spec, ep.buf, c, rng);
+    propose_chain(ep.spec, ep.buf, c, rng, false);
     rng_end(rng, ep, c);
+}
+
+// Writes the proposed slot of space `s` from the published edit scripts: one thread per
+// (output cell jo = blockIdx.y, chain), fully coalesced -- the O(K) part of every proposal.
+__global__ void k_apply_edit(const EngineParams *epp, int s) {
+    const EngineParams &ep = *epp;
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int mv = B.move[c];
+    if (mv == 4 * ep.spec.n_spaces || (mv >> 2) != s) return;
+    const int rm = B.edit[c], ins = B.edit[C + c];
+    if (rm < 0 && ins < 0) return;  // birth at kmax / death at kmin: nothing proposed
+    const bbb_space_spec &S = ep.spec.spaces[s];
+    const int cur = B.sel[s][c], prop = cur ^ 1;
+    const int jo = blockIdx.y;
+    if (jo >= B.k[s][(long long)prop * C + c]) return;
+    const int ndim = S.ndim, n_params = S.n_params;
+    const long long KC = (long long)S.kmax * C;
+    double *sites = B.sites[s];
+    double *vals = B.values[s];
+    if (jo == ins) {
+        for (int d = 0; d < ndim; ++d) sites[((long long)prop * ndim + d) * KC + (long long)jo * C + c] = B.edit_site[d * C + c];
+        for (int p = 0; p < n_params; ++p) vals[((long long)prop * n_params + p) * KC + (long long)jo * C + c] = B.edit_vals[p * C + c];
+    } else {
+        const int jp = jo - ((ins >= 0 && jo > ins) ? 1 : 0);
+        const int src = jp + ((rm >= 0 && jp >= rm) ? 1 : 0);
+        for (int d = 0; d < ndim; ++d)
+            sites[((long long)prop * ndim + d) * KC + (long long)jo * C + c] = sites[((long long)cur * ndim + d) * KC + (long long)src * C + c];
+        for (int p = 0; p < n_params; ++p)
+            vals[((long long)prop * n_params + p) * KC + (long long)jo * C + c] = vals[((long long)cur * n_params + p) * KC + (long long)src * C + c];
+    }
 }
 
 __global__ void __launch_bounds__(STEP_THREADS) k_finish(const EngineParams *epp) {
@@ -54,7 +87,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_fused_steps(const EngineParams
     for (long long it = 0; it < n_steps; ++it) {
         Rng rng;
         rng_begin(rng, ep, c, STREAM_STEP, false);
-        propose_chain(ep.spec, ep.buf, c, rng);
+        propose_chain(ep.spec, ep.buf, c, rng, true);
         finish_chain(ep, c, rng);
         rng_end(rng, ep, c);
     }
@@ -309,6 +342,11 @@ static inline int blocks_for(long long C, int threads) { return (int)((C + threa
 
 int launch_propose(const EngineParams *p, long long C, cudaStream_t st) {
     k_propose<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_apply_edit(const EngineParams *p, long long C, int space, int kmax, cudaStream_t st) {
+    dim3 grid(blocks_for(C, 128), kmax);
+    k_apply_edit<<<grid, 128, 0, st>>>(p, space);
     return (int)cudaGetLastError();
 }
 int launch_finish(const EngineParams *p, long long C, cudaStream_t st) {

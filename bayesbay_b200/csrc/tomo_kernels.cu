@@ -77,6 +77,126 @@ k_raster2d(RasterArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// F1, change-local: a proposal edits ONE cell (remove `rm` and/or insert at `ins`), so the nearest
+// site of a grid point only has to be re-derived from its current owner `o`:
+//   * o != rm: the owner survives (renumbered by the edit); if a cell was inserted, the new owner is
+//     the closer of (owner, inserted cell), the lower index on an exact tie -- 2 distance evaluations;
+//   * o == rm: the owner was removed or moved -> full scan of the proposed sites for this point.
+// This is exactly argmin over the proposed sites with the lowest-index tie rule (removing a
+// non-owner cannot change an argmin and the renumbering preserves index order), so the indices are
+// bit-identical to the brute-force kernel; cost ~ (2 + fraction_rescanned * k) evaluations per point
+// instead of k.  Reads the current index slot, writes the proposed one (every point: no copy needed
+// on accept, the slot bit is flipped).
+// ------------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(RASTER_WARPS * 32)
+k_raster2d_inc(RasterArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * CHAIN_TILE + lane;
+    const bool in_range = c < a.C;
+    bool active = false;
+    int cur = 0, icur = 0, rm = -1, ins = -1;
+    double nx = 0.0, ny = 0.0;
+    if (in_range) {
+        const int mv = a.move[c];
+        active = !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space && (mv & 3) != BBB_MOVE_VALUES;
+        cur = a.sel[c];
+        icur = a.idx_sel[c];
+        if (active) {
+            rm = a.edit[c];
+            ins = a.edit[a.C + c];
+            nx = a.edit_site[c];
+            ny = a.edit_site[a.C + c];
+        }
+    }
+    if (!__syncthreads_or(active ? 1 : 0)) return;
+    const long long cc = in_range ? c : 0;
+    const int k_new = active ? a.k[(long long)(cur ^ 1) * a.C + c] : 0;
+    const double *sx = a.sites + ((long long)(cur ^ 1) * 2 + 0) * a.K * a.C + cc;
+    const double *sy = a.sites + ((long long)(cur ^ 1) * 2 + 1) * a.K * a.C + cc;
+    const IdxT *in = reinterpret_cast<const IdxT *>(a.idx) + (long long)icur * a.G * a.C + cc;
+    IdxT *out = reinterpret_cast<IdxT *>(a.idx) + (long long)(icur ^ 1) * a.G * a.C + cc;
+
+    constexpr int PPL = RASTER_POINTS_PER_LANE;
+    const int g_begin = blockIdx.y * a.points_per_block;
+    const int g_end = min(a.G, g_begin + a.points_per_block);
+    for (int g0 = g_begin + warp * PPL; g0 < g_end; g0 += RASTER_WARPS * PPL) {
+        double gx[PPL], gy[PPL];
+        int m[PPL];
+        bool scan[PPL];
+        bool any_scan = false;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            const int g = min(g0 + q, a.G - 1);
+            gx[q] = a.px[g];
+            gy[q] = a.py[g];
+            const int o = active ? (int)in[(long long)g * a.C] : 0;
+            scan[q] = active && rm >= 0 && o == rm;
+            int mm = o - ((rm >= 0 && o > rm) ? 1 : 0);
+            mm += (ins >= 0 && mm >= ins) ? 1 : 0;
+            m[q] = mm;
+            any_scan |= scan[q];
+        }
+        if (active && ins >= 0) {
+            double ox[PPL], oy[PPL];
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                const int mm = scan[q] ? 0 : m[q];
+                ox[q] = sx[(long long)mm * a.C];
+                oy[q] = sy[(long long)mm * a.C];
+            }
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                const double dx = ox[q] - gx[q], dy = oy[q] - gy[q];
+                const double d_own = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                const double ex = nx - gx[q], ey = ny - gy[q];
+                const double d_new = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+                if (!scan[q] && (d_new < d_own || (d_new == d_own && ins < m[q]))) m[q] = ins;
+            }
+        }
+        if (__any_sync(0xffffffffu, any_scan)) {
+            const int kk = any_scan ? k_new : 0;
+            int kmax = kk;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+            double best[PPL];
+            int bi[PPL];
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) { best[q] = INFINITY; bi[q] = 0; }
+            for (int j = 0; j < kmax; ++j) {
+                if (j < kk) {
+                    const double x = sx[(long long)j * a.C];
+                    const double y = sy[(long long)j * a.C];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        const double dx = x - gx[q], dy = y - gy[q];
+                        const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        if (d < best[q]) { best[q] = d; bi[q] = j; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PPL; ++q)
+                if (scan[q]) m[q] = bi[q];
+        }
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < PPL; ++q)
+                if (g0 + q < g_end) out[(long long)(g0 + q) * a.C] = (IdxT)m[q];
+        }
+    }
+}
+
+int launch_raster2d_inc(const RasterArgs &a, cudaStream_t stream) {
+    const int chain_tiles = (int)((a.C + CHAIN_TILE - 1) / CHAIN_TILE);
+    dim3 grid(chain_tiles, (a.G + a.points_per_block - 1) / a.points_per_block);
+    if (a.idx_bytes == 1) k_raster2d_inc<uint8_t><<<grid, RASTER_WARPS * 32, 0, stream>>>(a);
+    else k_raster2d_inc<uint16_t><<<grid, RASTER_WARPS * 32, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
 int launch_raster2d(const RasterArgs &a, cudaStream_t stream) {
     const int chain_tiles = (int)((a.C + CHAIN_TILE - 1) / CHAIN_TILE);
     // enough blocks for >= ~4 waves of 148 SMs, each block at least 64 points
@@ -151,13 +271,27 @@ k_ray_spmm(SpmmArgs a) {
         const int j0 = a.indptr[r];
         const int j1 = a.indptr[r + 1];
         double acc = 0.0;
-        if (active) {
-            for (int jj = j0; jj < j1; ++jj) {
-                const int col = a.indices[jj];
-                const double v = a.data[jj];
-                const int cell = (int)idx[(long long)col * a.C];
-                acc += v * table[cell * 32 + lane];
+        // a chunk of 32 CSR entries is loaded once by the warp (coalesced) and broadcast by shuffles; the
+        // index gathers of 8 entries are issued back to back so ~8 L2 round trips overlap per warp
+        for (int jb = j0; jb < j1; jb += 32) {
+            const int jj = jb + lane;
+            const int my_col = (jj < j1) ? a.indices[jj] : 0;
+            const double my_val = (jj < j1) ? a.data[jj] : 0.0;
+            const int n = min(32, j1 - jb);
+            for (int q0 = 0; q0 < n; q0 += 8) {
+                int cell[8];
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int col = __shfl_sync(0xffffffffu, my_col, q0 + u);
+                    v[u] = __shfl_sync(0xffffffffu, my_val, q0 + u);
+                    cell[u] = active ? (int)idx[(long long)col * a.C] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u] * table[cell[u] * 32 + lane];
             }
+        }
+        if (active) {
             if (a.dpred != nullptr) a.dpred[(long long)r * a.C + c] = acc;
             const double res = acc - a.dobs[r];
             const double w = (a.w != nullptr) ? a.w[r] : 1.0;

@@ -131,6 +131,8 @@ typedef struct {
     /* last proposal / decision (inputs of the accept stage, outputs for step-replay parity) */
     int32_t *move;           /* [C] move id */
     int32_t *edit;           /* [2][C] (remove index or -1, insert index or -1) */
+    double *edit_site;       /* [2][C] site of the inserted cell */
+    double *edit_vals;       /* [BBB_MAX_PARAMS][C] values of the inserted cell */
     double *log_prob_ratio;  /* [C] */
     double *log_like_ratio;  /* [C] */
     int32_t *accepted;       /* [C] */

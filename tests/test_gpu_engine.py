@@ -178,3 +178,35 @@ def test_pt_swap_golden_and_oracle(golden_dir):
         t_out, n_acc = pt_swap(gathered, 99, 3, id0, nl)
         assert np.array_equal(t_out.cpu().numpy(), np.array(ref)[id0: id0 + nl]), n
         assert int(n_acc.item()) == n_ref
+
+
+def test_incremental_raster_equals_brute_force_at_scale():
+    """Size-independent property at a BASELINE-like size: after many accepted births/deaths/moves the resident
+    nearest-site index (maintained change-locally) is bit-identical to a from-scratch rasterisation of the
+    current sites, and the cached misfit equals a fresh forward evaluation."""
+    import ctypes as C
+
+    from bayesbay_b200 import _lib as L
+    from bayesbay_b200 import synthetic
+
+    ing = synthetic.tomography_2d(nx=64, ny=48, n_sources_per_side=6, n_receivers=20, kmin=3, kmax=300)
+    spec = problems.spec_from_ingredients(ing)
+    eng = _engine(spec, 200, seed=31)  # K = 300 -> uint16 index path, 200 chains -> ragged last chain tile
+    eng.init_states()
+    for _ in range(4):
+        eng.step(150)
+        k, sites, _ = eng.gather_space(0)
+        G = ing["points"].shape[0]
+        ref = torch.zeros((G, 200), dtype=torch.int16, device="cuda")
+        px = torch.as_tensor(ing["points"][:, 0].copy()).cuda()
+        py = torch.as_tensor(ing["points"][:, 1].copy()).cuda()
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        L.check(L.load().bbb_raster2d(p(sites), p(k), 300, 200, p(px), p(py), G, p(ref), None))
+        assert torch.equal(eng.current_cell_idx(0), ref)
+        m0, _ = eng.misfit_logdet()
+        eng.refresh()
+        m1, _ = eng.misfit_logdet()
+        np.testing.assert_allclose(m0.cpu().numpy(), m1.cpu().numpy(), rtol=1e-12)
+    assert eng.n_accepted.sum().item() > 0.2 * eng.n_proposed.sum().item()
+    kk = eng.gather_space(0)[0].cpu().numpy()
+    assert kk.min() >= 3 and kk.max() <= 300 and kk.std() > 0
