@@ -221,111 +221,177 @@ int raster_points_per_block(int G, long long C) {
 
 // ------------------------------------------------------------------------------------------------
 // F2: d_pred[r][c] = sum_j data[j] * f(value[cell_idx[indices[j]][c]][c]);  phi[c] = sum_r w_r res^2.
-// Block = 32 chains (lanes) x RAY_TILE rays (8 warps take rays round-robin).  The 32 chains'
-// (transformed) cell values are staged once per block in shared memory as table[j][lane]
-// (conflict-free: a lane only ever touches its own bank pair), so per non-zero a warp issues one
-// coalesced 32 B / 64 B index gather, one LDS and one DFMA; the CSR entry is a warp-uniform load.
-// The per-block misfit is written to partial[tile][c] and summed in tile order by the accept
-// stage, which keeps the result bit-reproducible run to run (no atomics).
+//
+// Block = 32*CPL chains x RAY_TILE rays.  Each lane owns CPL consecutive chains, so the nearest-site
+// indices of its chains at one grid point are ONE 32-bit word (4 x uint8 or 2 x uint16): per CSR
+// non-zero a warp issues one coalesced 128 B gather per index slot (the current and the proposed
+// slot, merged per chain with a byte permute), CPL conflict-free LDS from the per-block table of
+// (reciprocal) cell values table[cell][q][lane], and CPL DFMAs.  The CSR entries are loaded 32 at a
+// time (coalesced) and broadcast by shuffles, which is amortised over 32*CPL chains; eight entries'
+// gathers are issued back to back to overlap their L2 round trips.
+// The per-block misfit goes to partial[tile][c] and is summed in tile order by the accept stage:
+// bit-reproducible run to run (no atomics).  d_pred is only written on request.
 // ------------------------------------------------------------------------------------------------
-constexpr int SPMM_WARPS = 8;
+constexpr int SPMM_WARPS = 16;
 
-template <typename IdxT>
+template <typename IdxT, int CPL>
 __global__ void __launch_bounds__(SPMM_WARPS * 32)
 k_ray_spmm(SpmmArgs a) {
-    extern __shared__ double table[];  // [K_block][32]
-    __shared__ double red[SPMM_WARPS][32];
+    extern __shared__ double table[];  // [K_block][CPL][32], reused as the cross-warp reduction scratch
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const long long c = (long long)blockIdx.x * CHAIN_TILE + lane;
-    const bool in_range = c < a.C;
-    bool active = in_range;
-    int vslot = 0, islot = 0;
-    if (in_range) {
-        bool geom = false;
-        if (a.move != nullptr) {
-            const int mv = a.move[c];
-            active = !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space;
-            geom = (mv & 3) != BBB_MOVE_VALUES;
+    const long long c0 = (long long)blockIdx.x * (32 * CPL) + (long long)lane * CPL;
+    bool active[CPL];
+    int vslot[CPL], islot[CPL], k[CPL];
+    bool any_active = false;
+    int kmax = 0;
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+        const long long c = c0 + q;
+        active[q] = c < a.C;
+        vslot[q] = 0;
+        islot[q] = 0;
+        if (c < a.C) {
+            bool geom = false;
+            if (a.move != nullptr) {
+                const int mv = a.move[c];
+                active[q] = !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space;
+                geom = (mv & 3) != BBB_MOVE_VALUES;
+            }
+            if (a.sel != nullptr) vslot[q] = a.sel[c] ^ a.slot_xor;
+            if (a.idx_sel != nullptr) islot[q] = a.idx_sel[c] ^ ((a.move != nullptr && geom) ? 1 : 0);
         }
-        if (a.sel != nullptr) vslot = a.sel[c] ^ a.slot_xor;
-        if (a.idx_sel != nullptr) islot = a.idx_sel[c] ^ ((a.move != nullptr) ? (geom ? 1 : 0) : 0);
+        k[q] = active[q] ? a.k[(long long)vslot[q] * a.C + c] : 0;
+        any_active |= active[q];
+        kmax = max(kmax, k[q]);
     }
-    if (!__syncthreads_or(active ? 1 : 0)) return;
-    const int k = active ? a.k[(long long)vslot * a.C + c] : 0;
-    int kmax = k;
+    if (!__syncthreads_or(any_active ? 1 : 0)) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-    const double *vals = a.values + ((long long)vslot * a.n_params + a.param) * a.K * a.C + (in_range ? c : 0);
-    for (int j = warp; j < kmax; j += SPMM_WARPS) {
-        double v = (j < k) ? vals[(long long)j * a.C] : 1.0;
-        if (a.transform == BBB_TRANSFORM_RECIPROCAL) v = 1.0 / v;
-        table[j * 32 + lane] = v;
+    // stage the (transformed) cell values of this block's chains
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+        const long long c = min(c0 + q, a.C - 1);
+        const double *vals = a.values + ((long long)vslot[q] * a.n_params + a.param) * a.K * a.C + c;
+        for (int j = warp; j < kmax; j += SPMM_WARPS) {
+            double v = (j < k[q]) ? vals[(long long)j * a.C] : 1.0;
+            if (a.transform == BBB_TRANSFORM_RECIPROCAL) v = 1.0 / v;
+            table[(j * CPL + q) * 32 + lane] = v;
+        }
     }
     __syncthreads();
-    const IdxT *idx = reinterpret_cast<const IdxT *>(a.idx) + (long long)islot * a.G * a.C + (in_range ? c : 0);
+
+    const long long slot_stride = (long long)a.G * a.C;
+    const bool lane_ok = c0 + CPL - 1 < a.C;  // C is a multiple of CPL (checked by the launcher)
+    const IdxT *idx0 = reinterpret_cast<const IdxT *>(a.idx) + (lane_ok ? c0 : 0);
+    unsigned selector = 0;  // byte-permute selector merging the two slots' words per chain
+    if (CPL * sizeof(IdxT) == 4) {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+#pragma unroll
+            for (int b = 0; b < (int)sizeof(IdxT); ++b) {
+                const int byte = q * (int)sizeof(IdxT) + b;
+                selector |= (unsigned)(byte + 4 * islot[q]) << (4 * byte);
+            }
+    }
+    const double *tab = table + lane;
+
     const int r_begin = blockIdx.y * RAY_TILE;
     const int r_end = min(a.R, r_begin + RAY_TILE);
-    double ssq = 0.0;
+    double ssq[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) ssq[q] = 0.0;
     for (int r = r_begin + warp; r < r_end; r += SPMM_WARPS) {
         const int j0 = a.indptr[r];
         const int j1 = a.indptr[r + 1];
-        double acc = 0.0;
-        // a chunk of 32 CSR entries is loaded once by the warp (coalesced) and broadcast by shuffles; the
-        // index gathers of 8 entries are issued back to back so ~8 L2 round trips overlap per warp
+        double acc[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) acc[q] = 0.0;
         for (int jb = j0; jb < j1; jb += 32) {
             const int jj = jb + lane;
             const int my_col = (jj < j1) ? a.indices[jj] : 0;
             const double my_val = (jj < j1) ? a.data[jj] : 0.0;
             const int n = min(32, j1 - jb);
-            for (int q0 = 0; q0 < n; q0 += 8) {
-                int cell[8];
+            for (int u0 = 0; u0 < n; u0 += 8) {
+                unsigned w[8];
                 double v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int col = __shfl_sync(0xffffffffu, my_col, q0 + u);
-                    v[u] = __shfl_sync(0xffffffffu, my_val, q0 + u);
-                    cell[u] = active ? (int)idx[(long long)col * a.C] : 0;
+                    const long long col = __shfl_sync(0xffffffffu, my_col, u0 + u);
+                    v[u] = __shfl_sync(0xffffffffu, my_val, u0 + u);
+                    const IdxT *p = idx0 + col * a.C;
+                    if (CPL * sizeof(IdxT) == 4) {
+                        const unsigned w0 = lane_ok ? *reinterpret_cast<const unsigned *>(p) : 0u;
+                        const unsigned w1 = lane_ok ? *reinterpret_cast<const unsigned *>(p + slot_stride) : 0u;
+                        w[u] = __byte_perm(w0, w1, selector);
+                    } else {
+                        w[u] = lane_ok ? (unsigned)p[(long long)islot[0] * slot_stride] : 0u;
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc += v[u] * table[cell[u] * 32 + lane];
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const unsigned cell = (CPL == 1) ? w[u] : ((w[u] >> (8 * (int)sizeof(IdxT) * q)) & ((1u << (8 * sizeof(IdxT))) - 1u));
+                        acc[q] += v[u] * tab[(cell * CPL + q) * 32];
+                    }
+                }
             }
         }
-        if (active) {
-            if (a.dpred != nullptr) a.dpred[(long long)r * a.C + c] = acc;
-            const double res = acc - a.dobs[r];
-            const double w = (a.w != nullptr) ? a.w[r] : 1.0;
-            ssq += w * (res * res);
+        const double dob = a.dobs[r];
+        const double wr = (a.w != nullptr) ? a.w[r] : 1.0;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            if (active[q]) {
+                if (a.dpred != nullptr) a.dpred[(long long)r * a.C + c0 + q] = acc[q];
+                const double res = acc[q] - dob;
+                ssq[q] += wr * (res * res);
+            }
         }
     }
-    red[warp][lane] = ssq;
-    __syncthreads();
-    if (warp == 0 && active && a.partial != nullptr) {
-        double tot = 0.0;
+    __syncthreads();  // the table is dead: reuse it as red[warp][q][lane]
 #pragma unroll
-        for (int w = 0; w < SPMM_WARPS; ++w) tot += red[w][lane];
-        a.partial[(long long)blockIdx.y * a.C + c] = tot;
+    for (int q = 0; q < CPL; ++q) table[(warp * CPL + q) * 32 + lane] = ssq[q];
+    __syncthreads();
+    if (warp == 0 && a.partial != nullptr) {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            if (!active[q]) continue;
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < SPMM_WARPS; ++w) tot += table[(w * CPL + q) * 32 + lane];
+            a.partial[(long long)blockIdx.y * a.C + c0 + q] = tot;
+        }
     }
 }
 
-int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream) {
-    const int chain_tiles = (int)((a.C + CHAIN_TILE - 1) / CHAIN_TILE);
+template <typename IdxT, int CPL>
+static int launch_spmm_variant(const SpmmArgs &a, cudaStream_t stream) {
+    const int chain_tiles = (int)((a.C + 32 * CPL - 1) / (32 * CPL));
     const int ray_tiles = (a.R + RAY_TILE - 1) / RAY_TILE;
     dim3 grid(chain_tiles, ray_tiles);
-    const size_t smem = (size_t)a.K * 32 * sizeof(double);
-    cudaError_t err = cudaSuccess;
-    if (a.idx_bytes == 1) {
-        if (smem > 48 * 1024)
-            err = cudaFuncSetAttribute(k_ray_spmm<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = (size_t)a.K * CPL * 32 * sizeof(double);
+    const size_t red = (size_t)SPMM_WARPS * CPL * 32 * sizeof(double);
+    if (smem < red) smem = red;
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(k_ray_spmm<IdxT, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        k_ray_spmm<uint8_t><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
-    } else {
-        if (smem > 48 * 1024)
-            err = cudaFuncSetAttribute(k_ray_spmm<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        k_ray_spmm<uint16_t><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
     }
+    k_ray_spmm<IdxT, CPL><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
     return (int)cudaGetLastError();
+}
+
+int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream) {
+    const size_t budget = 200 * 1024;  // dynamic shared memory available to the value table
+    const size_t row = 32 * sizeof(double);
+    if (a.idx_bytes == 1) {
+        if (a.C % 4 == 0 && (size_t)a.K * 4 * row <= budget) return launch_spmm_variant<uint8_t, 4>(a, stream);
+        if ((size_t)a.K * row <= 227 * 1024 - 1024) return launch_spmm_variant<uint8_t, 1>(a, stream);
+    } else {
+        if (a.C % 2 == 0 && (size_t)a.K * 2 * row <= budget) return launch_spmm_variant<uint16_t, 2>(a, stream);
+        if ((size_t)a.K * row <= 227 * 1024 - 1024) return launch_spmm_variant<uint16_t, 1>(a, stream);
+    }
+    return (int)cudaErrorInvalidConfiguration;  // n_dimensions_max too large for the shared-memory value table
 }
 
 }  // namespace bbb
