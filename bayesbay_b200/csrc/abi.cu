@@ -34,6 +34,7 @@ struct bbb_engine {
     int device;
     bool bound;
     bool has_ray;
+    int n_sm;
     bool brute_force;  // BBB_BRUTE_FORCE_RASTER=1: re-rasterise every proposal from scratch (reference behaviour)
 };
 
@@ -125,6 +126,8 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
         e->brute_force = bf != nullptr && bf[0] == '1';
     }
     for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
+    e->n_sm = 148;
+    cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
     int err = (int)cudaMalloc(&e->dev, sizeof(EngineParams));
     if (err != 0) {
         delete e;
@@ -154,6 +157,14 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
         return fail(BBB_ERR_SHAPE, "a per-chain scalar buffer is missing");
     if (b->tape && b->tape_stride < 1) return fail(BBB_ERR_SHAPE, "tape_stride < 1");
     e->host.buf = *b;
+    for (int t = 0; t < P.n_targets; ++t) {
+        e->host.n_partial[t] = 0;
+        if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
+        const int K = P.spaces[P.targets[t].space].kmax;
+        e->host.n_partial[t] = spmm_ray_groups(P.targets[t].n_data, b->n_chains, K, K <= 256 ? 1 : 2, e->n_sm);
+        if (e->host.n_partial[t] == 0)
+            return fail(BBB_ERR_UNSUPPORTED, "target %d: n_dimensions_max %d is too large for the ray kernel's shared-memory value table", t, K);
+    }
     CU(cudaSetDevice(e->device));
     CU(cudaMemcpy(e->dev, &e->host, sizeof(EngineParams), cudaMemcpyHostToDevice));
     e->bound = true;
@@ -237,6 +248,7 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
     a.space = T.space;
     a.dpred = dpred;
     a.partial = write_partial ? B.partial[t] : nullptr;
+    a.n_groups = e->host.n_partial[t];
     return launch_ray_spmm(a, st);
 }
 
@@ -418,8 +430,13 @@ int bbb_ray_forward(const void *idx, const double *values, const int32_t *k, int
     a.w = w;
     a.dpred = dpred_out;
     a.partial = phi_out ? partial_scratch : nullptr;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    a.n_groups = spmm_ray_groups(R, C, K, a.idx_bytes, n_sm);
+    if (a.n_groups == 0) return fail(BBB_ERR_UNSUPPORTED, "K = %d is too large for the ray kernel's shared-memory value table", K);
     CU(launch_ray_spmm(a, (cudaStream_t)stream));
-    if (phi_out) CU(launch_phi_from_partial(partial_scratch, (R + RAY_TILE - 1) / RAY_TILE, C, phi_out, (cudaStream_t)stream));
+    if (phi_out) CU(launch_phi_from_partial(partial_scratch, a.n_groups, C, phi_out, (cudaStream_t)stream));
     return BBB_OK;
 }
 

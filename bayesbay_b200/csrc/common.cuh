@@ -25,6 +25,7 @@ struct EngineParams {
     bbb_problem_spec spec;
     bbb_buffers buf;
     Annealing anneal;
+    int n_partial[BBB_MAX_TARGETS];  // rows of partial[t] the ray kernel writes (its ray groups)
 };
 
 __device__ __forceinline__ double annealing_temperature(const Annealing &a, long long it) {

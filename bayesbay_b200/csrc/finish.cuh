@@ -67,8 +67,9 @@ __device__ inline double small_target_phi(const bbb_problem_spec &P, const bbb_b
     return phi;
 }
 
-__device__ __forceinline__ double ray_partial_sum(const bbb_buffers &B, const bbb_target_spec &T, int t, long long c) {
-    const int n_tiles = (T.n_data + RAY_TILE - 1) / RAY_TILE;
+__device__ __forceinline__ double ray_partial_sum(const EngineParams &ep, int t, long long c) {
+    const bbb_buffers &B = ep.buf;
+    const int n_tiles = ep.n_partial[t];
     double phi = 0.0;
     for (int i = 0; i < n_tiles; ++i) phi += B.partial[t][(long long)i * B.n_chains + c];
     return phi;
@@ -119,7 +120,7 @@ __device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rn
             const double phi_old = B.phi[t][c];
             double phi_new = phi_old;
             if (!noise && T.space == s) {
-                if (T.fwd_kind == BBB_FWD_RAY2D) phi_new = ray_partial_sum(B, T, t, c);
+                if (T.fwd_kind == BBB_FWD_RAY2D) phi_new = ray_partial_sum(ep, t, c);
                 else phi_new = small_target_phi(P, B, t, B.sel[s][c] ^ 1, c, nullptr, nullptr);
                 B.phi[t][C + c] = phi_new;
             }

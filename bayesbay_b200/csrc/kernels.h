@@ -47,7 +47,8 @@ struct SpmmArgs {
     const double *lpr;
     int n_spaces, space;
     double *dpred;            // [R][C] or nullptr
-    double *partial;          // [ray_tiles][C] or nullptr
+    double *partial;          // [n_groups][C] or nullptr
+    int n_groups;             // ray groups = gridDim.y (spmm_ray_groups)
 };
 
 int raster_points_per_block(int G, long long C);
@@ -55,6 +56,7 @@ int launch_raster2d(const RasterArgs &a, cudaStream_t stream);
 int launch_raster2d_inc(const RasterArgs &a, cudaStream_t stream);
 int launch_apply_edit(const EngineParams *dev_params, long long C, int space, int kmax, cudaStream_t stream);
 int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream);
+int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);
 
 // step_kernels.cu
 int launch_propose(const EngineParams *dev_params, long long C, cudaStream_t stream);

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_refresh_finish(const EnginePar
     for (int t = 0; t < P.n_targets; ++t) {
         const bbb_target_spec &T = P.targets[t];
         double phi;
-        if (T.fwd_kind == BBB_FWD_RAY2D) phi = ray_partial_sum(B, T, t, c);
+        if (T.fwd_kind == BBB_FWD_RAY2D) phi = ray_partial_sum(ep, t, c);
         else phi = small_target_phi(P, B, t, B.sel[T.space][c], c, nullptr, nullptr);
         B.phi[t][c] = phi;
         B.phi[t][B.n_chains + c] = phi;

@@ -222,22 +222,32 @@ int raster_points_per_block(int G, long long C) {
 // ------------------------------------------------------------------------------------------------
 // F2: d_pred[r][c] = sum_j data[j] * f(value[cell_idx[indices[j]][c]][c]);  phi[c] = sum_r w_r res^2.
 //
-// Block = 32*CPL chains x RAY_TILE rays.  Each lane owns CPL consecutive chains, so the nearest-site
-// indices of its chains at one grid point are ONE 32-bit word (4 x uint8 or 2 x uint16): per CSR
-// non-zero a warp issues one coalesced 128 B gather per index slot (the current and the proposed
-// slot, merged per chain with a byte permute), CPL conflict-free LDS from the per-block table of
-// (reciprocal) cell values table[cell][q][lane], and CPL DFMAs.  The CSR entries are loaded 32 at a
-// time (coalesced) and broadcast by shuffles, which is amortised over 32*CPL chains; eight entries'
-// gathers are issued back to back to overlap their L2 round trips.
-// The per-block misfit goes to partial[tile][c] and is summed in tile order by the accept stage:
+// Persistent blocks: grid = chain tiles x ray groups, sized to one block per SM.  A block owns 32*CPL
+// chains (each lane CPL consecutive chains) and stages their (reciprocal) cell values ONCE in shared
+// memory as CPL planes table_q[cell][lane] (256 B rows, bank-conflict free), then its 16 warps walk
+// the block's rays.  Per CSR non-zero a warp issues
+//   * 1 + 2 shuffles (column pre-multiplied by C, fp64 weight) -- the CSR entries were loaded 32 at a
+//     time, coalesced, and the broadcast is amortised over 32*CPL chains,
+//   * 2 coalesced 128 B gathers: the 32-bit word holding the nearest-site indices of the lane's CPL
+//     chains (4 x uint8 or 2 x uint16) in the current and in the proposed index slot, merged per chain
+//     with one byte permute,
+//   * per chain: one byte permute that BUILDS the shared-memory offset (cell * 256 + lane * 8), one
+//     LDS with the plane as immediate offset, one DFMA.
+// Eight entries are in flight per warp to overlap the L2 round trips of the gathers.
+// The block's misfit goes to partial[group][c] and is summed in group order by the accept stage:
 // bit-reproducible run to run (no atomics).  d_pred is only written on request.
 // ------------------------------------------------------------------------------------------------
 constexpr int SPMM_WARPS = 16;
+constexpr int SPMM_CHUNK = SPMM_WARPS;  // rays handed out per scheduling chunk (one per warp)
+
+template <int CPL> struct SpmmPlane { static constexpr int ROWS = (CPL == 4) ? 224 : (CPL == 2 ? 448 : 896); };
 
 template <typename IdxT, int CPL>
-__global__ void __launch_bounds__(SPMM_WARPS * 32)
+__global__ void __launch_bounds__(SPMM_WARPS * 32, 1)
 k_ray_spmm(SpmmArgs a) {
-    extern __shared__ double table[];  // [K_block][CPL][32], reused as the cross-warp reduction scratch
+    extern __shared__ __align__(256) unsigned char smem_raw[];  // CPL planes of ROWS x 32 doubles
+    constexpr int PLANE_BYTES = SpmmPlane<CPL>::ROWS * 256;
+    constexpr int IB = (int)sizeof(IdxT);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long c0 = (long long)blockIdx.x * (32 * CPL) + (long long)lane * CPL;
@@ -268,40 +278,51 @@ k_ray_spmm(SpmmArgs a) {
     if (!__syncthreads_or(any_active ? 1 : 0)) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-    // stage the (transformed) cell values of this block's chains
+    // stage the (transformed) cell values of this block's chains: plane q, row = cell, column = lane
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
         const long long c = min(c0 + q, a.C - 1);
         const double *vals = a.values + ((long long)vslot[q] * a.n_params + a.param) * a.K * a.C + c;
+        double *plane = reinterpret_cast<double *>(smem_raw + q * PLANE_BYTES);
         for (int j = warp; j < kmax; j += SPMM_WARPS) {
             double v = (j < k[q]) ? vals[(long long)j * a.C] : 1.0;
             if (a.transform == BBB_TRANSFORM_RECIPROCAL) v = 1.0 / v;
-            table[(j * CPL + q) * 32 + lane] = v;
+            plane[j * 32 + lane] = v;
         }
     }
     __syncthreads();
 
-    const long long slot_stride = (long long)a.G * a.C;
-    const bool lane_ok = c0 + CPL - 1 < a.C;  // C is a multiple of CPL (checked by the launcher)
-    const IdxT *idx0 = reinterpret_cast<const IdxT *>(a.idx) + (lane_ok ? c0 : 0);
-    unsigned selector = 0;  // byte-permute selector merging the two slots' words per chain
-    if (CPL * sizeof(IdxT) == 4) {
+    // 32-bit word view of the index slots; the lane's word of grid point `col` is word_base[col * words_per_point]
+    const bool lane_ok = c0 + CPL - 1 < a.C;
+    const unsigned words_per_point = (unsigned)(a.C * IB / 4);
+    // uniform bases + 32-bit per-thread word offsets keep the address arithmetic of the gathers short
+    const unsigned *w_slot0 = reinterpret_cast<const unsigned *>(a.idx);
+    const unsigned *w_slot1 = w_slot0 + (size_t)a.G * words_per_point;
+    const IdxT *e_slot = reinterpret_cast<const IdxT *>(a.idx) + (size_t)islot[0] * a.G * a.C;  // CPL == 1
+    // offsets in 32-bit words (CPL * IB == 4) or in elements (CPL == 1)
+    const unsigned point_stride = (CPL * IB == 4) ? words_per_point : (unsigned)a.C;
+    const unsigned lane_off = lane_ok ? (unsigned)((CPL * IB == 4) ? c0 * IB / 4 : c0) : 0u;
+    unsigned merge_sel = 0;  // per chain: take its bytes from slot 0 (nibble b) or slot 1 (nibble b + 4)
+    unsigned off_sel[CPL];   // builds (cell << 8) | (lane * 8) from the merged word and lane8
+    const unsigned lane8 = (unsigned)lane * 8u;
 #pragma unroll
-        for (int q = 0; q < CPL; ++q)
+    for (int q = 0; q < CPL; ++q) {
 #pragma unroll
-            for (int b = 0; b < (int)sizeof(IdxT); ++b) {
-                const int byte = q * (int)sizeof(IdxT) + b;
-                selector |= (unsigned)(byte + 4 * islot[q]) << (4 * byte);
-            }
+        for (int b = 0; b < IB; ++b) {
+            const int byte = q * IB + b;
+            merge_sel |= (unsigned)(byte + 4 * islot[q]) << (4 * byte);
+        }
+        // result byte0 = lane8.byte0 (index 4), byte1 = cell low byte, byte2 = cell high byte (u16) or 0, byte3 = 0
+        off_sel[q] = 0x5004u | ((unsigned)(q * IB) << 4) | ((IB == 2 ? (unsigned)(q * IB + 1) : 5u) << 8);
     }
-    const double *tab = table + lane;
 
-    const int r_begin = blockIdx.y * RAY_TILE;
-    const int r_end = min(a.R, r_begin + RAY_TILE);
     double ssq[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) ssq[q] = 0.0;
-    for (int r = r_begin + warp; r < r_end; r += SPMM_WARPS) {
+    const int n_chunks = (a.R + SPMM_CHUNK - 1) / SPMM_CHUNK;
+    for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+        const int r = chunk * SPMM_CHUNK + warp;
+        if (r >= a.R) continue;
         const int j0 = a.indptr[r];
         const int j1 = a.indptr[r + 1];
         double acc[CPL];
@@ -309,7 +330,7 @@ k_ray_spmm(SpmmArgs a) {
         for (int q = 0; q < CPL; ++q) acc[q] = 0.0;
         for (int jb = j0; jb < j1; jb += 32) {
             const int jj = jb + lane;
-            const int my_col = (jj < j1) ? a.indices[jj] : 0;
+            const unsigned my_col = (jj < j1) ? (unsigned)a.indices[jj] * point_stride : 0u;
             const double my_val = (jj < j1) ? a.data[jj] : 0.0;
             const int n = min(32, j1 - jb);
             for (int u0 = 0; u0 < n; u0 += 8) {
@@ -317,23 +338,21 @@ k_ray_spmm(SpmmArgs a) {
                 double v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const long long col = __shfl_sync(0xffffffffu, my_col, u0 + u);
+                    const unsigned col = __shfl_sync(0xffffffffu, my_col, u0 + u) + lane_off;
                     v[u] = __shfl_sync(0xffffffffu, my_val, u0 + u);
-                    const IdxT *p = idx0 + col * a.C;
-                    if (CPL * sizeof(IdxT) == 4) {
-                        const unsigned w0 = lane_ok ? *reinterpret_cast<const unsigned *>(p) : 0u;
-                        const unsigned w1 = lane_ok ? *reinterpret_cast<const unsigned *>(p + slot_stride) : 0u;
-                        w[u] = __byte_perm(w0, w1, selector);
-                    } else {
-                        w[u] = lane_ok ? (unsigned)p[(long long)islot[0] * slot_stride] : 0u;
+                    if (CPL * IB == 4) {
+                        w[u] = __byte_perm(w_slot0[col], w_slot1[col], merge_sel);
+                    } else {  // CPL == 1: one index per lane, read from the chain's own slot
+                        w[u] = (unsigned)e_slot[col];
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
-                        const unsigned cell = (CPL == 1) ? w[u] : ((w[u] >> (8 * (int)sizeof(IdxT) * q)) & ((1u << (8 * sizeof(IdxT))) - 1u));
-                        acc[q] += v[u] * tab[(cell * CPL + q) * 32];
+                        const unsigned off = __byte_perm(w[u], lane8, off_sel[q]);
+                        const double t = *reinterpret_cast<const double *>(smem_raw + off + q * PLANE_BYTES);
+                        acc[q] = fma(v[u], t, acc[q]);
                     }
                 }
             }
@@ -349,9 +368,10 @@ k_ray_spmm(SpmmArgs a) {
             }
         }
     }
-    __syncthreads();  // the table is dead: reuse it as red[warp][q][lane]
+    __syncthreads();  // the table is dead: reuse plane 0 as red[warp][q][lane]
+    double *red = reinterpret_cast<double *>(smem_raw);
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) table[(warp * CPL + q) * 32 + lane] = ssq[q];
+    for (int q = 0; q < CPL; ++q) red[(warp * CPL + q) * 32 + lane] = ssq[q];
     __syncthreads();
     if (warp == 0 && a.partial != nullptr) {
 #pragma unroll
@@ -359,37 +379,53 @@ k_ray_spmm(SpmmArgs a) {
             if (!active[q]) continue;
             double tot = 0.0;
 #pragma unroll
-            for (int w = 0; w < SPMM_WARPS; ++w) tot += table[(w * CPL + q) * 32 + lane];
+            for (int w = 0; w < SPMM_WARPS; ++w) tot += red[(w * CPL + q) * 32 + lane];
             a.partial[(long long)blockIdx.y * a.C + c0 + q] = tot;
         }
     }
 }
 
+// chains per lane the shared-memory value table allows for this K (0: K too large)
+static int spmm_cpl(int K, long long C, int idx_bytes) {
+    if (idx_bytes == 1) {
+        if (C % 4 == 0 && K <= SpmmPlane<4>::ROWS) return 4;
+    } else {
+        if (C % 2 == 0 && K <= SpmmPlane<2>::ROWS) return 2;
+    }
+    return K <= SpmmPlane<1>::ROWS ? 1 : 0;
+}
+
+int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm) {
+    const int cpl = spmm_cpl(K, C, idx_bytes);
+    if (cpl == 0) return 0;
+    const long long chain_tiles = (C + 32 * cpl - 1) / (32 * cpl);
+    long long groups = n_sm / chain_tiles;  // one persistent block per SM
+    const long long max_groups = (R + RAY_TILE - 1) / RAY_TILE;  // rows of the partial buffer
+    if (groups > max_groups) groups = max_groups;
+    if (groups < 1) groups = 1;
+    return (int)groups;
+}
+
 template <typename IdxT, int CPL>
 static int launch_spmm_variant(const SpmmArgs &a, cudaStream_t stream) {
     const int chain_tiles = (int)((a.C + 32 * CPL - 1) / (32 * CPL));
-    const int ray_tiles = (a.R + RAY_TILE - 1) / RAY_TILE;
-    dim3 grid(chain_tiles, ray_tiles);
-    size_t smem = (size_t)a.K * CPL * 32 * sizeof(double);
-    const size_t red = (size_t)SPMM_WARPS * CPL * 32 * sizeof(double);
-    if (smem < red) smem = red;
-    if (smem > 48 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(k_ray_spmm<IdxT, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-    }
+    dim3 grid(chain_tiles, a.n_groups);
+    const size_t smem = (size_t)CPL * SpmmPlane<CPL>::ROWS * 256;
+    cudaError_t err = cudaFuncSetAttribute(k_ray_spmm<IdxT, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
     k_ray_spmm<IdxT, CPL><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
     return (int)cudaGetLastError();
 }
 
 int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream) {
-    const size_t budget = 200 * 1024;  // dynamic shared memory available to the value table
-    const size_t row = 32 * sizeof(double);
+    if ((long long)a.G * a.C * a.idx_bytes * 2 / 4 >= (1LL << 32)) return (int)cudaErrorInvalidConfiguration;
+    const int cpl = spmm_cpl(a.K, a.C, a.idx_bytes);
     if (a.idx_bytes == 1) {
-        if (a.C % 4 == 0 && (size_t)a.K * 4 * row <= budget) return launch_spmm_variant<uint8_t, 4>(a, stream);
-        if ((size_t)a.K * row <= 227 * 1024 - 1024) return launch_spmm_variant<uint8_t, 1>(a, stream);
+        if (cpl == 4) return launch_spmm_variant<uint8_t, 4>(a, stream);
+        if (cpl == 1) return launch_spmm_variant<uint8_t, 1>(a, stream);
     } else {
-        if (a.C % 2 == 0 && (size_t)a.K * 2 * row <= budget) return launch_spmm_variant<uint16_t, 2>(a, stream);
-        if ((size_t)a.K * row <= 227 * 1024 - 1024) return launch_spmm_variant<uint16_t, 1>(a, stream);
+        if (cpl == 2) return launch_spmm_variant<uint16_t, 2>(a, stream);
+        if (cpl == 1) return launch_spmm_variant<uint16_t, 1>(a, stream);
     }
     return (int)cudaErrorInvalidConfiguration;  // n_dimensions_max too large for the shared-memory value table
 }
