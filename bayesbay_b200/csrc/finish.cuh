@@ -147,9 +147,16 @@ __device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rn
                 const bbb_target_spec &T = P.targets[t];
                 if (T.space != s) continue;
                 B.phi[t][c] = B.phi[t][C + c];
-                if (T.fwd_kind == BBB_FWD_RAY2D && move_is_geometry(move)) B.idx_sel[t][c] ^= 1;
             }
         }
+    }
+    // nearest-site index: the proposed index (slot 1) becomes current when a geometry move is accepted; the
+    // rasteriser commits it to slot 0 at the start of the next step (tomo_kernels.cu)
+    for (int t = 0; t < P.n_targets; ++t) {
+        const bbb_target_spec &T = P.targets[t];
+        if (T.fwd_kind != BBB_FWD_RAY2D) continue;
+        const bool geom_accepted = accepted && !noise && T.space == s && move_is_geometry(move) && !isinf(lpr);
+        B.idx_sel[t][c] = geom_accepted ? 1 : 0;  // any older pending commit was done by this step's rasteriser
     }
     B.log_like_ratio[c] = llr;
     B.accepted[c] = accepted ? 1 : 0;

@@ -25,6 +25,7 @@ struct RasterArgs {
     void *idx;                // [slots][G][C]
     int idx_bytes;            // 1 or 2
     int points_per_block;
+    int copy_only;            // incremental kernel: commit + copy current -> proposed for every chain, no geometry update
 };
 
 struct SpmmArgs {

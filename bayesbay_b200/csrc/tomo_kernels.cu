@@ -32,7 +32,7 @@ k_raster2d(RasterArgs a) {
                      (mv & 3) != BBB_MOVE_VALUES;
         }
         if (a.sel != nullptr) sslot = a.sel[c] ^ a.slot_xor;
-        if (a.idx_sel != nullptr) islot = a.idx_sel[c] ^ a.slot_xor;
+        islot = a.slot_xor;  // current states -> slot 0, proposals -> slot 1
     }
     if (!__syncthreads_or(active ? 1 : 0)) return;
     const int k = active ? a.k[(long long)sslot * a.C + c] : 0;
@@ -86,24 +86,32 @@ k_raster2d(RasterArgs a) {
 // This is exactly argmin over the proposed sites with the lowest-index tie rule (removing a
 // non-owner cannot change an argmin and the renumbering preserves index order), so the indices are
 // bit-identical to the brute-force kernel; cost ~ (2 + fraction_rescanned * k) evaluations per point
-// instead of k.  Reads the current index slot, writes the proposed one (every point: no copy needed
-// on accept, the slot bit is flipped).
+// instead of k.
+//
+// Index slots: slot 0 holds the CURRENT index of every chain, slot 1 the PROPOSED index of every chain
+// (so the ray kernel reads one slot for all chains).  This kernel therefore visits every chain every
+// step: chains whose last proposal changed the geometry and was accepted (idx_sel == 1) first commit
+// slot 1 -> slot 0; chains without a geometry proposal copy current -> proposed; the others get the
+// change-local update.  The sites of the block's 32 chains are staged in shared memory as
+// [cell][lane] so the per-point owner lookup is a conflict-free LDS instead of a 32-sector gather.
 // ------------------------------------------------------------------------------------------------
-template <typename IdxT>
+template <typename IdxT, bool STAGE>
 __global__ void __launch_bounds__(RASTER_WARPS * 32)
 k_raster2d_inc(RasterArgs a) {
+    extern __shared__ double s_sites[];  // STAGE: [2][K_block][32]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long c = (long long)blockIdx.x * CHAIN_TILE + lane;
     const bool in_range = c < a.C;
-    bool active = false;
-    int cur = 0, icur = 0, rm = -1, ins = -1;
+    bool active = false, pending = false;
+    int cur = 0, rm = -1, ins = -1;
     double nx = 0.0, ny = 0.0;
     if (in_range) {
         const int mv = a.move[c];
-        active = !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space && (mv & 3) != BBB_MOVE_VALUES;
+        active = !a.copy_only && !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space &&
+                 (mv & 3) != BBB_MOVE_VALUES;
         cur = a.sel[c];
-        icur = a.idx_sel[c];
+        pending = a.idx_sel[c] != 0;
         if (active) {
             rm = a.edit[c];
             ins = a.edit[a.C + c];
@@ -111,13 +119,24 @@ k_raster2d_inc(RasterArgs a) {
             ny = a.edit_site[a.C + c];
         }
     }
-    if (!__syncthreads_or(active ? 1 : 0)) return;
     const long long cc = in_range ? c : 0;
     const int k_new = active ? a.k[(long long)(cur ^ 1) * a.C + c] : 0;
     const double *sx = a.sites + ((long long)(cur ^ 1) * 2 + 0) * a.K * a.C + cc;
     const double *sy = a.sites + ((long long)(cur ^ 1) * 2 + 1) * a.K * a.C + cc;
-    const IdxT *in = reinterpret_cast<const IdxT *>(a.idx) + (long long)icur * a.G * a.C + cc;
-    IdxT *out = reinterpret_cast<IdxT *>(a.idx) + (long long)(icur ^ 1) * a.G * a.C + cc;
+    int kmax_blk = k_new;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmax_blk = max(kmax_blk, __shfl_xor_sync(0xffffffffu, kmax_blk, o));
+    double *tx = s_sites + lane;
+    double *ty = s_sites + (long long)a.K * 32 + lane;
+    if (STAGE) {
+        for (int j = warp; j < kmax_blk; j += RASTER_WARPS) {
+            tx[j * 32] = (j < k_new) ? sx[(long long)j * a.C] : 0.0;
+            ty[j * 32] = (j < k_new) ? sy[(long long)j * a.C] : 0.0;
+        }
+        __syncthreads();
+    }
+    IdxT *slot0 = reinterpret_cast<IdxT *>(a.idx) + cc;
+    IdxT *slot1 = slot0 + (long long)a.G * a.C;
 
     constexpr int PPL = RASTER_POINTS_PER_LANE;
     const int g_begin = blockIdx.y * a.points_per_block;
@@ -132,7 +151,11 @@ k_raster2d_inc(RasterArgs a) {
             const int g = min(g0 + q, a.G - 1);
             gx[q] = a.px[g];
             gy[q] = a.py[g];
-            const int o = active ? (int)in[(long long)g * a.C] : 0;
+            int o = 0;
+            if (in_range) {
+                o = (int)(pending ? slot1 : slot0)[(long long)g * a.C];
+                if (pending && g0 + q < g_end) slot0[(long long)g * a.C] = (IdxT)o;  // commit the accepted geometry
+            }
             scan[q] = active && rm >= 0 && o == rm;
             int mm = o - ((rm >= 0 && o > rm) ? 1 : 0);
             mm += (ins >= 0 && mm >= ins) ? 1 : 0;
@@ -144,8 +167,8 @@ k_raster2d_inc(RasterArgs a) {
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
                 const int mm = scan[q] ? 0 : m[q];
-                ox[q] = sx[(long long)mm * a.C];
-                oy[q] = sy[(long long)mm * a.C];
+                ox[q] = STAGE ? tx[mm * 32] : sx[(long long)mm * a.C];
+                oy[q] = STAGE ? ty[mm * 32] : sy[(long long)mm * a.C];
             }
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
@@ -167,8 +190,8 @@ k_raster2d_inc(RasterArgs a) {
             for (int q = 0; q < PPL; ++q) { best[q] = INFINITY; bi[q] = 0; }
             for (int j = 0; j < kmax; ++j) {
                 if (j < kk) {
-                    const double x = sx[(long long)j * a.C];
-                    const double y = sy[(long long)j * a.C];
+                    const double x = STAGE ? tx[j * 32] : sx[(long long)j * a.C];
+                    const double y = STAGE ? ty[j * 32] : sy[(long long)j * a.C];
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
                         const double dx = x - gx[q], dy = y - gy[q];
@@ -181,20 +204,33 @@ k_raster2d_inc(RasterArgs a) {
             for (int q = 0; q < PPL; ++q)
                 if (scan[q]) m[q] = bi[q];
         }
-        if (active) {
+        if (in_range) {
 #pragma unroll
             for (int q = 0; q < PPL; ++q)
-                if (g0 + q < g_end) out[(long long)(g0 + q) * a.C] = (IdxT)m[q];
+                if (g0 + q < g_end) slot1[(long long)(g0 + q) * a.C] = (IdxT)m[q];
         }
     }
+}
+
+template <typename IdxT>
+static int launch_inc_variant(const RasterArgs &a, dim3 grid, cudaStream_t stream) {
+    const size_t smem = (size_t)a.K * 32 * 2 * sizeof(double);
+    if (smem <= 100 * 1024) {  // two resident blocks per SM
+        if (smem > 48 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(k_raster2d_inc<IdxT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return (int)err;
+        }
+        k_raster2d_inc<IdxT, true><<<grid, RASTER_WARPS * 32, smem, stream>>>(a);
+    } else {
+        k_raster2d_inc<IdxT, false><<<grid, RASTER_WARPS * 32, 0, stream>>>(a);
+    }
+    return (int)cudaGetLastError();
 }
 
 int launch_raster2d_inc(const RasterArgs &a, cudaStream_t stream) {
     const int chain_tiles = (int)((a.C + CHAIN_TILE - 1) / CHAIN_TILE);
     dim3 grid(chain_tiles, (a.G + a.points_per_block - 1) / a.points_per_block);
-    if (a.idx_bytes == 1) k_raster2d_inc<uint8_t><<<grid, RASTER_WARPS * 32, 0, stream>>>(a);
-    else k_raster2d_inc<uint16_t><<<grid, RASTER_WARPS * 32, 0, stream>>>(a);
-    return (int)cudaGetLastError();
+    return a.idx_bytes == 1 ? launch_inc_variant<uint8_t>(a, grid, stream) : launch_inc_variant<uint16_t>(a, grid, stream);
 }
 
 int launch_raster2d(const RasterArgs &a, cudaStream_t stream) {
@@ -242,7 +278,7 @@ constexpr int SPMM_CHUNK = SPMM_WARPS;  // rays handed out per scheduling chunk 
 
 template <int CPL> struct SpmmPlane { static constexpr int ROWS = (CPL == 4) ? 224 : (CPL == 2 ? 448 : 896); };
 
-template <typename IdxT, int CPL>
+template <typename IdxT, int CPL, bool MERGE>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, 1)
 k_ray_spmm(SpmmArgs a) {
     extern __shared__ __align__(256) unsigned char smem_raw[];  // CPL planes of ROWS x 32 doubles
@@ -269,7 +305,10 @@ k_ray_spmm(SpmmArgs a) {
                 geom = (mv & 3) != BBB_MOVE_VALUES;
             }
             if (a.sel != nullptr) vslot[q] = a.sel[c] ^ a.slot_xor;
-            if (a.idx_sel != nullptr) islot[q] = a.idx_sel[c] ^ ((a.move != nullptr && geom) ? 1 : 0);
+            // proposals: every chain's proposed index is in slot 1; current states: slot idx_sel
+            if (a.move != nullptr) islot[q] = 1;
+            else if (a.idx_sel != nullptr) islot[q] = a.idx_sel[c];
+            (void)geom;
         }
         k[q] = active[q] ? a.k[(long long)vslot[q] * a.C + c] : 0;
         any_active |= active[q];
@@ -341,7 +380,8 @@ k_ray_spmm(SpmmArgs a) {
                     const unsigned col = __shfl_sync(0xffffffffu, my_col, u0 + u) + lane_off;
                     v[u] = __shfl_sync(0xffffffffu, my_val, u0 + u);
                     if (CPL * IB == 4) {
-                        w[u] = __byte_perm(w_slot0[col], w_slot1[col], merge_sel);
+                        if (MERGE) w[u] = __byte_perm(w_slot0[col], w_slot1[col], merge_sel);
+                        else w[u] = w_slot1[col];
                     } else {  // CPL == 1: one index per lane, read from the chain's own slot
                         w[u] = (unsigned)e_slot[col];
                     }
@@ -406,15 +446,20 @@ int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm) {
     return (int)groups;
 }
 
-template <typename IdxT, int CPL>
-static int launch_spmm_variant(const SpmmArgs &a, cudaStream_t stream) {
+template <typename IdxT, int CPL, bool MERGE>
+static int launch_spmm_merge(const SpmmArgs &a, cudaStream_t stream) {
     const int chain_tiles = (int)((a.C + 32 * CPL - 1) / (32 * CPL));
     dim3 grid(chain_tiles, a.n_groups);
     const size_t smem = (size_t)CPL * SpmmPlane<CPL>::ROWS * 256;
-    cudaError_t err = cudaFuncSetAttribute(k_ray_spmm<IdxT, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(k_ray_spmm<IdxT, CPL, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    k_ray_spmm<IdxT, CPL><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
+    k_ray_spmm<IdxT, CPL, MERGE><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
     return (int)cudaGetLastError();
+}
+template <typename IdxT, int CPL>
+static int launch_spmm_variant(const SpmmArgs &a, cudaStream_t stream) {
+    // proposals read slot 1 only; current states may sit in either slot (merge the two words)
+    return (a.move != nullptr) ? launch_spmm_merge<IdxT, CPL, false>(a, stream) : launch_spmm_merge<IdxT, CPL, true>(a, stream);
 }
 
 int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream) {

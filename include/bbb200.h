@@ -122,8 +122,8 @@ typedef struct {
     /* per target */
     double *sigma[BBB_MAX_TARGETS];   /* [2][C]  (0 = current, 1 = proposed) hierarchical only */
     double *phi[BBB_MAX_TARGETS];     /* [2][C]  sum_i w_i r_i^2 with sigma factored out */
-    void *cell_idx[BBB_MAX_TARGETS];  /* ray2d: [2][G][C] uint8 (K <= 256) or uint16 */
-    uint8_t *idx_sel[BBB_MAX_TARGETS];/* ray2d: [C] */
+    void *cell_idx[BBB_MAX_TARGETS];  /* ray2d: [2][G][C] uint8 (K <= 256) or uint16; slot 0 = current, slot 1 = proposed */
+    uint8_t *idx_sel[BBB_MAX_TARGETS];/* ray2d: [C] 1 = the current index is still in slot 1 (accepted, not yet committed) */
     double *partial[BBB_MAX_TARGETS]; /* ray2d: [n_ray_tiles][C], n_ray_tiles = bbb_ray_tiles(n_data) */
     /* chain scalars */
     double *temperature;     /* [C] */
