@@ -205,18 +205,16 @@ static int run_raster(bbb_engine *e, int t, bool proposal, cudaStream_t st) {
     a.idx = B.cell_idx[t];
     a.idx_bytes = idx_bytes_of(P, t);
     a.points_per_block = raster_points_per_block(a.G, a.C);
-    a.copy_only = 0;
     if (!proposal) {
         // current states: from-scratch rasterisation into slot 0, nothing pending afterwards
         int rc = (int)cudaMemsetAsync(B.idx_sel[t], 0, (size_t)B.n_chains, st);
         return rc != 0 ? rc : launch_raster2d(a, st);
     }
-    if (!e->brute_force) return launch_raster2d_inc(a, st);
-    // reference behaviour: commit/copy pass, then every geometry proposal re-rasterised from scratch
-    a.copy_only = 1;
-    int rc = launch_raster2d_inc(a, st);
-    a.copy_only = 0;
-    return rc != 0 ? rc : launch_raster2d(a, st);
+    // commit pending accepted geometries, proposed slot := current slot, then update the proposing chains:
+    // change-locally, or from scratch when BBB_BRUTE_FORCE_RASTER=1 (the reference's behaviour)
+    int rc = launch_idx_commit_copy(B.cell_idx[t], a.idx_bytes, B.idx_sel[t], a.G, a.C, st);
+    if (rc != 0) return rc;
+    return e->brute_force ? launch_raster2d(a, st) : launch_raster2d_inc(a, st);
 }
 
 // proposal + parallel write of the proposed slots

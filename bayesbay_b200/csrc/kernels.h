@@ -25,7 +25,6 @@ struct RasterArgs {
     void *idx;                // [slots][G][C]
     int idx_bytes;            // 1 or 2
     int points_per_block;
-    int copy_only;            // incremental kernel: commit + copy current -> proposed for every chain, no geometry update
 };
 
 struct SpmmArgs {
@@ -55,6 +54,7 @@ struct SpmmArgs {
 int raster_points_per_block(int G, long long C);
 int launch_raster2d(const RasterArgs &a, cudaStream_t stream);
 int launch_raster2d_inc(const RasterArgs &a, cudaStream_t stream);
+int launch_idx_commit_copy(void *idx, int idx_bytes, const uint8_t *idx_sel, int G, long long C, cudaStream_t stream);
 int launch_apply_edit(const EngineParams *dev_params, long long C, int space, int kmax, cudaStream_t stream);
 int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream);
 int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);

@@ -89,11 +89,10 @@ k_raster2d(RasterArgs a) {
 // instead of k.
 //
 // Index slots: slot 0 holds the CURRENT index of every chain, slot 1 the PROPOSED index of every chain
-// (so the ray kernel reads one slot for all chains).  This kernel therefore visits every chain every
-// step: chains whose last proposal changed the geometry and was accepted (idx_sel == 1) first commit
-// slot 1 -> slot 0; chains without a geometry proposal copy current -> proposed; the others get the
-// change-local update.  The sites of the block's 32 chains are staged in shared memory as
-// [cell][lane] so the per-point owner lookup is a conflict-free LDS instead of a 32-sector gather.
+// (so the ray kernel reads one slot for all chains); k_idx_commit_copy has just made slot 1 a copy of
+// slot 0, this kernel overwrites the chains that propose a geometry change.  The sites of the block's
+// 32 chains are staged in shared memory as [cell][lane] so the per-point owner lookup is a
+// conflict-free LDS instead of a 32-sector gather.
 // ------------------------------------------------------------------------------------------------
 template <typename IdxT, bool STAGE>
 __global__ void __launch_bounds__(RASTER_WARPS * 32)
@@ -103,15 +102,14 @@ k_raster2d_inc(RasterArgs a) {
     const int warp = threadIdx.x >> 5;
     const long long c = (long long)blockIdx.x * CHAIN_TILE + lane;
     const bool in_range = c < a.C;
-    bool active = false, pending = false;
+    bool active = false;
     int cur = 0, rm = -1, ins = -1;
     double nx = 0.0, ny = 0.0;
     if (in_range) {
         const int mv = a.move[c];
-        active = !a.copy_only && !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space &&
+        active = !isinf(a.lpr[c]) && mv != 4 * a.n_spaces && (mv >> 2) == a.space &&
                  (mv & 3) != BBB_MOVE_VALUES;
         cur = a.sel[c];
-        pending = a.idx_sel[c] != 0;
         if (active) {
             rm = a.edit[c];
             ins = a.edit[a.C + c];
@@ -119,6 +117,7 @@ k_raster2d_inc(RasterArgs a) {
             ny = a.edit_site[a.C + c];
         }
     }
+    if (!__syncthreads_or(active ? 1 : 0)) return;  // k_idx_commit_copy already wrote this tile's proposed slot
     const long long cc = in_range ? c : 0;
     const int k_new = active ? a.k[(long long)(cur ^ 1) * a.C + c] : 0;
     const double *sx = a.sites + ((long long)(cur ^ 1) * 2 + 0) * a.K * a.C + cc;
@@ -151,11 +150,7 @@ k_raster2d_inc(RasterArgs a) {
             const int g = min(g0 + q, a.G - 1);
             gx[q] = a.px[g];
             gy[q] = a.py[g];
-            int o = 0;
-            if (in_range) {
-                o = (int)(pending ? slot1 : slot0)[(long long)g * a.C];
-                if (pending && g0 + q < g_end) slot0[(long long)g * a.C] = (IdxT)o;  // commit the accepted geometry
-            }
+            const int o = active ? (int)slot0[(long long)g * a.C] : 0;
             scan[q] = active && rm >= 0 && o == rm;
             int mm = o - ((rm >= 0 && o > rm) ? 1 : 0);
             mm += (ins >= 0 && mm >= ins) ? 1 : 0;
@@ -204,12 +199,74 @@ k_raster2d_inc(RasterArgs a) {
             for (int q = 0; q < PPL; ++q)
                 if (scan[q]) m[q] = bi[q];
         }
-        if (in_range) {
+        if (active) {
 #pragma unroll
             for (int q = 0; q < PPL; ++q)
                 if (g0 + q < g_end) slot1[(long long)(g0 + q) * a.C] = (IdxT)m[q];
         }
     }
+}
+
+// Index-slot maintenance, one streaming pass per step over [G][C]: chains whose accepted geometry is still
+// pending in slot 1 (idx_sel == 1) are committed to slot 0, then slot 1 := slot 0 for EVERY chain, so that the
+// proposed slot is complete (the change-local kernel overwrites the chains with a geometry proposal).
+// 16 bytes (16 uint8 / 8 uint16 chains) per thread.
+template <typename IdxT>
+__global__ void k_idx_commit_copy(IdxT *idx, const uint8_t *idx_sel, int G, long long C) {
+    constexpr int V = 16 / (int)sizeof(IdxT);
+    const long long vec_per_row = C / V;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= vec_per_row * G) return;
+    const long long g = i / vec_per_row, cv = (i % vec_per_row) * V;
+    uint4 *p0 = reinterpret_cast<uint4 *>(idx + g * C + cv);
+    uint4 *p1 = reinterpret_cast<uint4 *>(idx + ((long long)G + g) * C + cv);
+    uint4 w = *p0;
+    unsigned pend = 0;
+    {
+        uint8_t flags[V];
+        if (V == 16) *reinterpret_cast<uint4 *>(flags) = *reinterpret_cast<const uint4 *>(idx_sel + cv);
+        else *reinterpret_cast<uint2 *>(flags) = *reinterpret_cast<const uint2 *>(idx_sel + cv);
+#pragma unroll
+        for (int v = 0; v < V; ++v) pend |= (flags[v] ? 1u : 0u) << v;
+    }
+    if (pend) {
+        const uint4 n = *p1;
+        IdxT *wb = reinterpret_cast<IdxT *>(&w);
+        const IdxT *nb = reinterpret_cast<const IdxT *>(&n);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if ((pend >> v) & 1u) wb[v] = nb[v];
+        *p0 = w;
+    }
+    *p1 = w;
+}
+template <typename IdxT>
+__global__ void k_idx_commit_copy_scalar(IdxT *idx, const uint8_t *idx_sel, int G, long long C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * G) return;
+    const long long c = i % C;
+    IdxT v = idx[i];
+    if (idx_sel[c]) {
+        v = idx[(long long)G * C + i];
+        idx[i] = v;
+    }
+    idx[(long long)G * C + i] = v;
+}
+
+int launch_idx_commit_copy(void *idx, int idx_bytes, const uint8_t *idx_sel, int G, long long C, cudaStream_t stream) {
+    const int V = 16 / idx_bytes;
+    if (C % V == 0) {
+        const long long n = C / V * G;
+        const int blocks = (int)((n + 255) / 256);
+        if (idx_bytes == 1) k_idx_commit_copy<uint8_t><<<blocks, 256, 0, stream>>>((uint8_t *)idx, idx_sel, G, C);
+        else k_idx_commit_copy<uint16_t><<<blocks, 256, 0, stream>>>((uint16_t *)idx, idx_sel, G, C);
+    } else {
+        const long long n = C * G;
+        const int blocks = (int)((n + 255) / 256);
+        if (idx_bytes == 1) k_idx_commit_copy_scalar<uint8_t><<<blocks, 256, 0, stream>>>((uint8_t *)idx, idx_sel, G, C);
+        else k_idx_commit_copy_scalar<uint16_t><<<blocks, 256, 0, stream>>>((uint16_t *)idx, idx_sel, G, C);
+    }
+    return (int)cudaGetLastError();
 }
 
 template <typename IdxT>
