@@ -16,7 +16,7 @@ import os
 from collections import defaultdict
 from typing import Dict, List, Union
 
-from . import _compile
+from . import _compile, _dist
 from ._batch import ChainBatch
 from ._markov_chain import BaseMarkovChain, MarkovChain
 from ._state import State
@@ -25,14 +25,6 @@ from .parameterization import Parameterization
 from .samplers import Sampler, VanillaSampler
 
 __all__ = ["BaseBayesianInversion", "BayesianInversion"]
-
-
-def _dist():
-    try:
-        import torch.distributed as dist
-    except Exception:  # pragma: no cover
-        return None
-    return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
 
 
 class BaseBayesianInversion:
@@ -116,25 +108,16 @@ class BayesianInversion(BaseBayesianInversion):
         self.perturbation_weights = parameterization.perturbation_weights + log_likelihood.perturbation_weights
         self.spec = _compile.compile_problem(parameterization, log_likelihood)
         # chain sharding over ranks (one process per GPU)
-        dist = _dist()
-        self.world_size = dist.get_world_size() if dist else 1
-        self.rank = dist.get_rank() if dist else 0
-        if n_chains % self.world_size:
-            raise ValueError(f"n_chains ({n_chains}) must be divisible by the number of ranks ({self.world_size})")
+        self.rank, self.world_size = _dist.world()
         self.n_chains_global = n_chains
-        n_local = n_chains // self.world_size
-        self.chain_id0 = self.rank * n_local
+        self.chain_id0, n_local = _dist.shard(n_chains)
+        if device is None:
+            device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
         if seed is None:
             from ._batch import next_seed
 
             seed = next_seed()
-        if dist:
-            import torch
-
-            t = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64,
-                             device=device or f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}")
-            dist.broadcast(t, src=0)
-            seed = int(t.item())
+        seed = _dist.broadcast_seed(seed, device)
         starts = None
         if walkers_starting_states is not None:
             starts = walkers_starting_states[self.chain_id0: self.chain_id0 + n_local]
@@ -179,14 +162,7 @@ class BayesianInversion(BaseBayesianInversion):
 
     def all_gather(self, local):
         """[C_local][3] -> [C_total][3] in global chain order (NCCL all-gather over NVLink when sharded)."""
-        dist = _dist()
-        if dist is None:
-            return local.clone()
-        import torch
-
-        out = torch.empty((local.shape[0] * self.world_size, local.shape[1]), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous())
-        return out
+        return _dist.all_gather(local)
 
     def update_log_likelihood_targets(self, targets):
         raise TypeError("targets cannot be added after the chains were placed on the device; build a new inversion")
