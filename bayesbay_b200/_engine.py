@@ -114,12 +114,6 @@ class Engine:
                 t.indptr = self._const(f["indptr"], np.int32).data_ptr()
                 t.indices = self._const(f["indices"], np.int32).data_ptr()
                 t.data = self._const(f["data"], np.float64).data_ptr()
-                stride = int(self.lib.bbb_ray_index_stride(spec["spaces"][f["space"]]["kmax"], self.C))
-                if stride > 0 and t.n_points * stride < 2 ** 31:
-                    rec = np.zeros(t.nnz, dtype=[("val", "<f8"), ("col", "<u4"), ("pad", "<u4")])
-                    rec["val"] = f["data"]
-                    rec["col"] = np.asarray(f["indices"], dtype=np.uint64) * stride
-                    t.packed_csr = self._const(rec.view(np.uint8), np.uint8).data_ptr()
                 t.points_x = self._const(pts[:, 0], np.float64).data_ptr()
                 t.points_y = self._const(pts[:, 1], np.float64).data_ptr()
             elif f["kind"] == "lookup1d":

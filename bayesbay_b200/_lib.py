@@ -47,7 +47,7 @@ class TargetSpec(C.Structure):
         ("dobs", _vp), ("cov_vec", _vp),
         ("fwd_kind", C.c_int32), ("space", C.c_int32), ("param", C.c_int32), ("transform", C.c_int32),
         ("n_points", C.c_int32), ("nnz", C.c_int64),
-        ("indptr", _vp), ("indices", _vp), ("data", _vp), ("packed_csr", _vp), ("points_x", _vp), ("points_y", _vp),
+        ("indptr", _vp), ("indices", _vp), ("data", _vp), ("points_x", _vp), ("points_y", _vp),
         ("x", _vp),
         ("n_lin_params", C.c_int32), ("lin_params", C.c_int32 * MAX_LINEAR_PARAMS),
         ("G", _vp),
@@ -80,7 +80,6 @@ _i32, _i64, _u64 = C.c_int32, C.c_int64, C.c_uint64
 SYMBOLS = {
     "bbb_abi_version": (C.c_int, []),
     "bbb_last_error": (C.c_char_p, []),
-    "bbb_ray_index_stride": (_i64, [_i32, _i64]),
     "bbb_ray_tiles": (_i64, [_i64]),
     "bbb_engine_create": (C.c_int, [C.POINTER(ProblemSpec), C.c_int, C.POINTER(_vp)]),
     "bbb_engine_bind_buffers": (C.c_int, [_vp, C.POINTER(Buffers)]),

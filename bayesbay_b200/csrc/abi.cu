@@ -42,7 +42,6 @@ extern "C" {
 
 int bbb_abi_version(void) { return BBB_ABI_VERSION; }
 const char *bbb_last_error(void) { return g_err; }
-int64_t bbb_ray_index_stride(int32_t kmax, int64_t n_chains) { return spmm_point_stride(kmax, n_chains, kmax <= 256 ? 1 : 2); }
 int64_t bbb_ray_tiles(int64_t n_data) { return (n_data + RAY_TILE - 1) / RAY_TILE; }
 
 static int validate_spec(const bbb_problem_spec *P) {
@@ -249,7 +248,6 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
     a.indptr = T.indptr;
     a.indices = T.indices;
     a.data = T.data;
-    a.packed = T.packed_csr;
     a.transform = T.transform;
     a.dobs = T.dobs;
     a.w = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec : nullptr;

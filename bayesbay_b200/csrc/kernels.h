@@ -40,7 +40,6 @@ struct SpmmArgs {
     int G, R;
     const int32_t *indptr, *indices;
     const double *data;
-    const void *packed;       // optional [nnz] records {f64 weight, u32 column * point_stride, u32 0} (or nullptr)
     int transform;
     const double *dobs;
     const double *w;          // [R] or nullptr
@@ -59,7 +58,6 @@ int launch_idx_commit_copy(void *idx, int idx_bytes, const uint8_t *idx_sel, int
 int launch_apply_edit(const EngineParams *dev_params, long long C, int space, int kmax, cudaStream_t stream);
 int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream);
 int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);
-long long spmm_point_stride(int K, long long C, int idx_bytes);
 
 // step_kernels.cu
 int launch_propose(const EngineParams *dev_params, long long C, cudaStream_t stream);

@@ -424,36 +424,6 @@ k_ray_spmm(SpmmArgs a) {
         double acc[CPL];
 #pragma unroll
         for (int q = 0; q < CPL; ++q) acc[q] = 0.0;
-        if (a.packed != nullptr) {
-            // packed CSR records {weight, column * point_stride, 0}: one warp-uniform 16-byte load per entry
-            // replaces the chunked coalesced load + three shuffles
-            const uint4 *rec = reinterpret_cast<const uint4 *>(a.packed);
-            for (int jb = j0; jb < j1; jb += 8) {
-                unsigned w[8];
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint4 e = (jb + u < j1) ? rec[jb + u] : make_uint4(0u, 0u, 0u, 0u);
-                    v[u] = __hiloint2double((int)e.y, (int)e.x);
-                    const unsigned col = e.z + lane_off;
-                    if (CPL * IB == 4) {
-                        if (MERGE) w[u] = __byte_perm(w_slot0[col], w_slot1[col], merge_sel);
-                        else w[u] = w_slot1[col];
-                    } else {
-                        w[u] = (unsigned)e_slot[col];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const unsigned off = __byte_perm(w[u], lane8, off_sel[q]);
-                        const double t = *reinterpret_cast<const double *>(smem_raw + off + q * PLANE_BYTES);
-                        acc[q] = fma(v[u], t, acc[q]);
-                    }
-                }
-            }
-        } else
         for (int jb = j0; jb < j1; jb += 32) {
             const int jj = jb + lane;
             const unsigned my_col = (jj < j1) ? (unsigned)a.indices[jj] * point_stride : 0u;
@@ -520,13 +490,6 @@ static int spmm_cpl(int K, long long C, int idx_bytes) {
         if (C % 2 == 0 && K <= SpmmPlane<2>::ROWS) return 2;
     }
     return K <= SpmmPlane<1>::ROWS ? 1 : 0;
-}
-
-// stride (in the units the kernel indexes the index grid with) between consecutive grid points
-long long spmm_point_stride(int K, long long C, int idx_bytes) {
-    const int cpl = spmm_cpl(K, C, idx_bytes);
-    if (cpl == 0) return 0;
-    return (cpl * idx_bytes == 4) ? C * idx_bytes / 4 : C;
 }
 
 int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm) {

@@ -91,9 +91,6 @@ typedef struct {
     const int32_t *indptr;   /* device [n_data + 1] */
     const int32_t *indices;  /* device [nnz] */
     const double *data;      /* device [nnz] */
-    const void *packed_csr;  /* optional device [nnz] 16-byte records {f64 data, u32 indices * stride, u32 0} with
-                              * stride = bbb_ray_index_stride(kmax, n_chains): lets the ray kernel fetch an entry with
-                              * one warp-uniform load; NULL = use indices/data */
     const double *points_x;  /* device [n_points] */
     const double *points_y;  /* device [n_points] */
     /* lookup1d: data positions */
@@ -152,9 +149,6 @@ typedef struct bbb_engine bbb_engine;
 
 int bbb_abi_version(void);
 const char *bbb_last_error(void);
-/* column stride the ray kernel uses inside packed_csr records for a space padded to kmax cells and
- * n_chains resident chains (0: the packed layout is not usable for this shape) */
-int64_t bbb_ray_index_stride(int32_t kmax, int64_t n_chains);
 /* number of ray tiles the partial-misfit buffer must hold for a ray target with n_data rays */
 int64_t bbb_ray_tiles(int64_t n_data);
 
