@@ -170,6 +170,8 @@ def cuda_arm(args):
     eng.step(max(args.burn, 0))
     for _ in range(args.warmup):
         eng.step(1)
+    if tempered:
+        swap_round(10 ** 6)  # warm the NCCL all-gather path (untimed)
     sync_all()
 
     # ---- timed region: exactly K steps; L2 flushed between steps, each step timed by its own events --
