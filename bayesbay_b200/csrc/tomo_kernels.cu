@@ -174,45 +174,30 @@ k_raster2d_inc(RasterArgs a) {
                 if (!scan[q] && (d_new < d_own || (d_new == d_own && ins < m[q]))) m[q] = ins;
             }
         }
-        // points whose owner was removed/moved: full scan of the proposed sites.  Done one point at a time --
-        // a lane needs it for ~1/k of its points, so per point only a few warps enter the k-loop at all
-        (void)any_scan;
-#pragma unroll
-        for (int q = 0; q < PPL; ++q) {
-            if (!__any_sync(0xffffffffu, scan[q])) continue;
-            const int kk = scan[q] ? k_new : 0;
+        if (__any_sync(0xffffffffu, any_scan)) {
+            const int kk = any_scan ? k_new : 0;
             int kmax = kk;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-            double best0 = INFINITY, best1 = INFINITY;
-            int bi0 = 0, bi1 = 0;
-            int j = 0;
-            for (; j + 1 < kmax; j += 2) {  // two independent argmin chains (even / odd sites) for ILP
+            double best[PPL];
+            int bi[PPL];
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) { best[q] = INFINITY; bi[q] = 0; }
+            for (int j = 0; j < kmax; ++j) {
                 if (j < kk) {
-                    const double x0 = STAGE ? tx[j * 32] : sx[(long long)j * a.C];
-                    const double y0 = STAGE ? ty[j * 32] : sy[(long long)j * a.C];
-                    const double dx0 = x0 - gx[q], dy0 = y0 - gy[q];
-                    const double d0 = __dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0));
-                    if (d0 < best0) { best0 = d0; bi0 = j; }
-                }
-                if (j + 1 < kk) {
-                    const double x1 = STAGE ? tx[(j + 1) * 32] : sx[(long long)(j + 1) * a.C];
-                    const double y1 = STAGE ? ty[(j + 1) * 32] : sy[(long long)(j + 1) * a.C];
-                    const double dx1 = x1 - gx[q], dy1 = y1 - gy[q];
-                    const double d1 = __dadd_rn(__dmul_rn(dx1, dx1), __dmul_rn(dy1, dy1));
-                    if (d1 < best1) { best1 = d1; bi1 = j + 1; }
+                    const double x = STAGE ? tx[j * 32] : sx[(long long)j * a.C];
+                    const double y = STAGE ? ty[j * 32] : sy[(long long)j * a.C];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        const double dx = x - gx[q], dy = y - gy[q];
+                        const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        if (d < best[q]) { best[q] = d; bi[q] = j; }
+                    }
                 }
             }
-            if (j < kk) {
-                const double x0 = STAGE ? tx[j * 32] : sx[(long long)j * a.C];
-                const double y0 = STAGE ? ty[j * 32] : sy[(long long)j * a.C];
-                const double dx0 = x0 - gx[q], dy0 = y0 - gy[q];
-                const double d0 = __dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0));
-                if (d0 < best0) { best0 = d0; bi0 = j; }
-            }
-            // merge the two chains: smaller distance wins, the lower index on a tie
-            if (best1 < best0 || (best1 == best0 && bi1 < bi0)) bi0 = bi1;
-            if (scan[q]) m[q] = bi0;
+#pragma unroll
+            for (int q = 0; q < PPL; ++q)
+                if (scan[q]) m[q] = bi[q];
         }
         if (active) {
 #pragma unroll
