@@ -149,6 +149,7 @@ class Engine:
             b.sites[i], b.values[i] = _ptr(self.sites[i]), _ptr(self.values[i])
             b.k[i], b.sel[i] = _ptr(self.k[i]), _ptr(self.sel[i])
         self.sigma, self.phi, self.cell_idx, self.idx_sel, self.partial = [], [], [], [], []
+        self.rescan_list, self.rescan_count = [], []
         for i, tg in enumerate(self.spec["targets"]):
             self.sigma.append(torch.ones((2, Cn), dtype=f64, device=dev) if tg["hierarchical"] else None)
             self.phi.append(z((2, Cn), f64))
@@ -159,12 +160,17 @@ class Engine:
                 self.cell_idx.append(z((2, G, Cn), u8 if K <= 256 else torch.int16))
                 self.idx_sel.append(z((Cn,), u8))
                 self.partial.append(z((tiles, Cn), f64))
+                self.rescan_list.append(torch.empty((Cn, G), dtype=i32, device=dev))
+                self.rescan_count.append(z((Cn,), i32))
             else:
+                self.rescan_list.append(None)
+                self.rescan_count.append(None)
                 self.cell_idx.append(None)
                 self.idx_sel.append(None)
                 self.partial.append(None)
             b.sigma[i], b.phi[i] = _ptr(self.sigma[i]), _ptr(self.phi[i])
             b.cell_idx[i], b.idx_sel[i], b.partial[i] = _ptr(self.cell_idx[i]), _ptr(self.idx_sel[i]), _ptr(self.partial[i])
+            b.rescan_list[i], b.rescan_count[i] = _ptr(self.rescan_list[i]), _ptr(self.rescan_count[i])
         nm = 4 * len(self.spec["spaces"]) + 1
         self.temperature = torch.ones((Cn,), dtype=f64, device=dev)
         self.iteration = z((Cn,), i64)

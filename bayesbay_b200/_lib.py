@@ -68,6 +68,7 @@ class Buffers(C.Structure):
         ("sites", _vp * MAX_SPACES), ("values", _vp * MAX_SPACES), ("k", _vp * MAX_SPACES), ("sel", _vp * MAX_SPACES),
         ("sigma", _vp * MAX_TARGETS), ("phi", _vp * MAX_TARGETS), ("cell_idx", _vp * MAX_TARGETS),
         ("idx_sel", _vp * MAX_TARGETS), ("partial", _vp * MAX_TARGETS),
+        ("rescan_list", _vp * MAX_TARGETS), ("rescan_count", _vp * MAX_TARGETS),
         ("temperature", _vp), ("iteration", _vp),
         ("move", _vp), ("edit", _vp), ("edit_site", _vp), ("edit_vals", _vp), ("log_prob_ratio", _vp), ("log_like_ratio", _vp), ("accepted", _vp),
         ("n_proposed", _vp), ("n_accepted", _vp),

@@ -149,8 +149,9 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
     for (int t = 0; t < P.n_targets; ++t) {
         if (!b->phi[t]) return fail(BBB_ERR_SHAPE, "target %d: phi buffer missing", t);
         if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL && !b->sigma[t]) return fail(BBB_ERR_SHAPE, "target %d: sigma buffer missing", t);
-        if (P.targets[t].fwd_kind == BBB_FWD_RAY2D && (!b->cell_idx[t] || !b->idx_sel[t] || !b->partial[t]))
-            return fail(BBB_ERR_SHAPE, "target %d: cell_idx/idx_sel/partial buffer missing", t);
+        if (P.targets[t].fwd_kind == BBB_FWD_RAY2D &&
+            (!b->cell_idx[t] || !b->idx_sel[t] || !b->partial[t] || !b->rescan_list[t] || !b->rescan_count[t]))
+            return fail(BBB_ERR_SHAPE, "target %d: cell_idx/idx_sel/partial/rescan buffer missing", t);
     }
     if (!b->temperature || !b->iteration || !b->move || !b->edit || !b->edit_site || !b->edit_vals || !b->log_prob_ratio || !b->log_like_ratio ||
         !b->accepted || !b->n_proposed || !b->n_accepted || !b->tape_cursor)
@@ -205,6 +206,8 @@ static int run_raster(bbb_engine *e, int t, bool proposal, cudaStream_t st) {
     a.idx = B.cell_idx[t];
     a.idx_bytes = idx_bytes_of(P, t);
     a.points_per_block = raster_points_per_block(a.G, a.C);
+    a.rescan_list = B.rescan_list[t];
+    a.rescan_count = B.rescan_count[t];
     if (!proposal) {
         // current states: from-scratch rasterisation into slot 0, nothing pending afterwards
         int rc = (int)cudaMemsetAsync(B.idx_sel[t], 0, (size_t)B.n_chains, st);

@@ -25,6 +25,8 @@ struct RasterArgs {
     void *idx;                // [slots][G][C]
     int idx_bytes;            // 1 or 2
     int points_per_block;
+    unsigned *rescan_list;    // [C][G] queue of grid points that lost their owner   -- incremental kernel only
+    int32_t *rescan_count;    // [C] queue lengths (zero between steps)
 };
 
 struct SpmmArgs {

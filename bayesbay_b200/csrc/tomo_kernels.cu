@@ -174,37 +174,71 @@ k_raster2d_inc(RasterArgs a) {
                 if (!scan[q] && (d_new < d_own || (d_new == d_own && ins < m[q]))) m[q] = ins;
             }
         }
-        if (__any_sync(0xffffffffu, any_scan)) {
-            const int kk = any_scan ? k_new : 0;
-            int kmax = kk;
+        // points whose owner was removed/moved need a full scan of the proposed sites.  Only ~1/k of a proposing
+        // chain's points do, so scanning here would idle 99 % of the lanes: queue them per chain instead and let
+        // k_raster2d_rescan do the scans with lanes = sites (warp-shuffle argmin).
+        (void)any_scan;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-            double best[PPL];
-            int bi[PPL];
-#pragma unroll
-            for (int q = 0; q < PPL; ++q) { best[q] = INFINITY; bi[q] = 0; }
-            for (int j = 0; j < kmax; ++j) {
-                if (j < kk) {
-                    const double x = STAGE ? tx[j * 32] : sx[(long long)j * a.C];
-                    const double y = STAGE ? ty[j * 32] : sy[(long long)j * a.C];
-#pragma unroll
-                    for (int q = 0; q < PPL; ++q) {
-                        const double dx = x - gx[q], dy = y - gy[q];
-                        const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                        if (d < best[q]) { best[q] = d; bi[q] = j; }
-                    }
-                }
+        for (int q = 0; q < PPL; ++q) {
+            if (scan[q] && g0 + q < g_end) {
+                const int pos = atomicAdd(a.rescan_count + c, 1);
+                a.rescan_list[(long long)c * a.G + pos] = (unsigned)(g0 + q);
             }
-#pragma unroll
-            for (int q = 0; q < PPL; ++q)
-                if (scan[q]) m[q] = bi[q];
         }
         if (active) {
 #pragma unroll
             for (int q = 0; q < PPL; ++q)
-                if (g0 + q < g_end) slot1[(long long)(g0 + q) * a.C] = (IdxT)m[q];
+                if (g0 + q < g_end && !scan[q]) slot1[(long long)(g0 + q) * a.C] = (IdxT)m[q];
         }
     }
+}
+
+// Second phase of the change-local update: one block per chain drains the chain's queue of grid points that
+// lost their owner.  The chain's proposed sites are staged in shared memory; one warp per point evaluates the
+// sites with lanes = sites and reduces (distance, index) lexicographically with shuffles, so the lowest index
+// wins ties exactly as in the brute-force kernel.
+constexpr int RESCAN_WARPS = 4;
+
+template <typename IdxT>
+__global__ void __launch_bounds__(RESCAN_WARPS * 32)
+k_raster2d_rescan(RasterArgs a) {
+    extern __shared__ double s_xy[];  // [2][k_new]
+    const long long c = blockIdx.x;
+    const int n = a.rescan_count[c];
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int prop = a.sel[c] ^ 1;
+    const int k_new = a.k[(long long)prop * a.C + c];
+    const double *sx = a.sites + ((long long)prop * 2 + 0) * a.K * a.C + c;
+    const double *sy = a.sites + ((long long)prop * 2 + 1) * a.K * a.C + c;
+    for (int j = threadIdx.x; j < k_new; j += blockDim.x) {
+        s_xy[j] = sx[(long long)j * a.C];
+        s_xy[a.K + j] = sy[(long long)j * a.C];
+    }
+    __syncthreads();
+    IdxT *slot1 = reinterpret_cast<IdxT *>(a.idx) + (long long)a.G * a.C + c;
+    const unsigned *list = a.rescan_list + c * a.G;
+    for (int item = warp; item < n; item += RESCAN_WARPS) {
+        const unsigned g = list[item];
+        const double gx = a.px[g], gy = a.py[g];
+        double best = INFINITY;
+        int bi = 0x7fffffff;
+        for (int j = lane; j < k_new; j += 32) {
+            const double dx = s_xy[j] - gx, dy = s_xy[a.K + j] - gy;
+            const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d < best) { best = d; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < best || (od == best && oj < bi)) { best = od; bi = oj; }
+        }
+        if (lane == 0) slot1[(long long)g * a.C] = (IdxT)bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.rescan_count[c] = 0;
 }
 
 // Index-slot maintenance, one streaming pass per step over [G][C]: chains whose accepted geometry is still
@@ -287,7 +321,12 @@ static int launch_inc_variant(const RasterArgs &a, dim3 grid, cudaStream_t strea
 int launch_raster2d_inc(const RasterArgs &a, cudaStream_t stream) {
     const int chain_tiles = (int)((a.C + CHAIN_TILE - 1) / CHAIN_TILE);
     dim3 grid(chain_tiles, (a.G + a.points_per_block - 1) / a.points_per_block);
-    return a.idx_bytes == 1 ? launch_inc_variant<uint8_t>(a, grid, stream) : launch_inc_variant<uint16_t>(a, grid, stream);
+    int rc = a.idx_bytes == 1 ? launch_inc_variant<uint8_t>(a, grid, stream) : launch_inc_variant<uint16_t>(a, grid, stream);
+    if (rc != 0) return rc;
+    const size_t smem = (size_t)a.K * 2 * sizeof(double);
+    if (a.idx_bytes == 1) k_raster2d_rescan<uint8_t><<<(unsigned)a.C, RESCAN_WARPS * 32, smem, stream>>>(a);
+    else k_raster2d_rescan<uint16_t><<<(unsigned)a.C, RESCAN_WARPS * 32, smem, stream>>>(a);
+    return (int)cudaGetLastError();
 }
 
 int launch_raster2d(const RasterArgs &a, cudaStream_t stream) {

@@ -125,6 +125,8 @@ typedef struct {
     void *cell_idx[BBB_MAX_TARGETS];  /* ray2d: [2][G][C] uint8 (K <= 256) or uint16; slot 0 = current, slot 1 = proposed */
     uint8_t *idx_sel[BBB_MAX_TARGETS];/* ray2d: [C] 1 = the current index is still in slot 1 (accepted, not yet committed) */
     double *partial[BBB_MAX_TARGETS]; /* ray2d: [n_ray_tiles][C], n_ray_tiles = bbb_ray_tiles(n_data) */
+    uint32_t *rescan_list[BBB_MAX_TARGETS]; /* ray2d: [C][G] scratch queue of the change-local rasteriser */
+    int32_t *rescan_count[BBB_MAX_TARGETS]; /* ray2d: [C], must be zero when bound */
     /* chain scalars */
     double *temperature;     /* [C] */
     int64_t *iteration;      /* [C] iterations done (Philox counter) */
