@@ -197,7 +197,8 @@ k_raster2d_inc(RasterArgs a) {
 // lost their owner.  The chain's proposed sites are staged in shared memory; one warp per point evaluates the
 // sites with lanes = sites and reduces (distance, index) lexicographically with shuffles, so the lowest index
 // wins ties exactly as in the brute-force kernel.
-constexpr int RESCAN_WARPS = 4;
+constexpr int RESCAN_WARPS = 8;
+constexpr int RESCAN_SPLIT = 4;  // blocks per chain (cell sizes vary a lot: keeps the largest cell off the critical path)
 
 template <typename IdxT>
 __global__ void __launch_bounds__(RESCAN_WARPS * 32)
@@ -219,7 +220,7 @@ k_raster2d_rescan(RasterArgs a) {
     __syncthreads();
     IdxT *slot1 = reinterpret_cast<IdxT *>(a.idx) + (long long)a.G * a.C + c;
     const unsigned *list = a.rescan_list + c * a.G;
-    for (int item = warp; item < n; item += RESCAN_WARPS) {
+    for (int item = blockIdx.y * RESCAN_WARPS + warp; item < n; item += RESCAN_WARPS * RESCAN_SPLIT) {
         const unsigned g = list[item];
         const double gx = a.px[g], gy = a.py[g];
         double best = INFINITY;
@@ -237,8 +238,6 @@ k_raster2d_rescan(RasterArgs a) {
         }
         if (lane == 0) slot1[(long long)g * a.C] = (IdxT)bi;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) a.rescan_count[c] = 0;
 }
 
 // Index-slot maintenance, one streaming pass per step over [G][C]: chains whose accepted geometry is still
@@ -324,9 +323,12 @@ int launch_raster2d_inc(const RasterArgs &a, cudaStream_t stream) {
     int rc = a.idx_bytes == 1 ? launch_inc_variant<uint8_t>(a, grid, stream) : launch_inc_variant<uint16_t>(a, grid, stream);
     if (rc != 0) return rc;
     const size_t smem = (size_t)a.K * 2 * sizeof(double);
-    if (a.idx_bytes == 1) k_raster2d_rescan<uint8_t><<<(unsigned)a.C, RESCAN_WARPS * 32, smem, stream>>>(a);
-    else k_raster2d_rescan<uint16_t><<<(unsigned)a.C, RESCAN_WARPS * 32, smem, stream>>>(a);
-    return (int)cudaGetLastError();
+    dim3 rgrid((unsigned)a.C, RESCAN_SPLIT);
+    if (a.idx_bytes == 1) k_raster2d_rescan<uint8_t><<<rgrid, RESCAN_WARPS * 32, smem, stream>>>(a);
+    else k_raster2d_rescan<uint16_t><<<rgrid, RESCAN_WARPS * 32, smem, stream>>>(a);
+    rc = (int)cudaGetLastError();
+    if (rc != 0) return rc;
+    return (int)cudaMemsetAsync(a.rescan_count, 0, (size_t)a.C * sizeof(int32_t), stream);  // queues drained
 }
 
 int launch_raster2d(const RasterArgs &a, cudaStream_t stream) {
