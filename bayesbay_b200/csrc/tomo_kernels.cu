@@ -374,13 +374,15 @@ int raster_points_per_block(int G, long long C) {
 constexpr int SPMM_WARPS = 16;
 constexpr int SPMM_CHUNK = SPMM_WARPS;  // rays handed out per scheduling chunk (one per warp)
 
-template <int CPL> struct SpmmPlane { static constexpr int ROWS = (CPL == 4) ? 224 : (CPL == 2 ? 448 : 896); };
+template <int CPL> struct SpmmPlane { static constexpr int ROWS = (CPL == 4) ? 208 : (CPL == 2 ? 416 : 832); };
+constexpr int SPMM_STAGE_BYTES = SPMM_WARPS * 32 * 16;  // per-warp staging of 32 CSR entries {weight, column}
 
 template <typename IdxT, int CPL, bool MERGE>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, 1)
 k_ray_spmm(SpmmArgs a) {
-    extern __shared__ __align__(256) unsigned char smem_raw[];  // CPL planes of ROWS x 32 doubles
+    extern __shared__ __align__(256) unsigned char smem_raw[];  // CPL planes of ROWS x 32 doubles, then CSR staging
     constexpr int PLANE_BYTES = SpmmPlane<CPL>::ROWS * 256;
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_raw + CPL * PLANE_BYTES) + (threadIdx.x >> 5) * 32;
     constexpr int IB = (int)sizeof(IdxT);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -466,17 +468,23 @@ k_ray_spmm(SpmmArgs a) {
 #pragma unroll
         for (int q = 0; q < CPL; ++q) acc[q] = 0.0;
         for (int jb = j0; jb < j1; jb += 32) {
+            // 32 CSR entries: one coalesced load per lane, parked in the warp's staging row; each entry is then
+            // fetched with ONE broadcast LDS.128 (cheaper on the shared-memory pipe than three shuffles)
             const int jj = jb + lane;
             const unsigned my_col = (jj < j1) ? (unsigned)a.indices[jj] * point_stride : 0u;
             const double my_val = (jj < j1) ? a.data[jj] : 0.0;
+            __syncwarp();
+            stage[lane] = make_uint4((unsigned)__double2loint(my_val), (unsigned)__double2hiint(my_val), my_col, 0u);
+            __syncwarp();
             const int n = min(32, j1 - jb);
             for (int u0 = 0; u0 < n; u0 += 8) {
                 unsigned w[8];
                 double v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const unsigned col = __shfl_sync(0xffffffffu, my_col, u0 + u) + lane_off;
-                    v[u] = __shfl_sync(0xffffffffu, my_val, u0 + u);
+                    const uint4 e = stage[u0 + u];
+                    v[u] = __hiloint2double((int)e.y, (int)e.x);
+                    const unsigned col = e.z + lane_off;
                     if (CPL * IB == 4) {
                         if (MERGE) w[u] = __byte_perm(w_slot0[col], w_slot1[col], merge_sel);
                         else w[u] = w_slot1[col];
@@ -548,7 +556,7 @@ template <typename IdxT, int CPL, bool MERGE>
 static int launch_spmm_merge(const SpmmArgs &a, cudaStream_t stream) {
     const int chain_tiles = (int)((a.C + 32 * CPL - 1) / (32 * CPL));
     dim3 grid(chain_tiles, a.n_groups);
-    const size_t smem = (size_t)CPL * SpmmPlane<CPL>::ROWS * 256;
+    const size_t smem = (size_t)CPL * SpmmPlane<CPL>::ROWS * 256 + SPMM_STAGE_BYTES;
     cudaError_t err = cudaFuncSetAttribute(k_ray_spmm<IdxT, CPL, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     k_ray_spmm<IdxT, CPL, MERGE><<<grid, SPMM_WARPS * 32, smem, stream>>>(a);
