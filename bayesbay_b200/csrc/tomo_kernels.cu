@@ -480,10 +480,8 @@ k_ray_spmm(SpmmArgs a) {
             for (int u0 = 0; u0 < n; u0 += 8) {
                 unsigned w[8];
                 double v[8];
-                const int nb = n - u0;  // warp-uniform: entries of this batch that exist (the rest is skipped)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    if (u >= nb) break;
                     const uint4 e = stage[u0 + u];
                     v[u] = __hiloint2double((int)e.y, (int)e.x);
                     const unsigned col = e.z + lane_off;
@@ -496,7 +494,6 @@ k_ray_spmm(SpmmArgs a) {
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    if (u >= nb) break;
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
                         const unsigned off = __byte_perm(w[u], lane8, off_sel[q]);
