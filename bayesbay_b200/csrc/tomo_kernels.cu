@@ -372,6 +372,7 @@ int raster_points_per_block(int G, long long C) {
 // bit-reproducible run to run (no atomics).  d_pred is only written on request.
 // ------------------------------------------------------------------------------------------------
 constexpr int SPMM_WARPS = 16;
+constexpr int SPMM_BATCH = 8;   // CSR entries whose index gathers are in flight together per warp
 constexpr int SPMM_CHUNK = SPMM_WARPS;  // rays handed out per scheduling chunk (one per warp)
 
 template <int CPL> struct SpmmPlane { static constexpr int ROWS = (CPL == 4) ? 208 : (CPL == 2 ? 416 : 832); };
@@ -477,11 +478,11 @@ k_ray_spmm(SpmmArgs a) {
             stage[lane] = make_uint4((unsigned)__double2loint(my_val), (unsigned)__double2hiint(my_val), my_col, 0u);
             __syncwarp();
             const int n = min(32, j1 - jb);
-            for (int u0 = 0; u0 < n; u0 += 8) {
-                unsigned w[8];
-                double v[8];
+            for (int u0 = 0; u0 < n; u0 += SPMM_BATCH) {
+                unsigned w[SPMM_BATCH];
+                double v[SPMM_BATCH];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < SPMM_BATCH; ++u) {
                     const uint4 e = stage[u0 + u];
                     v[u] = __hiloint2double((int)e.y, (int)e.x);
                     const unsigned col = e.z + lane_off;
@@ -493,7 +494,7 @@ k_ray_spmm(SpmmArgs a) {
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < SPMM_BATCH; ++u) {
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
                         const unsigned off = __byte_perm(w[u], lane8, off_sel[q]);
