@@ -44,18 +44,37 @@ __device__ inline int nearest_1d(const bbb_buffers &B, const bbb_space_spec &S, 
 // Voronoi.nearest_neighbour (discretization/_voronoi.py:462-465): argmin of the Euclidean distance,
 // lowest index on ties; squared distance with separately rounded products (no FMA).
 __device__ inline int nearest_2d(const bbb_buffers &B, const bbb_space_spec &S, int s, int slot,
-                                 long long c, int k, int skip, double px, double py) {
+                                 long long c, int k, int skip, double px, double py, bool coop) {
     double best = INFINITY;
-    int bi = 0, out = 0;
-    for (int j = 0; j < k; ++j) {
+    int bi = 0x7fffffff;
+    if (!coop) {
+        int out = 0;
+        bi = 0;
+        for (int j = 0; j < k; ++j) {
+            if (j == skip) continue;
+            const double dx = site_ref(B, S, s, slot, 0, j, c) - px;
+            const double dy = site_ref(B, S, s, slot, 1, j, c) - py;
+            const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d < best) { best = d; bi = out; }
+            ++out;
+        }
+        return bi;  // index among the remaining cells
+    }
+    // warp-cooperative: lanes = sites, then a lexicographic (distance, index) shuffle reduction
+    for (int j = threadIdx.x & 31; j < k; j += 32) {
         if (j == skip) continue;
         const double dx = site_ref(B, S, s, slot, 0, j, c) - px;
         const double dy = site_ref(B, S, s, slot, 1, j, c) - py;
         const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        if (d < best) { best = d; bi = out; }
-        ++out;
+        if (d < best) { best = d; bi = j; }
     }
-    return bi;  // index among the remaining cells
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < best || (od == best && oj < bi)) { best = od; bi = oj; }
+    }
+    return bi - ((skip >= 0 && bi > skip) ? 1 : 0);  // index among the remaining cells
 }
 
 __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, Rng &rng,
@@ -71,6 +90,7 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
     for (int t = 0; t < P.n_targets; ++t) any_hier |= (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL);
     if (any_hier) w[n_outer++] = 1.0;
     const int i_outer = rng.choice(w, n_outer);
+    const bool writer = !rng.coop || (threadIdx.x & 31) == 0;  // cooperative mode: lane 0 publishes the proposal
 
     if (i_outer >= P.n_spaces) {
         // ---- P7 NoisePerturbation.perturb (perturbations/_data_noise.py:21-77) ------------------
@@ -85,12 +105,14 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
                 new_v = cand;
                 break;
             }
-            B.sigma[t][B.n_chains + c] = new_v;
+            if (writer) B.sigma[t][B.n_chains + c] = new_v;
         }
-        B.move[c] = 4 * P.n_spaces;
-        B.edit[c] = -1;
-        B.edit[B.n_chains + c] = -1;
-        B.log_prob_ratio[c] = 0.0;
+        if (writer) {
+            B.move[c] = 4 * P.n_spaces;
+            B.edit[c] = -1;
+            B.edit[B.n_chains + c] = -1;
+            B.log_prob_ratio[c] = 0.0;
+        }
         return;
     }
 
@@ -172,7 +194,7 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
             } else {
                 // _initialize_params_from_neighbour (discretization/_discretization.py:323-375)
                 const int i_near = (S.ndim == 1) ? nearest_1d(B, S, s, cur, c, k, -1, e.site[0])
-                                                 : nearest_2d(B, S, s, cur, c, k, -1, e.site[0], e.site[1]);
+                                                 : nearest_2d(B, S, s, cur, c, k, -1, e.site[0], e.site[1], rng.coop);
                 for (int p = 0; p < S.n_params; ++p) {
                     const double theta = S.perturb_std_birth[p];
                     const double old_v = value_ref(B, S, s, cur, p, i_near, c);
@@ -204,7 +226,7 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
                 double pos[2] = {0.0, 0.0};
                 for (int d = 0; d < S.ndim; ++d) pos[d] = site_ref(B, S, s, cur, d, e.rm, c);
                 int i_near = (S.ndim == 1) ? nearest_1d(B, S, s, cur, c, k, e.rm, pos[0])
-                                           : nearest_2d(B, S, s, cur, c, k, e.rm, pos[0], pos[1]);
+                                           : nearest_2d(B, S, s, cur, c, k, e.rm, pos[0], pos[1], rng.coop);
                 i_near += (i_near >= e.rm) ? 1 : 0;  // back to indices of the current state
                 for (int p = 0; p < S.n_params; ++p) {
                     const double theta = S.perturb_std_birth[p];
@@ -222,10 +244,12 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
     // The edit (rm, ins, new cell) is published for k_apply_edit, which writes the proposed slot with one
     // thread per (cell, chain); the fused small-problem kernel applies it here, one lock-step loop for
     // every move kind.
-    for (int d = 0; d < S.ndim; ++d) B.edit_site[(long long)d * B.n_chains + c] = e.site[d];
-    for (int p = 0; p < S.n_params; ++p) B.edit_vals[(long long)p * B.n_chains + c] = e.vals[p];
     const int k_new = e.write ? k - (e.rm >= 0 ? 1 : 0) + (e.ins >= 0 ? 1 : 0) : k;
-    k_ref(B, s, prop, c) = k_new;
+    if (writer) {
+        for (int d = 0; d < S.ndim; ++d) B.edit_site[(long long)d * B.n_chains + c] = e.site[d];
+        for (int p = 0; p < S.n_params; ++p) B.edit_vals[(long long)p * B.n_chains + c] = e.vals[p];
+        k_ref(B, s, prop, c) = k_new;
+    }
     if (e.write && apply_now) {
         const int ndim = S.ndim, n_params = S.n_params;
         const long long C = B.n_chains, KC = (long long)S.kmax * C;
@@ -246,10 +270,12 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
             }
         }
     }
-    B.move[c] = 4 * s + inner;
-    B.edit[c] = e.rm;
-    B.edit[B.n_chains + c] = e.ins;
-    B.log_prob_ratio[c] = e.lpr;
+    if (writer) {
+        B.move[c] = 4 * s + inner;
+        B.edit[c] = e.rm;
+        B.edit[B.n_chains + c] = e.ins;
+        B.log_prob_ratio[c] = e.lpr;
+    }
 }
 
 }  // namespace bbb

@@ -37,6 +37,9 @@ __host__ __device__ inline double words_to_double(uint32_t w0, uint32_t w1) {
 }
 
 struct Rng {
+    // warp-cooperative mode: the 32 lanes of a warp work on ONE chain; lane 0 owns the generator and every
+    // draw is broadcast, so all lanes follow the same control flow with the same values
+    bool coop = false;
     // philox state
     uint32_t k0, k1, chain, it_lo, it_hi;
     uint32_t n;        // draws consumed in this (chain, iteration)
@@ -63,7 +66,7 @@ struct Rng {
         n = 0;
         blk = 0xFFFFFFFFu;
     }
-    __device__ double u() {
+    __device__ double raw_u() {
         if (tape != nullptr) {
             ++n;
             return tape[cursor++];
@@ -76,6 +79,13 @@ struct Rng {
         const uint32_t h = (n & 1u) * 2u;
         ++n;
         return words_to_double(w[h], w[h + 1]);
+    }
+    __device__ double u() {
+        if (!coop) return raw_u();
+        double v = 0.0;
+        if ((threadIdx.x & 31) == 0) v = raw_u();
+        else { ++n; ++cursor; }
+        return __shfl_sync(0xffffffffu, v, 0);
     }
     // random.random() restated: (0, 1]
     __device__ double unit() { return 1.0 - u(); }

@@ -24,14 +24,18 @@ __device__ __forceinline__ void rng_end(const Rng &rng, const EngineParams &ep, 
     B.tape_cursor[c] = (B.tape != nullptr) ? rng.cursor : (long long)rng.n;
 }
 
-__global__ void __launch_bounds__(STEP_THREADS) k_propose(const EngineParams *epp) {
+// One WARP per chain: lane 0 owns the generator (every draw is broadcast), the O(k) nearest-site searches of
+// birth/death-from-neighbour run with lanes = sites, and the proposed slot is written by k_apply_edit.
+constexpr int PROPOSE_WARPS = 4;
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const EngineParams *epp) {
     const EngineParams &ep = *epp;
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c = (long long)blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
     if (c >= ep.buf.n_chains) return;
     Rng rng;
     rng_begin(rng, ep, c, STREAM_STEP, false);
+    rng.coop = true;
     propose_chain(ep.spec, ep.buf, c, rng, false);
-    rng_end(rng, ep, c);
+    if ((threadIdx.x & 31) == 0) rng_end(rng, ep, c);
 }
 
 // Writes the proposed slot of space `s` from the published edit scripts: one thread per
@@ -341,7 +345,7 @@ __global__ void k_phi_from_partial(const double *partial, int n_tiles, long long
 static inline int blocks_for(long long C, int threads) { return (int)((C + threads - 1) / threads); }
 
 int launch_propose(const EngineParams *p, long long C, cudaStream_t st) {
-    k_propose<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p);
+    k_propose<<<blocks_for(C, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
 int launch_apply_edit(const EngineParams *p, long long C, int space, int kmax, cudaStream_t st) {
