@@ -48,6 +48,8 @@ class Engine:
         L.check(self.lib.bbb_engine_create(C.byref(self._cspec), self.dev_index, C.byref(self._handle)))
         self._alloc(tape)
         L.check(self.lib.bbb_engine_bind_buffers(self._handle, C.byref(self._cbuf)))
+        self._steps_since_sync = 0
+        self._has_ray = any(t["forward"]["kind"] == "ray2d" for t in spec["targets"])
 
     # ------------------------------------------------------------------ spec / buffers
     def _const(self, arr, dtype):
@@ -209,12 +211,38 @@ class Engine:
 
     def refresh(self):
         L.check(self.lib.bbb_engine_refresh(self._handle, self._stream))
+        self._steps_since_sync = self.K_BOUND_RESYNC  # the engine forgot its bound: tighten before the next step
+
+    K_BOUND_RESYNC = 64  # steps between two tightenings of the engine's bound on max k (one tiny D2H sync each)
 
     def step(self, n_steps: int = 1):
-        L.check(self.lib.bbb_engine_step(self._handle, int(n_steps), self._stream))
+        n_steps = int(n_steps)
+        while n_steps > 0:
+            if self._steps_since_sync >= self.K_BOUND_RESYNC:
+                self.sync_k_bound()
+            n = min(n_steps, self.K_BOUND_RESYNC - self._steps_since_sync)
+            L.check(self.lib.bbb_engine_step(self._handle, n, self._stream))
+            self._steps_since_sync += n
+            n_steps -= n
+
+    def sync_k_bound(self):
+        """Tell the engine the true maximum of k over the resident chains (it only knows an upper bound that
+        grows by one per step); shared-memory staging of the tomography kernels is sized by it."""
+        self._steps_since_sync = 0
+        if not self._has_ray:
+            return
+        for s, sp in enumerate(self.spec["spaces"]):
+            if sp["trans_d"]:
+                sel = self.sel[s].long()
+                kcur = torch.where(sel == 0, self.k[s][0], self.k[s][1])
+                L.check(self.lib.bbb_engine_set_k_bound(self._handle, s, int(kcur.max().item())))
 
     def stage(self, stage: int):
         """One stage of one step (0 propose, 1 raster, 2 ray forward + misfit, 3 accept)."""
+        if stage == 0:
+            if self._steps_since_sync >= self.K_BOUND_RESYNC:
+                self.sync_k_bound()
+            self._steps_since_sync += 1
         L.check(self.lib.bbb_engine_stage(self._handle, int(stage), self._stream))
 
     def set_annealing(self, temperature_start, cooling_rate, cooling_iterations, burnin_iterations):

@@ -87,6 +87,7 @@ SYMBOLS = {
     "bbb_engine_destroy": (None, [_vp]),
     "bbb_engine_init_states": (C.c_int, [_vp, _vp]),
     "bbb_engine_refresh": (C.c_int, [_vp, _vp]),
+    "bbb_engine_set_k_bound": (C.c_int, [_vp, C.c_int, _i32]),
     "bbb_engine_step": (C.c_int, [_vp, _i64, _vp]),
     "bbb_engine_stage": (C.c_int, [_vp, C.c_int, _vp]),
     "bbb_engine_set_annealing": (C.c_int, [_vp, C.c_double, C.c_double, _i64, _i64]),

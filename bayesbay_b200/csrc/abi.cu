@@ -35,6 +35,7 @@ struct bbb_engine {
     bool bound;
     bool has_ray;
     int n_sm;
+    int k_bound[BBB_MAX_SPACES];  // host-side upper bound of max_c k[s][c] (grows by one per step, tightened by the caller)
     bool brute_force;  // BBB_BRUTE_FORCE_RASTER=1: re-rasterise every proposal from scratch (reference behaviour)
 };
 
@@ -126,6 +127,7 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
         e->brute_force = bf != nullptr && bf[0] == '1';
     }
     for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
+    for (int s = 0; s < BBB_MAX_SPACES; ++s) e->k_bound[s] = s < spec->n_spaces ? spec->spaces[s].kmax : 0;
     e->n_sm = 148;
     cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
     int err = (int)cudaMalloc(&e->dev, sizeof(EngineParams));
@@ -190,6 +192,7 @@ static int run_raster(bbb_engine *e, int t, bool proposal, cudaStream_t st) {
     a.sites = B.sites[T.space];
     a.k = B.k[T.space];
     a.K = S.kmax;
+    a.k_rows = proposal ? (e->k_bound[T.space] + 1 < S.kmax ? e->k_bound[T.space] + 1 : S.kmax) : S.kmax;
     a.C = B.n_chains;
     a.sel = B.sel[T.space];
     a.idx_sel = B.idx_sel[t];
@@ -260,7 +263,16 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
     a.space = T.space;
     a.dpred = dpred;
     a.partial = write_partial ? B.partial[t] : nullptr;
-    a.n_groups = e->host.n_partial[t];
+    // the value table holds k_rows cells per chain; a tighter bound allows more chains per lane
+    a.k_rows = proposal ? (e->k_bound[T.space] + 1 < S.kmax ? e->k_bound[T.space] + 1 : S.kmax) : e->k_bound[T.space];
+    a.n_groups = spmm_ray_groups(a.R, a.C, a.k_rows, a.idx_bytes, e->n_sm);
+    if (a.n_groups == 0) return (int)cudaErrorInvalidConfiguration;
+    if (write_partial && a.n_groups != e->host.n_partial[t]) {
+        // the accept stage sums partial[0 .. n_partial): keep the device copy in step (stream ordered)
+        e->host.n_partial[t] = a.n_groups;
+        int rc = (int)cudaMemcpyAsync(&e->dev->n_partial[t], &e->host.n_partial[t], sizeof(int), cudaMemcpyHostToDevice, st);
+        if (rc != 0) return rc;
+    }
     return launch_ray_spmm(a, st);
 }
 
@@ -275,6 +287,7 @@ int bbb_engine_refresh(bbb_engine *e, void *stream) {
     NEED_BOUND(e);
     cudaStream_t st = (cudaStream_t)stream;
     const bbb_problem_spec &P = e->host.spec;
+    for (int s = 0; s < P.n_spaces; ++s) e->k_bound[s] = P.spaces[s].kmax;  // caller-written states: no knowledge
     for (int t = 0; t < P.n_targets; ++t) {
         if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
         CU(run_raster(e, t, false, st));
@@ -287,7 +300,21 @@ int bbb_engine_refresh(bbb_engine *e, void *stream) {
 int bbb_engine_init_states(bbb_engine *e, void *stream) {
     NEED_BOUND(e);
     CU(launch_init_states(e->dev, e->host.buf.n_chains, (cudaStream_t)stream));
-    return bbb_engine_refresh(e, stream);
+    int rc = bbb_engine_refresh(e, stream);
+    for (int s = 0; s < e->host.spec.n_spaces; ++s) {
+        const bbb_space_spec &S = e->host.spec.spaces[s];
+        e->k_bound[s] = S.trans_d ? S.kinit_max : S.kmin;  // the initialisation kernel draws k <= kinit_max
+    }
+    return rc;
+}
+
+int bbb_engine_set_k_bound(bbb_engine *e, int space, int32_t bound) {
+    if (!e) return fail(BBB_ERR_INVALID, "NULL engine");
+    if (space < 0 || space >= e->host.spec.n_spaces) return fail(BBB_ERR_INVALID, "space index");
+    const bbb_space_spec &S = e->host.spec.spaces[space];
+    if (bound < S.kmin || bound > S.kmax) return fail(BBB_ERR_INVALID, "bound outside [kmin, kmax]");
+    e->k_bound[space] = bound;
+    return BBB_OK;
 }
 
 int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
@@ -308,6 +335,8 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
             CU(run_spmm(e, t, true, nullptr, true, st));
         }
         CU(launch_finish(e->dev, C, st));
+        for (int s = 0; s < P.n_spaces; ++s)
+            if (e->k_bound[s] < P.spaces[s].kmax) ++e->k_bound[s];  // a step adds at most one cell
     }
     return BBB_OK;
 }
@@ -328,7 +357,11 @@ int bbb_engine_stage(bbb_engine *e, int stage, void *stream) {
             for (int t = 0; t < P.n_targets; ++t)
                 if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) CU(run_spmm(e, t, true, nullptr, true, st));
             break;
-        case 3: CU(launch_finish(e->dev, C, st)); break;
+        case 3:
+            CU(launch_finish(e->dev, C, st));
+            for (int s = 0; s < P.n_spaces; ++s)
+                if (e->k_bound[s] < P.spaces[s].kmax) ++e->k_bound[s];
+            break;
         default: return fail(BBB_ERR_INVALID, "stage must be 0..3");
     }
     return BBB_OK;
@@ -395,6 +428,7 @@ int bbb_raster2d(const double *sites, const int32_t *k, int32_t K, int64_t C, co
     a.sites = sites;
     a.k = k;
     a.K = K;
+    a.k_rows = K;
     a.C = C;
     a.px = points_x;
     a.py = points_y;
@@ -431,6 +465,7 @@ int bbb_ray_forward(const void *idx, const double *values, const int32_t *k, int
     a.n_params = 1;
     a.param = 0;
     a.K = K;
+    a.k_rows = K;
     a.C = C;
     a.G = G;
     a.R = R;

@@ -10,7 +10,8 @@ namespace bbb {
 struct RasterArgs {
     const double *sites;      // [slots][2][K][C]
     const int32_t *k;         // [slots][C]
-    int K;
+    int K;                    // pad of the site arrays (n_dimensions_max)
+    int k_rows;               // upper bound of k over the chains (<= K): sizes the shared-memory staging
     long long C;
     const uint8_t *sel;       // [C] or nullptr (slot 0)
     const uint8_t *idx_sel;   // [C] or nullptr (slot 0)
@@ -38,6 +39,7 @@ struct SpmmArgs {
     const uint8_t *sel;       // [C] or nullptr
     int slot_xor;
     int n_params, param, K;
+    int k_rows;               // upper bound of k over the chains (<= K): picks the chains-per-lane variant
     long long C;
     int G, R;
     const int32_t *indptr, *indices;

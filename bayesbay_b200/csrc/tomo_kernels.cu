@@ -126,7 +126,7 @@ k_raster2d_inc(RasterArgs a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kmax_blk = max(kmax_blk, __shfl_xor_sync(0xffffffffu, kmax_blk, o));
     double *tx = s_sites + lane;
-    double *ty = s_sites + (long long)a.K * 32 + lane;
+    double *ty = s_sites + (long long)a.k_rows * 32 + lane;
     if (STAGE) {
         for (int j = warp; j < kmax_blk; j += RASTER_WARPS) {
             tx[j * 32] = (j < k_new) ? sx[(long long)j * a.C] : 0.0;
@@ -215,7 +215,7 @@ k_raster2d_rescan(RasterArgs a) {
     const double *sy = a.sites + ((long long)prop * 2 + 1) * a.K * a.C + c;
     for (int j = threadIdx.x; j < k_new; j += blockDim.x) {
         s_xy[j] = sx[(long long)j * a.C];
-        s_xy[a.K + j] = sy[(long long)j * a.C];
+        s_xy[a.k_rows + j] = sy[(long long)j * a.C];
     }
     __syncthreads();
     IdxT *slot1 = reinterpret_cast<IdxT *>(a.idx) + (long long)a.G * a.C + c;
@@ -226,16 +226,17 @@ k_raster2d_rescan(RasterArgs a) {
         double best = INFINITY;
         int bi = 0x7fffffff;
         for (int j = lane; j < k_new; j += 32) {
-            const double dx = s_xy[j] - gx, dy = s_xy[a.K + j] - gy;
+            const double dx = s_xy[j] - gx, dy = s_xy[a.k_rows + j] - gy;
             const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
             if (d < best) { best = d; bi = j; }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oj = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (od < best || (od == best && oj < bi)) { best = od; bi = oj; }
-        }
+        // lexicographic (distance, index) minimum over the warp with three REDUX steps: non-negative doubles
+        // order like their bit patterns, so min the high word, then the low word among the lanes that hold the
+        // minimal high word, then the index among the lanes that hold the minimal distance
+        const unsigned hi = (unsigned)__double2hiint(best), lo = (unsigned)__double2loint(best);
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+        bi = (int)__reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? (unsigned)bi : 0xffffffffu);
         if (lane == 0) slot1[(long long)g * a.C] = (IdxT)bi;
     }
 }
@@ -304,8 +305,8 @@ int launch_idx_commit_copy(void *idx, int idx_bytes, const uint8_t *idx_sel, int
 
 template <typename IdxT>
 static int launch_inc_variant(const RasterArgs &a, dim3 grid, cudaStream_t stream) {
-    const size_t smem = (size_t)a.K * 32 * 2 * sizeof(double);
-    if (smem <= 100 * 1024) {  // two resident blocks per SM
+    const size_t smem = (size_t)a.k_rows * 32 * 2 * sizeof(double);  // rows = upper bound of k over the chains
+    if (smem <= 100 * 1024) {  // at least two resident blocks per SM
         if (smem > 48 * 1024) {
             cudaError_t err = cudaFuncSetAttribute(k_raster2d_inc<IdxT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (err != cudaSuccess) return (int)err;
@@ -322,7 +323,7 @@ int launch_raster2d_inc(const RasterArgs &a, cudaStream_t stream) {
     dim3 grid(chain_tiles, (a.G + a.points_per_block - 1) / a.points_per_block);
     int rc = a.idx_bytes == 1 ? launch_inc_variant<uint8_t>(a, grid, stream) : launch_inc_variant<uint16_t>(a, grid, stream);
     if (rc != 0) return rc;
-    const size_t smem = (size_t)a.K * 2 * sizeof(double);
+    const size_t smem = (size_t)a.k_rows * 2 * sizeof(double);
     dim3 rgrid((unsigned)a.C, RESCAN_SPLIT);
     if (a.idx_bytes == 1) k_raster2d_rescan<uint8_t><<<rgrid, RESCAN_WARPS * 32, smem, stream>>>(a);
     else k_raster2d_rescan<uint16_t><<<rgrid, RESCAN_WARPS * 32, smem, stream>>>(a);
@@ -571,7 +572,7 @@ static int launch_spmm_variant(const SpmmArgs &a, cudaStream_t stream) {
 
 int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream) {
     if ((long long)a.G * a.C * a.idx_bytes * 2 / 4 >= (1LL << 32)) return (int)cudaErrorInvalidConfiguration;
-    const int cpl = spmm_cpl(a.K, a.C, a.idx_bytes);
+    const int cpl = spmm_cpl(a.k_rows, a.C, a.idx_bytes);
     if (a.idx_bytes == 1) {
         if (cpl == 4) return launch_spmm_variant<uint8_t, 4>(a, stream);
         if (cpl == 1) return launch_spmm_variant<uint8_t, 1>(a, stream);

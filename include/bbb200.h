@@ -167,6 +167,11 @@ int bbb_engine_init_states(bbb_engine *e, void *stream);
 /* Re-evaluate rasterisation, forward and misfit of the CURRENT states (after the caller wrote
  * starting states, temperatures, ... into the bound buffers). */
 int bbb_engine_refresh(bbb_engine *e, void *stream);
+/* Performance hint: an upper bound of the current number of cells over all resident chains of `space`
+ * (kmin <= bound <= kmax).  The engine sizes shared-memory staging by it and raises it by one per step on its
+ * own; callers may tighten it with the true maximum of k at a synchronisation point.  A bound BELOW the
+ * true maximum is an error the engine cannot detect. */
+int bbb_engine_set_k_bound(bbb_engine *e, int space, int32_t bound);
 /* Advance every chain n_steps iterations: `BaseMarkovChain.advance_chain`
  * (src/bayesbay/_markov_chain.py:249-297) for all chains at once. */
 int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream);
