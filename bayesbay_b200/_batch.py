@@ -92,6 +92,28 @@ def host_dict_to_state(spec: dict, d: dict, temperature=1.0, state_cls=State, ps
     return state_cls(pv, temperature=float(temperature))
 
 
+def save_schedule(iteration: int, n_iterations: int, burnin_iterations: int, save_every: int):
+    """Split ``n_iterations`` (starting after ``iteration`` completed ones) into device launches
+    ``[(n_steps, save_after), ...]`` that stop exactly where the reference saves: iteration ``i`` (1-based,
+    counted over the chain's whole life) is saved iff ``i > burnin_iterations`` and
+    ``(i - burnin_iterations) % save_every == 0`` (src/bayesbay/_markov_chain.py:284-289)."""
+    if save_every < 1:
+        raise ValueError("save_every must be at least 1")
+    out = []
+    done = 0
+    while done < n_iterations:
+        i_next = iteration + done + 1
+        if i_next <= burnin_iterations:
+            to_save = burnin_iterations + save_every - i_next
+        else:
+            r = (i_next - burnin_iterations) % save_every
+            to_save = 0 if r == 0 else save_every - r
+        n = min(n_iterations - done, to_save + 1)
+        out.append((n, n == to_save + 1))
+        done += n
+    return out
+
+
 # --------------------------------------------------------------------------- #
 # the batch
 # --------------------------------------------------------------------------- #
@@ -114,6 +136,7 @@ class ChainBatch:
         self.engine = Engine(spec, self.n_chains, device=device, seed=self.seed, chain_id0=chain_id0)
         self.names = _compile.perturbation_names(spec)
         self.iteration = 0
+        self.swap_round = 0
         self.saved: List[dict] = []  # one entry per save point: host arrays + mask of chains saved
         self._torch = torch
         if starting_states is None:
@@ -129,24 +152,27 @@ class ChainBatch:
     def temperatures(self) -> np.ndarray:
         return self.engine.temperature.cpu().numpy()
 
+    # ---- checkpoint / resume ---------------------------------------------
+    def state_dict(self) -> dict:
+        return dict(engine=self.engine.state_dict(), iteration=self.iteration, saved=self.saved,
+                    swap_round=self.swap_round, seed_global=getattr(self, "seed_global", self.seed))
+
+    def load_state_dict(self, state: dict):
+        self.engine.load_state_dict(state["engine"])
+        self.iteration = int(state["iteration"])
+        self.swap_round = int(state.get("swap_round", 0))
+        self.saved = list(state["saved"])
+        self.seed_global = state["seed_global"]
+
     # ---- advancing -------------------------------------------------------
     def advance(self, n_iterations: int, burnin_iterations: int = 0, save_every: int = 100):
         """``BaseMarkovChain.advance_chain`` for all chains (src/bayesbay/_markov_chain.py:249-297):
         iteration ``i`` (1-based, global) is saved iff ``i > burnin`` and ``(i - burnin) % save_every == 0``
         and the chain's temperature is 1 (``_next_iteration`` :241-242)."""
-        done = 0
-        while done < n_iterations:
-            i_next = self.iteration + 1
-            if i_next <= burnin_iterations:
-                to_save = burnin_iterations + save_every - i_next
-            else:
-                r = (i_next - burnin_iterations) % save_every
-                to_save = 0 if r == 0 else save_every - r
-            n = min(n_iterations - done, to_save + 1)
+        for n, save in save_schedule(self.iteration, n_iterations, burnin_iterations, save_every):
             self.engine.step(n)
             self.iteration += n
-            done += n
-            if n == to_save + 1:
+            if save:
                 self._save()
 
     def _save(self):

@@ -160,6 +160,23 @@ class BayesianInversion(BaseBayesianInversion):
         if states:
             self._dirty = False
 
+    # ---- checkpoint / resume (the reference has none) ------------------------
+    def save_checkpoint(self, path):
+        """Write this rank's chains (device state, iteration counter, samples saved so far) to ``path``."""
+        import torch
+
+        torch.save(self.batch.state_dict(), path)
+
+    def load_checkpoint(self, path):
+        """Continue bit-identically from :meth:`save_checkpoint` (same problem, n_chains, seed and sharding)."""
+        import torch
+
+        self.batch.load_state_dict(torch.load(path, weights_only=False))
+        self._n_saved_synced = 0
+        for ch in self._chains:
+            ch._saved_states.clear()
+        self._mark_dirty()
+
     def all_gather(self, local):
         """[C_local][3] -> [C_total][3] in global chain order (NCCL all-gather over NVLink when sharded)."""
         return _dist.all_gather(local)

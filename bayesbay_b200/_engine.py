@@ -334,6 +334,41 @@ class Engine:
                 out[c]["sigma"].append(None if sg is None else float(sg[c]))
         return out
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def _mutable(self):
+        named = {"temperature": self.temperature, "iteration": self.iteration, "n_proposed": self.n_proposed,
+                 "n_accepted": self.n_accepted, "draw_cursor": self.draw_cursor, "move": self.move, "edit": self.edit,
+                 "log_prob_ratio": self.log_prob_ratio, "log_like_ratio": self.log_like_ratio, "accepted": self.accepted}
+        for i in range(len(self.spec["spaces"])):
+            named.update({f"sites{i}": self.sites[i], f"values{i}": self.values[i], f"k{i}": self.k[i], f"sel{i}": self.sel[i]})
+        for i in range(len(self.spec["targets"])):
+            named.update({f"sigma{i}": self.sigma[i], f"phi{i}": self.phi[i], f"cell_idx{i}": self.cell_idx[i],
+                          f"idx_sel{i}": self.idx_sel[i]})
+        return {k: v for k, v in named.items() if v is not None}
+
+    def state_dict(self) -> dict:
+        """Everything needed to continue the chains bit-identically (the Philox counters are the per-chain
+        iteration numbers, so no generator state has to be saved)."""
+        torch.cuda.synchronize(self.device)
+        out = {k: v.cpu() for k, v in self._mutable().items()}
+        out["_meta"] = dict(n_chains=self.C, seed=self.seed, chain_id0=self.chain_id0)
+        return out
+
+    def load_state_dict(self, state: dict):
+        meta = state["_meta"]
+        if meta["n_chains"] != self.C:
+            raise ValueError(f"checkpoint holds {meta['n_chains']} chains, this engine {self.C}")
+        if meta["seed"] != self.seed or meta["chain_id0"] != self.chain_id0:
+            raise ValueError("checkpoint was written with a different seed / chain shard")
+        for k, v in self._mutable().items():
+            if tuple(state[k].shape) != tuple(v.shape) or state[k].dtype != v.dtype:
+                raise ValueError(f"checkpoint buffer {k!r} does not match this problem")
+            v.copy_(state[k])
+        for s, sp in enumerate(self.spec["spaces"]):
+            L.check(self.lib.bbb_engine_set_k_bound(self._handle, s, sp["kmax"]))
+        self._steps_since_sync = self.K_BOUND_RESYNC
+        torch.cuda.synchronize(self.device)
+
     def close(self):
         if self._handle:
             self.lib.bbb_engine_destroy(self._handle)

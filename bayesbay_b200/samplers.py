@@ -151,8 +151,11 @@ class ParallelTempering(Sampler):
         gathered = owner.all_gather(local)
         from ._engine import pt_swap
 
-        t_out, n_acc = pt_swap(gathered, owner.batch.seed_global, self._round, owner.chain_id0, owner.batch.n_chains)
+        # the round number (Philox counter of the swap stream) lives with the chains so that it is checkpointed
+        t_out, n_acc = pt_swap(gathered, owner.batch.seed_global, owner.batch.swap_round, owner.chain_id0,
+                               owner.batch.n_chains)
         owner.batch.engine.temperature.copy_(t_out)
+        owner.batch.swap_round += 1
         self._round += 1
         self._last_n_acc = n_acc
 

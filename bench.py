@@ -215,6 +215,8 @@ def cuda_arm(args):
         warm_ms = float(t.item())
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) -----------------------------
+    # stages of bbb_engine_stage: 0 = k_propose + k_apply_edit, 1 = k_idx_commit_copy + k_raster2d_inc +
+    # k_raster2d_rescan, 2 = k_ray_spmm, 3 = k_finish  (7 kernel launches per step)
     names = ["propose", "raster2d", "ray_spmm", "finish"]
     stage_ms = np.zeros(4)
     active_fwd = 0
@@ -285,7 +287,7 @@ def cuda_arm(args):
         "wall_s_timed_region": wall,
         "clocks": {k: clk[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clk else None,
         "e2e": e2e,
-        "gpu_launches": 4 * args.steps + (n_swaps if tempered else 0),
+        "gpu_launches": 7 * args.steps + (2 * n_swaps if tempered else 0),
         "kernel_ms": {n: float(v) for n, v in zip(names, stage_ms)},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

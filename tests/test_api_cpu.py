@@ -192,3 +192,37 @@ def test_synthetic_ray_matrix_is_exact():
     rcv = np.array([[0.7, 0.9]])
     ip, ix, dt = synthetic.straight_ray_csr(src, rcv, 12, 10, normalise=False)
     np.testing.assert_allclose(dt.sum(), np.hypot(1.7, 1.2), rtol=1e-13)
+
+
+def test_save_schedule_follows_the_reference_rule():
+    """Launch splitting vs a literal replay of BaseMarkovChain.advance_chain (_markov_chain.py:284-289)."""
+    from bayesbay_b200._batch import save_schedule
+
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        it0, n, burnin, every = int(rng.integers(0, 50)), int(rng.integers(0, 120)), int(rng.integers(0, 80)), int(rng.integers(1, 25))
+        want = []
+        i = it0
+        for _ in range(n):
+            i += 1
+            if i > burnin and (i - burnin) % every == 0:
+                want.append(i)
+        got, i = [], it0
+        sched = save_schedule(it0, n, burnin, every)
+        for steps, save in sched:
+            assert steps >= 1
+            i += steps
+            if save:
+                got.append(i)
+        assert i == it0 + n and got == want
+        assert all(save for _, save in sched[:-1])  # only the last launch may stop short of a save point
+    # ParallelTempering.run quirk Q3: burn-in 1500 handed over window-relative (500) -> T=1 chains save from 600 on
+    saves, it = [], 0
+    for n_it, burnin_it in ((500, 500), (500, 500), (500, 500), (500, 0), (0, 0)):
+        for steps, save in save_schedule(it, n_it, burnin_it, 100):
+            it += steps
+            if save:
+                saves.append(it)
+    assert saves[0] == 600 and saves[-1] == 2000 and len(saves) == 15
+    with pytest.raises(ValueError):
+        save_schedule(0, 10, 0, 0)
