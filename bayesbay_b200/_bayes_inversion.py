@@ -142,23 +142,21 @@ class BayesianInversion(BaseBayesianInversion):
             ch._current_state = None
 
     def _sync_chains(self, states: bool = True):
-        """Refresh the per-chain views (statistics, saved states, current state, temperature)."""
-        if not self._dirty and (not states or self._chains[0]._current_state is not None):
-            return
-        stats = self.batch.statistics()
-        temps = self.batch.temperatures()
-        cur = self.batch.current_states() if states else None
-        start = self._n_saved_synced
-        for c, ch in enumerate(self._chains):
-            ch._statistics = stats[c]
-            ch._temperature = float(temps[c])
-            for key, vals in self.batch.saved_states_of(c, start).items():
-                ch._saved_states[key].extend(vals)
-            if cur is not None:
-                ch._current_state = cur[c]
-        self._n_saved_synced = len(self.batch.saved)
-        if states:
-            self._dirty = False
+        """Refresh the per-chain views (statistics, saved states, temperature; current state on request)."""
+        if self._dirty:
+            self._dirty = False  # first: the chain properties below consult it
+            stats = self.batch.statistics()
+            temps = self.batch.temperatures()
+            start = self._n_saved_synced
+            for c, ch in enumerate(self._chains):
+                ch._statistics = stats[c]
+                ch._temperature = float(temps[c])
+                for key, vals in self.batch.saved_states_of(c, start).items():
+                    ch._saved_states[key].extend(vals)
+            self._n_saved_synced = len(self.batch.saved)
+        if states and self._chains and self._chains[0]._current_state is None:
+            for ch, st in zip(self._chains, self.batch.current_states()):
+                ch._current_state = st
 
     # ---- checkpoint / resume (SURVEY.md section 8f rank 4; the reference has none) ------------------------
     def save_checkpoint(self, path):

@@ -38,10 +38,14 @@ class BaseMarkovChain:
         self.perturbation_types = [f.__name__ for f in funcs]
         self.perturbation_weights = weights
 
+    def _ensure_synced(self, states=False):
+        owner = getattr(self, "_batch_owner", None)
+        if owner is not None and (owner._dirty or (states and self._current_state is None)):
+            owner._sync_chains(states=states)
+
     @property
     def current_state(self):
-        if self._current_state is None and self._batch is not None:
-            self._batch_owner._sync_chains()
+        self._ensure_synced(states=True)
         return self._current_state
 
     @current_state.setter
@@ -51,6 +55,7 @@ class BaseMarkovChain:
     @property
     def temperature(self):
         """The current temperature used in the log likelihood ratio"""
+        self._ensure_synced()
         return self._temperature
 
     @temperature.setter
@@ -62,10 +67,12 @@ class BaseMarkovChain:
     @property
     def saved_states(self):
         """All the states saved so far"""
+        self._ensure_synced()
         return self._saved_states
 
     @property
     def statistics(self):
+        self._ensure_synced()
         return self._statistics
 
     @property
