@@ -139,6 +139,15 @@ class ChainBatch:
         self.swap_round = 0
         self.saved: List[dict] = []  # one entry per save point: host arrays + mask of chains saved
         self._torch = torch
+        # posterior field statistics of ray targets that ask for them (per chain: sum, sum of squares, count)
+        self.field_stats = {}
+        for t, tg in enumerate(spec["targets"]):
+            f = tg["forward"]
+            if f["kind"] == "ray2d" and f.get("save_field_as"):
+                G = int(np.asarray(f["points"]).shape[0])
+                z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.engine.device)  # noqa: E731
+                self.field_stats[t] = dict(name=f["save_field_as"], store=bool(f.get("store_field_samples", True)),
+                                           sum=z(G, self.n_chains), sumsq=z(G, self.n_chains), count=z(self.n_chains))
         if starting_states is None:
             self.engine.init_states()
         else:
@@ -154,7 +163,8 @@ class ChainBatch:
 
     # ---- checkpoint / resume ---------------------------------------------
     def state_dict(self) -> dict:
-        return dict(engine=self.engine.state_dict(), iteration=self.iteration, saved=self.saved,
+        fields = {t: {k: (v.cpu() if hasattr(v, "cpu") else v) for k, v in fs.items()} for t, fs in self.field_stats.items()}
+        return dict(engine=self.engine.state_dict(), iteration=self.iteration, saved=self.saved, field_stats=fields,
                     swap_round=self.swap_round, seed_global=getattr(self, "seed_global", self.seed))
 
     def load_state_dict(self, state: dict):
@@ -163,6 +173,9 @@ class ChainBatch:
         self.swap_round = int(state.get("swap_round", 0))
         self.saved = list(state["saved"])
         self.seed_global = state["seed_global"]
+        for t, fs in state.get("field_stats", {}).items():
+            for key in ("sum", "sumsq", "count"):
+                self.field_stats[t][key].copy_(fs[key])
 
     # ---- advancing -------------------------------------------------------
     def advance(self, n_iterations: int, burnin_iterations: int = 0, save_every: int = 100):
@@ -181,7 +194,18 @@ class ChainBatch:
         mask = temps == 1.0
         if not mask.any():
             return
-        entry = dict(mask=mask, spaces=[], sigma=[], dpred=[])
+        entry = dict(mask=mask, spaces=[], sigma=[], dpred=[], fields={})
+        for t, fs in self.field_stats.items():
+            # rasterised field of the current states: cell value looked up through the resident nearest-site index
+            f = self.spec["targets"][t]["forward"]
+            _, _, vals = eng.gather_space(f["space"])
+            field = self._torch.gather(vals[f["param"]], 0, eng.current_cell_idx(t).long() & 0xFFFF)  # [G][C]
+            m = self._torch.as_tensor(mask, device=field.device)
+            fs["sum"] += field * m
+            fs["sumsq"] += field * field * m
+            fs["count"] += m
+            if fs["store"]:
+                entry["fields"][fs["name"]] = field.cpu().numpy()
         for s in range(len(self.spec["spaces"])):
             k, sites, vals = eng.gather_space(s)
             entry["spaces"].append((k.cpu().numpy(), None if sites is None else sites.cpu().numpy(),
@@ -216,6 +240,8 @@ class ChainBatch:
             for tg, dp in zip(self.spec["targets"], entry["dpred"]):
                 if dp is not None:
                     out[f"{tg['name']}.dpred"].append(dp[:, c].copy())
+            for name, field in entry.get("fields", {}).items():
+                out[name].append(field[:, c].copy())
         return out
 
     def statistics(self):
@@ -245,6 +271,19 @@ class ChainBatch:
                 "exceptions": defaultdict(int),
             })
         return out
+
+    def field_statistics(self, name: str) -> dict:
+        """Posterior statistics of a saved field accumulated on the device over the saved (T = 1) samples:
+        ``mean`` / ``std`` [G] over all samples, ``chain_mean`` [C][G], ``count`` [C]."""
+        for fs in self.field_stats.values():
+            if fs["name"] == name:
+                n = fs["count"].sum().clamp(min=1)
+                mean = fs["sum"].sum(1) / n
+                var = (fs["sumsq"].sum(1) / n - mean * mean).clamp(min=0)
+                chain_mean = (fs["sum"] / fs["count"].clamp(min=1)).T
+                return dict(mean=mean.cpu().numpy(), std=var.sqrt().cpu().numpy(), chain_mean=chain_mean.cpu().numpy(),
+                            count=fs["count"].cpu().numpy())
+        raise KeyError(f"no forward operator saves a field named {name!r}")
 
     def current_states(self, **classes) -> List[State]:
         temps = self.temperatures()

@@ -158,6 +158,11 @@ class BayesianInversion(BaseBayesianInversion):
             for ch, st in zip(self._chains, self.batch.current_states()):
                 ch._current_state = st
 
+    def get_field_statistics(self, name: str) -> dict:
+        """Posterior mean / standard deviation map of a field a forward operator saves (``save_field_as``),
+        accumulated on the device over this rank's saved samples (no per-sample storage needed)."""
+        return self.batch.field_statistics(name)
+
     # ---- checkpoint / resume (SURVEY.md section 8f rank 4; the reference has none) ------------------------
     def save_checkpoint(self, path):
         """Write this rank's chains (device state, iteration counter, samples saved so far) to ``path``."""

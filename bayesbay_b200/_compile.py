@@ -121,6 +121,8 @@ def compile_target(tgt, fwd, space_index: dict, spaces: list) -> dict:
             raise ValueError("RayTomographyForward needs a Voronoi2D parameter space")
         spec["forward"] = dict(kind="ray2d", space=s, param=pnames.index(fwd.param_name), transform=fwd.transform,
                                indptr=fwd.indptr, indices=fwd.indices, data=fwd.data, points=fwd.grid_points)
+        if getattr(fwd, "save_field_as", None):
+            spec["forward"].update(save_field_as=fwd.save_field_as, store_field_samples=fwd.store_field_samples)
     elif kind == "lookup1d":
         if sp["kind"] != "voronoi1d":
             raise ValueError("NearestLookup1D needs a Voronoi1D parameter space")

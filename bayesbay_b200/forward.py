@@ -48,11 +48,20 @@ class RayTomographyForward(ForwardOperator):
         the Voronoi2D space and the parameter holding the cell values
     transform : {"reciprocal", "identity"}
         ``"reciprocal"`` multiplies the ray matrix with ``1 / value`` (velocity -> slowness)
+    save_field_as : str, optional
+        the tutorial's forward stores the rasterised field with ``state.save_to_extra_storage('interp_vel', ...)``
+        so that it shows up in ``get_results()``; give the key (e.g. ``"interp_vel"``) to get the same entry.
+        Running sums for the posterior mean / standard deviation map are kept on the device either way
+        (``BayesianInversion.get_field_statistics``).
+    store_field_samples : bool
+        keep every saved field (G doubles per chain per save point, as the reference does) in the results;
+        switch off for large runs and use the on-device statistics instead
     """
 
     kind = "ray2d"
 
-    def __init__(self, jacobian, grid_points, param_space_name="voronoi", param_name="vel", transform="reciprocal"):
+    def __init__(self, jacobian, grid_points, param_space_name="voronoi", param_name="vel", transform="reciprocal",
+                 save_field_as=None, store_field_samples=True):
         if isinstance(jacobian, (tuple, list)):
             indptr, indices, data = jacobian
         else:
@@ -74,6 +83,8 @@ class RayTomographyForward(ForwardOperator):
         self.param_space_name = param_space_name
         self.param_name = param_name
         self.transform = transform
+        self.save_field_as = save_field_as
+        self.store_field_samples = bool(store_field_samples)
 
     @property
     def n_data(self):

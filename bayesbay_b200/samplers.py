@@ -87,6 +87,7 @@ class Sampler(ABC):
             owner.batch.advance(n, burnin_iterations, save_every)
             done += n
             if verbose and owner.batch.iteration % print_every == 0:
+                owner._mark_dirty()
                 owner._sync_chains(states=False)
                 for ch in self._chains:
                     ch.print_statistics()

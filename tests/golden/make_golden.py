@@ -182,6 +182,7 @@ def reference_forward(ing):
             kdtree = voronoi.load_from_cache("kdtree")
             nearest = kdtree.query(points)[1]
             interp_vel = voronoi.get_param_values("vel")[nearest]
+            state.save_to_extra_storage("interp_vel", interp_vel)  # as the notebook does (cell 12)
             return jac @ (1 / interp_vel)
 
         return forward
@@ -514,6 +515,10 @@ if ps_name + '.n_dimensions' in res:
 out['dpred_mean'] = np.mean(res[tname + '.dpred'], axis=0)
 per_chain = inv.get_results(concatenate_chains=False)
 out['dpred_mean_chain'] = np.array([np.mean(v, axis=0) for v in per_chain[tname + '.dpred']])
+if 'interp_vel' in per_chain:
+    out['field_mean_chain'] = np.array([np.mean(v, axis=0) for v in per_chain['interp_vel']])
+for pname in par.parameter_spaces[ps_name].parameters:
+    out['chain_mean_' + pname] = np.array([np.mean([np.mean(a) for a in v]) for v in per_chain[ps_name + '.' + pname]])
 for pname in par.parameter_spaces[ps_name].parameters:
     vals = res[ps_name + '.' + pname]
     out['mean_' + pname] = np.array([np.mean(v) for v in vals])

@@ -18,7 +18,8 @@ from tests import problems  # noqa: E402
 
 def device_forward(ing):
     if ing["kind"] == "tomography_2d":
-        return RayTomographyForward((ing["indptr"], ing["indices"], ing["data"]), ing["points"], "voronoi", "vel")
+        return RayTomographyForward((ing["indptr"], ing["indices"], ing["data"]), ing["points"], "voronoi", "vel",
+                                    save_field_as="interp_vel")
     if ing["kind"] == "partition_1d":
         return NearestLookup1D(ing["x"], "voronoi", "y")
     return LinearForward(ing["G"], "my_param_space", ["m0", "m1", "m2", "m3"])
@@ -35,7 +36,17 @@ def test_results_and_statistics_shapes():
     inv = make_inversion(ing, 6, seed=3)
     inv.run(sampler=None, n_iterations=300, burnin_iterations=100, save_every=50, verbose=False)
     res = inv.get_results()
-    assert set(res) == {"voronoi.n_dimensions", "voronoi.discretization", "voronoi.vel", "d_obs.std", "d_obs.dpred"}
+    # 'interp_vel' is what the tutorial's forward stores with state.save_to_extra_storage (31_sw_tomography cell 12)
+    assert set(res) == {"voronoi.n_dimensions", "voronoi.discretization", "voronoi.vel", "d_obs.std", "d_obs.dpred",
+                        "interp_vel"}
+    from oracle import kernels as OK
+
+    for sites, vel, field in zip(res["voronoi.discretization"], res["voronoi.vel"], res["interp_vel"]):
+        assert np.array_equal(field, vel[OK.nearest_site_2d(sites, ing["points"])])
+    fs = inv.get_field_statistics("interp_vel")
+    np.testing.assert_allclose(fs["mean"], np.mean(res["interp_vel"], axis=0), rtol=1e-12)
+    np.testing.assert_allclose(fs["std"], np.std(res["interp_vel"], axis=0), rtol=1e-8, atol=1e-12)
+    assert fs["chain_mean"].shape == (6, ing["points"].shape[0]) and (fs["count"] == 4).all()
     n_saved = 6 * (300 - 100) // 50
     assert all(len(v) == n_saved for v in res.values())
     for k, sites, vel, dp in zip(res["voronoi.n_dimensions"], res["voronoi.discretization"], res["voronoi.vel"],
@@ -158,6 +169,30 @@ def test_full_run_statistics_match_reference(name, golden_dir):
         ref_k = g["k"].reshape(8, -1).mean(1)
         z = abs(kk.mean() - ref_k.mean()) / math.sqrt(kk.var(ddof=1) / 64 + ref_k.var(ddof=1) / 8)
         assert z < 5, ("k", kk.mean(), ref_k.mean(), z)
+    if "k" in g.files:
+        # dimension histogram (north star: "dimension histogram ... within Monte Carlo error"): per-bin frequency
+        # against the between-chain standard errors
+        kmax = int(max(g["k"].max(), max(max(v) for v in res["voronoi.n_dimensions"])))
+        h_dev = np.array([np.bincount(v, minlength=kmax + 1) / len(v) for v in res["voronoi.n_dimensions"]])
+        h_ref = np.array([np.bincount(v, minlength=kmax + 1) / len(v) for v in g["k"].reshape(8, -1)])
+        se = np.sqrt(h_dev.var(0, ddof=1) / 64 + h_ref.var(0, ddof=1) / 8) + 2e-3
+        z = np.abs(h_dev.mean(0) - h_ref.mean(0)) / se
+        assert z.max() < 5, ("k histogram", z.round(1))
+    if "field_mean_chain" in g.files:
+        # posterior mean model on the grid (the tutorial's inferred velocity map)
+        fs = inv.get_field_statistics("interp_vel")
+        ref_f = g["field_mean_chain"]
+        se2 = fs["chain_mean"].var(0, ddof=1) / 64 + ref_f.var(0, ddof=1) / 8
+        z = np.abs(fs["chain_mean"].mean(0) - ref_f.mean(0)) / np.sqrt(se2 + 1e-300)
+        assert z.max() < 6, ("mean field", z.max())
+        np.testing.assert_allclose(fs["mean"], np.mean(res["interp_vel"], axis=0), rtol=1e-10)
+    if name.startswith("polyfit"):
+        # posterior mean coefficients
+        for p in ("m0", "m1", "m2", "m3"):
+            dev_m = np.array([np.mean(v) for v in res[f"my_param_space.{p}"]])
+            ref_m = g[f"chain_mean_{p}"]
+            z = abs(dev_m.mean() - ref_m.mean()) / math.sqrt(dev_m.var(ddof=1) / 64 + ref_m.var(ddof=1) / 8)
+            assert z < 5, (p, dev_m.mean(), ref_m.mean(), z)
     # posterior-mean predicted data, per datum, against the between-chain standard errors of both sides
     dpc = np.array([np.mean(v, axis=0) for v in res[f"{tname}.dpred"]])  # [64][R]
     ref_dpc = g["dpred_mean_chain"]  # [8][R]
@@ -339,5 +374,6 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     res_b = inv2.get_results()
     assert len(res_a["d_obs.std"]) == len(res_b["d_obs.std"]) == 24 * 23
     assert res_a["d_obs.std"] == res_b["d_obs.std"]
+    assert np.array_equal(inv.get_field_statistics("interp_vel")["mean"], inv2.get_field_statistics("interp_vel")["mean"])
     with pytest.raises(ValueError):
         make_inversion(ing, 24, seed=100).load_checkpoint(ck)
