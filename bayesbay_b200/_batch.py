@@ -64,16 +64,23 @@ def state_to_host_dict(spec: dict, state: State) -> dict:
         elif sp["ndim"] == 2:
             sites = np.asarray(sites, dtype=np.float64).reshape(k, 2)
         spaces.append(dict(k=k, sites=sites, values=values))
-    sigma = []
+    sigma, corr = [], []
     for t in spec["targets"]:
         if t["hierarchical"]:
             noise = state[t["name"]]
             if noise is None:
                 raise ValueError(f"starting state has no data-noise entry for target {t['name']!r}")
             sigma.append(float(noise.std))
+            if t.get("correlated"):
+                if noise.correlation is None:
+                    raise ValueError(f"starting state of target {t['name']!r} has no noise correlation")
+                corr.append(float(noise.correlation))
+            else:
+                corr.append(None)
         else:
             sigma.append(None)
-    return dict(spaces=spaces, sigma=sigma)
+            corr.append(None)
+    return dict(spaces=spaces, sigma=sigma, corr=corr)
 
 
 def host_dict_to_state(spec: dict, d: dict, temperature=1.0, state_cls=State, ps_cls=ParameterSpaceState,
@@ -86,9 +93,9 @@ def host_dict_to_state(spec: dict, d: dict, temperature=1.0, state_cls=State, ps
         for p, v in zip(sp["params"], ss["values"]):
             vals[p["name"]] = v
         pv[sp["name"]] = ps_cls(int(ss["k"]), vals)
-    for t, sg in zip(spec["targets"], d["sigma"]):
+    for i, (t, sg) in enumerate(zip(spec["targets"], d["sigma"])):
         if t["hierarchical"]:
-            pv[t["name"]] = noise_cls(std=sg, correlation=None)
+            pv[t["name"]] = noise_cls(std=sg, correlation=d["corr"][i] if d.get("corr") else None)
     return state_cls(pv, temperature=float(temperature))
 
 
@@ -194,7 +201,7 @@ class ChainBatch:
         mask = temps == 1.0
         if not mask.any():
             return
-        entry = dict(mask=mask, spaces=[], sigma=[], dpred=[], fields={})
+        entry = dict(mask=mask, spaces=[], sigma=[], corr=[], dpred=[], fields={})
         for t, fs in self.field_stats.items():
             # rasterised field of the current states: cell value looked up through the resident nearest-site index
             f = self.spec["targets"][t]["forward"]
@@ -212,6 +219,7 @@ class ChainBatch:
                                     None if vals is None else vals.cpu().numpy()))
         for t, tg in enumerate(self.spec["targets"]):
             entry["sigma"].append(eng.sigma[t][0].cpu().numpy() if tg["hierarchical"] else None)
+            entry["corr"].append(eng.corr[t][0].cpu().numpy() if tg.get("correlated") else None)
             entry["dpred"].append(eng.dpred(t).cpu().numpy() if self.save_dpred else None)
         self.saved.append(entry)
 
@@ -234,9 +242,12 @@ class ChainBatch:
                     out[f"{sp['name']}.discretization"].append(sites[:, :kc, c].T.copy())
                 for j, p in enumerate(sp["params"]):
                     out[f"{sp['name']}.{p['name']}"].append(vals[j, :kc, c].copy())
-            for tg, sg in zip(self.spec["targets"], entry["sigma"]):
+            for i, (tg, sg) in enumerate(zip(self.spec["targets"], entry["sigma"])):
                 if sg is not None:
                     out[f"{tg['name']}.std"].append(float(sg[c]))
+                rr = entry.get("corr", [None] * len(entry["sigma"]))[i]
+                if rr is not None:  # DataNoiseState.todict: "{target}.correlation" (reference _state.py:26-46)
+                    out[f"{tg['name']}.correlation"].append(float(rr[c]))
             for tg, dp in zip(self.spec["targets"], entry["dpred"]):
                 if dp is not None:
                     out[f"{tg['name']}.dpred"].append(dp[:, c].copy())

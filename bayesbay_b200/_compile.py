@@ -88,13 +88,13 @@ def compile_space(ps) -> dict:
 
 
 def compile_target(tgt, fwd, space_index: dict, spaces: list) -> dict:
-    if getattr(tgt, "noise_is_correlated", False):
-        raise DeviceUnsupported(f"target {tgt.name!r}: correlated noise is not on the device yet (SURVEY.md 8f rank 3)")
     dobs = np.ascontiguousarray(tgt.dobs, dtype=np.float64).ravel()
     cov = getattr(tgt, "covariance_mat_inv", None)
     spec = dict(name=tgt.name, dobs=dobs, hierarchical=cov is None,
                 std_min=float(tgt.std_min), std_max=float(tgt.std_max), std_perturb_std=float(tgt.std_perturb_std),
-                cov_inv=None)
+                cov_inv=None, correlated=bool(getattr(tgt, "noise_is_correlated", False)) and cov is None,
+                corr_min=float(tgt.correlation_min), corr_max=float(tgt.correlation_max),
+                corr_perturb_std=float(tgt.correlation_perturb_std))
     if cov is not None:
         if np.isscalar(cov):
             spec["cov_inv"] = float(cov)

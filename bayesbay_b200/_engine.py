@@ -91,6 +91,9 @@ class Engine:
             if tg["hierarchical"]:
                 t.cov_kind = L.COV_HIERARCHICAL
                 t.std_min, t.std_max, t.std_perturb_std = tg["std_min"], tg["std_max"], tg["std_perturb_std"]
+                if tg.get("correlated"):
+                    t.correlated = 1
+                    t.corr_min, t.corr_max, t.corr_perturb_std = tg["corr_min"], tg["corr_max"], tg["corr_perturb_std"]
             elif np.isscalar(tg["cov_inv"]):
                 t.cov_kind = L.COV_SCALAR
                 t.cov_scalar = float(tg["cov_inv"])
@@ -152,9 +155,15 @@ class Engine:
             b.k[i], b.sel[i] = _ptr(self.k[i]), _ptr(self.sel[i])
         self.sigma, self.phi, self.cell_idx, self.idx_sel, self.partial = [], [], [], [], []
         self.rescan_list, self.rescan_count = [], []
+        self.corr, self.dpred_scratch = [], []
         for i, tg in enumerate(self.spec["targets"]):
             self.sigma.append(torch.ones((2, Cn), dtype=f64, device=dev) if tg["hierarchical"] else None)
-            self.phi.append(z((2, Cn), f64))
+            self.phi.append(z((2, 3, Cn), f64))
+            corr_t = bool(tg.get("correlated"))
+            self.corr.append(z((2, Cn), f64) if corr_t else None)
+            self.dpred_scratch.append(z((int(np.asarray(tg["dobs"]).size), Cn), f64)
+                                      if corr_t and tg["forward"]["kind"] == "ray2d" else None)
+            b.corr[i], b.dpred_scratch[i] = _ptr(self.corr[i]), _ptr(self.dpred_scratch[i])
             if tg["forward"]["kind"] == "ray2d":
                 K = self.spec["spaces"][tg["forward"]["space"]]["kmax"]
                 G = int(np.asarray(tg["forward"]["points"]).shape[0])
@@ -304,7 +313,12 @@ class Engine:
         for t, tg in enumerate(self.spec["targets"]):
             if tg["hierarchical"]:
                 sg = np.array([st["sigma"][t] for st in states], dtype=np.float64)
+                if (sg < tg["std_min"]).any() or (sg > tg["std_max"]).any():
+                    raise ValueError(f"starting state: noise std of {tg['name']!r} outside [std_min, std_max]")
                 self.sigma[t].copy_(torch.as_tensor(np.stack((sg, sg))))
+            if tg.get("correlated"):
+                rr = np.array([st["corr"][t] for st in states], dtype=np.float64)
+                self.corr[t].copy_(torch.as_tensor(np.stack((rr, rr))))
             if self.idx_sel[t] is not None:
                 self.idx_sel[t].zero_()
         if temperatures is not None:
@@ -313,7 +327,7 @@ class Engine:
 
     def fetch_states(self) -> List[dict]:
         """Current state of every chain as host dicts (inverse of :meth:`load_states`)."""
-        out = [dict(spaces=[], sigma=[]) for _ in range(self.C)]
+        out = [dict(spaces=[], sigma=[], corr=[]) for _ in range(self.C)]
         for s, sp in enumerate(self.spec["spaces"]):
             k, sites, vals = self.gather_space(s)
             k = k.cpu().numpy()
@@ -330,8 +344,10 @@ class Engine:
                 out[c]["spaces"].append(st)
         for t, tg in enumerate(self.spec["targets"]):
             sg = self.sigma[t][0].cpu().numpy() if tg["hierarchical"] else None
+            rr = self.corr[t][0].cpu().numpy() if tg.get("correlated") else None
             for c in range(self.C):
                 out[c]["sigma"].append(None if sg is None else float(sg[c]))
+                out[c]["corr"].append(None if rr is None else float(rr[c]))
         return out
 
     # ------------------------------------------------------------------ checkpoint / resume
@@ -342,8 +358,8 @@ class Engine:
         for i in range(len(self.spec["spaces"])):
             named.update({f"sites{i}": self.sites[i], f"values{i}": self.values[i], f"k{i}": self.k[i], f"sel{i}": self.sel[i]})
         for i in range(len(self.spec["targets"])):
-            named.update({f"sigma{i}": self.sigma[i], f"phi{i}": self.phi[i], f"cell_idx{i}": self.cell_idx[i],
-                          f"idx_sel{i}": self.idx_sel[i]})
+            named.update({f"sigma{i}": self.sigma[i], f"corr{i}": self.corr[i], f"phi{i}": self.phi[i],
+                          f"cell_idx{i}": self.cell_idx[i], f"idx_sel{i}": self.idx_sel[i]})
         return {k: v for k, v in named.items() if v is not None}
 
     def state_dict(self) -> dict:

@@ -43,6 +43,8 @@ class TargetSpec(C.Structure):
     _fields_ = [
         ("n_data", C.c_int32), ("cov_kind", C.c_int32),
         ("std_min", C.c_double), ("std_max", C.c_double), ("std_perturb_std", C.c_double),
+        ("correlated", C.c_int32),
+        ("corr_min", C.c_double), ("corr_max", C.c_double), ("corr_perturb_std", C.c_double),
         ("cov_scalar", C.c_double),
         ("dobs", _vp), ("cov_vec", _vp),
         ("fwd_kind", C.c_int32), ("space", C.c_int32), ("param", C.c_int32), ("transform", C.c_int32),
@@ -66,7 +68,8 @@ class Buffers(C.Structure):
     _fields_ = [
         ("n_chains", C.c_int64), ("chain_id0", C.c_int64),
         ("sites", _vp * MAX_SPACES), ("values", _vp * MAX_SPACES), ("k", _vp * MAX_SPACES), ("sel", _vp * MAX_SPACES),
-        ("sigma", _vp * MAX_TARGETS), ("phi", _vp * MAX_TARGETS), ("cell_idx", _vp * MAX_TARGETS),
+        ("sigma", _vp * MAX_TARGETS), ("corr", _vp * MAX_TARGETS), ("phi", _vp * MAX_TARGETS),
+        ("dpred_scratch", _vp * MAX_TARGETS), ("cell_idx", _vp * MAX_TARGETS),
         ("idx_sel", _vp * MAX_TARGETS), ("partial", _vp * MAX_TARGETS),
         ("rescan_list", _vp * MAX_TARGETS), ("rescan_count", _vp * MAX_TARGETS),
         ("temperature", _vp), ("iteration", _vp),

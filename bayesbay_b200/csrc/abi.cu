@@ -84,6 +84,11 @@ static int validate_spec(const bbb_problem_spec *P) {
         if (T.cov_kind == BBB_COV_HIERARCHICAL) {
             if (!(T.std_min >= 0) || !(T.std_max >= T.std_min) || !(T.std_perturb_std > 0))
                 return fail(BBB_ERR_INVALID, "target %d: noise std range", t);
+            if (T.correlated && (!(T.corr_min >= 0) || !(T.corr_max >= T.corr_min) || !(T.corr_max < 1.0 || T.corr_min < 1.0) ||
+                                 !(T.corr_perturb_std > 0) || T.n_data < 3))
+                return fail(BBB_ERR_INVALID, "target %d: noise correlation range (needs 0 <= min <= max, at least 3 data)", t);
+        } else if (T.correlated) {
+            return fail(BBB_ERR_INVALID, "target %d: correlated noise needs a hierarchical target", t);
         } else if (T.cov_kind == BBB_COV_VECTOR) {
             if (T.cov_vec == nullptr) return fail(BBB_ERR_INVALID, "target %d: cov_vec is NULL", t);
         } else if (T.cov_kind != BBB_COV_SCALAR) {
@@ -151,6 +156,9 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
     for (int t = 0; t < P.n_targets; ++t) {
         if (!b->phi[t]) return fail(BBB_ERR_SHAPE, "target %d: phi buffer missing", t);
         if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL && !b->sigma[t]) return fail(BBB_ERR_SHAPE, "target %d: sigma buffer missing", t);
+        if (P.targets[t].correlated && !b->corr[t]) return fail(BBB_ERR_SHAPE, "target %d: corr buffer missing", t);
+        if (P.targets[t].correlated && P.targets[t].fwd_kind == BBB_FWD_RAY2D && !b->dpred_scratch[t])
+            return fail(BBB_ERR_SHAPE, "target %d: dpred_scratch buffer missing", t);
         if (P.targets[t].fwd_kind == BBB_FWD_RAY2D &&
             (!b->cell_idx[t] || !b->idx_sel[t] || !b->partial[t] || !b->rescan_list[t] || !b->rescan_count[t]))
             return fail(BBB_ERR_SHAPE, "target %d: cell_idx/idx_sel/partial/rescan buffer missing", t);
@@ -262,6 +270,7 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
     a.n_spaces = P.n_spaces;
     a.space = T.space;
     a.dpred = dpred;
+    if (T.correlated && write_partial && dpred == nullptr) a.dpred = B.dpred_scratch[t];  // reduced by k_corr_sums
     a.partial = write_partial ? B.partial[t] : nullptr;
     // the value table holds k_rows cells per chain; a tighter bound allows more chains per lane
     a.k_rows = proposal ? (e->k_bound[T.space] + 1 < S.kmax ? e->k_bound[T.space] + 1 : S.kmax) : e->k_bound[T.space];
@@ -273,7 +282,9 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
         int rc = (int)cudaMemcpyAsync(&e->dev->n_partial[t], &e->host.n_partial[t], sizeof(int), cudaMemcpyHostToDevice, st);
         if (rc != 0) return rc;
     }
-    return launch_ray_spmm(a, st);
+    int rc = launch_ray_spmm(a, st);
+    if (rc == 0 && T.correlated && write_partial) rc = launch_corr_sums(e->dev, a.C, t, proposal ? 1 : 0, st);
+    return rc;
 }
 
 #define NEED_BOUND(e)                                                                  \

@@ -29,15 +29,43 @@ __device__ __forceinline__ int cell_1d(const bbb_buffers &B, const bbb_space_spe
     return cell_1d_at([&](int j) { return site_ref(B, S, s, slot, 0, j, c); }, k, xp, hint);
 }
 
-// phi = sum_r w_r (d_pred[r] - d_obs[r])^2 of a thread-evaluated target; optionally stores d_pred
-// (stride C) and the cell index (lookup1d, stride C).
-__device__ inline double small_target_phi(const bbb_problem_spec &P, const bbb_buffers &B, int t, int slot,
-                                          long long c, double *dpred_out, int32_t *idx_out) {
+// Residual sums of one target with the noise parameters factored out (so noise moves need no forward):
+//   s0 = sum_r w_r res_r^2,   se = res_0^2 + res_{n-1}^2,   s1 = sum_r res_r res_{r+1}
+// For correlated noise  res^T C^-1 res = [(1 + rho^2) s0 - rho^2 se - 2 rho s1] / (sigma^2 (1 - rho^2))  with the
+// tridiagonal C^-1 of inverse_covariance (_utils_1d.pyx:198-211).
+struct Phi3 {
+    double s0, se, s1;
+};
+__device__ __forceinline__ Phi3 load_phi(const bbb_buffers &B, int t, int slot, long long c) {
+    const long long C = B.n_chains;
+    const double *p = B.phi[t] + (long long)slot * 3 * C + c;
+    return Phi3{p[0], p[C], p[2 * C]};
+}
+__device__ __forceinline__ void store_phi(const bbb_buffers &B, int t, int slot, long long c, const Phi3 &v) {
+    const long long C = B.n_chains;
+    double *p = B.phi[t] + (long long)slot * 3 * C + c;
+    p[0] = v.s0; p[C] = v.se; p[2 * C] = v.s1;
+}
+struct ResidualSums {  // streaming accumulation of Phi3 over r = 0 .. n-1
+    Phi3 v{0.0, 0.0, 0.0};
+    double prev = 0.0;
+    __device__ __forceinline__ void add(int r, int n, double res, double w) {
+        v.s0 += w * (res * res);
+        if (r == 0 || r == n - 1) v.se += res * res;
+        if (r > 0) v.s1 += prev * res;
+        prev = res;
+    }
+};
+
+// Residual sums of a thread-evaluated target; optionally stores d_pred (stride C) and the cell index
+// (lookup1d, stride C).
+__device__ inline Phi3 small_target_phi(const bbb_problem_spec &P, const bbb_buffers &B, int t, int slot,
+                                        long long c, double *dpred_out, int32_t *idx_out) {
     const bbb_target_spec &T = P.targets[t];
     const int s = T.space;
     const bbb_space_spec &S = P.spaces[s];
     const long long C = B.n_chains;
-    double phi = 0.0;
+    ResidualSums acc;
     if (T.fwd_kind == BBB_FWD_LOOKUP1D) {
         // Voronoi1D.interpolate_tessellation(..., 'nuclei') (discretization/_voronoi.py:705-732)
         const int k = k_ref(B, s, slot, c);
@@ -47,8 +75,7 @@ __device__ inline double small_target_phi(const bbb_problem_spec &P, const bbb_b
             const double d = value_ref(B, S, s, slot, T.param, i, c);
             if (dpred_out) dpred_out[(long long)r * C + c] = d;
             if (idx_out) idx_out[(long long)r * C + c] = i;
-            const double res = d - T.dobs[r];
-            phi += data_weight(T, r) * (res * res);
+            acc.add(r, T.n_data, d - T.dobs[r], data_weight(T, r));
         }
     } else if (T.fwd_kind == BBB_FWD_LINEAR) {
         // fwd_operator @ m (02_hierarchical_polyfit.ipynb cell 12)
@@ -60,11 +87,10 @@ __device__ inline double small_target_phi(const bbb_problem_spec &P, const bbb_b
                 for (int j = 0; j < K; ++j)
                     d += T.G[(long long)r * M + q * K + j] * value_ref(B, S, s, slot, T.lin_params[q], j, c);
             if (dpred_out) dpred_out[(long long)r * C + c] = d;
-            const double res = d - T.dobs[r];
-            phi += data_weight(T, r) * (res * res);
+            acc.add(r, T.n_data, d - T.dobs[r], data_weight(T, r));
         }
     }
-    return phi;
+    return acc.v;
 }
 
 __device__ __forceinline__ double ray_partial_sum(const EngineParams &ep, int t, long long c) {
@@ -76,16 +102,22 @@ __device__ __forceinline__ double ray_partial_sum(const EngineParams &ep, int t,
 }
 
 // Target.inverse_covariance_times_vector / log_determinant_covariance (likelihood/_target.py:136-208)
-__device__ __forceinline__ void misfit_logdet_terms(const bbb_target_spec &T, double phi, double sigma,
+__device__ __forceinline__ void misfit_logdet_terms(const bbb_target_spec &T, const Phi3 &phi, double sigma, double rho,
                                                     double &misfit, double &logdet) {
     if (T.cov_kind == BBB_COV_HIERARCHICAL) {
-        misfit = (1.0 / (sigma * sigma)) * phi;
-        logdet = (2.0 * T.n_data) * log(sigma);
+        if (T.correlated) {
+            const double factor = 1.0 / ((sigma * sigma) * (1.0 - rho * rho));
+            misfit = factor * ((1.0 + rho * rho) * phi.s0 - (rho * rho) * phi.se - 2.0 * rho * phi.s1);
+            logdet = (2.0 * T.n_data) * log(sigma) + (double)(T.n_data - 1) * log(1.0 - rho * rho);
+        } else {
+            misfit = (1.0 / (sigma * sigma)) * phi.s0;
+            logdet = (2.0 * T.n_data) * log(sigma);
+        }
     } else if (T.cov_kind == BBB_COV_SCALAR) {
-        misfit = T.cov_scalar * phi;
+        misfit = T.cov_scalar * phi.s0;
         logdet = 0.0;
     } else {
-        misfit = phi;
+        misfit = phi.s0;
         logdet = 0.0;
     }
 }
@@ -117,18 +149,21 @@ __device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rn
         for (int t = 0; t < P.n_targets; ++t) {
             const bbb_target_spec &T = P.targets[t];
             const bool hier = (T.cov_kind == BBB_COV_HIERARCHICAL);
-            const double phi_old = B.phi[t][c];
-            double phi_new = phi_old;
+            const Phi3 phi_old = load_phi(B, t, 0, c);
+            Phi3 phi_new = phi_old;
             if (!noise && T.space == s) {
-                if (T.fwd_kind == BBB_FWD_RAY2D) phi_new = ray_partial_sum(ep, t, c);
-                else phi_new = small_target_phi(P, B, t, B.sel[s][c] ^ 1, c, nullptr, nullptr);
-                B.phi[t][C + c] = phi_new;
+                if (T.fwd_kind != BBB_FWD_RAY2D) phi_new = small_target_phi(P, B, t, B.sel[s][c] ^ 1, c, nullptr, nullptr);
+                else if (T.correlated) phi_new = load_phi(B, t, 1, c);  // written by k_corr_sums from d_pred
+                else phi_new = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
+                store_phi(B, t, 1, c, phi_new);
             }
             const double sig_old = hier ? B.sigma[t][c] : 1.0;
             const double sig_new = (hier && noise) ? B.sigma[t][C + c] : sig_old;
+            const double rho_old = T.correlated ? B.corr[t][c] : 0.0;
+            const double rho_new = (T.correlated && noise) ? B.corr[t][C + c] : rho_old;
             double m0, l0, m1, l1;
-            misfit_logdet_terms(T, phi_old, sig_old, m0, l0);
-            misfit_logdet_terms(T, phi_new, sig_new, m1, l1);
+            misfit_logdet_terms(T, phi_old, sig_old, rho_old, m0, l0);
+            misfit_logdet_terms(T, phi_new, sig_new, rho_new, m1, l1);
             old_m += m0; new_m += m1;
             if (hier) { old_ld += l0; new_ld += l1; }
         }
@@ -139,14 +174,16 @@ __device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rn
     const bool accepted = (lpr + llr) > log_u;  // NaN compares false -> rejected
     if (accepted) {
         if (noise) {
-            for (int t = 0; t < P.n_targets; ++t)
+            for (int t = 0; t < P.n_targets; ++t) {
                 if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL) B.sigma[t][c] = B.sigma[t][C + c];
+                if (P.targets[t].correlated) B.corr[t][c] = B.corr[t][C + c];
+            }
         } else {
             B.sel[s][c] ^= 1;
             for (int t = 0; t < P.n_targets; ++t) {
                 const bbb_target_spec &T = P.targets[t];
                 if (T.space != s) continue;
-                B.phi[t][c] = B.phi[t][C + c];
+                store_phi(B, t, 0, c, load_phi(B, t, 1, c));
             }
         }
     }

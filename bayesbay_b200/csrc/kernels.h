@@ -66,6 +66,7 @@ int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);
 // step_kernels.cu
 int launch_propose(const EngineParams *dev_params, long long C, cudaStream_t stream);
 int launch_finish(const EngineParams *dev_params, long long C, cudaStream_t stream);
+int launch_corr_sums(const EngineParams *dev_params, long long C, int target, int proposal, cudaStream_t stream);
 int launch_fused_steps(const EngineParams *dev_params, long long C, long long n_steps, cudaStream_t stream);
 int launch_init_states(const EngineParams *dev_params, long long C, cudaStream_t stream);
 int launch_refresh_finish(const EngineParams *dev_params, long long C, cudaStream_t stream);

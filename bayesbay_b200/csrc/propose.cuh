@@ -106,6 +106,17 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
                 break;
             }
             if (writer) B.sigma[t][B.n_chains + c] = new_v;
+            if (T.correlated) {  // to_be_perturbed = ["std", "correlation"] (_data_noise.py:61-76)
+                const double old_r = B.corr[t][c];
+                double new_r = old_r;
+                for (int it = 0; it < MAX_RESAMPLE; ++it) {
+                    const double cand = old_r + rng.normal(0.0, T.corr_perturb_std);
+                    if (cand < T.corr_min || cand > T.corr_max) continue;
+                    new_r = cand;
+                    break;
+                }
+                if (writer) B.corr[t][B.n_chains + c] = new_r;
+            }
         }
         if (writer) {
             B.move[c] = 4 * P.n_spaces;

@@ -137,6 +137,11 @@ __global__ void __launch_bounds__(STEP_THREADS) k_init_states(const EngineParams
             const double sg = rng.uniform(T.std_min, T.std_max);
             B.sigma[t][c] = sg;
             B.sigma[t][B.n_chains + c] = sg;
+            if (T.correlated) {  // Target.initialize: std, then correlation (likelihood/_target.py:124-131)
+                const double r0 = rng.uniform(T.corr_min, T.corr_max);
+                B.corr[t][c] = r0;
+                B.corr[t][B.n_chains + c] = r0;
+            }
         }
         if (T.fwd_kind == BBB_FWD_RAY2D) B.idx_sel[t][c] = 0;
     }
@@ -153,12 +158,30 @@ __global__ void __launch_bounds__(STEP_THREADS) k_refresh_finish(const EnginePar
     if (c >= B.n_chains) return;
     for (int t = 0; t < P.n_targets; ++t) {
         const bbb_target_spec &T = P.targets[t];
-        double phi;
-        if (T.fwd_kind == BBB_FWD_RAY2D) phi = ray_partial_sum(ep, t, c);
-        else phi = small_target_phi(P, B, t, B.sel[T.space][c], c, nullptr, nullptr);
-        B.phi[t][c] = phi;
-        B.phi[t][B.n_chains + c] = phi;
+        Phi3 phi;
+        if (T.fwd_kind != BBB_FWD_RAY2D) phi = small_target_phi(P, B, t, B.sel[T.space][c], c, nullptr, nullptr);
+        else if (T.correlated) phi = load_phi(B, t, 0, c);  // written by k_corr_sums from d_pred
+        else phi = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
+        store_phi(B, t, 0, c, phi);
+        store_phi(B, t, 1, c, phi);
     }
+}
+
+// Correlated noise on a ray target: the three residual sums need neighbouring rays, which different warps of the
+// ray kernel own, so that kernel writes d_pred and this one reduces it (one thread per chain, coalesced rows).
+// proposal != 0: only chains whose proposal touched the target, result into the proposed slot.
+__global__ void k_corr_sums(const EngineParams *epp, int t, int proposal) {
+    const EngineParams &ep = *epp;
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const bbb_target_spec &T = P.targets[t];
+    const long long C = B.n_chains;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (proposal && !target_touched(P, B.move[c], B.log_prob_ratio[c], t)) return;
+    ResidualSums acc;
+    for (int r = 0; r < T.n_data; ++r) acc.add(r, T.n_data, B.dpred_scratch[t][(long long)r * C + c] - T.dobs[r], 1.0);
+    store_phi(B, t, proposal ? 1 : 0, c, acc.v);
 }
 
 // O1: compact the current slot of one space, [..][K][C] (blockIdx.y = cell j)
@@ -197,7 +220,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_misfit_logdet(const EnginePara
         const bbb_target_spec &T = P.targets[t];
         const bool hier = (T.cov_kind == BBB_COV_HIERARCHICAL);
         double mt, lt;
-        misfit_logdet_terms(T, B.phi[t][c], hier ? B.sigma[t][c] : 1.0, mt, lt);
+        misfit_logdet_terms(T, load_phi(B, t, 0, c), hier ? B.sigma[t][c] : 1.0, T.correlated ? B.corr[t][c] : 0.0, mt, lt);
         m += mt;
         if (hier) ld += lt;
     }
@@ -351,6 +374,10 @@ int launch_propose(const EngineParams *p, long long C, cudaStream_t st) {
 int launch_apply_edit(const EngineParams *p, long long C, int space, int kmax, cudaStream_t st) {
     dim3 grid(blocks_for(C, 128), kmax);
     k_apply_edit<<<grid, 128, 0, st>>>(p, space);
+    return (int)cudaGetLastError();
+}
+int launch_corr_sums(const EngineParams *p, long long C, int target, int proposal, cudaStream_t st) {
+    k_corr_sums<<<blocks_for(C, 128), 128, 0, st>>>(p, target, proposal);
     return (int)cudaGetLastError();
 }
 int launch_finish(const EngineParams *p, long long C, cudaStream_t st) {

@@ -18,7 +18,7 @@ class Target:
 
     ``Target(name, dobs, covariance_mat_inv=None, noise_is_correlated=False, std_min=0.01, std_max=1,
     std_perturb_std=0.1, correlation_min=0.01, correlation_max=1, correlation_perturb_std=0.1)`` --
-    reference likelihood/_target.py:10-208.  Correlated noise is not on the device yet."""
+    reference likelihood/_target.py:10-208.  Full (2-D) inverse covariance matrices are not supported."""
 
     def __init__(self, name: str, dobs: np.ndarray, covariance_mat_inv: Union[Number, np.ndarray] = None,
                  noise_is_correlated: bool = False, std_min: Number = 0.01, std_max: Number = 1,
@@ -35,9 +35,9 @@ class Target:
         assert correlation_min <= correlation_max, "correlation minimum should be less than maximum"
         assert correlation_min >= 0, "correlation should always be positive"
         assert correlation_max <= 1, "correlation should always be less than 1"
-        if noise_is_correlated:
-            raise DeviceUnsupported("correlated data noise is not implemented by the device engine yet "
-                                    "(SURVEY.md section 8f rank 3)")
+        if noise_is_correlated and covariance_mat_inv is not None:
+            raise ValueError("`noise_is_correlated` describes hierarchical noise; it cannot be combined with a fixed "
+                             "`covariance_mat_inv`")
         if covariance_mat_inv is None:
             self.covariance_mat_inv = None
         elif np.isscalar(covariance_mat_inv):

@@ -132,7 +132,7 @@ def _boundary_sources(n_per_side, xmin=-1.0, xmax=1.0, ymin=-1.0, ymax=1.0):
 # problem ingredients
 # --------------------------------------------------------------------------- #
 def tomography_2d(nx=100, ny=100, n_sources_per_side=25, n_receivers=100, kmin=10, kmax=200,
-                  noise_std=0.002, seed_receivers=1, seed_noise=2):
+                  noise_std=0.002, seed_receivers=1, seed_noise=2, correlated=False):
     """2-D Voronoi straight-ray travel-time tomography (configs C3/C4/C5).
 
     C3: defaults (100x100 grid, 100 x 100 = 10 000 rays, k in [10, 200]).
@@ -157,7 +157,9 @@ def tomography_2d(nx=100, ny=100, n_sources_per_side=25, n_receivers=100, kmin=1
         voronoi=dict(name="voronoi", vmin=[-1.0, -1.0], vmax=[1.0, 1.0], perturb_std=0.05,
                      n_dimensions_min=kmin, n_dimensions_max=kmax, birth_from="neighbour",
                      compute_kdtree=True),
-        target=dict(name="d_obs", std_min=0.0, std_max=0.01, std_perturb_std=0.001),
+        target=dict(name="d_obs", std_min=0.0, std_max=0.01, std_perturb_std=0.001,
+                    **(dict(noise_is_correlated=True, correlation_min=0.01, correlation_max=0.9,
+                            correlation_perturb_std=0.1) if correlated else {})),
     )
 
 
@@ -173,7 +175,7 @@ def _piecewise(x):
     return out
 
 
-def partition_1d(n_data=100, noise_std=5.0, seed=30, kmin=2, kmax=40, birth_from="prior"):
+def partition_1d(n_data=100, noise_std=5.0, seed=30, kmin=2, kmax=40, birth_from="prior", correlated=False):
     """1-D Voronoi piecewise-constant regression (config C1)."""
     x = np.linspace(0.0, 10.0, n_data)
     rng = np.random.RandomState(seed)  # the notebook uses legacy np.random.seed(30)
@@ -184,7 +186,9 @@ def partition_1d(n_data=100, noise_std=5.0, seed=30, kmin=2, kmax=40, birth_from
         prior=dict(name="y", vmin=-35.0, vmax=35.0, perturb_std=3.5),
         voronoi=dict(name="voronoi", vmin=0.0, vmax=10.0, perturb_std=0.75,
                      n_dimensions_min=kmin, n_dimensions_max=kmax, birth_from=birth_from),
-        target=dict(name="d_obs", std_min=0.0, std_max=20.0, std_perturb_std=2.0),
+        target=dict(name="d_obs", std_min=0.0, std_max=20.0, std_perturb_std=2.0,
+                    **(dict(noise_is_correlated=True, correlation_min=0.01, correlation_max=0.9,
+                            correlation_perturb_std=0.1) if correlated else {})),
     )
 
 
@@ -253,7 +257,6 @@ def build_problem(ing, bb, make_forward):
         raise ValueError(kind)
     parameterization = bb.parameterization.Parameterization(space)
     t = ing["target"]
-    target = bb.likelihood.Target(t["name"], ing["d_obs"], std_min=t["std_min"], std_max=t["std_max"],
-                                  std_perturb_std=t["std_perturb_std"])
+    target = bb.likelihood.Target(t["name"], ing["d_obs"], **{k: v for k, v in t.items() if k != "name"})
     log_likelihood = bb.likelihood.LogLikelihood(targets=target, fwd_functions=make_forward(ing))
     return parameterization, log_likelihood

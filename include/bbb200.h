@@ -78,6 +78,9 @@ typedef struct {
     int32_t n_data;
     int32_t cov_kind;        /* BBB_COV_* */
     double std_min, std_max, std_perturb_std;
+    int32_t correlated;      /* hierarchical only: Target(noise_is_correlated=True), tridiagonal inverse covariance
+                              * inverse_covariance(sigma, r, n) (_utils_1d.pyx:198-211, likelihood/_target.py:167-170) */
+    double corr_min, corr_max, corr_perturb_std;
     double cov_scalar;
     const double *dobs;      /* device [n_data] */
     const double *cov_vec;   /* device [n_data] or NULL */
@@ -121,7 +124,11 @@ typedef struct {
     uint8_t *sel[BBB_MAX_SPACES];     /* [C] */
     /* per target */
     double *sigma[BBB_MAX_TARGETS];   /* [2][C]  (0 = current, 1 = proposed) hierarchical only */
-    double *phi[BBB_MAX_TARGETS];     /* [2][C]  sum_i w_i r_i^2 with sigma factored out */
+    double *corr[BBB_MAX_TARGETS];    /* [2][C]  noise correlation (correlated targets only) */
+    double *phi[BBB_MAX_TARGETS];     /* [2][3][C] residual sums with the noise parameters factored out:
+                                       * sum_i w_i r_i^2, r_0^2 + r_{n-1}^2, sum_i r_i r_{i+1} (the last two only
+                                       * for correlated noise) */
+    double *dpred_scratch[BBB_MAX_TARGETS]; /* [n_data][C], ray2d targets with correlated noise only */
     void *cell_idx[BBB_MAX_TARGETS];  /* ray2d: [2][G][C] uint8 (K <= 256) or uint16; slot 0 = current, slot 1 = proposed */
     uint8_t *idx_sel[BBB_MAX_TARGETS];/* ray2d: [C] 1 = the current index is still in slot 1 (accepted, not yet committed) */
     double *partial[BBB_MAX_TARGETS]; /* ray2d: [n_ray_tiles][C], n_ray_tiles = bbb_ray_tiles(n_data) */

@@ -54,10 +54,15 @@ class ChainState:
     sigma: List[Optional[float]]
     T: float = 1.0
     dpred: List[Optional[np.ndarray]] = field(default_factory=list)
+    corr: List[Optional[float]] = field(default_factory=list)  # noise correlation per target (None: uncorrelated)
+
+    def __post_init__(self):
+        if not self.corr:
+            self.corr = [None] * len(self.sigma)
 
     def copy(self):
         return ChainState([s.copy() for s in self.spaces], list(self.sigma), self.T,
-                          [None if d is None else d for d in self.dpred])
+                          [None if d is None else d for d in self.dpred], list(self.corr))
 
 
 def outer_moves(spec):
@@ -118,9 +123,11 @@ def init_state(spec, s, temperature=1.0):
             sites = np.array([_sample_site(sp, s) for _ in range(k)]).reshape(k, 2)
         values = [np.array([_prior_sample(p, s) for _ in range(k)]) for p in sp["params"]]
         spaces.append(SpaceState(k, sites, values))
-    sigma = [R.draw_uniform(s, t["std_min"], t["std_max"]) if t["hierarchical"] else None
-             for t in spec["targets"]]
-    st = ChainState(spaces, sigma, temperature, [None] * len(spec["targets"]))
+    sigma, corr = [], []
+    for t in spec["targets"]:
+        sigma.append(R.draw_uniform(s, t["std_min"], t["std_max"]) if t["hierarchical"] else None)
+        corr.append(R.draw_uniform(s, t["corr_min"], t["corr_max"]) if t.get("correlated") else None)
+    st = ChainState(spaces, sigma, temperature, [None] * len(spec["targets"]), corr)
     evaluate(spec, st)
     return st
 
@@ -153,7 +160,7 @@ def misfit_and_logdet(spec, st):
     misfit = 0.0
     logdet = 0.0
     for i, t in enumerate(spec["targets"]):
-        m, ld = K.misfit_and_logdet(st.dpred[i], t["dobs"], st.sigma[i], t["cov_inv"])
+        m, ld = K.misfit_and_logdet(st.dpred[i], t["dobs"], st.sigma[i], t["cov_inv"], st.corr[i])
         misfit += m
         if t["hierarchical"]:
             logdet += ld
@@ -270,8 +277,9 @@ def _death(sp, ss, s):
 
 def _move_noise(spec, st, s):
     """``NoisePerturbation.perturb`` (perturbations/_data_noise.py:21-77): every hierarchical
-    target's sigma random-walks, resampled until inside ``[std_min, std_max]``; ratio 0."""
-    sigma = list(st.sigma)
+    target's sigma (then its correlation, if the noise is correlated) random-walks, resampled until inside
+    its range; ratio 0."""
+    sigma, corr = list(st.sigma), list(st.corr)
     for i, t in enumerate(spec["targets"]):
         if not t["hierarchical"]:
             continue
@@ -281,7 +289,14 @@ def _move_noise(spec, st, s):
                 continue
             break
         sigma[i] = new
-    return sigma
+        if t.get("correlated"):
+            while True:
+                new = st.corr[i] + R.draw_normal(s, 0.0, t["corr_perturb_std"])
+                if new < t["corr_min"] or new > t["corr_max"]:
+                    continue
+                break
+            corr[i] = new
+    return sigma, corr
 
 
 def propose(spec, st, s):
@@ -293,7 +308,7 @@ def propose(spec, st, s):
     kind, isp, inner = moves[R.draw_choice(s, weights)]
     new = st.copy()
     if kind == "noise":
-        new.sigma = _move_noise(spec, st, s)
+        new.sigma, new.corr = _move_noise(spec, st, s)
         # quirk Q1: the reference re-runs the forward here; the result is identical, so keep d_pred
         return new, 0.0, 4 * len(spec["spaces"])
     sp = spec["spaces"][isp]

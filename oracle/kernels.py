@@ -175,18 +175,24 @@ def linear_forward(G, m):
 # --------------------------------------------------------------------------- #
 # L1-L3: likelihood and prior
 # --------------------------------------------------------------------------- #
-def misfit_and_logdet(dpred, dobs, std=None, cov_inv=None):
+def misfit_and_logdet(dpred, dobs, std=None, cov_inv=None, corr=None):
     """One target's contribution to ``LogLikelihood._get_misfit_and_det``
     (src/bayesbay/likelihood/_log_likelihood.py:308-332) with
-    ``Target.inverse_covariance_times_vector`` (likelihood/_target.py:136-170) and
-    ``Target.log_determinant_covariance`` (likelihood/_target.py:172-208), uncorrelated noise."""
+    ``Target.inverse_covariance_times_vector`` (likelihood/_target.py:136-170; correlated noise uses the
+    tridiagonal ``inverse_covariance``, _utils_1d.pyx:198-211) and ``Target.log_determinant_covariance``
+    (likelihood/_target.py:172-208)."""
     r = dpred - dobs
     if cov_inv is not None:
         misfit = float(r @ (cov_inv * r))
         return misfit, 0.0
-    misfit = float(r @ (1.0 / std ** 2 * r))
     n = dobs.size
-    log_det = (2 * n) * math.log(std) + (n - 1) * math.log(1.0 - 0.0 ** 2)
+    if corr is None:
+        misfit = float(r @ (1.0 / std ** 2 * r))
+        rho = 0.0
+    else:
+        misfit = float(r @ (inverse_covariance(std, corr, n) @ r))
+        rho = corr
+    log_det = (2 * n) * math.log(std) + (n - 1) * math.log(1.0 - rho ** 2)
     return misfit, log_det
 
 

@@ -227,6 +227,11 @@ class Recorder:
         return new_state, ratio
 
 
+def snapshot_corr(state, target_name):
+    c = state[target_name].correlation
+    return np.nan if c is None else c
+
+
 def snapshot(state, ps_name, param_names, target_name, kmax, ndim):
     ps = state[ps_name]
     k = ps.n_dimensions
@@ -286,7 +291,7 @@ def replay(bb, ing, n_chains, n_steps, seed0, name):
                 k=np.zeros((n_chains, n_steps + 1), np.int32),
                 sites=np.zeros((n_chains, n_steps + 1, kmax, max(ndim, 1))),
                 values=np.zeros((n_chains, n_steps + 1, len(pnames), kmax)),
-                sigma=np.zeros((n_chains, n_steps + 1)),
+                sigma=np.zeros((n_chains, n_steps + 1)), corr=np.zeros((n_chains, n_steps + 1)),
                 lpr=np.zeros((n_chains, n_steps)), llr=np.zeros((n_chains, n_steps)),
                 accepted=np.zeros((n_chains, n_steps), np.int8), move=np.zeros((n_chains, n_steps), np.int8),
                 cursor=np.zeros((n_chains, n_steps + 1), np.int64),
@@ -296,6 +301,7 @@ def replay(bb, ing, n_chains, n_steps, seed0, name):
         k, s, v, sg = snapshot(chain.current_state, ps_name, pnames, tname, kmax, ndim)
         out["k"][c, 0], out["sites"][c, 0], out["values"][c, 0], out["sigma"][c, 0] = k, s, v, sg
         out["cursor"][c, 0] = TAPE.n
+        out["corr"][c, 0] = snapshot_corr(chain.current_state, tname)
         chain.save_current_iteration = False
         for t in range(n_steps):
             log.clear()
@@ -308,6 +314,7 @@ def replay(bb, ing, n_chains, n_steps, seed0, name):
             k, s, v, sg = snapshot(chain.current_state, ps_name, pnames, tname, kmax, ndim)
             out["k"][c, t + 1], out["sites"][c, t + 1], out["values"][c, t + 1], out["sigma"][c, t + 1] = k, s, v, sg
             out["cursor"][c, t + 1] = TAPE.n
+            out["corr"][c, t + 1] = snapshot_corr(chain.current_state, tname)
         tapes.append(TAPE.values[: TAPE.n].copy())
     L = max(t.size for t in tapes)
     tape = np.zeros((n_chains, L))
@@ -408,6 +415,12 @@ def kernels_golden(bb):
     out["ll_new"] = np.array(ll._get_misfit_and_det(s_new))
     out["ll_ratio_T1"] = np.array(ll.log_likelihood_ratio(s_old, s_new, 1.0))
     out["ll_ratio_T3"] = np.array(ll.log_likelihood_ratio(s_old, s_new, 3.0))
+    # correlated hierarchical noise (tridiagonal inverse covariance)
+    tgc = Target("t", dobs, std_min=0, std_max=1, std_perturb_std=0.1, noise_is_correlated=True)
+    llc = LogLikelihood(tgc, lambda s: None)
+    sc = State({"p": ps_dummy.copy(), "t": DataNoiseState(std=0.23, correlation=0.37)}, temperature=1)
+    sc.save_to_cache("t.dpred", dp_old)
+    out["ll_corr"] = np.array(llc._get_misfit_and_det(sc))
     # fixed (non-hierarchical) covariance: scalar and vector inverse covariance
     w = rng.uniform(0.5, 2.0, n)
     for tag, ci in (("s", 4.0), ("v", w)):
@@ -551,6 +564,8 @@ def main():
            name="partition_1d")
     replay(bb, synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour"), n_chains=4,
            n_steps=80, seed0=250, name="partition_1d_nb")
+    replay(bb, synthetic.partition_1d(n_data=30, kmin=2, kmax=12, correlated=True), n_chains=6, n_steps=80, seed0=270,
+           name="partition_1d_corr")
     replay(bb, synthetic.polyfit(), n_chains=8, n_steps=60, seed0=300, name="polyfit")
     replay(bb, synthetic.polyfit(all_gaussian=False), n_chains=4, n_steps=60, seed0=350, name="polyfit_nb")
     pt_golden(bb)

@@ -21,9 +21,12 @@ def _prior(p):
 
 def _target(ing, forward):
     t = ing["target"]
-    return dict(name=t["name"], dobs=np.asarray(ing["d_obs"], dtype=np.float64), hierarchical=True,
-                std_min=float(t["std_min"]), std_max=float(t["std_max"]), std_perturb_std=float(t["std_perturb_std"]),
-                cov_inv=None, forward=forward)
+    out = dict(name=t["name"], dobs=np.asarray(ing["d_obs"], dtype=np.float64), hierarchical=True,
+               std_min=float(t["std_min"]), std_max=float(t["std_max"]), std_perturb_std=float(t["std_perturb_std"]),
+               cov_inv=None, correlated=bool(t.get("noise_is_correlated", False)),
+               corr_min=float(t.get("correlation_min", 0.01)), corr_max=float(t.get("correlation_max", 1.0)),
+               corr_perturb_std=float(t.get("correlation_perturb_std", 0.1)), forward=forward)
+    return out
 
 
 def spec_from_ingredients(ing):
@@ -66,6 +69,15 @@ REPLAYS = {
     "tomo_small": tomo_small,
     "partition_1d": partition_small,
     "partition_1d_nb": lambda: partition_small("neighbour"),
+    "partition_1d_corr": lambda: synthetic.partition_1d(n_data=30, kmin=2, kmax=12, correlated=True),
     "polyfit": synthetic.polyfit,
     "polyfit_nb": lambda: synthetic.polyfit(all_gaussian=False),
 }
+
+
+# oracle-vs-device cases without a reference replay fixture
+EXTRA = {
+    "tomo_small_corr": lambda: synthetic.tomography_2d(nx=12, ny=10, n_sources_per_side=3, n_receivers=5, kmin=4,
+                                                       kmax=20, correlated=True),
+}
+ALL = {**REPLAYS, **EXTRA}

@@ -138,8 +138,8 @@ def test_things_that_cannot_run_on_the_device_raise():
         bb.likelihood.LogLikelihood(log_like_func=lambda s: 0.0)
     with pytest.raises(TypeError):
         bb.BaseBayesianInversion([None], [lambda s: (s, 0)], n_chains=1)
-    with pytest.raises(DeviceUnsupported):
-        bb.likelihood.Target("d", np.zeros(3), noise_is_correlated=True)
+    with pytest.raises(ValueError):
+        bb.likelihood.Target("d", np.zeros(3), noise_is_correlated=True, covariance_mat_inv=2.0)
     with pytest.raises(DeviceUnsupported):
         bb.prior.UniformPrior("v", vmin=[0, 1], vmax=[1, 2], perturb_std=0.1, position=[0, 1])
     with pytest.raises(DeviceUnsupported):

@@ -35,6 +35,8 @@ def _check_states(states, g, t, spec, rtol=1e-12):
         for j in range(len(sp["params"])):
             np.testing.assert_allclose(ss["values"][j], g["values"][c, t, j, :k], rtol=rtol, atol=1e-15)
         np.testing.assert_allclose(st["sigma"][0], g["sigma"][c, t], rtol=rtol)
+        if "corr" in g.files and not np.isnan(g["corr"][c, t]):
+            np.testing.assert_allclose(st["corr"][0], g["corr"][c, t], rtol=rtol)
 
 
 @pytest.mark.parametrize("name", list(problems.REPLAYS))
@@ -75,16 +77,18 @@ def test_step_replay_against_reference(name, golden_dir):
 def _oracle_state(st):
     sp = st["spaces"][0]
     return OC.ChainState([OC.SpaceState(sp["k"], None if sp["sites"] is None else np.array(sp["sites"]),
-                                        [np.array(v) for v in sp["values"]])], list(st["sigma"]), 1.0, [None])
+                                        [np.array(v) for v in sp["values"]])], list(st["sigma"]), 1.0, [None],
+                         list(st.get("corr") or [None]))
 
 
 @pytest.mark.parametrize("name,n_chains,n_steps", [("tomo_small", 96, 40), ("partition_1d", 70, 60),
-                                                   ("partition_1d_nb", 33, 60), ("polyfit", 64, 50)])
+                                                   ("partition_1d_nb", 33, 60), ("partition_1d_corr", 40, 60),
+                                                   ("tomo_small_corr", 70, 40), ("polyfit", 64, 50)])
 def test_philox_steps_against_oracle(name, n_chains, n_steps):
     """Counter-based streams: device and oracle draw the same Philox4x32-10 uniforms, so whole
     trajectories must agree (until a 1-ulp difference flips a decision, which the test tolerates
     only by comparing chains that are still in step)."""
-    spec = problems.spec_from_ingredients(problems.REPLAYS[name]())
+    spec = problems.spec_from_ingredients(problems.ALL[name]())
     seed, id0 = 1234567890123, 1000
     eng = _engine(spec, n_chains, seed=seed, chain_id0=id0)
     eng.init_states()
@@ -100,6 +104,8 @@ def test_philox_steps_against_oracle(name, n_chains, n_steps):
         for a, b in zip(d.spaces[0].values, st.spaces[0].values):
             np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-15)
         np.testing.assert_allclose(d.sigma[0], st.sigma[0], rtol=1e-14)
+        if st.corr[0] is not None:
+            np.testing.assert_allclose(d.corr[0], st.corr[0], rtol=1e-14)
     in_step = np.ones(n_chains, bool)
     for t in range(n_steps):
         eng.step(1)

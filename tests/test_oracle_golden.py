@@ -87,6 +87,7 @@ def test_misfit_logdet_ratio(kg):
     np.testing.assert_allclose(mn, kg["ll_new"], rtol=RTOL)
     for T, key in ((1.0, "ll_ratio_T1"), (3.0, "ll_ratio_T3")):
         np.testing.assert_allclose(OK.log_like_ratio(mo[0], mo[1], mn[0], mn[1], T), float(kg[key]), rtol=RTOL)
+    np.testing.assert_allclose(OK.misfit_and_logdet(kg["ll_dp_old"], dobs, std=0.23, corr=0.37), kg["ll_corr"], rtol=RTOL)
     np.testing.assert_allclose(OK.misfit_and_logdet(kg["ll_dp_old"], dobs, cov_inv=4.0), kg["ll_fixed_s"], rtol=RTOL)
     np.testing.assert_allclose(OK.misfit_and_logdet(kg["ll_dp_old"], dobs, cov_inv=kg["ll_w"]), kg["ll_fixed_v"], rtol=RTOL)
 
@@ -107,7 +108,9 @@ def _state_from_fixture(spec, g, c, t):
     elif ndim == 1:
         sites = g["sites"][c, t, :k, 0].copy()
     vals = [g["values"][c, t, j, :k].copy() for j in range(len(sp["params"]))]
-    st = OC.ChainState([OC.SpaceState(k, sites, vals)], [float(g["sigma"][c, t])], 1.0, [None])
+    corr = float(g["corr"][c, t]) if "corr" in g.files else float("nan")
+    st = OC.ChainState([OC.SpaceState(k, sites, vals)], [float(g["sigma"][c, t])], 1.0, [None],
+                       [None if math.isnan(corr) else corr])
     OC.evaluate(spec, st)
     return st
 
@@ -149,6 +152,9 @@ def _assert_state_close(a, b):
     for va, vb in zip(sa.values, sb.values):
         np.testing.assert_allclose(va, vb, rtol=RTOL, atol=1e-15)
     np.testing.assert_allclose(a.sigma[0], b.sigma[0], rtol=RTOL)
+    assert (a.corr[0] is None) == (b.corr[0] is None)
+    if a.corr[0] is not None:
+        np.testing.assert_allclose(a.corr[0], b.corr[0], rtol=RTOL)
 
 
 def test_pt_swap_rounds(golden_dir):
