@@ -144,7 +144,9 @@ def cuda_arm(args):
     eng.init_states()
     tempered = world > 1
     if tempered:
-        ladder = np.repeat(np.geomspace(1.0, 5.0, 16), world * C // 16)
+        # interleaved ladder: every rank holds all 16 temperatures, so the ranks stay load balanced (hot chains
+        # accept more births and carry more cells)
+        ladder = np.tile(np.geomspace(1.0, 5.0, 16), world * C // 16)
         eng.temperature.copy_(torch.as_tensor(ladder[rank * C:(rank + 1) * C]))
 
     def swap_round(r):
