@@ -75,7 +75,53 @@ REPLAYS = {
 }
 
 
+def joint_small():
+    """Two parameter spaces and three targets with different noise models: a fixed-dimension plain space read by a
+    linear forward (hierarchical noise) and a per-datum-weighted copy of it, and a trans-d Voronoi1D space with
+    Gaussian + Laplace parameters read by a 1-D lookup (fixed scalar inverse covariance).  Spec dict only."""
+    poly = synthetic.polyfit()
+    part = synthetic.partition_1d(n_data=25, kmin=1, kmax=9, birth_from="neighbour")
+    rng = np.random.default_rng(4)
+    plain = dict(name="coeffs", kind="plain", ndim=0, trans_d=False, kmin=1, kmax=1, kinit_max=1, vmin=[], vmax=[],
+                 site_std=[], birth_from="prior", params=[_prior(p) for p in poly["priors"]],
+                 weights=dict(birth=0, death=0, values=3, sites=0))
+    vor = dict(name="layers", kind="voronoi1d", ndim=1, trans_d=True, kmin=1, kmax=9, kinit_max=3, vmin=[0.0], vmax=[10.0],
+               site_std=[0.75], birth_from="neighbour",
+               params=[dict(name="y", kind="gaussian", a=0.0, b=15.0, perturb_std=3.0, perturb_std_birth=4.0),
+                       dict(name="z", kind="laplace", a=1.0, b=2.0, perturb_std=0.5, perturb_std_birth=0.5)],
+               weights=dict(birth=1, death=1, values=3, sites=1))
+
+    def tgt(name, dobs, hier, cov, fwd, **kw):
+        return dict(name=name, dobs=np.asarray(dobs, dtype=np.float64), hierarchical=hier, std_min=0.0, std_max=40.0,
+                    std_perturb_std=4.0, cov_inv=cov, correlated=False, corr_min=0.01, corr_max=1.0,
+                    corr_perturb_std=0.1, forward=fwd, **kw)
+
+    targets = [
+        tgt("poly", poly["d_obs"], True, None, dict(kind="linear", space=0, params=[0, 1, 2, 3], G=poly["G"])),
+        tgt("poly_w", poly["d_obs"] + 1.0, False, rng.uniform(0.001, 0.004, poly["d_obs"].size),
+            dict(kind="linear", space=0, params=[3, 2, 1, 0], G=poly["G"][:, ::-1].copy())),
+        tgt("steps", part["d_obs"], False, 0.04, dict(kind="lookup1d", space=1, param=0, x=part["x"])),
+    ]
+    return dict(spaces=[plain, vor], targets=targets)
+
+
+def tomo_joint_small():
+    """Ray tomography plus a plain space with its own linear target: exercises the pipeline mode with a
+    thread-evaluated target next to the ray target (spec dict only)."""
+    spec = spec_from_ingredients(tomo_small())
+    poly = synthetic.polyfit()
+    spec["spaces"].append(dict(name="coeffs", kind="plain", ndim=0, trans_d=False, kmin=1, kmax=1, kinit_max=1, vmin=[],
+                               vmax=[], site_std=[], birth_from="prior", params=[_prior(p) for p in poly["priors"]],
+                               weights=dict(birth=0, death=0, values=3, sites=0)))
+    spec["targets"].append(dict(name="poly", dobs=poly["d_obs"], hierarchical=True, std_min=0.0, std_max=40.0,
+                                std_perturb_std=4.0, cov_inv=None, correlated=False, corr_min=0.01, corr_max=1.0,
+                                corr_perturb_std=0.1,
+                                forward=dict(kind="linear", space=1, params=[0, 1, 2, 3], G=poly["G"])))
+    return spec
+
+
 # oracle-vs-device cases without a reference replay fixture
+SPECS = {"joint_small": joint_small, "tomo_joint_small": tomo_joint_small}
 EXTRA = {
     "tomo_small_corr": lambda: synthetic.tomography_2d(nx=12, ny=10, n_sources_per_side=3, n_receivers=5, kmin=4,
                                                        kmax=20, correlated=True),

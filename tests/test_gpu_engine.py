@@ -75,10 +75,10 @@ def test_step_replay_against_reference(name, golden_dir):
 
 
 def _oracle_state(st):
-    sp = st["spaces"][0]
-    return OC.ChainState([OC.SpaceState(sp["k"], None if sp["sites"] is None else np.array(sp["sites"]),
-                                        [np.array(v) for v in sp["values"]])], list(st["sigma"]), 1.0, [None],
-                         list(st.get("corr") or [None]))
+    spaces = [OC.SpaceState(sp["k"], None if sp["sites"] is None else np.array(sp["sites"]),
+                            [np.array(v) for v in sp["values"]]) for sp in st["spaces"]]
+    n_t = len(st["sigma"])
+    return OC.ChainState(spaces, list(st["sigma"]), 1.0, [None] * n_t, list(st.get("corr") or [None] * n_t))
 
 
 @pytest.mark.parametrize("name,n_chains,n_steps", [("tomo_small", 96, 40), ("partition_1d", 70, 60),
@@ -216,3 +216,47 @@ def test_incremental_raster_equals_brute_force_at_scale():
     assert eng.n_accepted.sum().item() > 0.2 * eng.n_proposed.sum().item()
     kk = eng.gather_space(0)[0].cpu().numpy()
     assert kk.min() >= 3 and kk.max() <= 300 and kk.std() > 0
+
+
+@pytest.mark.parametrize("name,n_chains,n_steps", [("joint_small", 80, 80), ("tomo_joint_small", 48, 60)])
+def test_multi_space_multi_target_against_oracle(name, n_chains, n_steps):
+    """Several parameter spaces and targets (hierarchical, per-datum and scalar inverse covariance; linear,
+    1-D lookup and ray forwards side by side): move ids, outer weights and the summed likelihood ratio
+    (LogLikelihood._get_misfit_and_det over all targets) against the oracle on shared Philox streams."""
+    spec = problems.SPECS[name]()
+    seed, id0 = 424242, 7
+    eng = _engine(spec, n_chains, seed=seed, chain_id0=id0)
+    eng.init_states()
+    states = [OC.init_state(spec, OR.PhiloxStream(seed, id0 + c, 0, OR.STREAM_INIT)) for c in range(n_chains)]
+    for c, d in enumerate(eng.fetch_states()):
+        o = _oracle_state(d)
+        for a, b in zip(o.spaces, states[c].spaces):
+            assert a.k == b.k
+            for va, vb in zip(a.values, b.values):
+                np.testing.assert_allclose(va, vb, rtol=1e-13, atol=1e-15)
+    in_step = np.ones(n_chains, bool)
+    seen = set()
+    for t in range(n_steps):
+        eng.step(1)
+        move, lpr = eng.move.cpu().numpy(), eng.log_prob_ratio.cpu().numpy()
+        llr, acc = eng.log_like_ratio.cpu().numpy(), eng.accepted.cpu().numpy()
+        for c in range(n_chains):
+            if not in_step[c]:
+                continue
+            states[c], info = OC.step(spec, states[c], OR.PhiloxStream(seed, id0 + c, t))
+            assert info["move"] == move[c], (c, t)
+            seen.add(int(move[c]))
+            if math.isinf(info["log_prob_ratio"]):
+                assert lpr[c] == info["log_prob_ratio"]
+            else:
+                np.testing.assert_allclose(lpr[c], info["log_prob_ratio"], rtol=1e-10, atol=1e-11)
+                np.testing.assert_allclose(llr[c], info["log_like_ratio"], rtol=1e-8, atol=1e-8)
+            if bool(acc[c]) != info["accepted"]:
+                in_step[c] = False
+    assert in_step.mean() > 0.9
+    assert len(seen) >= 6  # moves of both spaces and the noise move all occurred
+    mis, ld = eng.misfit_logdet()
+    for c in np.flatnonzero(in_step)[:10]:
+        m, l_ = OC.misfit_and_logdet(spec, states[c])
+        np.testing.assert_allclose(mis[c].item(), m, rtol=1e-10)
+        np.testing.assert_allclose(ld[c].item(), l_, rtol=1e-12, atol=1e-12)
