@@ -27,23 +27,42 @@ def _scalar(x, what):
 
 
 def compile_prior(p) -> dict:
+    """Prior -> dict(name, kind, a, b, perturb_std, perturb_std_birth[, table]).  Scalar hyper-parameters, or --
+    with a 1-D ``position`` -- a table of per-position hyper-parameters the device interpolates linearly."""
     name = _cls(p)
-    if getattr(p, "position", None) is not None:
-        raise DeviceUnsupported(f"prior {p.name!r}: position-dependent priors are not on the device yet")
-    std = _scalar(p.perturb_std, f"{p.name}.perturb_std")
-    std_birth = getattr(p, "perturb_std_birth", None)
-    std_birth = std if std_birth is None else _scalar(std_birth, f"{p.name}.perturb_std_birth")
     if name in ("UniformPrior", "UniformParameter"):
-        kind, a, b = "uniform", _scalar(p.vmin, "vmin"), _scalar(p.vmax, "vmax")
+        kind, a_name, b_name = "uniform", "vmin", "vmax"
     elif name in ("GaussianPrior", "GaussianParameter"):
-        kind, a, b = "gaussian", _scalar(p.mean, "mean"), _scalar(p.std, "std")
+        kind, a_name, b_name = "gaussian", "mean", "std"
     elif name == "LaplacePrior":
-        kind, a, b = "laplace", _scalar(p.mean, "mean"), _scalar(p.scale, "scale")
+        kind, a_name, b_name = "laplace", "mean", "scale"
     else:
         raise DeviceUnsupported(
             f"prior {p.name!r} of type {name}: only Uniform/Gaussian/LaplacePrior run on the device "
             "(user callables cannot run in a CUDA kernel and there is no CPU fallback)")
-    return dict(name=p.name, kind=kind, a=a, b=b, perturb_std=std, perturb_std_birth=std_birth)
+
+    def raw(attr):
+        # the reference stores position-dependent hyper-parameters as interpolating partials; the raw arrays are in
+        # its _repr_args (prior/_prior.py:35-40)
+        v = getattr(p, attr, None)
+        if callable(v) or v is None:
+            v = getattr(p, "_repr_args", {}).get(attr)
+        return v
+
+    std = raw("perturb_std")
+    std_birth = raw("perturb_std_birth")
+    std_birth = std if std_birth is None else std_birth
+    a, b = raw(a_name), raw(b_name)
+    position = getattr(p, "position", None)
+    if position is None:
+        return dict(name=p.name, kind=kind, a=_scalar(a, a_name), b=_scalar(b, b_name),
+                    perturb_std=_scalar(std, "perturb_std"), perturb_std_birth=_scalar(std_birth, "perturb_std_birth"))
+    pos = np.asarray(position, dtype=np.float64)
+    if pos.ndim != 1:
+        raise DeviceUnsupported(f"prior {p.name!r}: only 1-D `position` arrays are supported on the device")
+    col = lambda v: np.broadcast_to(np.asarray(v, dtype=np.float64), pos.shape).copy()  # noqa: E731
+    return dict(name=p.name, kind=kind, a=None, b=None, perturb_std=None, perturb_std_birth=None,
+                table=dict(position=pos.copy(), a=col(a), b=col(b), perturb_std=col(std), perturb_std_birth=col(std_birth)))
 
 
 def compile_space(ps) -> dict:
@@ -61,6 +80,8 @@ def compile_space(ps) -> dict:
     kinit_max = min(max(kinit_max, kmin), kmax)
     spec = dict(name=ps.name, trans_d=trans_d, kmin=kmin, kmax=kmax, kinit_max=kinit_max,
                 params=[compile_prior(p) for p in params])
+    if name != "Voronoi1D" and any(q.get("table") is not None for q in spec["params"]):
+        raise DeviceUnsupported(f"parameter space {ps.name!r}: position-dependent priors need a Voronoi1D space")
     if name in ("Voronoi1D", "Voronoi2D"):
         ndim = 1 if name == "Voronoi1D" else 2
         if getattr(ps, "polygon", None) is not None:

@@ -81,8 +81,17 @@ class Engine:
             s.w_birth, s.w_death, s.w_values, s.w_sites = w["birth"], w["death"], w["values"], w["sites"]
             for j, p in enumerate(sp["params"]):
                 s.prior_kind[j] = _PRIOR_KIND[p["kind"]]
-                s.prior_a[j], s.prior_b[j] = p["a"], p["b"]
-                s.perturb_std[j], s.perturb_std_birth[j] = p["perturb_std"], p["perturb_std_birth"]
+                tab = p.get("table")
+                if tab is None:
+                    s.prior_a[j], s.prior_b[j] = p["a"], p["b"]
+                    s.perturb_std[j], s.perturb_std_birth[j] = p["perturb_std"], p["perturb_std_birth"]
+                else:  # position-dependent hyper-parameters: [5][n] rows position, a, b, perturb_std, perturb_std_birth
+                    rows = np.stack([np.asarray(tab[k], dtype=np.float64) for k in
+                                     ("position", "a", "b", "perturb_std", "perturb_std_birth")])
+                    if np.any(np.diff(rows[0]) <= 0):
+                        raise ValueError(f"prior {p['name']!r}: `position` must be strictly ascending")
+                    s.n_pos[j] = rows.shape[1]
+                    s.pos_table[j] = self._const(rows, np.float64).data_ptr()
         for i, tg in enumerate(spec["targets"]):
             t = ps.targets[i]
             dobs = self._const(tg["dobs"], np.float64)

@@ -36,6 +36,7 @@ class SpaceSpec(C.Structure):
         ("prior_kind", C.c_int32 * MAX_PARAMS),
         ("prior_a", C.c_double * MAX_PARAMS), ("prior_b", C.c_double * MAX_PARAMS),
         ("perturb_std", C.c_double * MAX_PARAMS), ("perturb_std_birth", C.c_double * MAX_PARAMS),
+        ("n_pos", C.c_int32 * MAX_PARAMS), ("pos_table", _vp * MAX_PARAMS),
     ]
 
 

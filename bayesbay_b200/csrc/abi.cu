@@ -70,6 +70,11 @@ static int validate_spec(const bbb_problem_spec *P) {
         for (int p = 0; p < S.n_params; ++p) {
             if (S.prior_kind[p] < BBB_PRIOR_UNIFORM || S.prior_kind[p] > BBB_PRIOR_LAPLACE)
                 return fail(BBB_ERR_INVALID, "space %d param %d: prior kind", s, p);
+            if (S.n_pos[p] > 0) {  // table validated by the caller (device memory)
+                if (S.ndim != 1) return fail(BBB_ERR_UNSUPPORTED, "space %d param %d: position-dependent priors need a Voronoi1D space", s, p);
+                if (S.n_pos[p] < 2 || !S.pos_table[p]) return fail(BBB_ERR_INVALID, "space %d param %d: position table", s, p);
+                continue;
+            }
             if (S.prior_kind[p] == BBB_PRIOR_UNIFORM ? !(S.prior_a[p] < S.prior_b[p]) : !(S.prior_b[p] > 0))
                 return fail(BBB_ERR_INVALID, "space %d param %d: prior hyper-parameters", s, p);
             if (!(S.perturb_std[p] > 0) || !(S.perturb_std_birth[p] > 0))

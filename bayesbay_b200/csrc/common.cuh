@@ -70,6 +70,37 @@ __device__ __forceinline__ double prior_sample(int kind, double a, double b, Rng
     return rng.laplace(a, b);
 }
 
+// Hyper-parameters of parameter p at site position x: Prior.get_hyper_param (prior/_prior.py:257-297) with
+// interpolate_linear_1d (_utils_1d.pyx:68-84) for position-dependent ones, the scalars otherwise.
+struct PriorAt {
+    int kind;
+    double a, b, pstd, pstd_birth;
+};
+__device__ inline PriorAt prior_at(const bbb_space_spec &S, int p, double x) {
+    PriorAt out{S.prior_kind[p], S.prior_a[p], S.prior_b[p], S.perturb_std[p], S.perturb_std_birth[p]};
+    const int n = S.n_pos[p];
+    if (n <= 0) return out;
+    const double *X = S.pos_table[p];
+    int i0, i1;
+    if (x <= X[0]) { i0 = i1 = 0; }
+    else if (x >= X[n - 1]) { i0 = i1 = n - 1; }
+    else {
+        i0 = 0;
+        while (!(X[i0] <= x && x <= X[i0 + 1])) ++i0;
+        i1 = i0 + 1;
+    }
+    auto at = [&](int row) {
+        const double y0 = X[(long long)row * n + i0];
+        if (i1 == i0) return y0;
+        return y0 + (x - X[i0]) * (X[(long long)row * n + i1] - y0) / (X[i1] - X[i0]);
+    };
+    out.a = at(1); out.b = at(2); out.pstd = at(3); out.pstd_birth = at(4);
+    return out;
+}
+__device__ __forceinline__ double prior_log_pdf(const PriorAt &q, double v) { return prior_log_pdf(q.kind, q.a, q.b, v); }
+__device__ __forceinline__ double prior_value_ratio(const PriorAt &q, double o, double n) { return prior_value_ratio(q.kind, q.a, q.b, o, n); }
+__device__ __forceinline__ double prior_sample(const PriorAt &q, Rng &rng) { return prior_sample(q.kind, q.a, q.b, rng); }
+
 __device__ __forceinline__ int n_move_types(const bbb_problem_spec &P) { return 4 * P.n_spaces + 1; }
 
 }  // namespace bbb

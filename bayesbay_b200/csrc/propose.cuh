@@ -155,9 +155,10 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         e.rm = e.ins = idx;
         for (int d = 0; d < S.ndim; ++d) e.site[d] = site_ref(B, S, s, cur, d, idx, c);
         for (int p = 0; p < S.n_params; ++p) {
+            const PriorAt q = prior_at(S, p, e.site[0]);
             const double old_v = value_ref(B, S, s, cur, p, idx, c);
-            const double new_v = old_v + rng.normal(0.0, S.perturb_std[p]);
-            e.lpr += prior_value_ratio(S.prior_kind[p], S.prior_a[p], S.prior_b[p], old_v, new_v);
+            const double new_v = old_v + rng.normal(0.0, q.pstd);
+            e.lpr += prior_value_ratio(q, old_v, new_v);
             e.vals[p] = new_v;
         }
     } else if (inner == BBB_MOVE_SITES) {
@@ -178,6 +179,10 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
                 for (int d = 0; d < S.ndim; ++d) e.site[d] = cand[d];
                 break;
             }
+        }
+        for (int p = 0; p < S.n_params; ++p) {
+            if (S.n_pos[p] <= 0) continue;  // log p(v; new site) - log p(v; old site), _voronoi.py:220-226
+            e.lpr += prior_log_pdf(prior_at(S, p, e.site[0]), e.vals[p]) - prior_log_pdf(prior_at(S, p, old_site[0]), e.vals[p]);
         }
         if (S.ndim == 1) {
             int pos = 0;
@@ -200,20 +205,19 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
             for (int d = 0; d < S.ndim; ++d) e.site[d] = rng.uniform(S.vmin[d], S.vmax[d]);
             if (S.birth_from == BBB_BIRTH_FROM_PRIOR) {
                 // _initialize_params_from_prior (discretization/_discretization.py:299-321)
-                for (int p = 0; p < S.n_params; ++p)
-                    e.vals[p] = prior_sample(S.prior_kind[p], S.prior_a[p], S.prior_b[p], rng);
+                for (int p = 0; p < S.n_params; ++p) e.vals[p] = prior_sample(prior_at(S, p, e.site[0]), rng);
             } else {
                 // _initialize_params_from_neighbour (discretization/_discretization.py:323-375)
                 const int i_near = (S.ndim == 1) ? nearest_1d(B, S, s, cur, c, k, -1, e.site[0])
                                                  : nearest_2d(B, S, s, cur, c, k, -1, e.site[0], e.site[1], rng.coop);
                 for (int p = 0; p < S.n_params; ++p) {
-                    const double theta = S.perturb_std_birth[p];
+                    const PriorAt q = prior_at(S, p, e.site[0]);
+                    const double theta = q.pstd_birth;
                     const double old_v = value_ref(B, S, s, cur, p, i_near, c);
                     const double new_v = old_v + rng.normal(0.0, theta);
                     e.vals[p] = new_v;
                     const double diff = new_v - old_v;
-                    e.lpr += prior_log_pdf(S.prior_kind[p], S.prior_a[p], S.prior_b[p], new_v) +
-                             (log(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta)));
+                    e.lpr += prior_log_pdf(q, new_v) + (log(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta)));
                 }
             }
             if (S.ndim == 1) {
@@ -240,11 +244,12 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
                                            : nearest_2d(B, S, s, cur, c, k, e.rm, pos[0], pos[1], rng.coop);
                 i_near += (i_near >= e.rm) ? 1 : 0;  // back to indices of the current state
                 for (int p = 0; p < S.n_params; ++p) {
-                    const double theta = S.perturb_std_birth[p];
+                    const PriorAt q = prior_at(S, p, pos[0]);
+                    const double theta = q.pstd_birth;
                     const double gone = value_ref(B, S, s, cur, p, e.rm, c);
                     const double near_v = value_ref(B, S, s, cur, p, i_near, c);
                     const double diff = gone - near_v;
-                    e.lpr -= prior_log_pdf(S.prior_kind[p], S.prior_a[p], S.prior_b[p], gone);
+                    e.lpr -= prior_log_pdf(q, gone);
                     e.lpr -= log(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta));
                 }
             }

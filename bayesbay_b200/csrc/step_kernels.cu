@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(STEP_THREADS) k_init_states(const EngineParams
         }
         for (int p = 0; p < S.n_params; ++p)
             for (int j = 0; j < k; ++j)
-                value_ref(B, S, s, 0, p, j, c) = prior_sample(S.prior_kind[p], S.prior_a[p], S.prior_b[p], rng);
+                value_ref(B, S, s, 0, p, j, c) =
+                    prior_sample(prior_at(S, p, S.ndim == 1 ? site_ref(B, S, s, 0, 0, j, c) : 0.0), rng);
         k_ref(B, s, 0, c) = k;
         k_ref(B, s, 1, c) = k;
         B.sel[s][c] = 0;

@@ -72,6 +72,12 @@ typedef struct {
     int32_t prior_kind[BBB_MAX_PARAMS];
     double prior_a[BBB_MAX_PARAMS], prior_b[BBB_MAX_PARAMS];
     double perturb_std[BBB_MAX_PARAMS], perturb_std_birth[BBB_MAX_PARAMS];
+    /* position-dependent hyper-parameters (Prior(..., position=...), prior/_prior.py:257-297; Voronoi1D only):
+     * n_pos[p] > 0 -> pos_table[p] is a device array [5][n_pos] with rows position (ascending), a, b,
+     * perturb_std, perturb_std_birth, linearly interpolated at the cell's site (interpolate_linear_1d,
+     * _utils_1d.pyx:68-84) and overriding the scalars above */
+    int32_t n_pos[BBB_MAX_PARAMS];
+    const double *pos_table[BBB_MAX_PARAMS];
 } bbb_space_spec;
 
 typedef struct {

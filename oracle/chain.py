@@ -90,9 +90,10 @@ def n_move_types(spec):
 # --------------------------------------------------------------------------- #
 # I1: initialisation
 # --------------------------------------------------------------------------- #
-def _prior_sample(p, s):
+def _prior_sample(p, s, position=None):
     """``UniformPrior.sample`` (prior/_prior.py:390-394), ``GaussianPrior.sample`` (:571-575),
-    ``LaplacePrior.sample``."""
+    ``LaplacePrior.sample``, hyper-parameters taken at ``position``."""
+    p = K.prior_at(p, position)
     if p["kind"] == "uniform":
         return R.draw_uniform(s, p["a"], p["b"])
     if p["kind"] == "gaussian":
@@ -121,7 +122,8 @@ def init_state(spec, s, temperature=1.0):
             sites = np.sort(np.array([_sample_site(sp, s) for _ in range(k)]))
         elif sp["ndim"] == 2:
             sites = np.array([_sample_site(sp, s) for _ in range(k)]).reshape(k, 2)
-        values = [np.array([_prior_sample(p, s) for _ in range(k)]) for p in sp["params"]]
+        values = [np.array([_prior_sample(p, s, None if sites is None or sp["ndim"] != 1 else sites[j]) for j in range(k)])
+                  for p in sp["params"]]
         spaces.append(SpaceState(k, sites, values))
     sigma, corr = [], []
     for t in spec["targets"]:
@@ -198,6 +200,7 @@ def _move_values(sp, ss, s):
     new = ss.copy()
     lpr = 0.0
     for j, p in enumerate(sp["params"]):
+        p = K.prior_at(p, ss.sites[idx] if sp["ndim"] == 1 else None)
         old = float(ss.values[j][idx])
         val = old + R.draw_normal(s, 0.0, p["perturb_std"])
         lpr += K.prior_value_ratio(p, old, val)
@@ -211,11 +214,16 @@ def _move_site(sp, ss, s):
     idx = R.draw_randint(s, 0, ss.k - 1)
     new = ss.copy()
     new.sites[idx] = _perturb_site(sp, ss.sites[idx], s)
+    lpr = 0.0
+    for j, p in enumerate(sp["params"]):
+        if p.get("table") is not None:  # position-dependent prior: log p(v; new site) - log p(v; old site), :220-226
+            v = float(ss.values[j][idx])
+            lpr += K.prior_log_pdf(K.prior_at(p, new.sites[idx]), v) - K.prior_log_pdf(K.prior_at(p, ss.sites[idx]), v)
     if sp["ndim"] == 1:
         order = np.argsort(new.sites, kind="stable")
         new.sites = new.sites[order]
         new.values = [v[order] for v in new.values]
-    return new, 0.0
+    return new, lpr
 
 
 def _birth(sp, ss, s):
@@ -231,11 +239,13 @@ def _birth(sp, ss, s):
     site = _sample_site(sp, s)
     lpr = 0.0
     born = []
+    pos = site if sp["ndim"] == 1 else None
     if sp["birth_from"] == "prior":
-        born = [_prior_sample(p, s) for p in sp["params"]]
+        born = [_prior_sample(p, s, pos) for p in sp["params"]]
     else:
         i_near = _nearest(sp, ss.sites, site)
         for j, p in enumerate(sp["params"]):
+            p = K.prior_at(p, pos)
             theta = p["perturb_std_birth"]
             old = float(ss.values[j][i_near])
             val = old + R.draw_normal(s, 0.0, theta)
@@ -267,6 +277,7 @@ def _death(sp, ss, s):
         pos = ss.sites[i_rm]
         i_near = _nearest(sp, sites, pos)
         for j, p in enumerate(sp["params"]):
+            p = K.prior_at(p, pos if sp["ndim"] == 1 else None)
             theta = p["perturb_std_birth"]
             gone = float(ss.values[j][i_rm])
             near = float(vals[j][i_near])

@@ -202,6 +202,29 @@ def log_like_ratio(old_misfit, old_logdet, new_misfit, new_logdet, temperature=1
     return (old_logdet - new_logdet + old_misfit - new_misfit) / 2 / temperature
 
 
+def interpolate_linear_1d(xp, x, y):
+    """``_interpolate_linear_1d`` (src/bayesbay/_utils_1d.pyx:68-84): clamp outside, linear inside."""
+    if xp <= x[0]:
+        return float(y[0])
+    if xp >= x[-1]:
+        return float(y[-1])
+    i = 0
+    while not (x[i] <= xp <= x[i + 1]):
+        i += 1
+    return float(y[i] + (xp - x[i]) * (y[i + 1] - y[i]) / (x[i + 1] - x[i]))
+
+
+def prior_at(p, position=None):
+    """Hyper-parameters of a prior at a position: ``Prior.get_hyper_param`` (src/bayesbay/prior/_prior.py:257-297).
+    ``p["table"] = dict(position, a, b, perturb_std, perturb_std_birth)`` holds position-dependent ones."""
+    tab = p.get("table")
+    if tab is None:
+        return p
+    x = float(position)
+    return dict(kind=p["kind"], name=p["name"], **{k: interpolate_linear_1d(x, tab["position"], tab[k])
+                                                   for k in ("a", "b", "perturb_std", "perturb_std_birth")})
+
+
 def prior_log_pdf(p, v):
     """``UniformPrior.log_prior`` (src/bayesbay/prior/_prior.py:453-481), ``GaussianPrior.log_prior``
     (:652-682), ``LaplacePrior.log_prior`` (:853-881) with scalar hyper-parameters."""

@@ -566,6 +566,8 @@ def main():
            n_steps=80, seed0=250, name="partition_1d_nb")
     replay(bb, synthetic.partition_1d(n_data=30, kmin=2, kmax=12, correlated=True), n_chains=6, n_steps=80, seed0=270,
            name="partition_1d_corr")
+    replay(bb, synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour", position_dependent=True),
+           n_chains=6, n_steps=100, seed0=280, name="partition_1d_posdep")
     replay(bb, synthetic.polyfit(), n_chains=8, n_steps=60, seed0=300, name="polyfit")
     replay(bb, synthetic.polyfit(all_gaussian=False), n_chains=4, n_steps=60, seed0=350, name="polyfit_nb")
     pt_golden(bb)

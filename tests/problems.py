@@ -15,8 +15,16 @@ def _prior(p):
         a, b = p["mean"], p["std"]
     else:
         a, b = p["mean"], p["scale"]
+    std_birth = p.get("perturb_std_birth")
+    std_birth = p["perturb_std"] if std_birth is None else std_birth
+    if p.get("position") is not None:
+        pos = np.asarray(p["position"], dtype=np.float64)
+        col = lambda v: np.broadcast_to(np.asarray(v, dtype=np.float64), pos.shape).copy()  # noqa: E731
+        return dict(name=p["name"], kind=kind, a=None, b=None, perturb_std=None, perturb_std_birth=None,
+                    table=dict(position=pos, a=col(a), b=col(b), perturb_std=col(p["perturb_std"]),
+                               perturb_std_birth=col(std_birth)))
     return dict(name=p["name"], kind=kind, a=float(a), b=float(b), perturb_std=float(p["perturb_std"]),
-                perturb_std_birth=float(p.get("perturb_std_birth") or p["perturb_std"]))
+                perturb_std_birth=float(std_birth))
 
 
 def _target(ing, forward):
@@ -70,6 +78,8 @@ REPLAYS = {
     "partition_1d": partition_small,
     "partition_1d_nb": lambda: partition_small("neighbour"),
     "partition_1d_corr": lambda: synthetic.partition_1d(n_data=30, kmin=2, kmax=12, correlated=True),
+    "partition_1d_posdep": lambda: synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour",
+                                                          position_dependent=True),
     "polyfit": synthetic.polyfit,
     "polyfit_nb": lambda: synthetic.polyfit(all_gaussian=False),
 }

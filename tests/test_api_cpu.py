@@ -122,7 +122,7 @@ def test_compiler_accepts_objects_of_the_unmodified_reference():
     import make_golden
 
     ref = make_golden.import_reference()
-    for name in ("tomo_small", "partition_1d", "polyfit_nb"):
+    for name in ("tomo_small", "partition_1d", "polyfit_nb", "partition_1d_corr", "partition_1d_posdep"):
         ing = problems.REPLAYS[name]()
         par, ll = synthetic.build_problem(ing, ref, lambda i: (lambda state: None))
         # the reference wraps forwards; swap in the device operator description for compilation
@@ -140,8 +140,12 @@ def test_things_that_cannot_run_on_the_device_raise():
         bb.BaseBayesianInversion([None], [lambda s: (s, 0)], n_chains=1)
     with pytest.raises(ValueError):
         bb.likelihood.Target("d", np.zeros(3), noise_is_correlated=True, covariance_mat_inv=2.0)
-    with pytest.raises(DeviceUnsupported):
-        bb.prior.UniformPrior("v", vmin=[0, 1], vmax=[1, 2], perturb_std=0.1, position=[0, 1])
+    with pytest.raises(DeviceUnsupported):  # N-D position grids (LinearNDInterpolator) are not on the device
+        bb.prior.UniformPrior("v", vmin=[0, 1], vmax=[1, 2], perturb_std=0.1, position=[[0, 0], [1, 1]])
+    pd = bb.prior.UniformPrior("v", vmin=[0, 1], vmax=[1, 2], perturb_std=0.1, position=[0, 1])
+    with pytest.raises(DeviceUnsupported):  # position-dependent priors need sites: Voronoi1D only
+        _compile.compile_problem(bb.parameterization.Parameterization(
+            bb.parameterization.ParameterSpace("flat", n_dimensions=2, parameters=[pd])))
     with pytest.raises(DeviceUnsupported):
         bb.discretization.Voronoi2D("v", polygon=[(0, 0), (1, 0), (1, 1)])
     cp = bb.prior.CustomPrior("c", lambda v: 0.0, lambda: 0.0, perturb_std=1.0)
@@ -226,3 +230,23 @@ def test_save_schedule_follows_the_reference_rule():
     assert saves[0] == 600 and saves[-1] == 2000 and len(saves) == 15
     with pytest.raises(ValueError):
         save_schedule(0, 10, 0, 0)
+
+
+def test_position_dependent_prior_host_api():
+    """Hyper-parameters interpolated at a position (reference prior/_prior.py:257-297, _utils_1d.pyx:68-84)."""
+    import math
+
+    p = bb.prior.UniformPrior("y", vmin=[-35.0, -20.0, -35.0], vmax=[35.0, 40.0, 10.0], perturb_std=[3.5, 2.0, 4.0],
+                              position=[0.0, 5.0, 10.0])
+    assert p.get_vmin_vmax(2.5) == (-27.5, 37.5) and p.get_vmin_vmax(-1) == (-35.0, 35.0) and p.get_vmin_vmax(99) == (-35.0, 10.0)
+    assert p.get_perturb_std(7.5) == 3.0 and p.get_perturb_std_birth(7.5) == 3.0
+    assert p.log_prior(0.0, 2.5) == -math.log(65.0) and p.log_prior(39.0, 2.5) == -math.inf
+    with pytest.raises(ValueError):
+        p.get_vmin_vmax(None)
+    g = bb.prior.GaussianPrior("g", mean=[0.0, 10.0], std=2.0, perturb_std=0.5, position=[0.0, 1.0])
+    assert g.get_mean(0.25) == 2.5 and g.get_std(0.25) == 2.0
+    spec = _compile.compile_prior(p)
+    assert spec["table"]["a"].tolist() == [-35.0, -20.0, -35.0] and spec["table"]["perturb_std_birth"].tolist() == [3.5, 2.0, 4.0]
+    ing = problems.REPLAYS["partition_1d_posdep"]()
+    par, ll = synthetic.build_problem(ing, bb, device_forward)
+    _same(_compile.compile_problem(par, ll), problems.spec_from_ingredients(ing))

@@ -83,7 +83,8 @@ def _oracle_state(st):
 
 @pytest.mark.parametrize("name,n_chains,n_steps", [("tomo_small", 96, 40), ("partition_1d", 70, 60),
                                                    ("partition_1d_nb", 33, 60), ("partition_1d_corr", 40, 60),
-                                                   ("tomo_small_corr", 70, 40), ("polyfit", 64, 50)])
+                                                   ("partition_1d_posdep", 50, 80), ("tomo_small_corr", 70, 40),
+                                                   ("polyfit", 64, 50)])
 def test_philox_steps_against_oracle(name, n_chains, n_steps):
     """Counter-based streams: device and oracle draw the same Philox4x32-10 uniforms, so whole
     trajectories must agree (until a 1-ulp difference flips a decision, which the test tolerates
