@@ -125,10 +125,10 @@ def compile_target(tgt, fwd, space_index: dict, spaces: list) -> dict:
                 raise DeviceUnsupported(f"target {tgt.name!r}: only scalar or per-datum inverse covariances are on the device")
             spec["cov_inv"] = cov
     kind = getattr(fwd, "kind", None)
-    if kind not in ("ray2d", "lookup1d", "linear"):
+    if kind not in ("ray2d", "lookup1d", "linear", "polynomial"):
         raise TypeError(
             f"forward function of target {tgt.name!r} is {fwd!r}: the device engine only runs the forward operators "
-            "of bayesbay_b200.forward (RayTomographyForward, NearestLookup1D, LinearForward). Arbitrary Python "
+            "of bayesbay_b200.forward (RayTomographyForward, NearestLookup1D, LinearForward, PolynomialForward). Arbitrary Python "
             "callables cannot run in a CUDA kernel and there is no CPU fallback.")
     if fwd.param_space_name not in space_index:
         raise ValueError(f"forward of target {tgt.name!r} reads unknown parameter space {fwd.param_space_name!r}")
@@ -148,6 +148,10 @@ def compile_target(tgt, fwd, space_index: dict, spaces: list) -> dict:
         if sp["kind"] != "voronoi1d":
             raise ValueError("NearestLookup1D needs a Voronoi1D parameter space")
         spec["forward"] = dict(kind="lookup1d", space=s, param=pnames.index(fwd.param_name), x=fwd.x)
+    elif kind == "polynomial":
+        if sp["kind"] != "plain":
+            raise ValueError("PolynomialForward needs a plain ParameterSpace")
+        spec["forward"] = dict(kind="polynomial", space=s, param=pnames.index(fwd.param_name), x=fwd.x)
     else:
         if sp["trans_d"]:
             raise ValueError("LinearForward needs a fixed-dimension parameter space")

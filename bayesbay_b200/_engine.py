@@ -20,7 +20,7 @@ from . import _lib as L
 
 _PRIOR_KIND = {"uniform": L.PRIOR_UNIFORM, "gaussian": L.PRIOR_GAUSSIAN, "laplace": L.PRIOR_LAPLACE}
 _SPACE_KIND = {"plain": L.SPACE_PLAIN, "voronoi1d": L.SPACE_VORONOI1D, "voronoi2d": L.SPACE_VORONOI2D}
-_FWD_KIND = {"ray2d": L.FWD_RAY2D, "lookup1d": L.FWD_LOOKUP1D, "linear": L.FWD_LINEAR}
+_FWD_KIND = {"ray2d": L.FWD_RAY2D, "lookup1d": L.FWD_LOOKUP1D, "linear": L.FWD_LINEAR, "polynomial": L.FWD_POLYNOMIAL}
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -130,11 +130,11 @@ class Engine:
                 t.data = self._const(f["data"], np.float64).data_ptr()
                 t.points_x = self._const(pts[:, 0], np.float64).data_ptr()
                 t.points_y = self._const(pts[:, 1], np.float64).data_ptr()
-            elif f["kind"] == "lookup1d":
+            elif f["kind"] in ("lookup1d", "polynomial"):
                 t.param = f["param"]
                 x = np.asarray(f["x"], dtype=np.float64)
                 if x.size != t.n_data:
-                    raise ValueError("lookup positions do not match the number of data")
+                    raise ValueError("data positions do not match the number of data")
                 t.x = self._const(x, np.float64).data_ptr()
             else:
                 G = np.asarray(f["G"], dtype=np.float64)

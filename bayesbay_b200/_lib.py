@@ -18,7 +18,7 @@ ABI_VERSION = 1
 SPACE_PLAIN, SPACE_VORONOI1D, SPACE_VORONOI2D = 0, 1, 2
 PRIOR_UNIFORM, PRIOR_GAUSSIAN, PRIOR_LAPLACE = 0, 1, 2
 BIRTH_FROM_PRIOR, BIRTH_FROM_NEIGHBOUR = 0, 1
-FWD_RAY2D, FWD_LOOKUP1D, FWD_LINEAR = 0, 1, 2
+FWD_RAY2D, FWD_LOOKUP1D, FWD_LINEAR, FWD_POLYNOMIAL = 0, 1, 2, 3
 TRANSFORM_IDENTITY, TRANSFORM_RECIPROCAL = 0, 1
 COV_HIERARCHICAL, COV_SCALAR, COV_VECTOR = 0, 1, 2
 MOVE_BIRTH, MOVE_DEATH, MOVE_VALUES, MOVE_SITES = 0, 1, 2, 3

@@ -107,6 +107,9 @@ static int validate_spec(const bbb_problem_spec *P) {
         } else if (T.fwd_kind == BBB_FWD_LOOKUP1D) {
             if (S.kind != BBB_SPACE_VORONOI1D) return fail(BBB_ERR_INVALID, "target %d: lookup1d forward needs a Voronoi1D space", t);
             if (T.param < 0 || T.param >= S.n_params || !T.x) return fail(BBB_ERR_INVALID, "target %d: lookup1d arrays", t);
+        } else if (T.fwd_kind == BBB_FWD_POLYNOMIAL) {
+            if (S.kind != BBB_SPACE_PLAIN) return fail(BBB_ERR_INVALID, "target %d: polynomial forward needs a plain ParameterSpace", t);
+            if (T.param < 0 || T.param >= S.n_params || !T.x) return fail(BBB_ERR_INVALID, "target %d: polynomial arrays", t);
         } else if (T.fwd_kind == BBB_FWD_LINEAR) {
             if (S.trans_d) return fail(BBB_ERR_INVALID, "target %d: linear forward needs a fixed-dimension space", t);
             if (T.n_lin_params < 1 || T.n_lin_params > BBB_MAX_LINEAR_PARAMS || !T.G)

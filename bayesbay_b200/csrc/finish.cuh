@@ -77,6 +77,19 @@ __device__ inline Phi3 small_target_phi(const bbb_problem_spec &P, const bbb_buf
             if (idx_out) idx_out[(long long)r * C + c] = i;
             acc.add(r, T.n_data, d - T.dobs[r], data_weight(T, r));
         }
+    } else if (T.fwd_kind == BBB_FWD_POLYNOMIAL) {
+        // np.vander(x, k, increasing=True) @ m (03_transd_polyfit.ipynb cell 5): powers by repeated multiplication
+        const int k = k_ref(B, s, slot, c);
+        for (int r = 0; r < T.n_data; ++r) {
+            const double xr = T.x[r];
+            double pw = 1.0, d = 0.0;
+            for (int j = 0; j < k; ++j) {
+                d += value_ref(B, S, s, slot, T.param, j, c) * pw;
+                pw *= xr;
+            }
+            if (dpred_out) dpred_out[(long long)r * C + c] = d;
+            acc.add(r, T.n_data, d - T.dobs[r], data_weight(T, r));
+        }
     } else if (T.fwd_kind == BBB_FWD_LINEAR) {
         // fwd_operator @ m (02_hierarchical_polyfit.ipynb cell 12)
         const int K = S.kmax;

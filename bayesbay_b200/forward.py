@@ -9,7 +9,9 @@ tutorials are provided as operator *descriptors* that carry the arrays the engin
   (docs/source/tutorials/31_sw_tomography.ipynb cell 12, tests/21_test_voronoi_2d.py:57-68);
 * :class:`NearestLookup1D` -- ``Voronoi1D.interpolate_tessellation(sites, values, x, 'nuclei')``
   (discretization/_voronoi.py:705-732; the lookup of 42_transd_partition_mod.ipynb cell 11);
-* :class:`LinearForward` -- ``G @ m`` (02_hierarchical_polyfit.ipynb cell 12).
+* :class:`LinearForward` -- ``G @ m`` (02_hierarchical_polyfit.ipynb cell 12);
+* :class:`PolynomialForward` -- ``np.vander(x, len(m), True) @ m`` on a trans-dimensional ``ParameterSpace``
+  (03_transd_polyfit.ipynb cell 5).
 
 They are listed where the reference lists forward callables.  Calling one on the host raises: the
 numpy adapters that turn a descriptor into a callable for the *unmodified reference* live in
@@ -19,7 +21,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["ForwardOperator", "RayTomographyForward", "NearestLookup1D", "LinearForward"]
+__all__ = ["ForwardOperator", "RayTomographyForward", "NearestLookup1D", "LinearForward", "PolynomialForward"]
 
 
 class ForwardOperator:
@@ -121,3 +123,20 @@ class LinearForward(ForwardOperator):
     @property
     def n_data(self):
         return self.G.shape[0]
+
+
+class PolynomialForward(ForwardOperator):
+    """``d_pred = np.vander(x, k, increasing=True) @ state[ps][param]`` with ``k`` the current number of
+    dimensions of a (trans-dimensional) ``ParameterSpace``: the forward of the trans-d polynomial regression
+    tutorial."""
+
+    kind = "polynomial"
+
+    def __init__(self, x, param_space_name, param_name):
+        self.x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        self.param_space_name = param_space_name
+        self.param_name = param_name
+
+    @property
+    def n_data(self):
+        return self.x.size

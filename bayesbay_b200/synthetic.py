@@ -20,6 +20,8 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = [
+    "transd_polyfit",
+    "partition_1d_fixed",
     "straight_ray_csr",
     "regular_grid_points",
     "checkerboard",
@@ -229,6 +231,29 @@ def polyfit(n_data=15, noise_std=20.0, seed=30, all_gaussian=True):
     )
 
 
+def transd_polyfit(n_data=20, noise_std=20.0, seed=30, kmin=1, kmax=8):
+    """Trans-dimensional polynomial regression: the number of coefficients is unknown
+    (docs/source/tutorials/03_transd_polyfit.ipynb); known data noise (fixed scalar inverse covariance)."""
+    x = np.linspace(-5.0, 10.0, n_data)
+    truth = np.array([20.0, -10.0, -3.0, 1.0])
+    rng = np.random.RandomState(seed)
+    d_obs = np.vander(x, 4, True) @ truth + rng.normal(0.0, noise_std, n_data)
+    return dict(
+        kind="transd_polyfit", x=x, d_obs=d_obs, truth=truth,
+        prior=dict(name="coefficients", vmin=-25.0, vmax=25.0, perturb_std=0.5),
+        space=dict(name="my_param_space", n_dimensions_min=kmin, n_dimensions_max=kmax),
+        target=dict(name="my_data", covariance_mat_inv=1.0 / noise_std ** 2),
+    )
+
+
+def partition_1d_fixed(n_data=30, n_cells=9, **kw):
+    """Fixed number of Voronoi cells (docs/source/tutorials/41_simple_partition_mod.ipynb): only value and site
+    moves."""
+    ing = partition_1d(n_data=n_data, **kw)
+    ing["voronoi"] = dict(name="voronoi", vmin=0.0, vmax=10.0, perturb_std=0.75, n_dimensions=n_cells)
+    return ing
+
+
 # --------------------------------------------------------------------------- #
 # API-object builder (works with bayesbay_b200 AND the unmodified reference)
 # --------------------------------------------------------------------------- #
@@ -248,6 +273,9 @@ def build_problem(ing, bb, make_forward):
     elif kind == "partition_1d":
         y = bb.prior.UniformPrior(**ing["prior"])
         space = bb.discretization.Voronoi1D(parameters=[y], **ing["voronoi"])
+    elif kind == "transd_polyfit":
+        coeff = bb.prior.UniformPrior(**ing["prior"])
+        space = bb.parameterization.ParameterSpace(parameters=[coeff], **ing["space"])
     elif kind == "polyfit":
         params = []
         for p in ing["priors"]:

@@ -51,7 +51,7 @@ enum { BBB_SPACE_PLAIN = 0, BBB_SPACE_VORONOI1D = 1, BBB_SPACE_VORONOI2D = 2 };
 enum { BBB_PRIOR_UNIFORM = 0, BBB_PRIOR_GAUSSIAN = 1, BBB_PRIOR_LAPLACE = 2 };
 enum { BBB_BIRTH_FROM_PRIOR = 0, BBB_BIRTH_FROM_NEIGHBOUR = 1 };
 /* forward operators (the user forward functions of the tutorials) */
-enum { BBB_FWD_RAY2D = 0, BBB_FWD_LOOKUP1D = 1, BBB_FWD_LINEAR = 2 };
+enum { BBB_FWD_RAY2D = 0, BBB_FWD_LOOKUP1D = 1, BBB_FWD_LINEAR = 2, BBB_FWD_POLYNOMIAL = 3 };
 enum { BBB_TRANSFORM_IDENTITY = 0, BBB_TRANSFORM_RECIPROCAL = 1 };
 /* data covariance: hierarchical sigma (Target(std_min,...)), fixed scalar / vector inverse covariance
  * (likelihood/_target.py:136-170) */
@@ -102,7 +102,9 @@ typedef struct {
     const double *data;      /* device [nnz] */
     const double *points_x;  /* device [n_points] */
     const double *points_y;  /* device [n_points] */
-    /* lookup1d: data positions */
+    /* lookup1d: data positions; polynomial: abscissae of d_pred[r] = sum_j values[param][j] * x[r]^j over the
+     * k current cells of a (possibly trans-dimensional) plain space: np.vander(x, k, True) @ m
+     * (docs/source/tutorials/03_transd_polyfit.ipynb cell 5) */
     const double *x;         /* device [n_data] */
     /* linear: d_pred = G @ concat(values[p] for p in lin_params), each of length kmax (fixed k) */
     int32_t n_lin_params;

@@ -147,6 +147,9 @@ def forward_target(t, st):
     if fwd["kind"] == "linear":
         m = np.concatenate([sp.values[p] for p in fwd["params"]])
         return K.linear_forward(fwd["G"], m)
+    if fwd["kind"] == "polynomial":  # docs/source/tutorials/03_transd_polyfit.ipynb cell 5
+        m = sp.values[fwd["param"]]
+        return np.vander(fwd["x"], len(m), True) @ m
     raise ValueError(fwd["kind"])
 
 

@@ -47,6 +47,9 @@ def _install_reference_style_forward(spec):
             return jac[i] @ (1.0 / field if f.get("transform", "reciprocal") == "reciprocal" else field)
         if f["kind"] == "lookup1d":
             return OK.lookup1d_forward(f["x"], sp.sites, sp.values[f["param"]])
+        if f["kind"] == "polynomial":
+            m = sp.values[f["param"]]
+            return np.vander(f["x"], len(m), True) @ m
         return OK.linear_forward(f["G"], np.concatenate([sp.values[p] for p in f["params"]]))
 
     OC.forward_target = forward_target

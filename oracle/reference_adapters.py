@@ -40,4 +40,10 @@ def as_reference_forward(op):
             return op.G @ np.concatenate([ps[n] for n in op.param_names])
 
         return forward
+    if kind == "polynomial":
+        def forward(state):  # docs/source/tutorials/03_transd_polyfit.ipynb cell 5
+            m = state[op.param_space_name][op.param_name]
+            return np.vander(op.x, len(m), True) @ m
+
+        return forward
     raise TypeError(f"not a device forward operator: {op!r}")

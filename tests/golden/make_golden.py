@@ -194,6 +194,14 @@ def reference_forward(ing):
             return Voronoi1D.interpolate_tessellation(voro["discretization"], voro["y"], x, "nuclei")
 
         return forward
+    if kind == "transd_polyfit":
+        x = ing["x"]
+
+        def forward(state):  # 03_transd_polyfit.ipynb cell 5
+            m = state["my_param_space"]["coefficients"]
+            return np.vander(x, len(m), True) @ m
+
+        return forward
     if kind == "polyfit":
         G = ing["G"]
 
@@ -228,12 +236,15 @@ class Recorder:
 
 
 def snapshot_corr(state, target_name):
+    if state[target_name] is None:
+        return np.nan
     c = state[target_name].correlation
     return np.nan if c is None else c
 
 
 def snapshot(state, ps_name, param_names, target_name, kmax, ndim):
     ps = state[ps_name]
+    noise = state[target_name]
     k = ps.n_dimensions
     sites = np.full((kmax, max(ndim, 1)), np.nan)
     if ndim > 0:
@@ -241,7 +252,7 @@ def snapshot(state, ps_name, param_names, target_name, kmax, ndim):
     vals = np.full((len(param_names), kmax), np.nan)
     for j, p in enumerate(param_names):
         vals[j, :k] = ps[p]
-    return k, sites, vals, state[target_name].std
+    return k, sites, vals, (np.nan if noise is None else noise.std)
 
 
 def move_id(inner, outer):
@@ -261,8 +272,9 @@ def replay(bb, ing, n_chains, n_steps, seed0, name):
     global TAPE
     from bayesbay_b200 import synthetic
 
-    ps_name = {"tomography_2d": "voronoi", "partition_1d": "voronoi", "polyfit": "my_param_space"}[ing["kind"]]
-    ndim = {"tomography_2d": 2, "partition_1d": 1, "polyfit": 0}[ing["kind"]]
+    ps_name = {"tomography_2d": "voronoi", "partition_1d": "voronoi", "polyfit": "my_param_space",
+               "transd_polyfit": "my_param_space"}[ing["kind"]]
+    ndim = {"tomography_2d": 2, "partition_1d": 1, "polyfit": 0, "transd_polyfit": 0}[ing["kind"]]
     out = None
     names = None
     for c in range(n_chains):
@@ -568,6 +580,8 @@ def main():
            name="partition_1d_corr")
     replay(bb, synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour", position_dependent=True),
            n_chains=6, n_steps=100, seed0=280, name="partition_1d_posdep")
+    replay(bb, synthetic.partition_1d_fixed(), n_chains=4, n_steps=60, seed0=290, name="partition_1d_fixed")
+    replay(bb, synthetic.transd_polyfit(), n_chains=8, n_steps=100, seed0=295, name="transd_polyfit")
     replay(bb, synthetic.polyfit(), n_chains=8, n_steps=60, seed0=300, name="polyfit")
     replay(bb, synthetic.polyfit(all_gaussian=False), n_chains=4, n_steps=60, seed0=350, name="polyfit_nb")
     pt_golden(bb)

@@ -29,9 +29,11 @@ def _prior(p):
 
 def _target(ing, forward):
     t = ing["target"]
-    out = dict(name=t["name"], dobs=np.asarray(ing["d_obs"], dtype=np.float64), hierarchical=True,
-               std_min=float(t["std_min"]), std_max=float(t["std_max"]), std_perturb_std=float(t["std_perturb_std"]),
-               cov_inv=None, correlated=bool(t.get("noise_is_correlated", False)),
+    cov = t.get("covariance_mat_inv")
+    out = dict(name=t["name"], dobs=np.asarray(ing["d_obs"], dtype=np.float64), hierarchical=cov is None,
+               std_min=float(t.get("std_min", 0.01)), std_max=float(t.get("std_max", 1)),
+               std_perturb_std=float(t.get("std_perturb_std", 0.1)),
+               cov_inv=cov, correlated=bool(t.get("noise_is_correlated", False)),
                corr_min=float(t.get("correlation_min", 0.01)), corr_max=float(t.get("correlation_max", 1.0)),
                corr_perturb_std=float(t.get("correlation_perturb_std", 0.1)), forward=forward)
     return out
@@ -42,19 +44,28 @@ def spec_from_ingredients(ing):
     if kind in ("tomography_2d", "partition_1d"):
         v = ing["voronoi"]
         ndim = 2 if kind == "tomography_2d" else 1
-        kmin, kmax = v["n_dimensions_min"], v["n_dimensions_max"]
+        trans_d = v.get("n_dimensions") is None
+        kmin, kmax = (v["n_dimensions_min"], v["n_dimensions_max"]) if trans_d else (v["n_dimensions"],) * 2
         space = dict(
-            name=v["name"], kind="voronoi2d" if ndim == 2 else "voronoi1d", ndim=ndim, trans_d=True,
+            name=v["name"], kind="voronoi2d" if ndim == 2 else "voronoi1d", ndim=ndim, trans_d=trans_d,
             kmin=kmin, kmax=kmax, kinit_max=int((kmax - kmin) * 0.3 + kmin),
             vmin=[float(x) for x in np.atleast_1d(v["vmin"])], vmax=[float(x) for x in np.atleast_1d(v["vmax"])],
-            site_std=[float(v["perturb_std"])] * ndim, birth_from=v["birth_from"],
-            params=[_prior(ing["prior"])], weights=dict(birth=1, death=1, values=3, sites=1),
+            site_std=[float(v["perturb_std"])] * ndim, birth_from=v.get("birth_from", "neighbour"),
+            params=[_prior(ing["prior"])],
+            weights=dict(birth=1 if trans_d else 0, death=1 if trans_d else 0, values=3, sites=1),
         )
         if ndim == 2:
             fwd = dict(kind="ray2d", space=0, param=0, transform="reciprocal", indptr=ing["indptr"],
                        indices=ing["indices"], data=ing["data"], points=ing["points"])
         else:
             fwd = dict(kind="lookup1d", space=0, param=0, x=ing["x"])
+    elif kind == "transd_polyfit":
+        sp = ing["space"]
+        kmin, kmax = sp["n_dimensions_min"], sp["n_dimensions_max"]
+        space = dict(name=sp["name"], kind="plain", ndim=0, trans_d=True, kmin=kmin, kmax=kmax,
+                     kinit_max=int((kmax - kmin) * 0.3 + kmin), vmin=[], vmax=[], site_std=[], birth_from="prior",
+                     params=[_prior(ing["prior"])], weights=dict(birth=1, death=1, values=3, sites=0))
+        fwd = dict(kind="polynomial", space=0, param=0, x=ing["x"])
     elif kind == "polyfit":
         space = dict(name=ing["space"]["name"], kind="plain", ndim=0, trans_d=False, kmin=1, kmax=1, kinit_max=1,
                      vmin=[], vmax=[], site_std=[], birth_from="prior", params=[_prior(p) for p in ing["priors"]],
@@ -80,6 +91,8 @@ REPLAYS = {
     "partition_1d_corr": lambda: synthetic.partition_1d(n_data=30, kmin=2, kmax=12, correlated=True),
     "partition_1d_posdep": lambda: synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour",
                                                           position_dependent=True),
+    "partition_1d_fixed": synthetic.partition_1d_fixed,
+    "transd_polyfit": synthetic.transd_polyfit,
     "polyfit": synthetic.polyfit,
     "polyfit_nb": lambda: synthetic.polyfit(all_gaussian=False),
 }

@@ -15,6 +15,10 @@ from tests import problems
 
 
 def device_forward(ing):
+    if ing["kind"] == "transd_polyfit":
+        from bayesbay_b200.forward import PolynomialForward
+
+        return PolynomialForward(ing["x"], "my_param_space", "coefficients")
     if ing["kind"] == "tomography_2d":
         return RayTomographyForward((ing["indptr"], ing["indices"], ing["data"]), ing["points"], "voronoi", "vel")
     if ing["kind"] == "partition_1d":
@@ -110,7 +114,8 @@ def test_compiler_emits_the_spec_the_oracle_runs(name):
     spec = _compile.compile_problem(par, ll)
     _same(spec, problems.spec_from_ingredients(ing))
     names = _compile.perturbation_names(spec)
-    assert len(names) == 5 and names[4][0].startswith("NoisePerturbation(")
+    assert len(names) == 5
+    assert (names[4] is None) if not spec["targets"][0]["hierarchical"] else names[4][0].startswith("NoisePerturbation(")
 
 
 def test_compiler_accepts_objects_of_the_unmodified_reference():
@@ -122,7 +127,8 @@ def test_compiler_accepts_objects_of_the_unmodified_reference():
     import make_golden
 
     ref = make_golden.import_reference()
-    for name in ("tomo_small", "partition_1d", "polyfit_nb", "partition_1d_corr", "partition_1d_posdep"):
+    for name in ("tomo_small", "partition_1d", "polyfit_nb", "partition_1d_corr", "partition_1d_posdep",
+                 "partition_1d_fixed", "transd_polyfit"):
         ing = problems.REPLAYS[name]()
         par, ll = synthetic.build_problem(ing, ref, lambda i: (lambda state: None))
         # the reference wraps forwards; swap in the device operator description for compilation

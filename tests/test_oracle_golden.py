@@ -109,7 +109,8 @@ def _state_from_fixture(spec, g, c, t):
         sites = g["sites"][c, t, :k, 0].copy()
     vals = [g["values"][c, t, j, :k].copy() for j in range(len(sp["params"]))]
     corr = float(g["corr"][c, t]) if "corr" in g.files else float("nan")
-    st = OC.ChainState([OC.SpaceState(k, sites, vals)], [float(g["sigma"][c, t])], 1.0, [None],
+    sig = float(g["sigma"][c, t])
+    st = OC.ChainState([OC.SpaceState(k, sites, vals)], [None if math.isnan(sig) else sig], 1.0, [None],
                        [None if math.isnan(corr) else corr])
     OC.evaluate(spec, st)
     return st
@@ -151,7 +152,9 @@ def _assert_state_close(a, b):
         np.testing.assert_allclose(sa.sites, sb.sites, rtol=RTOL, atol=1e-15)
     for va, vb in zip(sa.values, sb.values):
         np.testing.assert_allclose(va, vb, rtol=RTOL, atol=1e-15)
-    np.testing.assert_allclose(a.sigma[0], b.sigma[0], rtol=RTOL)
+    assert (a.sigma[0] is None) == (b.sigma[0] is None)
+    if a.sigma[0] is not None:
+        np.testing.assert_allclose(a.sigma[0], b.sigma[0], rtol=RTOL)
     assert (a.corr[0] is None) == (b.corr[0] is None)
     if a.corr[0] is not None:
         np.testing.assert_allclose(a.corr[0], b.corr[0], rtol=RTOL)
