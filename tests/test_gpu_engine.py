@@ -264,3 +264,56 @@ def test_multi_space_multi_target_against_oracle(name, n_chains, n_steps):
         m, l_ = OC.misfit_and_logdet(spec, states[c])
         np.testing.assert_allclose(mis[c].item(), m, rtol=1e-10)
         np.testing.assert_allclose(ld[c].item(), l_, rtol=1e-12, atol=1e-12)
+
+
+def test_full_size_config3_properties():
+    """BASELINE configs[2] at full size (100x100 grid, 10 000 rays, K = 200, 1024 chains): after a few hundred
+    iterations the resident nearest-site index equals a from-scratch rasterisation, the cached misfit equals a fresh
+    forward evaluation, d_pred of sampled chains equals the oracle (KD-tree + CSR mat-vec restatement), every chain
+    respects its bounds, and the move counters add up."""
+    import ctypes as C
+
+    import scipy.sparse
+    import scipy.spatial
+
+    from bayesbay_b200 import _lib as L
+    from bayesbay_b200 import synthetic
+
+    ing = synthetic.tomography_2d()
+    spec = problems.spec_from_ingredients(ing)
+    n = 1024
+    eng = _engine(spec, n, seed=2025)
+    eng.init_states()
+    eng.step(300)
+    k, sites, vals = eng.gather_space(0)
+    G = ing["points"].shape[0]
+    ref = torch.zeros((G, n), dtype=torch.uint8, device="cuda")
+    px = torch.as_tensor(ing["points"][:, 0].copy()).cuda()
+    py = torch.as_tensor(ing["points"][:, 1].copy()).cuda()
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    L.check(L.load().bbb_raster2d(p(sites), p(k), 200, n, p(px), p(py), G, p(ref), None))
+    assert torch.equal(eng.current_cell_idx(0), ref)
+    dp = eng.dpred(0)
+    m0, ld0 = eng.misfit_logdet()
+    eng.refresh()
+    m1, ld1 = eng.misfit_logdet()
+    np.testing.assert_allclose(m0.cpu().numpy(), m1.cpu().numpy(), rtol=1e-12)
+    assert torch.equal(ld0, ld1)
+    jac = scipy.sparse.csr_matrix((ing["data"], ing["indices"], ing["indptr"]), shape=(10000, G))
+    kk, ss, vv = k.cpu().numpy(), sites.cpu().numpy(), vals.cpu().numpy()
+    sig = eng.sigma[0][0].cpu().numpy()
+    for c in (0, 17, 511, 1023):
+        s_c, v_c = ss[:, : kk[c], c].T, vv[0, : kk[c], c]
+        nearest = scipy.spatial.KDTree(s_c).query(ing["points"])[1]
+        assert np.array_equal(nearest, ref[:, c].cpu().numpy())
+        want = jac @ (1.0 / v_c[nearest])
+        np.testing.assert_allclose(dp[:, c].cpu().numpy(), want, rtol=1e-12)
+        res = want - ing["d_obs"]
+        np.testing.assert_allclose(m1[c].item(), float(res @ res) / sig[c] ** 2, rtol=1e-10)
+    assert kk.min() >= 10 and kk.max() <= 200
+    assert (vv[0][np.arange(200)[:, None] < kk[None, :]] >= 2).all() and (vv[0][np.arange(200)[:, None] < kk[None, :]] <= 4).all()
+    assert (sig >= 0).all() and (sig <= 0.01).all()
+    prop = eng.n_proposed.cpu().numpy()
+    assert (prop.sum(0) == 300).all() and (eng.iteration.cpu().numpy() == 300).all()
+    share = prop.sum(1) / prop.sum()
+    np.testing.assert_allclose(share, [1 / 7, 1 / 7, 3 / 7, 1 / 7, 1 / 7], atol=0.005)
