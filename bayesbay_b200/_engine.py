@@ -27,6 +27,31 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def ray_matrix_csc_tiles(indptr, indices, data, n_points: int, tile_rays: int):
+    """Ray-tile-blocked CSC copy of a CSR ray matrix (``bbb_target_spec.csc_*``): entries sorted by
+    (ray tile, column, ray); returns ``(colptr [n_tiles][G+1] int32, rows [nnz] uint16 -- ray index inside its
+    tile --, data [nnz] float64, bound = max|data| * longest row)``."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    data = np.asarray(data, dtype=np.float64)
+    n_rays = indptr.size - 1
+    n_tiles = max(1, -(-n_rays // tile_rays))
+    lens = np.diff(indptr)
+    rows = np.repeat(np.arange(n_rays, dtype=np.int64), lens)
+    tile = rows // tile_rays
+    order = np.lexsort((rows, indices, tile))
+    counts = np.bincount(tile * n_points + indices, minlength=n_tiles * n_points)
+    cum = np.concatenate(([0], np.cumsum(counts)))
+    colptr = np.empty((n_tiles, n_points + 1), dtype=np.int64)
+    for q in range(n_tiles):
+        colptr[q] = cum[q * n_points: (q + 1) * n_points + 1]
+    if cum[-1] >= 2 ** 31:
+        raise ValueError("ray matrix too large for 32-bit CSC offsets")
+    bound = float(np.abs(data).max(initial=0.0)) * float(lens.max(initial=0))
+    return (colptr.astype(np.int32), (rows[order] - tile[order] * tile_rays).astype(np.uint16),
+            np.ascontiguousarray(data[order]), bound)
+
+
 class Engine:
     """One engine per (process, device).  ``spec`` is the plain-data problem description emitted by
     :func:`bayesbay_b200._compile.compile_problem`."""
@@ -50,6 +75,7 @@ class Engine:
         L.check(self.lib.bbb_engine_bind_buffers(self._handle, C.byref(self._cbuf)))
         self._steps_since_sync = 0
         self._has_ray = any(t["forward"]["kind"] == "ray2d" for t in spec["targets"])
+        self.chain_local = bool(self.lib.bbb_engine_chain_local(self._handle))
 
     # ------------------------------------------------------------------ spec / buffers
     def _const(self, arr, dtype):
@@ -130,6 +156,16 @@ class Engine:
                 t.data = self._const(f["data"], np.float64).data_ptr()
                 t.points_x = self._const(pts[:, 0], np.float64).data_ptr()
                 t.points_y = self._const(pts[:, 1], np.float64).data_ptr()
+                # CSC copy for the chain-local step (0 = this shape cannot run it: the engine then does full SpMMs)
+                K = spec["spaces"][f["space"]]["kmax"]
+                tile = int(self.lib.bbb_chain_local_tile_rays(t.n_data, K, t.n_points))
+                if tile > 0 and not tg.get("correlated"):
+                    colptr, rows, cdat, bound = ray_matrix_csc_tiles(f["indptr"], f["indices"], f["data"], t.n_points, tile)
+                    t.csc_tile_rays, t.csc_n_tiles = tile, colptr.shape[0]
+                    t.csc_colptr = self._const(colptr, np.int32).data_ptr()
+                    t.csc_rows = self._const(rows.view(np.int16), np.int16).data_ptr()
+                    t.csc_data = self._const(cdat, np.float64).data_ptr()
+                    t.csc_bound = bound
             elif f["kind"] in ("lookup1d", "polynomial"):
                 t.param = f["param"]
                 x = np.asarray(f["x"], dtype=np.float64)
@@ -164,15 +200,30 @@ class Engine:
             b.k[i], b.sel[i] = _ptr(self.k[i]), _ptr(self.sel[i])
         self.sigma, self.phi, self.cell_idx, self.idx_sel, self.partial = [], [], [], [], []
         self.rescan_list, self.rescan_count = [], []
+        self.idx_cm, self.res, self.change_list = [], [], []
         self.corr, self.dpred_scratch = [], []
+        n_ray = sum(tg["forward"]["kind"] == "ray2d" for tg in self.spec["targets"])
         for i, tg in enumerate(self.spec["targets"]):
             self.sigma.append(torch.ones((2, Cn), dtype=f64, device=dev) if tg["hierarchical"] else None)
             self.phi.append(z((2, 3, Cn), f64))
             corr_t = bool(tg.get("correlated"))
             self.corr.append(z((2, Cn), f64) if corr_t else None)
+            # chain-local step: one ray target whose CSC copy was built (see _build_spec)
+            local_t = tg["forward"]["kind"] == "ray2d" and n_ray == 1 and self._cspec.targets[i].csc_tile_rays > 0
             self.dpred_scratch.append(z((int(np.asarray(tg["dobs"]).size), Cn), f64)
-                                      if corr_t and tg["forward"]["kind"] == "ray2d" else None)
+                                      if (corr_t or local_t) and tg["forward"]["kind"] == "ray2d" else None)
             b.corr[i], b.dpred_scratch[i] = _ptr(self.corr[i]), _ptr(self.dpred_scratch[i])
+            if local_t:
+                G = int(np.asarray(tg["forward"]["points"]).shape[0])
+                K = self.spec["spaces"][tg["forward"]["space"]]["kmax"]
+                self.idx_cm.append(z((Cn, int(self.lib.bbb_idx_row_stride(G))), u8 if K <= 256 else torch.int16))
+                self.res.append(z((Cn, int(np.asarray(tg["dobs"]).size)), f64))
+                self.change_list.append(torch.empty((Cn, G), dtype=i32, device=dev))
+            else:
+                self.idx_cm.append(None)
+                self.res.append(None)
+                self.change_list.append(None)
+            b.idx_cm[i], b.res[i], b.change_list[i] = _ptr(self.idx_cm[i]), _ptr(self.res[i]), _ptr(self.change_list[i])
             if tg["forward"]["kind"] == "ray2d":
                 K = self.spec["spaces"][tg["forward"]["space"]]["kmax"]
                 G = int(np.asarray(tg["forward"]["points"]).shape[0])
@@ -231,6 +282,7 @@ class Engine:
         L.check(self.lib.bbb_engine_refresh(self._handle, self._stream))
         self._steps_since_sync = self.K_BOUND_RESYNC  # the engine forgot its bound: tighten before the next step
 
+    RESYNC_EVERY = 256   # chain-local engines: steps between two from-scratch evaluations of residuals and misfit
     K_BOUND_RESYNC = 64  # steps between two tightenings of the engine's bound on max k (one tiny D2H sync each)
 
     def step(self, n_steps: int = 1):
@@ -289,8 +341,16 @@ class Engine:
         L.check(self.lib.bbb_engine_misfit_logdet(self._handle, _ptr(m), _ptr(ld), self._stream))
         return m, ld
 
+    def resync(self):
+        """Chain-local engines: re-evaluate forward and misfit of the current states from scratch (the engine also
+        does this on its own every ``bbb_engine_set_resync`` steps)."""
+        L.check(self.lib.bbb_engine_resync(self._handle, self._stream))
+
     def current_cell_idx(self, t: int) -> torch.Tensor:
         """[G][C] nearest-site index of the current states of ray target ``t``."""
+        if self.chain_local:
+            G = self.cell_idx[t].shape[1]
+            return self.idx_cm[t][:, :G].t().contiguous()
         sel = self.idx_sel[t].long()
         idx = self.cell_idx[t]
         return torch.where(sel[None, :] == 0, idx[0], idx[1])
@@ -368,7 +428,8 @@ class Engine:
             named.update({f"sites{i}": self.sites[i], f"values{i}": self.values[i], f"k{i}": self.k[i], f"sel{i}": self.sel[i]})
         for i in range(len(self.spec["targets"])):
             named.update({f"sigma{i}": self.sigma[i], f"corr{i}": self.corr[i], f"phi{i}": self.phi[i],
-                          f"cell_idx{i}": self.cell_idx[i], f"idx_sel{i}": self.idx_sel[i]})
+                          f"cell_idx{i}": self.cell_idx[i], f"idx_sel{i}": self.idx_sel[i],
+                          f"idx_cm{i}": self.idx_cm[i], f"res{i}": self.res[i]})
         return {k: v for k, v in named.items() if v is not None}
 
     def state_dict(self) -> dict:
@@ -376,7 +437,8 @@ class Engine:
         iteration numbers, so no generator state has to be saved)."""
         torch.cuda.synchronize(self.device)
         out = {k: v.cpu() for k, v in self._mutable().items()}
-        out["_meta"] = dict(n_chains=self.C, seed=self.seed, chain_id0=self.chain_id0)
+        out["_meta"] = dict(n_chains=self.C, seed=self.seed, chain_id0=self.chain_id0,
+                            steps_since_resync=int(self.lib.bbb_engine_steps_since_resync(self._handle)))
         return out
 
     def load_state_dict(self, state: dict):
@@ -391,6 +453,7 @@ class Engine:
             v.copy_(state[k])
         for s, sp in enumerate(self.spec["spaces"]):
             L.check(self.lib.bbb_engine_set_k_bound(self._handle, s, sp["kmax"]))
+        L.check(self.lib.bbb_engine_set_resync(self._handle, self.RESYNC_EVERY, int(meta.get("steps_since_resync", 0))))
         self._steps_since_sync = self.K_BOUND_RESYNC
         torch.cuda.synchronize(self.device)
 

@@ -13,7 +13,7 @@ MAX_SPACES = 4
 MAX_PARAMS = 8
 MAX_TARGETS = 4
 MAX_LINEAR_PARAMS = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SPACE_PLAIN, SPACE_VORONOI1D, SPACE_VORONOI2D = 0, 1, 2
 PRIOR_UNIFORM, PRIOR_GAUSSIAN, PRIOR_LAPLACE = 0, 1, 2
@@ -54,6 +54,8 @@ class TargetSpec(C.Structure):
         ("x", _vp),
         ("n_lin_params", C.c_int32), ("lin_params", C.c_int32 * MAX_LINEAR_PARAMS),
         ("G", _vp),
+        ("csc_tile_rays", C.c_int32), ("csc_n_tiles", C.c_int32),
+        ("csc_colptr", _vp), ("csc_rows", _vp), ("csc_data", _vp), ("csc_bound", C.c_double),
     ]
 
 
@@ -73,6 +75,7 @@ class Buffers(C.Structure):
         ("dpred_scratch", _vp * MAX_TARGETS), ("cell_idx", _vp * MAX_TARGETS),
         ("idx_sel", _vp * MAX_TARGETS), ("partial", _vp * MAX_TARGETS),
         ("rescan_list", _vp * MAX_TARGETS), ("rescan_count", _vp * MAX_TARGETS),
+        ("idx_cm", _vp * MAX_TARGETS), ("res", _vp * MAX_TARGETS), ("change_list", _vp * MAX_TARGETS),
         ("temperature", _vp), ("iteration", _vp),
         ("move", _vp), ("edit", _vp), ("edit_site", _vp), ("edit_vals", _vp), ("log_prob_ratio", _vp), ("log_like_ratio", _vp), ("accepted", _vp),
         ("n_proposed", _vp), ("n_accepted", _vp),
@@ -86,6 +89,12 @@ SYMBOLS = {
     "bbb_abi_version": (C.c_int, []),
     "bbb_last_error": (C.c_char_p, []),
     "bbb_ray_tiles": (_i64, [_i64]),
+    "bbb_idx_row_stride": (_i64, [_i64]),
+    "bbb_chain_local_tile_rays": (_i64, [_i64, _i32, _i64]),
+    "bbb_engine_chain_local": (C.c_int, [_vp]),
+    "bbb_engine_set_resync": (C.c_int, [_vp, _i64, _i64]),
+    "bbb_engine_steps_since_resync": (_i64, [_vp]),
+    "bbb_engine_resync": (C.c_int, [_vp, _vp]),
     "bbb_engine_create": (C.c_int, [C.POINTER(ProblemSpec), C.c_int, C.POINTER(_vp)]),
     "bbb_engine_bind_buffers": (C.c_int, [_vp, C.POINTER(Buffers)]),
     "bbb_engine_destroy": (None, [_vp]),

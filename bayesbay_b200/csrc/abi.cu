@@ -37,6 +37,9 @@ struct bbb_engine {
     int n_sm;
     int k_bound[BBB_MAX_SPACES];  // host-side upper bound of max_c k[s][c] (grows by one per step, tightened by the caller)
     bool brute_force;  // BBB_BRUTE_FORCE_RASTER=1: re-rasterise every proposal from scratch (reference behaviour)
+    bool full_forward; // BBB_FULL_FORWARD=1: never use the chain-local step (full SpMM every proposal, reference behaviour)
+    int ray_t;         // chain-local engines: the one ray target
+    long long resync_every, steps_since_resync;
 };
 
 extern "C" {
@@ -44,6 +47,10 @@ extern "C" {
 int bbb_abi_version(void) { return BBB_ABI_VERSION; }
 const char *bbb_last_error(void) { return g_err; }
 int64_t bbb_ray_tiles(int64_t n_data) { return (n_data + RAY_TILE - 1) / RAY_TILE; }
+int64_t bbb_idx_row_stride(int64_t n_points) { return (n_points + 15) & ~(int64_t)15; }
+int64_t bbb_chain_local_tile_rays(int64_t n_data, int32_t kmax, int64_t n_points) {
+    return chain_local_tile_rays(n_data, kmax, n_points);
+}
 
 static int validate_spec(const bbb_problem_spec *P) {
     if (P->n_spaces < 1 || P->n_spaces > BBB_MAX_SPACES) return fail(BBB_ERR_INVALID, "n_spaces out of range");
@@ -104,6 +111,13 @@ static int validate_spec(const bbb_problem_spec *P) {
             if (T.param < 0 || T.param >= S.n_params) return fail(BBB_ERR_INVALID, "target %d: param index", t);
             if (T.n_points < 1 || !T.indptr || !T.indices || !T.data || !T.points_x || !T.points_y)
                 return fail(BBB_ERR_INVALID, "target %d: ray2d arrays", t);
+            if (T.csc_tile_rays != 0) {
+                if (T.csc_tile_rays != chain_local_tile_rays(T.n_data, S.kmax, T.n_points))
+                    return fail(BBB_ERR_INVALID, "target %d: csc_tile_rays must be bbb_chain_local_tile_rays()", t);
+                if (T.csc_n_tiles != (T.n_data + T.csc_tile_rays - 1) / T.csc_tile_rays || !T.csc_colptr || !T.csc_rows ||
+                    !T.csc_data || !(T.csc_bound >= 0))
+                    return fail(BBB_ERR_INVALID, "target %d: CSC arrays", t);
+            }
         } else if (T.fwd_kind == BBB_FWD_LOOKUP1D) {
             if (S.kind != BBB_SPACE_VORONOI1D) return fail(BBB_ERR_INVALID, "target %d: lookup1d forward needs a Voronoi1D space", t);
             if (T.param < 0 || T.param >= S.n_params || !T.x) return fail(BBB_ERR_INVALID, "target %d: lookup1d arrays", t);
@@ -138,7 +152,12 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
     {
         const char *bf = getenv("BBB_BRUTE_FORCE_RASTER");
         e->brute_force = bf != nullptr && bf[0] == '1';
+        const char *ff = getenv("BBB_FULL_FORWARD");
+        e->full_forward = ff != nullptr && ff[0] == '1';
     }
+    e->ray_t = -1;
+    e->resync_every = 256;
+    e->steps_since_resync = 0;
     for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
     for (int s = 0; s < BBB_MAX_SPACES; ++s) e->k_bound[s] = s < spec->n_spaces ? spec->spaces[s].kmax : 0;
     e->n_sm = 148;
@@ -183,6 +202,23 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
         e->host.n_partial[t] = spmm_ray_groups(P.targets[t].n_data, b->n_chains, K, K <= 256 ? 1 : 2, e->n_sm);
         if (e->host.n_partial[t] == 0)
             return fail(BBB_ERR_UNSUPPORTED, "target %d: n_dimensions_max %d is too large for the ray kernel's shared-memory value table", t, K);
+    }
+    // chain-local step: exactly one ray target, CSC copy of its matrix and the chain-major caches provided
+    e->host.chain_local = 0;
+    e->ray_t = -1;
+    {
+        int n_ray = 0, rt = -1;
+        for (int t = 0; t < P.n_targets; ++t)
+            if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) { ++n_ray; rt = t; }
+        if (n_ray == 1 && !e->full_forward && !e->brute_force && P.targets[rt].csc_tile_rays > 0 && !P.targets[rt].correlated) {
+            const bool have = b->idx_cm[rt] && b->res[rt] && b->change_list[rt] && b->dpred_scratch[rt];
+            if (!have && (b->idx_cm[rt] || b->res[rt] || b->change_list[rt]))
+                return fail(BBB_ERR_SHAPE, "target %d: the chain-local step needs idx_cm, res, change_list and dpred_scratch", rt);
+            if (have) {
+                e->host.chain_local = 1;
+                e->ray_t = rt;
+            }
+        }
     }
     CU(cudaSetDevice(e->device));
     CU(cudaMemcpy(e->dev, &e->host, sizeof(EngineParams), cudaMemcpyHostToDevice));
@@ -302,11 +338,43 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
         CU(cudaSetDevice((e)->device));                                                \
     } while (0)
 
+// Chain-local engines: bring the [G][C] index slot 0 in line with the chain-major index (the SpMM and the
+// result kernels read the former).
+static int sync_index_slot0(bbb_engine *e, cudaStream_t st) {
+    const int t = e->ray_t;
+    const bbb_buffers &B = e->host.buf;
+    const long long G = e->host.spec.targets[t].n_points;
+    int rc = launch_transpose_idx(B.idx_cm[t], B.cell_idx[t], idx_bytes_of(e->host.spec, t), B.n_chains, G,
+                                  bbb_idx_row_stride(G), B.n_chains, st);
+    return rc != 0 ? rc : (int)cudaMemsetAsync(B.idx_sel[t], 0, (size_t)B.n_chains, st);
+}
+
+// Chain-local engines: forward and misfit of the CURRENT states from scratch (full SpMM) into res / phi;
+// `reraster` also re-derives the nearest-site index from the sites.
+static int chain_local_from_scratch(bbb_engine *e, bool reraster, cudaStream_t st) {
+    const int t = e->ray_t;
+    const bbb_buffers &B = e->host.buf;
+    const bbb_target_spec &T = e->host.spec.targets[t];
+    const long long G = T.n_points, C = B.n_chains;
+    int rc = reraster ? run_raster(e, t, false, st) : sync_index_slot0(e, st);
+    if (rc == 0) rc = run_spmm(e, t, false, B.dpred_scratch[t], true, st);
+    if (rc == 0) rc = launch_refresh_finish(e->dev, C, st);
+    if (rc == 0 && reraster)
+        rc = launch_transpose_idx(B.cell_idx[t], B.idx_cm[t], idx_bytes_of(e->host.spec, t), G, C, C, bbb_idx_row_stride(G), st);
+    if (rc == 0) rc = launch_residual_transpose(B.dpred_scratch[t], B.res[t], T.n_data, C, T.dobs, st);
+    e->steps_since_resync = 0;
+    return rc;
+}
+
 int bbb_engine_refresh(bbb_engine *e, void *stream) {
     NEED_BOUND(e);
     cudaStream_t st = (cudaStream_t)stream;
     const bbb_problem_spec &P = e->host.spec;
     for (int s = 0; s < P.n_spaces; ++s) e->k_bound[s] = P.spaces[s].kmax;  // caller-written states: no knowledge
+    if (e->host.chain_local) {
+        CU(chain_local_from_scratch(e, true, st));
+        return BBB_OK;
+    }
     for (int t = 0; t < P.n_targets; ++t) {
         if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
         CU(run_raster(e, t, false, st));
@@ -314,6 +382,34 @@ int bbb_engine_refresh(bbb_engine *e, void *stream) {
     }
     CU(launch_refresh_finish(e->dev, e->host.buf.n_chains, st));
     return BBB_OK;
+}
+
+int bbb_engine_chain_local(bbb_engine *e) { return (e && e->bound && e->host.chain_local) ? 1 : 0; }
+
+int bbb_engine_set_resync(bbb_engine *e, int64_t every, int64_t steps_since) {
+    if (!e) return fail(BBB_ERR_INVALID, "NULL engine");
+    if (every < 0 || steps_since < 0) return fail(BBB_ERR_INVALID, "negative resync schedule");
+    e->resync_every = every;
+    e->steps_since_resync = steps_since;
+    return BBB_OK;
+}
+int64_t bbb_engine_steps_since_resync(bbb_engine *e) { return e ? e->steps_since_resync : 0; }
+
+int bbb_engine_resync(bbb_engine *e, void *stream) {
+    NEED_BOUND(e);
+    if (e->host.chain_local) CU(chain_local_from_scratch(e, false, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+static int run_chain_step(bbb_engine *e, cudaStream_t st) {
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_target_spec &T = P.targets[e->ray_t];
+    int rc = launch_chain_step(e->dev, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
+                               idx_bytes_of(P, e->ray_t), st);
+    if (rc != 0) return rc;
+    ++e->steps_since_resync;
+    if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) rc = chain_local_from_scratch(e, false, st);
+    return rc;
 }
 
 int bbb_engine_init_states(bbb_engine *e, void *stream) {
@@ -348,12 +444,16 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
     }
     for (int64_t it = 0; it < n_steps; ++it) {
         CU(run_propose(e, st));
-        for (int t = 0; t < P.n_targets; ++t) {
-            if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
-            CU(run_raster(e, t, true, st));
-            CU(run_spmm(e, t, true, nullptr, true, st));
+        if (e->host.chain_local) {
+            CU(run_chain_step(e, st));
+        } else {
+            for (int t = 0; t < P.n_targets; ++t) {
+                if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
+                CU(run_raster(e, t, true, st));
+                CU(run_spmm(e, t, true, nullptr, true, st));
+            }
+            CU(launch_finish(e->dev, C, st));
         }
-        CU(launch_finish(e->dev, C, st));
         for (int s = 0; s < P.n_spaces; ++s)
             if (e->k_bound[s] < P.spaces[s].kmax) ++e->k_bound[s];  // a step adds at most one cell
     }
@@ -369,15 +469,20 @@ int bbb_engine_stage(bbb_engine *e, int stage, void *stream) {
     switch (stage) {
         case 0: CU(run_propose(e, st)); break;
         case 1:
+            if (e->host.chain_local) break;
             for (int t = 0; t < P.n_targets; ++t)
                 if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) CU(run_raster(e, t, true, st));
             break;
         case 2:
+            if (e->host.chain_local) {
+                CU(run_chain_step(e, st));
+                break;
+            }
             for (int t = 0; t < P.n_targets; ++t)
                 if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) CU(run_spmm(e, t, true, nullptr, true, st));
             break;
         case 3:
-            CU(launch_finish(e->dev, C, st));
+            if (!e->host.chain_local) CU(launch_finish(e->dev, C, st));
             for (int s = 0; s < P.n_spaces; ++s)
                 if (e->k_bound[s] < P.spaces[s].kmax) ++e->k_bound[s];
             break;
@@ -413,8 +518,10 @@ int bbb_engine_gather_space(bbb_engine *e, int space, int32_t *k_out, double *si
 int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream) {
     NEED_BOUND(e);
     if (target < 0 || target >= e->host.spec.n_targets || !dpred_out) return fail(BBB_ERR_INVALID, "target index / NULL output");
-    if (e->host.spec.targets[target].fwd_kind == BBB_FWD_RAY2D)
+    if (e->host.spec.targets[target].fwd_kind == BBB_FWD_RAY2D) {
+        if (e->host.chain_local) CU(sync_index_slot0(e, (cudaStream_t)stream));
         CU(run_spmm(e, target, false, dpred_out, false, (cudaStream_t)stream));
+    }
     else
         CU(launch_small_dpred(e->dev, e->host.buf.n_chains, target, dpred_out, (cudaStream_t)stream));
     return BBB_OK;

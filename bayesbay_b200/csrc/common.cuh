@@ -26,6 +26,7 @@ struct EngineParams {
     bbb_buffers buf;
     Annealing anneal;
     int n_partial[BBB_MAX_TARGETS];  // rows of partial[t] the ray kernel writes (its ray groups)
+    int chain_local;                 // 1: the chain-local kernel (chain_kernels.cu) evaluates the ray target
 };
 
 __device__ __forceinline__ double annealing_temperature(const Annealing &a, long long it) {

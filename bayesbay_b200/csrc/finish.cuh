@@ -146,8 +146,26 @@ __device__ __forceinline__ bool move_is_geometry(int move) {
     return inner != BBB_MOVE_VALUES;
 }
 
-// Likelihood ratio, MH decision, commit, statistics: _next_iteration (_markov_chain.py:222-243)
-__device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rng) {
+// Generator of chain c for the current iteration (Philox counters or the recorded tape); `continue_step`
+// resumes after the draws the proposal kernel consumed.
+__device__ __forceinline__ void rng_begin(Rng &rng, const EngineParams &ep, long long c, uint32_t tag,
+                                          bool continue_step) {
+    const bbb_buffers &B = ep.buf;
+    if (B.tape != nullptr) {
+        rng.init_tape(B.tape + c * B.tape_stride, B.tape_cursor[c]);
+    } else {
+        rng.init_philox(ep.spec.seed, (uint64_t)(B.chain_id0 + c), (uint64_t)B.iteration[c], tag);
+        if (continue_step) rng.n = (uint32_t)B.tape_cursor[c];
+    }
+}
+__device__ __forceinline__ void rng_end(const Rng &rng, const EngineParams &ep, long long c) {
+    const bbb_buffers &B = ep.buf;
+    B.tape_cursor[c] = (B.tape != nullptr) ? rng.cursor : (long long)rng.n;
+}
+
+// Likelihood ratio, MH decision, commit, statistics: _next_iteration (_markov_chain.py:222-243).
+// Returns the accept bit.
+__device__ inline bool finish_chain(const EngineParams &ep, long long c, Rng &rng) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
@@ -166,7 +184,7 @@ __device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rn
             Phi3 phi_new = phi_old;
             if (!noise && T.space == s) {
                 if (T.fwd_kind != BBB_FWD_RAY2D) phi_new = small_target_phi(P, B, t, B.sel[s][c] ^ 1, c, nullptr, nullptr);
-                else if (T.correlated) phi_new = load_phi(B, t, 1, c);  // written by k_corr_sums from d_pred
+                else if (T.correlated || ep.chain_local) phi_new = load_phi(B, t, 1, c);  // k_corr_sums / k_chain_step
                 else phi_new = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
                 store_phi(B, t, 1, c, phi_new);
             }
@@ -204,7 +222,7 @@ __device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rn
     // rasteriser commits it to slot 0 at the start of the next step (tomo_kernels.cu)
     for (int t = 0; t < P.n_targets; ++t) {
         const bbb_target_spec &T = P.targets[t];
-        if (T.fwd_kind != BBB_FWD_RAY2D) continue;
+        if (T.fwd_kind != BBB_FWD_RAY2D || ep.chain_local) continue;
         const bool geom_accepted = accepted && !noise && T.space == s && move_is_geometry(move) && !isinf(lpr);
         B.idx_sel[t][c] = geom_accepted ? 1 : 0;  // any older pending commit was done by this step's rasteriser
     }
@@ -213,6 +231,7 @@ __device__ inline void finish_chain(const EngineParams &ep, long long c, Rng &rn
     B.n_proposed[(long long)move * C + c] += 1;
     B.n_accepted[(long long)move * C + c] += accepted ? 1 : 0;
     B.iteration[c] += 1;
+    return accepted;
 }
 
 }  // namespace bbb

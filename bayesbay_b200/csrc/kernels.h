@@ -63,6 +63,15 @@ int launch_apply_edit(const EngineParams *dev_params, long long C, int space, in
 int launch_ray_spmm(const SpmmArgs &a, cudaStream_t stream);
 int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);
 
+// chain_kernels.cu
+long long chain_local_tile_rays(long long n_data, int kmax, long long n_points);
+int launch_chain_step(const EngineParams *dev_params, long long C, int target, int tile_rays, int K, int idx_bytes,
+                      cudaStream_t stream);
+int launch_transpose_idx(const void *in, void *out, int idx_bytes, long long rows, long long cols, long long in_stride,
+                         long long out_stride, cudaStream_t stream);
+int launch_residual_transpose(const double *dpred, double *res, long long R, long long C, const double *dobs,
+                              cudaStream_t stream);
+
 // step_kernels.cu
 int launch_propose(const EngineParams *dev_params, long long C, cudaStream_t stream);
 int launch_finish(const EngineParams *dev_params, long long C, cudaStream_t stream);

@@ -9,21 +9,6 @@ namespace bbb {
 
 constexpr int STEP_THREADS = 64;  // 2 warps per block: spreads C = 1024 chains over 16 SMs' worth of blocks
 
-__device__ __forceinline__ void rng_begin(Rng &rng, const EngineParams &ep, long long c, uint32_t tag,
-                                          bool continue_step) {
-    const bbb_buffers &B = ep.buf;
-    if (B.tape != nullptr) {
-        rng.init_tape(B.tape + c * B.tape_stride, B.tape_cursor[c]);
-    } else {
-        rng.init_philox(ep.spec.seed, (uint64_t)(B.chain_id0 + c), (uint64_t)B.iteration[c], tag);
-        if (continue_step) rng.n = (uint32_t)B.tape_cursor[c];
-    }
-}
-__device__ __forceinline__ void rng_end(const Rng &rng, const EngineParams &ep, long long c) {
-    const bbb_buffers &B = ep.buf;
-    B.tape_cursor[c] = (B.tape != nullptr) ? rng.cursor : (long long)rng.n;
-}
-
 // One WARP per chain: lane 0 owns the generator (every draw is broadcast), the O(k) nearest-site searches of
 // birth/death-from-neighbour run with lanes = sites, and the proposed slot is written by k_apply_edit.
 constexpr int PROPOSE_WARPS = 4;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BBB_ABI_VERSION 1
+#define BBB_ABI_VERSION 2
 
 #define BBB_MAX_SPACES 4
 #define BBB_MAX_PARAMS 8
@@ -110,6 +110,19 @@ typedef struct {
     int32_t n_lin_params;
     int32_t lin_params[BBB_MAX_LINEAR_PARAMS];
     const double *G;         /* device [n_data][n_lin_params * kmax] row-major */
+    /* ray2d, optional (csc_tile_rays > 0): the SAME ray matrix in ray-tile-blocked CSC form, which enables the
+     * chain-local step (one thread block per chain; a proposal edits one cell, so only the columns of the grid
+     * points whose nearest site changed are visited: d_pred' = d_pred + sum_g G[:, g] * (f(v'(g)) - f(v(g))),
+     * the change-local form of `jacobian @ (1 / vel[nearest])`, 31_sw_tomography.ipynb cell 12).
+     * Rays are split into csc_n_tiles tiles of csc_tile_rays rays (bbb_chain_local_tile_rays(); the last tile may
+     * be shorter); the entries are sorted by (tile, column, row): entries of column g inside tile q are
+     * [csc_colptr[q * (n_points + 1) + g], csc_colptr[q * (n_points + 1) + g + 1]). */
+    int32_t csc_tile_rays, csc_n_tiles;
+    const int32_t *csc_colptr; /* device [csc_n_tiles][n_points + 1] */
+    const uint16_t *csc_rows;  /* device [nnz] ray index inside its tile */
+    const double *csc_data;    /* device [nnz] */
+    double csc_bound;          /* max|data| * (largest number of entries in a row): bounds any change of d_pred per
+                                * unit change of the cell function; scales the fixed-point ray accumulators */
 } bbb_target_spec;
 
 typedef struct {
@@ -142,6 +155,10 @@ typedef struct {
     double *partial[BBB_MAX_TARGETS]; /* ray2d: [n_ray_tiles][C], n_ray_tiles = bbb_ray_tiles(n_data) */
     uint32_t *rescan_list[BBB_MAX_TARGETS]; /* ray2d: [C][G] scratch queue of the change-local rasteriser */
     int32_t *rescan_count[BBB_MAX_TARGETS]; /* ray2d: [C], must be zero when bound */
+    /* ray2d, chain-local step (all three or none): chain-major caches of the CURRENT state */
+    void *idx_cm[BBB_MAX_TARGETS];    /* [C][bbb_idx_row_stride(G)] uint8 (K <= 256) or uint16 nearest-site index */
+    double *res[BBB_MAX_TARGETS];     /* [C][n_data] residual d_pred - d_obs */
+    uint32_t *change_list[BBB_MAX_TARGETS]; /* [C][G] scratch: grid points whose nearest site changes */
     /* chain scalars */
     double *temperature;     /* [C] */
     int64_t *iteration;      /* [C] iterations done (Philox counter) */
@@ -168,6 +185,11 @@ int bbb_abi_version(void);
 const char *bbb_last_error(void);
 /* number of ray tiles the partial-misfit buffer must hold for a ray target with n_data rays */
 int64_t bbb_ray_tiles(int64_t n_data);
+/* chain-local step: elements per chain row of idx_cm (G rounded up to a 16-byte multiple for either index type) */
+int64_t bbb_idx_row_stride(int64_t n_points);
+/* chain-local step: rays per CSC tile for a ray target with n_data rays whose space pads to kmax cells (the
+ * per-chain ray accumulators live in shared memory); 0 if the chain-local step cannot run this shape */
+int64_t bbb_chain_local_tile_rays(int64_t n_data, int32_t kmax, int64_t n_points);
 
 /* Engine life cycle.  Replaces the chain pool `Sampler.advance_chain`
  * (samplers/_samplers.py:191-239).  The spec is copied; device pointers inside it are borrowed. */
@@ -192,8 +214,21 @@ int bbb_engine_set_k_bound(bbb_engine *e, int space, int32_t bound);
 int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream);
 /* One stage of one step, for per-kernel timing and profiling: 0 proposal, 1 rasterisation of the
  * proposed geometry, 2 ray forward + misfit, 3 likelihood ratio / accept / commit.  Calling stages
- * 0,1,2,3 in order is exactly one iteration of bbb_engine_step (ray-tomography problems only). */
+ * 0,1,2,3 in order is exactly one iteration of bbb_engine_step (ray-tomography problems only).
+ * Chain-local engines do rasterisation, forward, misfit and accept in ONE kernel: stage 2 runs it, stages 1
+ * and 3 launch nothing. */
 int bbb_engine_stage(bbb_engine *e, int stage, void *stream);
+/* 1 if this engine runs the chain-local step (one ray target with CSC arrays and chain-major caches bound,
+ * uncorrelated noise, kmax <= 4096, n_points <= 2^20, BBB_FULL_FORWARD != 1), else 0. */
+int bbb_engine_chain_local(bbb_engine *e);
+/* Chain-local engines update residuals and misfit incrementally; every `every` steps (default 256, 0 = never)
+ * bbb_engine_step re-evaluates forward and misfit of the current states from scratch (full SpMM) so rounding
+ * cannot accumulate.  `steps_since` positions the schedule (checkpoint/resume). */
+int bbb_engine_set_resync(bbb_engine *e, int64_t every, int64_t steps_since);
+int64_t bbb_engine_steps_since_resync(bbb_engine *e);
+/* The from-scratch re-evaluation itself (forward + misfit of the current states; the nearest-site index is kept).
+ * Also brings the [G][C] index slot 0 in line with the chain-major index.  No-op for other engines. */
+int bbb_engine_resync(bbb_engine *e, void *stream);
 /* Simulated-annealing schedule `SimulatedAnnealing.on_begin_iteration` (samplers/_samplers.py:402-414):
  * while enabled (temperature_start > 0) every chain's temperature of iteration `it` is
  * max(1, temperature_start * exp(-cooling_rate * it)) for it < min(cooling_iterations, burnin_iterations)
