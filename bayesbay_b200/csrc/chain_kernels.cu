@@ -63,6 +63,28 @@ __device__ __forceinline__ double block_sum_to_thread0(double v, double *s_red) 
     return tot;
 }
 
+// 64-bit fixed-point accumulators kept as two 32-bit planes so that both halves use the native shared-memory
+// integer atomic (a 64-bit shared atomicAdd compiles to a compare-and-swap loop).  The low word's returned value
+// tells whether this addition wrapped; the wraps are carried into the high word.  Every addition is exact modulo
+// 2^64, so the final (hi, lo) does not depend on the order of the additions.
+__device__ __forceinline__ void fx_add(unsigned *lo, unsigned *hi, int r, long long v) {
+#ifdef CS_CAS64
+    // experiment: planes interleaved as one 64-bit word per ray
+    atomicAdd(reinterpret_cast<unsigned long long *>(lo) + r, (unsigned long long)v);
+    return;
+#endif
+    const unsigned xl = (unsigned)v, xh = (unsigned)((unsigned long long)v >> 32);
+    unsigned carry = 0;
+    if (xl != 0) {
+        const unsigned old = atomicAdd(lo + r, xl);
+        carry = ((unsigned)(old + xl) < xl) ? 1u : 0u;
+    }
+    const unsigned ah = xh + carry;
+    if (ah != 0) atomicAdd(hi + r, ah);
+}
+
+constexpr unsigned CS_UNTOUCHED = 0xFFFFFFFFu;  // (hi, lo) = all ones: a NaN pattern no residual can have
+
 template <typename IdxT>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams *epp, int t) {
     const EngineParams &ep = *epp;
@@ -89,10 +111,12 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
         }
         return;
     }
+    if (tid == CS_THREADS - 1) finish_prefetch(ep, c, move);  // thread 0 reads these after the forward
 
     extern __shared__ __align__(16) unsigned char cs_smem[];
     const int K = S.kmax, RT = T.csc_tile_rays, NT = T.csc_n_tiles, G = T.n_points, R = T.n_data;
-    long long *acc = reinterpret_cast<long long *>(cs_smem);
+    unsigned *acc_lo = reinterpret_cast<unsigned *>(cs_smem);
+    unsigned *acc_hi = acc_lo + RT;
     double *sx = reinterpret_cast<double *>(cs_smem + (size_t)RT * 8);
     double *sy = sx + K, *fo = sy + K, *fn = fo + K;
     PrepEntry *prep = reinterpret_cast<PrepEntry *>(fn + K);
@@ -103,6 +127,11 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
     const int rm = B.edit[c], ins = B.edit[C + c];
     const double nx = B.edit_site[c], ny = B.edit_site[C + c];
     const bool recip = T.transform == BBB_TRANSFORM_RECIPROCAL;
+    IdxT *row = reinterpret_cast<IdxT *>(B.idx_cm[t]) + c * ((long long)(G + 15) & ~15LL);
+    unsigned *list = B.change_list[t] + c * (long long)G;  // changed points from the front, re-derive queue from the back
+    constexpr int VEC = 16 / (int)sizeof(IdxT);
+    uint4 wv_next = make_uint4(0, 0, 0, 0);
+    if (tid * VEC < G) wv_next = *reinterpret_cast<const uint4 *>(row + tid * VEC);  // in flight while the tables load
 
     // ---- tables: proposed sites, cell function of the current (fo) and proposed (fn) state --------------------
     double fmax = 0.0;
@@ -122,7 +151,10 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
         fmax = fmax > fabs(v) ? fmax : fabs(v);
         if (!(fabs(v) <= 1.79769313486231570815e308)) fmax = INFINITY;
     }
-    for (int r = tid; r < RT; r += CS_THREADS) acc[r] = 0;
+    for (int r = tid * 4; r < 2 * RT; r += CS_THREADS * 4) {  // RT * 8 bytes is a multiple of 16
+        if (r + 4 <= 2 * RT) *reinterpret_cast<uint4 *>(acc_lo + r) = make_uint4(0, 0, 0, 0);
+        else for (int q = r; q < 2 * RT; ++q) acc_lo[q] = 0;
+    }
     if (tid == 0) { s_front = 0; s_back = 0; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -145,12 +177,12 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
     // ---- change-local rasterisation: which grid points get a new nearest site --------------------------------
     // (same rule as k_raster2d_inc in tomo_kernels.cu: a surviving owner is only challenged by the inserted cell;
     // points of the removed/moved cell are re-derived over all proposed sites; strict '<' with ascending index and
-    // separately rounded products keep the lowest-index tie rule of numpy argmin / KDTree.query)
-    IdxT *row = reinterpret_cast<IdxT *>(B.idx_cm[t]) + c * ((long long)(G + 15) & ~15LL);
-    unsigned *list = B.change_list[t] + c * (long long)G;  // changed points from the front, re-derive queue from the back
-    constexpr int VEC = 16 / (int)sizeof(IdxT);
+    // separately rounded products keep the lowest-index tie rule of numpy argmin / KDTree.query).
+    // List entries: front = (point << 12) | OLD owner, the new owner being the inserted cell; back (after the
+    // re-derivation) = (point << 12) | NEW owner, the old owner being the removed cell.
     for (int g0 = tid * VEC; g0 < G; g0 += CS_THREADS * VEC) {
-        const uint4 wv = *reinterpret_cast<const uint4 *>(row + g0);
+        const uint4 wv = wv_next;
+        if (g0 + CS_THREADS * VEC < G) wv_next = *reinterpret_cast<const uint4 *>(row + g0 + CS_THREADS * VEC);
         const IdxT *ow = reinterpret_cast<const IdxT *>(&wv);
         unsigned chg = 0, scn = 0;
         if (inner == BBB_MOVE_VALUES) {
@@ -182,7 +214,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
             while (chg) {
                 const int q = __ffs(chg) - 1;
                 chg &= chg - 1;
-                list[pos++] = ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)ins;
+                list[pos++] = ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)ow[q];
             }
         }
         if (scn) {
@@ -223,41 +255,83 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
                 if (pk != CS_NONE) {
                     const unsigned g = pk >> CS_M_BITS;
                     const int m = (int)(pk & ((1u << CS_M_BITS) - 1u));
-                    pe.dlt = fn[m] - fo[(int)row[g]];
                     pe.j0 = cp[g];
-                    pe.len = (pe.dlt != 0.0) ? cp[g + 1] - pe.j0 : 0;
+                    pe.len = cp[g + 1] - pe.j0;
+                    pe.dlt = e < n_front ? fn[ins] - fo[m] : fn[m] - fo[rm];
+                    if (pe.dlt == 0.0) pe.len = 0;
                 }
             }
             prep[tid] = pe;
             __syncthreads();
             const int n = min(CS_CHUNK, n_list - base);
-            for (int i = warp; i < n; i += CS_WARPS) {
-                const PrepEntry q = prep[i];
-                for (int j = lane; j < q.len; j += 32) {
-                    const int r = (int)T.csc_rows[q.j0 + j];
-                    const double term = __dmul_rn(T.csc_data[q.j0 + j], q.dlt);
-                    atomicAdd(reinterpret_cast<unsigned long long *>(acc + r), (unsigned long long)__double2ll_rn(term * scale));
+            // two columns per warp and round, four entries per lane and column: all loads of a round are issued
+            // before its first atomic
+            for (int i = warp; i < n; i += 2 * CS_WARPS) {
+                const PrepEntry qa = prep[i];
+                PrepEntry qb{0, 0, 0.0};
+                if (i + CS_WARPS < n) qb = prep[i + CS_WARPS];
+                const int len_max = max(qa.len, qb.len);
+                for (int j = lane; j < len_max; j += 128) {
+                    int ra[4], rb[4];
+                    double wa[4], wb[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int jj = j + 32 * u;
+                        const bool oa = jj < qa.len, ob = jj < qb.len;
+                        ra[u] = oa ? (int)T.csc_rows[qa.j0 + jj] : 0;
+                        wa[u] = oa ? T.csc_data[qa.j0 + jj] : 0.0;
+                        rb[u] = ob ? (int)T.csc_rows[qb.j0 + jj] : 0;
+                        wb[u] = ob ? T.csc_data[qb.j0 + jj] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const long long va = __double2ll_rn(__dmul_rn(wa[u], qa.dlt) * scale);
+                        if (va != 0) fx_add(acc_lo, acc_hi, ra[u], va);
+                        const long long vb = __double2ll_rn(__dmul_rn(wb[u], qb.dlt) * scale);
+                        if (vb != 0) fx_add(acc_lo, acc_hi, rb[u], vb);
+                    }
                 }
             }
             __syncthreads();
         }
     };
+    auto zero_acc = [&]() {
+        for (int r = tid; r < 2 * RT; r += CS_THREADS) acc_lo[r] = 0;
+        __syncthreads();
+    };
 
+    // ---- misfit: phi' - phi = sum_r w_r d_r (2 res_r + d_r) over the touched rays -----------------------------
+    // Single-tile problems leave the NEW residual of every touched ray in the accumulator planes (untouched rays
+    // get a marker), so an accepted proposal is committed with stores only.
     double *res = B.res[t] + c * (long long)R;
     double dphi = 0.0;
     for (int tile = 0; tile < NT; ++tile) {
-        if (tile > 0) {
-            for (int r = tid; r < RT; r += CS_THREADS) acc[r] = 0;
-            __syncthreads();
-        }
+        if (tile > 0) zero_acc();
         accumulate(tile);
         const int r0 = tile * RT, nr = min(RT, R - r0);
-        for (int r = tid; r < nr; r += CS_THREADS) {
-            const long long a = acc[r];
-            if (a != 0) {
-                const double d = (double)a * inv_scale;
-                const double wr = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r0 + r] : 1.0;
-                dphi += wr * (d * (2.0 * res[r0 + r] + d));  // w (res + d)^2 - w res^2
+        for (int rb = tid; rb < nr; rb += 4 * CS_THREADS) {
+            double rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = rb + u * CS_THREADS;
+                rr[u] = r < nr ? res[r0 + r] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = rb + u * CS_THREADS;
+                if (r >= nr) continue;
+                const unsigned lo = acc_lo[r], hi = acc_hi[r];
+                if ((lo | hi) != 0) {
+                    const double d = (double)(long long)(((unsigned long long)hi << 32) | lo) * inv_scale;
+                    const double wr = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r0 + r] : 1.0;
+                    dphi += wr * (d * (2.0 * rr[u] + d));  // w (res + d)^2 - w res^2
+                    const double nv = rr[u] + d;
+                    acc_lo[r] = (unsigned)__double2loint(nv);
+                    acc_hi[r] = (unsigned)__double2hiint(nv);
+                } else {
+                    acc_lo[r] = CS_UNTOUCHED;
+                    acc_hi[r] = CS_UNTOUCHED;
+                }
             }
         }
         if (NT > 1) __syncthreads();
@@ -276,18 +350,22 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
     __syncthreads();
     if (!s_accept) return;
 
-    for (int tile = 0; tile < NT; ++tile) {
-        if (NT > 1) {  // the accumulators of a multi-tile problem were recycled: rebuild the tile's
-            for (int r = tid; r < RT; r += CS_THREADS) acc[r] = 0;
-            __syncthreads();
+    if (NT == 1) {
+        for (int r = tid; r < R; r += CS_THREADS) {
+            const unsigned lo = acc_lo[r], hi = acc_hi[r];
+            if ((lo & hi) != CS_UNTOUCHED) res[r] = __hiloint2double((int)hi, (int)lo);
+        }
+    } else {
+        for (int tile = 0; tile < NT; ++tile) {  // the accumulators were recycled: rebuild each tile's
+            zero_acc();
             accumulate(tile);
+            const int r0 = tile * RT, nr = min(RT, R - r0);
+            for (int r = tid; r < nr; r += CS_THREADS) {
+                const unsigned lo = acc_lo[r], hi = acc_hi[r];
+                if ((lo | hi) != 0) res[r0 + r] += (double)(long long)(((unsigned long long)hi << 32) | lo) * inv_scale;
+            }
+            __syncthreads();
         }
-        const int r0 = tile * RT, nr = min(RT, R - r0);
-        for (int r = tid; r < nr; r += CS_THREADS) {
-            const long long a = acc[r];
-            if (a != 0) res[r0 + r] += (double)a * inv_scale;
-        }
-        if (NT > 1) __syncthreads();
     }
     // nearest-site index: renumber the survivors when the edit shifts cell indices (death), then the changed points
     const bool renumber = (rm >= 0 || ins >= 0) && rm != ins && !(rm < 0 && ins >= k_old);
@@ -308,7 +386,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
     }
     for (int e = tid; e < n_list; e += CS_THREADS) {
         const unsigned pk = e < n_front ? list[e] : list[G - 1 - (e - n_front)];
-        if (pk != CS_NONE) row[pk >> CS_M_BITS] = (IdxT)(pk & ((1u << CS_M_BITS) - 1u));
+        if (pk != CS_NONE) row[pk >> CS_M_BITS] = (IdxT)(e < n_front ? (unsigned)ins : (pk & ((1u << CS_M_BITS) - 1u)));
     }
 }
 

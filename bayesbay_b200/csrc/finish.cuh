@@ -163,6 +163,23 @@ __device__ __forceinline__ void rng_end(const Rng &rng, const EngineParams &ep, 
     B.tape_cursor[c] = (B.tape != nullptr) ? rng.cursor : (long long)rng.n;
 }
 
+// Pull the per-chain scalars finish_chain reads into L1 ahead of time (the chain-local kernel calls this at its
+// start, from an otherwise idle thread, so the decision at its end does not wait on a chain of L2 round trips).
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ inline void finish_prefetch(const EngineParams &ep, long long c, int move) {
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    prefetch_l1(B.temperature + c);
+    prefetch_l1(B.iteration + c);
+    prefetch_l1(B.tape_cursor + c);
+    prefetch_l1(B.n_proposed + (long long)move * C + c);
+    prefetch_l1(B.n_accepted + (long long)move * C + c);
+    for (int t = 0; t < ep.spec.n_targets; ++t) {
+        prefetch_l1(B.phi[t] + c);
+        if (ep.spec.targets[t].cov_kind == BBB_COV_HIERARCHICAL) prefetch_l1(B.sigma[t] + c);
+    }
+}
+
 // Likelihood ratio, MH decision, commit, statistics: _next_iteration (_markov_chain.py:222-243).
 // Returns the accept bit.
 __device__ inline bool finish_chain(const EngineParams &ep, long long c, Rng &rng) {
