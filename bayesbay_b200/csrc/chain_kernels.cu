@@ -21,6 +21,8 @@
 // walks one chain): idx_cm [C][G'] nearest-site index, res [C][R] residual d_pred - d_obs, phi = sum w res^2.
 // Rounding cannot accumulate without bound: the engine re-evaluates res and phi from scratch with the full SpMM
 // every `resync_every` steps (abi.cu).
+#include <cstdlib>
+
 #include "finish.cuh"
 #include "kernels.h"
 
@@ -48,6 +50,10 @@ long long chain_local_tile_rays(long long n_data, int kmax, long long n_points) 
     long long max_tile = (CS_SMEM_BLOCK - fixed) / 8;
     if (max_tile > 65535) max_tile = 65535;  // csc_rows is uint16
     if (max_tile < 1024) return 0;
+    if (const char *cap = getenv("BBB_CHAIN_TILE_RAYS")) {  // tests: force the multi-tile path on small problems
+        const long long v = atoll(cap);
+        if (v >= 1 && v < max_tile) max_tile = v;
+    }
     const long long n_tiles = (n_data + max_tile - 1) / max_tile;
     return (n_data + n_tiles - 1) / n_tiles;
 }

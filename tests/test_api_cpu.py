@@ -256,3 +256,25 @@ def test_position_dependent_prior_host_api():
     ing = problems.REPLAYS["partition_1d_posdep"]()
     par, ll = synthetic.build_problem(ing, bb, device_forward)
     _same(_compile.compile_problem(par, ll), problems.spec_from_ingredients(ing))
+
+
+def test_ray_matrix_csc_tiles_reproduces_the_matrix():
+    """The ray-tile-blocked CSC copy the chain-local step reads (host-side construction, no device needed)."""
+    import scipy.sparse as sp
+
+    pytest.importorskip("torch")
+    from bayesbay_b200._engine import ray_matrix_csc_tiles
+
+    A = sp.random(70, 40, 0.25, format="csr", random_state=3)
+    for tile in (70, 32, 16):
+        colptr, rows, dat, bound = ray_matrix_csc_tiles(A.indptr, A.indices, A.data, 40, tile)
+        n_tiles = -(-70 // tile)
+        assert colptr.shape == (n_tiles, 41) and colptr.dtype == np.int32 and rows.dtype == np.uint16
+        M = np.zeros((70, 40))
+        for q in range(n_tiles):
+            for g in range(40):
+                seg = slice(colptr[q, g], colptr[q, g + 1])
+                assert (np.diff(rows[seg].astype(int)) > 0).all()  # rows ascending inside a column
+                M[q * tile + rows[seg], g] += dat[seg]
+        assert np.array_equal(M, A.toarray())
+        assert bound == np.abs(A.data).max() * np.diff(A.indptr).max()

@@ -317,3 +317,82 @@ def test_full_size_config3_properties():
     assert (prop.sum(0) == 300).all() and (eng.iteration.cpu().numpy() == 300).all()
     share = prop.sum(1) / prop.sum()
     np.testing.assert_allclose(share, [1 / 7, 1 / 7, 3 / 7, 1 / 7, 1 / 7], atol=0.005)
+
+
+def _pair_of_engines(monkeypatch, spec, n_chains, seed, tile_cap=None):
+    """The same problem on the full-SpMM step (reference behaviour: every proposal re-evaluates all rays) and on
+    the chain-local step (change-local forward)."""
+    monkeypatch.setenv("BBB_FULL_FORWARD", "1")
+    full = _engine(spec, n_chains, seed=seed)
+    monkeypatch.setenv("BBB_FULL_FORWARD", "0")
+    if tile_cap is not None:
+        monkeypatch.setenv("BBB_CHAIN_TILE_RAYS", str(tile_cap))
+    local = _engine(spec, n_chains, seed=seed)
+    monkeypatch.delenv("BBB_CHAIN_TILE_RAYS", raising=False)
+    assert not full.chain_local and local.chain_local
+    return full, local
+
+
+@pytest.mark.parametrize("name,n_chains,n_steps,tile_cap", [("small", 64, 80, None), ("small", 48, 80, 16),
+                                                            ("mid", 120, 200, None), ("mid", 60, 120, 200)])
+def test_chain_local_step_equals_full_forward(monkeypatch, name, n_chains, n_steps, tile_cap):
+    """Change-local forward (columns of the ray matrix, fixed-point ray accumulators, incremental residuals)
+    against the full SpMM on the same Philox streams: same moves, same decisions, log-likelihood ratios within
+    1e-12 of the misfit scale, bit-identical nearest-site index, residuals and misfit equal to a from-scratch
+    evaluation.  `tile_cap` forces the multi-tile path (several passes over the ray accumulators)."""
+    from bayesbay_b200 import synthetic
+
+    ing = problems.tomo_small() if name == "small" else synthetic.tomography_2d(
+        nx=64, ny=48, n_sources_per_side=6, n_receivers=20, kmin=3, kmax=300)
+    spec = problems.spec_from_ingredients(ing)
+    full, local = _pair_of_engines(monkeypatch, spec, n_chains, 5, tile_cap)
+    full.init_states()
+    local.init_states()
+    alive = np.ones(n_chains, bool)
+    for t in range(n_steps):
+        full.step(1)
+        local.step(1)
+        assert np.array_equal(full.move.cpu().numpy()[alive], local.move.cpu().numpy()[alive]), t
+        l0, l1 = full.log_like_ratio.cpu().numpy(), local.log_like_ratio.cpu().numpy()
+        m0 = full.misfit_logdet()[0].cpu().numpy()
+        fin = alive & np.isfinite(l0)
+        np.testing.assert_allclose(l1[fin], l0[fin], rtol=1e-9, atol=1e-11 * np.abs(m0[fin]).max())
+        flip = alive & (full.accepted.cpu().numpy() != local.accepted.cpu().numpy())
+        alive &= ~flip  # a decision on a knife edge: stop following the chain
+    assert alive.mean() > 0.97
+    same = (full.current_cell_idx(0) == local.current_cell_idx(0)).all(0).cpu().numpy()
+    assert same[alive].all()
+    m_full = full.misfit_logdet()[0].cpu().numpy()
+    m_loc = local.misfit_logdet()[0].cpu().numpy()
+    np.testing.assert_allclose(m_loc[alive], m_full[alive], rtol=1e-12)
+    res_inc = local.res[0].clone()
+    local.resync()
+    np.testing.assert_allclose(local.misfit_logdet()[0].cpu().numpy(), m_loc, rtol=1e-13)
+    scale = local.res[0].abs().max().item()
+    assert (res_inc - local.res[0]).abs().max().item() <= 1e-13 * max(scale, 1e-300)
+    dp = local.dpred(0)
+    dobs = torch.as_tensor(np.asarray(spec["targets"][0]["dobs"])).cuda()
+    np.testing.assert_allclose((local.res[0].t() + dobs[:, None]).cpu().numpy(), dp.cpu().numpy(), rtol=1e-12)
+
+
+def test_chain_local_step_is_bit_reproducible_and_shard_independent():
+    """The ray accumulators are fixed point, so neither the thread timing of a launch nor the way chains are
+    sharded over engines may change a single bit of the trajectories."""
+    spec = problems.spec_from_ingredients(problems.tomo_small())
+
+    def run(n, id0):
+        eng = _engine(spec, n, seed=77, chain_id0=id0)
+        assert eng.chain_local
+        eng.init_states()
+        eng.step(120)
+        k, sites, vals = eng.gather_space(0)
+        return k, sites, vals, eng.phi[0][0, 0].clone(), eng.res[0].clone(), eng.n_accepted.clone()
+
+    a, b = run(96, 0), run(96, 0)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    lo, hi = run(40, 0), run(56, 40)
+    assert torch.equal(torch.cat((lo[0], hi[0])), a[0])
+    assert torch.equal(torch.cat((lo[2], hi[2]), dim=2), a[2])
+    assert torch.equal(torch.cat((lo[3], hi[3])), a[3])
+    assert torch.equal(torch.cat((lo[4], hi[4])), a[4])
