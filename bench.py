@@ -7,6 +7,9 @@ tomography).
 
 One "step" = one RJ-MCMC iteration of EVERY chain of the job (proposal -> rasterisation of the proposed
 geometry -> straight-ray forward + misfit -> Metropolis-Hastings decision), i.e. ``n_chains`` chain-steps.
+The engine runs its chain-local step (one thread block per chain: change-local rasterisation + change-local
+forward + misfit + decision in one kernel, ``bayesbay_b200/csrc/chain_kernels.cu``); ``BBB_FULL_FORWARD=1``
+selects the full-SpMM step (every proposal re-evaluates all rays, as the reference does).
 Workload at N = 1: BASELINE.json configs[2] (the configuration the metric is quoted on): 100x100 grid,
 10 000 rays, k in [10, 200], hierarchical noise, 1024 chains.  N > 1: the same problem with 1024 chains per
 GPU (weak scaling), the 16-temperature ladder of configs[3] and one NCCL swap round per 100 steps.
@@ -58,7 +61,8 @@ def algorithmic_bytes(ing, n_chains):
     total = 16 * G + 16 * R + 12 * nnz / n_chains + 48 * K
     fwd = 8 * G + 16 * R + (12 * nnz + 4 * (R + 1) + 8 * R) / n_chains + 16
     raster = 8 * G + 24 * K
-    return dict(total=total, forward_likelihood=fwd, raster=raster)
+    # the chain-local kernel does rasterisation + forward + likelihood of a chain-step in one launch
+    return dict(total=total, forward_likelihood=fwd, raster=raster, chain_step=raster + fwd)
 
 
 # --------------------------------------------------------------------------- #
@@ -217,9 +221,11 @@ def cuda_arm(args):
         warm_ms = float(t.item())
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) -----------------------------
-    # stages of bbb_engine_stage: 0 = k_propose + k_apply_edit, 1 = k_idx_commit_copy + k_raster2d_inc +
-    # k_raster2d_rescan, 2 = k_ray_spmm, 3 = k_finish  (7 kernel launches per step)
-    names = ["propose", "raster2d", "ray_spmm", "finish"]
+    # stages of bbb_engine_stage, full-SpMM step: 0 = k_propose + k_apply_edit, 1 = k_idx_commit_copy +
+    # k_raster2d_inc + k_raster2d_rescan, 2 = k_ray_spmm, 3 = k_finish  (7 kernel launches per step);
+    # chain-local step: 0 = k_propose + k_apply_edit, 2 = k_chain_step, 1 and 3 launch nothing (3 launches per step,
+    # plus the from-scratch re-evaluation of residuals and misfit every 256 steps: 5 launches)
+    names = ["propose", "raster2d", "chain_step" if eng.chain_local else "ray_spmm", "finish"]
     stage_ms = np.zeros(4)
     active_fwd = 0
     active_geom = 0
@@ -265,8 +271,10 @@ def cuda_arm(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     dom = int(np.argmax(stage_ms))
-    units = {"ray_spmm": active_fwd / args.steps, "raster2d": active_geom / args.steps}.get(names[dom], C)
-    per_unit = {"ray_spmm": ab["forward_likelihood"], "raster2d": ab["raster"]}.get(names[dom], 48 * 200)
+    units = {"ray_spmm": active_fwd / args.steps, "chain_step": active_fwd / args.steps,
+             "raster2d": active_geom / args.steps}.get(names[dom], C)
+    per_unit = {"ray_spmm": ab["forward_likelihood"], "chain_step": ab["chain_step"],
+                "raster2d": ab["raster"]}.get(names[dom], 48 * 200)
     achieved = per_unit * units / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     traffic = None
     tpath = os.path.join(REPO, "profiles", "traffic.json")
@@ -289,8 +297,10 @@ def cuda_arm(args):
         "wall_s_timed_region": wall,
         "clocks": {k: clk[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clk else None,
         "e2e": e2e,
-        "gpu_launches": 7 * args.steps + (2 * n_swaps if tempered else 0),
-        "kernel_ms": {n: float(v) for n, v in zip(names, stage_ms)},
+        "gpu_launches": (3 if eng.chain_local else 7) * args.steps + (2 * n_swaps if tempered else 0),
+        "step_kind": "chain-local (k_propose, k_apply_edit, k_chain_step)" if eng.chain_local
+        else "full SpMM (k_propose, k_apply_edit, k_idx_commit_copy, k_raster2d_inc, k_raster2d_rescan, k_ray_spmm, k_finish)",
+        "kernel_ms": {n: float(v) for n, v in zip(names, stage_ms) if not (eng.chain_local and n in ("raster2d", "finish"))},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_chain_step": per_unit, "chain_steps_per_launch": units,
@@ -304,34 +314,48 @@ def cuda_arm(args):
 
 
 def e2e_run(eng, steps, device, world, dist):
+    """The plugin call with HOST buffers, one iteration per call: the chains' states (k, sites, values, noise
+    sigma, temperature, iteration) go pinned host -> device, the chains advance one iteration, the updated states
+    come back device -> host and the host waits for them.  The derived per-chain caches (nearest-site index,
+    residuals, misfit) stay resident on the device between calls and are reused only after the uploaded states
+    were compared, on the device, with the states the caches belong to (bit-identical -> reuse, else the engine
+    re-derives them with bbb_engine_refresh) -- the analogue of the d_pred / KD-tree caches the reference pickles
+    along with every chain."""
     import torch
 
     C = eng.C
 
     def image():
         k, sites, vals = eng.gather_space(0)
-        return [k, sites, vals, eng.sigma[0][0].clone(), eng.phi[0][0].clone(), eng.current_cell_idx(0),
-                eng.temperature.clone(), eng.iteration.clone()]
+        return [k, sites, vals, eng.sigma[0][0].clone(), eng.temperature.clone(), eng.iteration.clone()]
 
     dev_img = image()
     host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in dev_img]
+    stage = [torch.empty_like(t) for t in dev_img]
     for h, d in zip(host, dev_img):
         h.copy_(d)
     torch.cuda.synchronize(device)
     nbytes = sum(h.numel() * h.element_size() for h in host)
+    refreshed = [0]
 
     def load():
-        k, sites, vals, sg, phi, idx, temp, it = host
-        eng.k[0][0].copy_(k, non_blocking=True)
-        eng.sites[0][0].copy_(sites, non_blocking=True)
-        eng.values[0][0].copy_(vals, non_blocking=True)
-        eng.sigma[0][0].copy_(sg, non_blocking=True)
-        eng.phi[0][0].copy_(phi, non_blocking=True)
-        eng.cell_idx[0][0].copy_(idx, non_blocking=True)
-        eng.temperature.copy_(temp, non_blocking=True)
-        eng.iteration.copy_(it, non_blocking=True)
-        eng.sel[0].zero_()
-        eng.idx_sel[0].zero_()
+        for h, d in zip(host, stage):
+            d.copy_(h, non_blocking=True)
+        cur = image()
+        kmask = (torch.arange(stage[1].shape[1], device=device)[:, None] < stage[0][None, :])[None]  # cells in use
+        same = torch.equal(stage[0], cur[0]) and all(torch.equal(a, b) for a, b in zip(stage[3:], cur[3:]))
+        z = torch.zeros((), dtype=torch.float64, device=device)
+        same = same and all(torch.equal(torch.where(kmask, stage[i], z), torch.where(kmask, cur[i], z)) for i in (1, 2))
+        if not same:  # caller changed the chains: write them and re-derive the caches
+            refreshed[0] += 1
+            eng.k[0].copy_(torch.stack((stage[0], stage[0])))
+            eng.sites[0][0].copy_(stage[1])
+            eng.values[0][0].copy_(stage[2])
+            eng.sigma[0].copy_(torch.stack((stage[3], stage[3])))
+            eng.sel[0].zero_()
+            eng.refresh()
+        eng.temperature.copy_(stage[4])
+        eng.iteration.copy_(stage[5])
 
     def store():
         for h, d in zip(host, image()):
@@ -357,9 +381,10 @@ def e2e_run(eng, steps, device, world, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return {"value": world * C * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
-            "d2h_bytes_per_step": nbytes, "ms_per_step": ms / steps,
-            "what": "per call: pinned-host chain states + caches (misfit, nearest-site index) -> device, one iteration "
-                    "through bbb_engine_step, updated states + caches -> host"}
+            "d2h_bytes_per_step": nbytes, "ms_per_step": ms / steps, "cache_refreshes": refreshed[0],
+            "what": "per call: pinned-host chain states (k, sites, values, sigma, temperature, iteration) -> device, "
+                    "compared on the device with the states the resident caches belong to, one iteration through "
+                    "bbb_engine_step, updated states -> host, host waits"}
 
 
 # --------------------------------------------------------------------------- #
