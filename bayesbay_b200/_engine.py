@@ -28,9 +28,9 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def ray_matrix_csc_tiles(indptr, indices, data, n_points: int, tile_rays: int):
-    """Ray-tile-blocked CSC copy of a CSR ray matrix (``bbb_target_spec.csc_*``): entries sorted by
+    """Ray-tile-blocked CSC copy of a CSR ray matrix (one level of ``bbb_target_spec.csc_*``): entries sorted by
     (ray tile, column, ray); returns ``(colptr [n_tiles][G+1] int32, rows [nnz] uint16 -- ray index inside its
-    tile --, data [nnz] float64, bound = max|data| * longest row)``."""
+    tile --, data [nnz] float64, bound = max over rays of sum |data|)``."""
     indptr = np.asarray(indptr, dtype=np.int64)
     indices = np.asarray(indices, dtype=np.int64)
     data = np.asarray(data, dtype=np.float64)
@@ -45,11 +45,49 @@ def ray_matrix_csc_tiles(indptr, indices, data, n_points: int, tile_rays: int):
     colptr = np.empty((n_tiles, n_points + 1), dtype=np.int64)
     for q in range(n_tiles):
         colptr[q] = cum[q * n_points: (q + 1) * n_points + 1]
-    if cum[-1] >= 2 ** 31:
-        raise ValueError("ray matrix too large for 32-bit CSC offsets")
-    bound = float(np.abs(data).max(initial=0.0)) * float(lens.max(initial=0))
+    if cum[-1] >= 2 ** 30:
+        raise ValueError("ray matrix too large for the CSC offsets")
+    bound = float(np.bincount(rows, weights=np.abs(data), minlength=n_rays).max(initial=0.0))
     return (colptr.astype(np.int32), (rows[order] - tile[order] * tile_rays).astype(np.uint16),
             np.ascontiguousarray(data[order]), bound)
+
+
+def ray_matrix_csc_levels(indptr, indices, data, n_points: int, tile_rays: int, n_levels: int = L.CSC_LEVELS):
+    """All levels of the CSC copy: level l sums every aligned group of 4**l consecutive columns into one."""
+    import scipy.sparse as sp
+
+    n_rays = np.asarray(indptr).size - 1
+    A = sp.csr_matrix((np.asarray(data, dtype=np.float64), np.asarray(indices), np.asarray(indptr)), shape=(n_rays, n_points))
+    out = []
+    for lvl in range(n_levels):
+        s = 4 ** lvl
+        if lvl == 0:
+            M = A
+        else:
+            n_groups = -(-n_points // s)
+            S = sp.csr_matrix((np.ones(n_points), (np.arange(n_points), np.arange(n_points) // s)), shape=(n_points, n_groups))
+            M = (A @ S).tocsr()
+            M.sum_duplicates()
+        out.append(ray_matrix_csc_tiles(M.indptr, M.indices, M.data, M.shape[1], tile_rays))
+    return out
+
+
+def morton_order(points):
+    """Permutation that lists 2-D points along a Morton (Z-order) curve of their coordinate RANKS, so that aligned
+    groups of 4 / 16 consecutive points are 2x2 / 4x4 blocks of a regular grid (and compact clusters of any other
+    point set).  ``perm[new] = old``."""
+    pts = np.asarray(points, dtype=np.float64)
+    ix = np.unique(pts[:, 0], return_inverse=True)[1].astype(np.uint64)
+    iy = np.unique(pts[:, 1], return_inverse=True)[1].astype(np.uint64)
+
+    def spread(v):
+        v = v & np.uint64(0xFFFFFFFF)
+        for sh, mask in ((16, 0x0000FFFF0000FFFF), (8, 0x00FF00FF00FF00FF), (4, 0x0F0F0F0F0F0F0F0F),
+                         (2, 0x3333333333333333), (1, 0x5555555555555555)):
+            v = (v | (v << np.uint64(sh))) & np.uint64(mask)
+        return v
+
+    return np.argsort(spread(ix) | (spread(iy) << np.uint64(1)), kind="stable")
 
 
 class Engine:
@@ -68,6 +106,7 @@ class Engine:
         self.seed = int(seed)
         self.chain_id0 = int(chain_id0)
         self._keep: List[torch.Tensor] = []  # device constants borrowed by the C side
+        self.point_perm = {}  # ray target -> (perm, inv) of its query points (device order = points[perm])
         self._handle = C.c_void_p()
         self._cspec = self._build_spec()
         L.check(self.lib.bbb_engine_create(C.byref(self._cspec), self.dev_index, C.byref(self._handle)))
@@ -146,6 +185,16 @@ class Engine:
                 t.transform = L.TRANSFORM_RECIPROCAL if f.get("transform", "reciprocal") == "reciprocal" else L.TRANSFORM_IDENTITY
                 pts = np.asarray(f["points"], dtype=np.float64)
                 t.n_points = pts.shape[0]
+                # the device sees the query points in Morton order (internal: current_cell_idx() undoes it)
+                K = spec["spaces"][f["space"]]["kmax"]
+                tile = int(self.lib.bbb_chain_local_tile_rays(t.n_data, K, t.n_points))
+                local = tile > 0 and not tg.get("correlated")
+                perm = morton_order(pts) if local else np.arange(t.n_points)
+                inv = np.empty_like(perm)
+                inv[perm] = np.arange(t.n_points)
+                self.point_perm[i] = (torch.as_tensor(perm).to(self.device), torch.as_tensor(inv).to(self.device))
+                pts = pts[perm]
+                f = dict(f, indices=inv[np.asarray(f["indices"])])
                 t.nnz = int(np.asarray(f["indices"]).size)
                 if np.asarray(f["indptr"]).size != t.n_data + 1:
                     raise ValueError("ray matrix rows do not match the number of data")
@@ -156,16 +205,15 @@ class Engine:
                 t.data = self._const(f["data"], np.float64).data_ptr()
                 t.points_x = self._const(pts[:, 0], np.float64).data_ptr()
                 t.points_y = self._const(pts[:, 1], np.float64).data_ptr()
-                # CSC copy for the chain-local step (0 = this shape cannot run it: the engine then does full SpMMs)
-                K = spec["spaces"][f["space"]]["kmax"]
-                tile = int(self.lib.bbb_chain_local_tile_rays(t.n_data, K, t.n_points))
-                if tile > 0 and not tg.get("correlated"):
-                    colptr, rows, cdat, bound = ray_matrix_csc_tiles(f["indptr"], f["indices"], f["data"], t.n_points, tile)
-                    t.csc_tile_rays, t.csc_n_tiles = tile, colptr.shape[0]
-                    t.csc_colptr = self._const(colptr, np.int32).data_ptr()
-                    t.csc_rows = self._const(rows.view(np.int16), np.int16).data_ptr()
-                    t.csc_data = self._const(cdat, np.float64).data_ptr()
-                    t.csc_bound = bound
+                # CSC copy for the chain-local step (tile == 0: this shape cannot run it, the engine does full SpMMs)
+                if local:
+                    levels = ray_matrix_csc_levels(f["indptr"], f["indices"], f["data"], t.n_points, tile)
+                    t.csc_tile_rays, t.csc_n_tiles, t.csc_n_levels = tile, levels[0][0].shape[0], len(levels)
+                    for lvl, (colptr, rows, cdat, bound) in enumerate(levels):
+                        t.csc_colptr[lvl] = self._const(colptr, np.int32).data_ptr()
+                        t.csc_rows[lvl] = self._const(rows.view(np.int16), np.int16).data_ptr()
+                        t.csc_data[lvl] = self._const(cdat, np.float64).data_ptr()
+                    t.csc_bound = levels[0][3]
             elif f["kind"] in ("lookup1d", "polynomial"):
                 t.param = f["param"]
                 x = np.asarray(f["x"], dtype=np.float64)
@@ -218,7 +266,7 @@ class Engine:
                 K = self.spec["spaces"][tg["forward"]["space"]]["kmax"]
                 self.idx_cm.append(z((Cn, int(self.lib.bbb_idx_row_stride(G))), u8 if K <= 256 else torch.int16))
                 self.res.append(z((Cn, int(np.asarray(tg["dobs"]).size)), f64))
-                self.change_list.append(torch.empty((Cn, G), dtype=i32, device=dev))
+                self.change_list.append(torch.empty((Cn, G + (G + 15) // 16), dtype=i32, device=dev))
             else:
                 self.idx_cm.append(None)
                 self.res.append(None)
@@ -348,12 +396,13 @@ class Engine:
 
     def current_cell_idx(self, t: int) -> torch.Tensor:
         """[G][C] nearest-site index of the current states of ray target ``t``."""
+        inv = self.point_perm[t][1]
         if self.chain_local:
             G = self.cell_idx[t].shape[1]
-            return self.idx_cm[t][:, :G].t().contiguous()
+            return self.idx_cm[t][:, :G].t().index_select(0, inv).contiguous()
         sel = self.idx_sel[t].long()
         idx = self.cell_idx[t]
-        return torch.where(sel[None, :] == 0, idx[0], idx[1])
+        return torch.where(sel[None, :] == 0, idx[0], idx[1]).index_select(0, inv)
 
     # ------------------------------------------------------------------ host <-> device state
     def load_states(self, states: List[dict], temperatures=None):

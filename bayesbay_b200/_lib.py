@@ -13,6 +13,7 @@ MAX_SPACES = 4
 MAX_PARAMS = 8
 MAX_TARGETS = 4
 MAX_LINEAR_PARAMS = 16
+CSC_LEVELS = 3
 ABI_VERSION = 2
 
 SPACE_PLAIN, SPACE_VORONOI1D, SPACE_VORONOI2D = 0, 1, 2
@@ -54,8 +55,9 @@ class TargetSpec(C.Structure):
         ("x", _vp),
         ("n_lin_params", C.c_int32), ("lin_params", C.c_int32 * MAX_LINEAR_PARAMS),
         ("G", _vp),
-        ("csc_tile_rays", C.c_int32), ("csc_n_tiles", C.c_int32),
-        ("csc_colptr", _vp), ("csc_rows", _vp), ("csc_data", _vp), ("csc_bound", C.c_double),
+        ("csc_tile_rays", C.c_int32), ("csc_n_tiles", C.c_int32), ("csc_n_levels", C.c_int32),
+        ("csc_colptr", _vp * CSC_LEVELS), ("csc_rows", _vp * CSC_LEVELS), ("csc_data", _vp * CSC_LEVELS),
+        ("csc_bound", C.c_double),
     ]
 
 

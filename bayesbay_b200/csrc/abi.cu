@@ -114,9 +114,11 @@ static int validate_spec(const bbb_problem_spec *P) {
             if (T.csc_tile_rays != 0) {
                 if (T.csc_tile_rays != chain_local_tile_rays(T.n_data, S.kmax, T.n_points))
                     return fail(BBB_ERR_INVALID, "target %d: csc_tile_rays must be bbb_chain_local_tile_rays()", t);
-                if (T.csc_n_tiles != (T.n_data + T.csc_tile_rays - 1) / T.csc_tile_rays || !T.csc_colptr || !T.csc_rows ||
-                    !T.csc_data || !(T.csc_bound >= 0))
-                    return fail(BBB_ERR_INVALID, "target %d: CSC arrays", t);
+                if (T.csc_n_tiles != (T.n_data + T.csc_tile_rays - 1) / T.csc_tile_rays || T.csc_n_levels < 1 ||
+                    T.csc_n_levels > BBB_CSC_LEVELS || !(T.csc_bound >= 0))
+                    return fail(BBB_ERR_INVALID, "target %d: CSC tiles / levels", t);
+                for (int l = 0; l < T.csc_n_levels; ++l)
+                    if (!T.csc_colptr[l] || !T.csc_rows[l] || !T.csc_data[l]) return fail(BBB_ERR_INVALID, "target %d: CSC arrays of level %d", t, l);
             }
         } else if (T.fwd_kind == BBB_FWD_LOOKUP1D) {
             if (S.kind != BBB_SPACE_VORONOI1D) return fail(BBB_ERR_INVALID, "target %d: lookup1d forward needs a Voronoi1D space", t);

@@ -17,6 +17,12 @@
 // 2^9 times finer than the fp64 rounding of a term of maximal size, and the result is bit-identical run to run
 // and independent of how chains are sharded.
 //
+// Merged columns: the changed points come in spatially compact runs, and neighbouring columns hold mostly the
+// same rays.  Besides the columns themselves (level 0) the CSC copy therefore holds the sums of every aligned group
+// of 4 (level 1) and 16 (level 2) consecutive columns; when all points of a group change between the same two
+// cells, ONE merged column replaces 4 or 16 (the host orders the grid points along a Morton curve, so a group is a
+// 2x2 / 4x4 block of the grid).  Fewer entries = fewer shared-memory atomics, the kernel's bound.
+//
 // Resident per-chain caches (chain-major, unlike the [..][C] arrays of the other kernels, because here one block
 // walks one chain): idx_cm [C][G'] nearest-site index, res [C][R] residual d_pred - d_obs, phi = sum w res^2.
 // Rounding cannot accumulate without bound: the engine re-evaluates res and phi from scratch with the full SpMM
@@ -32,12 +38,27 @@ constexpr int CS_THREADS = 512;
 constexpr int CS_WARPS = CS_THREADS / 32;
 constexpr int CS_CHUNK = CS_THREADS;       // change-list entries prepared per round
 constexpr unsigned CS_NONE = 0xFFFFFFFFu;  // list entry: point re-derived, nearest site unchanged
-constexpr int CS_M_BITS = 12;              // list entry = (grid point << 12) | new nearest site
+constexpr int CS_M_BITS = 12;              // list entry = back << 31 | level << 29 | group index << 12 | cell
+constexpr int CS_G_BITS = 17;              // bits of the group index: n_points <= 2^17
+constexpr unsigned CS_BACK = 1u << 31;     // entry of a point that LOST its owner: cell = its new owner (else: old owner)
+constexpr unsigned CS_G_MASK = (1u << CS_G_BITS) - 1u, CS_M_MASK = (1u << CS_M_BITS) - 1u;
+constexpr int CS_PTS = 16;                 // grid points per thread and pass = the largest merged group
 constexpr int CS_SMEM_BLOCK = 112 * 1024;  // two resident blocks per SM
 
 struct PrepEntry {
-    int j0, len;  // entries of the point's column inside the current ray tile
-    double dlt;   // change of the cell function at the point
+    int j0, len;  // entries of the (merged) column inside the current ray tile; the level rides in len's top 2 bits
+    double dlt;   // change of the cell function at the column's points
+};
+
+// 16 consecutive nearest-site indices of one chain (one or two 16-byte loads)
+template <typename IdxT>
+struct IdxVec {
+    uint4 w[sizeof(IdxT)];
+    __device__ __forceinline__ void load(const IdxT *p) {
+#pragma unroll
+        for (int i = 0; i < (int)sizeof(IdxT); ++i) w[i] = reinterpret_cast<const uint4 *>(p)[i];
+    }
+    __device__ __forceinline__ int at(int q) const { return (int)reinterpret_cast<const IdxT *>(w)[q]; }
 };
 
 __host__ __device__ inline size_t chain_step_smem(int tile_rays, int K) {
@@ -45,7 +66,7 @@ __host__ __device__ inline size_t chain_step_smem(int tile_rays, int K) {
 }
 
 long long chain_local_tile_rays(long long n_data, int kmax, long long n_points) {
-    if (kmax > (1 << CS_M_BITS) || n_points > (1LL << (32 - CS_M_BITS)) - 1 || n_data < 1) return 0;
+    if (kmax > (1 << CS_M_BITS) || n_points > (1LL << CS_G_BITS) || n_data < 1) return 0;
     const long long fixed = (long long)chain_step_smem(0, kmax) + 1024;
     long long max_tile = (CS_SMEM_BLOCK - fixed) / 8;
     if (max_tile > 65535) max_tile = 65535;  // csc_rows is uint16
@@ -134,10 +155,12 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
     const double nx = B.edit_site[c], ny = B.edit_site[C + c];
     const bool recip = T.transform == BBB_TRANSFORM_RECIPROCAL;
     IdxT *row = reinterpret_cast<IdxT *>(B.idx_cm[t]) + c * ((long long)(G + 15) & ~15LL);
-    unsigned *list = B.change_list[t] + c * (long long)G;  // changed points from the front, re-derive queue from the back
-    constexpr int VEC = 16 / (int)sizeof(IdxT);
-    uint4 wv_next = make_uint4(0, 0, 0, 0);
-    if (tid * VEC < G) wv_next = *reinterpret_cast<const uint4 *>(row + tid * VEC);  // in flight while the tables load
+    // change list [0, G) and, behind it, the queue of 16-point groups with points to re-derive
+    unsigned *list = B.change_list[t] + c * (long long)(G + (G + 15) / 16);
+    unsigned *queue = list + G;
+    const int n_levels = T.csc_n_levels;
+    IdxVec<IdxT> wv_next;
+    wv_next.load(row + min(tid * CS_PTS, G - 1) / CS_PTS * CS_PTS);  // in flight while the tables load
 
     // ---- tables: proposed sites, cell function of the current (fo) and proposed (fn) state --------------------
     double fmax = 0.0;
@@ -184,23 +207,23 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
     // (same rule as k_raster2d_inc in tomo_kernels.cu: a surviving owner is only challenged by the inserted cell;
     // points of the removed/moved cell are re-derived over all proposed sites; strict '<' with ascending index and
     // separately rounded products keep the lowest-index tie rule of numpy argmin / KDTree.query).
-    // List entries: front = (point << 12) | OLD owner, the new owner being the inserted cell; back (after the
-    // re-derivation) = (point << 12) | NEW owner, the old owner being the removed cell.
-    for (int g0 = tid * VEC; g0 < G; g0 += CS_THREADS * VEC) {
-        const uint4 wv = wv_next;
-        if (g0 + CS_THREADS * VEC < G) wv_next = *reinterpret_cast<const uint4 *>(row + g0 + CS_THREADS * VEC);
-        const IdxT *ow = reinterpret_cast<const IdxT *>(&wv);
+    // List entries (back << 31 | level << 29 | group << 12 | cell): points captured by the inserted cell carry their
+    // OLD owner; points that lost their owner (back = 1, after the re-derivation) their NEW owner, the old one being
+    // the removed cell.
+    for (int g0 = tid * CS_PTS; g0 < G; g0 += CS_THREADS * CS_PTS) {
+        const IdxVec<IdxT> wv = wv_next;
+        if (g0 + CS_THREADS * CS_PTS < G) wv_next.load(row + g0 + CS_THREADS * CS_PTS);
         unsigned chg = 0, scn = 0;
         if (inner == BBB_MOVE_VALUES) {
 #pragma unroll
-            for (int q = 0; q < VEC; ++q)
-                if (g0 + q < G && (int)ow[q] == rm) chg |= 1u << q;
+            for (int q = 0; q < CS_PTS; ++q)
+                if (g0 + q < G && wv.at(q) == rm) chg |= 1u << q;
         } else {
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) {
+            for (int q = 0; q < CS_PTS; ++q) {
                 const int g = g0 + q;
                 if (g >= G) continue;
-                const int o = (int)ow[q];
+                const int o = wv.at(q);
                 if (rm >= 0 && o == rm) {
                     scn |= 1u << q;
                 } else if (ins >= 0) {
@@ -216,55 +239,113 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
             }
         }
         if (chg) {
-            int pos = atomicAdd(&s_front, __popc(chg));
-            while (chg) {
-                const int q = __ffs(chg) - 1;
-                chg &= chg - 1;
-                list[pos++] = ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)ow[q];
+            // merged groups: all 16 points, or an aligned group of 4, change from the SAME old owner
+            unsigned quads = 0;
+            bool hex = false;
+            if (n_levels >= 3 && chg == 0xFFFFu) {
+                hex = true;
+#pragma unroll
+                for (int q = 1; q < CS_PTS; ++q) hex &= wv.at(q) == wv.at(0);
+            }
+            if (!hex && n_levels >= 2) {
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const bool same = wv.at(4 * qd + 1) == wv.at(4 * qd) && wv.at(4 * qd + 2) == wv.at(4 * qd) &&
+                                      wv.at(4 * qd + 3) == wv.at(4 * qd);
+                    if (((chg >> (4 * qd)) & 0xFu) == 0xFu && same) {
+                        quads |= 1u << qd;
+                        chg &= ~(0xFu << (4 * qd));
+                    }
+                }
+            }
+            if (hex) {
+                const int pos = atomicAdd(&s_front, 1);
+                list[pos] = (2u << 29) | ((unsigned)(g0 >> 4) << CS_M_BITS) | (unsigned)wv.at(0);
+            } else {
+                int pos = atomicAdd(&s_front, __popc(quads) + __popc(chg));
+                while (quads) {
+                    const int qd = __ffs(quads) - 1;
+                    quads &= quads - 1;
+                    list[pos++] = (1u << 29) | ((unsigned)((g0 >> 2) + qd) << CS_M_BITS) | (unsigned)wv.at(4 * qd);
+                }
+                while (chg) {
+                    const int q = __ffs(chg) - 1;
+                    chg &= chg - 1;
+                    list[pos++] = ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)wv.at(q);
+                }
             }
         }
-        if (scn) {
-            int pos = atomicAdd(&s_back, __popc(scn));
-            while (scn) {
-                const int q = __ffs(scn) - 1;
-                scn &= scn - 1;
-                list[G - 1 - pos++] = (unsigned)(g0 + q);
+        if (scn) queue[atomicAdd(&s_back, 1)] = ((unsigned)(g0 >> 4) << 16) | scn;
+    }
+    __syncthreads();
+    // (the queue is complete)
+    // re-derivation: 16 lanes per queued group, lane q = point q of the group; the group's new owners are then
+    // merged like the front entries (a moved cell that still owns a point changes nothing there: 2-D site move,
+    // rm == ins, values kept)
+    {
+        const int n_items = s_back;
+        const int q = tid & 15, half = lane >> 4;
+        for (int base = 0; base < n_items; base += CS_THREADS / 16) {
+            const int it = base + (tid >> 4);
+            const unsigned item = it < n_items ? queue[it] : 0u;
+            const int g0 = (int)(item >> 16) << 4;
+            const bool mine = (item >> q) & 1u;
+            int bi = -1;
+            if (mine) {
+                const double gx = T.points_x[g0 + q], gy = T.points_y[g0 + q];
+                double best = INFINITY;
+                for (int j = 0; j < k_new; ++j) {
+                    const double dx = sx[j] - gx, dy = sy[j] - gy;
+                    const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    if (d < best) { best = d; bi = j; }
+                }
+                if (rm == ins && bi == ins) bi = -1;  // unchanged
             }
+            // owners of the half-warp's 16 points; a point that is not re-derived or unchanged breaks a group
+            const unsigned full = 0xffffffffu;
+            const int b0 = __shfl_sync(full, bi, half * 16);
+            const unsigned all_same = __ballot_sync(full, bi >= 0 && bi == b0);
+            const bool hex = n_levels >= 3 && ((all_same >> (half * 16)) & 0xFFFFu) == 0xFFFFu;
+            const int bq = __shfl_sync(full, bi, (lane & ~3));
+            const unsigned quad_same = __ballot_sync(full, bi >= 0 && bi == bq);
+            const bool quad = !hex && n_levels >= 2 && ((quad_same >> (lane & ~3)) & 0xFu) == 0xFu;
+            unsigned entry = CS_NONE;
+            if (hex) {
+                if (q == 0) entry = CS_BACK | (2u << 29) | ((unsigned)(g0 >> 4) << CS_M_BITS) | (unsigned)bi;
+            } else if (quad) {
+                if ((q & 3) == 0) entry = CS_BACK | (1u << 29) | ((unsigned)((g0 + q) >> 2) << CS_M_BITS) | (unsigned)bi;
+            } else if (bi >= 0) {
+                entry = CS_BACK | ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)bi;
+            }
+            const unsigned emit = __ballot_sync(full, entry != CS_NONE);
+            int pos = 0;
+            if (lane == 0 && emit) pos = atomicAdd(&s_front, __popc(emit));
+            pos = __shfl_sync(full, pos, 0);
+            if (entry != CS_NONE) list[pos + __popc(emit & ((1u << lane) - 1u))] = entry;
         }
     }
     __syncthreads();
-    const int n_front = s_front, n_back = s_back;
-    for (int i = tid; i < n_back; i += CS_THREADS) {
-        const unsigned g = list[G - 1 - i];
-        const double gx = T.points_x[g], gy = T.points_y[g];
-        double best = INFINITY;
-        int bi = 0;
-        for (int j = 0; j < k_new; ++j) {
-            const double dx = sx[j] - gx, dy = sy[j] - gy;
-            const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (d < best) { best = d; bi = j; }
-        }
-        // a moved cell that still owns the point: nothing changes (2-D site move: rm == ins, values kept)
-        list[G - 1 - i] = (rm == ins && bi == ins) ? CS_NONE : ((g << CS_M_BITS) | (unsigned)bi);
-    }
-    __syncthreads();
-    const int n_list = n_front + n_back;
+    const int n_list = s_front;
 
     // ---- change-local forward: fixed-point accumulation of the ray changes of one ray tile ---------------------
+    const int32_t *cp0 = T.csc_colptr[0], *cp1 = T.csc_colptr[1], *cp2 = T.csc_colptr[2];
+    const unsigned short *rw0 = T.csc_rows[0], *rw1 = T.csc_rows[1], *rw2 = T.csc_rows[2];
+    const double *dt0 = T.csc_data[0], *dt1 = T.csc_data[1], *dt2 = T.csc_data[2];
     auto accumulate = [&](int tile) {
-        const int32_t *cp = T.csc_colptr + (long long)tile * (G + 1);
         for (int base = 0; base < n_list; base += CS_CHUNK) {
             const int e = base + tid;
             PrepEntry pe{0, 0, 0.0};
             if (e < n_list) {
-                const unsigned pk = e < n_front ? list[e] : list[G - 1 - (e - n_front)];
-                if (pk != CS_NONE) {
-                    const unsigned g = pk >> CS_M_BITS;
-                    const int m = (int)(pk & ((1u << CS_M_BITS) - 1u));
-                    pe.j0 = cp[g];
-                    pe.len = cp[g + 1] - pe.j0;
-                    pe.dlt = e < n_front ? fn[ins] - fo[m] : fn[m] - fo[rm];
-                    if (pe.dlt == 0.0) pe.len = 0;
+                const unsigned pk = list[e];
+                {
+                    const int lvl = (int)((pk >> 29) & 3u);
+                    const unsigned grp = (pk >> CS_M_BITS) & CS_G_MASK;
+                    const int m = (int)(pk & CS_M_MASK);
+                    const int n_groups = (G + (1 << (2 * lvl)) - 1) >> (2 * lvl);
+                    const int32_t *cp = (lvl == 0 ? cp0 : (lvl == 1 ? cp1 : cp2)) + (long long)tile * (n_groups + 1);
+                    pe.j0 = cp[grp];
+                    pe.dlt = (pk & CS_BACK) ? fn[m] - fo[rm] : fn[ins] - fo[m];
+                    pe.len = (pe.dlt != 0.0) ? ((cp[grp + 1] - pe.j0) | (lvl << 30)) : 0;
                 }
             }
             prep[tid] = pe;
@@ -273,9 +354,14 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
             // two columns per warp and round, four entries per lane and column: all loads of a round are issued
             // before its first atomic
             for (int i = warp; i < n; i += 2 * CS_WARPS) {
-                const PrepEntry qa = prep[i];
+                PrepEntry qa = prep[i];
                 PrepEntry qb{0, 0, 0.0};
                 if (i + CS_WARPS < n) qb = prep[i + CS_WARPS];
+                const int la = qa.len >> 30, lb = qb.len >> 30;
+                qa.len &= 0x3FFFFFFF;
+                qb.len &= 0x3FFFFFFF;
+                const unsigned short *rows_a = la == 0 ? rw0 : (la == 1 ? rw1 : rw2), *rows_b = lb == 0 ? rw0 : (lb == 1 ? rw1 : rw2);
+                const double *data_a = la == 0 ? dt0 : (la == 1 ? dt1 : dt2), *data_b = lb == 0 ? dt0 : (lb == 1 ? dt1 : dt2);
                 const int len_max = max(qa.len, qb.len);
                 for (int j = lane; j < len_max; j += 128) {
                     int ra[4], rb[4];
@@ -284,10 +370,10 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
                     for (int u = 0; u < 4; ++u) {
                         const int jj = j + 32 * u;
                         const bool oa = jj < qa.len, ob = jj < qb.len;
-                        ra[u] = oa ? (int)T.csc_rows[qa.j0 + jj] : 0;
-                        wa[u] = oa ? T.csc_data[qa.j0 + jj] : 0.0;
-                        rb[u] = ob ? (int)T.csc_rows[qb.j0 + jj] : 0;
-                        wb[u] = ob ? T.csc_data[qb.j0 + jj] : 0.0;
+                        ra[u] = oa ? (int)rows_a[qa.j0 + jj] : 0;
+                        wa[u] = oa ? data_a[qa.j0 + jj] : 0.0;
+                        rb[u] = ob ? (int)rows_b[qb.j0 + jj] : 0;
+                        wb[u] = ob ? data_b[qb.j0 + jj] : 0.0;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -374,6 +460,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
         }
     }
     // nearest-site index: renumber the survivors when the edit shifts cell indices (death), then the changed points
+    constexpr int VEC = 16 / (int)sizeof(IdxT);
     const bool renumber = (rm >= 0 || ins >= 0) && rm != ins && !(rm < 0 && ins >= k_old);
     if (renumber) {
         for (int g0 = tid * VEC; g0 < G; g0 += CS_THREADS * VEC) {
@@ -391,8 +478,11 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
         __syncthreads();
     }
     for (int e = tid; e < n_list; e += CS_THREADS) {
-        const unsigned pk = e < n_front ? list[e] : list[G - 1 - (e - n_front)];
-        if (pk != CS_NONE) row[pk >> CS_M_BITS] = (IdxT)(e < n_front ? (unsigned)ins : (pk & ((1u << CS_M_BITS) - 1u)));
+        const unsigned pk = list[e];
+        const int lvl = (int)((pk >> 29) & 3u);
+        const int g_first = (int)((pk >> CS_M_BITS) & CS_G_MASK) << (2 * lvl);
+        const IdxT owner = (IdxT)((pk & CS_BACK) ? (pk & CS_M_MASK) : (unsigned)ins);
+        for (int q = 0; q < (1 << (2 * lvl)); ++q) row[g_first + q] = owner;
     }
 }
 

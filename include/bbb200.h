@@ -34,6 +34,7 @@ extern "C" {
 #define BBB_MAX_PARAMS 8
 #define BBB_MAX_TARGETS 4
 #define BBB_MAX_LINEAR_PARAMS 16
+#define BBB_CSC_LEVELS 3    /* merged-column levels of the CSC copy: groups of 1, 4 and 16 consecutive columns */
 
 typedef enum {
     BBB_OK = 0,
@@ -115,14 +116,17 @@ typedef struct {
      * points whose nearest site changed are visited: d_pred' = d_pred + sum_g G[:, g] * (f(v'(g)) - f(v(g))),
      * the change-local form of `jacobian @ (1 / vel[nearest])`, 31_sw_tomography.ipynb cell 12).
      * Rays are split into csc_n_tiles tiles of csc_tile_rays rays (bbb_chain_local_tile_rays(); the last tile may
-     * be shorter); the entries are sorted by (tile, column, row): entries of column g inside tile q are
-     * [csc_colptr[q * (n_points + 1) + g], csc_colptr[q * (n_points + 1) + g + 1]). */
-    int32_t csc_tile_rays, csc_n_tiles;
-    const int32_t *csc_colptr; /* device [csc_n_tiles][n_points + 1] */
-    const uint16_t *csc_rows;  /* device [nnz] ray index inside its tile */
-    const double *csc_data;    /* device [nnz] */
-    double csc_bound;          /* max|data| * (largest number of entries in a row): bounds any change of d_pred per
-                                * unit change of the cell function; scales the fixed-point ray accumulators */
+     * be shorter).  Level l (0 <= l < csc_n_levels <= BBB_CSC_LEVELS) holds the matrix with every aligned group of
+     * 4^l consecutive columns summed into one (n_l = ceil(n_points / 4^l) columns; level 0 is the matrix itself):
+     * entries sorted by (tile, column, row), the entries of column b inside tile q are
+     * [csc_colptr[l][q * (n_l + 1) + b], csc_colptr[l][q * (n_l + 1) + b + 1]).  Merged levels pay off when
+     * consecutive point indices are spatial neighbours (the Python engine orders the points along a Morton curve). */
+    int32_t csc_tile_rays, csc_n_tiles, csc_n_levels;
+    const int32_t *csc_colptr[BBB_CSC_LEVELS]; /* device [csc_n_tiles][n_l + 1] */
+    const uint16_t *csc_rows[BBB_CSC_LEVELS];  /* device [nnz_l] ray index inside its tile */
+    const double *csc_data[BBB_CSC_LEVELS];    /* device [nnz_l] */
+    double csc_bound;          /* max over rays of sum_g |data|: bounds any change of d_pred per unit change of the
+                                * cell function; scales the fixed-point ray accumulators */
 } bbb_target_spec;
 
 typedef struct {
@@ -158,7 +162,7 @@ typedef struct {
     /* ray2d, chain-local step (all three or none): chain-major caches of the CURRENT state */
     void *idx_cm[BBB_MAX_TARGETS];    /* [C][bbb_idx_row_stride(G)] uint8 (K <= 256) or uint16 nearest-site index */
     double *res[BBB_MAX_TARGETS];     /* [C][n_data] residual d_pred - d_obs */
-    uint32_t *change_list[BBB_MAX_TARGETS]; /* [C][G] scratch: grid points whose nearest site changes */
+    uint32_t *change_list[BBB_MAX_TARGETS]; /* [C][G + ceil(G / 16)] scratch: grid points whose nearest site changes */
     /* chain scalars */
     double *temperature;     /* [C] */
     int64_t *iteration;      /* [C] iterations done (Philox counter) */
@@ -219,7 +223,7 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream);
  * and 3 launch nothing. */
 int bbb_engine_stage(bbb_engine *e, int stage, void *stream);
 /* 1 if this engine runs the chain-local step (one ray target with CSC arrays and chain-major caches bound,
- * uncorrelated noise, kmax <= 4096, n_points <= 2^20, BBB_FULL_FORWARD != 1), else 0. */
+ * uncorrelated noise, kmax <= 4096, n_points <= 2^17, BBB_FULL_FORWARD != 1), else 0. */
 int bbb_engine_chain_local(bbb_engine *e);
 /* Chain-local engines update residuals and misfit incrementally; every `every` steps (default 256, 0 = never)
  * bbb_engine_step re-evaluates forward and misfit of the current states from scratch (full SpMM) so rounding

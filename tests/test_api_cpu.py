@@ -258,23 +258,38 @@ def test_position_dependent_prior_host_api():
     _same(_compile.compile_problem(par, ll), problems.spec_from_ingredients(ing))
 
 
-def test_ray_matrix_csc_tiles_reproduces_the_matrix():
-    """The ray-tile-blocked CSC copy the chain-local step reads (host-side construction, no device needed)."""
+def test_ray_matrix_csc_levels_reproduce_the_matrix():
+    """The ray-tile-blocked, merged-column CSC copy the chain-local step reads (host-side construction, no device
+    needed): level l must equal the matrix with every aligned group of 4**l columns summed."""
     import scipy.sparse as sp
 
     pytest.importorskip("torch")
-    from bayesbay_b200._engine import ray_matrix_csc_tiles
+    from bayesbay_b200._engine import morton_order, ray_matrix_csc_levels
 
-    A = sp.random(70, 40, 0.25, format="csr", random_state=3)
+    A = sp.random(70, 43, 0.25, format="csr", random_state=3)
+    dense = A.toarray()
     for tile in (70, 32, 16):
-        colptr, rows, dat, bound = ray_matrix_csc_tiles(A.indptr, A.indices, A.data, 40, tile)
         n_tiles = -(-70 // tile)
-        assert colptr.shape == (n_tiles, 41) and colptr.dtype == np.int32 and rows.dtype == np.uint16
-        M = np.zeros((70, 40))
-        for q in range(n_tiles):
-            for g in range(40):
-                seg = slice(colptr[q, g], colptr[q, g + 1])
-                assert (np.diff(rows[seg].astype(int)) > 0).all()  # rows ascending inside a column
-                M[q * tile + rows[seg], g] += dat[seg]
-        assert np.array_equal(M, A.toarray())
-        assert bound == np.abs(A.data).max() * np.diff(A.indptr).max()
+        for lvl, (colptr, rows, dat, bound) in enumerate(ray_matrix_csc_levels(A.indptr, A.indices, A.data, 43, tile)):
+            s = 4 ** lvl
+            n_g = -(-43 // s)
+            assert colptr.shape == (n_tiles, n_g + 1) and colptr.dtype == np.int32 and rows.dtype == np.uint16
+            M = np.zeros((70, n_g))
+            for q in range(n_tiles):
+                for g in range(n_g):
+                    seg = slice(colptr[q, g], colptr[q, g + 1])
+                    assert (np.diff(rows[seg].astype(int)) > 0).all()  # rows ascending inside a column
+                    M[q * tile + rows[seg], g] += dat[seg]
+            want = np.add.reduceat(dense, np.arange(0, 43, s), axis=1)
+            np.testing.assert_allclose(M, want, rtol=1e-15, atol=0)
+            assert bound == pytest.approx(np.abs(dense).sum(1).max())
+    # Morton order: aligned groups of 4 / 16 consecutive points are 2x2 / 4x4 blocks of a regular grid
+    xs, ys = np.meshgrid(np.linspace(-1, 1, 12), np.linspace(0, 3, 8))
+    pts = np.column_stack((xs.ravel(), ys.ravel()))
+    perm = morton_order(pts)
+    assert sorted(perm.tolist()) == list(range(96))
+    p = pts[perm]
+    for b in range(0, 96, 4):
+        assert len(set(p[b:b + 4, 0])) == 2 and len(set(p[b:b + 4, 1])) == 2
+    for b in range(0, 96, 16):
+        assert len(set(p[b:b + 16, 0])) == 4 and len(set(p[b:b + 16, 1])) == 4
