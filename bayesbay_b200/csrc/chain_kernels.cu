@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
 
     __shared__ int s_front, s_back, s_accept;
     __shared__ double s_red[CS_WARPS];
+    __shared__ FinishIn s_fin;
 
     const int move = B.move[c];
     const double lpr = B.log_prob_ratio[c];
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
         }
         return;
     }
-    if (tid == CS_THREADS - 1) finish_prefetch(ep, c, move);  // thread 0 reads these after the forward
+    if (tid == CS_THREADS - 1) finish_gather(ep, c, s_fin);  // thread 0 decides from these after the forward
 
     extern __shared__ __align__(16) unsigned char cs_smem[];
     const int K = S.kmax, RT = T.csc_tile_rays, NT = T.csc_n_tiles, G = T.n_points, R = T.n_data;
@@ -432,11 +433,10 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
 
     // ---- likelihood ratio, decision, statistics (thread 0), then the commit by the whole block ----------------
     if (tid == 0) {
-        const Phi3 old = load_phi(B, t, 0, c);
-        store_phi(B, t, 1, c, Phi3{finite ? old.s0 + dphi : NAN, 0.0, 0.0});
+        const double phi_new = finite ? s_fin.phi_old[t].s0 + dphi : NAN;
         Rng rng;
-        rng_begin(rng, ep, c, STREAM_STEP, true);
-        s_accept = finish_chain(ep, c, rng) ? 1 : 0;
+        rng_resume(rng, ep, c, s_fin);
+        s_accept = finish_decide(ep, c, s_fin, rng, &phi_new) ? 1 : 0;
         rng_end(rng, ep, c);
     }
     __syncthreads();

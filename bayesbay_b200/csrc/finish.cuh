@@ -163,76 +163,101 @@ __device__ __forceinline__ void rng_end(const Rng &rng, const EngineParams &ep, 
     B.tape_cursor[c] = (B.tape != nullptr) ? rng.cursor : (long long)rng.n;
 }
 
-// Pull the per-chain scalars finish_chain reads into L1 ahead of time (the chain-local kernel calls this at its
-// start, from an otherwise idle thread, so the decision at its end does not wait on a chain of L2 round trips).
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ inline void finish_prefetch(const EngineParams &ep, long long c, int move) {
-    const bbb_buffers &B = ep.buf;
-    const long long C = B.n_chains;
-    prefetch_l1(B.temperature + c);
-    prefetch_l1(B.iteration + c);
-    prefetch_l1(B.tape_cursor + c);
-    prefetch_l1(B.n_proposed + (long long)move * C + c);
-    prefetch_l1(B.n_accepted + (long long)move * C + c);
-    for (int t = 0; t < ep.spec.n_targets; ++t) {
-        prefetch_l1(B.phi[t] + c);
-        if (ep.spec.targets[t].cov_kind == BBB_COV_HIERARCHICAL) prefetch_l1(B.sigma[t] + c);
-    }
-}
+// Everything the decision reads from global memory, gathered in one go (the chain-local kernel does this at its
+// start from an otherwise idle thread, so the decision at its end is arithmetic and stores only).
+struct FinishIn {
+    int move, sel_s;
+    double lpr, temperature;
+    long long iteration, cursor, n_prop, n_acc;
+    Phi3 phi_old[BBB_MAX_TARGETS];
+    double sig[BBB_MAX_TARGETS][2], rho[BBB_MAX_TARGETS][2];  // [current, proposed]
+};
 
-// Likelihood ratio, MH decision, commit, statistics: _next_iteration (_markov_chain.py:222-243).
-// Returns the accept bit.
-__device__ inline bool finish_chain(const EngineParams &ep, long long c, Rng &rng) {
+__device__ inline void finish_gather(const EngineParams &ep, long long c, FinishIn &in) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
-    if (ep.anneal.enabled) B.temperature[c] = annealing_temperature(ep.anneal, B.iteration[c]);
-    const int move = B.move[c];
-    const double lpr = B.log_prob_ratio[c];
+    in.move = B.move[c];
+    in.lpr = B.log_prob_ratio[c];
+    in.iteration = B.iteration[c];
+    in.cursor = B.tape_cursor[c];
+    in.temperature = ep.anneal.enabled ? annealing_temperature(ep.anneal, in.iteration) : B.temperature[c];
+    const bool noise = (in.move == 4 * P.n_spaces);
+    in.sel_s = noise ? 0 : (int)B.sel[in.move >> 2][c];
+    in.n_prop = B.n_proposed[(long long)in.move * C + c];
+    in.n_acc = B.n_accepted[(long long)in.move * C + c];
+    for (int t = 0; t < P.n_targets; ++t) {
+        const bbb_target_spec &T = P.targets[t];
+        const bool hier = (T.cov_kind == BBB_COV_HIERARCHICAL);
+        in.phi_old[t] = T.correlated ? load_phi(B, t, 0, c) : Phi3{B.phi[t][c], 0.0, 0.0};
+        in.sig[t][0] = hier ? B.sigma[t][c] : 1.0;
+        in.sig[t][1] = (hier && noise) ? B.sigma[t][C + c] : in.sig[t][0];
+        in.rho[t][0] = T.correlated ? B.corr[t][c] : 0.0;
+        in.rho[t][1] = (T.correlated && noise) ? B.corr[t][C + c] : in.rho[t][0];
+    }
+}
+
+// Generator continuing the chain's step from gathered counters (same streams as rng_begin(..., true)).
+__device__ __forceinline__ void rng_resume(Rng &rng, const EngineParams &ep, long long c, const FinishIn &in) {
+    const bbb_buffers &B = ep.buf;
+    if (B.tape != nullptr) {
+        rng.init_tape(B.tape + c * B.tape_stride, in.cursor);
+    } else {
+        rng.init_philox(ep.spec.seed, (uint64_t)(B.chain_id0 + c), (uint64_t)in.iteration, STREAM_STEP);
+        rng.n = (uint32_t)in.cursor;
+    }
+}
+
+// Likelihood ratio, MH decision, commit, statistics: _next_iteration (_markov_chain.py:222-243), from gathered
+// inputs.  `ray_phi_new` (chain-local kernel) is the proposed sum of squared residuals of the ray target, or
+// nullptr (read from where the full-SpMM kernels left it).  Returns the accept bit.
+__device__ inline bool finish_decide(const EngineParams &ep, long long c, const FinishIn &in, Rng &rng,
+                                     const double *ray_phi_new) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    if (ep.anneal.enabled) B.temperature[c] = in.temperature;
+    const int move = in.move;
+    const double lpr = in.lpr;
     const bool noise = (move == 4 * P.n_spaces);
     const int s = move >> 2;
     double llr = 0.0;
+    Phi3 phi_new[BBB_MAX_TARGETS];
     if (!isinf(lpr)) {
         double old_m = 0.0, new_m = 0.0, old_ld = 0.0, new_ld = 0.0;
         for (int t = 0; t < P.n_targets; ++t) {
             const bbb_target_spec &T = P.targets[t];
             const bool hier = (T.cov_kind == BBB_COV_HIERARCHICAL);
-            const Phi3 phi_old = load_phi(B, t, 0, c);
-            Phi3 phi_new = phi_old;
+            const Phi3 phi_old = in.phi_old[t];
+            phi_new[t] = phi_old;
             if (!noise && T.space == s) {
-                if (T.fwd_kind != BBB_FWD_RAY2D) phi_new = small_target_phi(P, B, t, B.sel[s][c] ^ 1, c, nullptr, nullptr);
-                else if (T.correlated || ep.chain_local) phi_new = load_phi(B, t, 1, c);  // k_corr_sums / k_chain_step
-                else phi_new = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
-                store_phi(B, t, 1, c, phi_new);
+                if (T.fwd_kind != BBB_FWD_RAY2D) phi_new[t] = small_target_phi(P, B, t, in.sel_s ^ 1, c, nullptr, nullptr);
+                else if (ray_phi_new != nullptr) phi_new[t] = Phi3{*ray_phi_new, 0.0, 0.0};  // k_chain_step
+                else if (T.correlated) phi_new[t] = load_phi(B, t, 1, c);                     // k_corr_sums
+                else phi_new[t] = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
+                store_phi(B, t, 1, c, phi_new[t]);
             }
-            const double sig_old = hier ? B.sigma[t][c] : 1.0;
-            const double sig_new = (hier && noise) ? B.sigma[t][C + c] : sig_old;
-            const double rho_old = T.correlated ? B.corr[t][c] : 0.0;
-            const double rho_new = (T.correlated && noise) ? B.corr[t][C + c] : rho_old;
             double m0, l0, m1, l1;
-            misfit_logdet_terms(T, phi_old, sig_old, rho_old, m0, l0);
-            misfit_logdet_terms(T, phi_new, sig_new, rho_new, m1, l1);
+            misfit_logdet_terms(T, phi_old, in.sig[t][0], in.rho[t][0], m0, l0);
+            misfit_logdet_terms(T, phi_new[t], in.sig[t][1], in.rho[t][1], m1, l1);
             old_m += m0; new_m += m1;
             if (hier) { old_ld += l0; new_ld += l1; }
         }
         // _log_likelihood_ratio_from_targets (likelihood/_log_likelihood.py:245-251), then / T (:243)
-        llr = (old_ld - new_ld + old_m - new_m) / 2.0 / B.temperature[c];
+        llr = (old_ld - new_ld + old_m - new_m) / 2.0 / in.temperature;
     }
     const double log_u = log(rng.unit());
     const bool accepted = (lpr + llr) > log_u;  // NaN compares false -> rejected
-    if (accepted) {
+    if (accepted) {  // (an accepted proposal has a finite lpr, so phi_new is set)
         if (noise) {
             for (int t = 0; t < P.n_targets; ++t) {
-                if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL) B.sigma[t][c] = B.sigma[t][C + c];
-                if (P.targets[t].correlated) B.corr[t][c] = B.corr[t][C + c];
+                if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL) B.sigma[t][c] = in.sig[t][1];
+                if (P.targets[t].correlated) B.corr[t][c] = in.rho[t][1];
             }
         } else {
-            B.sel[s][c] ^= 1;
-            for (int t = 0; t < P.n_targets; ++t) {
-                const bbb_target_spec &T = P.targets[t];
-                if (T.space != s) continue;
-                store_phi(B, t, 0, c, load_phi(B, t, 1, c));
-            }
+            B.sel[s][c] = (uint8_t)(in.sel_s ^ 1);
+            for (int t = 0; t < P.n_targets; ++t)
+                if (P.targets[t].space == s) store_phi(B, t, 0, c, phi_new[t]);
         }
     }
     // nearest-site index: the proposed index (slot 1) becomes current when a geometry move is accepted; the
@@ -245,10 +270,16 @@ __device__ inline bool finish_chain(const EngineParams &ep, long long c, Rng &rn
     }
     B.log_like_ratio[c] = llr;
     B.accepted[c] = accepted ? 1 : 0;
-    B.n_proposed[(long long)move * C + c] += 1;
-    B.n_accepted[(long long)move * C + c] += accepted ? 1 : 0;
-    B.iteration[c] += 1;
+    B.n_proposed[(long long)move * C + c] = in.n_prop + 1;
+    B.n_accepted[(long long)move * C + c] = in.n_acc + (accepted ? 1 : 0);
+    B.iteration[c] = in.iteration + 1;
     return accepted;
+}
+
+__device__ inline bool finish_chain(const EngineParams &ep, long long c, Rng &rng) {
+    FinishIn in;
+    finish_gather(ep, c, in);
+    return finish_decide(ep, c, in, rng, nullptr);
 }
 
 }  // namespace bbb
