@@ -110,8 +110,6 @@ __device__ __forceinline__ void fx_add(unsigned *lo, unsigned *hi, int r, long l
     if (ah != 0) atomicAdd(hi + r, ah);
 }
 
-constexpr unsigned CS_UNTOUCHED = 0xFFFFFFFFu;  // (hi, lo) = all ones: a NaN pattern no residual can have
-
 template <typename IdxT>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams *epp, int t) {
     const EngineParams &ep = *epp;
@@ -395,7 +393,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
 
     // ---- misfit: phi' - phi = sum_r w_r d_r (2 res_r + d_r) over the touched rays -----------------------------
     // Single-tile problems leave the NEW residual of every touched ray in the accumulator planes (untouched rays
-    // get a marker), so an accepted proposal is committed with stores only.
+    // keep their zeros), so an accepted proposal is committed with stores only.
     double *res = B.res[t] + c * (long long)R;
     double dphi = 0.0;
     for (int tile = 0; tile < NT; ++tile) {
@@ -418,12 +416,10 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
                     const double d = (double)(long long)(((unsigned long long)hi << 32) | lo) * inv_scale;
                     const double wr = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r0 + r] : 1.0;
                     dphi += wr * (d * (2.0 * rr[u] + d));  // w (res + d)^2 - w res^2
-                    const double nv = rr[u] + d;
+                    double nv = rr[u] + d;
+                    if (nv == 0.0) nv = -0.0;  // all-zero planes mean "untouched"; -0.0 is the same residual
                     acc_lo[r] = (unsigned)__double2loint(nv);
                     acc_hi[r] = (unsigned)__double2hiint(nv);
-                } else {
-                    acc_lo[r] = CS_UNTOUCHED;
-                    acc_hi[r] = CS_UNTOUCHED;
                 }
             }
         }
@@ -433,10 +429,11 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
 
     // ---- likelihood ratio, decision, statistics (thread 0), then the commit by the whole block ----------------
     if (tid == 0) {
-        const double phi_new = finite ? s_fin.phi_old[t].s0 + dphi : NAN;
         Rng rng;
+        FinishPre pre;
         rng_resume(rng, ep, c, s_fin);
-        s_accept = finish_decide(ep, c, s_fin, rng, &phi_new) ? 1 : 0;
+        finish_pre(ep, c, s_fin, rng, t, pre);
+        s_accept = finish_post(ep, c, s_fin, pre, t, finite ? s_fin.phi_old[t].s0 + dphi : NAN) ? 1 : 0;
         rng_end(rng, ep, c);
     }
     __syncthreads();
@@ -445,7 +442,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
     if (NT == 1) {
         for (int r = tid; r < R; r += CS_THREADS) {
             const unsigned lo = acc_lo[r], hi = acc_hi[r];
-            if ((lo & hi) != CS_UNTOUCHED) res[r] = __hiloint2double((int)hi, (int)lo);
+            if ((lo | hi) != 0) res[r] = __hiloint2double((int)hi, (int)lo);
         }
     } else {
         for (int tile = 0; tile < NT; ++tile) {  // the accumulators were recycled: rebuild each tile's

@@ -208,11 +208,49 @@ __device__ __forceinline__ void rng_resume(Rng &rng, const EngineParams &ep, lon
     }
 }
 
-// Likelihood ratio, MH decision, commit, statistics: _next_iteration (_markov_chain.py:222-243), from gathered
-// inputs.  `ray_phi_new` (chain-local kernel) is the proposed sum of squared residuals of the ray target, or
-// nullptr (read from where the full-SpMM kernels left it).  Returns the accept bit.
-__device__ inline bool finish_decide(const EngineParams &ep, long long c, const FinishIn &in, Rng &rng,
-                                     const double *ray_phi_new) {
+// The decision in two parts, so that the chain-local kernel can run the long part (logarithms, the generator,
+// the other targets) on an idle thread WHILE the forward of its ray target is being evaluated:
+//   finish_pre   everything that does not depend on the new misfit of the deferred ray target `ray_t`
+//                (ray_t = -1: nothing is deferred),
+//   finish_post  that target's misfit term, the sums in target order, the Metropolis-Hastings test, commit,
+//                statistics.
+// Together they evaluate exactly the expressions of _next_iteration (_markov_chain.py:222-243) in the same order.
+struct FinishPre {
+    double log_u, factor_ray;
+    double m0[BBB_MAX_TARGETS], m1[BBB_MAX_TARGETS], l0[BBB_MAX_TARGETS], l1[BBB_MAX_TARGETS];
+    Phi3 phi_new[BBB_MAX_TARGETS];
+};
+
+__device__ inline void finish_pre(const EngineParams &ep, long long c, const FinishIn &in, Rng &rng, int ray_t,
+                                  FinishPre &pre) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const bool noise = (in.move == 4 * P.n_spaces);
+    const int s = in.move >> 2;
+    pre.factor_ray = 1.0;
+    if (!isinf(in.lpr)) {
+        for (int t = 0; t < P.n_targets; ++t) {
+            const bbb_target_spec &T = P.targets[t];
+            const Phi3 phi_old = in.phi_old[t];
+            pre.phi_new[t] = phi_old;
+            if (!noise && T.space == s && t != ray_t) {
+                if (T.fwd_kind != BBB_FWD_RAY2D) pre.phi_new[t] = small_target_phi(P, B, t, in.sel_s ^ 1, c, nullptr, nullptr);
+                else if (T.correlated) pre.phi_new[t] = load_phi(B, t, 1, c);  // k_corr_sums
+                else pre.phi_new[t] = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
+                store_phi(B, t, 1, c, pre.phi_new[t]);
+            }
+            misfit_logdet_terms(T, phi_old, in.sig[t][0], in.rho[t][0], pre.m0[t], pre.l0[t]);
+            misfit_logdet_terms(T, pre.phi_new[t], in.sig[t][1], in.rho[t][1], pre.m1[t], pre.l1[t]);
+            if (t == ray_t)  // the factor misfit_logdet_terms applies to phi.s0 (the deferred target is uncorrelated)
+                pre.factor_ray = T.cov_kind == BBB_COV_HIERARCHICAL ? 1.0 / (in.sig[t][1] * in.sig[t][1])
+                                                                    : (T.cov_kind == BBB_COV_SCALAR ? T.cov_scalar : 1.0);
+        }
+    }
+    pre.log_u = log(rng.unit());
+}
+
+__device__ inline bool finish_post(const EngineParams &ep, long long c, const FinishIn &in, FinishPre &pre, int ray_t,
+                                   double ray_phi_new) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
@@ -222,32 +260,21 @@ __device__ inline bool finish_decide(const EngineParams &ep, long long c, const 
     const bool noise = (move == 4 * P.n_spaces);
     const int s = move >> 2;
     double llr = 0.0;
-    Phi3 phi_new[BBB_MAX_TARGETS];
     if (!isinf(lpr)) {
+        if (ray_t >= 0 && !noise && P.targets[ray_t].space == s) {
+            pre.phi_new[ray_t] = Phi3{ray_phi_new, 0.0, 0.0};
+            store_phi(B, ray_t, 1, c, pre.phi_new[ray_t]);
+            pre.m1[ray_t] = P.targets[ray_t].cov_kind == BBB_COV_VECTOR ? ray_phi_new : pre.factor_ray * ray_phi_new;
+        }
         double old_m = 0.0, new_m = 0.0, old_ld = 0.0, new_ld = 0.0;
         for (int t = 0; t < P.n_targets; ++t) {
-            const bbb_target_spec &T = P.targets[t];
-            const bool hier = (T.cov_kind == BBB_COV_HIERARCHICAL);
-            const Phi3 phi_old = in.phi_old[t];
-            phi_new[t] = phi_old;
-            if (!noise && T.space == s) {
-                if (T.fwd_kind != BBB_FWD_RAY2D) phi_new[t] = small_target_phi(P, B, t, in.sel_s ^ 1, c, nullptr, nullptr);
-                else if (ray_phi_new != nullptr) phi_new[t] = Phi3{*ray_phi_new, 0.0, 0.0};  // k_chain_step
-                else if (T.correlated) phi_new[t] = load_phi(B, t, 1, c);                     // k_corr_sums
-                else phi_new[t] = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
-                store_phi(B, t, 1, c, phi_new[t]);
-            }
-            double m0, l0, m1, l1;
-            misfit_logdet_terms(T, phi_old, in.sig[t][0], in.rho[t][0], m0, l0);
-            misfit_logdet_terms(T, phi_new[t], in.sig[t][1], in.rho[t][1], m1, l1);
-            old_m += m0; new_m += m1;
-            if (hier) { old_ld += l0; new_ld += l1; }
+            old_m += pre.m0[t]; new_m += pre.m1[t];
+            if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL) { old_ld += pre.l0[t]; new_ld += pre.l1[t]; }
         }
         // _log_likelihood_ratio_from_targets (likelihood/_log_likelihood.py:245-251), then / T (:243)
         llr = (old_ld - new_ld + old_m - new_m) / 2.0 / in.temperature;
     }
-    const double log_u = log(rng.unit());
-    const bool accepted = (lpr + llr) > log_u;  // NaN compares false -> rejected
+    const bool accepted = (lpr + llr) > pre.log_u;  // NaN compares false -> rejected
     if (accepted) {  // (an accepted proposal has a finite lpr, so phi_new is set)
         if (noise) {
             for (int t = 0; t < P.n_targets; ++t) {
@@ -257,7 +284,7 @@ __device__ inline bool finish_decide(const EngineParams &ep, long long c, const 
         } else {
             B.sel[s][c] = (uint8_t)(in.sel_s ^ 1);
             for (int t = 0; t < P.n_targets; ++t)
-                if (P.targets[t].space == s) store_phi(B, t, 0, c, phi_new[t]);
+                if (P.targets[t].space == s) store_phi(B, t, 0, c, pre.phi_new[t]);
         }
     }
     // nearest-site index: the proposed index (slot 1) becomes current when a geometry move is accepted; the
@@ -278,8 +305,10 @@ __device__ inline bool finish_decide(const EngineParams &ep, long long c, const 
 
 __device__ inline bool finish_chain(const EngineParams &ep, long long c, Rng &rng) {
     FinishIn in;
+    FinishPre pre;
     finish_gather(ep, c, in);
-    return finish_decide(ep, c, in, rng, nullptr);
+    finish_pre(ep, c, in, rng, -1, pre);
+    return finish_post(ep, c, in, pre, -1, 0.0);
 }
 
 }  // namespace bbb
