@@ -281,9 +281,8 @@ static int run_raster(bbb_engine *e, int t, bool proposal, cudaStream_t st) {
 static int run_propose(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const long long C = e->host.buf.n_chains;
-    int rc = launch_propose(e->dev, C, st);
-    for (int s = 0; s < P.n_spaces && rc == 0; ++s) rc = launch_apply_edit(e->dev, C, s, P.spaces[s].kmax, st);
-    return rc;
+    (void)P;
+    return launch_propose(e->host, C, st);  // the proposal warps also write the proposed slots
 }
 
 static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool write_partial, cudaStream_t st) {
@@ -406,7 +405,7 @@ int bbb_engine_resync(bbb_engine *e, void *stream) {
 static int run_chain_step(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
-    int rc = launch_chain_step(e->dev, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
+    int rc = launch_chain_step(e->host, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
                                idx_bytes_of(P, e->ray_t), st);
     if (rc != 0) return rc;
     ++e->steps_since_resync;
@@ -441,7 +440,7 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
     const bbb_problem_spec &P = e->host.spec;
     const long long C = e->host.buf.n_chains;
     if (!e->has_ray) {
-        if (n_steps > 0) CU(launch_fused_steps(e->dev, C, n_steps, st));
+        if (n_steps > 0) CU(launch_fused_steps(e->host, C, n_steps, st));
         return BBB_OK;
     }
     for (int64_t it = 0; it < n_steps; ++it) {
@@ -454,7 +453,7 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
                 CU(run_raster(e, t, true, st));
                 CU(run_spmm(e, t, true, nullptr, true, st));
             }
-            CU(launch_finish(e->dev, C, st));
+            CU(launch_finish(e->host, C, st));
         }
         for (int s = 0; s < P.n_spaces; ++s)
             if (e->k_bound[s] < P.spaces[s].kmax) ++e->k_bound[s];  // a step adds at most one cell
@@ -484,7 +483,7 @@ int bbb_engine_stage(bbb_engine *e, int stage, void *stream) {
                 if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) CU(run_spmm(e, t, true, nullptr, true, st));
             break;
         case 3:
-            if (!e->host.chain_local) CU(launch_finish(e->dev, C, st));
+            if (!e->host.chain_local) CU(launch_finish(e->host, C, st));
             for (int s = 0; s < P.n_spaces; ++s)
                 if (e->k_bound[s] < P.spaces[s].kmax) ++e->k_bound[s];
             break;

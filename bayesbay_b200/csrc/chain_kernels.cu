@@ -111,8 +111,7 @@ __device__ __forceinline__ void fx_add(unsigned *lo, unsigned *hi, int r, long l
 }
 
 template <typename IdxT>
-__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams *epp, int t) {
-    const EngineParams &ep = *epp;
+__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const bbb_target_spec &T = P.targets[t];
@@ -483,7 +482,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const EngineParams
     }
 }
 
-int launch_chain_step(const EngineParams *dev, long long C, int t, int tile_rays, int K, int idx_bytes, cudaStream_t st) {
+int launch_chain_step(const EngineParams &dev, long long C, int t, int tile_rays, int K, int idx_bytes, cudaStream_t st) {
     const size_t smem = chain_step_smem(tile_rays, K);
     cudaError_t err;
     if (idx_bytes == 1) {

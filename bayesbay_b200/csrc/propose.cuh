@@ -257,16 +257,37 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
     }
 
     // ---- write the proposed slot ------------------------------------------------------------------
-    // The edit (rm, ins, new cell) is published for k_apply_edit, which writes the proposed slot with one
-    // thread per (cell, chain); the fused small-problem kernel applies it here, one lock-step loop for
-    // every move kind.
+    // The edit (rm, ins, new cell) is published for the forward kernels; the proposed slot is written here: by
+    // the warp's lanes (lanes = output cells) in the cooperative proposal kernel, by the chain's own thread in the
+    // fused small-problem kernel -- one loop for every move kind.
     const int k_new = e.write ? k - (e.rm >= 0 ? 1 : 0) + (e.ins >= 0 ? 1 : 0) : k;
     if (writer) {
         for (int d = 0; d < S.ndim; ++d) B.edit_site[(long long)d * B.n_chains + c] = e.site[d];
         for (int p = 0; p < S.n_params; ++p) B.edit_vals[(long long)p * B.n_chains + c] = e.vals[p];
         k_ref(B, s, prop, c) = k_new;
     }
-    if (e.write && apply_now) {
+    if (e.write && rng.coop) {
+        // warp-cooperative proposal kernel: the 32 lanes (which all hold the same edit) write the proposed slot,
+        // lanes = output cells
+        const int ndim = S.ndim, n_params = S.n_params;
+        const long long C = B.n_chains, KC = (long long)S.kmax * C;
+        double *sites = B.sites[s], *vals = B.values[s];
+        if (e.rm >= 0 || e.ins >= 0) {
+            for (int jo = threadIdx.x & 31; jo < k_new; jo += 32) {
+                if (jo == e.ins) {
+                    for (int d = 0; d < ndim; ++d) sites[((long long)prop * ndim + d) * KC + (long long)jo * C + c] = e.site[d];
+                    for (int p = 0; p < n_params; ++p) vals[((long long)prop * n_params + p) * KC + (long long)jo * C + c] = e.vals[p];
+                } else {
+                    const int jp = jo - ((e.ins >= 0 && jo > e.ins) ? 1 : 0);
+                    const int src = jp + ((e.rm >= 0 && jp >= e.rm) ? 1 : 0);
+                    for (int d = 0; d < ndim; ++d)
+                        sites[((long long)prop * ndim + d) * KC + (long long)jo * C + c] = sites[((long long)cur * ndim + d) * KC + (long long)src * C + c];
+                    for (int p = 0; p < n_params; ++p)
+                        vals[((long long)prop * n_params + p) * KC + (long long)jo * C + c] = vals[((long long)cur * n_params + p) * KC + (long long)src * C + c];
+                }
+            }
+        }
+    } else if (e.write && apply_now) {
         const int ndim = S.ndim, n_params = S.n_params;
         const long long C = B.n_chains, KC = (long long)S.kmax * C;
         const double *__restrict__ s_cur = B.sites[s] + (long long)cur * ndim * KC + c;

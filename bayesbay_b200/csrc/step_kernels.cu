@@ -10,10 +10,9 @@ namespace bbb {
 constexpr int STEP_THREADS = 64;  // 2 warps per block: spreads C = 1024 chains over 16 SMs' worth of blocks
 
 // One WARP per chain: lane 0 owns the generator (every draw is broadcast), the O(k) nearest-site searches of
-// birth/death-from-neighbour run with lanes = sites, and the proposed slot is written by k_apply_edit.
+// birth/death-from-neighbour run with lanes = sites, and the lanes write the proposed slot (lanes = cells).
 constexpr int PROPOSE_WARPS = 4;
-__global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const EngineParams *epp) {
-    const EngineParams &ep = *epp;
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep) {
     const long long c = (long long)blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
     if (c >= ep.buf.n_chains) return;
     Rng rng;
@@ -23,41 +22,7 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const EnginePara
     if ((threadIdx.x & 31) == 0) rng_end(rng, ep, c);
 }
 
-// Writes the proposed slot of space `s` from the published edit scripts: one thread per
-// (output cell jo = blockIdx.y, chain), fully coalesced -- the O(K) part of every proposal.
-__global__ void k_apply_edit(const EngineParams *epp, int s) {
-    const EngineParams &ep = *epp;
-    const bbb_buffers &B = ep.buf;
-    const long long C = B.n_chains;
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const int mv = B.move[c];
-    if (mv == 4 * ep.spec.n_spaces || (mv >> 2) != s) return;
-    const int rm = B.edit[c], ins = B.edit[C + c];
-    if (rm < 0 && ins < 0) return;  // birth at kmax / death at kmin: nothing proposed
-    const bbb_space_spec &S = ep.spec.spaces[s];
-    const int cur = B.sel[s][c], prop = cur ^ 1;
-    const int jo = blockIdx.y;
-    if (jo >= B.k[s][(long long)prop * C + c]) return;
-    const int ndim = S.ndim, n_params = S.n_params;
-    const long long KC = (long long)S.kmax * C;
-    double *sites = B.sites[s];
-    double *vals = B.values[s];
-    if (jo == ins) {
-        for (int d = 0; d < ndim; ++d) sites[((long long)prop * ndim + d) * KC + (long long)jo * C + c] = B.edit_site[d * C + c];
-        for (int p = 0; p < n_params; ++p) vals[((long long)prop * n_params + p) * KC + (long long)jo * C + c] = B.edit_vals[p * C + c];
-    } else {
-        const int jp = jo - ((ins >= 0 && jo > ins) ? 1 : 0);
-        const int src = jp + ((rm >= 0 && jp >= rm) ? 1 : 0);
-        for (int d = 0; d < ndim; ++d)
-            sites[((long long)prop * ndim + d) * KC + (long long)jo * C + c] = sites[((long long)cur * ndim + d) * KC + (long long)src * C + c];
-        for (int p = 0; p < n_params; ++p)
-            vals[((long long)prop * n_params + p) * KC + (long long)jo * C + c] = vals[((long long)cur * n_params + p) * KC + (long long)src * C + c];
-    }
-}
-
-__global__ void __launch_bounds__(STEP_THREADS) k_finish(const EngineParams *epp) {
-    const EngineParams &ep = *epp;
+__global__ void __launch_bounds__(STEP_THREADS) k_finish(const __grid_constant__ EngineParams ep) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ep.buf.n_chains) return;
     Rng rng;
@@ -69,8 +34,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_finish(const EngineParams *epp
 // All forwards thread-evaluable (lookup1d / linear): the whole step is one thread's work and there
 // is no cross-chain dependency, so n_steps iterations run inside ONE launch (the 1-D and polyfit
 // configurations are launch-latency bound otherwise).
-__global__ void __launch_bounds__(STEP_THREADS) k_fused_steps(const EngineParams *epp, long long n_steps) {
-    const EngineParams &ep = *epp;
+__global__ void __launch_bounds__(STEP_THREADS) k_fused_steps(const __grid_constant__ EngineParams ep, long long n_steps) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ep.buf.n_chains) return;
     for (long long it = 0; it < n_steps; ++it) {
@@ -353,24 +317,19 @@ __global__ void k_phi_from_partial(const double *partial, int n_tiles, long long
 // ------------------------------------------------------------------------------------------------
 static inline int blocks_for(long long C, int threads) { return (int)((C + threads - 1) / threads); }
 
-int launch_propose(const EngineParams *p, long long C, cudaStream_t st) {
+int launch_propose(const EngineParams &p, long long C, cudaStream_t st) {
     k_propose<<<blocks_for(C, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p);
-    return (int)cudaGetLastError();
-}
-int launch_apply_edit(const EngineParams *p, long long C, int space, int kmax, cudaStream_t st) {
-    dim3 grid(blocks_for(C, 128), kmax);
-    k_apply_edit<<<grid, 128, 0, st>>>(p, space);
     return (int)cudaGetLastError();
 }
 int launch_corr_sums(const EngineParams *p, long long C, int target, int proposal, cudaStream_t st) {
     k_corr_sums<<<blocks_for(C, 128), 128, 0, st>>>(p, target, proposal);
     return (int)cudaGetLastError();
 }
-int launch_finish(const EngineParams *p, long long C, cudaStream_t st) {
+int launch_finish(const EngineParams &p, long long C, cudaStream_t st) {
     k_finish<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
-int launch_fused_steps(const EngineParams *p, long long C, long long n_steps, cudaStream_t st) {
+int launch_fused_steps(const EngineParams &p, long long C, long long n_steps, cudaStream_t st) {
     k_fused_steps<<<blocks_for(C, STEP_THREADS), STEP_THREADS, 0, st>>>(p, n_steps);
     return (int)cudaGetLastError();
 }
