@@ -221,10 +221,10 @@ def cuda_arm(args):
         warm_ms = float(t.item())
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) -----------------------------
-    # stages of bbb_engine_stage, full-SpMM step: 0 = k_propose + k_apply_edit, 1 = k_idx_commit_copy +
-    # k_raster2d_inc + k_raster2d_rescan, 2 = k_ray_spmm, 3 = k_finish  (7 kernel launches per step);
-    # chain-local step: 0 = k_propose + k_apply_edit, 2 = k_chain_step, 1 and 3 launch nothing (3 launches per step,
-    # plus the from-scratch re-evaluation of residuals and misfit every 256 steps: 5 launches)
+    # stages of bbb_engine_stage, full-SpMM step: 0 = k_propose, 1 = k_idx_commit_copy + k_raster2d_inc +
+    # k_raster2d_rescan, 2 = k_ray_spmm, 3 = k_finish  (6 kernel launches per step);
+    # chain-local step: 0 = k_propose, 2 = k_chain_step, 1 and 3 launch nothing (2 launches per step, plus the
+    # from-scratch re-evaluation of residuals and misfit every 256 steps: 5 launches)
     names = ["propose", "raster2d", "chain_step" if eng.chain_local else "ray_spmm", "finish"]
     stage_ms = np.zeros(4)
     active_fwd = 0
@@ -297,9 +297,9 @@ def cuda_arm(args):
         "wall_s_timed_region": wall,
         "clocks": {k: clk[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clk else None,
         "e2e": e2e,
-        "gpu_launches": (3 if eng.chain_local else 7) * args.steps + (2 * n_swaps if tempered else 0),
-        "step_kind": "chain-local (k_propose, k_apply_edit, k_chain_step)" if eng.chain_local
-        else "full SpMM (k_propose, k_apply_edit, k_idx_commit_copy, k_raster2d_inc, k_raster2d_rescan, k_ray_spmm, k_finish)",
+        "gpu_launches": (2 if eng.chain_local else 6) * args.steps + (2 * n_swaps if tempered else 0),
+        "step_kind": "chain-local (k_propose, k_chain_step)" if eng.chain_local
+        else "full SpMM (k_propose, k_idx_commit_copy, k_raster2d_inc, k_raster2d_rescan, k_ray_spmm, k_finish)",
         "kernel_ms": {n: float(v) for n, v in zip(names, stage_ms) if not (eng.chain_local and n in ("raster2d", "finish"))},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -324,54 +324,74 @@ def e2e_run(eng, steps, device, world, dist):
     import torch
 
     C = eng.C
+    K = eng.spec["spaces"][0]["kmax"]
 
     def image():
         k, sites, vals = eng.gather_space(0)
         return [k, sites, vals, eng.sigma[0][0].clone(), eng.temperature.clone(), eng.iteration.clone()]
 
-    dev_img = image()
-    host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in dev_img]
-    stage = [torch.empty_like(t) for t in dev_img]
-    for h, d in zip(host, dev_img):
+    resident = image()  # device copy of the states the resident caches belong to
+    host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in resident]
+    stage = [torch.empty_like(t) for t in resident]
+    for h, d in zip(host, resident):
         h.copy_(d)
     torch.cuda.synchronize(device)
-    nbytes = sum(h.numel() * h.element_size() for h in host)
     refreshed = [0]
+    moved = [0, 0]
+    rows = torch.arange(K, device=device)[:, None]
+    zero = torch.zeros((), dtype=torch.float64, device=device)
 
     def load():
-        for h, d in zip(host, stage):
-            d.copy_(h, non_blocking=True)
-        cur = image()
-        kmask = (torch.arange(stage[1].shape[1], device=device)[:, None] < stage[0][None, :])[None]  # cells in use
-        same = torch.equal(stage[0], cur[0]) and all(torch.equal(a, b) for a, b in zip(stage[3:], cur[3:]))
-        z = torch.zeros((), dtype=torch.float64, device=device)
-        same = same and all(torch.equal(torch.where(kmask, stage[i], z), torch.where(kmask, cur[i], z)) for i in (1, 2))
-        if not same:  # caller changed the chains: write them and re-derive the caches
+        # only the cells in use travel: rows [0, kb) of the padded [K][C] arrays, kb = largest k of the uploaded chains
+        kb = int(host[0].max())
+        stage[0].copy_(host[0], non_blocking=True)
+        for i in (1, 2):
+            for d in range(host[i].shape[0]):  # one contiguous [kb][C] block per plane
+                stage[i][d, :kb].copy_(host[i][d, :kb], non_blocking=True)
+        for i in (3, 4, 5):
+            stage[i].copy_(host[i], non_blocking=True)
+        moved[0] += host[0].numel() * 4 + (host[1].shape[0] + host[2].shape[0]) * kb * C * 8 + 3 * C * 8
+        used = (rows[:kb] < stage[0][None, :])[None]
+        same = (stage[0] == resident[0]).all()
+        for i in (1, 2):
+            same = same & (torch.where(used, stage[i][:, :kb], zero) == torch.where(used, resident[i][:, :kb], zero)).all()
+        for i in (3, 4, 5):
+            same = same & (stage[i] == resident[i]).all()
+        if not bool(same.item()):  # the caller changed the chains: write them and re-derive the caches
             refreshed[0] += 1
             eng.k[0].copy_(torch.stack((stage[0], stage[0])))
-            eng.sites[0][0].copy_(stage[1])
-            eng.values[0][0].copy_(stage[2])
+            eng.sites[0][0][:, :kb].copy_(stage[1][:, :kb])
+            eng.values[0][0][:, :kb].copy_(stage[2][:, :kb])
             eng.sigma[0].copy_(torch.stack((stage[3], stage[3])))
             eng.sel[0].zero_()
+            eng.temperature.copy_(stage[4])
+            eng.iteration.copy_(stage[5])
             eng.refresh()
-        eng.temperature.copy_(stage[4])
-        eng.iteration.copy_(stage[5])
+        return kb
 
-    def store():
-        for h, d in zip(host, image()):
-            h.copy_(d, non_blocking=True)
+    def store(kb):
+        kb = min(K, kb + 1)  # a step adds at most one cell
+        img = image()
+        for i in (0, 3, 4, 5):
+            host[i].copy_(img[i], non_blocking=True)
+        for i in (1, 2):
+            for d in range(host[i].shape[0]):
+                host[i][d, :kb].copy_(img[i][d, :kb], non_blocking=True)
+        moved[1] += host[0].numel() * 4 + (host[1].shape[0] + host[2].shape[0]) * kb * C * 8 + 3 * C * 8
+        resident[:] = img
 
     for _ in range(3):
-        load(); eng.step(1); store()
+        kb = load(); eng.step(1); store(kb)
     torch.cuda.synchronize(device)
+    moved[0] = moved[1] = 0
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        load()
+        kb = load()
         eng.step(1)
-        store()
+        store(kb)
         torch.cuda.synchronize(device)  # the host reads the step's result before the next call
     e1.record()
     torch.cuda.synchronize(device)
@@ -380,11 +400,11 @@ def e2e_run(eng, steps, device, world, dist):
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return {"value": world * C * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
-            "d2h_bytes_per_step": nbytes, "ms_per_step": ms / steps, "cache_refreshes": refreshed[0],
-            "what": "per call: pinned-host chain states (k, sites, values, sigma, temperature, iteration) -> device, "
-                    "compared on the device with the states the resident caches belong to, one iteration through "
-                    "bbb_engine_step, updated states -> host, host waits"}
+    return {"value": world * C * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": moved[0] // steps,
+            "d2h_bytes_per_step": moved[1] // steps, "ms_per_step": ms / steps, "cache_refreshes": refreshed[0],
+            "what": "per call: pinned-host chain states (k; sites and values of the cells in use; sigma, temperature, "
+                    "iteration) -> device, compared on the device with the states the resident caches belong to, one "
+                    "iteration through bbb_engine_step, updated states -> host, host waits"}
 
 
 # --------------------------------------------------------------------------- #
