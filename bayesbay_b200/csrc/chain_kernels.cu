@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     __shared__ int s_front, s_back, s_accept;
     __shared__ double s_red[CS_WARPS];
     __shared__ FinishIn s_fin;
+    __shared__ FinishPre s_pre;
+    constexpr int RW = CS_WARPS - 1;  // warps of the rasterisation pass; the last warp prepares the decision meanwhile
 
     const int move = B.move[c];
     const double lpr = B.log_prob_ratio[c];
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     unsigned *queue = list + G;
     const int n_levels = T.csc_n_levels;
     IdxVec<IdxT> wv_next;
-    wv_next.load(row + min(tid * CS_PTS, G - 1) / CS_PTS * CS_PTS);  // in flight while the tables load
+    if (warp < RW) wv_next.load(row + min(tid * CS_PTS, G - 1) / CS_PTS * CS_PTS);  // in flight while the tables load
 
     // ---- tables: proposed sites, cell function of the current (fo) and proposed (fn) state --------------------
     double fmax = 0.0;
@@ -208,9 +210,17 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     // List entries (back << 31 | level << 29 | group << 12 | cell): points captured by the inserted cell carry their
     // OLD owner; points that lost their owner (back = 1, after the re-derivation) their NEW owner, the old one being
     // the removed cell.
-    for (int g0 = tid * CS_PTS; g0 < G; g0 += CS_THREADS * CS_PTS) {
+    if (tid == CS_THREADS - 1) {
+        // everything of the decision that does not need the new misfit (logarithms, the generator, other targets):
+        // off the critical path, on the one warp without rasterisation work
+        Rng rng;
+        rng_resume(rng, ep, c, s_fin);
+        finish_pre(ep, c, s_fin, rng, t, s_pre);
+        rng_end(rng, ep, c);
+    }
+    for (int g0 = tid * CS_PTS; g0 < G && warp < RW; g0 += RW * 32 * CS_PTS) {
         const IdxVec<IdxT> wv = wv_next;
-        if (g0 + CS_THREADS * CS_PTS < G) wv_next.load(row + g0 + CS_THREADS * CS_PTS);
+        if (g0 + RW * 32 * CS_PTS < G) wv_next.load(row + g0 + RW * 32 * CS_PTS);
         unsigned chg = 0, scn = 0;
         if (inner == BBB_MOVE_VALUES) {
 #pragma unroll
@@ -427,14 +437,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     dphi = block_sum_to_thread0(dphi, s_red);
 
     // ---- likelihood ratio, decision, statistics (thread 0), then the commit by the whole block ----------------
-    if (tid == 0) {
-        Rng rng;
-        FinishPre pre;
-        rng_resume(rng, ep, c, s_fin);
-        finish_pre(ep, c, s_fin, rng, t, pre);
-        s_accept = finish_post(ep, c, s_fin, pre, t, finite ? s_fin.phi_old[t].s0 + dphi : NAN) ? 1 : 0;
-        rng_end(rng, ep, c);
-    }
+    if (tid == 0) s_accept = finish_post(ep, c, s_fin, s_pre, t, finite ? s_fin.phi_old[t].s0 + dphi : NAN) ? 1 : 0;
     __syncthreads();
     if (!s_accept) return;
 
