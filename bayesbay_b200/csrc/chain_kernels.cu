@@ -371,24 +371,35 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
                 const unsigned short *rows_a = la == 0 ? rw0 : (la == 1 ? rw1 : rw2), *rows_b = lb == 0 ? rw0 : (lb == 1 ? rw1 : rw2);
                 const double *data_a = la == 0 ? dt0 : (la == 1 ? dt1 : dt2), *data_b = lb == 0 ? dt0 : (lb == 1 ? dt1 : dt2);
                 const int len_max = max(qa.len, qb.len);
-                for (int j = lane; j < len_max; j += 128) {
+                for (int base_j = 0; base_j < len_max; base_j += 128) {
+                    // (all conditions on base_j are warp-uniform: sub-batches past a column's end are skipped, not
+                    // predicated off)
                     int ra[4], rb[4];
                     double wa[4], wb[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int jj = j + 32 * u;
-                        const bool oa = jj < qa.len, ob = jj < qb.len;
-                        ra[u] = oa ? (int)rows_a[qa.j0 + jj] : 0;
-                        wa[u] = oa ? data_a[qa.j0 + jj] : 0.0;
-                        rb[u] = ob ? (int)rows_b[qb.j0 + jj] : 0;
-                        wb[u] = ob ? data_b[qb.j0 + jj] : 0.0;
+                        const int jj = base_j + 32 * u + lane;
+                        ra[u] = rb[u] = 0;
+                        wa[u] = wb[u] = 0.0;
+                        if (base_j + 32 * u < qa.len && jj < qa.len) {
+                            ra[u] = (int)rows_a[qa.j0 + jj];
+                            wa[u] = data_a[qa.j0 + jj];
+                        }
+                        if (base_j + 32 * u < qb.len && jj < qb.len) {
+                            rb[u] = (int)rows_b[qb.j0 + jj];
+                            wb[u] = data_b[qb.j0 + jj];
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const long long va = __double2ll_rn(__dmul_rn(wa[u], qa.dlt) * scale);
-                        if (va != 0) fx_add(acc_lo, acc_hi, ra[u], va);
-                        const long long vb = __double2ll_rn(__dmul_rn(wb[u], qb.dlt) * scale);
-                        if (vb != 0) fx_add(acc_lo, acc_hi, rb[u], vb);
+                        if (base_j + 32 * u < qa.len) {
+                            const long long va = __double2ll_rn(__dmul_rn(wa[u], qa.dlt) * scale);
+                            if (va != 0) fx_add(acc_lo, acc_hi, ra[u], va);
+                        }
+                        if (base_j + 32 * u < qb.len) {
+                            const long long vb = __double2ll_rn(__dmul_rn(wb[u], qb.dlt) * scale);
+                            if (vb != 0) fx_add(acc_lo, acc_hi, rb[u], vb);
+                        }
                     }
                 }
             }
@@ -409,26 +420,49 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
         if (tile > 0) zero_acc();
         accumulate(tile);
         const int r0 = tile * RT, nr = min(RT, R - r0);
-        for (int rb = tid; rb < nr; rb += 4 * CS_THREADS) {
-            double rr[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int r = rb + u * CS_THREADS;
-                rr[u] = r < nr ? res[r0 + r] : 0.0;
+        const bool pairs = ((R | r0 | nr | RT) & 1) == 0;  // rays two at a time: 16-byte loads of the residual row
+        auto one_ray = [&](int r, double rr) {
+            const unsigned lo = acc_lo[r], hi = acc_hi[r];
+            if ((lo | hi) != 0) {
+                const double d = (double)(long long)(((unsigned long long)hi << 32) | lo) * inv_scale;
+                const double wr = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r0 + r] : 1.0;
+                dphi += wr * (d * (2.0 * rr + d));  // w (res + d)^2 - w res^2
+                double nv = rr + d;
+                if (nv == 0.0) nv = -0.0;  // all-zero planes mean "untouched"; -0.0 is the same residual
+                acc_lo[r] = (unsigned)__double2loint(nv);
+                acc_hi[r] = (unsigned)__double2hiint(nv);
             }
+        };
+        if (pairs) {
+            for (int rb = 2 * tid; rb < nr; rb += 8 * CS_THREADS) {
+                double2 rr[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int r = rb + u * CS_THREADS;
-                if (r >= nr) continue;
-                const unsigned lo = acc_lo[r], hi = acc_hi[r];
-                if ((lo | hi) != 0) {
-                    const double d = (double)(long long)(((unsigned long long)hi << 32) | lo) * inv_scale;
-                    const double wr = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r0 + r] : 1.0;
-                    dphi += wr * (d * (2.0 * rr[u] + d));  // w (res + d)^2 - w res^2
-                    double nv = rr[u] + d;
-                    if (nv == 0.0) nv = -0.0;  // all-zero planes mean "untouched"; -0.0 is the same residual
-                    acc_lo[r] = (unsigned)__double2loint(nv);
-                    acc_hi[r] = (unsigned)__double2hiint(nv);
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rb + 2 * u * CS_THREADS;
+                    rr[u] = r < nr ? *reinterpret_cast<const double2 *>(res + r0 + r) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rb + 2 * u * CS_THREADS;
+                    if (r >= nr) continue;
+                    const uint2 lo2 = *reinterpret_cast<const uint2 *>(acc_lo + r), hi2 = *reinterpret_cast<const uint2 *>(acc_hi + r);
+                    if ((lo2.x | lo2.y | hi2.x | hi2.y) == 0) continue;
+                    one_ray(r, rr[u].x);
+                    one_ray(r + 1, rr[u].y);
+                }
+            }
+        } else {
+            for (int rb = tid; rb < nr; rb += 4 * CS_THREADS) {
+                double rr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rb + u * CS_THREADS;
+                    rr[u] = r < nr ? res[r0 + r] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rb + u * CS_THREADS;
+                    if (r < nr) one_ray(r, rr[u]);
                 }
             }
         }
