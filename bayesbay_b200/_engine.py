@@ -468,6 +468,34 @@ class Engine:
                 out[c]["corr"].append(None if rr is None else float(rr[c]))
         return out
 
+    # ------------------------------------------------------------------ packed chain-state image
+    def _kb(self, kb):
+        n = len(self.spec["spaces"])
+        kb = [int(kb)] * n if np.isscalar(kb) else [int(v) for v in kb]
+        return (C.c_int32 * n)(*[min(max(v, 1), sp["kmax"]) for v, sp in zip(kb, self.spec["spaces"])])
+
+    def state_image_bytes(self, kb) -> int:
+        """Bytes of the packed image of all chains' current states when ``kb`` cell rows per space travel."""
+        return int(self.lib.bbb_engine_state_image_bytes(self._handle, self._kb(kb)))
+
+    def pack_states(self, kb, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Current state of every chain as ONE device buffer (int64 words; see include/bbb200.h)."""
+        n = self.state_image_bytes(kb) // 8
+        if out is None:
+            out = torch.empty((n,), dtype=torch.int64, device=self.device)
+        L.check(self.lib.bbb_engine_pack_states(self._handle, self._kb(kb), _ptr(out[:n]), self._stream))
+        return out[:n]
+
+    def states_differ(self, kb, image: torch.Tensor, flag: torch.Tensor) -> torch.Tensor:
+        """Sets ``flag`` (device int32, zeroed by the caller) if some chain's state is not bit-identical to ``image``."""
+        L.check(self.lib.bbb_engine_compare_states(self._handle, self._kb(kb), _ptr(image), _ptr(flag), self._stream))
+        return flag
+
+    def unpack_states(self, kb, image: torch.Tensor):
+        """Write a packed image into the engine and re-derive rasterisation, forward and misfit."""
+        L.check(self.lib.bbb_engine_unpack_states(self._handle, self._kb(kb), _ptr(image), self._stream))
+        self._steps_since_sync = self.K_BOUND_RESYNC
+
     # ------------------------------------------------------------------ checkpoint / resume
     def _mutable(self):
         named = {"temperature": self.temperature, "iteration": self.iteration, "n_proposed": self.n_proposed,

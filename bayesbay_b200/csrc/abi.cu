@@ -516,6 +516,42 @@ int bbb_engine_gather_space(bbb_engine *e, int space, int32_t *k_out, double *si
     return BBB_OK;
 }
 
+static int check_kb(bbb_engine *e, const int32_t *kb) {
+    if (!kb) return fail(BBB_ERR_INVALID, "kb is NULL");
+    for (int s = 0; s < e->host.spec.n_spaces; ++s)
+        if (kb[s] < 1 || kb[s] > e->host.spec.spaces[s].kmax) return fail(BBB_ERR_INVALID, "kb[%d] outside [1, kmax]", s);
+    return BBB_OK;
+}
+
+int64_t bbb_engine_state_image_bytes(bbb_engine *e, const int32_t *kb) {
+    if (!e || !e->bound || check_kb(e, kb) != BBB_OK) return -1;
+    return 8 * state_image_words(e->host, kb);
+}
+
+int bbb_engine_pack_states(bbb_engine *e, const int32_t *kb, void *image, void *stream) {
+    NEED_BOUND(e);
+    if (int rc = check_kb(e, kb)) return rc;
+    if (!image) return fail(BBB_ERR_INVALID, "image is NULL");
+    CU(launch_state_image(e->host, 0, kb, image, nullptr, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_engine_compare_states(bbb_engine *e, const int32_t *kb, const void *image, int32_t *differ, void *stream) {
+    NEED_BOUND(e);
+    if (int rc = check_kb(e, kb)) return rc;
+    if (!image || !differ) return fail(BBB_ERR_INVALID, "NULL argument");
+    CU(launch_state_image(e->host, 1, kb, const_cast<void *>(image), differ, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_engine_unpack_states(bbb_engine *e, const int32_t *kb, const void *image, void *stream) {
+    NEED_BOUND(e);
+    if (int rc = check_kb(e, kb)) return rc;
+    if (!image) return fail(BBB_ERR_INVALID, "image is NULL");
+    CU(launch_state_image(e->host, 2, kb, const_cast<void *>(image), nullptr, (cudaStream_t)stream));
+    return bbb_engine_refresh(e, stream);
+}
+
 int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream) {
     NEED_BOUND(e);
     if (target < 0 || target >= e->host.spec.n_targets || !dpred_out) return fail(BBB_ERR_INVALID, "target index / NULL output");

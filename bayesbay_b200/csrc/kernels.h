@@ -82,6 +82,9 @@ int launch_init_states(const EngineParams *dev_params, long long C, cudaStream_t
 int launch_refresh_finish(const EngineParams *dev_params, long long C, cudaStream_t stream);
 int launch_gather_space(const EngineParams *dev_params, long long C, int space, int kmax, int32_t *k_out,
                         double *sites_out, double *values_out, cudaStream_t stream);
+long long state_image_words(const EngineParams &host_params, const int32_t *kb);
+int launch_state_image(const EngineParams &host_params, int mode, const int32_t *kb, void *image, int32_t *differ,
+                       cudaStream_t stream);
 int launch_small_dpred(const EngineParams *dev_params, long long C, int target, double *dpred_out,
                        cudaStream_t stream);
 int launch_misfit_logdet(const EngineParams *dev_params, long long C, double *misfit_out,

@@ -151,6 +151,88 @@ __global__ void k_gather_space(const EngineParams *epp, int s, int32_t *k_out, d
         values_out[((long long)p * S.kmax + j) * B.n_chains + c] = value_ref(B, S, s, slot, p, j, c);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Chain-state image: the CURRENT state of every chain as one packed buffer of 8-byte words, so that a host <->
+// device exchange of the chains (what the reference's pool does with pickles on every advance_chain,
+// samplers/_samplers.py:225-237) is ONE copy each way.  Rows of C words:
+//   per space: k (int64), then sites [ndim][kb] and values [n_params][kb] (cells j >= k hold 0),
+//   per hierarchical target: sigma (and correlation), then temperature, iteration (int64).
+// MODE 0 packs the engine's state into the image, 1 compares (sets *differ when a chain's state is not bit-identical
+// to the image), 2 writes the image into slot 0 of the engine (the caller then re-derives the caches).
+// ------------------------------------------------------------------------------------------------
+struct ImageRows {
+    int kb[BBB_MAX_SPACES];
+    int first_row[BBB_MAX_SPACES + 1];  // first row of each space; [n_spaces] = first noise row
+    int n_rows;
+};
+
+template <int MODE>
+__global__ void k_state_image(const __grid_constant__ EngineParams ep, const __grid_constant__ ImageRows ir,
+                              unsigned long long *image, int32_t *differ) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int row = blockIdx.y;
+    unsigned long long *slot = image + (long long)row * C + c;
+    // where does this row live in the engine?
+    unsigned long long cur = 0;
+    unsigned long long *dst = nullptr, *dst2 = nullptr;  // MODE 2 targets
+    bool live = true;                                    // false: padding cell (j >= k), not compared
+    if (row < ir.first_row[P.n_spaces]) {
+        int s = 0;
+        while (row >= ir.first_row[s + 1]) ++s;
+        const bbb_space_spec &S = P.spaces[s];
+        const int rel = row - ir.first_row[s];
+        const int sl = (MODE == 2) ? 0 : (int)B.sel[s][c];
+        if (rel == 0) {
+            cur = (unsigned long long)(long long)k_ref(B, s, sl, c);
+            if (MODE == 2) {
+                const int kv = (int)(long long)*slot;
+                k_ref(B, s, 0, c) = kv;
+                k_ref(B, s, 1, c) = kv;
+                B.sel[s][c] = 0;
+                return;
+            }
+        } else {
+            const int q = (rel - 1) / ir.kb[s], j = (rel - 1) % ir.kb[s];
+            const int kc = (MODE == 2) ? (int)(long long)image[(long long)ir.first_row[s] * C + c] : k_ref(B, s, sl, c);
+            live = j < kc;
+            double *p = q < S.ndim ? &site_ref(B, S, s, sl, q, j, c) : &value_ref(B, S, s, sl, q - S.ndim, j, c);
+            cur = live ? (unsigned long long)__double_as_longlong(*p) : 0ull;
+            dst = reinterpret_cast<unsigned long long *>(p);
+        }
+    } else {
+        int rel = row - ir.first_row[P.n_spaces];
+        bool found = false;
+        for (int t = 0; t < P.n_targets && !found; ++t) {
+            const bbb_target_spec &T = P.targets[t];
+            if (T.cov_kind != BBB_COV_HIERARCHICAL) continue;
+            const int n = T.correlated ? 2 : 1;
+            if (rel < n) {
+                double *p = rel == 0 ? B.sigma[t] : B.corr[t];
+                dst = reinterpret_cast<unsigned long long *>(p + c);
+                dst2 = reinterpret_cast<unsigned long long *>(p + C + c);
+                found = true;
+            } else {
+                rel -= n;
+            }
+        }
+        if (!found) dst = rel == 0 ? reinterpret_cast<unsigned long long *>(B.temperature + c)
+                                   : reinterpret_cast<unsigned long long *>(B.iteration + c);
+        cur = *dst;
+    }
+    if (MODE == 0) {
+        *slot = cur;
+    } else if (MODE == 1) {
+        if (live && *slot != cur) *differ = 1;
+    } else if (live) {
+        *dst = *slot;
+        if (dst2 != nullptr) *dst2 = *slot;
+    }
+}
+
 __global__ void __launch_bounds__(STEP_THREADS) k_small_dpred(const EngineParams *epp, int t, double *dpred_out) {
     const EngineParams &ep = *epp;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -345,6 +427,32 @@ int launch_gather_space(const EngineParams *p, long long C, int space, int kmax,
                           double *sites_out, double *values_out, cudaStream_t st) {
     dim3 grid(blocks_for(C, 128), kmax);
     k_gather_space<<<grid, 128, 0, st>>>(p, space, k_out, sites_out, values_out);
+    return (int)cudaGetLastError();
+}
+static ImageRows image_rows(const EngineParams &p, const int32_t *kb) {
+    ImageRows ir;
+    int row = 0;
+    for (int s = 0; s < p.spec.n_spaces; ++s) {
+        const bbb_space_spec &S = p.spec.spaces[s];
+        ir.kb[s] = kb[s];
+        ir.first_row[s] = row;
+        row += 1 + (S.ndim + S.n_params) * kb[s];
+    }
+    ir.first_row[p.spec.n_spaces] = row;
+    for (int t = 0; t < p.spec.n_targets; ++t)
+        if (p.spec.targets[t].cov_kind == BBB_COV_HIERARCHICAL) row += p.spec.targets[t].correlated ? 2 : 1;
+    ir.n_rows = row + 2;  // temperature, iteration
+    return ir;
+}
+long long state_image_words(const EngineParams &p, const int32_t *kb) { return (long long)image_rows(p, kb).n_rows * p.buf.n_chains; }
+int launch_state_image(const EngineParams &p, int mode, const int32_t *kb, void *image, int32_t *differ, cudaStream_t st) {
+    const ImageRows ir = image_rows(p, kb);
+    if (ir.n_rows > 65535) return (int)cudaErrorInvalidConfiguration;
+    dim3 grid(blocks_for(p.buf.n_chains, 128), ir.n_rows);
+    unsigned long long *img = reinterpret_cast<unsigned long long *>(image);
+    if (mode == 0) k_state_image<0><<<grid, 128, 0, st>>>(p, ir, img, differ);
+    else if (mode == 1) k_state_image<1><<<grid, 128, 0, st>>>(p, ir, img, differ);
+    else k_state_image<2><<<grid, 128, 0, st>>>(p, ir, img, differ);
     return (int)cudaGetLastError();
 }
 int launch_small_dpred(const EngineParams *p, long long C, int target, double *dpred_out, cudaStream_t st) {

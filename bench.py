@@ -325,74 +325,56 @@ def e2e_run(eng, steps, device, world, dist):
 
     C = eng.C
     K = eng.spec["spaces"][0]["kmax"]
-
-    def image():
-        k, sites, vals = eng.gather_space(0)
-        return [k, sites, vals, eng.sigma[0][0].clone(), eng.temperature.clone(), eng.iteration.clone()]
-
-    resident = image()  # device copy of the states the resident caches belong to
-    host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in resident]
-    stage = [torch.empty_like(t) for t in resident]
-    for h, d in zip(host, resident):
-        h.copy_(d)
-    torch.cuda.synchronize(device)
+    cap = eng.state_image_bytes(K) // 8
+    host = torch.empty((cap,), dtype=torch.int64, pin_memory=True)    # the caller's chains (packed image)
+    stage = torch.empty((cap,), dtype=torch.int64, device=device)     # upload buffer
+    out = torch.empty((cap,), dtype=torch.int64, device=device)       # download buffer
+    flag = torch.zeros((1,), dtype=torch.int32, device=device)
+    flag_host = torch.zeros((1,), dtype=torch.int32, pin_memory=True)
     refreshed = [0]
     moved = [0, 0]
-    rows = torch.arange(K, device=device)[:, None]
-    zero = torch.zeros((), dtype=torch.float64, device=device)
 
-    def load():
-        # only the cells in use travel: rows [0, kb) of the padded [K][C] arrays, kb = largest k of the uploaded chains
-        kb = int(host[0].max())
-        stage[0].copy_(host[0], non_blocking=True)
-        for i in (1, 2):
-            for d in range(host[i].shape[0]):  # one contiguous [kb][C] block per plane
-                stage[i][d, :kb].copy_(host[i][d, :kb], non_blocking=True)
-        for i in (3, 4, 5):
-            stage[i].copy_(host[i], non_blocking=True)
-        moved[0] += host[0].numel() * 4 + (host[1].shape[0] + host[2].shape[0]) * kb * C * 8 + 3 * C * 8
-        used = (rows[:kb] < stage[0][None, :])[None]
-        same = (stage[0] == resident[0]).all()
-        for i in (1, 2):
-            same = same & (torch.where(used, stage[i][:, :kb], zero) == torch.where(used, resident[i][:, :kb], zero)).all()
-        for i in (3, 4, 5):
-            same = same & (stage[i] == resident[i]).all()
-        if not bool(same.item()):  # the caller changed the chains: write them and re-derive the caches
+    kb0 = min(K, int(eng.gather_space(0)[0].max().item()) + 1)
+    n0 = eng.state_image_bytes(kb0) // 8
+    host[:n0].copy_(eng.pack_states(kb0, out))
+    torch.cuda.synchronize(device)
+
+    def load(kb):
+        # only the cells in use travel (kb rows of the padded [K][C] arrays): ONE copy of the packed image
+        n = eng.state_image_bytes(kb) // 8
+        stage[:n].copy_(host[:n], non_blocking=True)
+        moved[0] += 8 * n
+        flag.zero_()
+        eng.states_differ(kb, stage, flag)
+        flag_host.copy_(flag, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        if int(flag_host[0]) != 0:  # the caller changed the chains: write them and re-derive the caches
             refreshed[0] += 1
-            eng.k[0].copy_(torch.stack((stage[0], stage[0])))
-            eng.sites[0][0][:, :kb].copy_(stage[1][:, :kb])
-            eng.values[0][0][:, :kb].copy_(stage[2][:, :kb])
-            eng.sigma[0].copy_(torch.stack((stage[3], stage[3])))
-            eng.sel[0].zero_()
-            eng.temperature.copy_(stage[4])
-            eng.iteration.copy_(stage[5])
-            eng.refresh()
-        return kb
+            eng.unpack_states(kb, stage)
 
     def store(kb):
-        kb = min(K, kb + 1)  # a step adds at most one cell
-        img = image()
-        for i in (0, 3, 4, 5):
-            host[i].copy_(img[i], non_blocking=True)
-        for i in (1, 2):
-            for d in range(host[i].shape[0]):
-                host[i][d, :kb].copy_(img[i][d, :kb], non_blocking=True)
-        moved[1] += host[0].numel() * 4 + (host[1].shape[0] + host[2].shape[0]) * kb * C * 8 + 3 * C * 8
-        resident[:] = img
+        n = eng.state_image_bytes(kb) // 8
+        host[:n].copy_(eng.pack_states(kb, out), non_blocking=True)
+        moved[1] += 8 * n
 
+    def call(kb_up):
+        load(kb_up)  # the image in `host` has kb_up cell rows
+        eng.step(1)
+        kb_down = min(K, int(host[:C].max()) + 1)  # largest k before the step (row 0 of the image) + the one a step can add
+        store(kb_down)
+        torch.cuda.synchronize(device)  # the host reads the step's result before the next call
+        return kb_down  # layout of the image now in `host`
+
+    kb = kb0
     for _ in range(3):
-        kb = load(); eng.step(1); store(kb)
-    torch.cuda.synchronize(device)
+        kb = call(kb)
     moved[0] = moved[1] = 0
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        kb = load()
-        eng.step(1)
-        store(kb)
-        torch.cuda.synchronize(device)  # the host reads the step's result before the next call
+        kb = call(kb)
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1)
@@ -402,9 +384,10 @@ def e2e_run(eng, steps, device, world, dist):
         ms = float(t.item())
     return {"value": world * C * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": moved[0] // steps,
             "d2h_bytes_per_step": moved[1] // steps, "ms_per_step": ms / steps, "cache_refreshes": refreshed[0],
-            "what": "per call: pinned-host chain states (k; sites and values of the cells in use; sigma, temperature, "
-                    "iteration) -> device, compared on the device with the states the resident caches belong to, one "
-                    "iteration through bbb_engine_step, updated states -> host, host waits"}
+            "what": "per call: packed image of the chains' states in pinned host memory (k; sites and values of the cells "
+                    "in use; sigma, temperature, iteration) -> device in one copy, compared on the device with the "
+                    "resident states the caches belong to (bbb_engine_compare_states), one iteration through "
+                    "bbb_engine_step, bbb_engine_pack_states, one copy -> host, host waits"}
 
 
 # --------------------------------------------------------------------------- #

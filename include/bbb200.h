@@ -243,6 +243,19 @@ int bbb_engine_set_annealing(bbb_engine *e, double temperature_start, double coo
  * src/bayesbay/_markov_chain.py:115-134): k [C] int32, sites [ndim][K][C], values [P][K][C]. */
 int bbb_engine_gather_space(bbb_engine *e, int space, int32_t *k_out, double *sites_out,
                             double *values_out, void *stream);
+/* Chain-state image: the CURRENT state of every chain packed into ONE buffer of 8-byte words, so that moving the
+ * chains between host and device -- what the reference's pool does with pickles on every advance_chain
+ * (samplers/_samplers.py:225-237) -- is one copy each way.  Rows of C words each: per space k (int64), sites
+ * [ndim][kb[s]] and values [n_params][kb[s]] (cells j >= k are 0; kb[s] <= kmax is the number of cell rows that
+ * travel, at least the largest k); per hierarchical target sigma (and correlation); temperature; iteration (int64).
+ *   pack     engine -> image (device buffer of bbb_engine_state_image_bytes());
+ *   compare  sets *differ (device int32, caller zeroes it) when some chain's state is not bit-identical to the image:
+ *            a caller that kept the chains resident uses it to learn whether its derived caches are still valid;
+ *   unpack   image -> engine (slot 0), then re-derives rasterisation, forward and misfit (bbb_engine_refresh). */
+int64_t bbb_engine_state_image_bytes(bbb_engine *e, const int32_t *kb);
+int bbb_engine_pack_states(bbb_engine *e, const int32_t *kb, void *image, void *stream);
+int bbb_engine_compare_states(bbb_engine *e, const int32_t *kb, const void *image, int32_t *differ, void *stream);
+int bbb_engine_unpack_states(bbb_engine *e, const int32_t *kb, const void *image, void *stream);
 /* d_pred of the CURRENT states of one target, [n_data][C] (the "{target}.dpred" cache entry,
  * likelihood/_log_likelihood.py:311-320). */
 int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream);

@@ -396,3 +396,44 @@ def test_chain_local_step_is_bit_reproducible_and_shard_independent():
     assert torch.equal(torch.cat((lo[2], hi[2]), dim=2), a[2])
     assert torch.equal(torch.cat((lo[3], hi[3])), a[3])
     assert torch.equal(torch.cat((lo[4], hi[4])), a[4])
+
+
+@pytest.mark.parametrize("name", ["tomo_small", "partition_1d_corr", "polyfit"])
+def test_packed_state_image_round_trip(name):
+    """bbb_engine_pack/compare/unpack_states: the packed image is bit-identical to the chains' current states,
+    detects any change, and restoring it reproduces states and misfit exactly."""
+    spec = problems.spec_from_ingredients(problems.ALL[name]())
+    n = 37
+    eng = _engine(spec, n, seed=3)
+    eng.init_states()
+    eng.step(30)
+    kmax = spec["spaces"][0]["kmax"]
+    kb = min(kmax, int(eng.gather_space(0)[0].max().item()) + 1)
+    img = eng.pack_states(kb).clone()
+    assert img.numel() * 8 == eng.state_image_bytes(kb)
+    before = eng.fetch_states()
+    m0, l0 = eng.misfit_logdet()
+    flag = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    assert int(eng.states_differ(kb, img, flag).item()) == 0
+    # k row of the image = current k; padding cells are zero
+    k = eng.gather_space(0)[0]
+    assert torch.equal(img[:n], k.long())
+    eng.step(7)
+    flag.zero_()
+    assert int(eng.states_differ(kb, img, flag).item()) == 1
+    eng.unpack_states(kb, img)
+    flag.zero_()
+    assert int(eng.states_differ(kb, img, flag).item()) == 0
+    after = eng.fetch_states()
+    for a, b in zip(before, after):
+        assert a["spaces"][0]["k"] == b["spaces"][0]["k"]
+        if a["spaces"][0]["sites"] is not None:
+            assert np.array_equal(a["spaces"][0]["sites"], b["spaces"][0]["sites"])
+        for va, vb in zip(a["spaces"][0]["values"], b["spaces"][0]["values"]):
+            assert np.array_equal(va, vb)
+        assert a["sigma"] == b["sigma"] and a["corr"] == b["corr"]
+    m1, l1 = eng.misfit_logdet()
+    np.testing.assert_allclose(m1.cpu().numpy(), m0.cpu().numpy(), rtol=1e-12)
+    assert torch.equal(l0, l1)
+    eng.step(5)  # and the chains go on
+    assert (eng.iteration.cpu().numpy() == 35).all()
