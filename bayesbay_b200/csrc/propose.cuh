@@ -271,20 +271,24 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         // lanes = output cells
         const int ndim = S.ndim, n_params = S.n_params;
         const long long C = B.n_chains, KC = (long long)S.kmax * C;
-        double *sites = B.sites[s], *vals = B.values[s];
+        // the two slots never overlap: __restrict__ lets the loads of a cell (and of the next cells) go out together
+        const double *__restrict__ s_cur = B.sites[s] + (long long)cur * ndim * KC + c;
+        double *__restrict__ s_new = B.sites[s] + (long long)prop * ndim * KC + c;
+        const double *__restrict__ v_cur = B.values[s] + (long long)cur * n_params * KC + c;
+        double *__restrict__ v_new = B.values[s] + (long long)prop * n_params * KC + c;
         if (e.rm >= 0 || e.ins >= 0) {
             for (int jo = threadIdx.x & 31; jo < k_new; jo += 32) {
+                const int jp = jo - ((e.ins >= 0 && jo > e.ins) ? 1 : 0);
+                const int src = (jo == e.ins) ? 0 : jp + ((e.rm >= 0 && jp >= e.rm) ? 1 : 0);
+                double tmp[2 + BBB_MAX_PARAMS];
+                for (int d = 0; d < ndim; ++d) tmp[d] = s_cur[d * KC + (long long)src * C];
+                for (int p = 0; p < n_params; ++p) tmp[2 + p] = v_cur[p * KC + (long long)src * C];
                 if (jo == e.ins) {
-                    for (int d = 0; d < ndim; ++d) sites[((long long)prop * ndim + d) * KC + (long long)jo * C + c] = e.site[d];
-                    for (int p = 0; p < n_params; ++p) vals[((long long)prop * n_params + p) * KC + (long long)jo * C + c] = e.vals[p];
-                } else {
-                    const int jp = jo - ((e.ins >= 0 && jo > e.ins) ? 1 : 0);
-                    const int src = jp + ((e.rm >= 0 && jp >= e.rm) ? 1 : 0);
-                    for (int d = 0; d < ndim; ++d)
-                        sites[((long long)prop * ndim + d) * KC + (long long)jo * C + c] = sites[((long long)cur * ndim + d) * KC + (long long)src * C + c];
-                    for (int p = 0; p < n_params; ++p)
-                        vals[((long long)prop * n_params + p) * KC + (long long)jo * C + c] = vals[((long long)cur * n_params + p) * KC + (long long)src * C + c];
+                    for (int d = 0; d < ndim; ++d) tmp[d] = e.site[d];
+                    for (int p = 0; p < n_params; ++p) tmp[2 + p] = e.vals[p];
                 }
+                for (int d = 0; d < ndim; ++d) s_new[d * KC + (long long)jo * C] = tmp[d];
+                for (int p = 0; p < n_params; ++p) v_new[p * KC + (long long)jo * C] = tmp[2 + p];
             }
         }
     } else if (e.write && apply_now) {
