@@ -40,6 +40,12 @@ struct bbb_engine {
     bool full_forward; // BBB_FULL_FORWARD=1: never use the chain-local step (full SpMM every proposal, reference behaviour)
     int ray_t;         // chain-local engines: the one ray target
     long long resync_every, steps_since_resync;
+    // chain-local engines, multi-iteration calls: the chains are split into two halves that run on two internal
+    // streams, so that one half's proposal kernel (a latency-bound kernel of one warp per chain) and the tail of its
+    // chain kernel overlap the other half's chain kernel (BBB_PIPELINE=0 disables)
+    bool pipeline;
+    cudaStream_t half_stream[2];
+    cudaEvent_t ev_fork, ev_join[2];
 };
 
 extern "C" {
@@ -160,6 +166,11 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
     e->ray_t = -1;
     e->resync_every = 256;
     e->steps_since_resync = 0;
+    {
+        const char *pl = getenv("BBB_PIPELINE");
+        e->pipeline = !(pl != nullptr && pl[0] == '0');
+    }
+    e->half_stream[0] = e->half_stream[1] = nullptr;
     for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
     for (int s = 0; s < BBB_MAX_SPACES; ++s) e->k_bound[s] = s < spec->n_spaces ? spec->spaces[s].kmax : 0;
     e->n_sm = 148;
@@ -231,6 +242,13 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
 void bbb_engine_destroy(bbb_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->half_stream[0] != nullptr) {
+        for (int h = 0; h < 2; ++h) {
+            cudaStreamDestroy(e->half_stream[h]);
+            cudaEventDestroy(e->ev_join[h]);
+        }
+        cudaEventDestroy(e->ev_fork);
+    }
     cudaFree(e->dev);
     delete e;
 }
@@ -282,7 +300,7 @@ static int run_propose(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const long long C = e->host.buf.n_chains;
     (void)P;
-    return launch_propose(e->host, C, st);  // the proposal warps also write the proposed slots
+    return launch_propose(e->host, 0, C, st);  // the proposal warps also write the proposed slots
 }
 
 static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool write_partial, cudaStream_t st) {
@@ -402,14 +420,58 @@ int bbb_engine_resync(bbb_engine *e, void *stream) {
     return BBB_OK;
 }
 
+// a step adds at most one cell: keep the host-side upper bound of k valid (BEFORE anything sized by it runs)
+static void bump_k_bound(bbb_engine *e, long long n) {
+    const bbb_problem_spec &P = e->host.spec;
+    for (int s = 0; s < P.n_spaces; ++s) {
+        const long long b = (long long)e->k_bound[s] + n;
+        e->k_bound[s] = b < P.spaces[s].kmax ? (int)b : P.spaces[s].kmax;
+    }
+}
+
 static int run_chain_step(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
-    int rc = launch_chain_step(e->host, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
+    int rc = launch_chain_step(e->host, 0, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
                                idx_bytes_of(P, e->ray_t), st);
     if (rc != 0) return rc;
+    bump_k_bound(e, 1);
     ++e->steps_since_resync;
     if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) rc = chain_local_from_scratch(e, false, st);
+    return rc;
+}
+
+// n chain-local iterations of all chains, the two halves of the chains on the engine's two internal streams
+// (chains never interact inside a step, so the halves need no ordering between them); joined back into `st`.
+static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st) {
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_target_spec &T = P.targets[e->ray_t];
+    const long long C = e->host.buf.n_chains;
+    const long long mid = (C / 2 + 3) & ~3LL;  // whole proposal blocks
+    if (e->half_stream[0] == nullptr) {
+        for (int h = 0; h < 2; ++h) {
+            int rc = (int)cudaStreamCreateWithFlags(&e->half_stream[h], cudaStreamNonBlocking);
+            if (rc == 0) rc = (int)cudaEventCreateWithFlags(&e->ev_join[h], cudaEventDisableTiming);
+            if (rc != 0) return rc;
+        }
+        int rc = (int)cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+        if (rc != 0) return rc;
+    }
+    int rc = (int)cudaEventRecord(e->ev_fork, st);
+    for (int h = 0; h < 2 && rc == 0; ++h) rc = (int)cudaStreamWaitEvent(e->half_stream[h], e->ev_fork, 0);
+    for (long long it = 0; it < n && rc == 0; ++it) {
+        for (int h = 0; h < 2 && rc == 0; ++h) {
+            const long long c0 = h == 0 ? 0 : mid, c1 = h == 0 ? mid : C;
+            rc = launch_propose(e->host, c0, c1, e->half_stream[h]);
+            if (rc == 0)
+                rc = launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
+                                       idx_bytes_of(P, e->ray_t), e->half_stream[h]);
+        }
+    }
+    for (int h = 0; h < 2 && rc == 0; ++h) {
+        rc = (int)cudaEventRecord(e->ev_join[h], e->half_stream[h]);
+        if (rc == 0) rc = (int)cudaStreamWaitEvent(st, e->ev_join[h], 0);
+    }
     return rc;
 }
 
@@ -443,6 +505,21 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
         if (n_steps > 0) CU(launch_fused_steps(e->host, C, n_steps, st));
         return BBB_OK;
     }
+    if (e->host.chain_local && e->pipeline && n_steps > 1 && C >= 2LL * e->n_sm) {
+        // segments between two from-scratch re-evaluations run pipelined
+        int64_t left = n_steps;
+        while (left > 0) {
+            int64_t seg = left;
+            if (e->resync_every > 0 && e->resync_every - e->steps_since_resync < seg) seg = e->resync_every - e->steps_since_resync;
+            if (seg < 1) seg = 1;
+            CU(run_chain_steps_pipelined(e, seg, st));
+            bump_k_bound(e, seg);
+            e->steps_since_resync += seg;
+            if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) CU(chain_local_from_scratch(e, false, st));
+            left -= seg;
+        }
+        return BBB_OK;
+    }
     for (int64_t it = 0; it < n_steps; ++it) {
         CU(run_propose(e, st));
         if (e->host.chain_local) {
@@ -454,9 +531,8 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
                 CU(run_spmm(e, t, true, nullptr, true, st));
             }
             CU(launch_finish(e->host, C, st));
+            bump_k_bound(e, 1);
         }
-        for (int s = 0; s < P.n_spaces; ++s)
-            if (e->k_bound[s] < P.spaces[s].kmax) ++e->k_bound[s];  // a step adds at most one cell
     }
     return BBB_OK;
 }
@@ -483,9 +559,10 @@ int bbb_engine_stage(bbb_engine *e, int stage, void *stream) {
                 if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) CU(run_spmm(e, t, true, nullptr, true, st));
             break;
         case 3:
-            if (!e->host.chain_local) CU(launch_finish(e->host, C, st));
-            for (int s = 0; s < P.n_spaces; ++s)
-                if (e->k_bound[s] < P.spaces[s].kmax) ++e->k_bound[s];
+            if (!e->host.chain_local) {
+                CU(launch_finish(e->host, C, st));
+                bump_k_bound(e, 1);
+            }
             break;
         default: return fail(BBB_ERR_INVALID, "stage must be 0..3");
     }

@@ -111,14 +111,14 @@ __device__ __forceinline__ void fx_add(unsigned *lo, unsigned *hi, int r, long l
 }
 
 template <typename IdxT>
-__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t) {
+__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const bbb_target_spec &T = P.targets[t];
     const int s = T.space;
     const bbb_space_spec &S = P.spaces[s];
     const long long C = B.n_chains;
-    const long long c = blockIdx.x;
+    const long long c = c_first + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     __shared__ int s_front, s_back, s_accept;
@@ -519,17 +519,19 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     }
 }
 
-int launch_chain_step(const EngineParams &dev, long long C, int t, int tile_rays, int K, int idx_bytes, cudaStream_t st) {
+int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, int K, int idx_bytes,
+                      cudaStream_t st) {
+    const long long C = c_end - c_first;
     const size_t smem = chain_step_smem(tile_rays, K);
     cudaError_t err;
     if (idx_bytes == 1) {
         err = cudaFuncSetAttribute(k_chain_step<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        k_chain_step<uint8_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t);
+        k_chain_step<uint8_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t, c_first);
     } else {
         err = cudaFuncSetAttribute(k_chain_step<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        k_chain_step<uint16_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t);
+        k_chain_step<uint16_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t, c_first);
     }
     return (int)cudaGetLastError();
 }

@@ -12,9 +12,9 @@ constexpr int STEP_THREADS = 64;  // 2 warps per block: spreads C = 1024 chains 
 // One WARP per chain: lane 0 owns the generator (every draw is broadcast), the O(k) nearest-site searches of
 // birth/death-from-neighbour run with lanes = sites, and the lanes write the proposed slot (lanes = cells).
 constexpr int PROPOSE_WARPS = 4;
-__global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep) {
-    const long long c = (long long)blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
-    if (c >= ep.buf.n_chains) return;
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep, long long c_first, long long c_end) {
+    const long long c = c_first + (long long)blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
+    if (c >= c_end) return;
     Rng rng;
     rng_begin(rng, ep, c, STREAM_STEP, false);
     rng.coop = true;
@@ -399,8 +399,8 @@ __global__ void k_phi_from_partial(const double *partial, int n_tiles, long long
 // ------------------------------------------------------------------------------------------------
 static inline int blocks_for(long long C, int threads) { return (int)((C + threads - 1) / threads); }
 
-int launch_propose(const EngineParams &p, long long C, cudaStream_t st) {
-    k_propose<<<blocks_for(C, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p);
+int launch_propose(const EngineParams &p, long long c_first, long long c_end, cudaStream_t st) {
+    k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end);
     return (int)cudaGetLastError();
 }
 int launch_corr_sums(const EngineParams *p, long long C, int target, int proposal, cudaStream_t st) {
