@@ -40,12 +40,12 @@ struct bbb_engine {
     bool full_forward; // BBB_FULL_FORWARD=1: never use the chain-local step (full SpMM every proposal, reference behaviour)
     int ray_t;         // chain-local engines: the one ray target
     long long resync_every, steps_since_resync;
-    // chain-local engines, multi-iteration calls: the chains are split into two halves that run on two internal
-    // streams, so that one half's proposal kernel (a latency-bound kernel of one warp per chain) and the tail of its
-    // chain kernel overlap the other half's chain kernel (BBB_PIPELINE=0 disables)
-    bool pipeline;
-    cudaStream_t half_stream[2];
-    cudaEvent_t ev_fork, ev_join[2];
+    // chain-local engines, multi-iteration calls: the chains are split into parts (default 4, BBB_PIPELINE=n, 1 = off)
+    // that run on internal streams, so that one part's proposal kernel (a latency-bound kernel of one warp per chain)
+    // and the tail of its chain kernel overlap the other parts' chain kernels
+    int pipeline;  // number of parts (1 = off)
+    cudaStream_t half_stream[4];
+    cudaEvent_t ev_fork, ev_join[4];
 };
 
 extern "C" {
@@ -168,9 +168,11 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
     e->steps_since_resync = 0;
     {
         const char *pl = getenv("BBB_PIPELINE");
-        e->pipeline = !(pl != nullptr && pl[0] == '0');
+        e->pipeline = pl != nullptr ? atoi(pl) : 4;
+        if (e->pipeline < 1) e->pipeline = 1;
+        if (e->pipeline > 4) e->pipeline = 4;
     }
-    e->half_stream[0] = e->half_stream[1] = nullptr;
+    for (int h = 0; h < 4; ++h) e->half_stream[h] = nullptr;
     for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
     for (int s = 0; s < BBB_MAX_SPACES; ++s) e->k_bound[s] = s < spec->n_spaces ? spec->spaces[s].kmax : 0;
     e->n_sm = 148;
@@ -243,7 +245,7 @@ void bbb_engine_destroy(bbb_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->half_stream[0] != nullptr) {
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < e->pipeline; ++h) {
             cudaStreamDestroy(e->half_stream[h]);
             cudaEventDestroy(e->ev_join[h]);
         }
@@ -441,15 +443,16 @@ static int run_chain_step(bbb_engine *e, cudaStream_t st) {
     return rc;
 }
 
-// n chain-local iterations of all chains, the two halves of the chains on the engine's two internal streams
-// (chains never interact inside a step, so the halves need no ordering between them); joined back into `st`.
+// n chain-local iterations of all chains, the parts of the chain set on the engine's internal streams (chains never
+// interact inside a step, so the parts need no ordering between them); joined back into `st`.
 static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
     const long long C = e->host.buf.n_chains;
-    const long long mid = (C / 2 + 3) & ~3LL;  // whole proposal blocks
+    const int NP = e->pipeline;
+    const long long part = ((C + NP - 1) / NP + 3) & ~3LL;  // whole proposal blocks
     if (e->half_stream[0] == nullptr) {
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NP; ++h) {
             int rc = (int)cudaStreamCreateWithFlags(&e->half_stream[h], cudaStreamNonBlocking);
             if (rc == 0) rc = (int)cudaEventCreateWithFlags(&e->ev_join[h], cudaEventDisableTiming);
             if (rc != 0) return rc;
@@ -458,17 +461,18 @@ static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st
         if (rc != 0) return rc;
     }
     int rc = (int)cudaEventRecord(e->ev_fork, st);
-    for (int h = 0; h < 2 && rc == 0; ++h) rc = (int)cudaStreamWaitEvent(e->half_stream[h], e->ev_fork, 0);
+    for (int h = 0; h < NP && rc == 0; ++h) rc = (int)cudaStreamWaitEvent(e->half_stream[h], e->ev_fork, 0);
     for (long long it = 0; it < n && rc == 0; ++it) {
-        for (int h = 0; h < 2 && rc == 0; ++h) {
-            const long long c0 = h == 0 ? 0 : mid, c1 = h == 0 ? mid : C;
+        for (int h = 0; h < NP && rc == 0; ++h) {
+            const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
+            if (c0 >= c1) continue;
             rc = launch_propose(e->host, c0, c1, e->half_stream[h]);
             if (rc == 0)
                 rc = launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
                                        idx_bytes_of(P, e->ray_t), e->half_stream[h]);
         }
     }
-    for (int h = 0; h < 2 && rc == 0; ++h) {
+    for (int h = 0; h < NP && rc == 0; ++h) {
         rc = (int)cudaEventRecord(e->ev_join[h], e->half_stream[h]);
         if (rc == 0) rc = (int)cudaStreamWaitEvent(st, e->ev_join[h], 0);
     }
@@ -505,7 +509,7 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
         if (n_steps > 0) CU(launch_fused_steps(e->host, C, n_steps, st));
         return BBB_OK;
     }
-    if (e->host.chain_local && e->pipeline && n_steps > 1 && C >= 2LL * e->n_sm) {
+    if (e->host.chain_local && e->pipeline > 1 && n_steps > 1 && C >= 2LL * e->n_sm) {
         // segments between two from-scratch re-evaluations run pipelined
         int64_t left = n_steps;
         while (left > 0) {
