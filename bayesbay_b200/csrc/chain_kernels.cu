@@ -228,21 +228,33 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
                 if (g0 + q < G && wv.at(q) == rm) chg |= 1u << q;
         } else {
 #pragma unroll
-            for (int q = 0; q < CS_PTS; ++q) {
-                const int g = g0 + q;
-                if (g >= G) continue;
-                const int o = wv.at(q);
-                if (rm >= 0 && o == rm) {
-                    scn |= 1u << q;
-                } else if (ins >= 0) {
-                    int mm = o - ((rm >= 0 && o > rm) ? 1 : 0);
-                    mm += (mm >= ins) ? 1 : 0;
-                    const double gx = T.points_x[g], gy = T.points_y[g];
-                    const double dx = sx[mm] - gx, dy = sy[mm] - gy;
-                    const double d_own = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                    const double ex = nx - gx, ey = ny - gy;
-                    const double d_new = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
-                    if (d_new < d_own || (d_new == d_own && ins < mm)) chg |= 1u << q;
+            for (int qd = 0; qd < CS_PTS / 4; ++qd) {
+                // the 4 points of a quad (a 2x2 block of the grid) mostly share their owner: its site is fetched
+                // once per quad (the owners' sites are a data-dependent, bank-conflicting shared-memory gather)
+                const int oq = wv.at(4 * qd);
+                int mq = oq - ((rm >= 0 && oq > rm) ? 1 : 0);
+                mq += (ins >= 0 && mq >= ins) ? 1 : 0;
+                const double oxq = sx[mq < K ? mq : 0], oyq = sy[mq < K ? mq : 0];
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int q = 4 * qd + qq;
+                    const int g = g0 + q;
+                    if (g >= G) continue;
+                    const int o = wv.at(q);
+                    if (rm >= 0 && o == rm) {
+                        scn |= 1u << q;
+                    } else if (ins >= 0) {
+                        int mm = o - ((rm >= 0 && o > rm) ? 1 : 0);
+                        mm += (mm >= ins) ? 1 : 0;
+                        double ox = oxq, oy = oyq;
+                        if (o != oq) { ox = sx[mm]; oy = sy[mm]; }
+                        const double gx = T.points_x[g], gy = T.points_y[g];
+                        const double dx = ox - gx, dy = oy - gy;
+                        const double d_own = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        const double ex = nx - gx, ey = ny - gy;
+                        const double d_new = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+                        if (d_new < d_own || (d_new == d_own && ins < mm)) chg |= 1u << q;
+                    }
                 }
             }
         }
