@@ -262,47 +262,97 @@ __global__ void __launch_bounds__(STEP_THREADS) k_misfit_logdet(const EnginePara
 
 // ------------------------------------------------------------------------------------------------
 // T1: ParallelTempering.on_end_advance_chain (samplers/_samplers.py:334-342).  n_total sequential
-// random-pair attempts; the pair, log u and the temperature-free part of the ratio of 32 attempts
-// are computed in parallel by the lanes of one warp, then applied in order (temperatures live in
-// shared memory when they fit).  Quirk Q2 (ratio already divided by T1) is reproduced.
+// random-pair attempts (temperatures live in shared memory when they fit).  Quirk Q2 (ratio already
+// divided by T1) is reproduced.
 // ------------------------------------------------------------------------------------------------
 constexpr int SWAP_THREADS = 256;
-constexpr int SWAP_SMEM_MAX = 24576;  // temperatures held in shared memory up to this many chains
+constexpr int SWAP_SMEM_MAX = 8192;   // temperatures, reciprocals and conflict stamps in shared memory up to this many chains
+constexpr int SWAP_CHUNK = 1024;      // attempts drawn by the whole block at a time
 
+// Round structure: the whole block draws SWAP_CHUNK attempts (pair, log u, temperature-free part of the ratio) in
+// parallel into shared memory; warp 0 then applies them in order, 32 at a time.  The attempts are sequential only
+// through the temperatures of the chains they touch: pairwise disjoint pairs commute, so every round of a batch
+// applies the longest pending prefix of mutually disjoint pairs at once (the whole batch 3 times out of 4 at 8192
+// chains, a few rounds otherwise).
+// 1 / T is kept next to T (same rounding as dividing afresh), so a decision costs one division.
 __global__ void __launch_bounds__(SWAP_THREADS) k_pt_swap(double *gathered, long long n_total, uint64_t seed,
                                                           long long round, long long id0, long long n_local,
                                                           double *temperature_out, int32_t *n_accepted_out,
                                                           const double *tape, int use_smem) {
-    extern __shared__ double temps_smem[];
-    double *temps = use_smem ? temps_smem : nullptr;
+    extern __shared__ double swap_smem[];
+    __shared__ double s_core[SWAP_CHUNK], s_logu[SWAP_CHUNK];
+    __shared__ int s_a[SWAP_CHUNK], s_b[SWAP_CHUNK];
+    double *temps = use_smem ? swap_smem : nullptr;
+    double *itemps = swap_smem + n_total;                               // use_smem: 1 / temps
+    int *stamp = reinterpret_cast<int *>(swap_smem + 2 * n_total);      // use_smem: which attempt touches a chain
     if (use_smem) {
-        for (long long i = threadIdx.x; i < n_total; i += blockDim.x) temps[i] = gathered[3 * i + 2];
+        for (long long i = threadIdx.x; i < n_total; i += blockDim.x) {
+            const double tv = gathered[3 * i + 2];
+            temps[i] = tv;
+            itemps[i] = 1.0 / tv;
+            stamp[i] = 0x7fffffff;
+        }
     }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int n_acc = 0;
-        for (long long base = 0; base < n_total; base += 32) {
-            const long long i = base + lane;
-            int a = 0, b = 0;
-            double log_u = 0.0, core = 0.0;
-            if (i < n_total) {
-                Rng rng;
-                if (tape != nullptr) {
-                    rng.init_tape(tape, 3 * i);
-                } else {
-                    rng.init_philox(seed, 0, (uint64_t)round, STREAM_SWAP);
-                    rng.n = (uint32_t)(3 * i);
-                }
-                const int n = (int)n_total;
-                a = min((int)(rng.u() * (double)n), n - 1);
-                b = min((int)(rng.u() * (double)(n - 1)), n - 2);
-                if (b >= a) ++b;
-                log_u = log(rng.unit());
-                core = (gathered[3 * (long long)a + 1] - gathered[3 * (long long)b + 1] +
-                        gathered[3 * (long long)a + 0] - gathered[3 * (long long)b + 0]) / 2.0;
+    int n_acc = 0;  // warp 0
+    for (long long chunk0 = 0; chunk0 < n_total; chunk0 += SWAP_CHUNK) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < SWAP_CHUNK; j += blockDim.x) {
+            const long long i = chunk0 + j;
+            if (i >= n_total) break;
+            Rng rng;
+            if (tape != nullptr) {
+                rng.init_tape(tape, 3 * i);
+            } else {
+                rng.init_philox(seed, 0, (uint64_t)round, STREAM_SWAP);
+                rng.n = (uint32_t)(3 * i);
             }
-            const int cnt = (int)min(32LL, n_total - base);
+            const int n = (int)n_total;
+            const int a = min((int)(rng.u() * (double)n), n - 1);
+            int b = min((int)(rng.u() * (double)(n - 1)), n - 2);
+            if (b >= a) ++b;
+            s_a[j] = a;
+            s_b[j] = b;
+            s_logu[j] = log(rng.unit());
+            s_core[j] = (gathered[3 * (long long)a + 1] - gathered[3 * (long long)b + 1] +
+                         gathered[3 * (long long)a + 0] - gathered[3 * (long long)b + 0]) / 2.0;
+        }
+        __syncthreads();
+        if (threadIdx.x >= 32) continue;
+        const int lane = threadIdx.x;
+        const int n_chunk = (int)min((long long)SWAP_CHUNK, n_total - chunk0);
+        for (int base = 0; base < n_chunk; base += 32) {
+            const int j = base + lane;
+            const bool mine = j < n_chunk;
+            const int a = mine ? s_a[j] : 0, b = mine ? s_b[j] : 0;
+            const double log_u = mine ? s_logu[j] : 0.0, core = mine ? s_core[j] : 0.0;
+            if (use_smem) {
+                // lanes still to be applied, in order: the longest prefix whose pairs are pairwise disjoint commutes
+                // and is decided by its own lanes at once; a lane whose pair meets an EARLIER pending lane's waits
+                unsigned todo = __ballot_sync(0xffffffffu, mine);
+                while (todo) {
+                    const bool active = (todo >> lane) & 1u;
+                    if (active) { atomicMin(&stamp[a], lane); atomicMin(&stamp[b], lane); }
+                    __syncwarp();
+                    const bool early = active && (stamp[a] < lane || stamp[b] < lane);
+                    const unsigned em = __ballot_sync(0xffffffffu, early);
+                    const unsigned go = em ? (todo & ((1u << (__ffs(em) - 1)) - 1u)) : todo;
+                    if (active) { stamp[a] = 0x7fffffff; stamp[b] = 0x7fffffff; }
+                    __syncwarp();
+                    bool swap = false;
+                    if ((go >> lane) & 1u) {
+                        const double t1 = temps[a], t2 = temps[b], i1 = itemps[a], i2 = itemps[b];
+                        const double llr = core / t1;
+                        const double prob = (i1 - i2) * llr;
+                        swap = prob > log_u;
+                        if (swap) { temps[a] = t2; temps[b] = t1; itemps[a] = i2; itemps[b] = i1; }
+                    }
+                    n_acc += __popc(__ballot_sync(0xffffffffu, swap));
+                    todo &= ~go;
+                    __syncwarp();
+                }
+                continue;
+            }
+            const int cnt = min(32, n_chunk - base);
             for (int q = 0; q < cnt; ++q) {
                 const int qa = __shfl_sync(0xffffffffu, a, q);
                 const int qb = __shfl_sync(0xffffffffu, b, q);
@@ -310,12 +360,13 @@ __global__ void __launch_bounds__(SWAP_THREADS) k_pt_swap(double *gathered, long
                 const double qcore = __shfl_sync(0xffffffffu, core, q);
                 const double t1 = use_smem ? temps[qa] : gathered[3 * (long long)qa + 2];
                 const double t2 = use_smem ? temps[qb] : gathered[3 * (long long)qb + 2];
+                const double i1 = use_smem ? itemps[qa] : 1.0 / t1, i2 = use_smem ? itemps[qb] : 1.0 / t2;
                 const double llr = qcore / t1;
-                const double prob = (1.0 / t1 - 1.0 / t2) * llr;
+                const double prob = (i1 - i2) * llr;
                 const bool swap = prob > qlu;
                 __syncwarp();
                 if (swap && lane == 0) {
-                    if (use_smem) { temps[qa] = t2; temps[qb] = t1; }
+                    if (use_smem) { temps[qa] = t2; temps[qb] = t1; itemps[qa] = i2; itemps[qb] = i1; }
                     else { gathered[3 * (long long)qa + 2] = t2; gathered[3 * (long long)qb + 2] = t1; }
                 }
                 if (!use_smem) __threadfence_block();
@@ -323,8 +374,8 @@ __global__ void __launch_bounds__(SWAP_THREADS) k_pt_swap(double *gathered, long
                 n_acc += swap ? 1 : 0;
             }
         }
-        if (lane == 0 && n_accepted_out != nullptr) *n_accepted_out = n_acc;
     }
+    if (threadIdx.x == 0 && n_accepted_out != nullptr) *n_accepted_out = n_acc;
     __syncthreads();
     if (use_smem) {
         for (long long i = threadIdx.x; i < n_total; i += blockDim.x) gathered[3 * i + 2] = temps[i];
@@ -468,8 +519,8 @@ int launch_pt_swap(const double *gathered, long long n_total, uint64_t seed, lon
                    long long n_local, double *temperature_out, int32_t *n_accepted_out, const double *tape,
                    cudaStream_t st) {
     const int use_smem = n_total <= SWAP_SMEM_MAX;
-    const size_t smem = use_smem ? (size_t)n_total * sizeof(double) : 0;
-    if (smem > 48 * 1024) {
+    const size_t smem = use_smem ? (size_t)n_total * (2 * sizeof(double) + sizeof(int)) : 0;
+    if (smem > 16 * 1024) {  // the kernel also has 24 KB of static shared memory
         cudaError_t err = cudaFuncSetAttribute(k_pt_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
     }
