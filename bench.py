@@ -295,6 +295,7 @@ def cuda_arm(args):
         "value_l2_warm": world * C * args.steps / (warm_ms * 1e-3),
         "ms_per_step_l2_warm": warm_ms / args.steps,
         "wall_s_timed_region": wall,
+        "step_ms_min_median_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
         "clocks": {k: clk[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clk else None,
         "e2e": e2e,
         "gpu_launches": (2 if eng.chain_local else 6) * args.steps + (2 * n_swaps if tempered else 0),
@@ -442,7 +443,25 @@ def reference_arm(args):
     print(json.dumps(out), flush=True)
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries (NCCL's version banner) write to file descriptor 1 too:
+    point fd 1 at stderr for the whole run and keep the real stdout for the JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global print
+    real_stdout = _claim_stdout()
+    _print = print
+
+    def print(*a, **kw):  # noqa: A001 - the module's JSON line goes to the real stdout
+        kw.setdefault("file", real_stdout)
+        _print(*a, **kw)
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
