@@ -143,8 +143,34 @@ def tomo_joint_small():
     return spec
 
 
+def tomo_weighted_fixed():
+    """Ray tomography variant for the chain-local step: per-datum inverse covariance (no noise move), the cell value
+    used as it is (slowness parameterisation, `transform="identity"`), Gaussian prior, FIXED number of cells (only value
+    and site moves).  Spec dict only."""
+    ing = synthetic.tomography_2d(nx=16, ny=12, n_sources_per_side=3, n_receivers=6, kmin=4, kmax=20)
+    spec = spec_from_ingredients(ing)
+    sp = spec["spaces"][0]
+    sp.update(trans_d=False, kmin=9, kmax=9, kinit_max=9, weights=dict(birth=0, death=0, values=3, sites=2))
+    sp["params"] = [dict(name="slow", kind="gaussian", a=0.33, b=0.05, perturb_std=0.01, perturb_std_birth=0.01)]
+    rng = np.random.default_rng(8)
+    tg = spec["targets"][0]
+    tg.update(hierarchical=False, cov_inv=rng.uniform(2e4, 2e5, np.asarray(tg["dobs"]).size))
+    tg["forward"] = dict(tg["forward"], transform="identity")
+    return spec
+
+
+def tomo_scalar_prior_birth():
+    """Ray tomography variant: fixed scalar inverse covariance, cells born from the prior."""
+    ing = synthetic.tomography_2d(nx=16, ny=12, n_sources_per_side=3, n_receivers=6, kmin=2, kmax=30)
+    spec = spec_from_ingredients(ing)
+    spec["spaces"][0]["birth_from"] = "prior"
+    spec["targets"][0].update(hierarchical=False, cov_inv=2.5e5)
+    return spec
+
+
 # oracle-vs-device cases without a reference replay fixture
-SPECS = {"joint_small": joint_small, "tomo_joint_small": tomo_joint_small}
+SPECS = {"joint_small": joint_small, "tomo_joint_small": tomo_joint_small, "tomo_weighted_fixed": tomo_weighted_fixed,
+         "tomo_scalar_prior_birth": tomo_scalar_prior_birth}
 EXTRA = {
     "tomo_small_corr": lambda: synthetic.tomography_2d(nx=12, ny=10, n_sources_per_side=3, n_receivers=5, kmin=4,
                                                        kmax=20, correlated=True),

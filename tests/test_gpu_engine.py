@@ -222,7 +222,8 @@ def test_incremental_raster_equals_brute_force_at_scale():
     assert kk.min() >= 3 and kk.max() <= 300 and kk.std() > 0
 
 
-@pytest.mark.parametrize("name,n_chains,n_steps", [("joint_small", 80, 80), ("tomo_joint_small", 48, 60)])
+@pytest.mark.parametrize("name,n_chains,n_steps", [("joint_small", 80, 80), ("tomo_joint_small", 48, 60),
+                                                   ("tomo_weighted_fixed", 60, 80), ("tomo_scalar_prior_birth", 60, 80)])
 def test_multi_space_multi_target_against_oracle(name, n_chains, n_steps):
     """Several parameter spaces and targets (hierarchical, per-datum and scalar inverse covariance; linear,
     1-D lookup and ray forwards side by side): move ids, outer weights and the summed likelihood ratio
@@ -258,7 +259,10 @@ def test_multi_space_multi_target_against_oracle(name, n_chains, n_steps):
             if bool(acc[c]) != info["accepted"]:
                 in_step[c] = False
     assert in_step.mean() > 0.9
-    assert len(seen) >= 6  # moves of both spaces and the noise move all occurred
+    if name.endswith("joint_small"):
+        assert len(seen) >= 6  # moves of both spaces and the noise move all occurred
+    else:
+        assert eng.chain_local and len(seen) >= 2
     mis, ld = eng.misfit_logdet()
     for c in np.flatnonzero(in_step)[:10]:
         m, l_ = OC.misfit_and_logdet(spec, states[c])
