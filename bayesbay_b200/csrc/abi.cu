@@ -434,7 +434,7 @@ static void bump_k_bound(bbb_engine *e, long long n) {
 static int run_chain_step(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
-    int rc = launch_chain_step(e->host, 0, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
+    int rc = launch_chain_step(e->host, 0, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
                                idx_bytes_of(P, e->ray_t), st);
     if (rc != 0) return rc;
     bump_k_bound(e, 1);
@@ -468,7 +468,7 @@ static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st
             if (c0 >= c1) continue;
             rc = launch_propose(e->host, c0, c1, e->half_stream[h]);
             if (rc == 0)
-                rc = launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, P.spaces[T.space].kmax,
+                rc = launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
                                        idx_bytes_of(P, e->ray_t), e->half_stream[h]);
         }
     }

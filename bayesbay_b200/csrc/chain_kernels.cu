@@ -61,8 +61,11 @@ struct IdxVec {
     __device__ __forceinline__ int at(int q) const { return (int)reinterpret_cast<const IdxT *>(w)[q]; }
 };
 
-__host__ __device__ inline size_t chain_step_smem(int tile_rays, int K) {
-    return (size_t)tile_rays * 8 + (size_t)K * 4 * 8 + (size_t)CS_CHUNK * sizeof(PrepEntry);
+// multi-tile problems also keep a bitmap of the touched rays (one bit per ray of the target)
+__host__ __device__ inline size_t chain_step_smem(int tile_rays, int K, long long n_data = 0) {
+    const bool multi = n_data > tile_rays;
+    return (size_t)tile_rays * 8 + (size_t)K * 4 * 8 + (size_t)CS_CHUNK * sizeof(PrepEntry) +
+           (multi ? (size_t)((n_data + 31) / 32) * 4 : 0);
 }
 
 long long chain_local_tile_rays(long long n_data, int kmax, long long n_points) {
@@ -75,8 +78,18 @@ long long chain_local_tile_rays(long long n_data, int kmax, long long n_points) 
         const long long v = atoll(cap);
         if (v >= 1 && v < max_tile) max_tile = v;
     }
+    if (n_data <= max_tile) return n_data;  // one tile
+    // several tiles: room for the touched-ray bitmap, tiles of whole 32-ray words
+    max_tile = (CS_SMEM_BLOCK - fixed - 4 * ((n_data + 31) / 32)) / 8;
+    if (const char *cap = getenv("BBB_CHAIN_TILE_RAYS")) {
+        const long long v = atoll(cap);
+        if (v >= 1 && v < max_tile) max_tile = v;
+    }
+    max_tile &= ~31LL;
+    if (max_tile < 32) max_tile = 32;
+    if (max_tile > 65504) max_tile = 65504;
     const long long n_tiles = (n_data + max_tile - 1) / max_tile;
-    return (n_data + n_tiles - 1) / n_tiles;
+    return (((n_data + n_tiles - 1) / n_tiles) + 31) & ~31LL;
 }
 
 __device__ __forceinline__ double block_sum_to_thread0(double v, double *s_red) {
@@ -147,6 +160,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     double *sx = reinterpret_cast<double *>(cs_smem + (size_t)RT * 8);
     double *sy = sx + K, *fo = sy + K, *fn = fo + K;
     PrepEntry *prep = reinterpret_cast<PrepEntry *>(fn + K);
+    unsigned *s_touch = reinterpret_cast<unsigned *>(prep + CS_CHUNK);  // multi-tile: bitmap of the touched rays
 
     const int cur = B.sel[s][c], prop = cur ^ 1;
     const int k_old = k_ref(B, s, cur, c), k_new = k_ref(B, s, prop, c);
@@ -432,6 +446,27 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
         if (tile > 0) zero_acc();
         accumulate(tile);
         const int r0 = tile * RT, nr = min(RT, R - r0);
+        if (NT > 1) {
+            // several ray tiles recycle the accumulators: the new residuals of the touched rays are parked in the
+            // chain's row of the (otherwise idle) d_pred scratch, the touched rays remembered in a bitmap
+            double *park = B.dpred_scratch[t] + c * (long long)R;
+            for (int w = warp; w < (nr + 31) / 32; w += CS_WARPS) {
+                const int r = 32 * w + lane;
+                const unsigned lo = r < nr ? acc_lo[r] : 0u, hi = r < nr ? acc_hi[r] : 0u;
+                const bool touched = (lo | hi) != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, touched);
+                if (lane == 0) s_touch[(r0 >> 5) + w] = m;
+                if (touched) {
+                    const double rr = res[r0 + r];
+                    const double d = (double)(long long)(((unsigned long long)hi << 32) | lo) * inv_scale;
+                    const double wr = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r0 + r] : 1.0;
+                    dphi += wr * (d * (2.0 * rr + d));
+                    park[r0 + r] = rr + d;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         const bool pairs = ((R | r0 | nr | RT) & 1) == 0;  // rays two at a time: 16-byte loads of the residual row
         auto one_ray = [&](int r, double rr) {
             const unsigned lo = acc_lo[r], hi = acc_hi[r];
@@ -493,16 +528,9 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             if ((lo | hi) != 0) res[r] = __hiloint2double((int)hi, (int)lo);
         }
     } else {
-        for (int tile = 0; tile < NT; ++tile) {  // the accumulators were recycled: rebuild each tile's
-            zero_acc();
-            accumulate(tile);
-            const int r0 = tile * RT, nr = min(RT, R - r0);
-            for (int r = tid; r < nr; r += CS_THREADS) {
-                const unsigned lo = acc_lo[r], hi = acc_hi[r];
-                if ((lo | hi) != 0) res[r0 + r] += (double)(long long)(((unsigned long long)hi << 32) | lo) * inv_scale;
-            }
-            __syncthreads();
-        }
+        const double *park = B.dpred_scratch[t] + c * (long long)R;
+        for (int w = warp; w < (R + 31) / 32; w += CS_WARPS)
+            if ((s_touch[w] >> lane) & 1u) res[32 * w + lane] = park[32 * w + lane];
     }
     // nearest-site index: renumber the survivors when the edit shifts cell indices (death), then the changed points
     constexpr int VEC = 16 / (int)sizeof(IdxT);
@@ -531,10 +559,10 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     }
 }
 
-int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, int K, int idx_bytes,
-                      cudaStream_t st) {
+int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, long long n_data, int K,
+                      int idx_bytes, cudaStream_t st) {
     const long long C = c_end - c_first;
-    const size_t smem = chain_step_smem(tile_rays, K);
+    const size_t smem = chain_step_smem(tile_rays, K, n_data);
     cudaError_t err;
     if (idx_bytes == 1) {
         err = cudaFuncSetAttribute(k_chain_step<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
