@@ -153,6 +153,7 @@ __device__ __forceinline__ void rng_begin(Rng &rng, const EngineParams &ep, long
     const bbb_buffers &B = ep.buf;
     if (B.tape != nullptr) {
         rng.init_tape(B.tape + c * B.tape_stride, B.tape_cursor[c]);
+        rng.tape_len = B.tape_stride;
     } else {
         rng.init_philox(ep.spec.seed, (uint64_t)(B.chain_id0 + c), (uint64_t)B.iteration[c], tag);
         if (continue_step) rng.n = (uint32_t)B.tape_cursor[c];

@@ -48,6 +48,12 @@ struct Rng {
     // tape state (tape != nullptr selects it)
     const double *tape;
     long long cursor;
+    long long tape_len = 0;  // entries of the chain's tape (bounds the look-ahead below)
+    // cooperative look-ahead: lane l holds the uniform at stream position l of this (chain, iteration) and the
+    // standard normal made of positions (l, l + 1), all computed in parallel up front; draws at positions < 32 are
+    // then one shuffle each instead of a serial Philox round / log / sqrt / cos on lane 0
+    bool ahead = false;
+    double ahead_u = 0.0, ahead_z = 0.0;
 
     __device__ void init_philox(uint64_t seed, uint64_t chain_id, uint64_t iteration, uint32_t tag) {
         k0 = (uint32_t)seed;
@@ -80,8 +86,29 @@ struct Rng {
         ++n;
         return words_to_double(w[h], w[h + 1]);
     }
+    // call once, by all 32 lanes, right after init_* of a cooperative generator that starts at position 0
+    __device__ void look_ahead() {
+        const uint32_t lane = threadIdx.x & 31u;
+        if (tape != nullptr) {
+            ahead_u = (cursor + lane < tape_len) ? tape[cursor + lane] : 0.0;
+        } else {
+            uint32_t o[4];
+            philox4x32_10(lane >> 1, chain, it_lo, it_hi, k0, k1, o);
+            const uint32_t h = (lane & 1u) * 2u;
+            ahead_u = words_to_double(o[h], o[h + 1]);
+        }
+        const double u2 = __shfl_down_sync(0xffffffffu, ahead_u, 1);
+        ahead_z = sqrt(-2.0 * log(1.0 - ahead_u)) * cos(6.283185307179586 * u2);  // same expression as std_normal()
+        ahead = true;
+    }
     __device__ double u() {
         if (!coop) return raw_u();
+        if (ahead && n < 32u) {
+            const double v = __shfl_sync(0xffffffffu, ahead_u, (int)n);
+            ++n;
+            ++cursor;
+            return v;
+        }
         double v = 0.0;
         if ((threadIdx.x & 31) == 0) v = raw_u();
         else { ++n; ++cursor; }
@@ -112,6 +139,12 @@ struct Rng {
         return i;
     }
     __device__ double std_normal() {
+        if (coop && ahead && n + 1u < 32u) {
+            const double z = __shfl_sync(0xffffffffu, ahead_z, (int)n);
+            n += 2u;
+            cursor += 2;
+            return z;
+        }
         const double u1 = u();
         const double u2 = u();
         return sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2);

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_con
     Rng rng;
     rng_begin(rng, ep, c, STREAM_STEP, false);
     rng.coop = true;
+    rng.look_ahead();
     propose_chain(ep.spec, ep.buf, c, rng, false);
     if ((threadIdx.x & 31) == 0) rng_end(rng, ep, c);
 }
