@@ -280,15 +280,21 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
             for (int jo = threadIdx.x & 31; jo < k_new; jo += 32) {
                 const int jp = jo - ((e.ins >= 0 && jo > e.ins) ? 1 : 0);
                 const int src = (jo == e.ins) ? 0 : jp + ((e.rm >= 0 && jp >= e.rm) ? 1 : 0);
-                double tmp[2 + BBB_MAX_PARAMS];
-                for (int d = 0; d < ndim; ++d) tmp[d] = s_cur[d * KC + (long long)src * C];
-                for (int p = 0; p < n_params; ++p) tmp[2 + p] = v_cur[p * KC + (long long)src * C];
-                if (jo == e.ins) {
-                    for (int d = 0; d < ndim; ++d) tmp[d] = e.site[d];
-                    for (int p = 0; p < n_params; ++p) tmp[2 + p] = e.vals[p];
-                }
-                for (int d = 0; d < ndim; ++d) s_new[d * KC + (long long)jo * C] = tmp[d];
-                for (int p = 0; p < n_params; ++p) v_new[p * KC + (long long)jo * C] = tmp[2 + p];
+                // constant trip counts: the values stay in registers and all loads of a cell go out together
+                double ts[2], tv[BBB_MAX_PARAMS];
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+                    if (d < ndim) ts[d] = s_cur[d * KC + (long long)src * C];
+#pragma unroll
+                for (int p = 0; p < BBB_MAX_PARAMS; ++p)
+                    if (p < n_params) tv[p] = v_cur[p * KC + (long long)src * C];
+                const bool fresh = jo == e.ins;
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+                    if (d < ndim) s_new[d * KC + (long long)jo * C] = fresh ? e.site[d] : ts[d];
+#pragma unroll
+                for (int p = 0; p < BBB_MAX_PARAMS; ++p)
+                    if (p < n_params) v_new[p * KC + (long long)jo * C] = fresh ? e.vals[p] : tv[p];
             }
         }
     } else if (e.write && apply_now) {
