@@ -195,13 +195,27 @@ class ChainBatch:
             if save:
                 self._save()
 
+    def _to_host(self, dev_tensor):
+        """Device -> host through a reusable PINNED staging buffer (a pageable ``.cpu()`` of the [C][R] d_pred image
+        of a save point runs at a few GB/s), returned as a numpy array the caller owns."""
+        t = self._torch
+        n = dev_tensor.numel() * dev_tensor.element_size()
+        if getattr(self, "_stage", None) is None or self._stage.numel() < n:
+            self._stage = t.empty((max(n, 1 << 20),), dtype=t.uint8, pin_memory=True)
+        dst = self._stage[:n].view(dev_tensor.dtype).view(dev_tensor.shape)
+        dst.copy_(dev_tensor.contiguous(), non_blocking=True)
+        t.cuda.current_stream(dev_tensor.device).synchronize()
+        return dst.numpy().copy()
+
     def _save(self):
+        """One save point.  Host arrays are stored CHAIN-MAJOR (``[C][...]``) so that handing a chain its samples
+        (:meth:`saved_states_of`) copies contiguous rows."""
         eng = self.engine
         temps = eng.temperature.cpu().numpy()
         mask = temps == 1.0
         if not mask.any():
             return
-        entry = dict(mask=mask, spaces=[], sigma=[], corr=[], dpred=[], fields={})
+        entry = dict(mask=mask, spaces=[], sigma=[], corr=[], dpred=[], fields={}, chain_major=True)
         for t, fs in self.field_stats.items():
             # rasterised field of the current states: cell value looked up through the resident nearest-site index
             f = self.spec["targets"][t]["forward"]
@@ -212,15 +226,17 @@ class ChainBatch:
             fs["sumsq"] += field * field * m
             fs["count"] += m
             if fs["store"]:
-                entry["fields"][fs["name"]] = field.cpu().numpy()
+                entry["fields"][fs["name"]] = self._to_host(field.t())  # [C][G]
         for s in range(len(self.spec["spaces"])):
             k, sites, vals = eng.gather_space(s)
-            entry["spaces"].append((k.cpu().numpy(), None if sites is None else sites.cpu().numpy(),
-                                    None if vals is None else vals.cpu().numpy()))
+            kb = max(int(k.max().item()), 1)  # only the cells in use travel
+            entry["spaces"].append((k.cpu().numpy(),
+                                    None if sites is None else self._to_host(sites[:, :kb].permute(2, 1, 0)),   # [C][kb][ndim]
+                                    None if vals is None else self._to_host(vals[:, :kb].permute(2, 0, 1))))    # [C][P][kb]
         for t, tg in enumerate(self.spec["targets"]):
             entry["sigma"].append(eng.sigma[t][0].cpu().numpy() if tg["hierarchical"] else None)
             entry["corr"].append(eng.corr[t][0].cpu().numpy() if tg.get("correlated") else None)
-            entry["dpred"].append(eng.dpred(t).cpu().numpy() if self.save_dpred else None)
+            entry["dpred"].append(self._to_host(eng.dpred_chain_major(t)) if self.save_dpred else None)  # [C][R]
         self.saved.append(entry)
 
     # ---- results in the reference's shapes -------------------------------
@@ -232,16 +248,17 @@ class ChainBatch:
         for entry in self.saved[start:]:
             if not entry["mask"][c]:
                 continue
+            cm = entry.get("chain_major", False)  # False: checkpoints written before the chain-major layout
             for sp, (k, sites, vals) in zip(self.spec["spaces"], entry["spaces"]):
                 kc = int(k[c])
                 if sp["trans_d"]:
                     out[f"{sp['name']}.n_dimensions"].append(kc)
                 if sp["ndim"] == 1:
-                    out[f"{sp['name']}.discretization"].append(sites[0, :kc, c].copy())
+                    out[f"{sp['name']}.discretization"].append((sites[c, :kc, 0] if cm else sites[0, :kc, c]).copy())
                 elif sp["ndim"] == 2:
-                    out[f"{sp['name']}.discretization"].append(sites[:, :kc, c].T.copy())
+                    out[f"{sp['name']}.discretization"].append((sites[c, :kc] if cm else sites[:, :kc, c].T).copy())
                 for j, p in enumerate(sp["params"]):
-                    out[f"{sp['name']}.{p['name']}"].append(vals[j, :kc, c].copy())
+                    out[f"{sp['name']}.{p['name']}"].append((vals[c, j, :kc] if cm else vals[j, :kc, c]).copy())
             for i, (tg, sg) in enumerate(zip(self.spec["targets"], entry["sigma"])):
                 if sg is not None:
                     out[f"{tg['name']}.std"].append(float(sg[c]))
@@ -250,9 +267,10 @@ class ChainBatch:
                     out[f"{tg['name']}.correlation"].append(float(rr[c]))
             for tg, dp in zip(self.spec["targets"], entry["dpred"]):
                 if dp is not None:
-                    out[f"{tg['name']}.dpred"].append(dp[:, c].copy())
+                    # (chain-major blocks: the chain's row is handed out as a view -- one host copy per sample less)
+                    out[f"{tg['name']}.dpred"].append(dp[c] if cm else dp[:, c].copy())
             for name, field in entry.get("fields", {}).items():
-                out[name].append(field[:, c].copy())
+                out[name].append(field[c] if cm else field[:, c].copy())
         return out
 
     def statistics(self):

@@ -328,17 +328,19 @@ class Engine:
 
     def refresh(self):
         L.check(self.lib.bbb_engine_refresh(self._handle, self._stream))
-        self._steps_since_sync = self.K_BOUND_RESYNC  # the engine forgot its bound: tighten before the next step
+        self._steps_since_sync = 1 << 30  # the engine forgot its bound: tighten before the next step
 
     RESYNC_EVERY = 256   # chain-local engines: steps between two from-scratch evaluations of residuals and misfit
     K_BOUND_RESYNC = 64  # steps between two tightenings of the engine's bound on max k (one tiny D2H sync each)
+    K_BOUND_RESYNC_LOCAL = 1024  # chain-local engines only size their rare from-scratch evaluations by the bound
 
     def step(self, n_steps: int = 1):
         n_steps = int(n_steps)
+        every = self.K_BOUND_RESYNC_LOCAL if self.chain_local else self.K_BOUND_RESYNC
         while n_steps > 0:
-            if self._steps_since_sync >= self.K_BOUND_RESYNC:
+            if self._steps_since_sync >= every:
                 self.sync_k_bound()
-            n = min(n_steps, self.K_BOUND_RESYNC - self._steps_since_sync)
+            n = min(n_steps, every - self._steps_since_sync)
             L.check(self.lib.bbb_engine_step(self._handle, n, self._stream))
             self._steps_since_sync += n
             n_steps -= n
@@ -358,7 +360,7 @@ class Engine:
     def stage(self, stage: int):
         """One stage of one step (0 propose, 1 raster, 2 ray forward + misfit, 3 accept)."""
         if stage == 0:
-            if self._steps_since_sync >= self.K_BOUND_RESYNC:
+            if self._steps_since_sync >= (self.K_BOUND_RESYNC_LOCAL if self.chain_local else self.K_BOUND_RESYNC):
                 self.sync_k_bound()
             self._steps_since_sync += 1
         L.check(self.lib.bbb_engine_stage(self._handle, int(stage), self._stream))
@@ -382,6 +384,15 @@ class Engine:
         out = torch.empty((R, self.C), dtype=torch.float64, device=self.device)
         L.check(self.lib.bbb_engine_dpred(self._handle, t, _ptr(out), self._stream))
         return out
+
+    def dpred_chain_major(self, t: int) -> torch.Tensor:
+        """[C][n_data] d_pred of the current states.  Chain-local engines hold the residual ``d_pred - d_obs`` of
+        the current states resident (re-based on a full evaluation every ``RESYNC_EVERY`` steps), so this is one
+        addition; other engines evaluate the forward."""
+        if self.chain_local and self.res[t] is not None:
+            dobs = torch.as_tensor(np.asarray(self.spec["targets"][t]["dobs"], dtype=np.float64)).to(self.device)
+            return self.res[t] + dobs[None, :]
+        return self.dpred(t).t().contiguous()
 
     def misfit_logdet(self):
         m = torch.empty((self.C,), dtype=torch.float64, device=self.device)
@@ -494,7 +505,7 @@ class Engine:
     def unpack_states(self, kb, image: torch.Tensor):
         """Write a packed image into the engine and re-derive rasterisation, forward and misfit."""
         L.check(self.lib.bbb_engine_unpack_states(self._handle, self._kb(kb), _ptr(image), self._stream))
-        self._steps_since_sync = self.K_BOUND_RESYNC
+        self._steps_since_sync = 1 << 30
 
     # ------------------------------------------------------------------ checkpoint / resume
     def _mutable(self):
@@ -531,7 +542,7 @@ class Engine:
         for s, sp in enumerate(self.spec["spaces"]):
             L.check(self.lib.bbb_engine_set_k_bound(self._handle, s, sp["kmax"]))
         L.check(self.lib.bbb_engine_set_resync(self._handle, self.RESYNC_EVERY, int(meta.get("steps_since_resync", 0))))
-        self._steps_since_sync = self.K_BOUND_RESYNC
+        self._steps_since_sync = 1 << 30
         torch.cuda.synchronize(self.device)
 
     def close(self):
