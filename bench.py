@@ -307,11 +307,32 @@ def cuda_arm(args):
                      "algorithmic_bytes_per_chain_step": per_unit, "chain_steps_per_launch": units,
                      "whole_step_frac": ab["total"] * C / (warm_ms / args.steps * 1e-3) / 1e9 / peak},
     }
+    if world == 1:
+        out["api_run"] = api_run(par, ll, bb, C)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(spec, args.cpu_seconds)
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def api_run(par, ll, bb, n_chains, n_iterations=2000, save_every=100):
+    """Wall clock of the call a user makes -- BayesianInversion.run with the reference's defaults for what is saved
+    (every chain's state AND d_pred at every save point come back to host lists, as in the reference) -- for
+    information; not the device-timed `value`."""
+    import torch
+
+    inv = bb.BayesianInversion(par, ll, n_chains=n_chains)
+    inv.run(n_iterations=200, burnin_iterations=100, save_every=save_every, verbose=False)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    inv.run(n_iterations=n_iterations, burnin_iterations=0, save_every=save_every, verbose=False)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    n_samples = len(inv.get_results()["voronoi.n_dimensions"])
+    return {"value": n_chains * n_iterations / wall, "unit": UNIT, "wall_s": wall,
+            "what": f"BayesianInversion.run(n_iterations={n_iterations}, save_every={save_every}) on the same problem and "
+                    f"chain count, host wall clock incl. the saved samples ({n_samples} states with d_pred) coming back"}
 
 
 def e2e_run(eng, steps, device, world, dist):
