@@ -124,7 +124,8 @@ SYMBOLS = {
     "bbb_philox_kat": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbbb200.so")
+# (BBB_LIB_PATH: developer override, e.g. an instrumented build of the same sources)
+LIB_PATH = os.environ.get("BBB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbbb200.so")
 _lib = None
 
 

@@ -34,6 +34,9 @@
 
 namespace bbb {
 
+#ifndef CS_AB_LIST
+#define CS_AB_LIST 1
+#endif
 constexpr int CS_THREADS = 512;
 constexpr int CS_WARPS = CS_THREADS / 32;
 constexpr int CS_CHUNK = CS_THREADS;       // change-list entries prepared per round
@@ -44,6 +47,7 @@ constexpr unsigned CS_BACK = 1u << 31;     // entry of a point that LOST its own
 constexpr unsigned CS_G_MASK = (1u << CS_G_BITS) - 1u, CS_M_MASK = (1u << CS_M_BITS) - 1u;
 constexpr int CS_PTS = 16;                 // grid points per thread and pass = the largest merged group
 constexpr int CS_SMEM_BLOCK = 112 * 1024;  // two resident blocks per SM
+constexpr int CS_LIST_SMEM = 1024;         // change-list entries kept in shared memory (the rest spill to the global list)
 
 struct PrepEntry {
     int j0, len;  // entries of the (merged) column inside the current ray tile; the level rides in len's top 2 bits
@@ -64,7 +68,7 @@ struct IdxVec {
 // multi-tile problems also keep a bitmap of the touched rays (one bit per ray of the target)
 __host__ __device__ inline size_t chain_step_smem(int tile_rays, int K, long long n_data = 0) {
     const bool multi = n_data > tile_rays;
-    return (size_t)tile_rays * 8 + (size_t)K * 4 * 8 + (size_t)CS_CHUNK * sizeof(PrepEntry) +
+    return (size_t)tile_rays * 8 + (size_t)K * 4 * 8 + (size_t)CS_CHUNK * sizeof(PrepEntry) + (size_t)CS_LIST_SMEM * 4 +
            (multi ? (size_t)((n_data + 31) / 32) * 4 : 0);
 }
 
@@ -123,6 +127,21 @@ __device__ __forceinline__ void fx_add(unsigned *lo, unsigned *hi, int r, long l
     if (ah != 0) atomicAdd(hi + r, ah);
 }
 
+// Developer instrumentation (-DCS_TIMELINE): SM clock at the phase boundaries of every block, read back by
+// bbb_debug_timeline (tools/timeline.py).  Not compiled into the product library.
+#ifdef CS_TIMELINE
+__device__ long long g_timeline[4096][24];
+#define CS_TL(i) do { if (threadIdx.x == 0 && blockIdx.x < 4096) g_timeline[blockIdx.x][i] = clock64(); } while (0)
+__device__ __forceinline__ long long cs_globaltimer() { long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; }
+__device__ __forceinline__ int cs_smid() { int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+#define CS_TL_G(i) do { if (threadIdx.x == 0 && blockIdx.x < 4096) g_timeline[blockIdx.x][i] = cs_globaltimer(); } while (0)
+#define CS_TL_T(i, thr) do { if (threadIdx.x == (thr) && blockIdx.x < 4096) g_timeline[blockIdx.x][i] = clock64(); } while (0)
+#else
+#define CS_TL(i) do {} while (0)
+#define CS_TL_G(i) do {} while (0)
+#define CS_TL_T(i, thr) do {} while (0)
+#endif
+
 template <typename IdxT>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first) {
     const bbb_problem_spec &P = ep.spec;
@@ -133,6 +152,11 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     const long long C = B.n_chains;
     const long long c = c_first + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    CS_TL(0);
+    CS_TL_G(16);
+#ifdef CS_TIMELINE
+    if (tid == 0 && blockIdx.x < 4096) g_timeline[blockIdx.x][18] = cs_smid();
+#endif
 
     __shared__ int s_front, s_back, s_accept;
     __shared__ double s_red[CS_WARPS];
@@ -140,14 +164,21 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     __shared__ FinishPre s_pre;
     constexpr int RW = CS_WARPS - 1;  // warps of the rasterisation pass; the last warp prepares the decision meanwhile
 
+    // every scalar of the chain's proposal is requested before the first one is used: ONE memory round trip instead
+    // of a chain of three (move -> selector -> cell counts)
     const int move = B.move[c];
     const double lpr = B.log_prob_ratio[c];
+    const int cur = B.sel[s][c], prop = cur ^ 1;
+    const int k_slot0 = k_ref(B, s, 0, c), k_slot1 = k_ref(B, s, 1, c);
+    const int rm = B.edit[c], ins = B.edit[C + c];
+    const double nx = B.edit_site[c], ny = B.edit_site[C + c];
     if (!target_touched(P, move, lpr, t)) {  // noise move, other space, or rejected by the prior: no forward
         if (tid == 0) {
             Rng rng;
             rng_begin(rng, ep, c, STREAM_STEP, true);
             finish_chain(ep, c, rng);
             rng_end(rng, ep, c);
+            CS_TL_G(17);
         }
         return;
     }
@@ -160,18 +191,22 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     double *sx = reinterpret_cast<double *>(cs_smem + (size_t)RT * 8);
     double *sy = sx + K, *fo = sy + K, *fn = fo + K;
     PrepEntry *prep = reinterpret_cast<PrepEntry *>(fn + K);
-    unsigned *s_touch = reinterpret_cast<unsigned *>(prep + CS_CHUNK);  // multi-tile: bitmap of the touched rays
+    // the head of the change list and the whole re-derivation queue (it aliases `prep`, which is idle until the
+    // forward) live in shared memory: a global round trip less between the phases that write and read them
+    unsigned *s_list = reinterpret_cast<unsigned *>(prep + CS_CHUNK);
+    unsigned *s_queue = reinterpret_cast<unsigned *>(prep);
+    constexpr int CS_QUEUE_SMEM = CS_CHUNK * (int)sizeof(PrepEntry) / 4;
+    unsigned *s_touch = s_list + CS_LIST_SMEM;  // multi-tile: bitmap of the touched rays
 
-    const int cur = B.sel[s][c], prop = cur ^ 1;
-    const int k_old = k_ref(B, s, cur, c), k_new = k_ref(B, s, prop, c);
+    const int k_old = cur ? k_slot1 : k_slot0, k_new = cur ? k_slot0 : k_slot1;
     const int inner = move & 3;
-    const int rm = B.edit[c], ins = B.edit[C + c];
-    const double nx = B.edit_site[c], ny = B.edit_site[C + c];
     const bool recip = T.transform == BBB_TRANSFORM_RECIPROCAL;
     IdxT *row = reinterpret_cast<IdxT *>(B.idx_cm[t]) + c * ((long long)(G + 15) & ~15LL);
     // change list [0, G) and, behind it, the queue of 16-point groups with points to re-derive
     unsigned *list = B.change_list[t] + c * (long long)(G + (G + 15) / 16);
     unsigned *queue = list + G;
+    auto list_at = [&](int pos) -> unsigned & { return pos < (CS_AB_LIST ? CS_LIST_SMEM : 0) ? s_list[pos] : list[pos]; };
+    auto queue_at = [&](int pos) -> unsigned & { return pos < (CS_AB_LIST ? CS_QUEUE_SMEM : 0) ? s_queue[pos] : queue[pos]; };
     const int n_levels = T.csc_n_levels;
     IdxVec<IdxT> wv_next;
     if (warp < RW) wv_next.load(row + min(tid * CS_PTS, G - 1) / CS_PTS * CS_PTS);  // in flight while the tables load
@@ -206,6 +241,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     }
     if (lane == 0) s_red[warp] = fmax;
     __syncthreads();
+    CS_TL(1);
     fmax = 0.0;
     for (int w = 0; w < CS_WARPS; ++w) fmax = fmax > s_red[w] ? fmax : s_red[w];
     __syncthreads();  // s_red is reused below
@@ -231,6 +267,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
         rng_resume(rng, ep, c, s_fin);
         finish_pre(ep, c, s_fin, rng, t, s_pre);
         rng_end(rng, ep, c);
+        CS_TL_T(9, CS_THREADS - 1);
     }
     for (int g0 = tid * CS_PTS; g0 < G && warp < RW; g0 += RW * 32 * CS_PTS) {
         const IdxVec<IdxT> wv = wv_next;
@@ -249,6 +286,27 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
                 int mq = oq - ((rm >= 0 && oq > rm) ? 1 : 0);
                 mq += (ins >= 0 && mq >= ins) ? 1 : 0;
                 const double oxq = sx[mq < K ? mq : 0], oyq = sy[mq < K ? mq : 0];
+                // coordinates of the quad's points: four independent 16-byte loads, issued whatever the owners are
+                // (a load per point behind the owner test costs one L2 round trip per point)
+                double gxq[4], gyq[4];
+                {
+                    const int gq = g0 + 4 * qd;
+                    if (ins >= 0 && gq + 3 < G) {
+                        const double2 xa = __ldg(reinterpret_cast<const double2 *>(T.points_x + gq));
+                        const double2 xb = __ldg(reinterpret_cast<const double2 *>(T.points_x + gq + 2));
+                        const double2 ya = __ldg(reinterpret_cast<const double2 *>(T.points_y + gq));
+                        const double2 yb = __ldg(reinterpret_cast<const double2 *>(T.points_y + gq + 2));
+                        gxq[0] = xa.x; gxq[1] = xa.y; gxq[2] = xb.x; gxq[3] = xb.y;
+                        gyq[0] = ya.x; gyq[1] = ya.y; gyq[2] = yb.x; gyq[3] = yb.y;
+                    } else {
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const int g = min(gq + qq, G - 1);
+                            gxq[qq] = ins >= 0 ? T.points_x[g] : 0.0;
+                            gyq[qq] = ins >= 0 ? T.points_y[g] : 0.0;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
                     const int q = 4 * qd + qq;
@@ -262,7 +320,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
                         mm += (mm >= ins) ? 1 : 0;
                         double ox = oxq, oy = oyq;
                         if (o != oq) { ox = sx[mm]; oy = sy[mm]; }
-                        const double gx = T.points_x[g], gy = T.points_y[g];
+                        const double gx = gxq[qq], gy = gyq[qq];
                         const double dx = ox - gx, dy = oy - gy;
                         const double d_own = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                         const double ex = nx - gx, ey = ny - gy;
@@ -294,24 +352,26 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             }
             if (hex) {
                 const int pos = atomicAdd(&s_front, 1);
-                list[pos] = (2u << 29) | ((unsigned)(g0 >> 4) << CS_M_BITS) | (unsigned)wv.at(0);
+                list_at(pos) = (2u << 29) | ((unsigned)(g0 >> 4) << CS_M_BITS) | (unsigned)wv.at(0);
             } else {
                 int pos = atomicAdd(&s_front, __popc(quads) + __popc(chg));
                 while (quads) {
                     const int qd = __ffs(quads) - 1;
                     quads &= quads - 1;
-                    list[pos++] = (1u << 29) | ((unsigned)((g0 >> 2) + qd) << CS_M_BITS) | (unsigned)wv.at(4 * qd);
+                    list_at(pos++) = (1u << 29) | ((unsigned)((g0 >> 2) + qd) << CS_M_BITS) | (unsigned)wv.at(4 * qd);
                 }
                 while (chg) {
                     const int q = __ffs(chg) - 1;
                     chg &= chg - 1;
-                    list[pos++] = ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)wv.at(q);
+                    list_at(pos++) = ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)wv.at(q);
                 }
             }
         }
-        if (scn) queue[atomicAdd(&s_back, 1)] = ((unsigned)(g0 >> 4) << 16) | scn;
+        if (scn) queue_at(atomicAdd(&s_back, 1)) = ((unsigned)(g0 >> 4) << 16) | scn;
     }
+    CS_TL(10);
     __syncthreads();
+    CS_TL(2);
     // (the queue is complete)
     // re-derivation: 16 lanes per queued group, lane q = point q of the group; the group's new owners are then
     // merged like the front entries (a moved cell that still owns a point changes nothing there: 2-D site move,
@@ -321,7 +381,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
         const int q = tid & 15, half = lane >> 4;
         for (int base = 0; base < n_items; base += CS_THREADS / 16) {
             const int it = base + (tid >> 4);
-            const unsigned item = it < n_items ? queue[it] : 0u;
+            const unsigned item = it < n_items ? queue_at(it) : 0u;
             const int g0 = (int)(item >> 16) << 4;
             const bool mine = (item >> q) & 1u;
             int bi = -1;
@@ -355,10 +415,11 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             int pos = 0;
             if (lane == 0 && emit) pos = atomicAdd(&s_front, __popc(emit));
             pos = __shfl_sync(full, pos, 0);
-            if (entry != CS_NONE) list[pos + __popc(emit & ((1u << lane) - 1u))] = entry;
+            if (entry != CS_NONE) list_at(pos + __popc(emit & ((1u << lane) - 1u))) = entry;
         }
     }
     __syncthreads();
+    CS_TL(3);
     const int n_list = s_front;
 
     // ---- change-local forward: fixed-point accumulation of the ray changes of one ray tile ---------------------
@@ -370,7 +431,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             const int e = base + tid;
             PrepEntry pe{0, 0, 0.0};
             if (e < n_list) {
-                const unsigned pk = list[e];
+                const unsigned pk = list_at(e);
                 {
                     const int lvl = (int)((pk >> 29) & 3u);
                     const unsigned grp = (pk >> CS_M_BITS) & CS_G_MASK;
@@ -384,6 +445,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             }
             prep[tid] = pe;
             __syncthreads();
+            if (base == 0) CS_TL(4);
             const int n = min(CS_CHUNK, n_list - base);
             // two columns per warp and round, four entries per lane and column: all loads of a round are issued
             // before its first atomic
@@ -445,6 +507,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     for (int tile = 0; tile < NT; ++tile) {
         if (tile > 0) zero_acc();
         accumulate(tile);
+        CS_TL(5);
         const int r0 = tile * RT, nr = min(RT, R - r0);
         if (NT > 1) {
             // several ray tiles recycle the accumulators: the new residuals of the touched rays are parked in the
@@ -515,11 +578,21 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
         }
         if (NT > 1) __syncthreads();
     }
+    CS_TL(11);
     dphi = block_sum_to_thread0(dphi, s_red);
+    CS_TL(6);
 
     // ---- likelihood ratio, decision, statistics (thread 0), then the commit by the whole block ----------------
     if (tid == 0) s_accept = finish_post(ep, c, s_fin, s_pre, t, finite ? s_fin.phi_old[t].s0 + dphi : NAN) ? 1 : 0;
     __syncthreads();
+    CS_TL(7);
+    if (tid == 0 && blockIdx.x < 4096) {
+#ifdef CS_TIMELINE
+        g_timeline[blockIdx.x][12] = n_list; g_timeline[blockIdx.x][13] = s_back; g_timeline[blockIdx.x][14] = s_accept;
+        g_timeline[blockIdx.x][15] = k_new; g_timeline[blockIdx.x][19] = move;
+#endif
+    }
+    CS_TL_G(17);
     if (!s_accept) return;
 
     if (NT == 1) {
@@ -551,13 +624,26 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
         __syncthreads();
     }
     for (int e = tid; e < n_list; e += CS_THREADS) {
-        const unsigned pk = list[e];
+        const unsigned pk = list_at(e);
         const int lvl = (int)((pk >> 29) & 3u);
         const int g_first = (int)((pk >> CS_M_BITS) & CS_G_MASK) << (2 * lvl);
         const IdxT owner = (IdxT)((pk & CS_BACK) ? (pk & CS_M_MASK) : (unsigned)ins);
         for (int q = 0; q < (1 << (2 * lvl)); ++q) row[g_first + q] = owner;
     }
+    CS_TL(8);
+    CS_TL_G(17);
 }
+
+#ifdef CS_TIMELINE
+extern "C" int bbb_debug_timeline(long long *host_out, int n_blocks) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 24 * (size_t)n_blocks);
+}
+extern "C" int bbb_debug_timeline_clear() {
+    void *p = nullptr;
+    cudaGetSymbolAddress(&p, g_timeline);
+    return (int)cudaMemset(p, 0, sizeof(g_timeline));
+}
+#endif
 
 int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, long long n_data, int K,
                       int idx_bytes, cudaStream_t st) {
