@@ -44,6 +44,8 @@ struct bbb_engine {
     // that run on internal streams, so that one part's proposal kernel (a latency-bound kernel of one warp per chain)
     // and the tail of its chain kernel overlap the other parts' chain kernels
     int pipeline;  // number of parts (1 = off)
+    int order_parity[4];  // per part: which set of block-order class counts the next proposal kernel counts into
+    bool order_pending[4];  // a proposal kernel has filed its chains and the chain kernel has not consumed them yet
     cudaStream_t half_stream[4];
     cudaEvent_t ev_fork, ev_join[4];
 };
@@ -221,6 +223,8 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
     // chain-local step: exactly one ray target, CSC copy of its matrix and the chain-major caches provided
     e->host.chain_local = 0;
     e->ray_t = -1;
+    e->host.ray_t = -1;
+    for (int h = 0; h < 4; ++h) { e->order_parity[h] = 0; e->order_pending[h] = false; }
     {
         int n_ray = 0, rt = -1;
         for (int t = 0; t < P.n_targets; ++t)
@@ -232,6 +236,7 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
             if (have) {
                 e->host.chain_local = 1;
                 e->ray_t = rt;
+                e->host.ray_t = rt;
             }
         }
     }
@@ -302,7 +307,8 @@ static int run_propose(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const long long C = e->host.buf.n_chains;
     (void)P;
-    return launch_propose(e->host, 0, C, st);  // the proposal warps also write the proposed slots
+    e->order_pending[0] = true;
+    return launch_propose(e->host, 0, C, e->order_parity[0] * 4, st);  // the proposal warps also write the proposed slots
 }
 
 static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool write_partial, cudaStream_t st) {
@@ -435,8 +441,9 @@ static int run_chain_step(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
     int rc = launch_chain_step(e->host, 0, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
-                               idx_bytes_of(P, e->ray_t), st);
+                               idx_bytes_of(P, e->ray_t), e->order_pending[0] ? e->order_parity[0] * 4 : -1, st);
     if (rc != 0) return rc;
+    if (e->order_pending[0]) { e->order_parity[0] ^= 1; e->order_pending[0] = false; }
     bump_k_bound(e, 1);
     ++e->steps_since_resync;
     if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) rc = chain_local_from_scratch(e, false, st);
@@ -466,10 +473,11 @@ static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st
         for (int h = 0; h < NP && rc == 0; ++h) {
             const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
             if (c0 >= c1) continue;
-            rc = launch_propose(e->host, c0, c1, e->half_stream[h]);
+            rc = launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, e->half_stream[h]);
             if (rc == 0)
                 rc = launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
-                                       idx_bytes_of(P, e->ray_t), e->half_stream[h]);
+                                       idx_bytes_of(P, e->ray_t), e->order_parity[h] * 4 + h, e->half_stream[h]);
+            e->order_parity[h] ^= 1;
         }
     }
     for (int h = 0; h < NP && rc == 0; ++h) {

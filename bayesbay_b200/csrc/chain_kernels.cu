@@ -143,15 +143,32 @@ __device__ __forceinline__ int cs_smid() { int v; asm volatile("mov.u32 %0, %%sm
 #endif
 
 template <typename IdxT>
-__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first) {
+__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
+                                                              int order_slot) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const bbb_target_spec &T = P.targets[t];
     const int s = T.space;
     const bbb_space_spec &S = P.spaces[s];
     const long long C = B.n_chains;
-    const long long c = c_first + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // longest-first block order (common.cuh): block b takes the b-th chain in cost-class order; class counts that do
+    // not add up to the grid (a proposal kernel that ran twice, a caller that binds no order buffer) mean index order
+    long long c = c_first + blockIdx.x;
+    if (order_slot >= 0) {
+        const int32_t *cnt = order_counts(B.block_order, C, order_slot >> 2, order_slot & 3);
+        int n[BBB_ORDER_BUCKETS];
+#pragma unroll
+        for (int i = 0; i < BBB_ORDER_BUCKETS; ++i) n[i] = cnt[i];
+        int tot = 0, cls = -1, off = 0;
+#pragma unroll
+        for (int i = 0; i < BBB_ORDER_BUCKETS; ++i) {
+            if (cls < 0 && (int)blockIdx.x < tot + n[i]) { cls = i; off = (int)blockIdx.x - tot; }
+            tot += n[i];
+        }
+        if (tot == (int)gridDim.x && cls >= 0) c = B.block_order[(long long)cls * C + c_first + off];
+        if (blockIdx.x == 0 && tid < 16) order_counts(B.block_order, C, (order_slot >> 2) ^ 1, order_slot & 3)[tid] = 0;
+    }
     CS_TL(0);
     CS_TL_G(16);
 #ifdef CS_TIMELINE
@@ -646,18 +663,19 @@ extern "C" int bbb_debug_timeline_clear() {
 #endif
 
 int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, long long n_data, int K,
-                      int idx_bytes, cudaStream_t st) {
+                      int idx_bytes, int order_slot, cudaStream_t st) {
+    if (dev.buf.block_order == nullptr) order_slot = -1;
     const long long C = c_end - c_first;
     const size_t smem = chain_step_smem(tile_rays, K, n_data);
     cudaError_t err;
     if (idx_bytes == 1) {
         err = cudaFuncSetAttribute(k_chain_step<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        k_chain_step<uint8_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t, c_first);
+        k_chain_step<uint8_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t, c_first, order_slot);
     } else {
         err = cudaFuncSetAttribute(k_chain_step<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        k_chain_step<uint16_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t, c_first);
+        k_chain_step<uint16_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t, c_first, order_slot);
     }
     return (int)cudaGetLastError();
 }

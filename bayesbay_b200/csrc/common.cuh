@@ -27,7 +27,16 @@ struct EngineParams {
     Annealing anneal;
     int n_partial[BBB_MAX_TARGETS];  // rows of partial[t] the ray kernel writes (its ray groups)
     int chain_local;                 // 1: the chain-local kernel (chain_kernels.cu) evaluates the ray target
+    int ray_t;                       // chain-local engines: the one ray target (else -1)
 };
+
+// Longest-first block order of the chain kernel.  The proposal kernel files every chain of a launch range
+// [c_first, c_end) under a cost class (atomic counter per class), the chain kernel's block b takes the b-th chain in
+// class order.  Class counts are double-buffered by launch parity: a chain kernel zeroes the set the NEXT proposal
+// kernel of its part will count into.  Whatever the order, results are the same (chains never interact in a step).
+__host__ __device__ inline int32_t *order_counts(int32_t *block_order, long long C, int parity, int part) {
+    return block_order + (long long)BBB_ORDER_BUCKETS * C + (parity * 4 + part) * 16;
+}
 
 __device__ __forceinline__ double annealing_temperature(const Annealing &a, long long it) {
     if (it < a.burnin_iterations && it < a.cooling_iterations) {

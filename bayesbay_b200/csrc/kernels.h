@@ -65,7 +65,7 @@ int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);
 // chain_kernels.cu
 long long chain_local_tile_rays(long long n_data, int kmax, long long n_points);
 int launch_chain_step(const EngineParams &host_params, long long c_first, long long c_end, int target, int tile_rays,
-                      long long n_data, int K, int idx_bytes, cudaStream_t stream);
+                      long long n_data, int K, int idx_bytes, int order_slot, cudaStream_t stream);
 int launch_transpose_idx(const void *in, void *out, int idx_bytes, long long rows, long long cols, long long in_stride,
                          long long out_stride, cudaStream_t stream);
 int launch_residual_transpose(const double *dpred, double *res, long long R, long long C, const double *dobs,
@@ -74,7 +74,8 @@ int launch_residual_transpose(const double *dpred, double *res, long long R, lon
 // step_kernels.cu
 // (the step kernels take the engine parameters BY VALUE, as a __grid_constant__ kernel argument: every scalar of the
 // problem spec and every buffer pointer is then a constant-bank read instead of a dependent global load)
-int launch_propose(const EngineParams &host_params, long long c_first, long long c_end, cudaStream_t stream);
+// order_slot = parity * 4 + part of the block-order class counts (common.cuh), -1: no block order
+int launch_propose(const EngineParams &host_params, long long c_first, long long c_end, int order_slot, cudaStream_t stream);
 int launch_finish(const EngineParams &host_params, long long C, cudaStream_t stream);
 int launch_corr_sums(const EngineParams *dev_params, long long C, int target, int proposal, cudaStream_t stream);
 int launch_fused_steps(const EngineParams &host_params, long long C, long long n_steps, cudaStream_t stream);

@@ -12,7 +12,31 @@ constexpr int STEP_THREADS = 64;  // 2 warps per block: spreads C = 1024 chains 
 // One WARP per chain: lane 0 owns the generator (every draw is broadcast), the O(k) nearest-site searches of
 // birth/death-from-neighbour run with lanes = sites, and the lanes write the proposed slot (lanes = cells).
 constexpr int PROPOSE_WARPS = 4;
-__global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep, long long c_first, long long c_end) {
+// Cost class of chain c's block in the chain kernel, 0 = longest.  est = a[move] + b[move] * (points per cell): block
+// times measured on the C3 shape (tools/timeline.py; birth 29.6 + 2.17 x, death 25.9 + 2.23 x, values 21.8 + 1.42 x,
+// sites 30.9 + 0.72 x microseconds, x = G / (100 k)).  Only the ORDER of the blocks depends on these numbers.
+__device__ __forceinline__ int block_cost_class(const EngineParams &ep, long long c) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const int t = ep.ray_t;
+    const int move = B.move[c];
+    if (!target_touched(P, move, B.log_prob_ratio[c], t)) return BBB_ORDER_BUCKETS - 1;  // no forward: a few microseconds
+    const bbb_target_spec &T = P.targets[t];
+    const int s = T.space;
+    const int k_new = k_ref(B, s, (int)B.sel[s][c] ^ 1, c);
+    const float x = (float)T.n_points / (100.0f * (float)(k_new > 0 ? k_new : 1));
+    const int inner = move & 3;
+    const float a = inner == BBB_MOVE_BIRTH ? 29.6f : (inner == BBB_MOVE_DEATH ? 25.9f : (inner == BBB_MOVE_VALUES ? 21.8f : 30.9f));
+    const float b = inner == BBB_MOVE_BIRTH ? 2.17f : (inner == BBB_MOVE_DEATH ? 2.23f : (inner == BBB_MOVE_VALUES ? 1.42f : 0.72f));
+    const float est = a + b * x;
+    // classes of 2.5 us between 23 and 43 us
+    int cls = (int)((43.0f - est) * 0.4f);
+    cls = cls < 0 ? 0 : (cls > BBB_ORDER_BUCKETS - 2 ? BBB_ORDER_BUCKETS - 2 : cls);
+    return cls;
+}
+
+__global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep, long long c_first, long long c_end,
+                                                                int order_slot) {
     const long long c = c_first + (long long)blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
     if (c >= c_end) return;
     Rng rng;
@@ -21,6 +45,15 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_con
     rng.look_ahead();
     propose_chain(ep.spec, ep.buf, c, rng, false);
     if ((threadIdx.x & 31) == 0) rng_end(rng, ep, c);
+    if (order_slot >= 0) {  // file the chain for the longest-first block order of the chain kernel
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            const long long C = ep.buf.n_chains;
+            const int cls = block_cost_class(ep, c);
+            const int pos = atomicAdd(order_counts(ep.buf.block_order, C, order_slot >> 2, order_slot & 3) + cls, 1);
+            if (pos < c_end - c_first) ep.buf.block_order[(long long)cls * C + c_first + pos] = (int32_t)c;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(STEP_THREADS) k_finish(const __grid_constant__ EngineParams ep) {
@@ -451,8 +484,9 @@ __global__ void k_phi_from_partial(const double *partial, int n_tiles, long long
 // ------------------------------------------------------------------------------------------------
 static inline int blocks_for(long long C, int threads) { return (int)((C + threads - 1) / threads); }
 
-int launch_propose(const EngineParams &p, long long c_first, long long c_end, cudaStream_t st) {
-    k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end);
+int launch_propose(const EngineParams &p, long long c_first, long long c_end, int order_slot, cudaStream_t st) {
+    if (!p.chain_local || p.buf.block_order == nullptr) order_slot = -1;
+    k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end, order_slot);
     return (int)cudaGetLastError();
 }
 int launch_corr_sums(const EngineParams *p, long long C, int target, int proposal, cudaStream_t st) {

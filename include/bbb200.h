@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define BBB_ABI_VERSION 2
+#define BBB_ABI_VERSION 3
+#define BBB_ORDER_BUCKETS 10
 
 #define BBB_MAX_SPACES 4
 #define BBB_MAX_PARAMS 8
@@ -181,6 +182,11 @@ typedef struct {
     const double *tape;      /* [C][tape_stride] */
     int64_t tape_stride;
     int64_t *tape_cursor;    /* [C] tape position (tape mode) / draws consumed in the step (Philox mode) */
+    /* chain-local step, optional (NULL: blocks take the chains in index order): scratch for the longest-first block
+     * order of the chain kernel -- the proposal kernel files every chain under one of BBB_ORDER_BUCKETS cost classes.
+     * [BBB_ORDER_BUCKETS][C] chain ids followed by [2][4][16] class counts; ZERO-INITIALISED by the caller.  The order
+     * never changes a result (chains do not interact inside a step), only when a chain's block is scheduled. */
+    int32_t *block_order;    /* [BBB_ORDER_BUCKETS * C + 128] */
 } bbb_buffers;
 
 typedef struct bbb_engine bbb_engine;
