@@ -34,6 +34,9 @@
 
 namespace bbb {
 
+#ifndef CS_MISFIT_U
+#define CS_MISFIT_U 4
+#endif
 #ifndef CS_AB_LIST
 #define CS_AB_LIST 1
 #endif
@@ -141,6 +144,43 @@ __device__ __forceinline__ int cs_smid() { int v; asm volatile("mov.u32 %0, %%sm
 #define CS_TL_G(i) do {} while (0)
 #define CS_TL_T(i, thr) do {} while (0)
 #endif
+
+// Native shared-memory atomics on 32-bit shared-window addresses (computed once per block): the generic-pointer
+// atomicAdd re-derives the window base in front of every atomic.
+// (predicated inside the asm statement: an `if` around it becomes a branch per atomic)
+__device__ __forceinline__ unsigned atoms_add_if(unsigned on, unsigned saddr, unsigned v) {
+    unsigned old = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+                 : "+r"(old) : "r"(saddr), "r"(v), "r"(on) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add_if(unsigned on, unsigned saddr, unsigned v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                 ::"r"(saddr), "r"(v), "r"(on) : "memory");
+}
+// Four entries of one column: the four low-word additions are issued back to back, the carries they return go into
+// the four high-word additions (adding zero leaves an untouched ray's planes zero, so nothing is tested per entry).
+__device__ __forceinline__ void fx_add4(unsigned lo_s, unsigned hi_s, const int (&r)[4], const double (&w)[4], double dlt,
+                                        double scale, int base_j, int len, int lane) {
+    unsigned xl[4], xh[4], old[4];
+    unsigned on[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        on[u] = base_j + 32 * u + lane < len ? 1u : 0u;
+        const long long v = __double2ll_rn(__dmul_rn(w[u], dlt) * scale);
+        xl[u] = (unsigned)v;
+        xh[u] = (unsigned)((unsigned long long)v >> 32);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        old[u] = atoms_add_if(on[u], lo_s + 4u * (unsigned)r[u], xl[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned carry = ((unsigned)(old[u] + xl[u]) < xl[u]) ? 1u : 0u;
+        reds_add_if(on[u], hi_s + 4u * (unsigned)r[u], xh[u] + carry);
+    }
+}
 
 template <typename IdxT>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
@@ -443,6 +483,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     const int32_t *cp0 = T.csc_colptr[0], *cp1 = T.csc_colptr[1], *cp2 = T.csc_colptr[2];
     const unsigned short *rw0 = T.csc_rows[0], *rw1 = T.csc_rows[1], *rw2 = T.csc_rows[2];
     const double *dt0 = T.csc_data[0], *dt1 = T.csc_data[1], *dt2 = T.csc_data[2];
+    const unsigned lo_s = (unsigned)__cvta_generic_to_shared(acc_lo), hi_s = (unsigned)__cvta_generic_to_shared(acc_hi);
     auto accumulate = [&](int tile) {
         for (int base = 0; base < n_list; base += CS_CHUNK) {
             const int e = base + tid;
@@ -495,17 +536,8 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
                             wb[u] = data_b[qb.j0 + jj];
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (base_j + 32 * u < qa.len) {
-                            const long long va = __double2ll_rn(__dmul_rn(wa[u], qa.dlt) * scale);
-                            if (va != 0) fx_add(acc_lo, acc_hi, ra[u], va);
-                        }
-                        if (base_j + 32 * u < qb.len) {
-                            const long long vb = __double2ll_rn(__dmul_rn(wb[u], qb.dlt) * scale);
-                            if (vb != 0) fx_add(acc_lo, acc_hi, rb[u], vb);
-                        }
-                    }
+                    if (base_j < qa.len) fx_add4(lo_s, hi_s, ra, wa, qa.dlt, scale, base_j, qa.len, lane);
+                    if (base_j < qb.len) fx_add4(lo_s, hi_s, rb, wb, qb.dlt, scale, base_j, qb.len, lane);
                 }
             }
             __syncthreads();
@@ -561,15 +593,16 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             }
         };
         if (pairs) {
-            for (int rb = 2 * tid; rb < nr; rb += 8 * CS_THREADS) {
-                double2 rr[4];
+            // CS_MISFIT_U 16-byte loads of the residual row in flight per thread (C3: the whole row in one round)
+            for (int rb = 2 * tid; rb < nr; rb += 2 * CS_MISFIT_U * CS_THREADS) {
+                double2 rr[CS_MISFIT_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < CS_MISFIT_U; ++u) {
                     const int r = rb + 2 * u * CS_THREADS;
                     rr[u] = r < nr ? *reinterpret_cast<const double2 *>(res + r0 + r) : make_double2(0.0, 0.0);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < CS_MISFIT_U; ++u) {
                     const int r = rb + 2 * u * CS_THREADS;
                     if (r >= nr) continue;
                     const uint2 lo2 = *reinterpret_cast<const uint2 *>(acc_lo + r), hi2 = *reinterpret_cast<const uint2 *>(acc_hi + r);
