@@ -44,6 +44,9 @@ struct bbb_engine {
     // that run on internal streams, so that one part's proposal kernel (a latency-bound kernel of one warp per chain)
     // and the tail of its chain kernel overlap the other parts' chain kernels
     int pipeline;  // number of parts (1 = off)
+    // programmatic dependent launch of the chain kernel behind the proposal kernel: 1 = single launches (default),
+    // 2 = also the parts of pipelined multi-iteration calls, 0 = off (BBB_DEPENDENT_LAUNCH)
+    int dependent_launch;
     int order_parity[4];  // per part: which set of block-order class counts the next proposal kernel counts into
     bool order_pending[4];  // a proposal kernel has filed its chains and the chain kernel has not consumed them yet
     cudaStream_t half_stream[4];
@@ -173,6 +176,10 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
         e->pipeline = pl != nullptr ? atoi(pl) : 4;
         if (e->pipeline < 1) e->pipeline = 1;
         if (e->pipeline > 4) e->pipeline = 4;
+    }
+    {
+        const char *dl = getenv("BBB_DEPENDENT_LAUNCH");
+        e->dependent_launch = dl != nullptr ? atoi(dl) : 1;
     }
     for (int h = 0; h < 4; ++h) e->half_stream[h] = nullptr;
     for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
@@ -441,7 +448,7 @@ static int run_chain_step(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
     int rc = launch_chain_step(e->host, 0, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
-                               idx_bytes_of(P, e->ray_t), e->order_pending[0] ? e->order_parity[0] * 4 : -1, st);
+                               idx_bytes_of(P, e->ray_t), e->order_pending[0] ? e->order_parity[0] * 4 : -1, e->dependent_launch >= 1, st);
     if (rc != 0) return rc;
     if (e->order_pending[0]) { e->order_parity[0] ^= 1; e->order_pending[0] = false; }
     bump_k_bound(e, 1);
@@ -476,7 +483,7 @@ static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st
             rc = launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, e->half_stream[h]);
             if (rc == 0)
                 rc = launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
-                                       idx_bytes_of(P, e->ray_t), e->order_parity[h] * 4 + h, e->half_stream[h]);
+                                       idx_bytes_of(P, e->ray_t), e->order_parity[h] * 4 + h, e->dependent_launch >= 2, e->half_stream[h]);
             e->order_parity[h] ^= 1;
         }
     }

@@ -192,6 +192,19 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     const bbb_space_spec &S = P.spaces[s];
     const long long C = B.n_chains;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    // Programmatic dependent launch: the proposal kernel releases its dependents as soon as it starts, so this block
+    // may be resident while the proposals are still being drawn.  Everything that does not read the proposal is done
+    // here, ahead of the dependency wait: zeroing the ray accumulators.
+    {
+        const int n_words = 2 * P.targets[t].csc_tile_rays;  // RT * 8 bytes is a multiple of 16
+        unsigned *acc = reinterpret_cast<unsigned *>(cs_smem);
+        for (int r = tid * 4; r < n_words; r += CS_THREADS * 4) {
+            if (r + 4 <= n_words) *reinterpret_cast<uint4 *>(acc + r) = make_uint4(0, 0, 0, 0);
+            else for (int q = r; q < n_words; ++q) acc[q] = 0;
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // longest-first block order (common.cuh): block b takes the b-th chain in cost-class order; class counts that do
     // not add up to the grid (a proposal kernel that ran twice, a caller that binds no order buffer) mean index order
     long long c = c_first + blockIdx.x;
@@ -241,7 +254,6 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     }
     if (tid == CS_THREADS - 1) finish_gather(ep, c, s_fin);  // thread 0 decides from these after the forward
 
-    extern __shared__ __align__(16) unsigned char cs_smem[];
     const int K = S.kmax, RT = T.csc_tile_rays, NT = T.csc_n_tiles, G = T.n_points, R = T.n_data;
     unsigned *acc_lo = reinterpret_cast<unsigned *>(cs_smem);
     unsigned *acc_hi = acc_lo + RT;
@@ -285,10 +297,6 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
         fo[j] = v;
         fmax = fmax > fabs(v) ? fmax : fabs(v);
         if (!(fabs(v) <= 1.79769313486231570815e308)) fmax = INFINITY;
-    }
-    for (int r = tid * 4; r < 2 * RT; r += CS_THREADS * 4) {  // RT * 8 bytes is a multiple of 16
-        if (r + 4 <= 2 * RT) *reinterpret_cast<uint4 *>(acc_lo + r) = make_uint4(0, 0, 0, 0);
-        else for (int q = r; q < 2 * RT; ++q) acc_lo[q] = 0;
     }
     if (tid == 0) { s_front = 0; s_back = 0; }
 #pragma unroll
@@ -696,19 +704,32 @@ extern "C" int bbb_debug_timeline_clear() {
 #endif
 
 int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, long long n_data, int K,
-                      int idx_bytes, int order_slot, cudaStream_t st) {
+                      int idx_bytes, int order_slot, bool dependent_launch, cudaStream_t st) {
     if (dev.buf.block_order == nullptr) order_slot = -1;
-    const long long C = c_end - c_first;
+    // programmatic dependent launch behind the proposal kernel of the same stream (see the kernel's prologue)
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(c_end - c_first));
+    cfg.blockDim = dim3(CS_THREADS);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = dependent_launch ? 1 : 0;
     const size_t smem = chain_step_smem(tile_rays, K, n_data);
     cudaError_t err;
     if (idx_bytes == 1) {
         err = cudaFuncSetAttribute(k_chain_step<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        k_chain_step<uint8_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t, c_first, order_slot);
+        cfg.dynamicSmemBytes = smem;
+        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint8_t>, dev, t, c_first, order_slot);
+        if (err != cudaSuccess) return (int)err;
     } else {
         err = cudaFuncSetAttribute(k_chain_step<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        k_chain_step<uint16_t><<<(unsigned)C, CS_THREADS, smem, st>>>(dev, t, c_first, order_slot);
+        cfg.dynamicSmemBytes = smem;
+        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint16_t>, dev, t, c_first, order_slot);
+        if (err != cudaSuccess) return (int)err;
     }
     return (int)cudaGetLastError();
 }

@@ -65,7 +65,7 @@ int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);
 // chain_kernels.cu
 long long chain_local_tile_rays(long long n_data, int kmax, long long n_points);
 int launch_chain_step(const EngineParams &host_params, long long c_first, long long c_end, int target, int tile_rays,
-                      long long n_data, int K, int idx_bytes, int order_slot, cudaStream_t stream);
+                      long long n_data, int K, int idx_bytes, int order_slot, bool dependent_launch, cudaStream_t stream);
 int launch_transpose_idx(const void *in, void *out, int idx_bytes, long long rows, long long cols, long long in_stride,
                          long long out_stride, cudaStream_t stream);
 int launch_residual_transpose(const double *dpred, double *res, long long R, long long C, const double *dobs,

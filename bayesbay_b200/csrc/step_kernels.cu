@@ -37,6 +37,8 @@ __device__ __forceinline__ int block_cost_class(const EngineParams &ep, long lon
 
 __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep, long long c_first, long long c_end,
                                                                 int order_slot) {
+    // the chain kernel behind this launch may become resident now (it waits for this grid before it reads a proposal)
+    asm volatile("griddepcontrol.launch_dependents;");
     const long long c = c_first + (long long)blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
     if (c >= c_end) return;
     Rng rng;
