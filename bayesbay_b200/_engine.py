@@ -11,6 +11,7 @@ temperature, iteration, counters).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -214,6 +215,12 @@ class Engine:
                         t.csc_rows[lvl] = self._const(rows.view(np.int16), np.int16).data_ptr()
                         t.csc_data[lvl] = self._const(cdat, np.float64).data_ptr()
                     t.csc_bound = levels[0][3]
+                    # bounding boxes of the 16-point groups (Morton order: compact blocks) for the rasteriser's pruning
+                    n_grp = (t.n_points + 15) // 16
+                    padded = np.concatenate([pts, np.repeat(pts[-1:], n_grp * 16 - t.n_points, axis=0)]).reshape(n_grp, 16, 2)
+                    box = np.stack([padded[:, :, 0].min(1), padded[:, :, 0].max(1), padded[:, :, 1].min(1), padded[:, :, 1].max(1)], 1)
+                    if not os.environ.get("BBB_NO_GROUP_BOX"):  # (developer switch: A/B of the pruning)
+                        t.group_box = self._const(box, np.float64).data_ptr()
             elif f["kind"] in ("lookup1d", "polynomial"):
                 t.param = f["param"]
                 x = np.asarray(f["x"], dtype=np.float64)

@@ -59,6 +59,7 @@ class TargetSpec(C.Structure):
         ("csc_tile_rays", C.c_int32), ("csc_n_tiles", C.c_int32), ("csc_n_levels", C.c_int32),
         ("csc_colptr", _vp * CSC_LEVELS), ("csc_rows", _vp * CSC_LEVELS), ("csc_data", _vp * CSC_LEVELS),
         ("csc_bound", C.c_double),
+        ("group_box", _vp),
     ]
 
 

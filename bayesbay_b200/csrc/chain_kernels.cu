@@ -66,6 +66,14 @@ struct IdxVec {
         for (int i = 0; i < (int)sizeof(IdxT); ++i) w[i] = reinterpret_cast<const uint4 *>(p)[i];
     }
     __device__ __forceinline__ int at(int q) const { return (int)reinterpret_cast<const IdxT *>(w)[q]; }
+    // all 16 indices equal
+    __device__ __forceinline__ bool uniform() const {
+        const unsigned x = w[0].x;
+        bool u = x == __funnelshift_l(x, x, 8 * (int)sizeof(IdxT)) && w[0].y == x && w[0].z == x && w[0].w == x;
+#pragma unroll
+        for (int i = 1; i < (int)sizeof(IdxT); ++i) u = u && w[i].x == x && w[i].y == x && w[i].z == x && w[i].w == x;
+        return u;
+    }
 };
 
 // multi-tile problems also keep a bitmap of the touched rays (one bit per ray of the target)
@@ -343,8 +351,31 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             for (int q = 0; q < CS_PTS; ++q)
                 if (g0 + q < G && wv.at(q) == rm) chg |= 1u << q;
         } else {
+            // Pruning: a group with ONE owner is decided from its bounding box.  d_new(g) - d_own(g) =
+            // |n|^2 - |o|^2 - 2 g.(n - o) is affine in the point g, so its minimum over the box is taken at a corner;
+            // when that minimum is positive by a margin far above any rounding of the per-point test (1e-9 of the
+            // squared coordinates against 1e-16), no point of the group can be captured by the inserted cell.
+            bool pruned = false;
+            if (ins >= 0 && T.group_box != nullptr && g0 + CS_PTS <= G && wv.uniform()) {
+                const int o0 = wv.at(0);
+                if (rm >= 0 && o0 == rm) {
+                    scn = 0xFFFFu;  // the whole group lost its owner
+                    pruned = true;
+                } else {
+                    const double2 bx = __ldg(reinterpret_cast<const double2 *>(T.group_box) + 2 * (g0 >> 4));
+                    const double2 by = __ldg(reinterpret_cast<const double2 *>(T.group_box) + 2 * (g0 >> 4) + 1);
+                    int mm = o0 - ((rm >= 0 && o0 > rm) ? 1 : 0);
+                    mm += (mm >= ins) ? 1 : 0;
+                    const double ox = sx[mm], oy = sy[mm];
+                    const double ddx = nx - ox, ddy = ny - oy;
+                    const double gmax = (ddx > 0.0 ? bx.y : bx.x) * ddx + (ddy > 0.0 ? by.y : by.x) * ddy;
+                    const double nn = nx * nx + ny * ny, oo = ox * ox + oy * oy;
+                    const double ax = ::fmax(fabs(bx.x), fabs(bx.y)), ay = ::fmax(fabs(by.x), fabs(by.y));
+                    pruned = (nn - oo) - 2.0 * gmax > 1e-9 * (nn + oo + ax * ax + ay * ay);
+                }
+            }
 #pragma unroll
-            for (int qd = 0; qd < CS_PTS / 4; ++qd) {
+            for (int qd = 0; qd < (pruned ? 0 : CS_PTS / 4); ++qd) {
                 // the 4 points of a quad (a 2x2 block of the grid) mostly share their owner: its site is fetched
                 // once per quad (the owners' sites are a data-dependent, bank-conflicting shared-memory gather)
                 const int oq = wv.at(4 * qd);

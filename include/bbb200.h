@@ -128,6 +128,10 @@ typedef struct {
     const double *csc_data[BBB_CSC_LEVELS];    /* device [nnz_l] */
     double csc_bound;          /* max over rays of sum_g |data|: bounds any change of d_pred per unit change of the
                                 * cell function; scales the fixed-point ray accumulators */
+    /* optional (NULL: none): bounding boxes (xmin, xmax, ymin, ymax) of the aligned groups of 16 consecutive grid
+     * points.  The change-local rasterisation skips a group that has one owner when the inserted cell cannot be
+     * nearer than that owner anywhere in the group's box (d_new - d_own is affine in the point). */
+    const double *group_box;   /* device [ceil(n_points / 16)][4] */
 } bbb_target_spec;
 
 typedef struct {
