@@ -317,7 +317,8 @@ class Engine:
         b.n_proposed, b.n_accepted = _ptr(self.n_proposed), _ptr(self.n_accepted)
         b.tape_cursor = _ptr(self.draw_cursor)
         # longest-first block order of the chain kernel (scratch of the chain-local step; must start zeroed)
-        self.block_order = z((L.ORDER_BUCKETS * Cn + 128,), i32) if any(x is not None for x in self.idx_cm) else None
+        self.block_order = (z((L.ORDER_BUCKETS * Cn + 128,), i32)
+                            if any(x is not None for x in self.idx_cm) and not os.environ.get("BBB_NO_BLOCK_ORDER") else None)
         b.block_order = _ptr(self.block_order)
         self.tape = None
         if tape is not None:

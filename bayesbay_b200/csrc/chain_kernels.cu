@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
 #endif
 
     __shared__ int s_front, s_back, s_accept;
+    __shared__ int s_wtot[CS_WARPS];
     __shared__ double s_red[CS_WARPS];
     __shared__ FinishIn s_fin;
     __shared__ FinishPre s_pre;
@@ -592,6 +593,11 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     // keep their zeros), so an accepted proposal is committed with stores only.
     double *res = B.res[t] + c * (long long)R;
     double dphi = 0.0;
+    // single-tile problems whose planes can be read four rays at a time: the touched rays are first compacted into a
+    // list (the idle `prep` area), so that the arithmetic below runs on dense warps
+    constexpr int CS_TOUCH_SMEM = CS_CHUNK * (int)sizeof(PrepEntry) / 2;
+    unsigned short *touch = reinterpret_cast<unsigned short *>(prep);
+    int n_touch = -1;  // >= 0: `touch` lists the touched rays of the (only) tile
     for (int tile = 0; tile < NT; ++tile) {
         if (tile > 0) zero_acc();
         accumulate(tile);
@@ -631,7 +637,68 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
                 acc_hi[r] = (unsigned)__double2hiint(nv);
             }
         };
-        if (pairs) {
+        if (NT == 1 && (RT & 3) == 0 && RT <= 8 * 4 * CS_THREADS) {
+            // (a) every thread scans 4 consecutive rays per round, bit (4 i + j) of m: ray 4 tid + 2048 i + j touched
+            unsigned m = 0;
+#pragma unroll 8
+            for (int i = 0; i < 8; ++i) {
+                const int r4 = 4 * tid + 4 * CS_THREADS * i;
+                if (r4 < nr) {
+                    const uint4 lo4 = *reinterpret_cast<const uint4 *>(acc_lo + r4), hi4 = *reinterpret_cast<const uint4 *>(acc_hi + r4);
+                    m |= (((lo4.x | hi4.x) != 0 ? 1u : 0u) | ((lo4.y | hi4.y) != 0 ? 2u : 0u) | ((lo4.z | hi4.z) != 0 ? 4u : 0u) |
+                          ((lo4.w | hi4.w) != 0 ? 8u : 0u)) << (4 * i);
+                }
+            }
+            // (b) list positions from a scan over (warp, lane): the order of the list -- and with it the order of the
+            // misfit sum -- does not depend on thread timing
+            const int cnt = __popc(m);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_wtot[warp] = incl;
+            __syncthreads();
+            int pos = incl - cnt;
+            n_touch = 0;
+#pragma unroll
+            for (int w = 0; w < CS_WARPS; ++w) {
+                const int wt = s_wtot[w];
+                if (w < warp) pos += wt;
+                n_touch += wt;
+            }
+            if (n_touch <= CS_TOUCH_SMEM) {
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    touch[pos++] = (unsigned short)(4 * tid + 4 * CS_THREADS * (b >> 2) + (b & 3));
+                }
+                __syncthreads();
+                // (c) the touched rays, four per thread in flight
+                for (int i0 = tid; i0 < n_touch; i0 += 4 * CS_THREADS) {
+                    int rq[4];
+                    double rr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * CS_THREADS;
+                        rq[u] = i < n_touch ? (int)touch[i] : -1;
+                        rr[u] = rq[u] >= 0 ? res[r0 + rq[u]] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (rq[u] >= 0) one_ray(rq[u], rr[u]);
+                }
+            } else {  // (more touched rays than the list holds: every thread handles the rays it scanned)
+                n_touch = -1;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int r = 4 * tid + 4 * CS_THREADS * (b >> 2) + (b & 3);
+                    one_ray(r, res[r0 + r]);
+                }
+            }
+        } else if (pairs) {
             // CS_MISFIT_U 16-byte loads of the residual row in flight per thread (C3: the whole row in one round)
             for (int rb = 2 * tid; rb < nr; rb += 2 * CS_MISFIT_U * CS_THREADS) {
                 double2 rr[CS_MISFIT_U];
@@ -684,7 +751,12 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     CS_TL_G(17);
     if (!s_accept) return;
 
-    if (NT == 1) {
+    if (NT == 1 && n_touch >= 0) {
+        for (int i = tid; i < n_touch; i += CS_THREADS) {
+            const int r = (int)touch[i];
+            res[r] = __hiloint2double((int)acc_hi[r], (int)acc_lo[r]);
+        }
+    } else if (NT == 1) {
         for (int r = tid; r < R; r += CS_THREADS) {
             const unsigned lo = acc_lo[r], hi = acc_hi[r];
             if ((lo | hi) != 0) res[r] = __hiloint2double((int)hi, (int)lo);

@@ -81,3 +81,11 @@ for mv, nm in enumerate(["birth", "death", "values", "sites"]):
     for lo, hi in ((0, 20), (20, 35), (35, 50), (50, 70), (70, 100), (100, 201)):
         mm = m & (kk >= lo) & (kk < hi)
         if mm.sum() > 5: print("     k in [%3d,%3d): n %4d mean %.1f p90 %.1f" % (lo, hi, mm.sum(), dur[mm].mean(), np.percentile(dur[mm], 90)))
+
+# phase durations by move (us, medians)
+print("phase medians by move: entry, raster, rederive, prep, accum, misfit, decide | decision-prep end, n_list")
+for mv, nm in enumerate(["birth", "death", "values", "sites"]):
+    m = inner == mv
+    if m.sum() < 10: continue
+    dd = np.diff(tt[m][:, :8], axis=1) / mhz
+    print("%-7s" % nm, " ".join("%6.2f" % np.median(dd[:, i]) for i in range(7)), "| %6.2f %5.0f" % (np.median((tt[m, 9] - tt[m, 0]) / mhz), np.median(tt[m, 12])))
