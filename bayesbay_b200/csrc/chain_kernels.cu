@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     CS_TL(1);
     fmax = 0.0;
     for (int w = 0; w < CS_WARPS; ++w) fmax = fmax > s_red[w] ? fmax : s_red[w];
-    __syncthreads();  // s_red is reused below
+    // (s_red is next written by the misfit sum, several barriers from here)
     // fixed-point scale: |sum of the terms of one ray| <= csc_bound * 2 fmax < 2^e  ->  quantum 2^(e - 61)
     const bool finite = fmax <= 1.79769313486231570815e308 && T.csc_bound * (2.0 * fmax) <= 1.79769313486231570815e308;
     int e2 = 0;
