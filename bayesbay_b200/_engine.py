@@ -518,6 +518,60 @@ class Engine:
         L.check(self.lib.bbb_engine_unpack_states(self._handle, self._kb(kb), _ptr(image), self._stream))
         self._steps_since_sync = 1 << 30
 
+    # ------------------------------------------------------------------ hosted step (chains held by the caller)
+    def hosted_parts(self):
+        """First chains of the parts of a hosted image (``len - 1`` parts; see include/bbb200.h)."""
+        first = (C.c_int64 * 5)()
+        n = int(self.lib.bbb_engine_hosted_parts(self._handle, first))
+        if n < 1:
+            raise RuntimeError("bbb_engine_hosted_parts failed")
+        return [int(first[h]) for h in range(n + 1)]
+
+    def pack_states_hosted(self, kb, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Current states as a HOSTED image: the parts' images back to back (device buffer of int64 words)."""
+        n = self.state_image_bytes(kb) // 8
+        rows = n // self.C
+        if out is None:
+            out = torch.empty((n,), dtype=torch.int64, device=self.device)
+        first = self.hosted_parts()
+        for c0, c1 in zip(first[:-1], first[1:]):
+            if c1 > c0:
+                L.check(self.lib.bbb_engine_pack_states_range(self._handle, self._kb(kb), c0, c1, _ptr(out[rows * c0:]), self._stream))
+        return out[:n]
+
+    def step_hosted(self, kb_in, host_in: torch.Tensor, host_out: torch.Tensor, stage: torch.Tensor, out: torch.Tensor):
+        """Enqueue ONE iteration on the chains of the pinned hosted image ``host_in`` (``kb_in`` cell rows); the new
+        states arrive in ``host_out`` with the returned number of cell rows once :meth:`step_hosted_wait` returned."""
+        if not (host_in.is_pinned() and host_out.is_pinned()):
+            raise ValueError("hosted images must live in pinned host memory")
+        if self._steps_since_sync >= self.K_BOUND_RESYNC_LOCAL:
+            self.sync_k_bound()
+        key = (tuple(kb_in) if not np.isscalar(kb_in) else int(kb_in), host_in.numel(), host_out.numel(), stage.numel(), out.numel())
+        cached = self._hosted_args.get(key) if hasattr(self, "_hosted_args") else None
+        if cached is None:
+            if not hasattr(self, "_hosted_args"):
+                self._hosted_args = {}
+            kb_c = self._kb(kb_in)
+            need_in = self.state_image_bytes(kb_c) // 8
+            kb_cap = self._kb([min(int(v) + 8, sp["kmax"]) for v, sp in zip(kb_c, self.spec["spaces"])])
+            need_out = self.state_image_bytes(kb_cap) // 8
+            if host_in.numel() < need_in or stage.numel() < need_in or host_out.numel() < need_out or out.numel() < need_out:
+                raise ValueError("hosted image buffers too small")
+            cached = self._hosted_args[key] = (kb_c, (C.c_int32 * len(self.spec["spaces"]))())
+        kb_in, kb_out = cached
+        L.check(self.lib.bbb_engine_step_hosted(self._handle, kb_in, C.c_void_p(host_in.data_ptr()), kb_out,
+                                                C.c_void_p(host_out.data_ptr()), _ptr(stage), _ptr(out), self._stream))
+        self._steps_since_sync += 1
+        return [int(v) for v in kb_out]
+
+    def step_hosted_wait(self) -> int:
+        """Wait for the hosted step; returns the number of parts whose caches had to be re-derived (0: fast path)."""
+        n = C.c_int32(0)
+        L.check(self.lib.bbb_engine_step_hosted_wait(self._handle, C.byref(n), self._stream))
+        if n.value:
+            self._steps_since_sync = 1 << 30
+        return int(n.value)
+
     # ------------------------------------------------------------------ checkpoint / resume
     def _mutable(self):
         named = {"temperature": self.temperature, "iteration": self.iteration, "n_proposed": self.n_proposed,

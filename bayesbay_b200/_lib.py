@@ -14,7 +14,7 @@ MAX_PARAMS = 8
 MAX_TARGETS = 4
 MAX_LINEAR_PARAMS = 16
 CSC_LEVELS = 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 ORDER_BUCKETS = 10
 
 SPACE_PLAIN, SPACE_VORONOI1D, SPACE_VORONOI2D = 0, 1, 2
@@ -114,6 +114,10 @@ SYMBOLS = {
     "bbb_engine_pack_states": (C.c_int, [_vp, C.POINTER(_i32), _vp, _vp]),
     "bbb_engine_compare_states": (C.c_int, [_vp, C.POINTER(_i32), _vp, _vp, _vp]),
     "bbb_engine_unpack_states": (C.c_int, [_vp, C.POINTER(_i32), _vp, _vp]),
+    "bbb_engine_pack_states_range": (C.c_int, [_vp, C.POINTER(_i32), _i64, _i64, _vp, _vp]),
+    "bbb_engine_hosted_parts": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "bbb_engine_step_hosted": (C.c_int, [_vp, C.POINTER(_i32), _vp, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
+    "bbb_engine_step_hosted_wait": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
     "bbb_engine_dpred": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "bbb_engine_misfit_logdet": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bbb_pt_swap": (C.c_int, [_vp, _i64, _u64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -51,7 +51,43 @@ struct bbb_engine {
     bool order_pending[4];  // a proposal kernel has filed its chains and the chain kernel has not consumed them yet
     cudaStream_t half_stream[4];
     cudaEvent_t ev_fork, ev_join[4];
+    // hosted step (bbb_engine_step_hosted / _wait): per-part "uploaded states differ" words on the device and their
+    // pinned host copy, and what the pending call needs should a part have to be redone
+    int32_t *hosted_flag_dev, *hosted_flag_host;
+    struct {
+        bool pending;
+        int32_t kb_in[BBB_MAX_SPACES], kb_out[BBB_MAX_SPACES];
+        void *host_out, *dev_stage, *dev_out;
+    } hosted;
+    // the hosted step is replayed from CUDA graphs (one launch instead of ~40 driver calls per iteration): captured on
+    // `cap_stream` the first time a combination of image sizes, buffers and block-order parities is seen
+    struct HostedGraph {
+        bool used;
+        int32_t kb_in[BBB_MAX_SPACES], kb_out[BBB_MAX_SPACES];
+        const void *host_in;
+        void *host_out, *dev_stage, *dev_out;
+        int parity;
+        cudaGraph_t graph;
+        cudaGraphExec_t exec;
+    } hosted_graph[16];
+    int hosted_graph_next;
+    int hosted_graphs;  // 1: replay from graphs (default), 0: enqueue every call (BBB_HOSTED_GRAPH=0, or capture failed)
+    cudaStream_t cap_stream, copy_stream;
+    cudaEvent_t ev_h2d[4], ev_hjoin[4], ev_hfork;
+    // parts of the hosted step (BBB_HOSTED_PARTS, default 2) and their streams
+    int hosted_np;
+    cudaStream_t hosted_stream[4];
 };
+
+// the cached graphs of the hosted step hold the engine parameters BY VALUE: whatever changes them drops the graphs
+static void hosted_graphs_drop(bbb_engine *e) {
+    for (auto &g : e->hosted_graph)
+        if (g.used) {
+            cudaGraphExecDestroy(g.exec);
+            cudaGraphDestroy(g.graph);
+            g.used = false;
+        }
+}
 
 extern "C" {
 
@@ -176,6 +212,10 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
         e->pipeline = pl != nullptr ? atoi(pl) : 4;
         if (e->pipeline < 1) e->pipeline = 1;
         if (e->pipeline > 4) e->pipeline = 4;
+        const char *hp = getenv("BBB_HOSTED_PARTS");
+        e->hosted_np = hp != nullptr ? atoi(hp) : (e->pipeline < 2 ? e->pipeline : 2);
+        if (e->hosted_np < 1) e->hosted_np = 1;
+        if (e->hosted_np > 4) e->hosted_np = 4;
     }
     {
         const char *dl = getenv("BBB_DEPENDENT_LAUNCH");
@@ -219,6 +259,7 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
         return fail(BBB_ERR_SHAPE, "a per-chain scalar buffer is missing");
     if (b->tape && b->tape_stride < 1) return fail(BBB_ERR_SHAPE, "tape_stride < 1");
     e->host.buf = *b;
+    hosted_graphs_drop(e);
     for (int t = 0; t < P.n_targets; ++t) {
         e->host.n_partial[t] = 0;
         if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
@@ -263,6 +304,17 @@ void bbb_engine_destroy(bbb_engine *e) {
         }
         cudaEventDestroy(e->ev_fork);
     }
+    hosted_graphs_drop(e);
+    if (e->cap_stream) {
+        cudaStreamDestroy(e->cap_stream);
+        cudaStreamDestroy(e->copy_stream);
+        for (auto &ev : e->ev_h2d) cudaEventDestroy(ev);
+        for (auto &ev : e->ev_hjoin) cudaEventDestroy(ev);
+        cudaEventDestroy(e->ev_hfork);
+        for (auto &st : e->hosted_stream) cudaStreamDestroy(st);
+    }
+    if (e->hosted_flag_dev) cudaFree(e->hosted_flag_dev);
+    if (e->hosted_flag_host) cudaFreeHost(e->hosted_flag_host);
     cudaFree(e->dev);
     delete e;
 }
@@ -315,7 +367,7 @@ static int run_propose(bbb_engine *e, cudaStream_t st) {
     const long long C = e->host.buf.n_chains;
     (void)P;
     e->order_pending[0] = true;
-    return launch_propose(e->host, 0, C, e->order_parity[0] * 4, st);  // the proposal warps also write the proposed slots
+    return launch_propose(e->host, 0, C, e->order_parity[0] * 4, nullptr, st);  // the proposal warps also write the proposed slots
 }
 
 static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool write_partial, cudaStream_t st) {
@@ -357,6 +409,7 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
     if (write_partial && a.n_groups != e->host.n_partial[t]) {
         // the accept stage sums partial[0 .. n_partial): keep the device copy in step (stream ordered)
         e->host.n_partial[t] = a.n_groups;
+        hosted_graphs_drop(e);
         int rc = (int)cudaMemcpyAsync(&e->dev->n_partial[t], &e->host.n_partial[t], sizeof(int), cudaMemcpyHostToDevice, st);
         if (rc != 0) return rc;
     }
@@ -448,13 +501,32 @@ static int run_chain_step(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
     int rc = launch_chain_step(e->host, 0, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
-                               idx_bytes_of(P, e->ray_t), e->order_pending[0] ? e->order_parity[0] * 4 : -1, e->dependent_launch >= 1, st);
+                               idx_bytes_of(P, e->ray_t), e->order_pending[0] ? e->order_parity[0] * 4 : -1, e->dependent_launch >= 1, nullptr, st);
     if (rc != 0) return rc;
     if (e->order_pending[0]) { e->order_parity[0] ^= 1; e->order_pending[0] = false; }
     bump_k_bound(e, 1);
     ++e->steps_since_resync;
     if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) rc = chain_local_from_scratch(e, false, st);
     return rc;
+}
+
+// parts of the chain set (whole proposal blocks) and their internal streams
+static long long hosted_part_chains(const bbb_engine *e) {
+    const long long C = e->host.buf.n_chains;
+    return ((C + e->hosted_np - 1) / e->hosted_np + 3) & ~3LL;
+}
+static long long part_chains(const bbb_engine *e) {
+    const long long C = e->host.buf.n_chains;
+    return ((C + e->pipeline - 1) / e->pipeline + 3) & ~3LL;
+}
+static int part_streams(bbb_engine *e) {
+    if (e->half_stream[0] != nullptr) return 0;
+    for (int h = 0; h < e->pipeline; ++h) {
+        int rc = (int)cudaStreamCreateWithFlags(&e->half_stream[h], cudaStreamNonBlocking);
+        if (rc == 0) rc = (int)cudaEventCreateWithFlags(&e->ev_join[h], cudaEventDisableTiming);
+        if (rc != 0) return rc;
+    }
+    return (int)cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
 }
 
 // n chain-local iterations of all chains, the parts of the chain set on the engine's internal streams (chains never
@@ -464,26 +536,19 @@ static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st
     const bbb_target_spec &T = P.targets[e->ray_t];
     const long long C = e->host.buf.n_chains;
     const int NP = e->pipeline;
-    const long long part = ((C + NP - 1) / NP + 3) & ~3LL;  // whole proposal blocks
-    if (e->half_stream[0] == nullptr) {
-        for (int h = 0; h < NP; ++h) {
-            int rc = (int)cudaStreamCreateWithFlags(&e->half_stream[h], cudaStreamNonBlocking);
-            if (rc == 0) rc = (int)cudaEventCreateWithFlags(&e->ev_join[h], cudaEventDisableTiming);
-            if (rc != 0) return rc;
-        }
-        int rc = (int)cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
-        if (rc != 0) return rc;
-    }
-    int rc = (int)cudaEventRecord(e->ev_fork, st);
+    const long long part = part_chains(e);
+    int rc = part_streams(e);
+    if (rc != 0) return rc;
+    rc = (int)cudaEventRecord(e->ev_fork, st);
     for (int h = 0; h < NP && rc == 0; ++h) rc = (int)cudaStreamWaitEvent(e->half_stream[h], e->ev_fork, 0);
     for (long long it = 0; it < n && rc == 0; ++it) {
         for (int h = 0; h < NP && rc == 0; ++h) {
             const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
             if (c0 >= c1) continue;
-            rc = launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, e->half_stream[h]);
+            rc = launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, nullptr, e->half_stream[h]);
             if (rc == 0)
                 rc = launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
-                                       idx_bytes_of(P, e->ray_t), e->order_parity[h] * 4 + h, e->dependent_launch >= 2, e->half_stream[h]);
+                                       idx_bytes_of(P, e->ray_t), e->order_parity[h] * 4 + h, e->dependent_launch >= 2, nullptr, e->half_stream[h]);
             e->order_parity[h] ^= 1;
         }
     }
@@ -592,6 +657,7 @@ int bbb_engine_set_annealing(bbb_engine *e, double temperature_start, double coo
                              int64_t burnin_iterations) {
     NEED_BOUND(e);
     if (temperature_start < 0 || cooling_iterations < 0 || burnin_iterations < 0) return fail(BBB_ERR_INVALID, "negative annealing parameter");
+    hosted_graphs_drop(e);
     e->host.anneal.enabled = temperature_start > 0 ? 1 : 0;
     e->host.anneal.t0 = temperature_start;
     e->host.anneal.rate = cooling_rate;
@@ -628,7 +694,7 @@ int bbb_engine_pack_states(bbb_engine *e, const int32_t *kb, void *image, void *
     NEED_BOUND(e);
     if (int rc = check_kb(e, kb)) return rc;
     if (!image) return fail(BBB_ERR_INVALID, "image is NULL");
-    CU(launch_state_image(e->host, 0, kb, image, nullptr, (cudaStream_t)stream));
+    CU(launch_state_image(e->host, 0, kb, image, nullptr, 0, e->host.buf.n_chains, (cudaStream_t)stream));
     return BBB_OK;
 }
 
@@ -636,7 +702,7 @@ int bbb_engine_compare_states(bbb_engine *e, const int32_t *kb, const void *imag
     NEED_BOUND(e);
     if (int rc = check_kb(e, kb)) return rc;
     if (!image || !differ) return fail(BBB_ERR_INVALID, "NULL argument");
-    CU(launch_state_image(e->host, 1, kb, const_cast<void *>(image), differ, (cudaStream_t)stream));
+    CU(launch_state_image(e->host, 1, kb, const_cast<void *>(image), differ, 0, e->host.buf.n_chains, (cudaStream_t)stream));
     return BBB_OK;
 }
 
@@ -644,8 +710,268 @@ int bbb_engine_unpack_states(bbb_engine *e, const int32_t *kb, const void *image
     NEED_BOUND(e);
     if (int rc = check_kb(e, kb)) return rc;
     if (!image) return fail(BBB_ERR_INVALID, "image is NULL");
-    CU(launch_state_image(e->host, 2, kb, const_cast<void *>(image), nullptr, (cudaStream_t)stream));
+    CU(launch_state_image(e->host, 2, kb, const_cast<void *>(image), nullptr, 0, e->host.buf.n_chains, (cudaStream_t)stream));
     return bbb_engine_refresh(e, stream);
+}
+
+int bbb_engine_pack_states_range(bbb_engine *e, const int32_t *kb, int64_t c_first, int64_t c_end, void *image, void *stream) {
+    NEED_BOUND(e);
+    if (int rc = check_kb(e, kb)) return rc;
+    if (!image) return fail(BBB_ERR_INVALID, "image is NULL");
+    if (c_first < 0 || c_end < c_first || c_end > e->host.buf.n_chains) return fail(BBB_ERR_INVALID, "chain range");
+    CU(launch_state_image(e->host, 0, kb, image, nullptr, c_first, c_end, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_engine_hosted_parts(bbb_engine *e, int64_t *first_chain) {
+    if (!e || !e->bound || !first_chain) return -1;
+    const long long C = e->host.buf.n_chains, part = hosted_part_chains(e);
+    for (int h = 0; h <= e->hosted_np; ++h) first_chain[h] = h * part < C ? h * part : C;
+    return e->hosted_np;
+}
+
+// row of the image that holds k of space s
+static long long image_k_row(const bbb_problem_spec &P, const int32_t *kb, int s) {
+    long long row = 0;
+    for (int q = 0; q < s; ++q) row += 1 + (long long)(P.spaces[q].ndim + P.spaces[q].n_params) * kb[q];
+    return row;
+}
+
+// Developer trace (BBB_HOSTED_TRACE=1, implies no graphs): timed events behind every operation of a hosted step,
+// printed by the wait as microseconds after the fork.
+static cudaEvent_t g_trace_ev[4][8], g_trace_fork;
+static bool g_trace_on = false, g_trace_init = false;
+static void trace_mark(int h, int i, cudaStream_t s) {
+    if (g_trace_on) cudaEventRecord(g_trace_ev[h][i], s);
+}
+
+// everything one hosted step puts on the device, from `st` through the parts' streams and back into `st`
+// (does not touch the engine's host-side bookkeeping: it is also what a graph capture records)
+#define ENQ(expr)                      \
+    do {                               \
+        int _e = (int)(expr);          \
+        if (_e != 0) return _e;        \
+    } while (0)
+static int hosted_enqueue(bbb_engine *e, const int32_t *kb_in, const void *host_in, const int32_t *kb_out, void *host_out,
+                          void *dev_stage, void *dev_out, cudaStream_t st) {
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_target_spec &T = P.targets[e->ray_t];
+    const long long C = e->host.buf.n_chains, part = hosted_part_chains(e);
+    const int NP = e->hosted_np;
+    const long long rows_in = state_image_rows(e->host, kb_in);
+    const long long *in_words = reinterpret_cast<const long long *>(host_in);
+    const long long rows_out = state_image_rows(e->host, kb_out);
+    ENQ(cudaMemsetAsync(e->hosted_flag_dev, 0, 4 * sizeof(int32_t), st));
+    if (g_trace_on) cudaEventRecord(g_trace_fork, st);
+    ENQ(cudaEventRecord(e->ev_hfork, st));
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(dev_stage), *out = reinterpret_cast<unsigned long long *>(dev_out);
+    // Uploads: all parts back to back on the copy stream (they share one copy engine anyway).
+    ENQ(cudaStreamWaitEvent(e->copy_stream, e->ev_hfork, 0));
+    for (int h = 0; h < NP; ++h) {
+        const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
+        if (c0 >= c1) continue;
+        const long long in_off = rows_in * c0;
+        ENQ(cudaMemcpyAsync(stage + in_off, in_words + in_off, (size_t)(rows_in * (c1 - c0)) * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        ENQ(cudaEventRecord(e->ev_h2d[h], e->copy_stream));
+    }
+    // Counter-based generators make the proposal a pure function of (resident state, iteration, chain): it is drawn
+    // SPECULATIVELY while the part's upload is in flight; should the uploaded states differ, the chain kernel is a
+    // no-op and the wait proposes again from the written states.  Tape-driven engines (tests) consume their tape, so
+    // there the proposal waits for the comparison and is guarded like the chain kernel.
+    const bool speculative = e->host.buf.tape == nullptr;
+    for (int h = 0; h < NP; ++h) {
+        const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
+        if (c0 >= c1) continue;
+        cudaStream_t hs = e->hosted_stream[h];
+        const long long n_c = c1 - c0, in_off = rows_in * c0, out_off = rows_out * c0;
+        ENQ(cudaStreamWaitEvent(hs, e->ev_hfork, 0));
+        trace_mark(h, 0, hs);
+        if (speculative) ENQ(launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, nullptr, hs));
+        trace_mark(h, 1, hs);
+        ENQ(cudaStreamWaitEvent(hs, e->ev_h2d[h], 0));
+        trace_mark(h, 2, hs);
+        ENQ(launch_state_image(e->host, 1, kb_in, stage + in_off, e->hosted_flag_dev + h, c0, c1, hs));
+        if (!speculative) ENQ(launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, e->hosted_flag_dev + h, hs));
+        trace_mark(h, 3, hs);
+        ENQ(launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax, idx_bytes_of(P, e->ray_t),
+                              e->order_parity[h] * 4 + h, !speculative && e->dependent_launch >= 1, e->hosted_flag_dev + h, hs));
+        trace_mark(h, 4, hs);
+        ENQ(launch_state_image(e->host, 0, kb_out, out + out_off, nullptr, c0, c1, hs));
+        trace_mark(h, 5, hs);
+        ENQ(cudaMemcpyAsync(reinterpret_cast<unsigned long long *>(host_out) + out_off, out + out_off, (size_t)(rows_out * n_c) * 8,
+                            cudaMemcpyDeviceToHost, hs));
+        trace_mark(h, 6, hs);
+        ENQ(cudaEventRecord(e->ev_hjoin[h], hs));
+        ENQ(cudaStreamWaitEvent(st, e->ev_hjoin[h], 0));
+    }
+    ENQ(cudaMemcpyAsync(e->hosted_flag_host, e->hosted_flag_dev, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+#undef ENQ
+
+int bbb_engine_step_hosted(bbb_engine *e, const int32_t *kb_in, const void *host_in, int32_t *kb_out, void *host_out,
+                           void *dev_stage, void *dev_out, void *stream) {
+    NEED_BOUND(e);
+    if (!e->host.chain_local) return fail(BBB_ERR_UNSUPPORTED, "the hosted step needs a chain-local engine (2-D ray target)");
+    if (e->hosted.pending) return fail(BBB_ERR_INVALID, "the previous hosted step was not waited for (bbb_engine_step_hosted_wait)");
+    if (int rc = check_kb(e, kb_in)) return rc;
+    if (!host_in || !host_out || !kb_out || !dev_stage || !dev_out) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (host_in == host_out || dev_stage == dev_out) return fail(BBB_ERR_INVALID, "in and out images must be different buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bbb_problem_spec &P = e->host.spec;
+    const long long C = e->host.buf.n_chains, part = hosted_part_chains(e);
+    const int NP = e->hosted_np;
+    const long long rows_in = state_image_rows(e->host, kb_in);
+    // rows of the downloaded image: the largest k of the uploaded chains plus the cell one step can add
+    const long long *in_words = reinterpret_cast<const long long *>(host_in);
+    for (int s = 0; s < P.n_spaces; ++s) {
+        const long long krow = image_k_row(P, kb_in, s);
+        long long kmax_seen = 1;
+        for (int h = 0; h < NP; ++h) {
+            const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
+            const long long *kr = in_words + rows_in * c0 + krow * (c1 - c0);
+            for (long long lc = 0; lc < c1 - c0; ++lc) kmax_seen = kr[lc] > kmax_seen ? kr[lc] : kmax_seen;
+        }
+        if (kmax_seen > kb_in[s]) return fail(BBB_ERR_INVALID, "space %d: the image holds k = %lld > kb = %d", s, kmax_seen, kb_in[s]);
+        // (a multiple of 8, so that the image sizes -- and with them the captured graphs -- change rarely)
+        const long long kb = P.spaces[s].trans_d ? ((kmax_seen + 1 + 7) & ~7LL) : kmax_seen;
+        kb_out[s] = (int32_t)(kb < P.spaces[s].kmax ? kb : P.spaces[s].kmax);
+    }
+    if (e->hosted_flag_dev == nullptr) {
+        CU(cudaMalloc(&e->hosted_flag_dev, 4 * sizeof(int32_t)));
+        CU(cudaHostAlloc(&e->hosted_flag_host, 4 * sizeof(int32_t), cudaHostAllocDefault));
+        CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (auto &ev : e->ev_h2d) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto &ev : e->ev_hjoin) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->ev_hfork, cudaEventDisableTiming));
+        for (auto &hs : e->hosted_stream) CU(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
+        const char *hg = getenv("BBB_HOSTED_GRAPH");
+        e->hosted_graphs = (hg != nullptr && atoi(hg) == 0) ? 0 : 1;
+        if (const char *tr = getenv("BBB_HOSTED_TRACE")) {
+            if (atoi(tr) != 0 && !g_trace_init) {
+                for (auto &row : g_trace_ev)
+                    for (auto &ev : row) cudaEventCreate(&ev);
+                cudaEventCreate(&g_trace_fork);
+                g_trace_init = g_trace_on = true;
+            }
+            if (g_trace_on) e->hosted_graphs = 0;
+        }
+    }
+    int parity = 0;
+    for (int h = 0; h < NP; ++h) parity |= e->order_parity[h] << h;
+    bool launched = false;
+    if (e->hosted_graphs) {
+        bbb_engine::HostedGraph *g = nullptr;
+        for (auto &c : e->hosted_graph) {
+            if (!c.used || c.host_in != host_in || c.host_out != host_out || c.dev_stage != dev_stage || c.dev_out != dev_out ||
+                c.parity != parity)
+                continue;
+            bool same = true;
+            for (int s = 0; s < P.n_spaces; ++s) same = same && c.kb_in[s] == kb_in[s] && c.kb_out[s] == kb_out[s];
+            if (same) { g = &c; break; }
+        }
+        if (g == nullptr) {
+            bbb_engine::HostedGraph &c = e->hosted_graph[e->hosted_graph_next];
+            e->hosted_graph_next = (e->hosted_graph_next + 1) % 16;
+            if (c.used) {
+                cudaGraphExecDestroy(c.exec);
+                cudaGraphDestroy(c.graph);
+                c.used = false;
+            }
+            int rc = (int)cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed);
+            if (rc == 0) {
+                rc = hosted_enqueue(e, kb_in, host_in, kb_out, host_out, dev_stage, dev_out, e->cap_stream);
+                cudaGraph_t graph = nullptr;
+                const int rc_end = (int)cudaStreamEndCapture(e->cap_stream, &graph);
+                if (rc == 0) rc = rc_end;
+                if (rc == 0) rc = (int)cudaGraphInstantiate(&c.exec, graph, 0);
+                if (rc == 0) {
+                    c.graph = graph;
+                    c.used = true;
+                    for (int s = 0; s < P.n_spaces; ++s) { c.kb_in[s] = kb_in[s]; c.kb_out[s] = kb_out[s]; }
+                    c.host_in = host_in; c.host_out = host_out; c.dev_stage = dev_stage; c.dev_out = dev_out; c.parity = parity;
+                    g = &c;
+                } else if (graph != nullptr) {
+                    cudaGraphDestroy(graph);
+                }
+            }
+            if (g == nullptr) {  // capture is not available here: enqueue every call from now on
+                (void)cudaGetLastError();
+                e->hosted_graphs = 0;
+            }
+        }
+        if (g != nullptr) {
+            CU(cudaGraphLaunch(g->exec, st));
+            launched = true;
+        }
+    }
+    if (!launched) CU(hosted_enqueue(e, kb_in, host_in, kb_out, host_out, dev_stage, dev_out, st));
+    for (int h = 0; h < NP; ++h) e->order_parity[h] ^= 1;
+    e->order_pending[0] = false;
+    bump_k_bound(e, 1);
+    ++e->steps_since_resync;
+    if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) CU(chain_local_from_scratch(e, false, st));
+    e->hosted.pending = true;
+    for (int s = 0; s < P.n_spaces; ++s) { e->hosted.kb_in[s] = kb_in[s]; e->hosted.kb_out[s] = kb_out[s]; }
+    e->hosted.host_out = host_out;
+    e->hosted.dev_stage = dev_stage;
+    e->hosted.dev_out = dev_out;
+    return BBB_OK;
+}
+
+int bbb_engine_step_hosted_wait(bbb_engine *e, int32_t *n_redone, void *stream) {
+    NEED_BOUND(e);
+    if (!e->hosted.pending) return fail(BBB_ERR_INVALID, "no hosted step pending");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaStreamSynchronize(st));
+    e->hosted.pending = false;
+    if (g_trace_on) {
+        static int n_printed = 0;
+        if (++n_printed % 50 == 0) {
+            const char *names[7] = {"start", "propose", "uploaded", "compare", "chain", "pack", "d2h"};
+            for (int h = 0; h < e->hosted_np; ++h) {
+                fprintf(stderr, "part %d:", h);
+                for (int i = 0; i < 7; ++i) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, g_trace_fork, g_trace_ev[h][i]);
+                    fprintf(stderr, " %s %.1f", names[i], ms * 1e3f);
+                }
+                fprintf(stderr, "\n");
+            }
+        }
+    }
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_target_spec &T = P.targets[e->ray_t];
+    const long long C = e->host.buf.n_chains, part = hosted_part_chains(e);
+    const int NP = e->hosted_np;
+    int redo = 0;
+    for (int h = 0; h < NP; ++h) redo += e->hosted_flag_host[h] != 0 ? 1 : 0;
+    if (n_redone) *n_redone = redo;
+    if (redo == 0) return BBB_OK;
+    // Parts whose uploaded states differ from the resident ones were left untouched by the guarded kernels: write
+    // their states, re-derive the caches of all chains (the other parts have already advanced; for them this is the
+    // periodic from-scratch re-evaluation), advance the differing parts and download them.
+    const long long rows_in = state_image_rows(e->host, e->hosted.kb_in), rows_out = state_image_rows(e->host, e->hosted.kb_out);
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(e->hosted.dev_stage), *out = reinterpret_cast<unsigned long long *>(e->hosted.dev_out);
+    for (int h = 0; h < NP; ++h) {
+        if (e->hosted_flag_host[h] == 0) continue;
+        const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
+        CU(launch_state_image(e->host, 2, e->hosted.kb_in, stage + rows_in * c0, nullptr, c0, c1, st));
+    }
+    if (int rc = bbb_engine_refresh(e, stream)) return rc;
+    for (int h = 0; h < NP; ++h) {
+        if (e->hosted_flag_host[h] == 0) continue;
+        const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
+        CU(launch_propose(e->host, c0, c1, -1, nullptr, st));
+        CU(launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax, idx_bytes_of(P, e->ray_t), -1,
+                             false, nullptr, st));
+        CU(launch_state_image(e->host, 0, e->hosted.kb_out, out + rows_out * c0, nullptr, c0, c1, st));
+        CU(cudaMemcpyAsync(reinterpret_cast<unsigned long long *>(e->hosted.host_out) + rows_out * c0, out + rows_out * c0,
+                           (size_t)(rows_out * (c1 - c0)) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return BBB_OK;
 }
 
 int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream) {

@@ -192,7 +192,7 @@ __device__ __forceinline__ void fx_add4(unsigned lo_s, unsigned hi_s, const int 
 
 template <typename IdxT>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
-                                                              int order_slot) {
+                                                              int order_slot, const int32_t *guard) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const bbb_target_spec &T = P.targets[t];
@@ -251,6 +251,8 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     const int k_slot0 = k_ref(B, s, 0, c), k_slot1 = k_ref(B, s, 1, c);
     const int rm = B.edit[c], ins = B.edit[C + c];
     const double nx = B.edit_site[c], ny = B.edit_site[C + c];
+    // hosted step: stale caches (see k_propose) -- the whole launch is a no-op
+    if (guard != nullptr && *guard != 0) return;
     if (!target_touched(P, move, lpr, t)) {  // noise move, other space, or rejected by the prior: no forward
         if (tid == 0) {
             Rng rng;
@@ -807,7 +809,7 @@ extern "C" int bbb_debug_timeline_clear() {
 #endif
 
 int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, long long n_data, int K,
-                      int idx_bytes, int order_slot, bool dependent_launch, cudaStream_t st) {
+                      int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard, cudaStream_t st) {
     if (dev.buf.block_order == nullptr) order_slot = -1;
     // programmatic dependent launch behind the proposal kernel of the same stream (see the kernel's prologue)
     cudaLaunchAttribute attr[1];
@@ -825,13 +827,13 @@ int launch_chain_step(const EngineParams &dev, long long c_first, long long c_en
         err = cudaFuncSetAttribute(k_chain_step<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
         cfg.dynamicSmemBytes = smem;
-        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint8_t>, dev, t, c_first, order_slot);
+        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint8_t>, dev, t, c_first, order_slot, guard);
         if (err != cudaSuccess) return (int)err;
     } else {
         err = cudaFuncSetAttribute(k_chain_step<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
         cfg.dynamicSmemBytes = smem;
-        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint16_t>, dev, t, c_first, order_slot);
+        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint16_t>, dev, t, c_first, order_slot, guard);
         if (err != cudaSuccess) return (int)err;
     }
     return (int)cudaGetLastError();

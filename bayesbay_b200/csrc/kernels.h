@@ -65,7 +65,8 @@ int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);
 // chain_kernels.cu
 long long chain_local_tile_rays(long long n_data, int kmax, long long n_points);
 int launch_chain_step(const EngineParams &host_params, long long c_first, long long c_end, int target, int tile_rays,
-                      long long n_data, int K, int idx_bytes, int order_slot, bool dependent_launch, cudaStream_t stream);
+                      long long n_data, int K, int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard,
+                      cudaStream_t stream);
 int launch_transpose_idx(const void *in, void *out, int idx_bytes, long long rows, long long cols, long long in_stride,
                          long long out_stride, cudaStream_t stream);
 int launch_residual_transpose(const double *dpred, double *res, long long R, long long C, const double *dobs,
@@ -75,7 +76,9 @@ int launch_residual_transpose(const double *dpred, double *res, long long R, lon
 // (the step kernels take the engine parameters BY VALUE, as a __grid_constant__ kernel argument: every scalar of the
 // problem spec and every buffer pointer is then a constant-bank read instead of a dependent global load)
 // order_slot = parity * 4 + part of the block-order class counts (common.cuh), -1: no block order
-int launch_propose(const EngineParams &host_params, long long c_first, long long c_end, int order_slot, cudaStream_t stream);
+// guard (device, may be NULL): a non-zero word makes the launch a no-op (hosted step, abi.cu)
+int launch_propose(const EngineParams &host_params, long long c_first, long long c_end, int order_slot, const int32_t *guard,
+                   cudaStream_t stream);
 int launch_finish(const EngineParams &host_params, long long C, cudaStream_t stream);
 int launch_corr_sums(const EngineParams *dev_params, long long C, int target, int proposal, cudaStream_t stream);
 int launch_fused_steps(const EngineParams &host_params, long long C, long long n_steps, cudaStream_t stream);
@@ -84,8 +87,10 @@ int launch_refresh_finish(const EngineParams *dev_params, long long C, cudaStrea
 int launch_gather_space(const EngineParams *dev_params, long long C, int space, int kmax, int32_t *k_out,
                         double *sites_out, double *values_out, cudaStream_t stream);
 long long state_image_words(const EngineParams &host_params, const int32_t *kb);
+long long state_image_rows(const EngineParams &host_params, const int32_t *kb);
+// chains [c_first, c_end): the image has rows of (c_end - c_first) words
 int launch_state_image(const EngineParams &host_params, int mode, const int32_t *kb, void *image, int32_t *differ,
-                       cudaStream_t stream);
+                       long long c_first, long long c_end, cudaStream_t stream);
 int launch_small_dpred(const EngineParams *dev_params, long long C, int target, double *dpred_out,
                        cudaStream_t stream);
 int launch_misfit_logdet(const EngineParams *dev_params, long long C, double *misfit_out,

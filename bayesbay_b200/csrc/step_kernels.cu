@@ -36,11 +36,14 @@ __device__ __forceinline__ int block_cost_class(const EngineParams &ep, long lon
 }
 
 __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep, long long c_first, long long c_end,
-                                                                int order_slot) {
+                                                                int order_slot, const int32_t *guard) {
     // the chain kernel behind this launch may become resident now (it waits for this grid before it reads a proposal)
     asm volatile("griddepcontrol.launch_dependents;");
     const long long c = c_first + (long long)blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
     if (c >= c_end) return;
+    // hosted step (bbb_engine_step_hosted): the uploaded states of this part differ from the resident ones, so the
+    // caches are stale and nothing may be drawn or stepped until the host has re-derived them
+    if (guard != nullptr && *guard != 0) return;
     Rng rng;
     rng_begin(rng, ep, c, STREAM_STEP, false);
     rng.coop = true;
@@ -204,14 +207,16 @@ struct ImageRows {
 
 template <int MODE>
 __global__ void k_state_image(const __grid_constant__ EngineParams ep, const __grid_constant__ ImageRows ir,
-                              unsigned long long *image, int32_t *differ) {
+                              unsigned long long *image, int32_t *differ, long long c_first, long long n_c) {
+    // the image holds the chains [c_first, c_first + n_c): rows of n_c words
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    const long long lc = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lc >= n_c) return;
+    const long long c = c_first + lc;
     const int row = blockIdx.y;
-    unsigned long long *slot = image + (long long)row * C + c;
+    unsigned long long *slot = image + (long long)row * n_c + lc;
     // where does this row live in the engine?
     unsigned long long cur = 0;
     unsigned long long *dst = nullptr, *dst2 = nullptr;  // MODE 2 targets
@@ -233,7 +238,7 @@ __global__ void k_state_image(const __grid_constant__ EngineParams ep, const __g
             }
         } else {
             const int q = (rel - 1) / ir.kb[s], j = (rel - 1) % ir.kb[s];
-            const int kc = (MODE == 2) ? (int)(long long)image[(long long)ir.first_row[s] * C + c] : k_ref(B, s, sl, c);
+            const int kc = (MODE == 2) ? (int)(long long)image[(long long)ir.first_row[s] * n_c + lc] : k_ref(B, s, sl, c);
             live = j < kc;
             double *p = q < S.ndim ? &site_ref(B, S, s, sl, q, j, c) : &value_ref(B, S, s, sl, q - S.ndim, j, c);
             cur = live ? (unsigned long long)__double_as_longlong(*p) : 0ull;
@@ -486,9 +491,9 @@ __global__ void k_phi_from_partial(const double *partial, int n_tiles, long long
 // ------------------------------------------------------------------------------------------------
 static inline int blocks_for(long long C, int threads) { return (int)((C + threads - 1) / threads); }
 
-int launch_propose(const EngineParams &p, long long c_first, long long c_end, int order_slot, cudaStream_t st) {
+int launch_propose(const EngineParams &p, long long c_first, long long c_end, int order_slot, const int32_t *guard, cudaStream_t st) {
     if (!p.chain_local || p.buf.block_order == nullptr) order_slot = -1;
-    k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end, order_slot);
+    k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end, order_slot, guard);
     return (int)cudaGetLastError();
 }
 int launch_corr_sums(const EngineParams *p, long long C, int target, int proposal, cudaStream_t st) {
@@ -532,15 +537,19 @@ static ImageRows image_rows(const EngineParams &p, const int32_t *kb) {
     ir.n_rows = row + 2;  // temperature, iteration
     return ir;
 }
+long long state_image_rows(const EngineParams &p, const int32_t *kb) { return image_rows(p, kb).n_rows; }
 long long state_image_words(const EngineParams &p, const int32_t *kb) { return (long long)image_rows(p, kb).n_rows * p.buf.n_chains; }
-int launch_state_image(const EngineParams &p, int mode, const int32_t *kb, void *image, int32_t *differ, cudaStream_t st) {
+int launch_state_image(const EngineParams &p, int mode, const int32_t *kb, void *image, int32_t *differ, long long c_first,
+                       long long c_end, cudaStream_t st) {
     const ImageRows ir = image_rows(p, kb);
     if (ir.n_rows > 65535) return (int)cudaErrorInvalidConfiguration;
-    dim3 grid(blocks_for(p.buf.n_chains, 128), ir.n_rows);
+    if (c_end <= c_first) return 0;
+    const long long n_c = c_end - c_first;
+    dim3 grid(blocks_for(n_c, 128), ir.n_rows);
     unsigned long long *img = reinterpret_cast<unsigned long long *>(image);
-    if (mode == 0) k_state_image<0><<<grid, 128, 0, st>>>(p, ir, img, differ);
-    else if (mode == 1) k_state_image<1><<<grid, 128, 0, st>>>(p, ir, img, differ);
-    else k_state_image<2><<<grid, 128, 0, st>>>(p, ir, img, differ);
+    if (mode == 0) k_state_image<0><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
+    else if (mode == 1) k_state_image<1><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
+    else k_state_image<2><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
     return (int)cudaGetLastError();
 }
 int launch_small_dpred(const EngineParams *p, long long C, int target, double *dpred_out, cudaStream_t st) {

@@ -336,80 +336,67 @@ def api_run(par, ll, bb, n_chains, n_iterations=2000, save_every=100):
 
 
 def e2e_run(eng, steps, device, world, dist):
-    """The plugin call with HOST buffers, one iteration per call: the chains' states (k, sites, values, noise
-    sigma, temperature, iteration) go pinned host -> device, the chains advance one iteration, the updated states
-    come back device -> host and the host waits for them.  The derived per-chain caches (nearest-site index,
-    residuals, misfit) stay resident on the device between calls and are reused only after the uploaded states
-    were compared, on the device, with the states the caches belong to (bit-identical -> reuse, else the engine
-    re-derives them with bbb_engine_refresh) -- the analogue of the d_pred / KD-tree caches the reference pickles
+    """The plugin call with HOST buffers, one iteration per call (bbb_engine_step_hosted + _wait): the chains' states
+    (k, sites, values, noise sigma, temperature, iteration) go pinned host -> device, the chains advance one
+    iteration, the updated states come back device -> host and the host waits for them.  The chain set travels in
+    parts on the engine's internal streams, so one part's copies overlap the other parts' kernels.  The derived
+    per-chain caches (nearest-site index, residuals, misfit) stay resident on the device between calls and are used
+    only after the uploaded states were compared, on the device, with the states the caches belong to
+    (bit-identical -> the part's kernels run; else they are no-ops and the wait re-derives the caches with
+    bbb_engine_refresh and advances the part) -- the analogue of the d_pred / KD-tree caches the reference pickles
     along with every chain."""
     import torch
 
-    C = eng.C
     K = eng.spec["spaces"][0]["kmax"]
     cap = eng.state_image_bytes(K) // 8
-    host = torch.empty((cap,), dtype=torch.int64, pin_memory=True)    # the caller's chains (packed image)
+    host = [torch.empty((cap,), dtype=torch.int64, pin_memory=True) for _ in range(2)]  # the caller's chains, in / out
     stage = torch.empty((cap,), dtype=torch.int64, device=device)     # upload buffer
     out = torch.empty((cap,), dtype=torch.int64, device=device)       # download buffer
-    flag = torch.zeros((1,), dtype=torch.int32, device=device)
-    flag_host = torch.zeros((1,), dtype=torch.int32, pin_memory=True)
     refreshed = [0]
     moved = [0, 0]
 
-    kb0 = min(K, int(eng.gather_space(0)[0].max().item()) + 1)
-    n0 = eng.state_image_bytes(kb0) // 8
-    host[:n0].copy_(eng.pack_states(kb0, out))
+    kb = min(K, int(eng.gather_space(0)[0].max().item()))
+    n0 = eng.state_image_bytes(kb) // 8
+    host[0][:n0].copy_(eng.pack_states_hosted(kb))
     torch.cuda.synchronize(device)
+    cur = 0
 
-    def load(kb):
-        # only the cells in use travel (kb rows of the padded [K][C] arrays): ONE copy of the packed image
-        n = eng.state_image_bytes(kb) // 8
-        stage[:n].copy_(host[:n], non_blocking=True)
-        moved[0] += 8 * n
-        flag.zero_()
-        eng.states_differ(kb, stage, flag)
-        flag_host.copy_(flag, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()
-        if int(flag_host[0]) != 0:  # the caller changed the chains: write them and re-derive the caches
-            refreshed[0] += 1
-            eng.unpack_states(kb, stage)
+    def call(kb_up, cur):
+        kb_down = eng.step_hosted(kb_up, host[cur], host[cur ^ 1], stage, out)[0]
+        refreshed[0] += eng.step_hosted_wait()  # the host reads the step's result before the next call
+        moved[0] += eng.state_image_bytes(kb_up)
+        moved[1] += eng.state_image_bytes(kb_down)
+        return kb_down
 
-    def store(kb):
-        n = eng.state_image_bytes(kb) // 8
-        host[:n].copy_(eng.pack_states(kb, out), non_blocking=True)
-        moved[1] += 8 * n
-
-    def call(kb_up):
-        load(kb_up)  # the image in `host` has kb_up cell rows
-        eng.step(1)
-        kb_down = min(K, int(host[:C].max()) + 1)  # largest k before the step (row 0 of the image) + the one a step can add
-        store(kb_down)
-        torch.cuda.synchronize(device)  # the host reads the step's result before the next call
-        return kb_down  # layout of the image now in `host`
-
-    kb = kb0
     for _ in range(3):
-        kb = call(kb)
+        kb = call(kb, cur)
+        cur ^= 1
     moved[0] = moved[1] = 0
+    refreshed[0] = 0
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
-        kb = call(kb)
+        kb = call(kb, cur)
+        cur ^= 1
     e1.record()
     torch.cuda.synchronize(device)
+    wall_ms = (time.perf_counter() - t0) * 1e3
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return {"value": world * C * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": moved[0] // steps,
-            "d2h_bytes_per_step": moved[1] // steps, "ms_per_step": ms / steps, "cache_refreshes": refreshed[0],
-            "what": "per call: packed image of the chains' states in pinned host memory (k; sites and values of the cells "
-                    "in use; sigma, temperature, iteration) -> device in one copy, compared on the device with the "
-                    "resident states the caches belong to (bbb_engine_compare_states), one iteration through "
-                    "bbb_engine_step, bbb_engine_pack_states, one copy -> host, host waits"}
+    return {"value": world * eng.C * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": moved[0] // steps,
+            "d2h_bytes_per_step": moved[1] // steps, "ms_per_step": ms / steps, "host_wall_ms_per_step": wall_ms / steps,
+            "cache_refreshes": refreshed[0], "parts": len(eng.hosted_parts()) - 1,
+            "what": "per call (bbb_engine_step_hosted + bbb_engine_step_hosted_wait): packed image of the chains' states in "
+                    "pinned host memory (k; sites and values of the cells in use; sigma, temperature, iteration) -> device, "
+                    "compared on the device with the resident states the caches belong to, one iteration, packed image -> "
+                    "pinned host memory, host waits; the chain set travels in parts on internal streams (copies of one part "
+                    "overlap the kernels of the others)"}
 
 
 # --------------------------------------------------------------------------- #

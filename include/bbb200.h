@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BBB_ABI_VERSION 3
+#define BBB_ABI_VERSION 4
 #define BBB_ORDER_BUCKETS 10
 
 #define BBB_MAX_SPACES 4
@@ -266,6 +266,28 @@ int64_t bbb_engine_state_image_bytes(bbb_engine *e, const int32_t *kb);
 int bbb_engine_pack_states(bbb_engine *e, const int32_t *kb, void *image, void *stream);
 int bbb_engine_compare_states(bbb_engine *e, const int32_t *kb, const void *image, int32_t *differ, void *stream);
 int bbb_engine_unpack_states(bbb_engine *e, const int32_t *kb, const void *image, void *stream);
+/* The same image for the chains [c_first, c_end) only: rows of (c_end - c_first) words. */
+int bbb_engine_pack_states_range(bbb_engine *e, const int32_t *kb, int64_t c_first, int64_t c_end, void *image,
+                                 void *stream);
+/* Hosted step: ONE iteration on chains the CALLER holds in pinned host memory -- the reference's
+ * `Sampler.advance_chain` round trip (samplers/_samplers.py:225-237: chains pickled to the pool, advanced, pickled
+ * back), with the copies overlapped with the kernels.  The chain set is split into bbb_engine_hosted_parts() parts
+ * (first_chain[0..n], n <= 4; chain-local engines only); a HOSTED image is the concatenation of the parts' images
+ * (bbb_engine_pack_states_range layout; part h starts at word rows(kb) * first_chain[h]).  Per part, on its own
+ * internal stream: host_in -> dev_stage, compared on the device with the resident states the derived caches belong
+ * to, proposal kernel + chain kernel (no-ops for a part whose states differ), packed with kb_out rows into dev_out,
+ * dev_out -> host_out.  kb_out[s] (written by the call) = largest k in host_in + 1 (the cell a step can add) rounded
+ * up to a multiple of 8, capped at kmax.  The work of a call is replayed from a CUDA graph captured the first time a
+ * combination of image sizes and buffers is seen (BBB_HOSTED_GRAPH=0: enqueued call by call).  host_in / host_out (pinned) and dev_stage / dev_out (device) hold bbb_engine_state_image_bytes(kb_in) /
+ * (kb_out) bytes and must be four different buffers.  Asynchronous: bbb_engine_step_hosted_wait synchronises
+ * `stream`, and if the uploaded states of some parts differed from the resident ones writes those parts into the
+ * engine, re-derives the caches (bbb_engine_refresh), advances those parts and downloads them before it returns
+ * (*n_redone = number of such parts; 0 on the fast path).  Every chain has advanced exactly one iteration and
+ * host_out holds the new states when the wait returns. */
+int bbb_engine_hosted_parts(bbb_engine *e, int64_t *first_chain /* [5] */);
+int bbb_engine_step_hosted(bbb_engine *e, const int32_t *kb_in, const void *host_in, int32_t *kb_out, void *host_out,
+                           void *dev_stage, void *dev_out, void *stream);
+int bbb_engine_step_hosted_wait(bbb_engine *e, int32_t *n_redone, void *stream);
 /* d_pred of the CURRENT states of one target, [n_data][C] (the "{target}.dpred" cache entry,
  * likelihood/_log_likelihood.py:311-320). */
 int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream);

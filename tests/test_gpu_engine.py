@@ -467,3 +467,87 @@ def test_pipelined_halves_are_bit_identical(monkeypatch):
         for x, y in zip(a, run(parts)):
             assert torch.equal(x, y)
     assert (a[-1] == 346).all()
+
+
+@pytest.mark.parametrize("pipeline,graph", [(1, 1), (2, 1), (4, 1), (4, 0)])
+def test_hosted_step_equals_resident_step(monkeypatch, pipeline, graph):
+    """bbb_engine_step_hosted: chains held by the caller in pinned host memory, copies overlapped with the parts'
+    kernels.  (a) Fast path: every bit of the downloaded states equals the resident engine's; no part is redone.
+    (b) The caller edits a chain of ONE part: that part is detected on the device, left untouched by the guarded
+    kernels, written + re-derived + advanced by the wait; the other parts are not redone; all chains advance once."""
+    from bayesbay_b200 import synthetic
+
+    monkeypatch.setenv("BBB_HOSTED_PARTS", str(pipeline))
+    monkeypatch.setenv("BBB_HOSTED_GRAPH", str(graph))  # replayed from captured CUDA graphs / enqueued every call
+    ing = synthetic.tomography_2d(nx=32, ny=32, n_sources_per_side=5, n_receivers=12, kmin=4, kmax=60)
+    spec = problems.spec_from_ingredients(ing)
+    n = 148 + 37
+    K = spec["spaces"][0]["kmax"]
+    ref, eng = _engine(spec, n, seed=5), _engine(spec, n, seed=5)
+    for e in (ref, eng):
+        e.init_states()
+        e.step(20)
+    first = eng.hosted_parts()
+    assert first[0] == 0 and first[-1] == n and len(first) == pipeline + 1
+    cap = eng.state_image_bytes(K) // 8
+    host = [torch.empty((cap,), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    stage = torch.empty((cap,), dtype=torch.int64, device="cuda")
+    out = torch.empty((cap,), dtype=torch.int64, device="cuda")
+    kb = min(K, int(eng.gather_space(0)[0].max().item()))
+    nw = eng.state_image_bytes(kb) // 8
+    host[0][:nw].copy_(eng.pack_states_hosted(kb))
+    torch.cuda.synchronize()
+    # a hosted image is the parts' images back to back
+    rows = nw // n
+    whole = eng.pack_states(kb).view(rows, n)
+    for c0, c1 in zip(first[:-1], first[1:]):
+        assert torch.equal(host[0][rows * c0:rows * c1].view(rows, c1 - c0), whole[:, c0:c1].cpu())
+    n_steps = 300  # crosses the from-scratch re-evaluation at 256
+    for it in range(n_steps):
+        kb_new = eng.step_hosted(kb, host[it & 1], host[(it + 1) & 1], stage, out)[0]
+        assert eng.step_hosted_wait() == 0
+        assert kb_new <= kb + 8 and (kb_new % 8 == 0 or kb_new == K)
+        kb = kb_new
+        ref.step(1)
+    nw = eng.state_image_bytes(kb) // 8
+    assert torch.equal(host[n_steps & 1][:nw], ref.pack_states_hosted(kb).cpu())
+    assert torch.equal(eng.pack_states(kb), ref.pack_states(kb))
+    assert torch.equal(eng.res[0], ref.res[0]) and torch.equal(eng.idx_cm[0], ref.idx_cm[0])
+    assert torch.equal(eng.n_accepted, ref.n_accepted)
+
+    # (b) the caller edits one chain of the LAST part (value of its first cell)
+    src = host[n_steps & 1]
+    rows = nw // n
+    c_edit = n - 3
+    part = max(h for h in range(len(first) - 1) if first[h] <= c_edit)
+    c0, c1 = first[part], first[part + 1]
+    value_row = 1 + 2 * kb  # k row, 2 x kb site rows, then the values
+    pos = rows * c0 + value_row * (c1 - c0) + (c_edit - c0)
+    new_value = src[pos:pos + 1].view(torch.float64) * 1.03125
+    src[pos:pos + 1] = new_value.view(torch.int64)
+    dst = host[(n_steps + 1) & 1]
+    kb2 = eng.step_hosted(kb, src, dst, stage, out)[0]
+    assert eng.step_hosted_wait() == 1
+    assert (eng.iteration.cpu().numpy() == 20 + n_steps + 1).all()
+    nw2 = eng.state_image_bytes(kb2) // 8
+    assert torch.equal(dst[:nw2], eng.pack_states_hosted(kb2).cpu())
+    # the other parts advanced exactly like the resident engine; the edited part went through unpack + refresh + step
+    ref.step(1)
+    rows2 = nw2 // n
+    ref_img = ref.pack_states_hosted(kb2).cpu()
+    for h, (a0, a1) in enumerate(zip(first[:-1], first[1:])):
+        if h != part:
+            assert torch.equal(dst[rows2 * a0:rows2 * a1], ref_img[rows2 * a0:rows2 * a1])
+    # edited part: same chains except the edited one (its caches were re-derived from scratch: the decision can only
+    # differ where the misfit rounding decides, which these seeds do not hit)
+    a = dst[rows2 * c0:rows2 * c1].view(rows2, c1 - c0)
+    b = ref_img[rows2 * c0:rows2 * c1].view(rows2, c1 - c0)
+    keep = [c for c in range(c1 - c0) if c != c_edit - c0]
+    assert torch.equal(a[:, keep], b[:, keep])
+    # the engine carries on from the edited state, caches consistent: resident steps, then a from-scratch check
+    eng.step(10)
+    res_inc = eng.res[0].clone()
+    eng.resync()
+    np.testing.assert_allclose(eng.res[0].cpu().numpy(), res_inc.cpu().numpy(), rtol=0, atol=1e-9)
+    with pytest.raises(Exception):
+        eng.step_hosted(kb2, dst, dst, stage, out)
