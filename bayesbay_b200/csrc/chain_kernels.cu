@@ -190,9 +190,15 @@ __device__ __forceinline__ void fx_add4(unsigned lo_s, unsigned hi_s, const int 
     }
 }
 
+// developer switch: persistent launch of the chain kernel (measured slower, see k_chain_step)
+#ifndef CS_PERSISTENT
+#define CS_PERSISTENT 0
+#endif
+
+// One chain's step by one block (everything below the scalars of the proposal); see k_chain_step.
 template <typename IdxT>
-__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
-                                                              int order_slot, const int32_t *guard) {
+__device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, long long c, const int32_t *guard,
+                                                unsigned char *cs_smem) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const bbb_target_spec &T = P.targets[t];
@@ -200,36 +206,6 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     const bbb_space_spec &S = P.spaces[s];
     const long long C = B.n_chains;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    extern __shared__ __align__(16) unsigned char cs_smem[];
-    // Programmatic dependent launch: the proposal kernel releases its dependents as soon as it starts, so this block
-    // may be resident while the proposals are still being drawn.  Everything that does not read the proposal is done
-    // here, ahead of the dependency wait: zeroing the ray accumulators.
-    {
-        const int n_words = 2 * P.targets[t].csc_tile_rays;  // RT * 8 bytes is a multiple of 16
-        unsigned *acc = reinterpret_cast<unsigned *>(cs_smem);
-        for (int r = tid * 4; r < n_words; r += CS_THREADS * 4) {
-            if (r + 4 <= n_words) *reinterpret_cast<uint4 *>(acc + r) = make_uint4(0, 0, 0, 0);
-            else for (int q = r; q < n_words; ++q) acc[q] = 0;
-        }
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    // longest-first block order (common.cuh): block b takes the b-th chain in cost-class order; class counts that do
-    // not add up to the grid (a proposal kernel that ran twice, a caller that binds no order buffer) mean index order
-    long long c = c_first + blockIdx.x;
-    if (order_slot >= 0) {
-        const int32_t *cnt = order_counts(B.block_order, C, order_slot >> 2, order_slot & 3);
-        int n[BBB_ORDER_BUCKETS];
-#pragma unroll
-        for (int i = 0; i < BBB_ORDER_BUCKETS; ++i) n[i] = cnt[i];
-        int tot = 0, cls = -1, off = 0;
-#pragma unroll
-        for (int i = 0; i < BBB_ORDER_BUCKETS; ++i) {
-            if (cls < 0 && (int)blockIdx.x < tot + n[i]) { cls = i; off = (int)blockIdx.x - tot; }
-            tot += n[i];
-        }
-        if (tot == (int)gridDim.x && cls >= 0) c = B.block_order[(long long)cls * C + c_first + off];
-        if (blockIdx.x == 0 && tid < 16) order_counts(B.block_order, C, (order_slot >> 2) ^ 1, order_slot & 3)[tid] = 0;
-    }
     CS_TL(0);
     CS_TL_G(16);
 #ifdef CS_TIMELINE
@@ -797,6 +773,71 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     CS_TL_G(17);
 }
 
+// One block per chain.  -DCS_PERSISTENT=1 (developer switch) launches 2 blocks per SM that take chains from a work
+// counter (the 16th word of the launch's block-order class counts, zeroed by the proposal kernel) in longest-first
+// order; measured SLOWER than letting the hardware dispatch one block per chain (chain kernel 0.111 vs 0.103 ms: the
+// atomic, two more barriers per chain and the in-loop zeroing cost more than the block dispatch they replace).
+template <typename IdxT>
+__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
+                                                              int order_slot, const int32_t *guard, int n_launch) {
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    __shared__ int s_work, s_cum[BBB_ORDER_BUCKETS + 1];
+    // Programmatic dependent launch: the proposal kernel releases its dependents as soon as it starts, so this block
+    // may be resident while the proposals are still being drawn.  Everything that does not read the proposal is done
+    // here, ahead of the dependency wait: zeroing the ray accumulators.
+    auto zero_planes = [&]() {
+        const int n_words = 2 * ep.spec.targets[t].csc_tile_rays;  // RT * 8 bytes is a multiple of 16
+        unsigned *acc = reinterpret_cast<unsigned *>(cs_smem);
+        for (int r = tid * 4; r < n_words; r += CS_THREADS * 4) {
+            if (r + 4 <= n_words) *reinterpret_cast<uint4 *>(acc + r) = make_uint4(0, 0, 0, 0);
+            else for (int q = r; q < n_words; ++q) acc[q] = 0;
+        }
+    };
+    zero_planes();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // longest-first block order (common.cuh): work item b is the b-th chain in cost-class order; class counts that do
+    // not add up to the launch (a proposal kernel that ran twice, a caller that binds no order buffer) mean index order
+    bool ordered = false;
+    int32_t *counter = nullptr;
+    if (order_slot >= 0) {
+        int32_t *cnt = order_counts(B.block_order, C, order_slot >> 2, order_slot & 3);
+        counter = cnt + 15;
+        if (tid == 0) {
+            int tot = 0;
+            for (int i = 0; i < BBB_ORDER_BUCKETS; ++i) { s_cum[i] = tot; tot += cnt[i]; }
+            s_cum[BBB_ORDER_BUCKETS] = tot;
+        }
+        if (blockIdx.x == 0 && tid < 15) order_counts(B.block_order, C, (order_slot >> 2) ^ 1, order_slot & 3)[tid] = 0;
+        __syncthreads();
+        ordered = s_cum[BBB_ORDER_BUCKETS] == n_launch;
+    }
+    const bool persistent = CS_PERSISTENT && counter != nullptr && (int)gridDim.x < n_launch;
+    for (int iter = 0;; ++iter) {
+        int b = (int)blockIdx.x;
+        if (persistent) {
+            if (tid == 0) s_work = atomicAdd(counter, 1);
+            __syncthreads();
+            b = s_work;
+            if (b >= n_launch) break;
+            if (iter > 0) zero_planes();
+        } else if (iter > 0) {
+            break;
+        }
+        long long c = c_first + b;
+        if (ordered) {
+            int cls = 0;
+#pragma unroll
+            for (int i = 1; i < BBB_ORDER_BUCKETS; ++i) cls += b >= s_cum[i] ? 1 : 0;
+            c = B.block_order[(long long)cls * C + c_first + (b - s_cum[cls])];
+        }
+        chain_step_body<IdxT>(ep, t, c, guard, cs_smem);
+        if (persistent) __syncthreads();
+    }
+}
+
 #ifdef CS_TIMELINE
 extern "C" int bbb_debug_timeline(long long *host_out, int n_blocks) {
     return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 24 * (size_t)n_blocks);
@@ -816,7 +857,16 @@ int launch_chain_step(const EngineParams &dev, long long c_first, long long c_en
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(c_end - c_first));
+    // persistent launch: two blocks per SM (what registers and shared memory allow) take the chains from a work counter
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long n_launch = c_end - c_first;
+    const bool persistent = CS_PERSISTENT && order_slot >= 0 && n_launch > 2LL * n_sm;
+    cfg.gridDim = dim3((unsigned)(persistent ? 2 * n_sm : n_launch));
     cfg.blockDim = dim3(CS_THREADS);
     cfg.stream = st;
     cfg.attrs = attr;
@@ -827,13 +877,13 @@ int launch_chain_step(const EngineParams &dev, long long c_first, long long c_en
         err = cudaFuncSetAttribute(k_chain_step<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
         cfg.dynamicSmemBytes = smem;
-        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint8_t>, dev, t, c_first, order_slot, guard);
+        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint8_t>, dev, t, c_first, order_slot, guard, (int)n_launch);
         if (err != cudaSuccess) return (int)err;
     } else {
         err = cudaFuncSetAttribute(k_chain_step<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
         cfg.dynamicSmemBytes = smem;
-        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint16_t>, dev, t, c_first, order_slot, guard);
+        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint16_t>, dev, t, c_first, order_slot, guard, (int)n_launch);
         if (err != cudaSuccess) return (int)err;
     }
     return (int)cudaGetLastError();

@@ -39,6 +39,9 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_con
                                                                 int order_slot, const int32_t *guard) {
     // the chain kernel behind this launch may become resident now (it waits for this grid before it reads a proposal)
     asm volatile("griddepcontrol.launch_dependents;");
+    // work counter of the (persistent) chain kernel behind this launch: the 16th word of the launch's class counts
+    if (order_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
+        order_counts(ep.buf.block_order, ep.buf.n_chains, order_slot >> 2, order_slot & 3)[15] = 0;
     const long long c = c_first + (long long)blockIdx.x * PROPOSE_WARPS + (threadIdx.x >> 5);
     if (c >= c_end) return;
     // hosted step (bbb_engine_step_hosted): the uploaded states of this part differ from the resident ones, so the
