@@ -21,10 +21,11 @@ for ln in open(sass):
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/", ln)
         if m: line_of[int(m.group(1), 16)] = cur
 marks = {"tables: proposed": "tables", "change-local rasterisation: which": "rasterisation", "re-derivation: 16 lanes": "re-derivation",
-         "change-local forward: fixed": "forward (columns)", "misfit: phi": "misfit", "likelihood ratio, decision": "decision + commit"}
+         "change-local forward: fixed": "forward (columns)", "misfit: phi": "misfit", "likelihood ratio, decision": "decision + commit",
+         "One block per chain.": "kernel entry (zeroing, dependency wait, block order)"}
 bounds, kstart = [], None
 for i, ln in enumerate(open(cu), 1):
-    if "k_chain_step(const __grid_constant__" in ln: kstart = i
+    if "void chain_step_body(const EngineParams &ep" in ln: kstart = i
     for k, v in marks.items():
         if k in ln: bounds.append((i, v))
 bounds = [(kstart, "entry / gather")] + bounds
