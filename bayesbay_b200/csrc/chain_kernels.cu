@@ -789,12 +789,13 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
     // may be resident while the proposals are still being drawn.  Everything that does not read the proposal is done
     // here, ahead of the dependency wait: zeroing the ray accumulators.
     auto zero_planes = [&]() {
-        const int n_words = 2 * ep.spec.targets[t].csc_tile_rays;  // RT * 8 bytes is a multiple of 16
+        const int n_words = 2 * ep.spec.targets[t].csc_tile_rays;
+        uint4 *acc4 = reinterpret_cast<uint4 *>(cs_smem);
+        const int n4 = n_words >> 2;
+#pragma unroll 4
+        for (int i = tid; i < n4; i += CS_THREADS) acc4[i] = make_uint4(0, 0, 0, 0);
         unsigned *acc = reinterpret_cast<unsigned *>(cs_smem);
-        for (int r = tid * 4; r < n_words; r += CS_THREADS * 4) {
-            if (r + 4 <= n_words) *reinterpret_cast<uint4 *>(acc + r) = make_uint4(0, 0, 0, 0);
-            else for (int q = r; q < n_words; ++q) acc[q] = 0;
-        }
+        for (int q = (n4 << 2) + tid; q < n_words; q += CS_THREADS) acc[q] = 0;
     };
     zero_planes();
     asm volatile("griddepcontrol.wait;" ::: "memory");
