@@ -323,6 +323,53 @@ def test_full_size_config3_properties():
     np.testing.assert_allclose(share, [1 / 7, 1 / 7, 3 / 7, 1 / 7, 1 / 7], atol=0.005)
 
 
+def test_full_size_config5_properties():
+    """BASELINE configs[4] at full problem size (256x256 grid, 100 000 rays, nnz 21 M, K = 500 -> 16-bit nearest-site
+    index, 10 ray tiles per chain-local step) on 96 chains: after 120 iterations the resident index equals a
+    from-scratch rasterisation, the incrementally maintained misfit equals a fresh forward evaluation, d_pred of
+    sampled chains equals the KD-tree + CSR mat-vec restatement, bounds hold and the counters add up."""
+    import ctypes as C
+
+    import scipy.sparse
+    import scipy.spatial
+
+    from bayesbay_b200 import _lib as L
+    from bayesbay_b200 import synthetic
+
+    ing = synthetic.tomography_2d(nx=256, ny=256, n_sources_per_side=100, n_receivers=250, kmin=50, kmax=500)
+    spec = problems.spec_from_ingredients(ing)
+    R, G = ing["indptr"].size - 1, ing["points"].shape[0]
+    assert R == 100_000 and G == 65_536
+    n, n_it = 96, 120
+    eng = _engine(spec, n, seed=77)
+    assert eng.chain_local
+    eng.init_states()
+    eng.step(n_it)
+    k, sites, vals = eng.gather_space(0)
+    ref = torch.zeros((G, n), dtype=torch.int16, device="cuda")
+    px = torch.as_tensor(ing["points"][:, 0].copy()).cuda()
+    py = torch.as_tensor(ing["points"][:, 1].copy()).cuda()
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    L.check(L.load().bbb_raster2d(p(sites), p(k), 500, n, p(px), p(py), G, p(ref), None))
+    assert torch.equal(eng.current_cell_idx(0).to(torch.int64), ref.to(torch.int64))
+    dp = eng.dpred(0)
+    m0, ld0 = eng.misfit_logdet()
+    eng.refresh()
+    m1, ld1 = eng.misfit_logdet()
+    np.testing.assert_allclose(m0.cpu().numpy(), m1.cpu().numpy(), rtol=1e-12)
+    assert torch.equal(ld0, ld1)
+    jac = scipy.sparse.csr_matrix((ing["data"], ing["indices"], ing["indptr"]), shape=(R, G))
+    kk, ss, vv = k.cpu().numpy(), sites.cpu().numpy(), vals.cpu().numpy()
+    for c in (0, 41, 95):
+        s_c, v_c = ss[:, : kk[c], c].T, vv[0, : kk[c], c]
+        nearest = scipy.spatial.KDTree(s_c).query(ing["points"])[1]
+        assert np.array_equal(nearest, ref[:, c].cpu().numpy().astype(np.int64))
+        np.testing.assert_allclose(dp[:, c].cpu().numpy(), jac @ (1.0 / v_c[nearest]), rtol=1e-12)
+    assert kk.min() >= 50 and kk.max() <= 500
+    prop = eng.n_proposed.cpu().numpy()
+    assert (prop.sum(0) == n_it).all() and (eng.iteration.cpu().numpy() == n_it).all()
+
+
 def _pair_of_engines(monkeypatch, spec, n_chains, seed, tile_cap=None):
     """The same problem on the full-SpMM step (reference behaviour: every proposal re-evaluates all rays) and on
     the chain-local step (change-local forward)."""
