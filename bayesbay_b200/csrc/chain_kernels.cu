@@ -196,7 +196,9 @@ __device__ __forceinline__ void fx_add4(unsigned lo_s, unsigned hi_s, const int 
 #endif
 
 // One chain's step by one block (everything below the scalars of the proposal); see k_chain_step.
-template <typename IdxT>
+// MULTI: the target's rays need several accumulator tiles (csc_n_tiles > 1); problems with one tile get an
+// instantiation without any of the multi-tile code.
+template <typename IdxT, bool MULTI>
 __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, long long c, const int32_t *guard,
                                                 unsigned char *cs_smem) {
     const bbb_problem_spec &P = ep.spec;
@@ -241,7 +243,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
     }
     if (tid == CS_THREADS - 1) finish_gather(ep, c, s_fin);  // thread 0 decides from these after the forward
 
-    const int K = S.kmax, RT = T.csc_tile_rays, NT = T.csc_n_tiles, G = T.n_points, R = T.n_data;
+    const int K = S.kmax, RT = T.csc_tile_rays, NT = MULTI ? T.csc_n_tiles : 1, G = T.n_points, R = T.n_data;
     unsigned *acc_lo = reinterpret_cast<unsigned *>(cs_smem);
     unsigned *acc_hi = acc_lo + RT;
     double *sx = reinterpret_cast<double *>(cs_smem + (size_t)RT * 8);
@@ -562,7 +564,10 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
         }
     };
     auto zero_acc = [&]() {
-        for (int r = tid; r < 2 * RT; r += CS_THREADS) acc_lo[r] = 0;
+        uint4 *acc4 = reinterpret_cast<uint4 *>(acc_lo);  // (several tiles: RT is a multiple of 32)
+#pragma unroll 4
+        for (int i = tid; i < (2 * RT) >> 2; i += CS_THREADS) acc4[i] = make_uint4(0, 0, 0, 0);
+        for (int r = ((2 * RT) & ~3) + tid; r < 2 * RT; r += CS_THREADS) acc_lo[r] = 0;
         __syncthreads();
     };
 
@@ -581,22 +586,36 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
         accumulate(tile);
         CS_TL(5);
         const int r0 = tile * RT, nr = min(RT, R - r0);
-        if (NT > 1) {
+        if (MULTI) {
             // several ray tiles recycle the accumulators: the new residuals of the touched rays are parked in the
             // chain's row of the (otherwise idle) d_pred scratch, the touched rays remembered in a bitmap
             double *park = B.dpred_scratch[t] + c * (long long)R;
-            for (int w = warp; w < (nr + 31) / 32; w += CS_WARPS) {
-                const int r = 32 * w + lane;
-                const unsigned lo = r < nr ? acc_lo[r] : 0u, hi = r < nr ? acc_hi[r] : 0u;
-                const bool touched = (lo | hi) != 0;
-                const unsigned m = __ballot_sync(0xffffffffu, touched);
-                if (lane == 0) s_touch[(r0 >> 5) + w] = m;
-                if (touched) {
-                    const double rr = res[r0 + r];
-                    const double d = (double)(long long)(((unsigned long long)hi << 32) | lo) * inv_scale;
+            // eight 32-ray words per warp and round: the residuals of all eight are requested before the first is
+            // used (one word at a time, every round waited for its own load); each thread still adds its rays in
+            // ascending order, so the sum is the same
+            const int n_words = (nr + 31) / 32;
+            for (int w0 = warp; w0 < n_words; w0 += 8 * CS_WARPS) {
+                unsigned lo[8], hi[8];
+                double rr[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int w = w0 + u * CS_WARPS, r = 32 * w + lane;
+                    const bool in = w < n_words && r < nr;
+                    lo[u] = in ? acc_lo[r] : 0u;
+                    hi[u] = in ? acc_hi[r] : 0u;
+                    const bool touched = (lo[u] | hi[u]) != 0;
+                    const unsigned m = __ballot_sync(0xffffffffu, touched);
+                    if (lane == 0 && w < n_words) s_touch[(r0 >> 5) + w] = m;
+                    rr[u] = touched ? res[r0 + r] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if ((lo[u] | hi[u]) == 0) continue;
+                    const int r = 32 * (w0 + u * CS_WARPS) + lane;
+                    const double d = (double)(long long)(((unsigned long long)hi[u] << 32) | lo[u]) * inv_scale;
                     const double wr = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r0 + r] : 1.0;
-                    dphi += wr * (d * (2.0 * rr + d));
-                    park[r0 + r] = rr + d;
+                    dphi += wr * (d * (2.0 * rr[u] + d));
+                    park[r0 + r] = rr[u] + d;
                 }
             }
             __syncthreads();
@@ -615,7 +634,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                 acc_hi[r] = (unsigned)__double2hiint(nv);
             }
         };
-        if (NT == 1 && (RT & 3) == 0 && RT <= 8 * 4 * CS_THREADS) {
+        if (!MULTI && (RT & 3) == 0 && RT <= 8 * 4 * CS_THREADS) {
             // (a) every thread scans 4 consecutive rays per round, bit (4 i + j) of m: ray 4 tid + 2048 i + j touched
             unsigned m = 0;
 #pragma unroll 8
@@ -710,7 +729,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                 }
             }
         }
-        if (NT > 1) __syncthreads();
+        if (MULTI) __syncthreads();
     }
     CS_TL(11);
     dphi = block_sum_to_thread0(dphi, s_red);
@@ -729,20 +748,33 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
     CS_TL_G(17);
     if (!s_accept) return;
 
-    if (NT == 1 && n_touch >= 0) {
+    if (!MULTI && n_touch >= 0) {
         for (int i = tid; i < n_touch; i += CS_THREADS) {
             const int r = (int)touch[i];
             res[r] = __hiloint2double((int)acc_hi[r], (int)acc_lo[r]);
         }
-    } else if (NT == 1) {
+    } else if (!MULTI) {
         for (int r = tid; r < R; r += CS_THREADS) {
             const unsigned lo = acc_lo[r], hi = acc_hi[r];
             if ((lo | hi) != 0) res[r] = __hiloint2double((int)hi, (int)lo);
         }
     } else {
         const double *park = B.dpred_scratch[t] + c * (long long)R;
-        for (int w = warp; w < (R + 31) / 32; w += CS_WARPS)
-            if ((s_touch[w] >> lane) & 1u) res[32 * w + lane] = park[32 * w + lane];
+        // (eight words per warp and round: all loads of a round ahead of its stores)
+        const int n_words = (R + 31) / 32;
+        for (int w0 = warp; w0 < n_words; w0 += 8 * CS_WARPS) {
+            double v[8];
+            bool on[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int w = w0 + u * CS_WARPS;
+                on[u] = w < n_words && ((s_touch[w] >> lane) & 1u);
+                v[u] = on[u] ? park[32 * w + lane] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (on[u]) res[32 * (w0 + u * CS_WARPS) + lane] = v[u];
+        }
     }
     // nearest-site index: renumber the survivors when the edit shifts cell indices (death), then the changed points
     constexpr int VEC = 16 / (int)sizeof(IdxT);
@@ -777,7 +809,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
 // counter (the 16th word of the launch's block-order class counts, zeroed by the proposal kernel) in longest-first
 // order; measured SLOWER than letting the hardware dispatch one block per chain (chain kernel 0.111 vs 0.103 ms: the
 // atomic, two more barriers per chain and the in-loop zeroing cost more than the block dispatch they replace).
-template <typename IdxT>
+template <typename IdxT, bool MULTI>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
                                                               int order_slot, const int32_t *guard, int n_launch) {
     const bbb_buffers &B = ep.buf;
@@ -834,7 +866,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             for (int i = 1; i < BBB_ORDER_BUCKETS; ++i) cls += b >= s_cum[i] ? 1 : 0;
             c = B.block_order[(long long)cls * C + c_first + (b - s_cum[cls])];
         }
-        chain_step_body<IdxT>(ep, t, c, guard, cs_smem);
+        chain_step_body<IdxT, MULTI>(ep, t, c, guard, cs_smem);
         if (persistent) __syncthreads();
     }
 }
@@ -873,20 +905,17 @@ int launch_chain_step(const EngineParams &dev, long long c_first, long long c_en
     cfg.attrs = attr;
     cfg.numAttrs = dependent_launch ? 1 : 0;
     const size_t smem = chain_step_smem(tile_rays, K, n_data);
-    cudaError_t err;
-    if (idx_bytes == 1) {
-        err = cudaFuncSetAttribute(k_chain_step<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool multi = n_data > tile_rays;
+    cfg.dynamicSmemBytes = smem;
+    auto launch = [&](auto kernel) -> int {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        cfg.dynamicSmemBytes = smem;
-        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint8_t>, dev, t, c_first, order_slot, guard, (int)n_launch);
-        if (err != cudaSuccess) return (int)err;
-    } else {
-        err = cudaFuncSetAttribute(k_chain_step<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        cfg.dynamicSmemBytes = smem;
-        err = cudaLaunchKernelEx(&cfg, k_chain_step<uint16_t>, dev, t, c_first, order_slot, guard, (int)n_launch);
-        if (err != cudaSuccess) return (int)err;
-    }
+        return (int)cudaLaunchKernelEx(&cfg, kernel, dev, t, c_first, order_slot, guard, (int)n_launch);
+    };
+    int rc;
+    if (idx_bytes == 1) rc = multi ? launch(k_chain_step<uint8_t, true>) : launch(k_chain_step<uint8_t, false>);
+    else rc = multi ? launch(k_chain_step<uint16_t, true>) : launch(k_chain_step<uint16_t, false>);
+    if (rc != 0) return rc;
     return (int)cudaGetLastError();
 }
 
