@@ -332,17 +332,17 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
             for (int q = 0; q < CS_PTS; ++q)
                 if (g0 + q < G && wv.at(q) == rm) chg |= 1u << q;
         } else {
-            // Pruning: a group with ONE owner is decided from its bounding box.  d_new(g) - d_own(g) =
-            // |n|^2 - |o|^2 - 2 g.(n - o) is affine in the point g, so its minimum over the box is taken at a corner;
-            // when that minimum is positive by a margin far above any rounding of the per-point test (1e-9 of the
-            // squared coordinates against 1e-16), no point of the group can be captured by the inserted cell.
+            // Pruning: a group is decided from its bounding box.  With o0 the current owner of ANY of its points,
+            // d_own(g) <= d(g, o0) for every point g of the group (the owner is the nearest site), hence
+            // d_new(g) - d_own(g) >= d_new(g) - d(g, o0) = |n|^2 - |o0|^2 - 2 g.(n - o0), which is affine in g: its
+            // minimum over the box is taken at a corner, and when that minimum is positive by a margin far above any
+            // rounding of the per-point test (1e-9 of the squared coordinates against 1e-16), no point of the group can
+            // be captured by the inserted cell.  Points of the removed cell are found by comparing indices.
             bool pruned = false;
-            if (ins >= 0 && T.group_box != nullptr && g0 + CS_PTS <= G && wv.uniform()) {
-                const int o0 = wv.at(0);
-                if (rm >= 0 && o0 == rm) {
-                    scn = 0xFFFFu;  // the whole group lost its owner
-                    pruned = true;
-                } else {
+            if (ins >= 0 && T.group_box != nullptr && g0 + CS_PTS <= G) {
+                int o0 = wv.at(0);
+                if (rm >= 0 && o0 == rm) o0 = wv.at(CS_PTS - 1);
+                if (!(rm >= 0 && o0 == rm)) {
                     const double2 bx = __ldg(reinterpret_cast<const double2 *>(T.group_box) + 2 * (g0 >> 4));
                     const double2 by = __ldg(reinterpret_cast<const double2 *>(T.group_box) + 2 * (g0 >> 4) + 1);
                     int mm = o0 - ((rm >= 0 && o0 > rm) ? 1 : 0);
@@ -353,6 +353,11 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                     const double nn = nx * nx + ny * ny, oo = ox * ox + oy * oy;
                     const double ax = ::fmax(fabs(bx.x), fabs(bx.y)), ay = ::fmax(fabs(by.x), fabs(by.y));
                     pruned = (nn - oo) - 2.0 * gmax > 1e-9 * (nn + oo + ax * ax + ay * ay);
+                }
+                if (pruned && rm >= 0) {
+#pragma unroll
+                    for (int q = 0; q < CS_PTS; ++q)
+                        if (wv.at(q) == rm) scn |= 1u << q;
                 }
             }
 #pragma unroll

@@ -60,7 +60,8 @@ __device__ __forceinline__ int32_t &k_ref(const bbb_buffers &B, int s, int slot,
 }
 
 // ---- priors (prior/_prior.py: Uniform :400-481, Gaussian :599-682, Laplace :800-881) ----------
-__device__ __forceinline__ double prior_log_pdf(int kind, double a, double b, double v) {
+// (out of line, like the generator's arithmetic in rng.cuh: plain values in, one value out)
+__device__ __noinline__ inline double prior_log_pdf(int kind, double a, double b, double v) {
     if (kind == BBB_PRIOR_UNIFORM) return (a <= v && v <= b) ? -log(b - a) : -INFINITY;
     if (kind == BBB_PRIOR_GAUSSIAN) {
         const double z = (v - a) / b;
@@ -74,7 +75,8 @@ __device__ __forceinline__ double prior_value_ratio(int kind, double a, double b
     if (kind == BBB_PRIOR_GAUSSIAN) return (old_v - new_v) * (old_v + new_v - 2.0 * a) / (2.0 * (b * b));
     return (fabs(old_v - a) - fabs(new_v - a)) / b;
 }
-__device__ __forceinline__ double prior_sample(int kind, double a, double b, Rng &rng) {
+template <class R>
+__device__ __forceinline__ double prior_sample(int kind, double a, double b, R &rng) {
     if (kind == BBB_PRIOR_UNIFORM) return rng.uniform(a, b);
     if (kind == BBB_PRIOR_GAUSSIAN) return rng.normal(a, b);
     return rng.laplace(a, b);
@@ -86,11 +88,8 @@ struct PriorAt {
     int kind;
     double a, b, pstd, pstd_birth;
 };
-__device__ inline PriorAt prior_at(const bbb_space_spec &S, int p, double x) {
-    PriorAt out{S.prior_kind[p], S.prior_a[p], S.prior_b[p], S.perturb_std[p], S.perturb_std_birth[p]};
-    const int n = S.n_pos[p];
-    if (n <= 0) return out;
-    const double *X = S.pos_table[p];
+// position-dependent part (the table lives in global memory)
+__device__ __noinline__ inline void prior_at_table(const double *X, int n, double x, double &a, double &b, double &pstd, double &pstd_birth) {
     int i0, i1;
     if (x <= X[0]) { i0 = i1 = 0; }
     else if (x >= X[n - 1]) { i0 = i1 = n - 1; }
@@ -104,12 +103,18 @@ __device__ inline PriorAt prior_at(const bbb_space_spec &S, int p, double x) {
         if (i1 == i0) return y0;
         return y0 + (x - X[i0]) * (X[(long long)row * n + i1] - y0) / (X[i1] - X[i0]);
     };
-    out.a = at(1); out.b = at(2); out.pstd = at(3); out.pstd_birth = at(4);
+    a = at(1); b = at(2); pstd = at(3); pstd_birth = at(4);
+}
+__device__ __forceinline__ PriorAt prior_at(const bbb_space_spec &S, int p, double x) {
+    PriorAt out{S.prior_kind[p], S.prior_a[p], S.prior_b[p], S.perturb_std[p], S.perturb_std_birth[p]};
+    const int n = S.n_pos[p];
+    if (n > 0) prior_at_table(S.pos_table[p], n, x, out.a, out.b, out.pstd, out.pstd_birth);
     return out;
 }
 __device__ __forceinline__ double prior_log_pdf(const PriorAt &q, double v) { return prior_log_pdf(q.kind, q.a, q.b, v); }
 __device__ __forceinline__ double prior_value_ratio(const PriorAt &q, double o, double n) { return prior_value_ratio(q.kind, q.a, q.b, o, n); }
-__device__ __forceinline__ double prior_sample(const PriorAt &q, Rng &rng) { return prior_sample(q.kind, q.a, q.b, rng); }
+template <class R>
+__device__ __forceinline__ double prior_sample(const PriorAt &q, R &rng) { return prior_sample(q.kind, q.a, q.b, rng); }
 
 __device__ __forceinline__ int n_move_types(const bbb_problem_spec &P) { return 4 * P.n_spaces + 1; }
 

@@ -59,8 +59,8 @@ struct ResidualSums {  // streaming accumulation of Phi3 over r = 0 .. n-1
 
 // Residual sums of a thread-evaluated target; optionally stores d_pred (stride C) and the cell index
 // (lookup1d, stride C).
-__device__ inline Phi3 small_target_phi(const bbb_problem_spec &P, const bbb_buffers &B, int t, int slot,
-                                        long long c, double *dpred_out, int32_t *idx_out) {
+__device__ __noinline__ inline Phi3 small_target_phi(const bbb_problem_spec &P, const bbb_buffers &B, int t, int slot,
+                                                     long long c, double *dpred_out, int32_t *idx_out) {
     const bbb_target_spec &T = P.targets[t];
     const int s = T.space;
     const bbb_space_spec &S = P.spaces[s];
@@ -115,24 +115,36 @@ __device__ __forceinline__ double ray_partial_sum(const EngineParams &ep, int t,
 }
 
 // Target.inverse_covariance_times_vector / log_determinant_covariance (likelihood/_target.py:136-208)
+// (out of line, plain values in and out: see rng.cuh)
+struct MisfitLogdet {
+    double misfit, logdet;
+};
+__device__ __noinline__ inline MisfitLogdet misfit_logdet_values(int cov_kind, int correlated, int n_data, double cov_scalar, double s0,
+                                                                  double se, double s1, double sigma, double rho) {
+    MisfitLogdet out;
+    if (cov_kind == BBB_COV_HIERARCHICAL) {
+        if (correlated) {
+            const double factor = 1.0 / ((sigma * sigma) * (1.0 - rho * rho));
+            out.misfit = factor * ((1.0 + rho * rho) * s0 - (rho * rho) * se - 2.0 * rho * s1);
+            out.logdet = (2.0 * n_data) * log(sigma) + (double)(n_data - 1) * log(1.0 - rho * rho);
+        } else {
+            out.misfit = (1.0 / (sigma * sigma)) * s0;
+            out.logdet = (2.0 * n_data) * log(sigma);
+        }
+    } else if (cov_kind == BBB_COV_SCALAR) {
+        out.misfit = cov_scalar * s0;
+        out.logdet = 0.0;
+    } else {
+        out.misfit = s0;
+        out.logdet = 0.0;
+    }
+    return out;
+}
 __device__ __forceinline__ void misfit_logdet_terms(const bbb_target_spec &T, const Phi3 &phi, double sigma, double rho,
                                                     double &misfit, double &logdet) {
-    if (T.cov_kind == BBB_COV_HIERARCHICAL) {
-        if (T.correlated) {
-            const double factor = 1.0 / ((sigma * sigma) * (1.0 - rho * rho));
-            misfit = factor * ((1.0 + rho * rho) * phi.s0 - (rho * rho) * phi.se - 2.0 * rho * phi.s1);
-            logdet = (2.0 * T.n_data) * log(sigma) + (double)(T.n_data - 1) * log(1.0 - rho * rho);
-        } else {
-            misfit = (1.0 / (sigma * sigma)) * phi.s0;
-            logdet = (2.0 * T.n_data) * log(sigma);
-        }
-    } else if (T.cov_kind == BBB_COV_SCALAR) {
-        misfit = T.cov_scalar * phi.s0;
-        logdet = 0.0;
-    } else {
-        misfit = phi.s0;
-        logdet = 0.0;
-    }
+    const MisfitLogdet v = misfit_logdet_values(T.cov_kind, T.correlated, T.n_data, T.cov_scalar, phi.s0, phi.se, phi.s1, sigma, rho);
+    misfit = v.misfit;
+    logdet = v.logdet;
 }
 
 // True when the current proposal of chain c requires target t's forward to be re-evaluated.
@@ -247,7 +259,7 @@ __device__ inline void finish_pre(const EngineParams &ep, long long c, const Fin
                                                                     : (T.cov_kind == BBB_COV_SCALAR ? T.cov_scalar : 1.0);
         }
     }
-    pre.log_u = log(rng.unit());
+    pre.log_u = dlog(rng.unit());
 }
 
 __device__ inline bool finish_post(const EngineParams &ep, long long c, const FinishIn &in, FinishPre &pre, int ray_t,

@@ -28,10 +28,20 @@ struct Edit {
     bool write;
 };
 
-// nearest_neighbour_1d (_utils_1d.pyx:102-114) over the cells of `slot`, optionally skipping `skip`
-__device__ inline int nearest_1d(const bbb_buffers &B, const bbb_space_spec &S, int s, int slot,
-                                 long long c, int k, int skip, double xp) {
-    auto at = [&](int j) { return site_ref(B, S, s, slot, 0, j + (skip >= 0 && j >= skip ? 1 : 0), c); };
+// Where a proposal reads the cells of the CURRENT state from: the [..][K][C] arrays in global memory.  (An accessor
+// type so that the same move code can draw from other representations of the cells.)
+struct GlobalCells {
+    const bbb_buffers &B;
+    const bbb_space_spec &S;
+    int s, slot;
+    long long c;
+    __device__ __forceinline__ double site(int d, int j) const { return site_ref(B, S, s, slot, d, j, c); }
+    __device__ __forceinline__ double value(int p, int j) const { return value_ref(B, S, s, slot, p, j, c); }
+};
+// nearest_neighbour_1d (_utils_1d.pyx:102-114) over the cells of the state, optionally skipping `skip`
+template <class Cells>
+__device__ inline int nearest_1d(const Cells &cells, int k, int skip, double xp) {
+    auto at = [&](int j) { return cells.site(0, j + (skip >= 0 && j >= skip ? 1 : 0)); };
     const int n = k - (skip >= 0 ? 1 : 0);
     if (n == 1 || xp < at(0)) return 0;
     for (int i = 0; i < n - 1; ++i) {
@@ -43,8 +53,8 @@ __device__ inline int nearest_1d(const bbb_buffers &B, const bbb_space_spec &S, 
 
 // Voronoi.nearest_neighbour (discretization/_voronoi.py:462-465): argmin of the Euclidean distance,
 // lowest index on ties; squared distance with separately rounded products (no FMA).
-__device__ inline int nearest_2d(const bbb_buffers &B, const bbb_space_spec &S, int s, int slot,
-                                 long long c, int k, int skip, double px, double py, bool coop) {
+template <class Cells>
+__device__ inline int nearest_2d(const Cells &cells, int k, int skip, double px, double py, bool coop) {
     double best = INFINITY;
     int bi = 0x7fffffff;
     if (!coop) {
@@ -52,8 +62,8 @@ __device__ inline int nearest_2d(const bbb_buffers &B, const bbb_space_spec &S, 
         bi = 0;
         for (int j = 0; j < k; ++j) {
             if (j == skip) continue;
-            const double dx = site_ref(B, S, s, slot, 0, j, c) - px;
-            const double dy = site_ref(B, S, s, slot, 1, j, c) - py;
+            const double dx = cells.site(0, j) - px;
+            const double dy = cells.site(1, j) - py;
             const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
             if (d < best) { best = d; bi = out; }
             ++out;
@@ -63,8 +73,8 @@ __device__ inline int nearest_2d(const bbb_buffers &B, const bbb_space_spec &S, 
     // warp-cooperative: lanes = sites, then a lexicographic (distance, index) shuffle reduction
     for (int j = threadIdx.x & 31; j < k; j += 32) {
         if (j == skip) continue;
-        const double dx = site_ref(B, S, s, slot, 0, j, c) - px;
-        const double dy = site_ref(B, S, s, slot, 1, j, c) - py;
+        const double dx = cells.site(0, j) - px;
+        const double dy = cells.site(1, j) - py;
         const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         if (d < best) { best = d; bi = j; }
     }
@@ -77,9 +87,11 @@ __device__ inline int nearest_2d(const bbb_buffers &B, const bbb_space_spec &S, 
     return bi - ((skip >= 0 && bi > skip) ? 1 : 0);  // index among the remaining cells
 }
 
-__device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, Rng &rng,
-                                     bool apply_now) {
-    // ---- outer choice: _markov_chain.py:208-210 ------------------------------------------------
+// ---- outer choice (_markov_chain.py:208-210), then the inner choice of ParamSpacePerturbation
+// (.perturb_param_space_state, perturbations/_param_space.py:79-92).  Returns the move id: 4 * space + kind, or
+// 4 * n_spaces for the noise perturbation.
+template <class R>
+__device__ inline int choose_move(const bbb_problem_spec &P, R &rng) {
     double w[BBB_MAX_SPACES + 1];
     int n_outer = 0;
     for (int s = 0; s < P.n_spaces; ++s) {
@@ -90,46 +102,8 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
     for (int t = 0; t < P.n_targets; ++t) any_hier |= (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL);
     if (any_hier) w[n_outer++] = 1.0;
     const int i_outer = rng.choice(w, n_outer);
-    const bool writer = !rng.coop || (threadIdx.x & 31) == 0;  // cooperative mode: lane 0 publishes the proposal
-
-    if (i_outer >= P.n_spaces) {
-        // ---- P7 NoisePerturbation.perturb (perturbations/_data_noise.py:21-77) ------------------
-        for (int t = 0; t < P.n_targets; ++t) {
-            const bbb_target_spec &T = P.targets[t];
-            if (T.cov_kind != BBB_COV_HIERARCHICAL) continue;
-            const double old_v = B.sigma[t][c];
-            double new_v = old_v;
-            for (int it = 0; it < MAX_RESAMPLE; ++it) {
-                const double cand = old_v + rng.normal(0.0, T.std_perturb_std);
-                if (cand < T.std_min || cand > T.std_max) continue;
-                new_v = cand;
-                break;
-            }
-            if (writer) B.sigma[t][B.n_chains + c] = new_v;
-            if (T.correlated) {  // to_be_perturbed = ["std", "correlation"] (_data_noise.py:61-76)
-                const double old_r = B.corr[t][c];
-                double new_r = old_r;
-                for (int it = 0; it < MAX_RESAMPLE; ++it) {
-                    const double cand = old_r + rng.normal(0.0, T.corr_perturb_std);
-                    if (cand < T.corr_min || cand > T.corr_max) continue;
-                    new_r = cand;
-                    break;
-                }
-                if (writer) B.corr[t][B.n_chains + c] = new_r;
-            }
-        }
-        if (writer) {
-            B.move[c] = 4 * P.n_spaces;
-            B.edit[c] = -1;
-            B.edit[B.n_chains + c] = -1;
-            B.log_prob_ratio[c] = 0.0;
-        }
-        return;
-    }
-
-    // ---- inner choice: ParamSpacePerturbation.perturb_param_space_state (_param_space.py:79-92)
-    const int s = i_outer;
-    const bbb_space_spec &S = P.spaces[s];
+    if (i_outer >= P.n_spaces) return 4 * P.n_spaces;
+    const bbb_space_spec &S = P.spaces[i_outer];
     double wi[4];
     int kinds[4];
     int n_inner = 0;
@@ -137,12 +111,36 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
     if (S.w_death > 0) { wi[n_inner] = S.w_death; kinds[n_inner++] = BBB_MOVE_DEATH; }
     if (S.w_values > 0) { wi[n_inner] = S.w_values; kinds[n_inner++] = BBB_MOVE_VALUES; }
     if (S.w_sites > 0) { wi[n_inner] = S.w_sites; kinds[n_inner++] = BBB_MOVE_SITES; }
-    const int inner = kinds[rng.choice(wi, n_inner)];
+    return 4 * i_outer + kinds[rng.choice(wi, n_inner)];
+}
 
-    const int cur = B.sel[s][c];
-    const int prop = cur ^ 1;
-    const int k = k_ref(B, s, cur, c);
-    Edit e;
+// ---- P7 NoisePerturbation.perturb (perturbations/_data_noise.py:21-77) of one hierarchical target: new std (and
+// correlation: to_be_perturbed = ["std", "correlation"], :61-76), each resampled until inside its range
+template <class R>
+__device__ inline void propose_noise_target(const bbb_target_spec &T, R &rng, double old_v, double old_r, double &new_v,
+                                            double &new_r) {
+    new_v = old_v;
+    for (int it = 0; it < MAX_RESAMPLE; ++it) {
+        const double cand = old_v + rng.normal(0.0, T.std_perturb_std);
+        if (cand < T.std_min || cand > T.std_max) continue;
+        new_v = cand;
+        break;
+    }
+    new_r = old_r;
+    if (T.correlated) {
+        for (int it = 0; it < MAX_RESAMPLE; ++it) {
+            const double cand = old_r + rng.normal(0.0, T.corr_perturb_std);
+            if (cand < T.corr_min || cand > T.corr_max) continue;
+            new_r = cand;
+            break;
+        }
+    }
+}
+
+// ---- P2-P6: one move of kind `inner` on a space whose current state (k cells) is read through `cells`; the
+// result is the edit script (header of this file) with the prior/proposal ratio
+template <class Cells, class R>
+__device__ inline void propose_space_move(const bbb_space_spec &S, const Cells &cells, int k, int inner, R &rng, Edit &e) {
     e.rm = -1;
     e.ins = -1;
     e.lpr = 0.0;
@@ -153,10 +151,10 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         // P2 ParamPerturbation.perturb_param_space_state (perturbations/_param_values.py:60-84)
         const int idx = rng.randint(0, k - 1);
         e.rm = e.ins = idx;
-        for (int d = 0; d < S.ndim; ++d) e.site[d] = site_ref(B, S, s, cur, d, idx, c);
+        for (int d = 0; d < S.ndim; ++d) e.site[d] = cells.site(d, idx);
         for (int p = 0; p < S.n_params; ++p) {
             const PriorAt q = prior_at(S, p, e.site[0]);
-            const double old_v = value_ref(B, S, s, cur, p, idx, c);
+            const double old_v = cells.value(p, idx);
             const double new_v = old_v + rng.normal(0.0, q.pstd);
             e.lpr += prior_value_ratio(q, old_v, new_v);
             e.vals[p] = new_v;
@@ -165,9 +163,9 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         // P3 Voronoi.perturb_value + _perturb_site (_voronoi.py:171-232; 1-D :566-591)
         const int idx = rng.randint(0, k - 1);
         e.rm = idx;
-        for (int p = 0; p < S.n_params; ++p) e.vals[p] = value_ref(B, S, s, cur, p, idx, c);
+        for (int p = 0; p < S.n_params; ++p) e.vals[p] = cells.value(p, idx);
         double old_site[2] = {0.0, 0.0};
-        for (int d = 0; d < S.ndim; ++d) old_site[d] = e.site[d] = site_ref(B, S, s, cur, d, idx, c);
+        for (int d = 0; d < S.ndim; ++d) old_site[d] = e.site[d] = cells.site(d, idx);
         for (int it = 0; it < MAX_RESAMPLE; ++it) {
             double cand[2];
             bool ok = true;
@@ -187,7 +185,7 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         if (S.ndim == 1) {
             int pos = 0;
             for (int j = 0; j < k; ++j)
-                if (j != idx && site_ref(B, S, s, cur, 0, j, c) < e.site[0]) ++pos;
+                if (j != idx && cells.site(0, j) < e.site[0]) ++pos;
             e.ins = pos;
         } else {
             e.ins = idx;
@@ -208,22 +206,22 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
                 for (int p = 0; p < S.n_params; ++p) e.vals[p] = prior_sample(prior_at(S, p, e.site[0]), rng);
             } else {
                 // _initialize_params_from_neighbour (discretization/_discretization.py:323-375)
-                const int i_near = (S.ndim == 1) ? nearest_1d(B, S, s, cur, c, k, -1, e.site[0])
-                                                 : nearest_2d(B, S, s, cur, c, k, -1, e.site[0], e.site[1], rng.coop);
+                const int i_near = (S.ndim == 1) ? nearest_1d(cells, k, -1, e.site[0])
+                                                 : nearest_2d(cells, k, -1, e.site[0], e.site[1], rng.coop);
                 for (int p = 0; p < S.n_params; ++p) {
                     const PriorAt q = prior_at(S, p, e.site[0]);
                     const double theta = q.pstd_birth;
-                    const double old_v = value_ref(B, S, s, cur, p, i_near, c);
+                    const double old_v = cells.value(p, i_near);
                     const double new_v = old_v + rng.normal(0.0, theta);
                     e.vals[p] = new_v;
                     const double diff = new_v - old_v;
-                    e.lpr += prior_log_pdf(q, new_v) + (log(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta)));
+                    e.lpr += prior_log_pdf(q, new_v) + (dlog(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta)));
                 }
             }
             if (S.ndim == 1) {
                 int pos = 0;  // bisect_left
                 for (int j = 0; j < k; ++j)
-                    if (site_ref(B, S, s, cur, 0, j, c) < e.site[0]) ++pos;
+                    if (cells.site(0, j) < e.site[0]) ++pos;
                 e.ins = pos;
             } else {
                 e.ins = k;
@@ -239,34 +237,38 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
             if (S.kind != BBB_SPACE_PLAIN && S.birth_from == BBB_BIRTH_FROM_NEIGHBOUR) {
                 // _log_prob_death_parameters (discretization/_discretization.py:435-465)
                 double pos[2] = {0.0, 0.0};
-                for (int d = 0; d < S.ndim; ++d) pos[d] = site_ref(B, S, s, cur, d, e.rm, c);
-                int i_near = (S.ndim == 1) ? nearest_1d(B, S, s, cur, c, k, e.rm, pos[0])
-                                           : nearest_2d(B, S, s, cur, c, k, e.rm, pos[0], pos[1], rng.coop);
+                for (int d = 0; d < S.ndim; ++d) pos[d] = cells.site(d, e.rm);
+                int i_near = (S.ndim == 1) ? nearest_1d(cells, k, e.rm, pos[0])
+                                           : nearest_2d(cells, k, e.rm, pos[0], pos[1], rng.coop);
                 i_near += (i_near >= e.rm) ? 1 : 0;  // back to indices of the current state
                 for (int p = 0; p < S.n_params; ++p) {
                     const PriorAt q = prior_at(S, p, pos[0]);
                     const double theta = q.pstd_birth;
-                    const double gone = value_ref(B, S, s, cur, p, e.rm, c);
-                    const double near_v = value_ref(B, S, s, cur, p, i_near, c);
+                    const double gone = cells.value(p, e.rm);
+                    const double near_v = cells.value(p, i_near);
                     const double diff = gone - near_v;
                     e.lpr -= prior_log_pdf(q, gone);
-                    e.lpr -= log(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta));
+                    e.lpr -= dlog(theta * SQRT_TWO_PI) + diff * diff / (2.0 * (theta * theta));
                 }
             }
         }
     }
+}
 
+// Writes the proposed slot (cur ^ 1) of space s from the current slot and the edit, and its cell count; returns the
+// proposed cell count.  coop: the 32 lanes of the warp (which all hold the same edit) share the work, lanes = output
+// cells; else the calling thread writes everything when `apply_now`.
+__device__ inline int write_proposed_slot(const bbb_buffers &B, const bbb_space_spec &S, int s, int cur, int k, long long c,
+                                          const Edit &e, bool coop, bool apply_now) {
     // ---- write the proposed slot ------------------------------------------------------------------
     // The edit (rm, ins, new cell) is published for the forward kernels; the proposed slot is written here: by
     // the warp's lanes (lanes = output cells) in the cooperative proposal kernel, by the chain's own thread in the
     // fused small-problem kernel -- one loop for every move kind.
+    const int prop = cur ^ 1;
+    const bool writer = !coop || (threadIdx.x & 31) == 0;
     const int k_new = e.write ? k - (e.rm >= 0 ? 1 : 0) + (e.ins >= 0 ? 1 : 0) : k;
-    if (writer) {
-        for (int d = 0; d < S.ndim; ++d) B.edit_site[(long long)d * B.n_chains + c] = e.site[d];
-        for (int p = 0; p < S.n_params; ++p) B.edit_vals[(long long)p * B.n_chains + c] = e.vals[p];
-        k_ref(B, s, prop, c) = k_new;
-    }
-    if (e.write && rng.coop) {
+    if (writer) k_ref(B, s, prop, c) = k_new;
+    if (e.write && coop) {
         // warp-cooperative proposal kernel: the 32 lanes (which all hold the same edit) write the proposed slot,
         // lanes = output cells
         const int ndim = S.ndim, n_params = S.n_params;
@@ -317,6 +319,46 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
             }
         }
     }
+    return k_new;
+}
+
+template <class R>
+__device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, R &rng,
+                                     bool apply_now) {
+    const int move = choose_move(P, rng);
+    const bool writer = !rng.coop || (threadIdx.x & 31) == 0;  // cooperative mode: lane 0 publishes the proposal
+
+    if (move == 4 * P.n_spaces) {
+        for (int t = 0; t < P.n_targets; ++t) {
+            const bbb_target_spec &T = P.targets[t];
+            if (T.cov_kind != BBB_COV_HIERARCHICAL) continue;
+            double new_v, new_r;
+            propose_noise_target(T, rng, B.sigma[t][c], T.correlated ? B.corr[t][c] : 0.0, new_v, new_r);
+            if (writer) B.sigma[t][B.n_chains + c] = new_v;
+            if (T.correlated && writer) B.corr[t][B.n_chains + c] = new_r;
+        }
+        if (writer) {
+            B.move[c] = move;
+            B.edit[c] = -1;
+            B.edit[B.n_chains + c] = -1;
+            B.log_prob_ratio[c] = 0.0;
+        }
+        return;
+    }
+
+    const int s = move >> 2, inner = move & 3;
+    const bbb_space_spec &S = P.spaces[s];
+    const int cur = B.sel[s][c];
+    const int k = k_ref(B, s, cur, c);
+    Edit e;
+    propose_space_move(S, GlobalCells{B, S, s, cur, c}, k, inner, rng, e);
+
+    const int k_new = write_proposed_slot(B, S, s, cur, k, c, e, rng.coop, apply_now);
+    if (writer) {
+        for (int d = 0; d < S.ndim; ++d) B.edit_site[(long long)d * B.n_chains + c] = e.site[d];
+        for (int p = 0; p < S.n_params; ++p) B.edit_vals[(long long)p * B.n_chains + c] = e.vals[p];
+    }
+    (void)k_new;
     if (writer) {
         B.move[c] = 4 * s + inner;
         B.edit[c] = e.rm;

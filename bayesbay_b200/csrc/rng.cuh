@@ -36,6 +36,19 @@ __host__ __device__ inline double words_to_double(uint32_t w0, uint32_t w1) {
     return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// Out-of-line copies of the long arithmetic sequences: every draw site of the step kernels used to inline its own
+// Philox rounds / logarithm / square root / cosine, which made those kernels several hundred KB of code (an
+// instruction-cache problem, not an arithmetic one: a proposal is a latency-bound chain on one warp or thread).
+__device__ __noinline__ inline uint4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    uint32_t o[4];
+    philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+__device__ __noinline__ inline double box_muller(double u1, double u2) {
+    return sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2);
+}
+__device__ __noinline__ inline double dlog(double x) { return log(x); }
+
 struct Rng {
     // warp-cooperative mode: the 32 lanes of a warp work on ONE chain; lane 0 owns the generator and every
     // draw is broadcast, so all lanes follow the same control flow with the same values
@@ -79,12 +92,13 @@ struct Rng {
         }
         const uint32_t b = n >> 1;
         if (b != blk) {
-            philox4x32_10(b, chain, it_lo, it_hi, k0, k1, w);
+            const uint4 o = philox_block(b, chain, it_lo, it_hi, k0, k1);
+            w[0] = o.x; w[1] = o.y; w[2] = o.z; w[3] = o.w;
             blk = b;
         }
-        const uint32_t h = (n & 1u) * 2u;
+        const bool hi = (n & 1u) != 0;
         ++n;
-        return words_to_double(w[h], w[h + 1]);
+        return hi ? words_to_double(w[2], w[3]) : words_to_double(w[0], w[1]);
     }
     // call once, by all 32 lanes, right after init_* of a cooperative generator that starts at position 0
     __device__ void look_ahead() {
@@ -92,13 +106,11 @@ struct Rng {
         if (tape != nullptr) {
             ahead_u = (cursor + lane < tape_len) ? tape[cursor + lane] : 0.0;
         } else {
-            uint32_t o[4];
-            philox4x32_10(lane >> 1, chain, it_lo, it_hi, k0, k1, o);
-            const uint32_t h = (lane & 1u) * 2u;
-            ahead_u = words_to_double(o[h], o[h + 1]);
+            const uint4 o = philox_block(lane >> 1, chain, it_lo, it_hi, k0, k1);
+            ahead_u = (lane & 1u) ? words_to_double(o.z, o.w) : words_to_double(o.x, o.y);
         }
         const double u2 = __shfl_down_sync(0xffffffffu, ahead_u, 1);
-        ahead_z = sqrt(-2.0 * log(1.0 - ahead_u)) * cos(6.283185307179586 * u2);  // same expression as std_normal()
+        ahead_z = box_muller(ahead_u, u2);  // same expression as std_normal()
         ahead = true;
     }
     __device__ double u() {
@@ -116,7 +128,9 @@ struct Rng {
     }
     // random.random() restated: (0, 1]
     __device__ double unit() { return 1.0 - u(); }
-    __device__ double uniform(double a, double b) { return a + (b - a) * u(); }
+    // (values that enter a chain's state are formed with explicitly unfused operations, like the reference's Python
+    // floats: every kernel that draws them -- whatever its inlining context -- then produces the same bits)
+    __device__ double uniform(double a, double b) { return __dadd_rn(a, __dmul_rn(b - a, u())); }
     __device__ int randint(int a, int b) {
         if (a == b) return a;
         const int m = b - a + 1;
@@ -147,13 +161,96 @@ struct Rng {
         }
         const double u1 = u();
         const double u2 = u();
-        return sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2);
+        return box_muller(u1, u2);
     }
-    __device__ double normal(double mu, double sigma) { return mu + sigma * std_normal(); }
+    __device__ double normal(double mu, double sigma) { return __dadd_rn(mu, __dmul_rn(sigma, std_normal())); }
     __device__ double laplace(double mu, double scale) {
         const double v = u();
-        if (v >= 0.5) return mu - scale * log(2.0 - v - v);
-        if (v > 0.0) return mu + scale * log(v + v);
+        if (v >= 0.5) return __dsub_rn(mu, __dmul_rn(scale, dlog(2.0 - v - v)));
+        if (v > 0.0) return __dadd_rn(mu, __dmul_rn(scale, dlog(v + v)));
+        return mu;
+    }
+    // tape position (tape-driven) / draws consumed in this (chain, iteration)
+    __device__ long long after() const { return tape != nullptr ? cursor : (long long)n; }
+};
+
+// The same stream for a warp that draws ONE chain's proposal with all its lanes (proposal kernel): the first 32 uniforms
+// of the (chain, iteration) -- and the standard normals made of positions (l, l + 1) -- are computed by the 32 lanes at
+// once into two shared-memory tables; a draw is then one shared-memory read that every lane makes alike (no shuffles,
+// no lane-0 ownership), which keeps the draw sites of the proposal code a few instructions long.  Positions past the
+// tables (long resampling loops) are computed on demand by every lane redundantly.
+__device__ __noinline__ inline double stream_u(const double *tape, long long cursor0, long long tape_len, uint32_t k0, uint32_t k1,
+                                               uint32_t chain, uint32_t it_lo, uint32_t it_hi, int pos) {
+    if (tape != nullptr) return cursor0 + pos < tape_len ? tape[cursor0 + pos] : 0.0;
+    const uint4 o = philox_block((uint32_t)pos >> 1, chain, it_lo, it_hi, k0, k1);
+    return (pos & 1) ? words_to_double(o.z, o.w) : words_to_double(o.x, o.y);
+}
+struct FastRng {
+    static constexpr bool coop = true;
+    const double *su, *sz;
+    const double *tape;
+    long long cursor0, tape_len;
+    uint32_t k0, k1, chain, it_lo, it_hi;
+    int n;
+    // all 32 lanes; su / sz: 32 doubles each, private to the calling warp
+    __device__ void begin(double *su_w, double *sz_w, const double *tape_c, long long cursor, long long tape_length, uint64_t seed,
+                          uint64_t chain_id, uint64_t iteration, uint32_t tag) {
+        su = su_w; sz = sz_w;
+        tape = tape_c; cursor0 = cursor; tape_len = tape_length;
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        chain = (uint32_t)chain_id;
+        it_lo = (uint32_t)iteration;
+        it_hi = ((uint32_t)(iteration >> 32) & 0x0FFFFFFFu) | (tag << 28);
+        n = 0;
+        const int lane = threadIdx.x & 31;
+        const double ul = stream_u(tape, cursor0, tape_len, k0, k1, chain, it_lo, it_hi, lane);
+        su_w[lane] = ul;
+        __syncwarp();
+        sz_w[lane] = lane < 31 ? box_muller(ul, su_w[lane + 1]) : 0.0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ double u() {
+        const int i = n++;
+        return i < 32 ? su[i] : stream_u(tape, cursor0, tape_len, k0, k1, chain, it_lo, it_hi, i);
+    }
+    __device__ __forceinline__ long long after() const { return tape != nullptr ? cursor0 + n : (long long)n; }
+    __device__ __forceinline__ double unit() { return 1.0 - u(); }
+    __device__ __forceinline__ double uniform(double a, double b) { return __dadd_rn(a, __dmul_rn(b - a, u())); }
+    __device__ __forceinline__ int randint(int a, int b) {
+        if (a == b) return a;
+        const int m = b - a + 1;
+        int i = (int)(u() * (double)m);
+        if (i > m - 1) i = m - 1;
+        return a + i;
+    }
+    __device__ __forceinline__ int choice(const double *wts, int m) {
+        if (m == 1) return 0;
+        double tot = 0.0;
+        for (int i = 0; i < m; ++i) tot += wts[i];
+        const double x = u() * tot;
+        double cum = 0.0;
+        int i = 0;
+        for (; i < m - 1; ++i) {
+            cum += wts[i];
+            if (x < cum) break;
+        }
+        return i;
+    }
+    __device__ __forceinline__ double std_normal() {
+        const int i = n;
+        if (i + 1 < 32) {
+            n += 2;
+            return sz[i];
+        }
+        const double u1 = u();
+        const double u2 = u();
+        return box_muller(u1, u2);
+    }
+    __device__ __forceinline__ double normal(double mu, double sigma) { return __dadd_rn(mu, __dmul_rn(sigma, std_normal())); }
+    __device__ __forceinline__ double laplace(double mu, double scale) {
+        const double v = u();
+        if (v >= 0.5) return __dsub_rn(mu, __dmul_rn(scale, dlog(2.0 - v - v)));
+        if (v > 0.0) return __dadd_rn(mu, __dmul_rn(scale, dlog(v + v)));
         return mu;
     }
 };

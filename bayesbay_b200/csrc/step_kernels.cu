@@ -47,12 +47,16 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_con
     // hosted step (bbb_engine_step_hosted): the uploaded states of this part differ from the resident ones, so the
     // caches are stale and nothing may be drawn or stepped until the host has re-derived them
     if (guard != nullptr && *guard != 0) return;
-    Rng rng;
-    rng_begin(rng, ep, c, STREAM_STEP, false);
-    rng.coop = true;
-    rng.look_ahead();
+    // the warp's generator: the first 32 draws of the (chain, iteration) computed by the lanes at once into shared memory
+    __shared__ double s_draw[PROPOSE_WARPS][2][32];
+    const bbb_buffers &B = ep.buf;
+    const int w = threadIdx.x >> 5;
+    FastRng rng;
+    rng.begin(s_draw[w][0], s_draw[w][1], B.tape != nullptr ? B.tape + c * B.tape_stride : nullptr,
+              B.tape != nullptr ? B.tape_cursor[c] : 0, B.tape_stride, ep.spec.seed, (uint64_t)(B.chain_id0 + c), (uint64_t)B.iteration[c],
+              STREAM_STEP);
     propose_chain(ep.spec, ep.buf, c, rng, false);
-    if ((threadIdx.x & 31) == 0) rng_end(rng, ep, c);
+    if ((threadIdx.x & 31) == 0) B.tape_cursor[c] = rng.after();
     if (order_slot >= 0) {  // file the chain for the longest-first block order of the chain kernel
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
