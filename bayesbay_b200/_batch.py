@@ -321,8 +321,7 @@ class ChainBatch:
 
     def misfit_logdet_T(self):
         """[C][3] (misfit, logdet, T) of the current states: the only data a PT swap round needs."""
-        m, ld = self.engine.misfit_logdet()
-        return self._torch.stack((m, ld, self.engine.temperature), dim=1).contiguous()
+        return self.engine.misfit_logdet_T()
 
 
 # --------------------------------------------------------------------------- #

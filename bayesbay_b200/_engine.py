@@ -411,6 +411,18 @@ class Engine:
         L.check(self.lib.bbb_engine_misfit_logdet(self._handle, _ptr(m), _ptr(ld), self._stream))
         return m, ld
 
+    def misfit_logdet_T(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[C][3] rows (misfit, logdet, T) of the current states, written by one kernel: what this rank contributes
+        to a parallel-tempering swap round."""
+        if out is None:
+            out = torch.empty((self.C, 3), dtype=torch.float64, device=self.device)
+        L.check(self.lib.bbb_engine_swap_rows(self._handle, _ptr(out), self._stream))
+        return out
+
+    def ray_tiles(self, t: int) -> int:
+        """Ray tiles of the chain-local step of ray target ``t`` (1: all rays' accumulators fit one block)."""
+        return max(1, int(self._cspec.targets[t].csc_n_tiles))
+
     def resync(self):
         """Chain-local engines: re-evaluate forward and misfit of the current states from scratch (the engine also
         does this on its own every ``bbb_engine_set_resync`` steps)."""
@@ -623,13 +635,15 @@ class Engine:
 
 
 def pt_swap(gathered: torch.Tensor, seed: int, round_: int, id0: int, n_local: int,
-            tape: Optional[torch.Tensor] = None):
+            tape: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
     """Run one parallel-tempering swap round on ``gathered`` [n_total][3] (misfit, logdet, T).
-    Returns ``(local temperatures [n_local], number of accepted swaps)``."""
+    Returns ``(local temperatures [n_local], number of accepted swaps)``; ``out`` (e.g. the engine's temperature
+    buffer) receives the local temperatures in place of a fresh tensor."""
     lib = L.load()
     n_total = gathered.shape[0]
     assert gathered.is_contiguous() and gathered.dtype == torch.float64
-    t_out = torch.empty((n_local,), dtype=torch.float64, device=gathered.device)
+    t_out = torch.empty((n_local,), dtype=torch.float64, device=gathered.device) if out is None else out
+    assert t_out.is_contiguous() and t_out.dtype == torch.float64 and t_out.numel() >= n_local
     n_acc = torch.zeros((1,), dtype=torch.int32, device=gathered.device)
     stream = C.c_void_p(torch.cuda.current_stream(gathered.device).cuda_stream)
     L.check(lib.bbb_pt_swap(_ptr(gathered), n_total, seed & 0xFFFFFFFFFFFFFFFF, int(round_), int(id0), int(n_local),

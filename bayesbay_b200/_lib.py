@@ -120,6 +120,7 @@ SYMBOLS = {
     "bbb_engine_step_hosted_wait": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
     "bbb_engine_dpred": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "bbb_engine_misfit_logdet": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bbb_engine_swap_rows": (C.c_int, [_vp, _vp, _vp]),
     "bbb_pt_swap": (C.c_int, [_vp, _i64, _u64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bbb_raster2d": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp]),
     "bbb_raster1d": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),

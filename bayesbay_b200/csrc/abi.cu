@@ -993,6 +993,13 @@ int bbb_engine_misfit_logdet(bbb_engine *e, double *misfit_out, double *logdet_o
     return BBB_OK;
 }
 
+int bbb_engine_swap_rows(bbb_engine *e, double *rows_out, void *stream) {
+    NEED_BOUND(e);
+    if (!rows_out) return fail(BBB_ERR_INVALID, "NULL output");
+    CU(launch_misfit_logdet(e->dev, e->host.buf.n_chains, rows_out, nullptr, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
 int bbb_pt_swap(double *gathered, int64_t n_total, uint64_t seed, int64_t round, int64_t id0, int64_t n_local,
                 double *temperature_out, int32_t *n_accepted_out, const double *tape, void *stream) {
     if (!gathered || !temperature_out) return fail(BBB_ERR_INVALID, "NULL argument");

@@ -304,8 +304,14 @@ __global__ void __launch_bounds__(STEP_THREADS) k_misfit_logdet(const EnginePara
         m += mt;
         if (hier) ld += lt;
     }
-    misfit_out[c] = m;
-    logdet_out[c] = ld;
+    if (logdet_out != nullptr) {
+        misfit_out[c] = m;
+        logdet_out[c] = ld;
+    } else {  // packed rows (misfit, logdet, T): what a rank contributes to a parallel-tempering swap round
+        misfit_out[3 * c + 0] = m;
+        misfit_out[3 * c + 1] = ld;
+        misfit_out[3 * c + 2] = B.temperature[c];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,6 +436,82 @@ __global__ void __launch_bounds__(SWAP_THREADS) k_pt_swap(double *gathered, long
     }
     for (long long i = threadIdx.x; i < n_local; i += blockDim.x)
         temperature_out[i] = use_smem ? temps[id0 + i] : gathered[3 * (id0 + i) + 2];
+}
+
+constexpr int SWAP_WAVE_THREADS = 1024;  // attempts in flight in the wave-parallel kernel (one per thread)
+
+// The attempts are sequential only through the temperatures of the chains they touch: two attempts commute unless
+// they share a chain.  Every thread holds one attempt of the current window of 1024; in every wave the attempts stamp
+// their two chains with atomicMin(index), and an attempt whose two stamps are its own index has no EARLIER pending
+// attempt on either chain -- everything before it on those chains has been applied -- so it decides and swaps now.
+// All such attempts of a wave are pairwise disjoint.  A window drains in as many waves as its longest chain of
+// attempts sharing chains (3-4 at 8192 chains, ~10 at 1024); the result is bit-identical to the sequential loop.
+// 1 / T is kept next to T (same rounding as dividing afresh), so a decision costs one division.
+__global__ void __launch_bounds__(SWAP_WAVE_THREADS) k_pt_swap_waves(double *gathered, long long n_total, uint64_t seed,
+                                                                     long long round, long long id0, long long n_local,
+                                                                     double *temperature_out, int32_t *n_accepted_out,
+                                                                     const double *tape) {
+    extern __shared__ double swap_smem[];
+    double *temps = swap_smem, *itemps = swap_smem + n_total;
+    int *stamp = reinterpret_cast<int *>(swap_smem + 2 * n_total);
+    __shared__ int s_acc;
+    const int n = (int)n_total, tid = threadIdx.x;
+    for (int i = tid; i < n; i += SWAP_WAVE_THREADS) {
+        const double tv = gathered[3 * (long long)i + 2];
+        temps[i] = tv;
+        itemps[i] = 1.0 / tv;
+        stamp[i] = 0x7fffffff;
+    }
+    if (tid == 0) s_acc = 0;
+    __syncthreads();
+    int n_acc = 0;
+    for (long long w0 = 0; w0 < n_total; w0 += SWAP_WAVE_THREADS) {
+        const long long i = w0 + tid;
+        bool pending = i < n_total;
+        int a = 0, b = 0;
+        double log_u = 0.0, core = 0.0;
+        if (pending) {
+            Rng rng;
+            if (tape != nullptr) {
+                rng.init_tape(tape, 3 * i);
+            } else {
+                rng.init_philox(seed, 0, (uint64_t)round, STREAM_SWAP);
+                rng.n = (uint32_t)(3 * i);
+            }
+            a = min((int)(rng.u() * (double)n), n - 1);
+            b = min((int)(rng.u() * (double)(n - 1)), n - 2);
+            if (b >= a) ++b;
+            log_u = dlog(rng.unit());
+            core = (gathered[3 * (long long)a + 1] - gathered[3 * (long long)b + 1] + gathered[3 * (long long)a + 0] -
+                    gathered[3 * (long long)b + 0]) / 2.0;
+        }
+        for (;;) {
+            if (pending) {
+                atomicMin(&stamp[a], tid);
+                atomicMin(&stamp[b], tid);
+            }
+            __syncthreads();
+            const bool ready = pending && stamp[a] == tid && stamp[b] == tid;
+            __syncthreads();
+            if (pending) { stamp[a] = 0x7fffffff; stamp[b] = 0x7fffffff; }
+            if (ready) {
+                const double t1 = temps[a], t2 = temps[b], i1 = itemps[a], i2 = itemps[b];
+                const double llr = core / t1;
+                const double prob = (i1 - i2) * llr;
+                if (prob > log_u) {
+                    temps[a] = t2; temps[b] = t1; itemps[a] = i2; itemps[b] = i1;
+                    ++n_acc;
+                }
+                pending = false;
+            }
+            if (!__syncthreads_or(pending ? 1 : 0)) break;
+        }
+    }
+    if (n_acc) atomicAdd(&s_acc, n_acc);
+    __syncthreads();
+    if (tid == 0 && n_accepted_out != nullptr) *n_accepted_out = s_acc;
+    for (int i = tid; i < n; i += SWAP_WAVE_THREADS) gathered[3 * (long long)i + 2] = temps[i];
+    for (long long i = tid; i < n_local; i += SWAP_WAVE_THREADS) temperature_out[i] = temps[id0 + i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -571,8 +653,18 @@ int launch_misfit_logdet(const EngineParams *p, long long C, double *misfit_out,
 int launch_pt_swap(const double *gathered, long long n_total, uint64_t seed, long long round, long long id0,
                    long long n_local, double *temperature_out, int32_t *n_accepted_out, const double *tape,
                    cudaStream_t st) {
-    const int use_smem = n_total <= SWAP_SMEM_MAX;
-    const size_t smem = use_smem ? (size_t)n_total * (2 * sizeof(double) + sizeof(int)) : 0;
+    if (n_total <= SWAP_SMEM_MAX) {  // temperatures fit in shared memory: wave-parallel replay
+        const size_t smem_w = (size_t)n_total * (2 * sizeof(double) + sizeof(int));
+        if (smem_w > 32 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(k_pt_swap_waves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+            if (err != cudaSuccess) return (int)err;
+        }
+        k_pt_swap_waves<<<1, SWAP_WAVE_THREADS, smem_w, st>>>(const_cast<double *>(gathered), n_total, seed, round, id0, n_local,
+                                                              temperature_out, n_accepted_out, tape);
+        return (int)cudaGetLastError();
+    }
+    const int use_smem = 0;
+    const size_t smem = 0;
     if (smem > 16 * 1024) {  // the kernel also has 24 KB of static shared memory
         cudaError_t err = cudaFuncSetAttribute(k_pt_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;

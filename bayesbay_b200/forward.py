@@ -13,9 +13,12 @@ tutorials are provided as operator *descriptors* that carry the arrays the engin
 * :class:`PolynomialForward` -- ``np.vander(x, len(m), True) @ m`` on a trans-dimensional ``ParameterSpace``
   (03_transd_polyfit.ipynb cell 5).
 
-They are listed where the reference lists forward callables.  Calling one on the host raises: the
-numpy adapters that turn a descriptor into a callable for the *unmodified reference* live in
-``oracle/reference_adapters.py`` (test infrastructure).
+They are listed where the reference lists forward callables, and they ARE valid reference forwards: called on
+the host with a ``State`` (of this package or of the unmodified reference) they evaluate exactly what the
+tutorials' forward functions evaluate, with scipy / numpy (``Callable[[State], np.ndarray]``,
+likelihood/_log_likelihood.py:67-78, 325-331).  That is how the same problem object is run inside the reference
+(``bayesbay_b200.plugin``, the parity tests, the reference arm of ``bench.py``).  The CUDA engine never calls
+them -- it reads the arrays they carry -- so this is not a fallback of the device path.
 """
 from __future__ import annotations
 
@@ -27,10 +30,8 @@ __all__ = ["ForwardOperator", "RayTomographyForward", "NearestLookup1D", "Linear
 class ForwardOperator:
     kind = None
 
-    def __call__(self, state):
-        raise TypeError(
-            f"{type(self).__name__} is evaluated inside the CUDA engine; it has no host implementation "
-            "(see oracle/reference_adapters.py for running it inside the unmodified reference)")
+    def __call__(self, state):  # pragma: no cover - abstract
+        raise NotImplementedError
 
     @property
     def __name__(self):
@@ -92,6 +93,31 @@ class RayTomographyForward(ForwardOperator):
     def n_data(self):
         return self.indptr.size - 1
 
+    def __call__(self, state):
+        """Host evaluation on one ``State`` (31_sw_tomography.ipynb cell 12): nearest site of every grid point with
+        the space's cached KD-tree when there is one, then ``jacobian @ field``."""
+        import scipy.sparse
+        import scipy.spatial
+
+        if getattr(self, "_jacobian", None) is None:
+            self._jacobian = scipy.sparse.csr_matrix((self.data, self.indices, self.indptr),
+                                                     shape=(self.indptr.size - 1, self.grid_points.shape[0]))
+        ps = state[self.param_space_name]
+        tree = None
+        if hasattr(ps, "saved_in_cache") and ps.saved_in_cache("kdtree"):
+            tree = ps.load_from_cache("kdtree")
+        if tree is None:
+            tree = scipy.spatial.KDTree(ps["discretization"])
+        field = ps[self.param_name][tree.query(self.grid_points)[1]]
+        if self.save_field_as is not None and hasattr(state, "save_to_extra_storage"):
+            state.save_to_extra_storage(self.save_field_as, field)
+        return self._jacobian @ (1 / field if self.transform == "reciprocal" else field)
+
+    def __getstate__(self):  # (the cached scipy matrix is rebuilt where the object lands)
+        d = dict(self.__dict__)
+        d.pop("_jacobian", None)
+        return d
+
 
 class NearestLookup1D(ForwardOperator):
     """``d_pred[i] = values[nearest_site(x[i])]`` on a Voronoi1D space."""
@@ -106,6 +132,22 @@ class NearestLookup1D(ForwardOperator):
     @property
     def n_data(self):
         return self.x.size
+
+    def __call__(self, state):
+        """``Voronoi1D.interpolate_tessellation(sites, values, x, 'nuclei')`` (discretization/_voronoi.py:705-732;
+        nearest_neighbour_1d, _utils_1d.pyx:102-114): below the first site -> cell 0, past the last -> the last,
+        between two sites the nearer one, the upper one on a tie."""
+        ps = state[self.param_space_name]
+        sites = np.asarray(ps["discretization"], dtype=np.float64)
+        values = np.asarray(ps[self.param_name])
+        k = sites.size
+        if k == 1:
+            return np.full(self.x.shape, values[0])
+        hi = np.clip(np.searchsorted(sites, self.x, side="left"), 1, k - 1)  # first site >= x (clipped): x in [lo, hi]
+        lo = hi - 1
+        idx = np.where(np.abs(sites[lo] - self.x) < np.abs(sites[hi] - self.x), lo, hi)
+        idx = np.where(self.x < sites[0], 0, idx)
+        return values[idx]
 
 
 class LinearForward(ForwardOperator):
@@ -124,6 +166,10 @@ class LinearForward(ForwardOperator):
     def n_data(self):
         return self.G.shape[0]
 
+    def __call__(self, state):  # 02_hierarchical_polyfit.ipynb cell 12
+        ps = state[self.param_space_name]
+        return self.G @ np.concatenate([np.atleast_1d(ps[n]) for n in self.param_names])
+
 
 class PolynomialForward(ForwardOperator):
     """``d_pred = np.vander(x, k, increasing=True) @ state[ps][param]`` with ``k`` the current number of
@@ -140,3 +186,7 @@ class PolynomialForward(ForwardOperator):
     @property
     def n_data(self):
         return self.x.size
+
+    def __call__(self, state):  # 03_transd_polyfit.ipynb cell 5
+        m = np.asarray(state[self.param_space_name][self.param_name])
+        return np.vander(self.x, len(m), True) @ m

@@ -153,9 +153,8 @@ class ParallelTempering(Sampler):
         from ._engine import pt_swap
 
         # the round number (Philox counter of the swap stream) lives with the chains so that it is checkpointed
-        t_out, n_acc = pt_swap(gathered, owner.batch.seed_global, owner.batch.swap_round, owner.chain_id0,
-                               owner.batch.n_chains)
-        owner.batch.engine.temperature.copy_(t_out)
+        _, n_acc = pt_swap(gathered, owner.batch.seed_global, owner.batch.swap_round, owner.chain_id0,
+                           owner.batch.n_chains, out=owner.batch.engine.temperature)
         owner.batch.swap_round += 1
         self._round += 1
         self._last_n_acc = n_acc

@@ -257,7 +257,25 @@ def partition_1d_fixed(n_data=30, n_cells=9, **kw):
 # --------------------------------------------------------------------------- #
 # API-object builder (works with bayesbay_b200 AND the unmodified reference)
 # --------------------------------------------------------------------------- #
-def build_problem(ing, bb, make_forward):
+def forward_operator(ing):
+    """The device forward operator (bayesbay_b200.forward) of a synthetic problem -- also a valid forward function
+    for the unmodified reference."""
+    from .forward import LinearForward, NearestLookup1D, PolynomialForward, RayTomographyForward
+
+    kind = ing["kind"]
+    if kind == "tomography_2d":
+        return RayTomographyForward((ing["indptr"], ing["indices"], ing["data"]), ing["points"], ing["voronoi"]["name"],
+                                    ing["prior"]["name"])
+    if kind == "partition_1d":
+        return NearestLookup1D(ing["x"], ing["voronoi"]["name"], ing["prior"]["name"])
+    if kind == "transd_polyfit":
+        return PolynomialForward(ing["x"], ing["space"]["name"], ing["prior"]["name"])
+    if kind == "polyfit":
+        return LinearForward(ing["G"], ing["space"]["name"], [p["name"] for p in ing["priors"]])
+    raise ValueError(kind)
+
+
+def build_problem(ing, bb, make_forward=forward_operator):
     """Build ``(parameterization, log_likelihood)`` from ingredients using package ``bb``.
 
     ``bb`` is either :mod:`bayesbay_b200` or the reference :mod:`bayesbay` -- the

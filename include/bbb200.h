@@ -295,12 +295,17 @@ int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream)
  * (`LogLikelihood._get_misfit_and_det`, likelihood/_log_likelihood.py:308-332), both [C]. */
 int bbb_engine_misfit_logdet(bbb_engine *e, double *misfit_out, double *logdet_out, void *stream);
 
+/* The rows this engine contributes to a parallel-tempering swap round: [C][3] (misfit, logdet, T), written by one
+ * kernel (what the caller all-gathers over NCCL before bbb_pt_swap). */
+int bbb_engine_swap_rows(bbb_engine *e, double *rows_out, void *stream);
+
 /* Parallel-tempering swap round: `ParallelTempering.on_end_advance_chain`
  * (samplers/_samplers.py:334-342).  `gathered` is [n_total][3] (misfit, logdet, T) for ALL chains
  * of the job in global chain order (all-gathered by the caller over NCCL); every rank runs the
  * same n_total sequential attempts from the shared Philox key (seed, round) and writes the new
- * temperatures of its own chains [id0, id0 + n_local) to temperature_out [n_local]; the temperature
- * column of `gathered` is updated in place.
+ * temperatures of its own chains [id0, id0 + n_local) to temperature_out [n_local] (which may be the engine's own
+ * temperature buffer); the temperature column of `gathered` is updated in place.  Up to 8192 chains the attempts are
+ * replayed in parallel waves of pairwise disjoint attempts (bit-identical to the sequential loop).
  * If `tape` is not NULL the uniforms come from it (3 per attempt). */
 int bbb_pt_swap(double *gathered, int64_t n_total, uint64_t seed, int64_t round,
                 int64_t id0, int64_t n_local, double *temperature_out, int32_t *n_accepted_out,

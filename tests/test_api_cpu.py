@@ -165,8 +165,6 @@ def test_things_that_cannot_run_on_the_device_raise():
         bb.discretization.Voronoi("v", 2, 0, 1, 0.1)
     with pytest.raises(ValueError, match="duplicate"):
         bb.parameterization.Parameterization([ps, ps])
-    with pytest.raises(TypeError):
-        RayTomographyForward((np.array([0, 1]), np.array([0]), np.array([1.0])), np.zeros((1, 2)))(None)
     with pytest.raises(AssertionError):
         bb.likelihood.Target("d", np.zeros(3), std_min=2, std_max=1)
 
