@@ -144,6 +144,7 @@ class ChainBatch:
         self.names = _compile.perturbation_names(spec)
         self.iteration = 0
         self.swap_round = 0
+        self.resumed = False  # set by BayesianInversion.load_checkpoint: the next run keeps the restored temperatures
         self.saved: List[dict] = []  # one entry per save point: host arrays + mask of chains saved
         self._torch = torch
         # posterior field statistics of ray targets that ask for them (per chain: sum, sum of squares, count)
@@ -171,7 +172,8 @@ class ChainBatch:
     # ---- checkpoint / resume ---------------------------------------------
     def state_dict(self) -> dict:
         fields = {t: {k: (v.cpu() if hasattr(v, "cpu") else v) for k, v in fs.items()} for t, fs in self.field_stats.items()}
-        return dict(engine=self.engine.state_dict(), iteration=self.iteration, saved=self.saved, field_stats=fields,
+        # (a copy of the list: a snapshot kept in memory must not grow with the run; the entries are never mutated)
+        return dict(engine=self.engine.state_dict(), iteration=self.iteration, saved=list(self.saved), field_stats=fields,
                     swap_round=self.swap_round, seed_global=getattr(self, "seed_global", self.seed))
 
     def load_state_dict(self, state: dict):
@@ -278,6 +280,7 @@ class ChainBatch:
         ``_save_statistics``, src/bayesbay/_markov_chain.py:106-157)."""
         prop = self.engine.n_proposed.cpu().numpy()
         acc = self.engine.n_accepted.cpu().numpy()
+        exc = self.engine.n_exceptions.cpu().numpy()
         out = []
         for c in range(self.n_chains):
             n_prop = defaultdict(lambda: defaultdict(float))
@@ -297,7 +300,10 @@ class ChainBatch:
                 "n_accepted_models": n_acc,
                 "n_proposed_models_total": int(prop[:, c].sum()),
                 "n_accepted_models_total": int(acc[:, c].sum()),
-                "exceptions": defaultdict(int),
+                # device analogue of the reference's exception counts (_markov_chain.py:205-247): proposals with a
+                # non-finite likelihood ratio (rejected), rejection-sampling loops that gave up (old value kept)
+                "exceptions": defaultdict(int, {k: int(v) for k, v in (("NonFiniteLikelihoodRatio", exc[0, c]),
+                                                                       ("ResamplingLimitReached", exc[1, c])) if v}),
             })
         return out
 

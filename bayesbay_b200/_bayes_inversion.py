@@ -171,10 +171,15 @@ class BayesianInversion(BaseBayesianInversion):
         torch.save(self.batch.state_dict(), path)
 
     def load_checkpoint(self, path):
-        """Continue bit-identically from :meth:`save_checkpoint` (same problem, n_chains, seed and sharding)."""
+        """Continue bit-identically from :meth:`save_checkpoint` (same problem, n_chains, seed and sharding).  The
+        NEXT ``run`` continues the tempering state of the checkpoint: ``ParallelTempering`` keeps the per-chain
+        temperatures as the swap rounds left them (instead of laying the initial ladder again) and
+        ``SimulatedAnnealing`` keeps its schedule position.  The file is a ``torch.save`` pickle of tensors, numpy
+        arrays and ints: load checkpoints from trusted sources only."""
         import torch
 
         self.batch.load_state_dict(torch.load(path, weights_only=False))
+        self.batch.resumed = True
         self._n_saved_synced = 0
         for ch in self._chains:
             ch._saved_states.clear()

@@ -310,12 +310,14 @@ class Engine:
         self.n_proposed = z((nm, Cn), i64)
         self.n_accepted = z((nm, Cn), i64)
         self.draw_cursor = z((Cn,), i64)
+        self.n_exceptions = z((2, Cn), i64)  # non-finite likelihood ratios, resampling loops that gave up
         b.temperature, b.iteration = _ptr(self.temperature), _ptr(self.iteration)
         b.move, b.edit = _ptr(self.move), _ptr(self.edit)
         b.edit_site, b.edit_vals = _ptr(self.edit_site), _ptr(self.edit_vals)
         b.log_prob_ratio, b.log_like_ratio, b.accepted = _ptr(self.log_prob_ratio), _ptr(self.log_like_ratio), _ptr(self.accepted)
         b.n_proposed, b.n_accepted = _ptr(self.n_proposed), _ptr(self.n_accepted)
         b.tape_cursor = _ptr(self.draw_cursor)
+        b.n_exceptions = _ptr(self.n_exceptions)
         # longest-first block order of the chain kernel (scratch of the chain-local step; must start zeroed)
         self.block_order = (z((L.ORDER_BUCKETS * Cn + 128,), i32)
                             if any(x is not None for x in self.idx_cm) and not os.environ.get("BBB_NO_BLOCK_ORDER") else None)
@@ -587,7 +589,7 @@ class Engine:
     # ------------------------------------------------------------------ checkpoint / resume
     def _mutable(self):
         named = {"temperature": self.temperature, "iteration": self.iteration, "n_proposed": self.n_proposed,
-                 "n_accepted": self.n_accepted, "draw_cursor": self.draw_cursor, "move": self.move, "edit": self.edit,
+                 "n_accepted": self.n_accepted, "n_exceptions": self.n_exceptions, "draw_cursor": self.draw_cursor, "move": self.move, "edit": self.edit,
                  "log_prob_ratio": self.log_prob_ratio, "log_like_ratio": self.log_like_ratio, "accepted": self.accepted}
         for i in range(len(self.spec["spaces"])):
             named.update({f"sites{i}": self.sites[i], f"values{i}": self.values[i], f"k{i}": self.k[i], f"sel{i}": self.sel[i]})

@@ -14,7 +14,7 @@ MAX_PARAMS = 8
 MAX_TARGETS = 4
 MAX_LINEAR_PARAMS = 16
 CSC_LEVELS = 3
-ABI_VERSION = 4
+ABI_VERSION = 5
 ORDER_BUCKETS = 10
 
 SPACE_PLAIN, SPACE_VORONOI1D, SPACE_VORONOI2D = 0, 1, 2
@@ -83,6 +83,7 @@ class Buffers(C.Structure):
         ("temperature", _vp), ("iteration", _vp),
         ("move", _vp), ("edit", _vp), ("edit_site", _vp), ("edit_vals", _vp), ("log_prob_ratio", _vp), ("log_like_ratio", _vp), ("accepted", _vp),
         ("n_proposed", _vp), ("n_accepted", _vp),
+        ("n_exceptions", _vp),
         ("tape", _vp), ("tape_stride", C.c_int64), ("tape_cursor", _vp),
         ("block_order", _vp),
     ]

@@ -288,6 +288,8 @@ __device__ inline bool finish_post(const EngineParams &ep, long long c, const Fi
         llr = (old_ld - new_ld + old_m - new_m) / 2.0 / in.temperature;
     }
     const bool accepted = (lpr + llr) > pre.log_u;  // NaN compares false -> rejected
+    // what the reference would surface as a ForwardException / a NaN misfit: counted, the proposal is rejected
+    if (!(fabs(llr) <= 1.79769313486231570815e308) && B.n_exceptions != nullptr) B.n_exceptions[c] += 1;
     if (accepted) {  // (an accepted proposal has a finite lpr, so phi_new is set)
         if (noise) {
             for (int t = 0; t < P.n_targets; ++t) {

@@ -26,6 +26,7 @@ struct Edit {
     double vals[BBB_MAX_PARAMS];
     double lpr;
     bool write;
+    bool gave_up;  // a rejection-sampling loop hit MAX_RESAMPLE (the old value was kept)
 };
 
 // Where a proposal reads the cells of the CURRENT state from: the [..][K][C] arrays in global memory.  (An accessor
@@ -116,25 +117,32 @@ __device__ inline int choose_move(const bbb_problem_spec &P, R &rng) {
 
 // ---- P7 NoisePerturbation.perturb (perturbations/_data_noise.py:21-77) of one hierarchical target: new std (and
 // correlation: to_be_perturbed = ["std", "correlation"], :61-76), each resampled until inside its range
+// (returns true when a loop gave up)
 template <class R>
-__device__ inline void propose_noise_target(const bbb_target_spec &T, R &rng, double old_v, double old_r, double &new_v,
+__device__ inline bool propose_noise_target(const bbb_target_spec &T, R &rng, double old_v, double old_r, double &new_v,
                                             double &new_r) {
+    bool gave_up = true;
     new_v = old_v;
     for (int it = 0; it < MAX_RESAMPLE; ++it) {
         const double cand = old_v + rng.normal(0.0, T.std_perturb_std);
         if (cand < T.std_min || cand > T.std_max) continue;
         new_v = cand;
+        gave_up = false;
         break;
     }
     new_r = old_r;
     if (T.correlated) {
+        bool found = false;
         for (int it = 0; it < MAX_RESAMPLE; ++it) {
             const double cand = old_r + rng.normal(0.0, T.corr_perturb_std);
             if (cand < T.corr_min || cand > T.corr_max) continue;
             new_r = cand;
+            found = true;
             break;
         }
+        gave_up |= !found;
     }
+    return gave_up;
 }
 
 // ---- P2-P6: one move of kind `inner` on a space whose current state (k cells) is read through `cells`; the
@@ -145,6 +153,7 @@ __device__ inline void propose_space_move(const bbb_space_spec &S, const Cells &
     e.ins = -1;
     e.lpr = 0.0;
     e.write = true;
+    e.gave_up = false;
     e.site[0] = e.site[1] = 0.0;
 
     if (inner == BBB_MOVE_VALUES) {
@@ -166,6 +175,7 @@ __device__ inline void propose_space_move(const bbb_space_spec &S, const Cells &
         for (int p = 0; p < S.n_params; ++p) e.vals[p] = cells.value(p, idx);
         double old_site[2] = {0.0, 0.0};
         for (int d = 0; d < S.ndim; ++d) old_site[d] = e.site[d] = cells.site(d, idx);
+        e.gave_up = true;
         for (int it = 0; it < MAX_RESAMPLE; ++it) {
             double cand[2];
             bool ok = true;
@@ -175,6 +185,7 @@ __device__ inline void propose_space_move(const bbb_space_spec &S, const Cells &
             }
             if (ok) {
                 for (int d = 0; d < S.ndim; ++d) e.site[d] = cand[d];
+                e.gave_up = false;
                 break;
             }
         }
@@ -333,7 +344,8 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
             const bbb_target_spec &T = P.targets[t];
             if (T.cov_kind != BBB_COV_HIERARCHICAL) continue;
             double new_v, new_r;
-            propose_noise_target(T, rng, B.sigma[t][c], T.correlated ? B.corr[t][c] : 0.0, new_v, new_r);
+            const bool gave_up = propose_noise_target(T, rng, B.sigma[t][c], T.correlated ? B.corr[t][c] : 0.0, new_v, new_r);
+            if (gave_up && writer && B.n_exceptions != nullptr) B.n_exceptions[B.n_chains + c] += 1;
             if (writer) B.sigma[t][B.n_chains + c] = new_v;
             if (T.correlated && writer) B.corr[t][B.n_chains + c] = new_r;
         }
@@ -359,6 +371,7 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         for (int p = 0; p < S.n_params; ++p) B.edit_vals[(long long)p * B.n_chains + c] = e.vals[p];
     }
     (void)k_new;
+    if (writer && e.gave_up && B.n_exceptions != nullptr) B.n_exceptions[B.n_chains + c] += 1;
     if (writer) {
         B.move[c] = 4 * s + inner;
         B.edit[c] = e.rm;

@@ -100,7 +100,7 @@ class VanillaSampler(Sampler):
     """High-level class for the Vanilla MCMC sampler (reference :242-276)."""
 
     def on_initialize(self, chains):
-        pass
+        self._owner.batch.resumed = False
 
     def on_end_advance_chain(self):
         pass
@@ -130,6 +130,12 @@ class ParallelTempering(Sampler):
 
     def on_initialize(self, chains):
         owner = self._owner
+        if owner.batch.resumed:
+            # continuing a checkpoint: the per-chain temperatures ARE the accumulated swap permutation
+            owner.batch.resumed = False
+            for c, t in enumerate(owner.batch.temperatures()):
+                chains[c].temperature = float(t)
+            return
         n_total = owner.n_chains_global
         if self._temperatures is not None:
             if self._temperatures.size != n_total:
@@ -185,6 +191,9 @@ class SimulatedAnnealing(Sampler):
         self.cooling_fraction = float(cooling_fraction)
 
     def on_initialize(self, chains):
+        if self._owner.batch.resumed:  # continuing a checkpoint: the schedule is a function of the iteration counter
+            self._owner.batch.resumed = False
+            return
         self._owner.batch.set_temperatures(np.full(len(chains), float(self.temperature_start)))
         for chain in chains:
             chain.temperature = self.temperature_start

@@ -178,9 +178,10 @@ def _piecewise(x):
 
 
 def partition_1d(n_data=100, noise_std=5.0, seed=30, kmin=2, kmax=40, birth_from="prior", correlated=False,
-                 position_dependent=False):
+                 position_dependent=False, prior_kind="uniform"):
     """1-D Voronoi piecewise-constant regression (config C1).  ``position_dependent`` gives the value prior
-    position-dependent bounds and step sizes (reference prior/_prior.py:257-297, tests/19_*.py)."""
+    position-dependent bounds and step sizes (reference prior/_prior.py:257-297, tests/19_*.py);
+    ``prior_kind="laplace"`` puts a LaplacePrior(mean 0, scale 15) on the cell values."""
     x = np.linspace(0.0, 10.0, n_data)
     rng = np.random.RandomState(seed)  # the notebook uses legacy np.random.seed(30)
     d_obs = _piecewise(x) + rng.normal(0.0, noise_std, x.size)
@@ -189,7 +190,8 @@ def partition_1d(n_data=100, noise_std=5.0, seed=30, kmin=2, kmax=40, birth_from
         x=x, d_obs=d_obs,
         prior=(dict(name="y", vmin=[-35.0, -20.0, -35.0], vmax=[35.0, 40.0, 10.0], perturb_std=[3.5, 2.0, 4.0],
                     perturb_std_birth=[5.0, 3.0, 5.0], position=[0.0, 5.0, 10.0]) if position_dependent
-               else dict(name="y", vmin=-35.0, vmax=35.0, perturb_std=3.5)),
+               else (dict(kind="laplace", name="y", mean=0.0, scale=15.0, perturb_std=3.5) if prior_kind == "laplace"
+                     else dict(name="y", vmin=-35.0, vmax=35.0, perturb_std=3.5))),
         voronoi=dict(name="voronoi", vmin=0.0, vmax=10.0, perturb_std=0.75,
                      n_dimensions_min=kmin, n_dimensions_max=kmax, birth_from=birth_from),
         target=dict(name="d_obs", std_min=0.0, std_max=20.0, std_perturb_std=2.0,
@@ -289,7 +291,8 @@ def build_problem(ing, bb, make_forward=forward_operator):
         vel = bb.prior.UniformPrior(p["name"], vmin=p["vmin"], vmax=p["vmax"], perturb_std=p["perturb_std"])
         space = bb.discretization.Voronoi2D(parameters=[vel], **ing["voronoi"])
     elif kind == "partition_1d":
-        y = bb.prior.UniformPrior(**ing["prior"])
+        p = dict(ing["prior"])
+        y = {"uniform": bb.prior.UniformPrior, "laplace": bb.prior.LaplacePrior}[p.pop("kind", "uniform")](**p)
         space = bb.discretization.Voronoi1D(parameters=[y], **ing["voronoi"])
     elif kind == "transd_polyfit":
         coeff = bb.prior.UniformPrior(**ing["prior"])

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BBB_ABI_VERSION 4
+#define BBB_ABI_VERSION 5
 #define BBB_ORDER_BUCKETS 10
 
 #define BBB_MAX_SPACES 4
@@ -182,6 +182,12 @@ typedef struct {
     /* statistics: _save_statistics (src/bayesbay/_markov_chain.py:136-157) */
     int64_t *n_proposed;     /* [4*n_spaces+1][C] */
     int64_t *n_accepted;     /* [4*n_spaces+1][C] */
+    /* optional (NULL: not counted), ZERO-INITIALISED by the caller: what the reference would have reported as
+     * exceptions (`statistics["exceptions"]`, src/bayesbay/_markov_chain.py:205-247).  Row 0: proposals whose likelihood
+     * ratio was not finite (NaN / infinite forward or misfit; rejected).  Row 1: rejection-sampling loops of a site or
+     * noise move (unbounded in the reference, _voronoi.py:171-188, _data_noise.py:61-76) that gave up after 100 000
+     * tries and kept the old value. */
+    int64_t *n_exceptions;   /* [2][C] */
     /* optional recorded uniforms (step-replay parity); NULL selects Philox */
     const double *tape;      /* [C][tape_stride] */
     int64_t tape_stride;

@@ -141,6 +141,24 @@ def _np_normal(loc=0.0, scale=1.0, size=None):
     return np.array([loc_b[i] + scale_b[i] * _std_normal() for i in range(n)]).reshape(size)
 
 
+def _np_laplace(loc=0.0, scale=1.0, size=None):
+    """numpy's inverse-CDF rule on one uniform per value (oracle/rng.py draw_laplace)."""
+    def one(mu, b):
+        u = TAPE.u()
+        if u >= 0.5:
+            return mu - b * math.log(2.0 - u - u)
+        if u > 0.0:
+            return mu + b * math.log(u + u)
+        return mu
+
+    if size is None:
+        return one(loc, scale)
+    n = int(np.prod(size))
+    loc_b = np.broadcast_to(np.asarray(loc, dtype=float), (n,))
+    scale_b = np.broadcast_to(np.asarray(scale, dtype=float), (n,))
+    return np.array([one(loc_b[i], scale_b[i]) for i in range(n)]).reshape(size)
+
+
 def _np_choice(a, size=None, replace=True, p=None):
     assert size == 2 and replace is False
     n = len(a)
@@ -160,6 +178,7 @@ def install_patches():
     random.gauss = _p_normalvariate
     np.random.uniform = _np_uniform
     np.random.normal = _np_normal
+    np.random.laplace = _np_laplace
     np.random.choice = _np_choice
 
 
@@ -501,6 +520,63 @@ def pt_golden(bb):
     np.savez_compressed(os.path.join(HERE, "pt_ladder.npz"), **lad)
 
 
+def sa_golden(bb):
+    """Tape-driven ``SimulatedAnnealing.run`` (samplers/_samplers.py:368-448) on polyfit chains, one chain at a time in
+    this process (n_jobs = 1): per iteration the temperature the iteration ran at, the accept count, sigma and the
+    coefficients, and the tape position -- the device schedule is replayed against it."""
+    global TAPE
+    from bayesbay_b200 import synthetic
+
+    ing = synthetic.polyfit()
+    n_chains, n_it, burnin = 4, 60, 40
+    t_start, frac = 8.0, 0.6
+    out = dict(temperature=np.zeros((n_chains, n_it)), accepted=np.zeros((n_chains, n_it), np.int64),
+               sigma=np.zeros((n_chains, n_it + 1)), values=np.zeros((n_chains, n_it + 1, 4)),
+               cursor=np.zeros((n_chains, n_it + 1), np.int64))
+    tapes = []
+    for c in range(n_chains):
+        TAPE = Tape(500 + c)
+        parameterization, log_likelihood = synthetic.build_problem(ing, bb, reference_forward)
+        inv = bb.BayesianInversion(parameterization, log_likelihood, n_chains=1)
+        chain = inv.chains[0]
+        sampler = bb.samplers.SimulatedAnnealing(temperature_start=t_start, cooling_fraction=frac)
+        rec = dict(t=[], acc=[], sig=[], val=[], cur=[])
+
+        def snap(ch):
+            st = ch.current_state
+            rec["sig"].append(st["my_data"].std)
+            rec["val"].append([float(np.squeeze(st["my_param_space"][f"m{i}"])) for i in range(4)])
+            rec["cur"].append(TAPE.n)
+
+        snap(chain)
+        sampler.add_on_begin_iteration(lambda s, ch: None)
+        # the temperature an iteration runs at is set by on_begin_iteration; read it right after
+        orig_begin = sampler.on_begin_iteration
+
+        def begin(ch, _o=orig_begin):
+            _o(ch)
+            rec["t"].append(ch.temperature)
+
+        sampler.on_begin_iteration = begin
+        sampler.add_on_end_iteration(lambda s, ch: (rec["acc"].append(ch.statistics["n_accepted_models_total"]), snap(ch)))
+        inv.run(sampler=sampler, n_iterations=n_it, burnin_iterations=burnin, save_every=10, verbose=False,
+                parallel_config={"n_jobs": 1})
+        out["temperature"][c] = rec["t"]
+        out["accepted"][c] = rec["acc"]
+        out["sigma"][c] = rec["sig"]
+        out["values"][c] = rec["val"]
+        out["cursor"][c] = rec["cur"]
+        tapes.append(TAPE.values[: TAPE.n].copy())
+        meta = (sampler.cooling_rate, sampler.cooling_iterations)
+    L = max(t.size for t in tapes)
+    tape = np.zeros((n_chains, L))
+    for c, t in enumerate(tapes):
+        tape[c, : t.size] = t
+    np.savez_compressed(os.path.join(HERE, "sa_schedule.npz"), tape=tape, temperature_start=t_start, cooling_fraction=frac,
+                        burnin_iterations=burnin, n_iterations=n_it, cooling_rate=meta[0], cooling_iterations=meta[1], **out)
+    print("sa_schedule.npz: temperatures", np.round(out["temperature"][0, ::8], 3), "cooling iterations", meta[1])
+
+
 # --------------------------------------------------------------------------- #
 # 5. long-run statistics with the reference's own RNG (distributional targets)
 # --------------------------------------------------------------------------- #
@@ -580,11 +656,14 @@ def main():
            name="partition_1d_corr")
     replay(bb, synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour", position_dependent=True),
            n_chains=6, n_steps=100, seed0=280, name="partition_1d_posdep")
+    replay(bb, synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour", prior_kind="laplace"),
+           n_chains=6, n_steps=100, seed0=285, name="partition_1d_laplace")
     replay(bb, synthetic.partition_1d_fixed(), n_chains=4, n_steps=60, seed0=290, name="partition_1d_fixed")
     replay(bb, synthetic.transd_polyfit(), n_chains=8, n_steps=100, seed0=295, name="transd_polyfit")
     replay(bb, synthetic.polyfit(), n_chains=8, n_steps=60, seed0=300, name="polyfit")
     replay(bb, synthetic.polyfit(all_gaussian=False), n_chains=4, n_steps=60, seed0=350, name="polyfit_nb")
     pt_golden(bb)
+    sa_golden(bb)
 
 
 if __name__ == "__main__":

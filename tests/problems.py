@@ -91,6 +91,8 @@ REPLAYS = {
     "partition_1d_corr": lambda: synthetic.partition_1d(n_data=30, kmin=2, kmax=12, correlated=True),
     "partition_1d_posdep": lambda: synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour",
                                                           position_dependent=True),
+    "partition_1d_laplace": lambda: synthetic.partition_1d(n_data=30, kmin=2, kmax=12, birth_from="neighbour",
+                                                           prior_kind="laplace"),
     "partition_1d_fixed": synthetic.partition_1d_fixed,
     "transd_polyfit": synthetic.transd_polyfit,
     "polyfit": synthetic.polyfit,

@@ -376,3 +376,70 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     assert np.array_equal(inv.get_field_statistics("interp_vel")["mean"], inv2.get_field_statistics("interp_vel")["mean"])
     with pytest.raises(ValueError):
         make_inversion(ing, 24, seed=100).load_checkpoint(ck)
+
+
+def test_checkpoint_resume_under_parallel_tempering(tmp_path):
+    """A checkpoint taken between two parallel-tempering runs continues with the temperatures the swap rounds left
+    (the accumulated permutation), not with the initial ladder: states, temperatures and samples of the continued
+    run are bit-identical to the uninterrupted one."""
+    ing = problems.tomo_small()
+    kw = dict(temperature_max=4.0, chains_with_unit_temperature=0.4, swap_every=25)
+    inv = make_inversion(ing, 24, seed=7)
+    inv.run(sampler=bb.samplers.ParallelTempering(**kw), n_iterations=100, burnin_iterations=20, save_every=10, verbose=False)
+    t_mid = inv.batch.temperatures().copy()
+    ck = tmp_path / "pt.pt"
+    inv.save_checkpoint(ck)
+    snap = inv.batch.state_dict()
+    n_snap = len(snap["saved"])
+
+    inv2 = make_inversion(ing, 24, seed=7)
+    inv2.load_checkpoint(ck)
+    np.testing.assert_array_equal(inv2.batch.temperatures(), t_mid)
+    s2 = bb.samplers.ParallelTempering(**kw)
+    inv2.run(sampler=s2, n_iterations=200, burnin_iterations=20, save_every=10, verbose=False)
+
+    # the uninterrupted continuation: same engine, temperatures kept by hand (what a resumed run must reproduce)
+    inv.batch.resumed = True
+    inv.run(sampler=bb.samplers.ParallelTempering(**kw), n_iterations=200, burnin_iterations=20, save_every=10, verbose=False)
+    assert len(snap["saved"]) == n_snap  # the in-memory snapshot did not grow with the run
+    np.testing.assert_array_equal(inv.batch.temperatures(), inv2.batch.temperatures())
+    assert inv.batch.swap_round == inv2.batch.swap_round
+    for sa, sb in zip(inv.batch.engine.fetch_states(), inv2.batch.engine.fetch_states()):
+        assert np.array_equal(sa["spaces"][0]["sites"], sb["spaces"][0]["sites"])
+        assert np.array_equal(sa["spaces"][0]["values"][0], sb["spaces"][0]["values"][0])
+    assert inv.get_results()["d_obs.std"] == inv2.get_results()["d_obs.std"]
+    # a fresh run, by contrast, lays the ladder again
+    inv3 = make_inversion(ing, 24, seed=7)
+    inv3.run(sampler=bb.samplers.ParallelTempering(**kw), n_iterations=25, burnin_iterations=0, save_every=10, verbose=False)
+    assert sorted(inv3.batch.temperatures()) == sorted(t_mid)
+
+
+def test_simulated_annealing_against_reference_fixture(golden_dir):
+    """Tape-driven ``SimulatedAnnealing.run`` of the unmodified reference (tests/golden/sa_schedule.npz): the device
+    schedule runs every iteration at the reference's temperature and -- fed the same tape -- makes the same decisions."""
+    from bayesbay_b200._engine import Engine
+
+    g = np.load(os.path.join(golden_dir, "sa_schedule.npz"))
+    spec = problems.spec_from_ingredients(synthetic.polyfit())
+    n_chains, n_it = g["temperature"].shape
+    eng = Engine(spec, n_chains, tape=g["tape"])
+    eng.init_states()
+    assert np.array_equal(eng.draw_cursor.cpu().numpy(), g["cursor"][:, 0])
+    sa = bb.samplers.SimulatedAnnealing(temperature_start=float(g["temperature_start"]), cooling_fraction=float(g["cooling_fraction"]))
+    # the schedule constants as SimulatedAnnealing.run derives them (samplers/_samplers.py:430-439)
+    burnin = int(g["burnin_iterations"])
+    cf = min(max(sa.cooling_fraction, 0.0), 1.0)
+    cooling_iterations = max(1, min(burnin, int(round(cf * burnin))))
+    rate = math.log(sa.temperature_start) / cooling_iterations
+    assert cooling_iterations == int(g["cooling_iterations"]) and rate == float(g["cooling_rate"])
+    eng.set_annealing(sa.temperature_start, rate, cooling_iterations, burnin)
+    acc_total = np.zeros(n_chains, np.int64)
+    for t in range(n_it):
+        eng.step(1)
+        np.testing.assert_allclose(eng.temperature.cpu().numpy(), g["temperature"][:, t], rtol=1e-15)
+        acc_total += eng.accepted.cpu().numpy()
+        assert np.array_equal(acc_total, g["accepted"][:, t]), t
+        assert np.array_equal(eng.draw_cursor.cpu().numpy(), g["cursor"][:, t + 1]), t
+        np.testing.assert_allclose(eng.sigma[0][0].cpu().numpy(), g["sigma"][:, t + 1], rtol=1e-12)
+        for c, st in enumerate(eng.fetch_states()):
+            np.testing.assert_allclose([v[0] for v in st["spaces"][0]["values"]], g["values"][c, t + 1], rtol=1e-12)

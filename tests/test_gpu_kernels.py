@@ -169,7 +169,7 @@ def test_ray_forward_vs_oracle_and_golden(lib, kg):
             ref, ridx = OK.tomography_forward(fwd, sites_list[c], vals_list[c])
             np.testing.assert_allclose(d[:, c], ref, rtol=RTOL)
             res = ref - ing["d_obs"]
-            np.testing.assert_allclose(phi[c].item(), np.sum((1.0 if wt is None else wt) * res * res), rtol=1e-11)
+            np.testing.assert_allclose(phi[c].item(), np.sum((1.0 if wt is None else wt) * res * res), rtol=1e-12)
     # identity transform
     chk(lib.bbb_ray_forward(ptr(idx), ptr(dev(v)), ptr(dev(k)), K, Cn, G, R, ptr(dev(indptr, np.int32)),
                             ptr(dev(indices, np.int32)), ptr(dev(data)), 0, ptr(dev(ing["d_obs"])), None, ptr(dpred),

@@ -38,6 +38,12 @@ for rep in range(3):
     e1.record()
     torch.cuda.synchronize()
     out.append((ms.mean(), e0.elapsed_time(e1) / steps))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+eng.step(1024)
+e1.record()
+torch.cuda.synchronize()
+print("1024 iterations in one call: %.4f ms/step" % (e0.elapsed_time(e1) / 1024))
 fl = min(o[0] for o in out)
 bb = min(o[1] for o in out)
 print("flushed %.4f ms/step (%.2f M/s)   back-to-back %.4f ms/step (%.2f M/s)   all: %s" % (
