@@ -172,8 +172,10 @@ class ChainBatch:
     # ---- checkpoint / resume ---------------------------------------------
     def state_dict(self) -> dict:
         fields = {t: {k: (v.cpu() if hasattr(v, "cpu") else v) for k, v in fs.items()} for t, fs in self.field_stats.items()}
-        # (a copy of the list: a snapshot kept in memory must not grow with the run; the entries are never mutated)
-        return dict(engine=self.engine.state_dict(), iteration=self.iteration, saved=list(self.saved), field_stats=fields,
+        self.flush_saves()
+        # (a copy of the list: a snapshot kept in memory must not grow with the run; the entries' arrays are never mutated)
+        saved = [{k: v for k, v in e.items() if k != "views"} for e in self.saved]
+        return dict(engine=self.engine.state_dict(), iteration=self.iteration, saved=saved, field_stats=fields,
                     swap_round=self.swap_round, seed_global=getattr(self, "seed_global", self.seed))
 
     def load_state_dict(self, state: dict):
@@ -197,83 +199,259 @@ class ChainBatch:
             if save:
                 self._save()
 
-    def _to_host(self, dev_tensor):
-        """Device -> host through a reusable PINNED staging buffer (a pageable ``.cpu()`` of the [C][R] d_pred image
-        of a save point runs at a few GB/s), returned as a numpy array the caller owns."""
-        t = self._torch
-        n = dev_tensor.numel() * dev_tensor.element_size()
-        if getattr(self, "_stage", None) is None or self._stage.numel() < n:
-            self._stage = t.empty((max(n, 1 << 20),), dtype=t.uint8, pin_memory=True)
-        dst = self._stage[:n].view(dev_tensor.dtype).view(dev_tensor.shape)
-        dst.copy_(dev_tensor.contiguous(), non_blocking=True)
-        t.cuda.current_stream(dev_tensor.device).synchronize()
-        return dst.numpy().copy()
+    # ---- save points: device image -> pinned ring -> host, off the stepping stream -----------------------------
+    N_SLOTS = 3  # images in flight (device buffer + pinned host buffer each)
+
+    def _save_setup(self):
+        """Layout of a save-point image (bbb_engine_save_point, include/bbb200.h) and the transfer machinery: a ring of
+        device images written by the save kernels on the stepping stream, copied to a ring of pinned host buffers on a
+        copy stream, and handed to the sample list by a worker thread -- the chains keep stepping meanwhile."""
+        import queue
+        import threading
+
+        t, eng, C = self._torch, self.engine, self.n_chains
+        self._kb_save = [sp["kmax"] for sp in self.spec["spaces"]]  # (all cell rows travel: no sync to learn the largest k)
+        off = 0
+        lay = dict(spaces=[], noise=[], dpred=[])
+        for sp, kb in zip(self.spec["spaces"], self._kb_save):
+            nd, P = sp["ndim"], len(sp["params"])
+            lay["spaces"].append(dict(k=off, sites=off + C, values=off + C + C * kb * nd, kb=kb, nd=nd, P=P))
+            off += C * (1 + kb * (nd + P))
+        for tg in self.spec["targets"]:
+            ent = dict(sigma=None, corr=None)
+            if tg["hierarchical"]:
+                ent["sigma"] = off
+                off += C
+                if tg.get("correlated"):
+                    ent["corr"] = off
+                    off += C
+            lay["noise"].append(ent)
+        lay["temperature"] = off
+        off += C
+        for tg in self.spec["targets"]:
+            R = int(np.asarray(tg["dobs"]).size)
+            lay["dpred"].append((off, R) if self.save_dpred else None)
+            if self.save_dpred:
+                off += C * R
+        lay["words"] = off
+        if 8 * off != eng.save_point_bytes(self._kb_save, self.save_dpred):
+            raise RuntimeError("save-point layout mismatch between the host and libbbb200.so")
+        self._lay = lay
+        dev = eng.device
+        self._save_dev = [t.empty((off,), dtype=t.int64, device=dev) for _ in range(self.N_SLOTS)]
+        self._save_pin = [t.empty((off,), dtype=t.int64, pin_memory=True) for _ in range(self.N_SLOTS)]
+        self._save_packed = [t.cuda.Event() for _ in range(self.N_SLOTS)]
+        self._save_copied = [t.cuda.Event() for _ in range(self.N_SLOTS)]
+        self._save_used = [False] * self.N_SLOTS
+        self._copy_stream = t.cuda.Stream(device=dev)
+        needs_scratch = self.save_dpred and any(not (eng.chain_local and eng.res[i] is not None)
+                                                for i in range(len(self.spec["targets"])))
+        r_max = max((int(np.asarray(tg["dobs"]).size) for tg in self.spec["targets"]), default=0)
+        self._save_scratch = t.empty((r_max, C), dtype=t.float64, device=dev) if needs_scratch and r_max else None
+        self._free = queue.Queue()
+        for i in range(self.N_SLOTS):
+            self._free.put(i)
+        self._todo = queue.Queue()
+        self._save_errors = []
+        # (the worker holds the queues, events and pinned buffers, not the batch: the batch stays collectable)
+        self._worker = threading.Thread(target=self._save_worker, daemon=True,
+                                        args=(self._todo, self._free, self._save_copied, self._save_pin, self._save_errors))
+        self._worker.start()
+
+    @staticmethod
+    def _save_worker(todo, free, copied, pinned, errors):
+        while True:
+            item = todo.get()
+            if item is None:
+                todo.task_done()
+                return
+            slot, entry = item
+            try:
+                copied[slot].synchronize()
+                entry["image"] = pinned[slot].numpy().copy()  # (the GIL is released for the copy)
+            except Exception as exc:  # pragma: no cover
+                errors.append(exc)
+            finally:
+                free.put(slot)
+                todo.task_done()
+
+    def __del__(self):
+        todo = getattr(self, "_todo", None)
+        if todo is not None:
+            todo.put(None)
+
+    def flush_saves(self):
+        """Wait until every save point submitted so far has arrived in ``self.saved``."""
+        if getattr(self, "_todo", None) is not None:
+            self._todo.join()
+            if self._save_errors:
+                raise self._save_errors[0]
 
     def _save(self):
-        """One save point.  Host arrays are stored CHAIN-MAJOR (``[C][...]``) so that handing a chain its samples
-        (:meth:`saved_states_of`) copies contiguous rows."""
-        eng = self.engine
-        temps = eng.temperature.cpu().numpy()
-        mask = temps == 1.0
-        if not mask.any():
-            return
-        entry = dict(mask=mask, spaces=[], sigma=[], corr=[], dpred=[], fields={}, chain_major=True)
-        for t, fs in self.field_stats.items():
+        """One save point: the save kernels write the chain-major image into a free device slot (stepping stream), the
+        copy stream brings it to pinned host memory, the worker thread appends it to the sample list.  Nothing here
+        waits for the device unless all slots are in flight."""
+        t, eng = self._torch, self.engine
+        if getattr(self, "_lay", None) is None:
+            self._save_setup()
+        entry = dict(image=None, layout=self._lay, fields={}, chain_major=True)
+        for ti, fs in self.field_stats.items():
             # rasterised field of the current states: cell value looked up through the resident nearest-site index
-            f = self.spec["targets"][t]["forward"]
+            f = self.spec["targets"][ti]["forward"]
             _, _, vals = eng.gather_space(f["space"])
-            field = self._torch.gather(vals[f["param"]], 0, eng.current_cell_idx(t).long() & 0xFFFF)  # [G][C]
-            m = self._torch.as_tensor(mask, device=field.device)
+            field = t.gather(vals[f["param"]], 0, eng.current_cell_idx(ti).long() & 0xFFFF)  # [G][C]
+            m = (eng.temperature == 1.0).to(field.dtype)
             fs["sum"] += field * m
             fs["sumsq"] += field * field * m
             fs["count"] += m
             if fs["store"]:
-                entry["fields"][fs["name"]] = self._to_host(field.t())  # [C][G]
-        for s in range(len(self.spec["spaces"])):
-            k, sites, vals = eng.gather_space(s)
-            kb = max(int(k.max().item()), 1)  # only the cells in use travel
-            entry["spaces"].append((k.cpu().numpy(),
-                                    None if sites is None else self._to_host(sites[:, :kb].permute(2, 1, 0)),   # [C][kb][ndim]
-                                    None if vals is None else self._to_host(vals[:, :kb].permute(2, 0, 1))))    # [C][P][kb]
-        for t, tg in enumerate(self.spec["targets"]):
-            entry["sigma"].append(eng.sigma[t][0].cpu().numpy() if tg["hierarchical"] else None)
-            entry["corr"].append(eng.corr[t][0].cpu().numpy() if tg.get("correlated") else None)
-            entry["dpred"].append(self._to_host(eng.dpred_chain_major(t)) if self.save_dpred else None)  # [C][R]
+                entry["fields"][fs["name"]] = field.t().contiguous().cpu().numpy()  # [C][G]
+        slot = self._free.get()  # (blocks only when N_SLOTS images are in flight)
+        main = t.cuda.current_stream(eng.device)
+        if self._save_used[slot]:
+            main.wait_event(self._save_copied[slot])  # the slot's previous image has left the device buffer
+        eng.save_point(self._kb_save, self.save_dpred, self._save_dev[slot], self._save_scratch)
+        self._save_packed[slot].record(main)
+        with t.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._save_packed[slot])
+            self._save_pin[slot].copy_(self._save_dev[slot], non_blocking=True)
+            self._save_copied[slot].record(self._copy_stream)
+        self._save_used[slot] = True
         self.saved.append(entry)
+        self._todo.put((slot, entry))
+
+    @staticmethod
+    def _entry_views(entry, spec, C):
+        """Numpy views into a save point's host image: mask of saved chains, per space (k, sites, values), noise, d_pred."""
+        if "views" in entry:
+            return entry["views"]
+        img, lay = entry["image"], entry["layout"]
+        f64 = img.view(np.float64)
+        v = dict(mask=f64[lay["temperature"]: lay["temperature"] + C] == 1.0, spaces=[], sigma=[], corr=[], dpred=[])
+        for sl in lay["spaces"]:
+            kb, nd, P = sl["kb"], sl["nd"], sl["P"]
+            v["spaces"].append((img[sl["k"]: sl["k"] + C],
+                                f64[sl["sites"]: sl["sites"] + C * kb * nd].reshape(C, kb, nd) if nd else None,
+                                f64[sl["values"]: sl["values"] + C * P * kb].reshape(C, P, kb) if P else None))
+        for nl in lay["noise"]:
+            v["sigma"].append(None if nl["sigma"] is None else f64[nl["sigma"]: nl["sigma"] + C])
+            v["corr"].append(None if nl["corr"] is None else f64[nl["corr"]: nl["corr"] + C])
+        for dl in lay["dpred"]:
+            v["dpred"].append(None if dl is None else f64[dl[0]: dl[0] + C * dl[1]].reshape(C, dl[1]))
+        entry["views"] = v
+        return v
 
     # ---- results in the reference's shapes -------------------------------
     def saved_states_of(self, c: int, start: int = 0):
         """``chain.saved_states`` (src/bayesbay/_markov_chain.py:115-134): ``defaultdict(list)`` keyed
         ``"{ps}.n_dimensions"`` (trans-d only), ``"{ps}.discretization"``, ``"{ps}.{param}"``,
         ``"{target}.std"``, ``"{target}.dpred"``."""
+        self.flush_saves()
         out = defaultdict(list)
+        C = self.n_chains
         for entry in self.saved[start:]:
-            if not entry["mask"][c]:
+            if entry.get("image") is None and "spaces" in entry:
+                self._legacy_entry(entry, c, out)  # (checkpoints written before the image layout)
                 continue
-            cm = entry.get("chain_major", False)  # False: checkpoints written before the chain-major layout
-            for sp, (k, sites, vals) in zip(self.spec["spaces"], entry["spaces"]):
+            v = self._entry_views(entry, self.spec, C)
+            if not v["mask"][c]:
+                continue
+            for sp, (k, sites, vals) in zip(self.spec["spaces"], v["spaces"]):
                 kc = int(k[c])
                 if sp["trans_d"]:
                     out[f"{sp['name']}.n_dimensions"].append(kc)
                 if sp["ndim"] == 1:
-                    out[f"{sp['name']}.discretization"].append((sites[c, :kc, 0] if cm else sites[0, :kc, c]).copy())
+                    out[f"{sp['name']}.discretization"].append(sites[c, :kc, 0].copy())
                 elif sp["ndim"] == 2:
-                    out[f"{sp['name']}.discretization"].append((sites[c, :kc] if cm else sites[:, :kc, c].T).copy())
+                    out[f"{sp['name']}.discretization"].append(sites[c, :kc].copy())
                 for j, p in enumerate(sp["params"]):
-                    out[f"{sp['name']}.{p['name']}"].append((vals[c, j, :kc] if cm else vals[j, :kc, c]).copy())
-            for i, (tg, sg) in enumerate(zip(self.spec["targets"], entry["sigma"])):
+                    out[f"{sp['name']}.{p['name']}"].append(vals[c, j, :kc].copy())
+            for tg, sg, rr in zip(self.spec["targets"], v["sigma"], v["corr"]):
                 if sg is not None:
                     out[f"{tg['name']}.std"].append(float(sg[c]))
-                rr = entry.get("corr", [None] * len(entry["sigma"]))[i]
                 if rr is not None:  # DataNoiseState.todict: "{target}.correlation" (reference _state.py:26-46)
                     out[f"{tg['name']}.correlation"].append(float(rr[c]))
-            for tg, dp in zip(self.spec["targets"], entry["dpred"]):
+            for tg, dp in zip(self.spec["targets"], v["dpred"]):
                 if dp is not None:
-                    # (chain-major blocks: the chain's row is handed out as a view -- one host copy per sample less)
-                    out[f"{tg['name']}.dpred"].append(dp[c] if cm else dp[:, c].copy())
+                    out[f"{tg['name']}.dpred"].append(dp[c])  # (the chain's row of the image, handed out as a view)
             for name, field in entry.get("fields", {}).items():
-                out[name].append(field[c] if cm else field[:, c].copy())
+                out[name].append(field[c])
         return out
+
+    def results(self, keys=None):
+        """All saved samples of all chains of this batch in the order of the reference's ``get_results`` with
+        ``concatenate_chains=True`` (chain by chain, ``_bayes_inversion.py:310-318``), built per save point from
+        views of the host images instead of per chain."""
+        self.flush_saves()
+        if any(e.get("image") is None for e in self.saved):
+            return None  # (entries of an old checkpoint layout: the per-chain path handles them)
+        C, E = self.n_chains, len(self.saved)
+        want = (lambda k: True) if keys is None else (lambda k: k in keys)
+        cols = defaultdict(list)
+        masks = []
+        for entry in self.saved:
+            v = self._entry_views(entry, self.spec, C)
+            masks.append(v["mask"])
+            for sp, (k, sites, vals) in zip(self.spec["spaces"], v["spaces"]):
+                kl = k.tolist()
+                name = sp["name"]
+                if sp["trans_d"] and want(f"{name}.n_dimensions"):
+                    cols[f"{name}.n_dimensions"].append(kl)
+                if sp["ndim"] and want(f"{name}.discretization"):
+                    cols[f"{name}.discretization"].append([sites[c, :kc, 0] for c, kc in enumerate(kl)] if sp["ndim"] == 1
+                                                          else [sites[c, :kc] for c, kc in enumerate(kl)])
+                for j, p in enumerate(sp["params"]):
+                    if want(f"{name}.{p['name']}"):
+                        cols[f"{name}.{p['name']}"].append([vals[c, j, :kc] for c, kc in enumerate(kl)])
+            for tg, sg, rr, dp in zip(self.spec["targets"], v["sigma"], v["corr"], v["dpred"]):
+                if sg is not None and want(f"{tg['name']}.std"):
+                    cols[f"{tg['name']}.std"].append(sg.tolist())
+                if rr is not None and want(f"{tg['name']}.correlation"):
+                    cols[f"{tg['name']}.correlation"].append(rr.tolist())
+                if dp is not None and want(f"{tg['name']}.dpred"):
+                    cols[f"{tg['name']}.dpred"].append(list(dp))
+            for name, field in entry.get("fields", {}).items():
+                if want(name):
+                    cols[name].append(list(field))
+        if E == 0:
+            return {}
+        M = np.array(masks)
+        full = bool(M.all())
+        out = {}
+        for key, per_entry in cols.items():
+            if len(per_entry) != E:
+                return None  # (a key that is not present at every save point: leave it to the per-chain path)
+            if full:
+                out[key] = [per_entry[e][c] for c in range(C) for e in range(E)]
+            else:
+                out[key] = [per_entry[e][c] for c in range(C) for e in range(E) if M[e, c]]
+        return out
+
+    def _legacy_entry(self, entry, c, out):
+        if not entry["mask"][c]:
+            return
+        cm = entry.get("chain_major", False)
+        for sp, (k, sites, vals) in zip(self.spec["spaces"], entry["spaces"]):
+            kc = int(k[c])
+            if sp["trans_d"]:
+                out[f"{sp['name']}.n_dimensions"].append(kc)
+            if sp["ndim"] == 1:
+                out[f"{sp['name']}.discretization"].append((sites[c, :kc, 0] if cm else sites[0, :kc, c]).copy())
+            elif sp["ndim"] == 2:
+                out[f"{sp['name']}.discretization"].append((sites[c, :kc] if cm else sites[:, :kc, c].T).copy())
+            for j, p in enumerate(sp["params"]):
+                out[f"{sp['name']}.{p['name']}"].append((vals[c, j, :kc] if cm else vals[j, :kc, c]).copy())
+        for i, (tg, sg) in enumerate(zip(self.spec["targets"], entry["sigma"])):
+            if sg is not None:
+                out[f"{tg['name']}.std"].append(float(sg[c]))
+            rr = entry.get("corr", [None] * len(entry["sigma"]))[i]
+            if rr is not None:
+                out[f"{tg['name']}.correlation"].append(float(rr[c]))
+        for tg, dp in zip(self.spec["targets"], entry["dpred"]):
+            if dp is not None:
+                out[f"{tg['name']}.dpred"].append(dp[c] if cm else dp[:, c].copy())
+        for name, field in entry.get("fields", {}).items():
+            out[name].append(field[c] if cm else field[:, c].copy())
 
     def statistics(self):
         """Per-chain statistics dictionaries in the reference's shape (``_init_statistics`` /

@@ -57,10 +57,17 @@ class BaseBayesianInversion:
         sampler.parallel_config = _parallel_config
         self._chains = sampler.run(n_iterations=n_iterations, burnin_iterations=burnin_iterations,
                                    save_every=save_every, verbose=verbose, print_every=print_every)
-        self._sync_chains()
+        # the samples are in host memory when run() returns (save points travel while the chains keep stepping); the
+        # per-chain views (saved_states, statistics, current_state) are filled when they are first read
+        self.batch.flush_saves()
+        self._mark_dirty()
 
     def get_results(self, keys: Union[str, List[str]] = None, concatenate_chains: bool = True):
         """Saved samples of this rank's chains (reference ``_bayes_inversion.py:251-326``)."""
+        if concatenate_chains and getattr(self, "batch", None) is not None:
+            fast = self.batch.results([keys] if isinstance(keys, str) else keys)
+            if fast is not None:
+                return fast
         return self.get_results_from_chains(self.chains, keys, concatenate_chains)
 
     @staticmethod

@@ -392,6 +392,14 @@ class Engine:
         L.check(self.lib.bbb_engine_gather_space(self._handle, s, _ptr(k), _ptr(sites), _ptr(vals), self._stream))
         return k, sites, vals
 
+    def save_point_bytes(self, kb, want_dpred: bool) -> int:
+        return int(self.lib.bbb_engine_save_point_bytes(self._handle, self._kb(kb), int(bool(want_dpred))))
+
+    def save_point(self, kb, want_dpred: bool, image: torch.Tensor, scratch: Optional[torch.Tensor] = None):
+        """The current state of every chain (and d_pred) as one chain-major device image (include/bbb200.h)."""
+        L.check(self.lib.bbb_engine_save_point(self._handle, self._kb(kb), int(bool(want_dpred)), _ptr(image), _ptr(scratch),
+                                               self._stream))
+
     def dpred(self, t: int) -> torch.Tensor:
         R = int(np.asarray(self.spec["targets"][t]["dobs"]).size)
         out = torch.empty((R, self.C), dtype=torch.float64, device=self.device)

@@ -111,6 +111,8 @@ SYMBOLS = {
     "bbb_engine_stage": (C.c_int, [_vp, C.c_int, _vp]),
     "bbb_engine_set_annealing": (C.c_int, [_vp, C.c_double, C.c_double, _i64, _i64]),
     "bbb_engine_gather_space": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "bbb_engine_save_point_bytes": (_i64, [_vp, C.POINTER(_i32), _i32]),
+    "bbb_engine_save_point": (C.c_int, [_vp, C.POINTER(_i32), _i32, _vp, _vp, _vp]),
     "bbb_engine_state_image_bytes": (_i64, [_vp, C.POINTER(_i32)]),
     "bbb_engine_pack_states": (C.c_int, [_vp, C.POINTER(_i32), _vp, _vp]),
     "bbb_engine_compare_states": (C.c_int, [_vp, C.POINTER(_i32), _vp, _vp, _vp]),

@@ -1051,6 +1051,40 @@ int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream)
     return BBB_OK;
 }
 
+int64_t bbb_engine_save_point_bytes(bbb_engine *e, const int32_t *kb, int32_t want_dpred) {
+    if (!e || !e->bound || check_kb(e, kb) != BBB_OK) return -1;
+    long long n = save_point_state_words(e->host, kb);
+    if (want_dpred)
+        for (int t = 0; t < e->host.spec.n_targets; ++t) n += e->host.buf.n_chains * (long long)e->host.spec.targets[t].n_data;
+    return 8 * n;
+}
+
+int bbb_engine_save_point(bbb_engine *e, const int32_t *kb, int32_t want_dpred, void *image, double *scratch, void *stream) {
+    NEED_BOUND(e);
+    if (int rc = check_kb(e, kb)) return rc;
+    if (!image) return fail(BBB_ERR_INVALID, "image is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_buffers &B = e->host.buf;
+    const long long C = B.n_chains;
+    CU(launch_save_states(e->host, kb, image, st));
+    if (!want_dpred) return BBB_OK;
+    double *out = reinterpret_cast<double *>(image) + save_point_state_words(e->host, kb);
+    for (int t = 0; t < P.n_targets; ++t) {
+        const bbb_target_spec &T = P.targets[t];
+        if (e->host.chain_local && t == e->ray_t) {
+            // the residuals of the current states are resident, chain-major: d_pred = res + d_obs
+            CU(launch_save_dpred_local(B.res[t], T.dobs, C, T.n_data, out, st));
+        } else {
+            if (!scratch) return fail(BBB_ERR_INVALID, "target %d: a [n_data][C] scratch buffer is needed for its d_pred", t);
+            if (int rc = bbb_engine_dpred(e, t, scratch, stream)) return rc;
+            CU(launch_transpose_f64(scratch, out, T.n_data, C, st));
+        }
+        out += C * (long long)T.n_data;
+    }
+    return BBB_OK;
+}
+
 int bbb_engine_misfit_logdet(bbb_engine *e, double *misfit_out, double *logdet_out, void *stream) {
     NEED_BOUND(e);
     if (!misfit_out || !logdet_out) return fail(BBB_ERR_INVALID, "NULL output");

@@ -964,6 +964,11 @@ int launch_transpose_idx(const void *in, void *out, int idx_bytes, long long row
     return launch_transpose_t<uint16_t, false>((const uint16_t *)in, (uint16_t *)out, rows, cols, in_stride, out_stride, nullptr, st);
 }
 
+// out[j][i] = in[i][j] (dense)
+int launch_transpose_f64(const double *in, double *out, long long rows, long long cols, cudaStream_t st) {
+    return launch_transpose_t<double, false>(in, out, rows, cols, cols, rows, nullptr, st);
+}
+
 // res[c][r] = dpred[r][c] - dobs[r]
 int launch_residual_transpose(const double *dpred, double *res, long long R, long long C, const double *dobs, cudaStream_t st) {
     return launch_transpose_t<double, true>(dpred, res, R, C, C, R, dobs, st);

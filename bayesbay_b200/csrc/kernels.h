@@ -91,6 +91,12 @@ long long state_image_rows(const EngineParams &host_params, const int32_t *kb);
 // chains [c_first, c_end): the image has rows of (c_end - c_first) words
 int launch_state_image(const EngineParams &host_params, int mode, const int32_t *kb, void *image, int32_t *differ,
                        long long c_first, long long c_end, cudaStream_t stream);
+// save point: states + noise + temperature sections of the chain-major image (step_kernels.cu), d_pred of a chain-local
+// ray target from its resident residuals
+long long save_point_state_words(const EngineParams &host_params, const int32_t *kb);
+int launch_save_states(const EngineParams &host_params, const int32_t *kb, void *image, cudaStream_t stream);
+int launch_save_dpred_local(const double *res, const double *dobs, long long C, int R, double *out, cudaStream_t stream);
+int launch_transpose_f64(const double *in, double *out, long long rows, long long cols, cudaStream_t stream);
 int launch_small_dpred(const EngineParams *dev_params, long long C, int target, double *dpred_out,
                        cudaStream_t stream);
 int launch_misfit_logdet(const EngineParams *dev_params, long long C, double *misfit_out,

@@ -281,6 +281,72 @@ __global__ void k_state_image(const __grid_constant__ EngineParams ep, const __g
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Save point (`_save_state`, src/bayesbay/_markov_chain.py:115-134): the CURRENT state of every chain as ONE
+// chain-major image of 8-byte words, so that a save point is one asynchronous device -> host copy and a chain's
+// sample is a contiguous slice on the host.  Sections (include/bbb200.h):
+//   per space: k [C] (int64) | sites [C][kb][ndim] | values [C][n_params][kb]   (cells j >= k hold 0)
+//   per hierarchical target: sigma [C] | correlation [C] (correlated targets);  temperature [C];
+//   d_pred [C][n_data] per target (written by k_save_dpred_local / a forward + transpose, abi.cu).
+// One thread per (chain, cell): reads are coalesced over chains, the (small) writes are strided.
+// ------------------------------------------------------------------------------------------------
+struct SaveLayout {
+    long long space_off[BBB_MAX_SPACES];  // word offset of the space's k row
+    int kb[BBB_MAX_SPACES];
+    long long noise_off;                  // sigma / correlation rows in target order, then temperature
+};
+
+__global__ void k_save_states(const __grid_constant__ EngineParams ep, const __grid_constant__ SaveLayout lay, unsigned long long *image) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int s = blockIdx.z, j = blockIdx.y;
+    if (s < P.n_spaces) {
+        const bbb_space_spec &S = P.spaces[s];
+        const int kb = lay.kb[s];
+        if (j >= kb) return;
+        const int slot = B.sel[s][c];
+        const int k = k_ref(B, s, slot, c);
+        unsigned long long *base = image + lay.space_off[s];
+        if (j == 0) base[c] = (unsigned long long)(long long)k;
+        unsigned long long *sites = base + C, *vals = sites + C * (long long)kb * S.ndim;
+        for (int d = 0; d < S.ndim; ++d)
+            sites[(c * kb + j) * S.ndim + d] = j < k ? (unsigned long long)__double_as_longlong(site_ref(B, S, s, slot, d, j, c)) : 0ull;
+        for (int p = 0; p < S.n_params; ++p)
+            vals[(c * S.n_params + p) * kb + j] = j < k ? (unsigned long long)__double_as_longlong(value_ref(B, S, s, slot, p, j, c)) : 0ull;
+    } else if (j == 0) {  // the noise rows and the temperature
+        unsigned long long *row = image + lay.noise_off;
+        for (int t = 0; t < P.n_targets; ++t) {
+            const bbb_target_spec &T = P.targets[t];
+            if (T.cov_kind != BBB_COV_HIERARCHICAL) continue;
+            row[c] = (unsigned long long)__double_as_longlong(B.sigma[t][c]);
+            row += C;
+            if (T.correlated) {
+                row[c] = (unsigned long long)__double_as_longlong(B.corr[t][c]);
+                row += C;
+            }
+        }
+        row[c] = (unsigned long long)__double_as_longlong(B.temperature[c]);
+    }
+}
+
+// d_pred of a chain-local ray target from the resident residuals: out[c][r] = res[c][r] + dobs[r]
+__global__ void k_save_dpred_local(const double *res, const double *dobs, long long n, int R, double *out) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < n) {
+        const double2 v = *reinterpret_cast<const double2 *>(res + i);
+        const int r = (int)(i % R);
+        double2 o;
+        o.x = v.x + dobs[r];
+        o.y = v.y + dobs[r + 1 < R ? r + 1 : 0];
+        *reinterpret_cast<double2 *>(out + i) = o;
+    } else if (i < n) {
+        out[i] = res[i] + dobs[i % R];
+    }
+}
+
 __global__ void __launch_bounds__(STEP_THREADS) k_small_dpred(const EngineParams *epp, int t, double *dpred_out) {
     const EngineParams &ep = *epp;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -639,6 +705,42 @@ int launch_state_image(const EngineParams &p, int mode, const int32_t *kb, void 
     if (mode == 0) k_state_image<0><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
     else if (mode == 1) k_state_image<1><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
     else k_state_image<2><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
+    return (int)cudaGetLastError();
+}
+static SaveLayout save_layout(const EngineParams &p, const int32_t *kb, long long *n_words_states) {
+    SaveLayout lay;
+    const long long C = p.buf.n_chains;
+    long long off = 0;
+    for (int s = 0; s < p.spec.n_spaces; ++s) {
+        const bbb_space_spec &S = p.spec.spaces[s];
+        lay.space_off[s] = off;
+        lay.kb[s] = kb[s];
+        off += C * (1 + (long long)kb[s] * (S.ndim + S.n_params));
+    }
+    lay.noise_off = off;
+    for (int t = 0; t < p.spec.n_targets; ++t)
+        if (p.spec.targets[t].cov_kind == BBB_COV_HIERARCHICAL) off += C * (p.spec.targets[t].correlated ? 2 : 1);
+    off += C;  // temperature
+    *n_words_states = off;
+    return lay;
+}
+long long save_point_state_words(const EngineParams &p, const int32_t *kb) {
+    long long n = 0;
+    save_layout(p, kb, &n);
+    return n;
+}
+int launch_save_states(const EngineParams &p, const int32_t *kb, void *image, cudaStream_t st) {
+    long long n = 0;
+    const SaveLayout lay = save_layout(p, kb, &n);
+    int kb_max = 1;
+    for (int s = 0; s < p.spec.n_spaces; ++s) kb_max = kb[s] > kb_max ? kb[s] : kb_max;
+    dim3 grid(blocks_for(p.buf.n_chains, 128), kb_max, p.spec.n_spaces + 1);
+    k_save_states<<<grid, 128, 0, st>>>(p, lay, reinterpret_cast<unsigned long long *>(image));
+    return (int)cudaGetLastError();
+}
+int launch_save_dpred_local(const double *res, const double *dobs, long long C, int R, double *out, cudaStream_t st) {
+    const long long n = C * R;
+    k_save_dpred_local<<<blocks_for((n + 1) / 2, 256), 256, 0, st>>>(res, dobs, n, R, out);
     return (int)cudaGetLastError();
 }
 int launch_small_dpred(const EngineParams *p, long long C, int target, double *dpred_out, cudaStream_t st) {

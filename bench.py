@@ -504,15 +504,19 @@ def api_run(par, ll, bb, n_chains, n_iterations=2000, save_every=100):
 
     inv = bb.BayesianInversion(par, ll, n_chains=n_chains)
     inv.run(n_iterations=200, burnin_iterations=100, save_every=save_every, verbose=False)  # warm-up
+    n_before = len(inv.get_results()["voronoi.n_dimensions"])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     inv.run(n_iterations=n_iterations, burnin_iterations=0, save_every=save_every, verbose=False)
     torch.cuda.synchronize()
+    wall_run = time.perf_counter() - t0
+    res = inv.get_results()
     wall = time.perf_counter() - t0
-    n_samples = len(inv.get_results()["voronoi.n_dimensions"])
-    return {"value": n_chains * n_iterations / wall, "unit": UNIT, "wall_s": wall,
-            "what": f"BayesianInversion.run(n_iterations={n_iterations}, save_every={save_every}) on the same problem and "
-                    f"chain count, host wall clock incl. the saved samples ({n_samples} states with d_pred) coming back"}
+    n_samples = len(res["voronoi.n_dimensions"]) - n_before
+    return {"value": n_chains * n_iterations / wall, "unit": UNIT, "wall_s": wall, "wall_s_run_only": wall_run,
+            "what": f"BayesianInversion.run(n_iterations={n_iterations}, save_every={save_every}) + get_results() on the same "
+                    f"problem and chain count, host wall clock: the saved samples ({n_samples} states with d_pred, the "
+                    "reference's defaults) are in host memory when run() returns and in the reference's result lists at the end"}
 
 
 def e2e_run(eng, steps, device, world, dist):

@@ -259,6 +259,16 @@ int bbb_engine_set_annealing(bbb_engine *e, double temperature_start, double coo
  * src/bayesbay/_markov_chain.py:115-134): k [C] int32, sites [ndim][K][C], values [P][K][C]. */
 int bbb_engine_gather_space(bbb_engine *e, int space, int32_t *k_out, double *sites_out,
                             double *values_out, void *stream);
+/* Save point (`_save_state`, src/bayesbay/_markov_chain.py:115-134, for all chains at once): the CURRENT state of
+ * every chain as ONE chain-major image of 8-byte words in device memory, so that a save point is one asynchronous
+ * device -> host copy and a chain's sample is a contiguous slice of the host copy.  Sections, in this order:
+ *   per space s: k [C] (int64) | sites [C][kb[s]][ndim] | values [C][n_params][kb[s]]   (cells j >= k hold 0);
+ *   per hierarchical target: sigma [C] | correlation [C] (correlated targets only);   temperature [C];
+ *   if want_dpred: per target d_pred [C][n_data] (the "{target}.dpred" entries the reference saves by default).
+ * kb[s] >= the largest k of space s (e.g. n_dimensions_max).  `scratch` ([n_data][C] doubles, may be NULL) is only
+ * needed for d_pred of targets other than the ray target of a chain-local engine. */
+int64_t bbb_engine_save_point_bytes(bbb_engine *e, const int32_t *kb, int32_t want_dpred);
+int bbb_engine_save_point(bbb_engine *e, const int32_t *kb, int32_t want_dpred, void *image, double *scratch, void *stream);
 /* Chain-state image: the CURRENT state of every chain packed into ONE buffer of 8-byte words, so that moving the
  * chains between host and device -- what the reference's pool does with pickles on every advance_chain
  * (samplers/_samplers.py:225-237) -- is one copy each way.  Rows of C words each: per space k (int64), sites
