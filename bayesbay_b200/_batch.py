@@ -200,7 +200,7 @@ class ChainBatch:
                 self._save()
 
     # ---- save points: device image -> pinned ring -> host, off the stepping stream -----------------------------
-    N_SLOTS = 3  # images in flight (device buffer + pinned host buffer each)
+    N_SLOTS = 4  # images in flight (device buffer + pinned host buffer each), one worker thread per slot
 
     def _save_setup(self):
         """Layout of a save-point image (bbb_engine_save_point, include/bbb200.h) and the transfer machinery: a ring of
@@ -254,9 +254,13 @@ class ChainBatch:
         self._todo = queue.Queue()
         self._save_errors = []
         # (the worker holds the queues, events and pinned buffers, not the batch: the batch stays collectable)
-        self._worker = threading.Thread(target=self._save_worker, daemon=True,
-                                        args=(self._todo, self._free, self._save_copied, self._save_pin, self._save_errors))
-        self._worker.start()
+        # (several workers: copying an image out of the pinned ring first-touches ~90 MB of fresh host memory, which one
+        # thread does at 3-4 GB/s -- slower than the chains produce save points)
+        self._workers = [threading.Thread(target=self._save_worker, daemon=True,
+                                          args=(self._todo, self._free, self._save_copied, self._save_pin, self._save_errors))
+                         for _ in range(self.N_SLOTS)]
+        for w in self._workers:
+            w.start()
 
     @staticmethod
     def _save_worker(todo, free, copied, pinned, errors):
@@ -278,7 +282,8 @@ class ChainBatch:
     def __del__(self):
         todo = getattr(self, "_todo", None)
         if todo is not None:
-            todo.put(None)
+            for _ in getattr(self, "_workers", [None]):
+                todo.put(None)
 
     def flush_saves(self):
         """Wait until every save point submitted so far has arrived in ``self.saved``."""

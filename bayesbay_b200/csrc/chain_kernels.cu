@@ -323,175 +323,145 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
         rng_end(rng, ep, c);
         CS_TL_T(9, CS_THREADS - 1);
     }
+    // Pass 1, one thread per group of 16 points (one 16-byte load of the index row): a value move lists the cell's own
+    // points; a geometry move only SORTS the groups -- those that hold points of the removed / moved cell (found by
+    // comparing indices) and those the inserted cell might reach (every group the bounding-box test cannot rule out)
+    // are queued for pass 2, where 16 lanes share a group's points.  No distance is evaluated per point here, so the
+    // pass costs the same whatever the move and wherever the new cell lies.
     for (int g0 = tid * CS_PTS; g0 < G && warp < RW; g0 += RW * 32 * CS_PTS) {
         const IdxVec<IdxT> wv = wv_next;
         if (g0 + RW * 32 * CS_PTS < G) wv_next.load(row + g0 + RW * 32 * CS_PTS);
-        unsigned chg = 0, scn = 0;
+        unsigned scn = 0;
         if (inner == BBB_MOVE_VALUES) {
+            unsigned chg = 0;
 #pragma unroll
             for (int q = 0; q < CS_PTS; ++q)
                 if (g0 + q < G && wv.at(q) == rm) chg |= 1u << q;
-        } else {
-            // Pruning: a group is decided from its bounding box.  With o0 the current owner of ANY of its points,
-            // d_own(g) <= d(g, o0) for every point g of the group (the owner is the nearest site), hence
-            // d_new(g) - d_own(g) >= d_new(g) - d(g, o0) = |n|^2 - |o0|^2 - 2 g.(n - o0), which is affine in g: its
-            // minimum over the box is taken at a corner, and when that minimum is positive by a margin far above any
-            // rounding of the per-point test (1e-9 of the squared coordinates against 1e-16), no point of the group can
-            // be captured by the inserted cell.  Points of the removed cell are found by comparing indices.
-            bool pruned = false;
-            if (ins >= 0 && T.group_box != nullptr && g0 + CS_PTS <= G) {
-                int o0 = wv.at(0);
-                if (rm >= 0 && o0 == rm) o0 = wv.at(CS_PTS - 1);
-                if (!(rm >= 0 && o0 == rm)) {
-                    const double2 bx = __ldg(reinterpret_cast<const double2 *>(T.group_box) + 2 * (g0 >> 4));
-                    const double2 by = __ldg(reinterpret_cast<const double2 *>(T.group_box) + 2 * (g0 >> 4) + 1);
-                    int mm = o0 - ((rm >= 0 && o0 > rm) ? 1 : 0);
-                    mm += (mm >= ins) ? 1 : 0;
-                    const double ox = sx[mm], oy = sy[mm];
-                    const double ddx = nx - ox, ddy = ny - oy;
-                    const double gmax = (ddx > 0.0 ? bx.y : bx.x) * ddx + (ddy > 0.0 ? by.y : by.x) * ddy;
-                    const double nn = nx * nx + ny * ny, oo = ox * ox + oy * oy;
-                    const double ax = ::fmax(fabs(bx.x), fabs(bx.y)), ay = ::fmax(fabs(by.x), fabs(by.y));
-                    pruned = (nn - oo) - 2.0 * gmax > 1e-9 * (nn + oo + ax * ax + ay * ay);
-                }
-                if (pruned && rm >= 0) {
+            if (chg) {
+                // merged groups: all 16 points, or an aligned group of 4, of the cell
+                unsigned quads = 0;
+                const bool hex = n_levels >= 3 && chg == 0xFFFFu;
+                if (!hex && n_levels >= 2) {
 #pragma unroll
-                    for (int q = 0; q < CS_PTS; ++q)
-                        if (wv.at(q) == rm) scn |= 1u << q;
-                }
-            }
-#pragma unroll
-            for (int qd = 0; qd < (pruned ? 0 : CS_PTS / 4); ++qd) {
-                // the 4 points of a quad (a 2x2 block of the grid) mostly share their owner: its site is fetched
-                // once per quad (the owners' sites are a data-dependent, bank-conflicting shared-memory gather)
-                const int oq = wv.at(4 * qd);
-                int mq = oq - ((rm >= 0 && oq > rm) ? 1 : 0);
-                mq += (ins >= 0 && mq >= ins) ? 1 : 0;
-                const double oxq = sx[mq < K ? mq : 0], oyq = sy[mq < K ? mq : 0];
-                // coordinates of the quad's points: four independent 16-byte loads, issued whatever the owners are
-                // (a load per point behind the owner test costs one L2 round trip per point)
-                double gxq[4], gyq[4];
-                {
-                    const int gq = g0 + 4 * qd;
-                    if (ins >= 0 && gq + 3 < G) {
-                        const double2 xa = __ldg(reinterpret_cast<const double2 *>(T.points_x + gq));
-                        const double2 xb = __ldg(reinterpret_cast<const double2 *>(T.points_x + gq + 2));
-                        const double2 ya = __ldg(reinterpret_cast<const double2 *>(T.points_y + gq));
-                        const double2 yb = __ldg(reinterpret_cast<const double2 *>(T.points_y + gq + 2));
-                        gxq[0] = xa.x; gxq[1] = xa.y; gxq[2] = xb.x; gxq[3] = xb.y;
-                        gyq[0] = ya.x; gyq[1] = ya.y; gyq[2] = yb.x; gyq[3] = yb.y;
-                    } else {
-#pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            const int g = min(gq + qq, G - 1);
-                            gxq[qq] = ins >= 0 ? T.points_x[g] : 0.0;
-                            gyq[qq] = ins >= 0 ? T.points_y[g] : 0.0;
+                    for (int qd = 0; qd < 4; ++qd) {
+                        if (((chg >> (4 * qd)) & 0xFu) == 0xFu) {
+                            quads |= 1u << qd;
+                            chg &= ~(0xFu << (4 * qd));
                         }
                     }
                 }
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int q = 4 * qd + qq;
-                    const int g = g0 + q;
-                    if (g >= G) continue;
-                    const int o = wv.at(q);
-                    if (rm >= 0 && o == rm) {
-                        scn |= 1u << q;
-                    } else if (ins >= 0) {
-                        int mm = o - ((rm >= 0 && o > rm) ? 1 : 0);
-                        mm += (mm >= ins) ? 1 : 0;
-                        double ox = oxq, oy = oyq;
-                        if (o != oq) { ox = sx[mm]; oy = sy[mm]; }
-                        const double gx = gxq[qq], gy = gyq[qq];
-                        const double dx = ox - gx, dy = oy - gy;
-                        const double d_own = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                        const double ex = nx - gx, ey = ny - gy;
-                        const double d_new = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
-                        if (d_new < d_own || (d_new == d_own && ins < mm)) chg |= 1u << q;
+                if (hex) {
+                    const int pos = atomicAdd(&s_front, 1);
+                    list_at(pos) = (2u << 29) | ((unsigned)(g0 >> 4) << CS_M_BITS) | (unsigned)rm;
+                } else {
+                    int pos = atomicAdd(&s_front, __popc(quads) + __popc(chg));
+                    while (quads) {
+                        const int qd = __ffs(quads) - 1;
+                        quads &= quads - 1;
+                        list_at(pos++) = (1u << 29) | ((unsigned)((g0 >> 2) + qd) << CS_M_BITS) | (unsigned)rm;
+                    }
+                    while (chg) {
+                        const int q = __ffs(chg) - 1;
+                        chg &= chg - 1;
+                        list_at(pos++) = ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)rm;
                     }
                 }
             }
+            continue;
         }
-        if (chg) {
-            // merged groups: all 16 points, or an aligned group of 4, change from the SAME old owner
-            unsigned quads = 0;
-            bool hex = false;
-            if (n_levels >= 3 && chg == 0xFFFFu) {
-                hex = true;
+        if (rm >= 0) {
 #pragma unroll
-                for (int q = 1; q < CS_PTS; ++q) hex &= wv.at(q) == wv.at(0);
-            }
-            if (!hex && n_levels >= 2) {
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const bool same = wv.at(4 * qd + 1) == wv.at(4 * qd) && wv.at(4 * qd + 2) == wv.at(4 * qd) &&
-                                      wv.at(4 * qd + 3) == wv.at(4 * qd);
-                    if (((chg >> (4 * qd)) & 0xFu) == 0xFu && same) {
-                        quads |= 1u << qd;
-                        chg &= ~(0xFu << (4 * qd));
-                    }
-                }
-            }
-            if (hex) {
-                const int pos = atomicAdd(&s_front, 1);
-                list_at(pos) = (2u << 29) | ((unsigned)(g0 >> 4) << CS_M_BITS) | (unsigned)wv.at(0);
-            } else {
-                int pos = atomicAdd(&s_front, __popc(quads) + __popc(chg));
-                while (quads) {
-                    const int qd = __ffs(quads) - 1;
-                    quads &= quads - 1;
-                    list_at(pos++) = (1u << 29) | ((unsigned)((g0 >> 2) + qd) << CS_M_BITS) | (unsigned)wv.at(4 * qd);
-                }
-                while (chg) {
-                    const int q = __ffs(chg) - 1;
-                    chg &= chg - 1;
-                    list_at(pos++) = ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)wv.at(q);
-                }
+            for (int q = 0; q < CS_PTS; ++q)
+                if (g0 + q < G && wv.at(q) == rm) scn |= 1u << q;
+        }
+        // Pruning: a group is decided from its bounding box.  With o0 the current owner of ANY of its points,
+        // d_own(g) <= d(g, o0) for every point g of the group (the owner is the nearest site), hence
+        // d_new(g) - d_own(g) >= d_new(g) - d(g, o0) = |n|^2 - |o0|^2 - 2 g.(n - o0), which is affine in g: its
+        // minimum over the box is taken at a corner, and when that minimum is positive by a margin far above any
+        // rounding of the per-point test (1e-9 of the squared coordinates against 1e-16), no point of the group can
+        // be captured by the inserted cell.
+        bool reach = ins >= 0;
+        if (ins >= 0 && T.group_box != nullptr && g0 + CS_PTS <= G) {
+            int o0 = wv.at(0);
+            if (rm >= 0 && o0 == rm) o0 = wv.at(CS_PTS - 1);
+            if (!(rm >= 0 && o0 == rm)) {
+                const double2 bx = __ldg(reinterpret_cast<const double2 *>(T.group_box) + 2 * (g0 >> 4));
+                const double2 by = __ldg(reinterpret_cast<const double2 *>(T.group_box) + 2 * (g0 >> 4) + 1);
+                int mm = o0 - ((rm >= 0 && o0 > rm) ? 1 : 0);
+                mm += (mm >= ins) ? 1 : 0;
+                const double ox = sx[mm], oy = sy[mm];
+                const double ddx = nx - ox, ddy = ny - oy;
+                const double gmax = (ddx > 0.0 ? bx.y : bx.x) * ddx + (ddy > 0.0 ? by.y : by.x) * ddy;
+                const double nn = nx * nx + ny * ny, oo = ox * ox + oy * oy;
+                const double ax = ::fmax(fabs(bx.x), fabs(bx.y)), ay = ::fmax(fabs(by.x), fabs(by.y));
+                reach = !((nn - oo) - 2.0 * gmax > 1e-9 * (nn + oo + ax * ax + ay * ay));
             }
         }
-        if (scn) queue_at(atomicAdd(&s_back, 1)) = ((unsigned)(g0 >> 4) << 16) | scn;
+        // queue item: group << 17 | reach << 16 | mask of the points that lost their owner
+        if (scn || reach) queue_at(atomicAdd(&s_back, 1)) = ((unsigned)(g0 >> 4) << 17) | (reach ? 1u << 16 : 0u) | scn;
     }
     CS_TL(10);
     __syncthreads();
     CS_TL(2);
     // (the queue is complete)
-    // re-derivation: 16 lanes per queued group, lane q = point q of the group; the group's new owners are then
-    // merged like the front entries (a moved cell that still owns a point changes nothing there: 2-D site move,
-    // rm == ins, values kept)
+    // Pass 2: 16 lanes per queued group, lane q = point q of the group.  A point of the removed / moved cell is
+    // re-derived over all proposed sites; any other point of a group within reach is tested against the inserted cell
+    // alone (its owner survives: the same rule as k_raster2d_inc in tomo_kernels.cu -- strict '<' with ascending index and
+    // separately rounded products keep the lowest-index tie rule of numpy argmin / KDTree.query).  List entries
+    // (back << 31 | level << 29 | group << 12 | cell): points captured by the inserted cell carry their OLD owner; points
+    // that lost their owner (back = 1) their NEW owner, the old one being the removed cell (a moved cell that still owns a
+    // point changes nothing there: 2-D site move, rm == ins, values kept).  Aligned groups of 4 / 16 points that change
+    // between the same two cells become one entry of a merged level.
     {
         const int n_items = s_back;
         const int q = tid & 15, half = lane >> 4;
         for (int base = 0; base < n_items; base += CS_THREADS / 16) {
             const int it = base + (tid >> 4);
             const unsigned item = it < n_items ? queue_at(it) : 0u;
-            const int g0 = (int)(item >> 16) << 4;
-            const bool mine = (item >> q) & 1u;
-            int bi = -1;
-            if (mine) {
+            const int g0 = (int)(item >> 17) << 4;
+            const bool live = it < n_items && g0 + q < G;
+            const bool lost = live && ((item >> q) & 1u);
+            const bool test = live && !lost && ((item >> 16) & 1u);
+            int bi = -1;   // new owner of a point that lost its owner
+            int old = -1;  // old owner of a point the inserted cell captures
+            if (lost || test) {
                 const double gx = T.points_x[g0 + q], gy = T.points_y[g0 + q];
-                double best = INFINITY;
-                for (int j = 0; j < k_new; ++j) {
-                    const double dx = sx[j] - gx, dy = sy[j] - gy;
-                    const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                    if (d < best) { best = d; bi = j; }
+                if (lost) {
+                    double best = INFINITY;
+                    for (int j = 0; j < k_new; ++j) {
+                        const double dx = sx[j] - gx, dy = sy[j] - gy;
+                        const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        if (d < best) { best = d; bi = j; }
+                    }
+                    if (rm == ins && bi == ins) bi = -1;  // unchanged
+                } else {
+                    const int o = (int)row[g0 + q];
+                    int mm = o - ((rm >= 0 && o > rm) ? 1 : 0);
+                    mm += (mm >= ins) ? 1 : 0;
+                    const double dx = sx[mm] - gx, dy = sy[mm] - gy;
+                    const double d_own = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    const double ex = nx - gx, ey = ny - gy;
+                    const double d_new = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+                    if (d_new < d_own || (d_new == d_own && ins < mm)) old = o;
                 }
-                if (rm == ins && bi == ins) bi = -1;  // unchanged
             }
-            // owners of the half-warp's 16 points; a point that is not re-derived or unchanged breaks a group
             const unsigned full = 0xffffffffu;
-            const int b0 = __shfl_sync(full, bi, half * 16);
-            const unsigned all_same = __ballot_sync(full, bi >= 0 && bi == b0);
+            // the half-warp's 16 points: merged entries need every point of the aligned group to change alike
+            const int key = bi >= 0 ? bi : (old >= 0 ? (old | 0x10000) : -1);  // (new owner) or (old owner, captured)
+            const int k0 = __shfl_sync(full, key, half * 16);
+            const unsigned all_same = __ballot_sync(full, key >= 0 && key == k0);
             const bool hex = n_levels >= 3 && ((all_same >> (half * 16)) & 0xFFFFu) == 0xFFFFu;
-            const int bq = __shfl_sync(full, bi, (lane & ~3));
-            const unsigned quad_same = __ballot_sync(full, bi >= 0 && bi == bq);
+            const int kq = __shfl_sync(full, key, (lane & ~3));
+            const unsigned quad_same = __ballot_sync(full, key >= 0 && key == kq);
             const bool quad = !hex && n_levels >= 2 && ((quad_same >> (lane & ~3)) & 0xFu) == 0xFu;
+            const unsigned tagged = bi >= 0 ? (CS_BACK | (unsigned)bi) : (unsigned)(old >= 0 ? old : 0);
             unsigned entry = CS_NONE;
             if (hex) {
-                if (q == 0) entry = CS_BACK | (2u << 29) | ((unsigned)(g0 >> 4) << CS_M_BITS) | (unsigned)bi;
+                if (q == 0) entry = tagged | (2u << 29) | ((unsigned)(g0 >> 4) << CS_M_BITS);
             } else if (quad) {
-                if ((q & 3) == 0) entry = CS_BACK | (1u << 29) | ((unsigned)((g0 + q) >> 2) << CS_M_BITS) | (unsigned)bi;
-            } else if (bi >= 0) {
-                entry = CS_BACK | ((unsigned)(g0 + q) << CS_M_BITS) | (unsigned)bi;
+                if ((q & 3) == 0) entry = tagged | (1u << 29) | ((unsigned)((g0 + q) >> 2) << CS_M_BITS);
+            } else if (key >= 0) {
+                entry = tagged | ((unsigned)(g0 + q) << CS_M_BITS);
             }
             const unsigned emit = __ballot_sync(full, entry != CS_NONE);
             int pos = 0;

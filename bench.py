@@ -418,8 +418,10 @@ def alt_rooflines(kernel, live_ms):
         add("hbm (bytes moved, ncu)", cnt["dram_bytes"] / s / 1e9, float(load_json("MEASURED_PEAKS.json").get("hbm_gbs", 6650.0)), "GB/s")
     if "l2_bytes" in cnt:
         add("l2", cnt["l2_bytes"] / s / 1e9, peaks["l2_read_gbs"], "GB/s")
-    if "fp64_flops" in cnt:
-        add("fp64", cnt["fp64_flops"] / s / 1e12, peaks["fp64_fma_tflops"], "TFLOP/s")
+    if cnt.get("fp64_pipe_pct_of_peak_active") and cnt.get("ncu_duration_us"):
+        # ncu's fp64-pipe utilisation of the captured launch, rescaled to the live launch time
+        frac = cnt["fp64_pipe_pct_of_peak_active"] / 100.0 * (cnt["ncu_duration_us"] * 1e-6) / s
+        add("fp64 pipe", frac * peaks["fp64_fma_tflops"], peaks["fp64_fma_tflops"], "TFLOP/s")
     if "smem_atomic_lane_ops" in cnt:
         add("shared-memory atomics", cnt["smem_atomic_lane_ops"] / s, peaks["smem_atoms_lane_ops_per_s"], "lane-ops/s")
     if "smem_bytes" in cnt:
