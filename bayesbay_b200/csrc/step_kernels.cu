@@ -13,8 +13,9 @@ constexpr int STEP_THREADS = 64;  // 2 warps per block: spreads C = 1024 chains 
 // birth/death-from-neighbour run with lanes = sites, and the lanes write the proposed slot (lanes = cells).
 constexpr int PROPOSE_WARPS = 4;
 // Cost class of chain c's block in the chain kernel, 0 = longest.  est = a[move] + b[move] * (points per cell): block
-// times measured on the C3 shape (tools/timeline.py; birth 29.6 + 2.17 x, death 25.9 + 2.23 x, values 21.8 + 1.42 x,
-// sites 30.9 + 0.72 x microseconds, x = G / (100 k)).  Only the ORDER of the blocks depends on these numbers.
+// times measured on the C3 shape with the two-pass rasterisation (tools/timeline.py: birth 20.1 + 2.49 x, death
+// 18.8 + 2.72 x, values 14.5 + 2.11 x, sites 21.0 + 0.96 x microseconds, x = G / (100 k)).  Only the ORDER of the
+// blocks depends on these numbers.
 __device__ __forceinline__ int block_cost_class(const EngineParams &ep, long long c) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
@@ -26,11 +27,11 @@ __device__ __forceinline__ int block_cost_class(const EngineParams &ep, long lon
     const int k_new = k_ref(B, s, (int)B.sel[s][c] ^ 1, c);
     const float x = (float)T.n_points / (100.0f * (float)(k_new > 0 ? k_new : 1));
     const int inner = move & 3;
-    const float a = inner == BBB_MOVE_BIRTH ? 29.6f : (inner == BBB_MOVE_DEATH ? 25.9f : (inner == BBB_MOVE_VALUES ? 21.8f : 30.9f));
-    const float b = inner == BBB_MOVE_BIRTH ? 2.17f : (inner == BBB_MOVE_DEATH ? 2.23f : (inner == BBB_MOVE_VALUES ? 1.42f : 0.72f));
+    const float a = inner == BBB_MOVE_BIRTH ? 20.1f : (inner == BBB_MOVE_DEATH ? 18.8f : (inner == BBB_MOVE_VALUES ? 14.5f : 21.0f));
+    const float b = inner == BBB_MOVE_BIRTH ? 2.49f : (inner == BBB_MOVE_DEATH ? 2.72f : (inner == BBB_MOVE_VALUES ? 2.11f : 0.96f));
     const float est = a + b * x;
-    // classes of 2.5 us between 23 and 43 us
-    int cls = (int)((43.0f - est) * 0.4f);
+    // classes of 2.5 us between 15.5 and 38 us
+    int cls = (int)((38.0f - est) * 0.4f);
     cls = cls < 0 ? 0 : (cls > BBB_ORDER_BUCKETS - 2 ? BBB_ORDER_BUCKETS - 2 : cls);
     return cls;
 }

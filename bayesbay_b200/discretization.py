@@ -108,9 +108,27 @@ class Voronoi1D(Voronoi):
 
     @staticmethod
     def interpolate_tessellation(voronoi_cells, param_values, interp_positions, input_type="nuclei"):
-        """Nearest-nuclei interpolation on the device (reference _voronoi.py:705-732)."""
+        """Reference _voronoi.py:705-732.  ``'nuclei'``: nearest-nuclei interpolation on the device
+        (``interpolate_nearest_1d``, _utils_1d.pyx:171-192).  ``'extents'``: the layer whose cumulative extent interval
+        ``[sum(extents[:i]), sum(extents[:i+1]))`` holds the position (``interpolate_depth_profile``,
+        _utils_1d.pyx:119-140) -- a results-side utility on one host array, evaluated on the host with the reference's
+        sweep semantics (the layer pointer never moves back; positions past the last interface, and everything after a
+        position below zero, fall in the last layer)."""
+        if input_type == "extents":
+            extents = np.asarray(voronoi_cells, dtype=np.float64)
+            values = np.asarray(param_values, dtype=np.float64)
+            x0 = np.atleast_1d(np.asarray(interp_positions, dtype=np.float64))
+            upper = np.cumsum(extents)          # running sums, accumulated in the reference's order
+            lower = np.concatenate(([0.0], upper[:-1]))
+            out = np.empty(x0.shape, dtype=np.float64)
+            layer, last = 0, extents.size - 1
+            for i, x in enumerate(x0):
+                while not (lower[layer] <= x < upper[layer]) and layer < last:
+                    layer += 1
+                out[i] = values[layer]
+            return out
         if input_type != "nuclei":
-            raise DeviceUnsupported("only input_type='nuclei' is implemented on the device")
+            raise ValueError("`input_type` should either be 'nuclei' or 'extents'")
         from ._batch import device_interpolate_1d
 
         return device_interpolate_1d([np.asarray(voronoi_cells)], [np.asarray(param_values)], interp_positions)[0]

@@ -1,4 +1,5 @@
-"""Multi-GPU check, run under torchrun on a GPU box (not collected by pytest):
+"""Multi-GPU check, run under torchrun on a GPU box (tests/test_gpu_multi.py launches it from `pytest -m gpu` when the
+box has at least 2 GPUs):
 
     torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 
@@ -26,10 +27,8 @@ def run(spec, C, id0, n_total, temps, gather, seed=99, rounds=4, steps=25):
     eng.temperature.copy_(torch.as_tensor(temps[id0: id0 + C]))
     for r in range(rounds):
         eng.step(steps)
-        m, ld = eng.misfit_logdet()
-        g = gather(torch.stack((m, ld, eng.temperature), dim=1).contiguous())
-        t_out, _ = pt_swap(g, seed, r, id0, C)
-        eng.temperature.copy_(t_out)
+        g = gather(eng.misfit_logdet_T())
+        pt_swap(g, seed, r, id0, C, out=eng.temperature)
     k, sites, vals = eng.gather_space(0)
     return k.cpu(), sites.cpu(), vals.cpu(), eng.sigma[0][0].cpu(), eng.temperature.cpu(), eng.n_accepted.cpu()
 

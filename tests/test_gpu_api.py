@@ -19,7 +19,7 @@ from tests import problems  # noqa: E402
 def device_forward(ing):
     if ing["kind"] == "tomography_2d":
         return RayTomographyForward((ing["indptr"], ing["indices"], ing["data"]), ing["points"], "voronoi", "vel",
-                                    save_field_as="interp_vel")
+                                    save_field_as="interp_vel", store_field_samples=ing["points"].shape[0] <= 1000)
     if ing["kind"] == "partition_1d":
         return NearestLookup1D(ing["x"], "voronoi", "y")
     return LinearForward(ing["G"], "my_param_space", ["m0", "m1", "m2", "m3"])
@@ -121,6 +121,8 @@ STAT_CASES = {
     "polyfit": (synthetic.polyfit, 40000, 5000),
     "polyfit_nb": (lambda: synthetic.polyfit(all_gaussian=False), 40000, 5000),
     "tomo_small": (problems.tomo_small, 30000, 5000),
+    # BASELINE configs[2] at full size (100x100 grid, 10 000 rays, k in [10, 200]); reference fixture: 8 chains
+    "tomo_c3": (synthetic.tomography_2d, 24000, 8000),
 }
 
 
@@ -132,8 +134,9 @@ def test_full_run_statistics_match_reference(name, golden_dir):
     g = np.load(os.path.join(golden_dir, f"stats_{name}.npz"))
     mk, n_it, burnin = STAT_CASES[name]
     ing = mk()
+    big = name == "tomo_c3"  # (thinned saving: 160 save points of 64 x 10 000 predicted data instead of 1600)
     inv = make_inversion(ing, 64, seed=20240 + len(name))
-    inv.run(n_iterations=n_it, burnin_iterations=burnin, save_every=10, verbose=False)
+    inv.run(n_iterations=n_it, burnin_iterations=burnin, save_every=100 if big else 10, verbose=False)
     ref_rate, ref_se = _rates(g["proposed"], g["accepted"])
     names = [str(n) for n in g["names"]]
     prop = np.zeros((64, len(names)))

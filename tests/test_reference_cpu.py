@@ -55,3 +55,26 @@ def test_unmodified_reference_runs_the_descriptor_problem():
     assert len(dpred_keys) == 1 and len(res[dpred_keys[0]][0]) == ing["d_obs"].size
     assert all(ch.statistics["n_proposed_models_total"] == 40 for ch in inv.chains)
     assert rate > 0
+
+
+@pytest.mark.skipif(not RR.available(), reason="baseline/_ref is not installed (run __graft_entry__.build())")
+def test_interpolate_tessellation_extents_matches_the_reference():
+    """Voronoi1D.interpolate_tessellation(..., input_type='extents') (discretization/_voronoi.py:705-732,
+    interpolate_depth_profile in _utils_1d.pyx:119-140) incl. its sweep semantics."""
+    import bayesbay_b200 as bb
+
+    ref = RR.import_reference()
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        k = int(rng.integers(1, 9))
+        ext = rng.uniform(0.2, 3.0, k)
+        vals = rng.normal(size=k)
+        x0 = np.sort(rng.uniform(0.0, ext.sum() * 1.3, 40))
+        x0[rng.integers(0, 40, 3)] = np.cumsum(ext)[rng.integers(0, k, 3)]  # exactly on interfaces (unsorted on purpose)
+        want = ref.discretization.Voronoi1D.interpolate_tessellation(ext, vals, x0, input_type="extents")
+        got = bb.discretization.Voronoi1D.interpolate_tessellation(ext, vals, x0, input_type="extents")
+        np.testing.assert_array_equal(got, want)
+    x0 = np.array([-0.5, 0.1, 0.7])  # a position below zero sends the sweep to the last layer for good
+    ext, vals = np.array([1.0, 1.0, 1.0]), np.array([1.0, 2.0, 3.0])
+    np.testing.assert_array_equal(bb.discretization.Voronoi1D.interpolate_tessellation(ext, vals, x0, input_type="extents"),
+                                  ref.discretization.Voronoi1D.interpolate_tessellation(ext, vals, x0, input_type="extents"))
