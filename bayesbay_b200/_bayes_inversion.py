@@ -200,7 +200,78 @@ class BayesianInversion(BaseBayesianInversion):
         raise TypeError("targets cannot be added after the chains were placed on the device; build a new inversion")
 
     def set_perturbation_funcs(self, perturbation_funcs, perturbation_weights=None):
-        raise TypeError("custom perturbation lists are not supported by the device engine")
+        """Custom perturbation list and weights (reference ``_bayes_inversion.py:117-171``).  The device engine runs
+        the library's own perturbations only, so the list must be made of THIS inversion's perturbation objects: the
+        ``ParamSpacePerturbation`` of a space (a new weight for the space as a whole), or its inner birth / death /
+        value / site perturbations one by one (``inversion.perturbation_funcs[0].perturbation_funcs``, as the
+        reference's tests 11 and 19 do -- each then gets its own weight and its own statistics entry), and the
+        ``NoisePerturbation`` (left out: the noise level is never perturbed).  Like the reference, a death weight
+        that differs from its birth weight is reset to the birth weight.  Call it before the first ``run``."""
+        import warnings
+
+        from .perturbations import (BirthPerturbation, DeathPerturbation, NoisePerturbation, ParamPerturbation,
+                                    ParamSpacePerturbation)
+
+        funcs = list(perturbation_funcs)
+        weights = [1] * len(funcs) if perturbation_weights is None else list(perturbation_weights)
+        assert len(funcs) == len(weights), (
+            "`perturbation_funcs` should have the same length of "
+            f"`perturbation_weights`: {len(funcs)} != {len(weights)}")
+        if self.batch.iteration > 0:
+            raise RuntimeError("set_perturbation_funcs must be called before the chains have advanced")
+        spec = dict(self.spec, spaces=[dict(sp) for sp in self.spec["spaces"]])
+        index = {sp["name"]: i for i, sp in enumerate(spec["spaces"])}
+        kinds = ("birth", "death", "values", "sites")
+        whole, inner = {}, {}
+        w_noise = 0.0
+        for f, w in zip(funcs, weights):
+            if not (w > 0):
+                raise ValueError("perturbation weights must be positive")
+            if isinstance(f, ParamSpacePerturbation):
+                whole[f.param_space_name] = whole.get(f.param_space_name, 0.0) + float(w)
+            elif isinstance(f, (BirthPerturbation, DeathPerturbation, ParamPerturbation)):
+                d = inner.setdefault(f.param_space_name, {})
+                if kinds[f.move_kind] in d:
+                    raise ValueError(f"{f.__name__} is listed twice")
+                d[kinds[f.move_kind]] = float(w)
+            elif isinstance(f, NoisePerturbation):
+                w_noise += float(w)
+            else:
+                raise TypeError(f"{f!r}: only the perturbation objects of this inversion run on the device (Python "
+                                "callables cannot run in a CUDA kernel and there is no CPU fallback)")
+        for name in set(whole) | set(inner):
+            if name not in index:
+                raise ValueError(f"unknown parameter space {name!r}")
+            if name in whole and name in inner:
+                raise ValueError(f"parameter space {name!r}: list either its ParamSpacePerturbation or its inner perturbations")
+        for sp in spec["spaces"]:
+            name = sp["name"]
+            if name in whole:
+                sp["w_outer"], sp["flat"] = whole[name], False
+            elif name in inner:
+                d = inner[name]
+                if ("birth" in d) != ("death" in d):
+                    raise ValueError("there should be exactly one birth and one death perturbation function for each "
+                                     f"trans-dimensional parameter space, but {name} has only one of them")
+                if "birth" in d and d["birth"] != d["death"]:
+                    warnings.warn(f"weights for the birth and death perturbations of {name} are different: {d['birth']} != "
+                                  f"{d['death']}. We will default the death perturbation weight to be the same as birth weight")
+                    d["death"] = d["birth"]
+                sp["weights"] = {k: d.get(k, 0.0) for k in kinds}
+                sp["w_outer"], sp["flat"] = None, True
+            else:
+                raise ValueError(f"parameter space {name!r} has no perturbation in the list (its state would never move)")
+        spec["w_noise"] = w_noise if any(t["hierarchical"] for t in spec["targets"]) else None
+        self.spec = spec
+        self.perturbation_funcs, self.perturbation_weights = funcs, weights
+        old = self.batch
+        self.batch = ChainBatch(spec, old.n_chains, device=old.engine.device, seed=old.seed, chain_id0=old.chain_id0,
+                                starting_states=old.current_states(), save_dpred=old.save_dpred)
+        self.batch.seed_global = getattr(old, "seed_global", old.seed)
+        for ch in self._chains:
+            ch._batch = self.batch
+            ch.set_perturbation_funcs(funcs, weights)
+        self._mark_dirty()
 
     def __repr__(self) -> str:
         return (f"{self.__class__.__name__}(parameterization={self.parameterization}, "

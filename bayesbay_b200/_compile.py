@@ -199,7 +199,13 @@ def perturbation_names(spec: dict):
             "sites": f"ParamPerturbation({sp['name']}.discretization)",
         }
         for kind in ("birth", "death", "values", "sites"):
-            out.append((outer, names[kind]) if sp["weights"][kind] > 0 else None)
+            if sp["weights"][kind] <= 0:
+                out.append(None)
+            elif sp.get("flat"):  # the inner perturbations sit in the chain's own list (set_perturbation_funcs)
+                out.append((names[kind], None))
+            else:
+                out.append((outer, names[kind]))
     hier = [t["name"] for t in spec["targets"] if t["hierarchical"]]
-    out.append((f"NoisePerturbation({str(hier) if len(hier) > 1 else hier[0]})", None) if hier else None)
+    out.append((f"NoisePerturbation({str(hier) if len(hier) > 1 else hier[0]})", None)
+               if hier and spec.get("w_noise") != 0 else None)
     return out

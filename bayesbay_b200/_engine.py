@@ -131,6 +131,7 @@ class Engine:
         ps.n_spaces = len(spec["spaces"])
         ps.n_targets = len(spec["targets"])
         ps.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        ps.w_noise = -1.0 if spec.get("w_noise") is None else float(spec["w_noise"])
         for i, sp in enumerate(spec["spaces"]):
             s = ps.spaces[i]
             s.kind = _SPACE_KIND[sp["kind"]]
@@ -145,6 +146,7 @@ class Engine:
                 s.vmin[d], s.vmax[d], s.site_std[d] = sp["vmin"][d], sp["vmax"][d], sp["site_std"][d]
             w = sp["weights"]
             s.w_birth, s.w_death, s.w_values, s.w_sites = w["birth"], w["death"], w["values"], w["sites"]
+            s.w_outer = float(sp.get("w_outer") or 0.0)
             for j, p in enumerate(sp["params"]):
                 s.prior_kind[j] = _PRIOR_KIND[p["kind"]]
                 tab = p.get("table")

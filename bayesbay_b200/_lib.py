@@ -35,6 +35,7 @@ class SpaceSpec(C.Structure):
         ("birth_from", C.c_int32), ("n_params", C.c_int32),
         ("vmin", C.c_double * 2), ("vmax", C.c_double * 2), ("site_std", C.c_double * 2),
         ("w_birth", C.c_double), ("w_death", C.c_double), ("w_values", C.c_double), ("w_sites", C.c_double),
+        ("w_outer", C.c_double),
         ("prior_kind", C.c_int32 * MAX_PARAMS),
         ("prior_a", C.c_double * MAX_PARAMS), ("prior_b", C.c_double * MAX_PARAMS),
         ("perturb_std", C.c_double * MAX_PARAMS), ("perturb_std_birth", C.c_double * MAX_PARAMS),
@@ -68,6 +69,7 @@ class ProblemSpec(C.Structure):
         ("n_spaces", C.c_int32), ("n_targets", C.c_int32),
         ("spaces", SpaceSpec * MAX_SPACES), ("targets", TargetSpec * MAX_TARGETS),
         ("seed", C.c_uint64),
+        ("w_noise", C.c_double),
     ]
 
 

@@ -59,7 +59,7 @@ struct bbb_engine {
         int parity;
         cudaGraph_t graph;
         cudaGraphExec_t exec;
-    } step_graph[16];
+    } step_graph[2][16];  // [16 iterations | 4 iterations][parity mask]
     int step_graphs;  // 1: on (default), 0: BBB_STEP_GRAPH=0 or capture failed
     cudaStream_t step_cap_stream;
     // hosted step (bbb_engine_step_hosted / _wait): per-part "uploaded states differ" words on the device and their
@@ -92,12 +92,13 @@ struct bbb_engine {
 
 // the cached graphs hold the engine parameters BY VALUE: whatever changes them drops the graphs
 static void hosted_graphs_drop(bbb_engine *e) {
-    for (auto &g : e->step_graph)
-        if (g.used) {
-            cudaGraphExecDestroy(g.exec);
-            cudaGraphDestroy(g.graph);
-            g.used = false;
-        }
+    for (auto &row : e->step_graph)
+        for (auto &g : row)
+            if (g.used) {
+                cudaGraphExecDestroy(g.exec);
+                cudaGraphDestroy(g.graph);
+                g.used = false;
+            }
     for (auto &g : e->hosted_graph)
         if (g.used) {
             cudaGraphExecDestroy(g.exec);
@@ -432,7 +433,9 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
     if (write_partial && a.n_groups != e->host.n_partial[t]) {
         // the accept stage sums partial[0 .. n_partial): keep the device copy in step (stream ordered)
         e->host.n_partial[t] = a.n_groups;
-        hosted_graphs_drop(e);
+        // (captured launches hold the parameters by value; the kernels of a chain-local engine's graphs -- proposal,
+        // chain step, state images -- never read n_partial, so its graphs stay)
+        if (!e->host.chain_local) hosted_graphs_drop(e);
         int rc = (int)cudaMemcpyAsync(&e->dev->n_partial[t], &e->host.n_partial[t], sizeof(int), cudaMemcpyHostToDevice, st);
         if (rc != 0) return rc;
     }
@@ -582,15 +585,18 @@ static int run_chain_steps_direct(bbb_engine *e, long long n, cudaStream_t st) {
     return rc;
 }
 
-constexpr int STEP_GRAPH_ITERS = 16;  // (even: the parts' block-order parities are back where they started)
+// graphs of 16 and of 4 iterations (even counts: the parts' block-order parities are back where they started)
+constexpr int STEP_GRAPH_ITERS[2] = {16, 4};
 
 static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st) {
     int rc = part_streams(e);
     if (rc != 0) return rc;
-    while (n >= STEP_GRAPH_ITERS && e->step_graphs) {
+    while (n >= STEP_GRAPH_ITERS[1] && e->step_graphs) {
+        const int size = n >= STEP_GRAPH_ITERS[0] ? 0 : 1;
+        const int iters = STEP_GRAPH_ITERS[size];
         int parity = 0;
         for (int h = 0; h < 4; ++h) parity |= e->order_parity[h] << h;
-        bbb_engine::StepGraph &g = e->step_graph[parity];
+        bbb_engine::StepGraph &g = e->step_graph[size][parity];
         if (!g.used) {
             if (e->step_cap_stream == nullptr) {
                 rc = (int)cudaStreamCreateWithFlags(&e->step_cap_stream, cudaStreamNonBlocking);
@@ -598,7 +604,7 @@ static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st
             }
             rc = (int)cudaStreamBeginCapture(e->step_cap_stream, cudaStreamCaptureModeRelaxed);
             if (rc == 0) {
-                rc = run_chain_steps_direct(e, STEP_GRAPH_ITERS, e->step_cap_stream);
+                rc = run_chain_steps_direct(e, iters, e->step_cap_stream);
                 cudaGraph_t graph = nullptr;
                 const int rc_end = (int)cudaStreamEndCapture(e->step_cap_stream, &graph);
                 if (rc == 0) rc = rc_end;
@@ -619,7 +625,7 @@ static int run_chain_steps_pipelined(bbb_engine *e, long long n, cudaStream_t st
         }
         rc = (int)cudaGraphLaunch(g.exec, st);
         if (rc != 0) return rc;
-        n -= STEP_GRAPH_ITERS;
+        n -= iters;
     }
     return n > 0 ? run_chain_steps_direct(e, n, st) : 0;
 }

@@ -97,11 +97,11 @@ __device__ inline int choose_move(const bbb_problem_spec &P, R &rng) {
     int n_outer = 0;
     for (int s = 0; s < P.n_spaces; ++s) {
         const bbb_space_spec &S = P.spaces[s];
-        w[n_outer++] = S.w_birth + S.w_death + S.w_values + S.w_sites;
+        w[n_outer++] = S.w_outer > 0.0 ? S.w_outer : S.w_birth + S.w_death + S.w_values + S.w_sites;
     }
     bool any_hier = false;
     for (int t = 0; t < P.n_targets; ++t) any_hier |= (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL);
-    if (any_hier) w[n_outer++] = 1.0;
+    if (any_hier && P.w_noise != 0.0) w[n_outer++] = P.w_noise > 0.0 ? P.w_noise : 1.0;
     const int i_outer = rng.choice(w, n_outer);
     if (i_outer >= P.n_spaces) return 4 * P.n_spaces;
     const bbb_space_spec &S = P.spaces[i_outer];

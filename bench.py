@@ -278,12 +278,16 @@ def cuda_arm(args):
     value = world * C * args.steps / (total_ms * 1e-3)
 
     # ---- the same K steps back to back without the flush (L2-warm steady state) ----------------------------
+    # (every back-to-back protocol is rehearsed once untimed: graph captures, lazily loaded kernels and the first use
+    # of a collective otherwise land inside a 2 ms timed region)
+    timed_call(ctx, eng, args.steps, swap if tempered_main else None)
     warm_ms = timed_call(ctx, eng, args.steps, swap if tempered_main else None)
 
     # ---- the other per-GPU workload (see the module docstring), same protocol ------------------------------
     set_ladder(ctx, eng, C, not tempered_main)
     eng.step(40)  # let the chains settle under the changed temperatures (untimed)
     o_ms, o_step, _, o_swaps = timed_steps(ctx, eng, args.steps, None if tempered_main else swap)
+    timed_call(ctx, eng, args.steps, None if tempered_main else swap)
     o_warm = timed_call(ctx, eng, args.steps, None if tempered_main else swap)
     other = {"value": world * C * args.steps / (o_ms * 1e-3), "ms_per_step": o_ms / args.steps,
              "value_l2_warm": world * C * args.steps / (o_warm * 1e-3), "swap_rounds_timed": o_swaps,
@@ -295,6 +299,7 @@ def cuda_arm(args):
 
     # ---- a long run in one call: >= 1000 iterations incl. the from-scratch re-evaluations every 256 steps ---
     long_n = 1024
+    timed_call(ctx, eng, 512, swap if tempered_main else None)  # (rehearsal: crosses two from-scratch re-evaluations)
     long_ms = timed_call(ctx, eng, long_n, swap if tempered_main else None)
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) -----------------------------------
@@ -691,6 +696,7 @@ def emit(obj):
 def main():
     global _JSON_OUT
     _JSON_OUT = _claim_stdout()
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # (no kernel is loaded for the first time inside a timed region)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

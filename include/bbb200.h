@@ -71,6 +71,9 @@ typedef struct {
     int32_t n_params;
     double vmin[2], vmax[2], site_std[2];
     double w_birth, w_death, w_values, w_sites; /* inner weights 1,1,3,1 (0 = move absent) */
+    double w_outer;          /* weight of the space in the chain's outer choice; 0 = the sum of the inner weights (what
+                              * BayesianInversion builds, _bayes_inversion.py:458-466); another value after
+                              * BaseBayesianInversion.set_perturbation_funcs (:117-171) */
     int32_t prior_kind[BBB_MAX_PARAMS];
     double prior_a[BBB_MAX_PARAMS], prior_b[BBB_MAX_PARAMS];
     double perturb_std[BBB_MAX_PARAMS], perturb_std_birth[BBB_MAX_PARAMS];
@@ -139,6 +142,8 @@ typedef struct {
     bbb_space_spec spaces[BBB_MAX_SPACES];
     bbb_target_spec targets[BBB_MAX_TARGETS];
     uint64_t seed;           /* Philox key */
+    double w_noise;          /* weight of the noise perturbation in the outer choice; < 0 = the default (1 when a target
+                              * is hierarchical), 0 = no noise move (set_perturbation_funcs without it) */
 } bbb_problem_spec;
 
 /* Device buffers of one engine (all owned by the caller).  "slot" arrays are double-buffered:

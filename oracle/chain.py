@@ -76,10 +76,12 @@ def outer_moves(spec):
     for i, sp in enumerate(spec["spaces"]):
         inner = [(j, sp["weights"][name]) for j, name in enumerate(INNER) if sp["weights"][name] > 0]
         moves.append(("space", i, inner))
-        weights.append(sum(w for _, w in inner))
-    if any(t["hierarchical"] for t in spec["targets"]):
+        weights.append(sp.get("w_outer") or sum(w for _, w in inner))
+    # (custom weights: BaseBayesianInversion.set_perturbation_funcs, _bayes_inversion.py:117-171)
+    w_noise = spec.get("w_noise")
+    if any(t["hierarchical"] for t in spec["targets"]) and w_noise != 0:
         moves.append(("noise", None, None))
-        weights.append(1)
+        weights.append(1 if w_noise is None else w_noise)
     return moves, weights
 
 

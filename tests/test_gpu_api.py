@@ -446,3 +446,55 @@ def test_simulated_annealing_against_reference_fixture(golden_dir):
         np.testing.assert_allclose(eng.sigma[0][0].cpu().numpy(), g["sigma"][:, t + 1], rtol=1e-12)
         for c, st in enumerate(eng.fetch_states()):
             np.testing.assert_allclose([v[0] for v in st["spaces"][0]["values"]], g["values"][c, t + 1], rtol=1e-12)
+
+
+def test_set_perturbation_funcs_custom_weights():
+    """BaseBayesianInversion.set_perturbation_funcs (reference _bayes_inversion.py:117-171): the inner perturbations of a
+    space used directly, with their own weights, as the reference's tests 11 and 19 do; without the NoisePerturbation the
+    noise level never moves.  The move choice is checked against the oracle on shared Philox streams and against the
+    weights; the statistics carry the flat names."""
+    from oracle import chain as OC
+    from oracle import rng as OR
+
+    ing = synthetic.partition_1d(n_data=30, kmin=2, kmax=12)
+    inv = make_inversion(ing, 48, seed=31)
+    inner = inv.perturbation_funcs[0].perturbation_funcs
+    assert [f.__name__ for f in inner] == ["BirthPerturbation(voronoi)", "DeathPerturbation(voronoi)",
+                                           "ParamPerturbation(voronoi.y)", "ParamPerturbation(voronoi.discretization)"]
+    with pytest.warns(UserWarning):
+        inv.set_perturbation_funcs(inner, [2, 3, 1, 5])  # death weight reset to the birth weight, like the reference
+    assert inv.spec["spaces"][0]["weights"] == dict(birth=2.0, death=2.0, values=1.0, sites=5.0) and inv.spec["w_noise"] == 0.0
+    eng = inv.batch.engine
+    sig0 = eng.sigma[0][0].clone()
+    # the first steps, chain by chain, against the oracle running the same spec
+    spec, seed = inv.spec, inv.batch.seed
+    states = [OC.init_state(problems.spec_from_ingredients(ing), OR.PhiloxStream(seed, c, 0, OR.STREAM_INIT)) for c in range(48)]
+    for t in range(6):
+        eng.step(1)
+        move = eng.move.cpu().numpy()
+        acc = eng.accepted.cpu().numpy()
+        for c in range(48):
+            if states[c] is None:
+                continue
+            states[c], info = OC.step(spec, states[c], OR.PhiloxStream(seed, c, t))
+            assert info["move"] == move[c] and move[c] != 4, (c, t)
+            if bool(acc[c]) != info["accepted"]:
+                states[c] = None
+    inv.batch.iteration = 6
+    inv.run(n_iterations=3000, burnin_iterations=1000, save_every=100, verbose=False)
+    assert torch.equal(eng.sigma[0][0], sig0)  # no noise perturbation in the list
+    prop = eng.n_proposed.cpu().numpy().sum(1)
+    np.testing.assert_allclose(prop[:4] / prop.sum(), [0.2, 0.2, 0.1, 0.5], atol=0.01)
+    assert prop[4] == 0
+    st = inv.chains[0].statistics
+    assert set(st["n_proposed_models"]) == {f.__name__ for f in inner}
+    assert sum(st["n_proposed_models"].values()) == st["n_proposed_models_total"] == 3006
+    # the space as a whole with another weight, noise kept: 3 : 1 between the space and the noise move
+    inv2 = make_inversion(ing, 48, seed=32)
+    inv2.set_perturbation_funcs(inv2.perturbation_funcs, [3, 1])
+    inv2.run(n_iterations=2000, burnin_iterations=0, save_every=500, verbose=False)
+    p2 = inv2.batch.engine.n_proposed.cpu().numpy().sum(1)
+    np.testing.assert_allclose(p2[4] / p2.sum(), 0.25, atol=0.01)
+    np.testing.assert_allclose(p2[:4] / p2[:4].sum(), [1 / 6, 1 / 6, 3 / 6, 1 / 6], atol=0.012)
+    with pytest.raises(TypeError):
+        inv2.set_perturbation_funcs([lambda state: (state, 0.0)])
