@@ -217,8 +217,6 @@ class BayesianInversion(BaseBayesianInversion):
         assert len(funcs) == len(weights), (
             "`perturbation_funcs` should have the same length of "
             f"`perturbation_weights`: {len(funcs)} != {len(weights)}")
-        if self.batch.iteration > 0:
-            raise RuntimeError("set_perturbation_funcs must be called before the chains have advanced")
         spec = dict(self.spec, spaces=[dict(sp) for sp in self.spec["spaces"]])
         index = {sp["name"]: i for i, sp in enumerate(spec["spaces"])}
         kinds = ("birth", "death", "values", "sites")
@@ -239,6 +237,8 @@ class BayesianInversion(BaseBayesianInversion):
             else:
                 raise TypeError(f"{f!r}: only the perturbation objects of this inversion run on the device (Python "
                                 "callables cannot run in a CUDA kernel and there is no CPU fallback)")
+        if self.batch.iteration > 0:
+            raise RuntimeError("set_perturbation_funcs must be called before the chains have advanced")
         for name in set(whole) | set(inner):
             if name not in index:
                 raise ValueError(f"unknown parameter space {name!r}")
