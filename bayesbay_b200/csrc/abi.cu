@@ -62,6 +62,14 @@ struct bbb_engine {
     } step_graph[2][16];  // [16 iterations | 4 iterations][parity mask]
     int step_graphs;  // 1: on (default), 0: BBB_STEP_GRAPH=0 or capture failed
     cudaStream_t step_cap_stream;
+    // chain-local engines, BBB_FUSED_RUN=1 (developer switch, off by default): bbb_engine_step runs the fused persistent
+    // kernel (k_chain_run: proposal + chain step + decision of all iterations up to the next from-scratch re-evaluation
+    // in ONE launch) instead of the per-iteration launches above.  Bit-identical results; measured SLOWER on B200
+    // (0.109 against 0.083 ms per iteration back to back: the proposer warps' straight-line code and the workers'
+    // loops thrash the SM's 32 KB instruction cache -- profiles/r2_fused_run_ncu.md).  run_ctl: the kernel's control
+    // words (ticket counters, per-chain progress, ready queue).
+    int fused_run;
+    int32_t *run_ctl;
     // hosted step (bbb_engine_step_hosted / _wait): per-part "uploaded states differ" words on the device and their
     // pinned host copy, and what the pending call needs should a part have to be redone
     int32_t *hosted_flag_dev, *hosted_flag_host;
@@ -245,6 +253,11 @@ int bbb_engine_create(const bbb_problem_spec *spec, int device, bbb_engine **out
         e->step_graphs = (sg != nullptr && atoi(sg) == 0) ? 0 : 1;
         e->step_cap_stream = nullptr;
     }
+    {
+        const char *fr = getenv("BBB_FUSED_RUN");
+        e->fused_run = (fr != nullptr && atoi(fr) == 1) ? 1 : 0;
+        e->run_ctl = nullptr;
+    }
     for (int t = 0; t < spec->n_targets; ++t) e->has_ray |= (spec->targets[t].fwd_kind == BBB_FWD_RAY2D);
     for (int s = 0; s < BBB_MAX_SPACES; ++s) e->k_bound[s] = s < spec->n_spaces ? spec->spaces[s].kmax : 0;
     e->n_sm = 148;
@@ -313,6 +326,11 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
     }
     CU(cudaSetDevice(e->device));
     CU(cudaMemcpy(e->dev, &e->host, sizeof(EngineParams), cudaMemcpyHostToDevice));
+    if (e->run_ctl) { cudaFree(e->run_ctl); e->run_ctl = nullptr; }
+    if (e->host.chain_local) {
+        CU(cudaMalloc(&e->run_ctl, sizeof(int32_t) * (size_t)chain_run_ctl_words(b->n_chains)));
+        CU(cudaMemset(e->run_ctl, 0, sizeof(int32_t) * (size_t)chain_run_ctl_words(b->n_chains)));
+    }
     e->bound = true;
     return BBB_OK;
 }
@@ -337,6 +355,7 @@ void bbb_engine_destroy(bbb_engine *e) {
         cudaEventDestroy(e->ev_hfork);
         for (auto &st : e->hosted_stream) cudaStreamDestroy(st);
     }
+    if (e->run_ctl) cudaFree(e->run_ctl);
     if (e->hosted_flag_dev) cudaFree(e->hosted_flag_dev);
     if (e->hosted_flag_host) cudaFreeHost(e->hosted_flag_host);
     cudaFree(e->dev);
@@ -658,6 +677,24 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
     const long long C = e->host.buf.n_chains;
     if (!e->has_ray) {
         if (n_steps > 0) CU(launch_fused_steps(e->host, C, n_steps, st));
+        return BBB_OK;
+    }
+    if (e->host.chain_local && e->fused_run && n_steps > 0) {
+        // segments between two from-scratch re-evaluations: ONE persistent launch each
+        const bbb_target_spec &T = P.targets[e->ray_t];
+        int64_t left = n_steps;
+        while (left > 0) {
+            int64_t seg = left;
+            if (e->resync_every > 0 && e->resync_every - e->steps_since_resync < seg) seg = e->resync_every - e->steps_since_resync;
+            if (seg < 1) seg = 1;
+            if (seg * C > (1LL << 30)) seg = (1LL << 30) / C > 0 ? (1LL << 30) / C : 1;
+            CU(launch_chain_run(e->host, 0, C, seg, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax, idx_bytes_of(P, e->ray_t),
+                                e->run_ctl, 2 * e->n_sm, st));
+            bump_k_bound(e, seg);
+            e->steps_since_resync += seg;
+            if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) CU(chain_local_from_scratch(e, false, st));
+            left -= seg;
+        }
         return BBB_OK;
     }
     if (e->host.chain_local && e->pipeline > 1 && n_steps > 1 && C >= 2LL * e->n_sm) {

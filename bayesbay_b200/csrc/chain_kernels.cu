@@ -31,6 +31,7 @@
 
 #include "finish.cuh"
 #include "kernels.h"
+#include "propose.cuh"
 
 namespace bbb {
 
@@ -51,6 +52,35 @@ constexpr unsigned CS_G_MASK = (1u << CS_G_BITS) - 1u, CS_M_MASK = (1u << CS_M_B
 constexpr int CS_PTS = 16;                 // grid points per thread and pass = the largest merged group
 constexpr int CS_SMEM_BLOCK = 112 * 1024;  // two resident blocks per SM
 constexpr int CS_LIST_SMEM = 1024;         // change-list entries kept in shared memory (the rest spill to the global list)
+// The misfit phases (touched-ray scan, residual arithmetic, block sum) are mapped onto the first CS_MAIN_WARPS warps in
+// EVERY variant of the kernel: the order of the floating-point misfit sum then does not depend on whether the block's
+// last warp is a worker (k_chain_step) or the proposer of the fused kernel (k_chain_run), and the variants stay
+// bit-identical to each other.
+#ifndef CS_N_PROPOSERS
+#define CS_N_PROPOSERS 1
+#endif
+constexpr int CS_PROPOSERS = CS_N_PROPOSERS;  // fused kernel: warps of a block that draw proposals
+constexpr int CS_MAIN_WARPS = CS_WARPS - CS_PROPOSERS;
+constexpr int CS_MAIN = CS_MAIN_WARPS * 32;
+
+// One drawn proposal on its way from the proposer warp to the workers of the fused kernel (shared memory): the scalars
+// k_chain_step reads from the proposal kernel's global outputs, and everything of the decision that does not need the
+// new misfit.
+struct ItemRec {
+    long long c;  // chain (-1: no more work)
+    int move, cur, k_old, k_new, rm, ins;
+    double lpr, nx, ny;
+    FinishIn fin;
+    FinishPre pre;
+};
+
+// block-wide barrier of the step body: all 512 threads (one block per chain), or the 480 workers of the fused kernel
+// (named barrier 1; the proposer warp never joins it)
+template <bool FUSED>
+__device__ __forceinline__ void cs_sync() {
+    if constexpr (FUSED) asm volatile("bar.sync 1, %0;" ::"n"(CS_MAIN) : "memory");
+    else __syncthreads();
+}
 
 struct PrepEntry {
     int j0, len;  // entries of the (merged) column inside the current ray tile; the level rides in len's top 2 bits
@@ -107,14 +137,15 @@ long long chain_local_tile_rays(long long n_data, int kmax, long long n_points) 
     return (((n_data + n_tiles - 1) / n_tiles) + 31) & ~31LL;
 }
 
+template <bool FUSED>
 __device__ __forceinline__ double block_sum_to_thread0(double v, double *s_red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
+    cs_sync<FUSED>();
     double tot = 0.0;
     if (threadIdx.x == 0)
-        for (int w = 0; w < CS_WARPS; ++w) tot += s_red[w];
+        for (int w = 0; w < CS_MAIN_WARPS; ++w) tot += s_red[w];  // (the misfit terms live on the first CS_MAIN_WARPS warps)
     return tot;
 }
 
@@ -198,9 +229,14 @@ __device__ __forceinline__ void fx_add4(unsigned lo_s, unsigned hi_s, const int 
 // One chain's step by one block (everything below the scalars of the proposal); see k_chain_step.
 // MULTI: the target's rays need several accumulator tiles (csc_n_tiles > 1); problems with one tile get an
 // instantiation without any of the multi-tile code.
-template <typename IdxT, bool MULTI>
-__device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, long long c, const int32_t *guard,
-                                                unsigned char *cs_smem) {
+// FUSED: the body runs on the 480 workers of k_chain_run with the proposal handed over in shared memory (`rec`).
+// Returns what the accumulator planes hold afterwards: n >= 0 -- only the n rays listed in the touched-ray list (the
+// `prep` area) are non-zero; -1 -- anything; -2 -- untouched (still zero).
+template <typename IdxT, bool MULTI, bool FUSED>
+__device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, long long c, const int32_t *guard,
+                                               unsigned char *cs_smem, ItemRec *rec) {
+    constexpr int NW = FUSED ? CS_MAIN_WARPS : CS_WARPS;  // warps in the body
+    constexpr int NTH = NW * 32;
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const bbb_target_spec &T = P.targets[t];
@@ -219,29 +255,41 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
     __shared__ double s_red[CS_WARPS];
     __shared__ FinishIn s_fin;
     __shared__ FinishPre s_pre;
-    constexpr int RW = CS_WARPS - 1;  // warps of the rasterisation pass; the last warp prepares the decision meanwhile
+    constexpr int RW = CS_MAIN_WARPS;  // warps of the rasterisation pass; the last warp prepares the decision meanwhile
+    FinishIn &fin = FUSED ? rec->fin : s_fin;
+    FinishPre &pre = FUSED ? rec->pre : s_pre;
 
-    // every scalar of the chain's proposal is requested before the first one is used: ONE memory round trip instead
-    // of a chain of three (move -> selector -> cell counts)
-    const int move = B.move[c];
-    const double lpr = B.log_prob_ratio[c];
-    const int cur = B.sel[s][c], prop = cur ^ 1;
-    const int k_slot0 = k_ref(B, s, 0, c), k_slot1 = k_ref(B, s, 1, c);
-    const int rm = B.edit[c], ins = B.edit[C + c];
-    const double nx = B.edit_site[c], ny = B.edit_site[C + c];
-    // hosted step: stale caches (see k_propose) -- the whole launch is a no-op
-    if (guard != nullptr && *guard != 0) return;
-    if (!target_touched(P, move, lpr, t)) {  // noise move, other space, or rejected by the prior: no forward
-        if (tid == 0) {
-            Rng rng;
-            rng_begin(rng, ep, c, STREAM_STEP, true);
-            finish_chain(ep, c, rng);
-            rng_end(rng, ep, c);
-            CS_TL_G(17);
+    int move, cur, k_old, k_new, rm, ins;
+    double lpr, nx, ny;
+    if constexpr (FUSED) {
+        move = rec->move; cur = rec->cur; k_old = rec->k_old; k_new = rec->k_new; rm = rec->rm; ins = rec->ins;
+        lpr = rec->lpr; nx = rec->nx; ny = rec->ny;
+    } else {
+        // every scalar of the chain's proposal is requested before the first one is used: ONE memory round trip
+        // instead of a chain of three (move -> selector -> cell counts)
+        move = B.move[c];
+        lpr = B.log_prob_ratio[c];
+        cur = B.sel[s][c];
+        const int k_slot0 = k_ref(B, s, 0, c), k_slot1 = k_ref(B, s, 1, c);
+        rm = B.edit[c]; ins = B.edit[C + c];
+        nx = B.edit_site[c]; ny = B.edit_site[C + c];
+        k_old = cur ? k_slot1 : k_slot0; k_new = cur ? k_slot0 : k_slot1;
+        // hosted step: stale caches (see k_propose) -- the whole launch is a no-op
+        if (guard != nullptr && *guard != 0) return -2;
+        if (!target_touched(P, move, lpr, t)) {  // noise move, other space, or rejected by the prior: no forward
+            if (tid == 0) {
+                Rng rng;
+                rng_begin(rng, ep, c, STREAM_STEP, true);
+                finish_chain(ep, c, rng);
+                rng_end(rng, ep, c);
+                CS_TL_G(17);
+            }
+            return -2;
         }
-        return;
+        if (tid == CS_THREADS - 1) finish_gather(ep, c, s_fin);  // thread 0 decides from these after the forward
     }
-    if (tid == CS_THREADS - 1) finish_gather(ep, c, s_fin);  // thread 0 decides from these after the forward
+    const int prop = cur ^ 1;
+    (void)move;
 
     const int K = S.kmax, RT = T.csc_tile_rays, NT = MULTI ? T.csc_n_tiles : 1, G = T.n_points, R = T.n_data;
     unsigned *acc_lo = reinterpret_cast<unsigned *>(cs_smem);
@@ -256,7 +304,6 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
     constexpr int CS_QUEUE_SMEM = CS_CHUNK * (int)sizeof(PrepEntry) / 4;
     unsigned *s_touch = s_list + CS_LIST_SMEM;  // multi-tile: bitmap of the touched rays
 
-    const int k_old = cur ? k_slot1 : k_slot0, k_new = cur ? k_slot0 : k_slot1;
     const int inner = move & 3;
     const bool recip = T.transform == BBB_TRANSFORM_RECIPROCAL;
     IdxT *row = reinterpret_cast<IdxT *>(B.idx_cm[t]) + c * ((long long)(G + 15) & ~15LL);
@@ -271,7 +318,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
 
     // ---- tables: proposed sites, cell function of the current (fo) and proposed (fn) state --------------------
     double fmax = 0.0;
-    for (int j = tid; j < k_new; j += CS_THREADS) {
+    for (int j = tid; j < k_new; j += NTH) {
         sx[j] = site_ref(B, S, s, prop, 0, j, c);
         sy[j] = site_ref(B, S, s, prop, 1, j, c);
         double v = value_ref(B, S, s, prop, T.param, j, c);
@@ -280,7 +327,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
         fmax = fmax > fabs(v) ? fmax : fabs(v);
         if (!(fabs(v) <= 1.79769313486231570815e308)) fmax = INFINITY;  // NaN / inf
     }
-    for (int j = tid; j < k_old; j += CS_THREADS) {
+    for (int j = tid; j < k_old; j += NTH) {
         double v = value_ref(B, S, s, cur, T.param, j, c);
         if (recip) v = 1.0 / v;
         fo[j] = v;
@@ -294,10 +341,10 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
         fmax = fmax > other ? fmax : other;
     }
     if (lane == 0) s_red[warp] = fmax;
-    __syncthreads();
+    cs_sync<FUSED>();
     CS_TL(1);
     fmax = 0.0;
-    for (int w = 0; w < CS_WARPS; ++w) fmax = fmax > s_red[w] ? fmax : s_red[w];
+    for (int w = 0; w < NW; ++w) fmax = fmax > s_red[w] ? fmax : s_red[w];
     // (s_red is next written by the misfit sum, several barriers from here)
     // fixed-point scale: |sum of the terms of one ray| <= csc_bound * 2 fmax < 2^e  ->  quantum 2^(e - 61)
     const bool finite = fmax <= 1.79769313486231570815e308 && T.csc_bound * (2.0 * fmax) <= 1.79769313486231570815e308;
@@ -314,7 +361,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
     // List entries (back << 31 | level << 29 | group << 12 | cell): points captured by the inserted cell carry their
     // OLD owner; points that lost their owner (back = 1, after the re-derivation) their NEW owner, the old one being
     // the removed cell.
-    if (tid == CS_THREADS - 1) {
+    if (!FUSED && tid == CS_THREADS - 1) {
         // everything of the decision that does not need the new misfit (logarithms, the generator, other targets):
         // off the critical path, on the one warp without rasterisation work
         Rng rng;
@@ -401,7 +448,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
         if (scn || reach) queue_at(atomicAdd(&s_back, 1)) = ((unsigned)(g0 >> 4) << 17) | (reach ? 1u << 16 : 0u) | scn;
     }
     CS_TL(10);
-    __syncthreads();
+    cs_sync<FUSED>();
     CS_TL(2);
     // (the queue is complete)
     // Pass 2: 16 lanes per queued group, lane q = point q of the group.  A point of the removed / moved cell is
@@ -415,7 +462,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
     {
         const int n_items = s_back;
         const int q = tid & 15, half = lane >> 4;
-        for (int base = 0; base < n_items; base += CS_THREADS / 16) {
+        for (int base = 0; base < n_items; base += NTH / 16) {
             const int it = base + (tid >> 4);
             const unsigned item = it < n_items ? queue_at(it) : 0u;
             const int g0 = (int)(item >> 17) << 4;
@@ -470,7 +517,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
             if (entry != CS_NONE) list_at(pos + __popc(emit & ((1u << lane) - 1u))) = entry;
         }
     }
-    __syncthreads();
+    cs_sync<FUSED>();
     CS_TL(3);
     const int n_list = s_front;
 
@@ -480,7 +527,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
     const double *dt0 = T.csc_data[0], *dt1 = T.csc_data[1], *dt2 = T.csc_data[2];
     const unsigned lo_s = (unsigned)__cvta_generic_to_shared(acc_lo), hi_s = (unsigned)__cvta_generic_to_shared(acc_hi);
     auto accumulate = [&](int tile) {
-        for (int base = 0; base < n_list; base += CS_CHUNK) {
+        for (int base = 0; base < n_list; base += NTH) {
             const int e = base + tid;
             PrepEntry pe{0, 0, 0.0};
             if (e < n_list) {
@@ -497,15 +544,15 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                 }
             }
             prep[tid] = pe;
-            __syncthreads();
+            cs_sync<FUSED>();
             if (base == 0) CS_TL(4);
-            const int n = min(CS_CHUNK, n_list - base);
+            const int n = min(NTH, n_list - base);
             // two columns per warp and round, four entries per lane and column: all loads of a round are issued
             // before its first atomic
-            for (int i = warp; i < n; i += 2 * CS_WARPS) {
+            for (int i = warp; i < n; i += 2 * NW) {
                 PrepEntry qa = prep[i];
                 PrepEntry qb{0, 0, 0.0};
-                if (i + CS_WARPS < n) qb = prep[i + CS_WARPS];
+                if (i + NW < n) qb = prep[i + NW];
                 const int la = qa.len >> 30, lb = qb.len >> 30;
                 qa.len &= 0x3FFFFFFF;
                 qb.len &= 0x3FFFFFFF;
@@ -535,15 +582,15 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                     if (base_j < qb.len) fx_add4(lo_s, hi_s, rb, wb, qb.dlt, scale, base_j, qb.len, lane);
                 }
             }
-            __syncthreads();
+            cs_sync<FUSED>();
         }
     };
     auto zero_acc = [&]() {
         uint4 *acc4 = reinterpret_cast<uint4 *>(acc_lo);  // (several tiles: RT is a multiple of 32)
 #pragma unroll 4
-        for (int i = tid; i < (2 * RT) >> 2; i += CS_THREADS) acc4[i] = make_uint4(0, 0, 0, 0);
-        for (int r = ((2 * RT) & ~3) + tid; r < 2 * RT; r += CS_THREADS) acc_lo[r] = 0;
-        __syncthreads();
+        for (int i = tid; i < (2 * RT) >> 2; i += NTH) acc4[i] = make_uint4(0, 0, 0, 0);
+        for (int r = ((2 * RT) & ~3) + tid; r < 2 * RT; r += NTH) acc_lo[r] = 0;
+        cs_sync<FUSED>();
     };
 
     // ---- misfit: phi' - phi = sum_r w_r d_r (2 res_r + d_r) over the touched rays -----------------------------
@@ -569,12 +616,12 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
             // used (one word at a time, every round waited for its own load); each thread still adds its rays in
             // ascending order, so the sum is the same
             const int n_words = (nr + 31) / 32;
-            for (int w0 = warp; w0 < n_words; w0 += 8 * CS_WARPS) {
+            for (int w0 = warp; w0 < n_words && warp < CS_MAIN_WARPS; w0 += 8 * CS_MAIN_WARPS) {
                 unsigned lo[8], hi[8];
                 double rr[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int w = w0 + u * CS_WARPS, r = 32 * w + lane;
+                    const int w = w0 + u * CS_MAIN_WARPS, r = 32 * w + lane;
                     const bool in = w < n_words && r < nr;
                     lo[u] = in ? acc_lo[r] : 0u;
                     hi[u] = in ? acc_hi[r] : 0u;
@@ -586,14 +633,14 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if ((lo[u] | hi[u]) == 0) continue;
-                    const int r = 32 * (w0 + u * CS_WARPS) + lane;
+                    const int r = 32 * (w0 + u * CS_MAIN_WARPS) + lane;
                     const double d = (double)(long long)(((unsigned long long)hi[u] << 32) | lo[u]) * inv_scale;
                     const double wr = (T.cov_kind == BBB_COV_VECTOR) ? T.cov_vec[r0 + r] : 1.0;
                     dphi += wr * (d * (2.0 * rr[u] + d));
                     park[r0 + r] = rr[u] + d;
                 }
             }
-            __syncthreads();
+            cs_sync<FUSED>();
             continue;
         }
         const bool pairs = ((R | r0 | nr | RT) & 1) == 0;  // rays two at a time: 16-byte loads of the residual row
@@ -609,13 +656,14 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                 acc_hi[r] = (unsigned)__double2hiint(nv);
             }
         };
-        if (!MULTI && (RT & 3) == 0 && RT <= 8 * 4 * CS_THREADS) {
-            // (a) every thread scans 4 consecutive rays per round, bit (4 i + j) of m: ray 4 tid + 2048 i + j touched
+        if (!MULTI && (RT & 3) == 0 && RT <= 8 * 4 * CS_MAIN) {
+            // (a) every thread of the first CS_MAIN_WARPS warps scans 4 consecutive rays per round, bit (4 i + j) of m:
+            // ray 4 tid + 4 CS_MAIN i + j touched
             unsigned m = 0;
 #pragma unroll 8
             for (int i = 0; i < 8; ++i) {
-                const int r4 = 4 * tid + 4 * CS_THREADS * i;
-                if (r4 < nr) {
+                const int r4 = 4 * tid + 4 * CS_MAIN * i;
+                if (r4 < nr && tid < CS_MAIN) {
                     const uint4 lo4 = *reinterpret_cast<const uint4 *>(acc_lo + r4), hi4 = *reinterpret_cast<const uint4 *>(acc_hi + r4);
                     m |= (((lo4.x | hi4.x) != 0 ? 1u : 0u) | ((lo4.y | hi4.y) != 0 ? 2u : 0u) | ((lo4.z | hi4.z) != 0 ? 4u : 0u) |
                           ((lo4.w | hi4.w) != 0 ? 8u : 0u)) << (4 * i);
@@ -631,11 +679,11 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                 if (lane >= o) incl += v;
             }
             if (lane == 31) s_wtot[warp] = incl;
-            __syncthreads();
+            cs_sync<FUSED>();
             int pos = incl - cnt;
             n_touch = 0;
 #pragma unroll
-            for (int w = 0; w < CS_WARPS; ++w) {
+            for (int w = 0; w < CS_MAIN_WARPS; ++w) {
                 const int wt = s_wtot[w];
                 if (w < warp) pos += wt;
                 n_touch += wt;
@@ -644,16 +692,16 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                 while (m) {
                     const int b = __ffs(m) - 1;
                     m &= m - 1;
-                    touch[pos++] = (unsigned short)(4 * tid + 4 * CS_THREADS * (b >> 2) + (b & 3));
+                    touch[pos++] = (unsigned short)(4 * tid + 4 * CS_MAIN * (b >> 2) + (b & 3));
                 }
-                __syncthreads();
+                cs_sync<FUSED>();
                 // (c) the touched rays, four per thread in flight
-                for (int i0 = tid; i0 < n_touch; i0 += 4 * CS_THREADS) {
+                for (int i0 = tid; i0 < n_touch && tid < CS_MAIN; i0 += 4 * CS_MAIN) {
                     int rq[4];
                     double rr[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + u * CS_THREADS;
+                        const int i = i0 + u * CS_MAIN;
                         rq[u] = i < n_touch ? (int)touch[i] : -1;
                         rr[u] = rq[u] >= 0 ? res[r0 + rq[u]] : 0.0;
                     }
@@ -666,22 +714,22 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                 while (m) {
                     const int b = __ffs(m) - 1;
                     m &= m - 1;
-                    const int r = 4 * tid + 4 * CS_THREADS * (b >> 2) + (b & 3);
+                    const int r = 4 * tid + 4 * CS_MAIN * (b >> 2) + (b & 3);
                     one_ray(r, res[r0 + r]);
                 }
             }
         } else if (pairs) {
             // CS_MISFIT_U 16-byte loads of the residual row in flight per thread (C3: the whole row in one round)
-            for (int rb = 2 * tid; rb < nr; rb += 2 * CS_MISFIT_U * CS_THREADS) {
+            for (int rb = 2 * tid; rb < nr && tid < CS_MAIN; rb += 2 * CS_MISFIT_U * CS_MAIN) {
                 double2 rr[CS_MISFIT_U];
 #pragma unroll
                 for (int u = 0; u < CS_MISFIT_U; ++u) {
-                    const int r = rb + 2 * u * CS_THREADS;
+                    const int r = rb + 2 * u * CS_MAIN;
                     rr[u] = r < nr ? *reinterpret_cast<const double2 *>(res + r0 + r) : make_double2(0.0, 0.0);
                 }
 #pragma unroll
                 for (int u = 0; u < CS_MISFIT_U; ++u) {
-                    const int r = rb + 2 * u * CS_THREADS;
+                    const int r = rb + 2 * u * CS_MAIN;
                     if (r >= nr) continue;
                     const uint2 lo2 = *reinterpret_cast<const uint2 *>(acc_lo + r), hi2 = *reinterpret_cast<const uint2 *>(acc_hi + r);
                     if ((lo2.x | lo2.y | hi2.x | hi2.y) == 0) continue;
@@ -690,29 +738,29 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
                 }
             }
         } else {
-            for (int rb = tid; rb < nr; rb += 4 * CS_THREADS) {
+            for (int rb = tid; rb < nr && tid < CS_MAIN; rb += 4 * CS_MAIN) {
                 double rr[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int r = rb + u * CS_THREADS;
+                    const int r = rb + u * CS_MAIN;
                     rr[u] = r < nr ? res[r0 + r] : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int r = rb + u * CS_THREADS;
+                    const int r = rb + u * CS_MAIN;
                     if (r < nr) one_ray(r, rr[u]);
                 }
             }
         }
-        if (MULTI) __syncthreads();
+        if (MULTI) cs_sync<FUSED>();
     }
     CS_TL(11);
-    dphi = block_sum_to_thread0(dphi, s_red);
+    dphi = block_sum_to_thread0<FUSED>(dphi, s_red);
     CS_TL(6);
 
     // ---- likelihood ratio, decision, statistics (thread 0), then the commit by the whole block ----------------
-    if (tid == 0) s_accept = finish_post(ep, c, s_fin, s_pre, t, finite ? s_fin.phi_old[t].s0 + dphi : NAN) ? 1 : 0;
-    __syncthreads();
+    if (tid == 0) s_accept = finish_post(ep, c, fin, pre, t, finite ? fin.phi_old[t].s0 + dphi : NAN) ? 1 : 0;
+    cs_sync<FUSED>();
     CS_TL(7);
     if (tid == 0 && blockIdx.x < 4096) {
 #ifdef CS_TIMELINE
@@ -721,15 +769,16 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
 #endif
     }
     CS_TL_G(17);
-    if (!s_accept) return;
+    const int planes = MULTI ? -1 : n_touch;
+    if (!s_accept) return planes;
 
     if (!MULTI && n_touch >= 0) {
-        for (int i = tid; i < n_touch; i += CS_THREADS) {
+        for (int i = tid; i < n_touch; i += NTH) {
             const int r = (int)touch[i];
             res[r] = __hiloint2double((int)acc_hi[r], (int)acc_lo[r]);
         }
     } else if (!MULTI) {
-        for (int r = tid; r < R; r += CS_THREADS) {
+        for (int r = tid; r < R; r += NTH) {
             const unsigned lo = acc_lo[r], hi = acc_hi[r];
             if ((lo | hi) != 0) res[r] = __hiloint2double((int)hi, (int)lo);
         }
@@ -737,25 +786,25 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
         const double *park = B.dpred_scratch[t] + c * (long long)R;
         // (eight words per warp and round: all loads of a round ahead of its stores)
         const int n_words = (R + 31) / 32;
-        for (int w0 = warp; w0 < n_words; w0 += 8 * CS_WARPS) {
+        for (int w0 = warp; w0 < n_words; w0 += 8 * NW) {
             double v[8];
             bool on[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int w = w0 + u * CS_WARPS;
+                const int w = w0 + u * NW;
                 on[u] = w < n_words && ((s_touch[w] >> lane) & 1u);
                 v[u] = on[u] ? park[32 * w + lane] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (on[u]) res[32 * (w0 + u * CS_WARPS) + lane] = v[u];
+                if (on[u]) res[32 * (w0 + u * NW) + lane] = v[u];
         }
     }
     // nearest-site index: renumber the survivors when the edit shifts cell indices (death), then the changed points
     constexpr int VEC = 16 / (int)sizeof(IdxT);
     const bool renumber = (rm >= 0 || ins >= 0) && rm != ins && !(rm < 0 && ins >= k_old);
     if (renumber) {
-        for (int g0 = tid * VEC; g0 < G; g0 += CS_THREADS * VEC) {
+        for (int g0 = tid * VEC; g0 < G; g0 += NTH * VEC) {
             uint4 wv = *reinterpret_cast<const uint4 *>(row + g0);
             IdxT *ow = reinterpret_cast<IdxT *>(&wv);
 #pragma unroll
@@ -767,9 +816,9 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
             }
             *reinterpret_cast<uint4 *>(row + g0) = wv;
         }
-        __syncthreads();
+        cs_sync<FUSED>();
     }
-    for (int e = tid; e < n_list; e += CS_THREADS) {
+    for (int e = tid; e < n_list; e += NTH) {
         const unsigned pk = list_at(e);
         const int lvl = (int)((pk >> 29) & 3u);
         const int g_first = (int)((pk >> CS_M_BITS) & CS_G_MASK) << (2 * lvl);
@@ -778,6 +827,7 @@ __device__ __forceinline__ void chain_step_body(const EngineParams &ep, int t, l
     }
     CS_TL(8);
     CS_TL_G(17);
+    return planes;
 }
 
 // One block per chain.  -DCS_PERSISTENT=1 (developer switch) launches 2 blocks per SM that take chains from a work
@@ -841,14 +891,332 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             for (int i = 1; i < BBB_ORDER_BUCKETS; ++i) cls += b >= s_cum[i] ? 1 : 0;
             c = B.block_order[(long long)cls * C + c_first + (b - s_cum[cls])];
         }
-        chain_step_body<IdxT, MULTI>(ep, t, c, guard, cs_smem);
+        chain_step_body<IdxT, MULTI, false>(ep, t, c, guard, cs_smem, nullptr);
         if (persistent) __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused chain-local run: proposal + chain step + decision of MANY iterations in ONE persistent launch
+// (`BaseMarkovChain.advance_chain`, src/bayesbay/_markov_chain.py:284-295 -- the per-chain loop -- for all chains).
+//
+// Two blocks per SM stay resident for the whole launch, so there is no per-iteration launch, no wave tail per
+// iteration, and the slow chains of one iteration overlap the fast chains of the next.  Work = (chain, its next
+// iteration); a chain is READY when its previous iteration is complete.  Ready chains wait in a global FIFO (ctl):
+// tickets from a `head` counter, entries published with release stores by whoever completes a chain's iteration
+// (ticket h < n_chains is chain h itself: every chain starts ready).  A chain is therefore never claimed before it
+// can run, whatever the number of proposals in flight.
+// A block is warp-specialised:
+//   * the last CS_PROPOSERS warps, the PROPOSERS, each take a ticket when one of their two records is free, draw
+//     the chain's proposal exactly as k_propose does, and
+//       - decide proposals that need no forward (noise moves, proposals the prior rejects) on their own,
+//       - hand the others to the workers (record index into a block-level FIFO in shared memory, mbarrier per FIFO
+//         position / per record), together with everything of the decision that does not need the new misfit;
+//     (CS_N_PROPOSERS is a compile-time choice: one proposer needs ~34 us of its own time per forward item against
+//     the workers' ~22 us; two are slower still, because every further instruction stream lowers the hit rate of the
+//     SM's instruction cache for all of them -- see the measurement note below);
+//   * the first CS_MAIN_WARPS warps, the WORKERS, run chain_step_body on the records in arrival order: change-local
+//     rasterisation, forward, misfit, decision, commit.  They clear only the accumulator words the item touched.
+// Results are bit-identical to k_propose + k_chain_step (same draws, same arithmetic, same summation order); they do
+// not depend on which block runs which item.
+// MEASURED (B200, C3, 1024 chains, profiles/r2_fused_run_ncu.md): 0.109 ms per iteration with one proposer per block,
+// 0.122 with two, against 0.083 for k_propose + k_chain_step pipelined on four streams.  The kernel is bound by
+// instruction fetch: the proposal is ~3 000 executed instructions of straight-line code per item (7 000 in the
+// binary), the SM's L1.5 instruction cache holds 2 000, and proposers and workers evict each other (instruction-cache
+// hit rate 52 %, `no_instruction` the second largest stall reason, GPC instruction-fetch path at 77 % of its peak).
+// It therefore stays behind the developer switch BBB_FUSED_RUN=1; the default step keeps the two kernels apart.
+// ctl (device int32 words, zero when the launch starts, zero again when it ends): [0] head (tickets), [1] blocks done,
+// [2] tail (entries published), [4 + c] iterations chain c completed in this launch, then (8-byte aligned) n_chains
+// 64-bit FIFO entries (ticket tag << 32 | chain).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+}
+// (polling with acquire loads would invalidate the SM's L1 on every probe and slow every other warp of the SM down:
+// the FIFO entry is polled with relaxed loads, ONE fence follows the hit)
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+#ifdef CS_TIMELINE
+__device__ long long g_runstats[1024][16];
+#define RS_ADD(i, v) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024) atomicAdd((unsigned long long *)&g_runstats[blockIdx.x][i], (unsigned long long)(v)); } while (0)
+#define RS_CLK() clock64()
+#else
+#define RS_ADD(i, v) do { (void)(v); } while (0)
+#define RS_CLK() 0LL
+#endif
+
+constexpr int CS_RECS = 2 * CS_PROPOSERS;  // records of a block: two per proposer (one at / waiting for the workers, one being drawn)
+
+struct RunShared {
+    unsigned long long ready[CS_RECS];  // block FIFO position filled
+    unsigned long long empty[CS_RECS];  // record released by the workers
+    int fifo[CS_RECS];
+    int tail;
+    int last;
+    double draw[CS_PROPOSERS][2][32];
+    Edit edit[CS_PROPOSERS];  // the proposers' edit scripts (all lanes of a proposer build the same one)
+    ItemRec rec[CS_RECS];
+};
+
+__host__ __device__ inline long long run_ctl_queue_offset(long long n_chains_engine) { return (4 + n_chains_engine + 1) & ~1LL; }
+
+// a chain's iteration is complete (one thread, after a barrier / warp sync behind the item's last global store):
+// count it and, unless it was the chain's last one of this launch, publish the chain as ready
+__device__ __forceinline__ void run_complete(int32_t *ctl, unsigned long long *queue, long long c, int n_chains, int n_iters) {
+    const int done = ctl[4 + c] + 1;
+    ctl[4 + c] = done;
+    if (done >= n_iters) return;
+    __threadfence();
+    const unsigned j = atomicAdd(reinterpret_cast<unsigned *>(ctl + 2), 1u);
+    st_release_gpu_u64(queue + (j % (unsigned)n_chains), ((unsigned long long)(j + 1u) << 32) | (unsigned long long)(unsigned)c);
+}
+
+__device__ __noinline__ void run_proposer(const EngineParams &ep, int t, long long c_first, int n_chains, int n_iters, int32_t *ctl,
+                                          RunShared &sh, int pw) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    const int lane = threadIdx.x & 31;
+    const unsigned total = (unsigned)n_chains * (unsigned)n_iters;
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(ctl + run_ctl_queue_offset(C));
+    int produced = 0;
+    auto hand_over = [&](int r) {  // lane 0: record r into the block's FIFO
+        const int pos = atomicAdd(&sh.tail, 1) % CS_RECS;
+        sh.fifo[pos] = r;
+        mbar_arrive(&sh.ready[pos]);
+    };
+    for (;;) {
+        // a ticket is taken only when a record is free for the chain it brings
+        const int r = 2 * pw + (produced & 1);
+        if (produced >= 2) {
+            const long long t0 = RS_CLK();
+            mbar_wait(&sh.empty[r], (unsigned)((produced >> 1) - 1) & 1u);
+            RS_ADD(3, RS_CLK() - t0);
+        }
+        ItemRec &rec = sh.rec[r];
+        unsigned h = 0;
+        if (lane == 0) h = atomicAdd(reinterpret_cast<unsigned *>(ctl), 1u);
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (h >= total) {
+            if (lane == 0) {  // end mark
+                rec.c = -1;
+                hand_over(r);
+            }
+            return;
+        }
+        RS_ADD(4, 1);
+        long long c = c_first + h;
+        if (h >= (unsigned)n_chains) {  // the (h - n_chains)-th chain to become ready again
+            const long long t0 = RS_CLK();
+            const unsigned j = h - (unsigned)n_chains;
+            unsigned cc = 0;
+            if (lane == 0) {
+                const unsigned long long *slot = queue + (j % (unsigned)n_chains);
+                unsigned long long v;
+                while ((unsigned)((v = ld_relaxed_gpu_u64(slot)) >> 32) != j + 1u) __nanosleep(200);
+                cc = (unsigned)v;
+                __threadfence();  // acquire: the chain's state as its last iteration left it
+            }
+            c = (long long)__shfl_sync(0xffffffffu, cc, 0);
+            RS_ADD(0, RS_CLK() - t0);
+        }
+        const long long t_prop = RS_CLK();
+        FastRng rng;
+        rng.begin(sh.draw[pw][0], sh.draw[pw][1], B.tape != nullptr ? B.tape + c * B.tape_stride : nullptr,
+                  B.tape != nullptr ? B.tape_cursor[c] : 0, B.tape_stride, P.seed, (uint64_t)(B.chain_id0 + c), (uint64_t)B.iteration[c],
+                  STREAM_STEP);
+        Edit &ed = sh.edit[pw];
+        propose_chain(P, B, c, rng, false, ed);
+        const long long cursor = rng.after();
+        if (lane == 0) B.tape_cursor[c] = cursor;
+        __syncwarp();
+        const int move = ed.move;  // (every lane built the same script)
+        const double lpr = ed.lpr;
+        RS_ADD(1, RS_CLK() - t_prop);
+        if (!target_touched(P, move, lpr, t)) {  // no forward: the whole decision is this warp's
+            const long long t0 = RS_CLK();
+            RS_ADD(5, 1);
+            if (lane == 0) {  // (finish_chain with its working set in the free record instead of local memory)
+                rec.fin.move = move;
+                rec.fin.lpr = lpr;
+                rec.fin.cursor = cursor;
+                finish_gather_rest(ep, c, rec.fin);
+                Rng r2;
+                rng_resume(r2, ep, c, rec.fin);
+                finish_pre(ep, c, rec.fin, r2, -1, rec.pre);
+                rng_end(r2, ep, c);
+                finish_post(ep, c, rec.fin, rec.pre, -1, 0.0);
+                run_complete(ctl, queue, c, n_chains, n_iters);
+            }
+            __syncwarp();
+            RS_ADD(6, RS_CLK() - t0);
+            continue;
+        }
+        const long long t_fill = RS_CLK();
+        if (lane == 0) {
+            rec.c = c;
+            rec.move = move;
+            rec.lpr = lpr;
+            rec.cur = ed.cur;
+            rec.k_old = ed.k_old;
+            rec.k_new = ed.k_new;
+            rec.rm = ed.rm;
+            rec.ins = ed.ins;
+            rec.nx = ed.site[0];
+            rec.ny = ed.site[1];
+            rec.fin.move = move;
+            rec.fin.lpr = lpr;
+            rec.fin.cursor = cursor;
+            finish_gather_rest(ep, c, rec.fin);
+            Rng r2;
+            rng_resume(r2, ep, c, rec.fin);
+            finish_pre(ep, c, rec.fin, r2, t, rec.pre);
+            rng_end(r2, ep, c);
+        }
+        __syncwarp();  // (the lanes' stores of the proposed slot are ordered before the hand-over)
+        RS_ADD(2, RS_CLK() - t_fill);
+        if (lane == 0) hand_over(r);
+        ++produced;
+    }
+}
+
+template <typename IdxT, bool MULTI>
+__global__ void __launch_bounds__(CS_THREADS, 2) k_chain_run(const __grid_constant__ EngineParams ep, int t, long long c_first,
+                                                             int n_chains, int n_iters, int32_t *ctl) {
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    __shared__ RunShared sh;
+    const int tid = threadIdx.x;
+    const int n_words = 2 * ep.spec.targets[t].csc_tile_rays;
+    auto zero_planes = [&](int n_threads) {
+        uint4 *acc4 = reinterpret_cast<uint4 *>(cs_smem);
+        const int n4 = n_words >> 2;
+#pragma unroll 4
+        for (int i = tid; i < n4; i += n_threads) acc4[i] = make_uint4(0, 0, 0, 0);
+        unsigned *acc = reinterpret_cast<unsigned *>(cs_smem);
+        for (int q = (n4 << 2) + tid; q < n_words; q += n_threads) acc[q] = 0;
+    };
+    zero_planes(CS_THREADS);
+    if (tid == 0) {
+        for (int i = 0; i < CS_RECS; ++i) { mbar_init(&sh.ready[i], 1); mbar_init(&sh.empty[i], 1); }
+        sh.tail = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(ctl + run_ctl_queue_offset(ep.buf.n_chains));
+    if (tid >= CS_MAIN) {
+        run_proposer(ep, t, c_first, n_chains, n_iters, ctl, sh, (tid - CS_MAIN) >> 5);
+    } else {
+        unsigned *acc_lo = reinterpret_cast<unsigned *>(cs_smem);
+        unsigned *acc_hi = acc_lo + ep.spec.targets[t].csc_tile_rays;
+        // (the touched-ray list of the body: the `prep` area behind the planes and the four cell tables)
+        const unsigned short *touch = reinterpret_cast<const unsigned short *>(
+            cs_smem + (size_t)ep.spec.targets[t].csc_tile_rays * 8 + (size_t)ep.spec.spaces[ep.spec.targets[t].space].kmax * 32);
+        const long long t_start = RS_CLK();
+        int ended = 0;
+        for (int i = 0; ended < CS_PROPOSERS; ++i) {
+            const int pos = i % CS_RECS;
+            // (one thread watches the barrier of the FIFO position, the others sleep in the named barrier instead of polling)
+            const long long t0 = RS_CLK();
+            if (tid == 0) mbar_wait(&sh.ready[pos], (unsigned)(i / CS_RECS) & 1u);
+            cs_sync<true>();
+            const long long t1 = RS_CLK();
+            const int r = sh.fifo[pos];
+            ItemRec *rec = &sh.rec[r];
+            const long long c = rec->c;
+            if (c < 0) {  // a proposer's end mark
+                ++ended;
+                cs_sync<true>();  // (everyone has read the position before its next use)
+                continue;
+            }
+            const int planes = chain_step_body<IdxT, MULTI, true>(ep, t, c, nullptr, cs_smem, rec);
+            const long long t2 = RS_CLK();
+            // leave the planes zero for the next item: only the words this item touched, when the body listed them
+            if (planes >= 0) {
+                for (int q = tid; q < planes; q += CS_MAIN) {
+                    const int rr = (int)touch[q];
+                    acc_lo[rr] = 0;
+                    acc_hi[rr] = 0;
+                }
+            } else if (planes == -1) {
+                zero_planes(CS_MAIN);
+            }
+            cs_sync<true>();  // every worker is done with the record, the lists and its global stores
+            if (tid == 0) {
+                run_complete(ctl, queue, c, n_chains, n_iters);
+                mbar_arrive(&sh.empty[r]);
+                RS_ADD(8, t1 - t0);
+                RS_ADD(9, t2 - t1);
+                RS_ADD(10, RS_CLK() - t2);
+                RS_ADD(11, 1);
+            }
+        }
+        if (tid == 0) RS_ADD(12, RS_CLK() - t_start);
+    }
+    __syncthreads();
+    // the last block to finish leaves the control words zero for the next launch
+    if (tid == 0) {
+        __threadfence();
+        sh.last = atomicAdd(reinterpret_cast<unsigned *>(ctl + 1), 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh.last) {
+        __threadfence();
+        const long long n_ctl = run_ctl_queue_offset(ep.buf.n_chains) + 2 * (long long)ep.buf.n_chains;
+        for (long long i = tid; i < n_ctl; i += CS_THREADS) ctl[i] = 0;
+    }
+}
+
+long long chain_run_ctl_words(long long n_chains_engine) { return run_ctl_queue_offset(n_chains_engine) + 2 * n_chains_engine; }
+
+int launch_chain_run(const EngineParams &dev, long long c_first, long long c_end, long long n_iters, int t, int tile_rays,
+                     long long n_data, int K, int idx_bytes, int32_t *ctl, int n_blocks, cudaStream_t st) {
+    const long long n_chains = c_end - c_first;
+    if (n_chains < 1 || n_iters < 1) return 0;
+    if (n_chains * n_iters >= (1LL << 31) - 65536) return (int)cudaErrorInvalidValue;
+    const size_t smem = chain_step_smem(tile_rays, K, n_data);
+    const bool multi = n_data > tile_rays;
+    long long grid = n_blocks;
+    if (grid > n_chains) grid = n_chains;
+    auto launch = [&](auto kernel) -> int {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        kernel<<<dim3((unsigned)grid), dim3(CS_THREADS), smem, st>>>(dev, t, c_first, (int)n_chains, (int)n_iters, ctl);
+        return (int)cudaGetLastError();
+    };
+    if (idx_bytes == 1) return multi ? launch(k_chain_run<uint8_t, true>) : launch(k_chain_run<uint8_t, false>);
+    return multi ? launch(k_chain_run<uint16_t, true>) : launch(k_chain_run<uint16_t, false>);
 }
 
 #ifdef CS_TIMELINE
 extern "C" int bbb_debug_timeline(long long *host_out, int n_blocks) {
     return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 24 * (size_t)n_blocks);
+}
+extern "C" int bbb_debug_runstats(long long *host_out, int clear) {
+    int rc = (int)cudaMemcpyFromSymbol(host_out, g_runstats, sizeof(g_runstats));
+    if (rc == 0 && clear) {
+        void *p = nullptr;
+        cudaGetSymbolAddress(&p, g_runstats);
+        rc = (int)cudaMemset(p, 0, sizeof(g_runstats));
+    }
+    return rc;
 }
 extern "C" int bbb_debug_timeline_clear() {
     void *p = nullptr;

@@ -186,14 +186,21 @@ struct FinishIn {
     double sig[BBB_MAX_TARGETS][2], rho[BBB_MAX_TARGETS][2];  // [current, proposed]
 };
 
+// (the caller that drew the proposal itself passes what it already holds -- move, ratio, generator position -- so
+// that nothing here depends on a load)
+__device__ inline void finish_gather_rest(const EngineParams &ep, long long c, FinishIn &in);
 __device__ inline void finish_gather(const EngineParams &ep, long long c, FinishIn &in) {
+    const bbb_buffers &B = ep.buf;
+    in.move = B.move[c];
+    in.lpr = B.log_prob_ratio[c];
+    in.cursor = B.tape_cursor[c];
+    finish_gather_rest(ep, c, in);
+}
+__device__ inline void finish_gather_rest(const EngineParams &ep, long long c, FinishIn &in) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
-    in.move = B.move[c];
-    in.lpr = B.log_prob_ratio[c];
     in.iteration = B.iteration[c];
-    in.cursor = B.tape_cursor[c];
     in.temperature = ep.anneal.enabled ? annealing_temperature(ep.anneal, in.iteration) : B.temperature[c];
     const bool noise = (in.move == 4 * P.n_spaces);
     in.sel_s = noise ? 0 : (int)B.sel[in.move >> 2][c];

@@ -67,6 +67,11 @@ long long chain_local_tile_rays(long long n_data, int kmax, long long n_points);
 int launch_chain_step(const EngineParams &host_params, long long c_first, long long c_end, int target, int tile_rays,
                       long long n_data, int K, int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard,
                       cudaStream_t stream);
+long long chain_run_ctl_words(long long n_chains_engine);
+// the fused persistent run (k_chain_run): n_iters iterations of the chains [c_first, c_end) in one launch of n_blocks
+// blocks; ctl = chain_run_ctl_words(n_chains of the engine) int32 control words, zero before the launch (left zero by it)
+int launch_chain_run(const EngineParams &host_params, long long c_first, long long c_end, long long n_iters, int target,
+                     int tile_rays, long long n_data, int K, int idx_bytes, int32_t *ctl, int n_blocks, cudaStream_t stream);
 int launch_transpose_idx(const void *in, void *out, int idx_bytes, long long rows, long long cols, long long in_stride,
                          long long out_stride, cudaStream_t stream);
 int launch_residual_transpose(const double *dpred, double *res, long long R, long long C, const double *dobs,

@@ -27,6 +27,9 @@ struct Edit {
     double lpr;
     bool write;
     bool gave_up;  // a rejection-sampling loop hit MAX_RESAMPLE (the old value was kept)
+    // filled by propose_chain for callers that go on with the proposal in the same kernel: the move id, the slot of the
+    // current state and the cell counts of the current / proposed state (space moves only)
+    int move, cur, k_old, k_new;
 };
 
 // Where a proposal reads the cells of the CURRENT state from: the [..][K][C] arrays in global memory.  (An accessor
@@ -91,28 +94,60 @@ __device__ inline int nearest_2d(const Cells &cells, int k, int skip, double px,
 // ---- outer choice (_markov_chain.py:208-210), then the inner choice of ParamSpacePerturbation
 // (.perturb_param_space_state, perturbations/_param_space.py:79-92).  Returns the move id: 4 * space + kind, or
 // 4 * n_spaces for the noise perturbation.
+// (the weights are walked twice -- total, then cumulative sums in the same order -- instead of being copied into a
+// local array first: dynamically indexed local arrays live in local memory, an L2 round trip per access when the L1 is
+// as small as the chain kernels leave it.  Same draws and same sums as R::choice: one uniform when there are at least
+// two candidates, bisect_right(cumsum(w), u * total) clipped to the last.)
 template <class R>
 __device__ inline int choose_move(const bbb_problem_spec &P, R &rng) {
-    double w[BBB_MAX_SPACES + 1];
-    int n_outer = 0;
-    for (int s = 0; s < P.n_spaces; ++s) {
+    auto outer_w = [&](int s) {
         const bbb_space_spec &S = P.spaces[s];
-        w[n_outer++] = S.w_outer > 0.0 ? S.w_outer : S.w_birth + S.w_death + S.w_values + S.w_sites;
-    }
+        return S.w_outer > 0.0 ? S.w_outer : S.w_birth + S.w_death + S.w_values + S.w_sites;
+    };
     bool any_hier = false;
     for (int t = 0; t < P.n_targets; ++t) any_hier |= (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL);
-    if (any_hier && P.w_noise != 0.0) w[n_outer++] = P.w_noise > 0.0 ? P.w_noise : 1.0;
-    const int i_outer = rng.choice(w, n_outer);
+    const bool with_noise = any_hier && P.w_noise != 0.0;
+    const double w_noise = P.w_noise > 0.0 ? P.w_noise : 1.0;
+    const int n_outer = P.n_spaces + (with_noise ? 1 : 0);
+    int i_outer = 0;
+    if (n_outer > 1) {
+        double tot = 0.0;
+        for (int s = 0; s < P.n_spaces; ++s) tot += outer_w(s);
+        if (with_noise) tot += w_noise;
+        const double x = rng.u() * tot;
+        double cum = 0.0;
+        for (; i_outer < n_outer - 1; ++i_outer) {
+            cum += i_outer < P.n_spaces ? outer_w(i_outer) : w_noise;
+            if (x < cum) break;
+        }
+    }
     if (i_outer >= P.n_spaces) return 4 * P.n_spaces;
     const bbb_space_spec &S = P.spaces[i_outer];
-    double wi[4];
-    int kinds[4];
-    int n_inner = 0;
-    if (S.w_birth > 0) { wi[n_inner] = S.w_birth; kinds[n_inner++] = BBB_MOVE_BIRTH; }
-    if (S.w_death > 0) { wi[n_inner] = S.w_death; kinds[n_inner++] = BBB_MOVE_DEATH; }
-    if (S.w_values > 0) { wi[n_inner] = S.w_values; kinds[n_inner++] = BBB_MOVE_VALUES; }
-    if (S.w_sites > 0) { wi[n_inner] = S.w_sites; kinds[n_inner++] = BBB_MOVE_SITES; }
-    return 4 * i_outer + kinds[rng.choice(wi, n_inner)];
+    // candidates in the order birth, death, values, sites; those with a zero weight are not candidates
+    const double wk[4] = {S.w_birth > 0 ? S.w_birth : 0.0, S.w_death > 0 ? S.w_death : 0.0, S.w_values > 0 ? S.w_values : 0.0,
+                          S.w_sites > 0 ? S.w_sites : 0.0};
+    const int n_inner = (wk[0] > 0 ? 1 : 0) + (wk[1] > 0 ? 1 : 0) + (wk[2] > 0 ? 1 : 0) + (wk[3] > 0 ? 1 : 0);
+    int last = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (wk[q] > 0) last = q;
+    if (n_inner == 1) return 4 * i_outer + last;
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (wk[q] > 0) tot += wk[q];
+    const double x = rng.u() * tot;
+    double cum = 0.0;
+    int kind = last;
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (wk[q] > 0 && q != last && !found) {
+            cum += wk[q];
+            if (x < cum) { kind = q; found = true; }
+        }
+    }
+    return 4 * i_outer + kind;
 }
 
 // ---- P7 NoisePerturbation.perturb (perturbations/_data_noise.py:21-77) of one hierarchical target: new std (and
@@ -173,18 +208,26 @@ __device__ inline void propose_space_move(const bbb_space_spec &S, const Cells &
         const int idx = rng.randint(0, k - 1);
         e.rm = idx;
         for (int p = 0; p < S.n_params; ++p) e.vals[p] = cells.value(p, idx);
+        // (constant trip counts: the two coordinates stay in registers)
         double old_site[2] = {0.0, 0.0};
-        for (int d = 0; d < S.ndim; ++d) old_site[d] = e.site[d] = cells.site(d, idx);
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+            if (d < S.ndim) old_site[d] = e.site[d] = cells.site(d, idx);
         e.gave_up = true;
         for (int it = 0; it < MAX_RESAMPLE; ++it) {
-            double cand[2];
+            double cand[2] = {0.0, 0.0};
             bool ok = true;
-            for (int d = 0; d < S.ndim; ++d) {
-                cand[d] = old_site[d] + rng.normal(0.0, S.site_std[d]);
-                ok &= (cand[d] >= S.vmin[d]) && (cand[d] <= S.vmax[d]);
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                if (d < S.ndim) {
+                    cand[d] = old_site[d] + rng.normal(0.0, S.site_std[d]);
+                    ok &= (cand[d] >= S.vmin[d]) && (cand[d] <= S.vmax[d]);
+                }
             }
             if (ok) {
-                for (int d = 0; d < S.ndim; ++d) e.site[d] = cand[d];
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+                    if (d < S.ndim) e.site[d] = cand[d];
                 e.gave_up = false;
                 break;
             }
@@ -248,7 +291,9 @@ __device__ inline void propose_space_move(const bbb_space_spec &S, const Cells &
             if (S.kind != BBB_SPACE_PLAIN && S.birth_from == BBB_BIRTH_FROM_NEIGHBOUR) {
                 // _log_prob_death_parameters (discretization/_discretization.py:435-465)
                 double pos[2] = {0.0, 0.0};
-                for (int d = 0; d < S.ndim; ++d) pos[d] = cells.site(d, e.rm);
+#pragma unroll
+                for (int d = 0; d < 2; ++d)
+                    if (d < S.ndim) pos[d] = cells.site(d, e.rm);
                 int i_near = (S.ndim == 1) ? nearest_1d(cells, k, e.rm, pos[0])
                                            : nearest_2d(cells, k, e.rm, pos[0], pos[1], rng.coop);
                 i_near += (i_near >= e.rm) ? 1 : 0;  // back to indices of the current state
@@ -333,11 +378,15 @@ __device__ inline int write_proposed_slot(const bbb_buffers &B, const bbb_space_
     return k_new;
 }
 
+// `e`: where the edit script is built.  A thread that proposes for its own chain passes a local; the warp-cooperative
+// proposers of the fused chain kernel (all lanes build the same script) pass one in shared memory, which keeps the
+// script's arrays out of local memory.
 template <class R>
 __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, R &rng,
-                                     bool apply_now) {
+                                     bool apply_now, Edit &e) {
     const int move = choose_move(P, rng);
     const bool writer = !rng.coop || (threadIdx.x & 31) == 0;  // cooperative mode: lane 0 publishes the proposal
+    e.move = move;
 
     if (move == 4 * P.n_spaces) {
         for (int t = 0; t < P.n_targets; ++t) {
@@ -355,6 +404,7 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
             B.edit[B.n_chains + c] = -1;
             B.log_prob_ratio[c] = 0.0;
         }
+        e.lpr = 0.0;
         return;
     }
 
@@ -362,7 +412,6 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
     const bbb_space_spec &S = P.spaces[s];
     const int cur = B.sel[s][c];
     const int k = k_ref(B, s, cur, c);
-    Edit e;
     propose_space_move(S, GlobalCells{B, S, s, cur, c}, k, inner, rng, e);
 
     const int k_new = write_proposed_slot(B, S, s, cur, k, c, e, rng.coop, apply_now);
@@ -370,7 +419,9 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         for (int d = 0; d < S.ndim; ++d) B.edit_site[(long long)d * B.n_chains + c] = e.site[d];
         for (int p = 0; p < S.n_params; ++p) B.edit_vals[(long long)p * B.n_chains + c] = e.vals[p];
     }
-    (void)k_new;
+    e.cur = cur;
+    e.k_old = k;
+    e.k_new = k_new;
     if (writer && e.gave_up && B.n_exceptions != nullptr) B.n_exceptions[B.n_chains + c] += 1;
     if (writer) {
         B.move[c] = 4 * s + inner;
@@ -378,6 +429,12 @@ __device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffer
         B.edit[B.n_chains + c] = e.ins;
         B.log_prob_ratio[c] = e.lpr;
     }
+}
+template <class R>
+__device__ inline void propose_chain(const bbb_problem_spec &P, const bbb_buffers &B, long long c, R &rng,
+                                     bool apply_now) {
+    Edit e;
+    propose_chain(P, B, c, rng, apply_now, e);
 }
 
 }  // namespace bbb
