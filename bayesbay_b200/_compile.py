@@ -121,8 +121,9 @@ def compile_target(tgt, fwd, space_index: dict, spaces: list) -> dict:
             spec["cov_inv"] = float(cov)
         else:
             cov = np.asarray(cov, dtype=np.float64)
-            if cov.ndim != 1 or cov.size != dobs.size:
-                raise DeviceUnsupported(f"target {tgt.name!r}: only scalar or per-datum inverse covariances are on the device")
+            if not ((cov.ndim == 1 and cov.size == dobs.size) or (cov.ndim == 2 and cov.shape == (dobs.size, dobs.size))):
+                raise ValueError(f"target {tgt.name!r}: covariance_mat_inv must be a scalar, a vector [{dobs.size}] or a "
+                                 f"matrix [{dobs.size}][{dobs.size}], got shape {cov.shape}")
             spec["cov_inv"] = cov
     kind = getattr(fwd, "kind", None)
     if kind not in ("ray2d", "lookup1d", "linear", "polynomial"):

@@ -176,10 +176,14 @@ class Engine:
                 t.cov_scalar = float(tg["cov_inv"])
             else:
                 cov = np.asarray(tg["cov_inv"], dtype=np.float64)
-                if cov.ndim != 1 or cov.size != t.n_data:
-                    raise ValueError("only scalar or per-datum (1-D) inverse covariances run on the device")
-                t.cov_kind = L.COV_VECTOR
-                t.cov_vec = self._const(cov, np.float64).data_ptr()
+                if cov.ndim == 2 and cov.shape == (t.n_data, t.n_data):
+                    # `covariance_mat_inv @ vector` (likelihood/_target.py:150-151): row-major [n][n]
+                    t.cov_kind = L.COV_MATRIX
+                elif cov.ndim == 1 and cov.size == t.n_data:
+                    t.cov_kind = L.COV_VECTOR
+                else:
+                    raise ValueError("an inverse covariance is a scalar, a per-datum vector [n] or a matrix [n][n]")
+                t.cov_vec = self._const(np.ascontiguousarray(cov), np.float64).data_ptr()
             f = tg["forward"]
             t.fwd_kind = _FWD_KIND[f["kind"]]
             t.space = f["space"]
@@ -191,7 +195,7 @@ class Engine:
                 # the device sees the query points in Morton order (internal: current_cell_idx() undoes it)
                 K = spec["spaces"][f["space"]]["kmax"]
                 tile = int(self.lib.bbb_chain_local_tile_rays(t.n_data, K, t.n_points))
-                local = tile > 0 and not tg.get("correlated")
+                local = tile > 0 and not tg.get("correlated") and not (not tg["hierarchical"] and np.ndim(tg["cov_inv"]) == 2)
                 perm = morton_order(pts) if local else np.arange(t.n_points)
                 inv = np.empty_like(perm)
                 inv[perm] = np.arange(t.n_points)
@@ -267,8 +271,9 @@ class Engine:
             self.corr.append(z((2, Cn), f64) if corr_t else None)
             # chain-local step: one ray target whose CSC copy was built (see _build_spec)
             local_t = tg["forward"]["kind"] == "ray2d" and n_ray == 1 and self._cspec.targets[i].csc_tile_rays > 0
+            matrix_t = (not tg["hierarchical"]) and np.ndim(tg["cov_inv"]) == 2  # residuals kept for res^T M res
             self.dpred_scratch.append(z((int(np.asarray(tg["dobs"]).size), Cn), f64)
-                                      if (corr_t or local_t) and tg["forward"]["kind"] == "ray2d" else None)
+                                      if ((corr_t or local_t) and tg["forward"]["kind"] == "ray2d") or matrix_t else None)
             b.corr[i], b.dpred_scratch[i] = _ptr(self.corr[i]), _ptr(self.dpred_scratch[i])
             if local_t:
                 G = int(np.asarray(tg["forward"]["points"]).shape[0])
@@ -587,6 +592,55 @@ class Engine:
                                                 C.c_void_p(host_out.data_ptr()), _ptr(stage), _ptr(out), self._stream))
         self._steps_since_sync += 1
         return [int(v) for v in kb_out]
+
+    # ---- ragged hosted image: only the cells in use travel (include/bbb200.h)
+    def hosted_ragged_words(self) -> int:
+        """Capacity of a ragged hosted image in 8-byte words (all four buffers of :meth:`step_hosted_ragged`)."""
+        n = int(self.lib.bbb_engine_hosted_ragged_bytes(self._handle))
+        if n < 0:
+            raise RuntimeError("bbb_engine_hosted_ragged_bytes failed")
+        return n // 8
+
+    def pack_states_ragged(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Current states of all chains as a ragged hosted image (device buffer of int64 words; words behind a part's
+        content are left as they are)."""
+        if out is None:
+            out = torch.zeros((self.hosted_ragged_words(),), dtype=torch.int64, device=self.device)
+        L.check(self.lib.bbb_engine_pack_states_ragged(self._handle, _ptr(out), self._stream))
+        return out
+
+    def ragged_parts(self, image: torch.Tensor):
+        """The content of a ragged hosted image (host or device tensor of int64 words): per part ``(c0, c1, words)``
+        with ``words`` the slice the part's header and cells occupy."""
+        first = self.hosted_parts()
+        stride = self.hosted_ragged_words() // (len(first) - 1)
+        n_noise = sum((2 if tg.get("correlated") else 1) for tg in self.spec["targets"] if tg["hierarchical"])
+        hr = len(self.spec["spaces"]) + n_noise + 2
+        out = []
+        for h, (c0, c1) in enumerate(zip(first[:-1], first[1:])):
+            n_c = c1 - c0
+            words = hr * n_c
+            for s, sp in enumerate(self.spec["spaces"]):
+                k = image[stride * h + s * n_c: stride * h + (s + 1) * n_c]
+                words += int(k.sum().item()) * (sp["ndim"] + len(sp["params"]))
+            out.append((c0, c1, image[stride * h: stride * h + words]))
+        return out
+
+    def step_hosted_ragged(self, host_in: torch.Tensor, host_out: torch.Tensor, stage: torch.Tensor, out: torch.Tensor):
+        """Enqueue ONE iteration on the chains of the pinned ragged hosted image ``host_in``; the new states arrive in
+        ``host_out`` once :meth:`step_hosted_wait` returned.  Returns the bytes copied (host -> device, device -> host)."""
+        if not (host_in.is_pinned() and host_out.is_pinned()):
+            raise ValueError("hosted images must live in pinned host memory")
+        need = self.hosted_ragged_words()
+        if min(host_in.numel(), host_out.numel(), stage.numel(), out.numel()) < need:
+            raise ValueError("hosted image buffers too small")
+        if self._steps_since_sync >= self.K_BOUND_RESYNC_LOCAL:
+            self.sync_k_bound()
+        up, down = C.c_int64(0), C.c_int64(0)
+        L.check(self.lib.bbb_engine_step_hosted_ragged(self._handle, C.c_void_p(host_in.data_ptr()), C.c_void_p(host_out.data_ptr()),
+                                                       _ptr(stage), _ptr(out), C.byref(up), C.byref(down), self._stream))
+        self._steps_since_sync += 1
+        return int(up.value), int(down.value)
 
     def step_hosted_wait(self) -> int:
         """Wait for the hosted step; returns the number of parts whose caches had to be re-derived (0: fast path)."""

@@ -22,7 +22,7 @@ PRIOR_UNIFORM, PRIOR_GAUSSIAN, PRIOR_LAPLACE = 0, 1, 2
 BIRTH_FROM_PRIOR, BIRTH_FROM_NEIGHBOUR = 0, 1
 FWD_RAY2D, FWD_LOOKUP1D, FWD_LINEAR, FWD_POLYNOMIAL = 0, 1, 2, 3
 TRANSFORM_IDENTITY, TRANSFORM_RECIPROCAL = 0, 1
-COV_HIERARCHICAL, COV_SCALAR, COV_VECTOR = 0, 1, 2
+COV_HIERARCHICAL, COV_SCALAR, COV_VECTOR, COV_MATRIX = 0, 1, 2, 3
 MOVE_BIRTH, MOVE_DEATH, MOVE_VALUES, MOVE_SITES = 0, 1, 2, 3
 
 _vp = C.c_void_p
@@ -123,6 +123,9 @@ SYMBOLS = {
     "bbb_engine_hosted_parts": (C.c_int, [_vp, C.POINTER(_i64)]),
     "bbb_engine_step_hosted": (C.c_int, [_vp, C.POINTER(_i32), _vp, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
     "bbb_engine_step_hosted_wait": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
+    "bbb_engine_hosted_ragged_bytes": (_i64, [_vp]),
+    "bbb_engine_pack_states_ragged": (C.c_int, [_vp, _vp, _vp]),
+    "bbb_engine_step_hosted_ragged": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "bbb_engine_dpred": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "bbb_engine_misfit_logdet": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bbb_engine_swap_rows": (C.c_int, [_vp, _vp, _vp]),

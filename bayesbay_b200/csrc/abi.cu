@@ -73,16 +73,32 @@ struct bbb_engine {
     // hosted step (bbb_engine_step_hosted / _wait): per-part "uploaded states differ" words on the device and their
     // pinned host copy, and what the pending call needs should a part have to be redone
     int32_t *hosted_flag_dev, *hosted_flag_host;
+    // shape of one hosted call: the wire format, and where each part's image lives in the four buffers (word offsets)
+    // and how many words of it travel each way
+    struct HostedShape {
+        int ragged;  // 0: rows of kb cells per chain (bbb_engine_step_hosted), 1: only the cells in use (.._ragged)
+        int32_t kb_in[BBB_MAX_SPACES], kb_out[BBB_MAX_SPACES];
+        long long in_off[4], in_words[4], out_off[4], out_words[4];
+        bool same(const HostedShape &o, int n_spaces, int n_parts) const {
+            if (ragged != o.ragged) return false;
+            for (int s = 0; s < n_spaces && !ragged; ++s)
+                if (kb_in[s] != o.kb_in[s] || kb_out[s] != o.kb_out[s]) return false;
+            for (int h = 0; h < n_parts; ++h)
+                if (in_off[h] != o.in_off[h] || in_words[h] != o.in_words[h] || out_off[h] != o.out_off[h] || out_words[h] != o.out_words[h])
+                    return false;
+            return true;
+        }
+    };
     struct {
         bool pending;
-        int32_t kb_in[BBB_MAX_SPACES], kb_out[BBB_MAX_SPACES];
+        HostedShape shape;
         void *host_out, *dev_stage, *dev_out;
     } hosted;
     // the hosted step is replayed from CUDA graphs (one launch instead of ~40 driver calls per iteration): captured on
     // `cap_stream` the first time a combination of image sizes, buffers and block-order parities is seen
     struct HostedGraph {
         bool used;
-        int32_t kb_in[BBB_MAX_SPACES], kb_out[BBB_MAX_SPACES];
+        HostedShape shape;
         const void *host_in;
         void *host_out, *dev_stage, *dev_out;
         int parity;
@@ -174,7 +190,7 @@ static int validate_spec(const bbb_problem_spec *P) {
                 return fail(BBB_ERR_INVALID, "target %d: noise correlation range (needs 0 <= min <= max, at least 3 data)", t);
         } else if (T.correlated) {
             return fail(BBB_ERR_INVALID, "target %d: correlated noise needs a hierarchical target", t);
-        } else if (T.cov_kind == BBB_COV_VECTOR) {
+        } else if (T.cov_kind == BBB_COV_VECTOR || T.cov_kind == BBB_COV_MATRIX) {
             if (T.cov_vec == nullptr) return fail(BBB_ERR_INVALID, "target %d: cov_vec is NULL", t);
         } else if (T.cov_kind != BBB_COV_SCALAR) {
             return fail(BBB_ERR_INVALID, "target %d: cov_kind", t);
@@ -284,7 +300,8 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
         if (!b->phi[t]) return fail(BBB_ERR_SHAPE, "target %d: phi buffer missing", t);
         if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL && !b->sigma[t]) return fail(BBB_ERR_SHAPE, "target %d: sigma buffer missing", t);
         if (P.targets[t].correlated && !b->corr[t]) return fail(BBB_ERR_SHAPE, "target %d: corr buffer missing", t);
-        if (P.targets[t].correlated && P.targets[t].fwd_kind == BBB_FWD_RAY2D && !b->dpred_scratch[t])
+        if (((P.targets[t].correlated && P.targets[t].fwd_kind == BBB_FWD_RAY2D) || P.targets[t].cov_kind == BBB_COV_MATRIX) &&
+            !b->dpred_scratch[t])
             return fail(BBB_ERR_SHAPE, "target %d: dpred_scratch buffer missing", t);
         if (P.targets[t].fwd_kind == BBB_FWD_RAY2D &&
             (!b->cell_idx[t] || !b->idx_sel[t] || !b->partial[t] || !b->rescan_list[t] || !b->rescan_count[t]))
@@ -313,7 +330,7 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
         int n_ray = 0, rt = -1;
         for (int t = 0; t < P.n_targets; ++t)
             if (P.targets[t].fwd_kind == BBB_FWD_RAY2D) { ++n_ray; rt = t; }
-        if (n_ray == 1 && !e->full_forward && !e->brute_force && P.targets[rt].csc_tile_rays > 0 && !P.targets[rt].correlated) {
+        if (n_ray == 1 && !e->full_forward && !e->brute_force && P.targets[rt].csc_tile_rays > 0 && !reduces_dpred(P.targets[rt])) {
             const bool have = b->idx_cm[rt] && b->res[rt] && b->change_list[rt] && b->dpred_scratch[rt];
             if (!have && (b->idx_cm[rt] || b->res[rt] || b->change_list[rt]))
                 return fail(BBB_ERR_SHAPE, "target %d: the chain-local step needs idx_cm, res, change_list and dpred_scratch", rt);
@@ -443,7 +460,7 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
     a.n_spaces = P.n_spaces;
     a.space = T.space;
     a.dpred = dpred;
-    if (T.correlated && write_partial && dpred == nullptr) a.dpred = B.dpred_scratch[t];  // reduced by k_corr_sums
+    if (reduces_dpred(T) && write_partial && dpred == nullptr) a.dpred = B.dpred_scratch[t];  // reduced by k_corr_sums
     a.partial = write_partial ? B.partial[t] : nullptr;
     // the value table holds k_rows cells per chain; a tighter bound allows more chains per lane
     a.k_rows = proposal ? (e->k_bound[T.space] + 1 < S.kmax ? e->k_bound[T.space] + 1 : S.kmax) : e->k_bound[T.space];
@@ -459,7 +476,7 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
         if (rc != 0) return rc;
     }
     int rc = launch_ray_spmm(a, st);
-    if (rc == 0 && T.correlated && write_partial) rc = launch_corr_sums(e->dev, a.C, t, proposal ? 1 : 0, st);
+    if (rc == 0 && reduces_dpred(T) && write_partial) rc = launch_corr_sums(e->dev, a.C, t, proposal ? 1 : 0, st);
     return rc;
 }
 
@@ -860,15 +877,20 @@ static void trace_mark(int h, int i, cudaStream_t s) {
         int _e = (int)(expr);          \
         if (_e != 0) return _e;        \
     } while (0)
-static int hosted_enqueue(bbb_engine *e, const int32_t *kb_in, const void *host_in, const int32_t *kb_out, void *host_out,
+// image kernels of either wire format (mode: 0 pack, 1 compare, 2 unpack)
+static int hosted_image(bbb_engine *e, const bbb_engine::HostedShape &sh, int mode, bool out_side, void *image, int32_t *differ,
+                        long long c0, long long c1, cudaStream_t st) {
+    if (sh.ragged) return launch_state_image_ragged(e->host, mode, image, differ, c0, c1, st);
+    return launch_state_image(e->host, mode, out_side ? sh.kb_out : sh.kb_in, image, differ, c0, c1, st);
+}
+
+static int hosted_enqueue(bbb_engine *e, const bbb_engine::HostedShape &sh, const void *host_in, void *host_out,
                           void *dev_stage, void *dev_out, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
     const long long C = e->host.buf.n_chains, part = hosted_part_chains(e);
     const int NP = e->hosted_np;
-    const long long rows_in = state_image_rows(e->host, kb_in);
     const long long *in_words = reinterpret_cast<const long long *>(host_in);
-    const long long rows_out = state_image_rows(e->host, kb_out);
     ENQ(cudaMemsetAsync(e->hosted_flag_dev, 0, 4 * sizeof(int32_t), st));
     if (g_trace_on) cudaEventRecord(g_trace_fork, st);
     ENQ(cudaEventRecord(e->ev_hfork, st));
@@ -878,8 +900,8 @@ static int hosted_enqueue(bbb_engine *e, const int32_t *kb_in, const void *host_
     for (int h = 0; h < NP; ++h) {
         const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
         if (c0 >= c1) continue;
-        const long long in_off = rows_in * c0;
-        ENQ(cudaMemcpyAsync(stage + in_off, in_words + in_off, (size_t)(rows_in * (c1 - c0)) * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        const long long in_off = sh.in_off[h];
+        ENQ(cudaMemcpyAsync(stage + in_off, in_words + in_off, (size_t)sh.in_words[h] * 8, cudaMemcpyHostToDevice, e->copy_stream));
         ENQ(cudaEventRecord(e->ev_h2d[h], e->copy_stream));
     }
     // Counter-based generators make the proposal a pure function of (resident state, iteration, chain): it is drawn
@@ -891,22 +913,22 @@ static int hosted_enqueue(bbb_engine *e, const int32_t *kb_in, const void *host_
         const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
         if (c0 >= c1) continue;
         cudaStream_t hs = e->hosted_stream[h];
-        const long long n_c = c1 - c0, in_off = rows_in * c0, out_off = rows_out * c0;
+        const long long in_off = sh.in_off[h], out_off = sh.out_off[h];
         ENQ(cudaStreamWaitEvent(hs, e->ev_hfork, 0));
         trace_mark(h, 0, hs);
         if (speculative) ENQ(launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, nullptr, hs));
         trace_mark(h, 1, hs);
         ENQ(cudaStreamWaitEvent(hs, e->ev_h2d[h], 0));
         trace_mark(h, 2, hs);
-        ENQ(launch_state_image(e->host, 1, kb_in, stage + in_off, e->hosted_flag_dev + h, c0, c1, hs));
+        ENQ(hosted_image(e, sh, 1, false, stage + in_off, e->hosted_flag_dev + h, c0, c1, hs));
         if (!speculative) ENQ(launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, e->hosted_flag_dev + h, hs));
         trace_mark(h, 3, hs);
         ENQ(launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax, idx_bytes_of(P, e->ray_t),
                               e->order_parity[h] * 4 + h, !speculative && e->dependent_launch >= 1, e->hosted_flag_dev + h, hs));
         trace_mark(h, 4, hs);
-        ENQ(launch_state_image(e->host, 0, kb_out, out + out_off, nullptr, c0, c1, hs));
+        ENQ(hosted_image(e, sh, 0, true, out + out_off, nullptr, c0, c1, hs));
         trace_mark(h, 5, hs);
-        ENQ(cudaMemcpyAsync(reinterpret_cast<unsigned long long *>(host_out) + out_off, out + out_off, (size_t)(rows_out * n_c) * 8,
+        ENQ(cudaMemcpyAsync(reinterpret_cast<unsigned long long *>(host_out) + out_off, out + out_off, (size_t)sh.out_words[h] * 8,
                             cudaMemcpyDeviceToHost, hs));
         trace_mark(h, 6, hs);
         ENQ(cudaEventRecord(e->ev_hjoin[h], hs));
@@ -917,6 +939,98 @@ static int hosted_enqueue(bbb_engine *e, const int32_t *kb_in, const void *host_
 }
 #undef ENQ
 
+// First-use resources of the hosted step.
+static int hosted_init(bbb_engine *e) {
+    if (e->hosted_flag_dev != nullptr) return BBB_OK;
+    CU(cudaMalloc(&e->hosted_flag_dev, 4 * sizeof(int32_t)));
+    CU(cudaHostAlloc(&e->hosted_flag_host, 4 * sizeof(int32_t), cudaHostAllocDefault));
+    CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : e->ev_h2d) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : e->ev_hjoin) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_hfork, cudaEventDisableTiming));
+    for (auto &hs : e->hosted_stream) CU(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
+    const char *hg = getenv("BBB_HOSTED_GRAPH");
+    e->hosted_graphs = (hg != nullptr && atoi(hg) == 0) ? 0 : 1;
+    if (const char *tr = getenv("BBB_HOSTED_TRACE")) {
+        if (atoi(tr) != 0 && !g_trace_init) {
+            for (auto &row : g_trace_ev)
+                for (auto &ev : row) cudaEventCreate(&ev);
+            cudaEventCreate(&g_trace_fork);
+            g_trace_init = g_trace_on = true;
+        }
+        if (g_trace_on) e->hosted_graphs = 0;
+    }
+    return BBB_OK;
+}
+
+// Put one hosted call of shape `sh` on the device (replayed from a captured graph when there is one) and do the
+// engine's host-side bookkeeping of an iteration.
+static int hosted_launch(bbb_engine *e, const bbb_engine::HostedShape &sh, const void *host_in, void *host_out, void *dev_stage,
+                         void *dev_out, cudaStream_t st) {
+    const bbb_problem_spec &P = e->host.spec;
+    const int NP = e->hosted_np;
+    if (int rc = hosted_init(e)) return rc;
+    int parity = 0;
+    for (int h = 0; h < NP; ++h) parity |= e->order_parity[h] << h;
+    bool launched = false;
+    if (e->hosted_graphs) {
+        bbb_engine::HostedGraph *g = nullptr;
+        for (auto &c : e->hosted_graph) {
+            if (!c.used || c.host_in != host_in || c.host_out != host_out || c.dev_stage != dev_stage || c.dev_out != dev_out ||
+                c.parity != parity)
+                continue;
+            if (c.shape.same(sh, P.n_spaces, NP)) { g = &c; break; }
+        }
+        if (g == nullptr) {
+            bbb_engine::HostedGraph &c = e->hosted_graph[e->hosted_graph_next];
+            e->hosted_graph_next = (e->hosted_graph_next + 1) % 16;
+            if (c.used) {
+                cudaGraphExecDestroy(c.exec);
+                cudaGraphDestroy(c.graph);
+                c.used = false;
+            }
+            int rc = (int)cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed);
+            if (rc == 0) {
+                rc = hosted_enqueue(e, sh, host_in, host_out, dev_stage, dev_out, e->cap_stream);
+                cudaGraph_t graph = nullptr;
+                const int rc_end = (int)cudaStreamEndCapture(e->cap_stream, &graph);
+                if (rc == 0) rc = rc_end;
+                if (rc == 0) rc = (int)cudaGraphInstantiate(&c.exec, graph, 0);
+                if (rc == 0) {
+                    c.graph = graph;
+                    c.used = true;
+                    c.shape = sh;
+                    c.host_in = host_in; c.host_out = host_out; c.dev_stage = dev_stage; c.dev_out = dev_out; c.parity = parity;
+                    g = &c;
+                } else if (graph != nullptr) {
+                    cudaGraphDestroy(graph);
+                }
+            }
+            if (g == nullptr) {  // capture is not available here: enqueue every call from now on
+                (void)cudaGetLastError();
+                e->hosted_graphs = 0;
+            }
+        }
+        if (g != nullptr) {
+            CU(cudaGraphLaunch(g->exec, st));
+            launched = true;
+        }
+    }
+    if (!launched) CU(hosted_enqueue(e, sh, host_in, host_out, dev_stage, dev_out, st));
+    for (int h = 0; h < NP; ++h) e->order_parity[h] ^= 1;
+    e->order_pending[0] = false;
+    bump_k_bound(e, 1);
+    ++e->steps_since_resync;
+    if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) CU(chain_local_from_scratch(e, false, st));
+    e->hosted.pending = true;
+    e->hosted.shape = sh;
+    e->hosted.host_out = host_out;
+    e->hosted.dev_stage = dev_stage;
+    e->hosted.dev_out = dev_out;
+    return BBB_OK;
+}
+
 int bbb_engine_step_hosted(bbb_engine *e, const int32_t *kb_in, const void *host_in, int32_t *kb_out, void *host_out,
                            void *dev_stage, void *dev_out, void *stream) {
     NEED_BOUND(e);
@@ -925,7 +1039,6 @@ int bbb_engine_step_hosted(bbb_engine *e, const int32_t *kb_in, const void *host
     if (int rc = check_kb(e, kb_in)) return rc;
     if (!host_in || !host_out || !kb_out || !dev_stage || !dev_out) return fail(BBB_ERR_INVALID, "NULL argument");
     if (host_in == host_out || dev_stage == dev_out) return fail(BBB_ERR_INVALID, "in and out images must be different buffers");
-    cudaStream_t st = (cudaStream_t)stream;
     const bbb_problem_spec &P = e->host.spec;
     const long long C = e->host.buf.n_chains, part = hosted_part_chains(e);
     const int NP = e->hosted_np;
@@ -945,87 +1058,96 @@ int bbb_engine_step_hosted(bbb_engine *e, const int32_t *kb_in, const void *host
         const long long kb = P.spaces[s].trans_d ? ((kmax_seen + 1 + 7) & ~7LL) : kmax_seen;
         kb_out[s] = (int32_t)(kb < P.spaces[s].kmax ? kb : P.spaces[s].kmax);
     }
-    if (e->hosted_flag_dev == nullptr) {
-        CU(cudaMalloc(&e->hosted_flag_dev, 4 * sizeof(int32_t)));
-        CU(cudaHostAlloc(&e->hosted_flag_host, 4 * sizeof(int32_t), cudaHostAllocDefault));
-        CU(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        for (auto &ev : e->ev_h2d) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        for (auto &ev : e->ev_hjoin) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&e->ev_hfork, cudaEventDisableTiming));
-        for (auto &hs : e->hosted_stream) CU(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
-        const char *hg = getenv("BBB_HOSTED_GRAPH");
-        e->hosted_graphs = (hg != nullptr && atoi(hg) == 0) ? 0 : 1;
-        if (const char *tr = getenv("BBB_HOSTED_TRACE")) {
-            if (atoi(tr) != 0 && !g_trace_init) {
-                for (auto &row : g_trace_ev)
-                    for (auto &ev : row) cudaEventCreate(&ev);
-                cudaEventCreate(&g_trace_fork);
-                g_trace_init = g_trace_on = true;
-            }
-            if (g_trace_on) e->hosted_graphs = 0;
-        }
+    bbb_engine::HostedShape sh{};
+    sh.ragged = 0;
+    for (int s = 0; s < P.n_spaces; ++s) { sh.kb_in[s] = kb_in[s]; sh.kb_out[s] = kb_out[s]; }
+    const long long rows_out = state_image_rows(e->host, kb_out);
+    for (int h = 0; h < NP; ++h) {
+        const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
+        sh.in_off[h] = rows_in * c0;
+        sh.in_words[h] = rows_in * (c1 - c0);
+        sh.out_off[h] = rows_out * c0;
+        sh.out_words[h] = rows_out * (c1 - c0);
     }
-    int parity = 0;
-    for (int h = 0; h < NP; ++h) parity |= e->order_parity[h] << h;
-    bool launched = false;
-    if (e->hosted_graphs) {
-        bbb_engine::HostedGraph *g = nullptr;
-        for (auto &c : e->hosted_graph) {
-            if (!c.used || c.host_in != host_in || c.host_out != host_out || c.dev_stage != dev_stage || c.dev_out != dev_out ||
-                c.parity != parity)
-                continue;
-            bool same = true;
-            for (int s = 0; s < P.n_spaces; ++s) same = same && c.kb_in[s] == kb_in[s] && c.kb_out[s] == kb_out[s];
-            if (same) { g = &c; break; }
-        }
-        if (g == nullptr) {
-            bbb_engine::HostedGraph &c = e->hosted_graph[e->hosted_graph_next];
-            e->hosted_graph_next = (e->hosted_graph_next + 1) % 16;
-            if (c.used) {
-                cudaGraphExecDestroy(c.exec);
-                cudaGraphDestroy(c.graph);
-                c.used = false;
-            }
-            int rc = (int)cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed);
-            if (rc == 0) {
-                rc = hosted_enqueue(e, kb_in, host_in, kb_out, host_out, dev_stage, dev_out, e->cap_stream);
-                cudaGraph_t graph = nullptr;
-                const int rc_end = (int)cudaStreamEndCapture(e->cap_stream, &graph);
-                if (rc == 0) rc = rc_end;
-                if (rc == 0) rc = (int)cudaGraphInstantiate(&c.exec, graph, 0);
-                if (rc == 0) {
-                    c.graph = graph;
-                    c.used = true;
-                    for (int s = 0; s < P.n_spaces; ++s) { c.kb_in[s] = kb_in[s]; c.kb_out[s] = kb_out[s]; }
-                    c.host_in = host_in; c.host_out = host_out; c.dev_stage = dev_stage; c.dev_out = dev_out; c.parity = parity;
-                    g = &c;
-                } else if (graph != nullptr) {
-                    cudaGraphDestroy(graph);
-                }
-            }
-            if (g == nullptr) {  // capture is not available here: enqueue every call from now on
-                (void)cudaGetLastError();
-                e->hosted_graphs = 0;
-            }
-        }
-        if (g != nullptr) {
-            CU(cudaGraphLaunch(g->exec, st));
-            launched = true;
-        }
+    return hosted_launch(e, sh, host_in, host_out, dev_stage, dev_out, (cudaStream_t)stream);
+}
+
+// ---- ragged hosted image: part h of a hosted image starts at word h * ragged_part_stride(e), whatever it holds ----
+static long long ragged_part_words(const bbb_engine *e, long long n_c, const long long *cells /* per space */) {
+    const bbb_problem_spec &P = e->host.spec;
+    long long n = (long long)ragged_header_rows(e->host) * n_c;
+    for (int s = 0; s < P.n_spaces; ++s) n += cells[s] * (P.spaces[s].ndim + P.spaces[s].n_params);
+    return n;
+}
+static long long ragged_part_stride(const bbb_engine *e) {
+    const bbb_problem_spec &P = e->host.spec;
+    const long long part = hosted_part_chains(e);
+    long long cells[BBB_MAX_SPACES];
+    for (int s = 0; s < P.n_spaces; ++s) cells[s] = part * P.spaces[s].kmax;
+    return (ragged_part_words(e, part, cells) + 511) & ~511LL;
+}
+constexpr long long RAGGED_COPY_QUANTUM = 4096;  // words: copy sizes are rounded up to 32 KiB, so that the captured graphs change rarely
+
+int64_t bbb_engine_hosted_ragged_bytes(bbb_engine *e) {
+    if (!e || !e->bound) return -1;
+    return 8 * ragged_part_stride(e) * e->hosted_np;
+}
+
+int bbb_engine_pack_states_ragged(bbb_engine *e, void *image, void *stream) {
+    NEED_BOUND(e);
+    if (!image) return fail(BBB_ERR_INVALID, "image is NULL");
+    const long long C = e->host.buf.n_chains, part = hosted_part_chains(e), stride = ragged_part_stride(e);
+    for (int h = 0; h < e->hosted_np; ++h) {
+        const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
+        CU(launch_state_image_ragged(e->host, 0, reinterpret_cast<unsigned long long *>(image) + stride * h, nullptr, c0, c1, (cudaStream_t)stream));
     }
-    if (!launched) CU(hosted_enqueue(e, kb_in, host_in, kb_out, host_out, dev_stage, dev_out, st));
-    for (int h = 0; h < NP; ++h) e->order_parity[h] ^= 1;
-    e->order_pending[0] = false;
-    bump_k_bound(e, 1);
-    ++e->steps_since_resync;
-    if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) CU(chain_local_from_scratch(e, false, st));
-    e->hosted.pending = true;
-    for (int s = 0; s < P.n_spaces; ++s) { e->hosted.kb_in[s] = kb_in[s]; e->hosted.kb_out[s] = kb_out[s]; }
-    e->hosted.host_out = host_out;
-    e->hosted.dev_stage = dev_stage;
-    e->hosted.dev_out = dev_out;
     return BBB_OK;
+}
+
+int bbb_engine_step_hosted_ragged(bbb_engine *e, const void *host_in, void *host_out, void *dev_stage, void *dev_out,
+                                  int64_t *h2d_bytes, int64_t *d2h_bytes, void *stream) {
+    NEED_BOUND(e);
+    if (!e->host.chain_local) return fail(BBB_ERR_UNSUPPORTED, "the hosted step needs a chain-local engine (2-D ray target)");
+    if (e->hosted.pending) return fail(BBB_ERR_INVALID, "the previous hosted step was not waited for (bbb_engine_step_hosted_wait)");
+    if (!host_in || !host_out || !dev_stage || !dev_out) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (host_in == host_out || dev_stage == dev_out) return fail(BBB_ERR_INVALID, "in and out images must be different buffers");
+    const bbb_problem_spec &P = e->host.spec;
+    const long long C = e->host.buf.n_chains, part = hosted_part_chains(e), stride = ragged_part_stride(e);
+    const int NP = e->hosted_np;
+    const long long *in_words = reinterpret_cast<const long long *>(host_in);
+    bbb_engine::HostedShape sh{};
+    sh.ragged = 1;
+    long long up = 0, down = 0;
+    for (int h = 0; h < NP; ++h) {
+        const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C, n_c = c1 - c0;
+        sh.in_off[h] = sh.out_off[h] = stride * h;
+        if (n_c <= 0) continue;
+        // the k rows of the uploaded header say how many cells travel; a step adds at most one cell per chain
+        long long cells_in[BBB_MAX_SPACES], cells_out[BBB_MAX_SPACES];
+        for (int s = 0; s < P.n_spaces; ++s) {
+            const long long *kr = in_words + stride * h + (long long)s * n_c;
+            long long tot = 0;
+            for (long long lc = 0; lc < n_c; ++lc) {
+                if (kr[lc] < 0 || kr[lc] > P.spaces[s].kmax)
+                    return fail(BBB_ERR_INVALID, "space %d: the image holds k = %lld for chain %lld (kmax %d)", s, kr[lc], c0 + lc, P.spaces[s].kmax);
+                tot += kr[lc];
+            }
+            cells_in[s] = tot;
+            cells_out[s] = tot + (P.spaces[s].trans_d ? n_c : 0);
+            if (cells_out[s] > n_c * P.spaces[s].kmax) cells_out[s] = n_c * P.spaces[s].kmax;
+        }
+        auto rounded = [&](long long w) {
+            w = (w + RAGGED_COPY_QUANTUM - 1) / RAGGED_COPY_QUANTUM * RAGGED_COPY_QUANTUM;
+            return w < stride ? w : stride;
+        };
+        sh.in_words[h] = rounded(ragged_part_words(e, n_c, cells_in));
+        sh.out_words[h] = rounded(ragged_part_words(e, n_c, cells_out));
+        up += sh.in_words[h];
+        down += sh.out_words[h];
+    }
+    if (h2d_bytes) *h2d_bytes = 8 * up;
+    if (d2h_bytes) *d2h_bytes = 8 * down;
+    return hosted_launch(e, sh, host_in, host_out, dev_stage, dev_out, (cudaStream_t)stream);
 }
 
 int bbb_engine_step_hosted_wait(bbb_engine *e, int32_t *n_redone, void *stream) {
@@ -1060,12 +1182,12 @@ int bbb_engine_step_hosted_wait(bbb_engine *e, int32_t *n_redone, void *stream) 
     // Parts whose uploaded states differ from the resident ones were left untouched by the guarded kernels: write
     // their states, re-derive the caches of all chains (the other parts have already advanced; for them this is the
     // periodic from-scratch re-evaluation), advance the differing parts and download them.
-    const long long rows_in = state_image_rows(e->host, e->hosted.kb_in), rows_out = state_image_rows(e->host, e->hosted.kb_out);
+    const bbb_engine::HostedShape &sh = e->hosted.shape;
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(e->hosted.dev_stage), *out = reinterpret_cast<unsigned long long *>(e->hosted.dev_out);
     for (int h = 0; h < NP; ++h) {
         if (e->hosted_flag_host[h] == 0) continue;
         const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
-        CU(launch_state_image(e->host, 2, e->hosted.kb_in, stage + rows_in * c0, nullptr, c0, c1, st));
+        CU(hosted_image(e, sh, 2, false, stage + sh.in_off[h], nullptr, c0, c1, st));
     }
     if (int rc = bbb_engine_refresh(e, stream)) return rc;
     for (int h = 0; h < NP; ++h) {
@@ -1074,9 +1196,9 @@ int bbb_engine_step_hosted_wait(bbb_engine *e, int32_t *n_redone, void *stream) 
         CU(launch_propose(e->host, c0, c1, -1, nullptr, st));
         CU(launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax, idx_bytes_of(P, e->ray_t), -1,
                              false, nullptr, st));
-        CU(launch_state_image(e->host, 0, e->hosted.kb_out, out + rows_out * c0, nullptr, c0, c1, st));
-        CU(cudaMemcpyAsync(reinterpret_cast<unsigned long long *>(e->hosted.host_out) + rows_out * c0, out + rows_out * c0,
-                           (size_t)(rows_out * (c1 - c0)) * 8, cudaMemcpyDeviceToHost, st));
+        CU(hosted_image(e, sh, 0, true, out + sh.out_off[h], nullptr, c0, c1, st));
+        CU(cudaMemcpyAsync(reinterpret_cast<unsigned long long *>(e->hosted.host_out) + sh.out_off[h], out + sh.out_off[h],
+                           (size_t)sh.out_words[h] * 8, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
     return BBB_OK;

@@ -116,6 +116,12 @@ __device__ __forceinline__ double prior_value_ratio(const PriorAt &q, double o, 
 template <class R>
 __device__ __forceinline__ double prior_sample(const PriorAt &q, R &rng) { return prior_sample(q.kind, q.a, q.b, rng); }
 
+// Targets whose misfit is not a plain weighted sum of squares (AR(1) noise, full inverse covariance matrix): their
+// residual vector is materialised per chain in dpred_scratch[t] ([n_data][C]) and reduced from there.
+__host__ __device__ __forceinline__ bool reduces_dpred(const bbb_target_spec &T) {
+    return T.correlated != 0 || T.cov_kind == BBB_COV_MATRIX;
+}
+
 __device__ __forceinline__ int n_move_types(const bbb_problem_spec &P) { return 4 * P.n_spaces + 1; }
 
 }  // namespace bbb

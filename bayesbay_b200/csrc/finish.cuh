@@ -46,10 +46,26 @@ __device__ __forceinline__ void store_phi(const bbb_buffers &B, int t, int slot,
     double *p = B.phi[t] + (long long)slot * 3 * C + c;
     p[0] = v.s0; p[C] = v.se; p[2 * C] = v.s1;
 }
+// Full inverse covariance matrix (BBB_COV_MATRIX): s0 = res^T M res = sum_i res_i (M res)_i, the order of
+// `residual @ (covariance_mat_inv @ residual)` (likelihood/_log_likelihood.py:293-301, _target.py:150-151); `res` is
+// the chain's column of a [n][C] scratch, M (row-major) is read by every chain alike (broadcast loads).
+__device__ __noinline__ inline double matrix_quadratic_form(const double *M, const double *res, long long stride, int n) {
+    double tot = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double mv = 0.0;
+        const double *row = M + (long long)i * n;
+        for (int j = 0; j < n; ++j) mv += row[j] * res[(long long)j * stride];
+        tot += res[(long long)i * stride] * mv;
+    }
+    return tot;
+}
 struct ResidualSums {  // streaming accumulation of Phi3 over r = 0 .. n-1
     Phi3 v{0.0, 0.0, 0.0};
     double prev = 0.0;
+    double *keep = nullptr;  // BBB_COV_MATRIX: the residuals are kept (stride `stride`) for matrix_quadratic_form
+    long long stride = 0;
     __device__ __forceinline__ void add(int r, int n, double res, double w) {
+        if (keep) keep[(long long)r * stride] = res;
         v.s0 += w * (res * res);
         if (r == 0 || r == n - 1) v.se += res * res;
         if (r > 0) v.s1 += prev * res;
@@ -66,6 +82,8 @@ __device__ __noinline__ inline Phi3 small_target_phi(const bbb_problem_spec &P, 
     const bbb_space_spec &S = P.spaces[s];
     const long long C = B.n_chains;
     ResidualSums acc;
+    const bool full_matrix = T.cov_kind == BBB_COV_MATRIX;
+    if (full_matrix) { acc.keep = B.dpred_scratch[t] + c; acc.stride = C; }
     if (T.fwd_kind == BBB_FWD_LOOKUP1D) {
         // Voronoi1D.interpolate_tessellation(..., 'nuclei') (discretization/_voronoi.py:705-732)
         const int k = k_ref(B, s, slot, c);
@@ -103,6 +121,7 @@ __device__ __noinline__ inline Phi3 small_target_phi(const bbb_problem_spec &P, 
             acc.add(r, T.n_data, d - T.dobs[r], data_weight(T, r));
         }
     }
+    if (full_matrix) acc.v.s0 = matrix_quadratic_form(T.cov_vec, acc.keep, C, T.n_data);
     return acc.v;
 }
 
@@ -209,7 +228,7 @@ __device__ inline void finish_gather_rest(const EngineParams &ep, long long c, F
     for (int t = 0; t < P.n_targets; ++t) {
         const bbb_target_spec &T = P.targets[t];
         const bool hier = (T.cov_kind == BBB_COV_HIERARCHICAL);
-        in.phi_old[t] = T.correlated ? load_phi(B, t, 0, c) : Phi3{B.phi[t][c], 0.0, 0.0};
+        in.phi_old[t] = T.correlated ? load_phi(B, t, 0, c) : Phi3{B.phi[t][c], 0.0, 0.0};  // (only AR(1) noise reads se, s1)
         in.sig[t][0] = hier ? B.sigma[t][c] : 1.0;
         in.sig[t][1] = (hier && noise) ? B.sigma[t][C + c] : in.sig[t][0];
         in.rho[t][0] = T.correlated ? B.corr[t][c] : 0.0;
@@ -255,7 +274,7 @@ __device__ inline void finish_pre(const EngineParams &ep, long long c, const Fin
             pre.phi_new[t] = phi_old;
             if (!noise && T.space == s && t != ray_t) {
                 if (T.fwd_kind != BBB_FWD_RAY2D) pre.phi_new[t] = small_target_phi(P, B, t, in.sel_s ^ 1, c, nullptr, nullptr);
-                else if (T.correlated) pre.phi_new[t] = load_phi(B, t, 1, c);  // k_corr_sums
+                else if (reduces_dpred(T)) pre.phi_new[t] = load_phi(B, t, 1, c);  // k_corr_sums
                 else pre.phi_new[t] = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
                 store_phi(B, t, 1, c, pre.phi_new[t]);
             }

@@ -96,6 +96,10 @@ long long state_image_rows(const EngineParams &host_params, const int32_t *kb);
 // chains [c_first, c_end): the image has rows of (c_end - c_first) words
 int launch_state_image(const EngineParams &host_params, int mode, const int32_t *kb, void *image, int32_t *differ,
                        long long c_first, long long c_end, cudaStream_t stream);
+// ragged image of the chains [c_first, c_end) (only the cells in use; layout: step_kernels.cu); mode as above
+int ragged_header_rows(const EngineParams &host_params);
+int launch_state_image_ragged(const EngineParams &host_params, int mode, void *image, int32_t *differ, long long c_first,
+                              long long c_end, cudaStream_t stream);
 // save point: states + noise + temperature sections of the chain-major image (step_kernels.cu), d_pred of a chain-local
 // ray target from its resident residuals
 long long save_point_state_words(const EngineParams &host_params, const int32_t *kb);

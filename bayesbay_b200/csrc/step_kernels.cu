@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_refresh_finish(const EnginePar
         const bbb_target_spec &T = P.targets[t];
         Phi3 phi;
         if (T.fwd_kind != BBB_FWD_RAY2D) phi = small_target_phi(P, B, t, B.sel[T.space][c], c, nullptr, nullptr);
-        else if (T.correlated) phi = load_phi(B, t, 0, c);  // written by k_corr_sums from d_pred
+        else if (reduces_dpred(T)) phi = load_phi(B, t, 0, c);  // written by k_corr_sums from d_pred
         else phi = Phi3{ray_partial_sum(ep, t, c), 0.0, 0.0};
         store_phi(B, t, 0, c, phi);
         store_phi(B, t, 1, c, phi);
@@ -177,7 +177,14 @@ __global__ void k_corr_sums(const EngineParams *epp, int t, int proposal) {
     if (c >= C) return;
     if (proposal && !target_touched(P, B.move[c], B.log_prob_ratio[c], t)) return;
     ResidualSums acc;
-    for (int r = 0; r < T.n_data; ++r) acc.add(r, T.n_data, B.dpred_scratch[t][(long long)r * C + c] - T.dobs[r], 1.0);
+    if (T.cov_kind == BBB_COV_MATRIX) {
+        // d_pred -> residual in place (every consumer of the scratch re-derives it with the SpMM first), then res^T M res
+        double *col = B.dpred_scratch[t] + c;
+        for (int r = 0; r < T.n_data; ++r) col[(long long)r * C] -= T.dobs[r];
+        acc.v.s0 = matrix_quadratic_form(T.cov_vec, col, C, T.n_data);
+    } else {
+        for (int r = 0; r < T.n_data; ++r) acc.add(r, T.n_data, B.dpred_scratch[t][(long long)r * C + c] - T.dobs[r], 1.0);
+    }
     store_phi(B, t, proposal ? 1 : 0, c, acc.v);
 }
 
@@ -279,6 +286,122 @@ __global__ void k_state_image(const __grid_constant__ EngineParams ep, const __g
     } else if (live) {
         *dst = *slot;
         if (dst2 != nullptr) *dst2 = *slot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RAGGED chain-state image (the hosted step's wire format): only the cells IN USE travel -- what a pickle of the
+// reference's chain holds (samplers/_samplers.py:225-237 moves arrays of k cells, not n_dimensions_max).  Image of
+// the chains [c_first, c_first + n_c), 8-byte words:
+//   header, HR rows of n_c words: k of every space (int64) | sigma (and correlation) per hierarchical target |
+//           temperature | iteration (int64);
+//   then per space s, chain after chain: the chain's k_s cells, w_s = ndim + n_params words each (site coordinates,
+//           then parameter values); chain lc of space s starts at word
+//           HR n_c + sum_{s' < s} w_s' sum_lc' k_s'[lc'] + w_s sum_{lc' < lc} k_s[lc'].
+// One warp per (space, chain), lanes = cells; the offsets come from block-wide sums over the k row (of the engine when
+// packing, of the image when comparing / unpacking).  blockIdx.y == n_spaces: the header rows.
+// MODE as k_state_image: 0 pack, 1 compare (sets *differ), 2 unpack into slot 0.
+// ------------------------------------------------------------------------------------------------
+constexpr int RAGGED_THREADS = 256, RAGGED_WARPS = RAGGED_THREADS / 32;
+
+template <int MODE>
+__global__ void __launch_bounds__(RAGGED_THREADS) k_state_image_ragged(const __grid_constant__ EngineParams ep, unsigned long long *image,
+                                                                       int32_t *differ, long long c_first, long long n_c) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int n_noise = 0;
+    for (int t = 0; t < P.n_targets; ++t)
+        if (P.targets[t].cov_kind == BBB_COV_HIERARCHICAL) n_noise += P.targets[t].correlated ? 2 : 1;
+    const int HR = P.n_spaces + n_noise + 2;
+    if ((int)blockIdx.y == P.n_spaces) {
+        // ---- header rows: one thread per (row, chain)
+        for (long long i = (long long)blockIdx.x * RAGGED_THREADS + tid; i < (long long)HR * n_c; i += (long long)gridDim.x * RAGGED_THREADS) {
+            const int row = (int)(i / n_c);
+            const long long lc = i % n_c, c = c_first + lc;
+            unsigned long long *slot = image + i;
+            if (row < P.n_spaces) {
+                const int s = row;
+                if (MODE == 2) {
+                    const int kv = (int)(long long)*slot;
+                    k_ref(B, s, 0, c) = kv;
+                    k_ref(B, s, 1, c) = kv;
+                    B.sel[s][c] = 0;
+                } else {
+                    const unsigned long long cur = (unsigned long long)(long long)k_ref(B, s, (int)B.sel[s][c], c);
+                    if (MODE == 0) *slot = cur;
+                    else if (*slot != cur) *differ = 1;
+                }
+                continue;
+            }
+            int rel = row - P.n_spaces;
+            unsigned long long *dst = nullptr, *dst2 = nullptr;
+            for (int t = 0; t < P.n_targets && dst == nullptr; ++t) {
+                const bbb_target_spec &T = P.targets[t];
+                if (T.cov_kind != BBB_COV_HIERARCHICAL) continue;
+                const int n = T.correlated ? 2 : 1;
+                if (rel < n) {
+                    double *p = rel == 0 ? B.sigma[t] : B.corr[t];
+                    dst = reinterpret_cast<unsigned long long *>(p + c);
+                    dst2 = reinterpret_cast<unsigned long long *>(p + C + c);
+                } else {
+                    rel -= n;
+                }
+            }
+            if (dst == nullptr) dst = rel == 0 ? reinterpret_cast<unsigned long long *>(B.temperature + c)
+                                               : reinterpret_cast<unsigned long long *>(B.iteration + c);
+            if (MODE == 0) *slot = *dst;
+            else if (MODE == 1) { if (*slot != *dst) *differ = 1; }
+            else { *dst = *slot; if (dst2 != nullptr) *dst2 = *slot; }
+        }
+        return;
+    }
+    // ---- cells of space s: warp = chain
+    const int s = blockIdx.y;
+    const bbb_space_spec &S = P.spaces[s];
+    __shared__ long long s_part[RAGGED_WARPS];
+    __shared__ int s_k[RAGGED_WARPS];
+    // number of cells a chain of space q occupies in the image
+    auto k_of = [&](int q, long long lc) -> int {
+        if (MODE == 0) return k_ref(B, q, (int)B.sel[q][c_first + lc], c_first + lc);
+        const long long kv = (long long)image[(long long)q * n_c + lc];
+        return kv < 0 ? 0 : (kv > P.spaces[q].kmax ? P.spaces[q].kmax : (int)kv);
+    };
+    const long long lc0 = (long long)blockIdx.x * RAGGED_WARPS;  // first chain of this block
+    // words in front of this block's first chain: the earlier spaces' cells, and the earlier chains' cells of this space
+    long long mine = 0;
+    for (int q = 0; q < s; ++q) {
+        const int w = P.spaces[q].ndim + P.spaces[q].n_params;
+        for (long long i = tid; i < n_c; i += RAGGED_THREADS) mine += (long long)w * k_of(q, i);
+    }
+    const int w = S.ndim + S.n_params;
+    for (long long i = tid; i < lc0 && i < n_c; i += RAGGED_THREADS) mine += (long long)w * k_of(s, i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    const long long lc = lc0 + warp;
+    const int k_img = lc < n_c ? k_of(s, lc) : 0;
+    if (lane == 0) { s_part[warp] = mine; s_k[warp] = k_img; }
+    __syncthreads();
+    if (lc >= n_c) return;
+    long long base = (long long)HR * n_c;
+    for (int i = 0; i < RAGGED_WARPS; ++i) base += s_part[i];
+    for (int i = 0; i < warp; ++i) base += (long long)w * s_k[i];
+    const long long c = c_first + lc;
+    const int sl = MODE == 2 ? 0 : (int)B.sel[s][c];
+    if (MODE == 1 && k_ref(B, s, sl, c) != k_img) {  // (the header block flags it too)
+        if (lane == 0) *differ = 1;
+        return;
+    }
+    unsigned long long *cells = image + base;
+    for (int j = lane; j < k_img; j += 32) {
+        for (int q = 0; q < w; ++q) {
+            double *p = q < S.ndim ? &site_ref(B, S, s, sl, q, j, c) : &value_ref(B, S, s, sl, q - S.ndim, j, c);
+            unsigned long long *slot = cells + (long long)j * w + q;
+            if (MODE == 0) *slot = (unsigned long long)__double_as_longlong(*p);
+            else if (MODE == 1) { if (*slot != (unsigned long long)__double_as_longlong(*p)) *differ = 1; }
+            else *p = __longlong_as_double((long long)*slot);
+        }
     }
 }
 
@@ -706,6 +829,23 @@ int launch_state_image(const EngineParams &p, int mode, const int32_t *kb, void 
     if (mode == 0) k_state_image<0><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
     else if (mode == 1) k_state_image<1><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
     else k_state_image<2><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
+    return (int)cudaGetLastError();
+}
+int ragged_header_rows(const EngineParams &p) {
+    int rows = p.spec.n_spaces + 2;  // k per space, temperature, iteration
+    for (int t = 0; t < p.spec.n_targets; ++t)
+        if (p.spec.targets[t].cov_kind == BBB_COV_HIERARCHICAL) rows += p.spec.targets[t].correlated ? 2 : 1;
+    return rows;
+}
+int launch_state_image_ragged(const EngineParams &p, int mode, void *image, int32_t *differ, long long c_first, long long c_end,
+                              cudaStream_t st) {
+    if (c_end <= c_first) return 0;
+    const long long n_c = c_end - c_first;
+    dim3 grid((unsigned)((n_c + RAGGED_WARPS - 1) / RAGGED_WARPS), p.spec.n_spaces + 1);
+    unsigned long long *img = reinterpret_cast<unsigned long long *>(image);
+    if (mode == 0) k_state_image_ragged<0><<<grid, RAGGED_THREADS, 0, st>>>(p, img, differ, c_first, n_c);
+    else if (mode == 1) k_state_image_ragged<1><<<grid, RAGGED_THREADS, 0, st>>>(p, img, differ, c_first, n_c);
+    else k_state_image_ragged<2><<<grid, RAGGED_THREADS, 0, st>>>(p, img, differ, c_first, n_c);
     return (int)cudaGetLastError();
 }
 static SaveLayout save_layout(const EngineParams &p, const int32_t *kb, long long *n_words_states) {

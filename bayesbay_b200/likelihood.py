@@ -6,7 +6,6 @@ from typing import List, Union
 
 import numpy as np
 
-from .exceptions import DeviceUnsupported
 from .forward import ForwardOperator
 from .perturbations import NoisePerturbation
 
@@ -44,8 +43,8 @@ class Target:
             self.covariance_mat_inv = covariance_mat_inv
         else:
             self.covariance_mat_inv = np.array(covariance_mat_inv)
-            if self.covariance_mat_inv.ndim != 1:
-                raise DeviceUnsupported("full inverse covariance matrices are not implemented by the device engine")
+            if self.covariance_mat_inv.ndim not in (1, 2):
+                raise ValueError("covariance_mat_inv must be a scalar, a 1-D (diagonal) or a 2-D (full) array")
 
     @property
     def name(self) -> str:

@@ -527,7 +527,7 @@ def api_run(par, ll, bb, n_chains, n_iterations=2000, save_every=100):
 
 
 def e2e_run(eng, steps, device, world, dist):
-    """The plugin call with HOST buffers, one iteration per call (bbb_engine_step_hosted + _wait): the chains' states
+    """The plugin call with HOST buffers, one iteration per call (bbb_engine_step_hosted_ragged + _wait): the chains' states
     (k, sites, values, noise sigma, temperature, iteration) go pinned host -> device, the chains advance one
     iteration, the updated states come back device -> host and the host waits for them.  The chain set travels in
     parts on the engine's internal streams, so one part's copies overlap the other parts' kernels.  The derived
@@ -538,26 +538,24 @@ def e2e_run(eng, steps, device, world, dist):
     along with every chain."""
     import torch
 
-    K = eng.spec["spaces"][0]["kmax"]
-    cap = eng.state_image_bytes(K) // 8
-    host = [torch.empty((cap,), dtype=torch.int64, pin_memory=True) for _ in range(2)]  # the caller's chains, in / out
-    stage = torch.empty((cap,), dtype=torch.int64, device=device)     # upload buffer
-    out = torch.empty((cap,), dtype=torch.int64, device=device)       # download buffer
+    cap = eng.hosted_ragged_words()
+    host = [torch.zeros((cap,), dtype=torch.int64, pin_memory=True) for _ in range(2)]  # the caller's chains, in / out
+    stage = torch.zeros((cap,), dtype=torch.int64, device=device)     # upload buffer
+    out = torch.zeros((cap,), dtype=torch.int64, device=device)       # download buffer
     refreshed = [0]
     moved = [0, 0]
 
-    kb = min(K, int(eng.gather_space(0)[0].max().item()))
-    n0 = eng.state_image_bytes(kb) // 8
-    host[0][:n0].copy_(eng.pack_states_hosted(kb))
+    host[0].copy_(eng.pack_states_ragged())
     torch.cuda.synchronize(device)
     cur = 0
+    kb = None
 
-    def call(kb_up, cur):
-        kb_down = eng.step_hosted(kb_up, host[cur], host[cur ^ 1], stage, out)[0]
+    def call(_, cur):
+        up, down = eng.step_hosted_ragged(host[cur], host[cur ^ 1], stage, out)
         refreshed[0] += eng.step_hosted_wait()  # the host reads the step's result before the next call
-        moved[0] += eng.state_image_bytes(kb_up)
-        moved[1] += eng.state_image_bytes(kb_down)
-        return kb_down
+        moved[0] += up
+        moved[1] += down
+        return None
 
     for _ in range(3):
         kb = call(kb, cur)
@@ -583,8 +581,10 @@ def e2e_run(eng, steps, device, world, dist):
     return {"value": world * eng.C * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": moved[0] // steps,
             "d2h_bytes_per_step": moved[1] // steps, "ms_per_step": ms / steps, "host_wall_ms_per_step": wall_ms / steps,
             "cache_refreshes": refreshed[0], "parts": len(eng.hosted_parts()) - 1,
-            "what": "per call (bbb_engine_step_hosted + bbb_engine_step_hosted_wait): packed image of the chains' states in "
-                    "pinned host memory (k; sites and values of the cells in use; sigma, temperature, iteration) -> device, "
+            "k_mean": float(eng.gather_space(0)[0].double().mean().item()),
+            "what": "per call (bbb_engine_step_hosted_ragged + bbb_engine_step_hosted_wait): RAGGED packed image of the chains' "
+                    "states in pinned host memory (k; sites and values of the k cells in use; sigma, temperature, iteration; "
+                    "copy sizes rounded up to 32 KiB) -> device, "
                     "compared on the device with the resident states the caches belong to, one iteration, packed image -> "
                     "pinned host memory, host waits; the chain set travels in parts on internal streams (copies of one part "
                     "overlap the kernels of the others)"}

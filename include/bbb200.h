@@ -55,9 +55,9 @@ enum { BBB_BIRTH_FROM_PRIOR = 0, BBB_BIRTH_FROM_NEIGHBOUR = 1 };
 /* forward operators (the user forward functions of the tutorials) */
 enum { BBB_FWD_RAY2D = 0, BBB_FWD_LOOKUP1D = 1, BBB_FWD_LINEAR = 2, BBB_FWD_POLYNOMIAL = 3 };
 enum { BBB_TRANSFORM_IDENTITY = 0, BBB_TRANSFORM_RECIPROCAL = 1 };
-/* data covariance: hierarchical sigma (Target(std_min,...)), fixed scalar / vector inverse covariance
- * (likelihood/_target.py:136-170) */
-enum { BBB_COV_HIERARCHICAL = 0, BBB_COV_SCALAR = 1, BBB_COV_VECTOR = 2 };
+/* data covariance: hierarchical sigma (Target(std_min,...)), fixed scalar / per-datum vector / full matrix inverse
+ * covariance (likelihood/_target.py:136-170: `covariance_mat_inv * vector` or, for ndim == 2, `covariance_mat_inv @ vector`) */
+enum { BBB_COV_HIERARCHICAL = 0, BBB_COV_SCALAR = 1, BBB_COV_VECTOR = 2, BBB_COV_MATRIX = 3 };
 /* inner move kinds; move id = 4 * space + kind, noise move id = 4 * n_spaces */
 enum { BBB_MOVE_BIRTH = 0, BBB_MOVE_DEATH = 1, BBB_MOVE_VALUES = 2, BBB_MOVE_SITES = 3 };
 
@@ -94,7 +94,7 @@ typedef struct {
     double corr_min, corr_max, corr_perturb_std;
     double cov_scalar;
     const double *dobs;      /* device [n_data] */
-    const double *cov_vec;   /* device [n_data] or NULL */
+    const double *cov_vec;   /* BBB_COV_VECTOR: device [n_data]; BBB_COV_MATRIX: device [n_data][n_data] row-major; else NULL */
     int32_t fwd_kind;        /* BBB_FWD_* */
     int32_t space;           /* parameter space the forward reads */
     int32_t param;           /* ray2d / lookup1d: parameter index inside the space */
@@ -309,6 +309,25 @@ int bbb_engine_hosted_parts(bbb_engine *e, int64_t *first_chain /* [5] */);
 int bbb_engine_step_hosted(bbb_engine *e, const int32_t *kb_in, const void *host_in, int32_t *kb_out, void *host_out,
                            void *dev_stage, void *dev_out, void *stream);
 int bbb_engine_step_hosted_wait(bbb_engine *e, int32_t *n_redone, void *stream);
+/* The hosted step on a RAGGED image: only the cells in use travel, as in the pickles the reference's pool moves
+ * (samplers/_samplers.py:225-237: a chain's arrays hold k cells, not n_dimensions_max).  A ragged hosted image is
+ * bbb_engine_hosted_ragged_bytes() bytes; part h (bbb_engine_hosted_parts) starts at byte h * bytes / n_parts and
+ * holds, for its n_c chains, 8-byte words:
+ *   header, rows of n_c words: k of every space (int64) | sigma (and correlation) per hierarchical target |
+ *           temperature | iteration (int64);
+ *   then per space, chain after chain: the chain's k cells, (ndim + n_params) words each (site coordinates, then
+ *           the parameter values) -- chain lc of space s starts (ndim + n_params) * (k[0] + ... + k[lc - 1]) words into
+ *           the space's block, and the blocks of the spaces follow one another without gaps.
+ * bbb_engine_pack_states_ragged writes the current states of all chains in this format (device buffer).
+ * bbb_engine_step_hosted_ragged is bbb_engine_step_hosted for such images: per part the header's k rows (read on the
+ * host) say how many words go up; what comes down is bounded by one more cell per chain of a trans-dimensional
+ * space; both are rounded up to 32 KiB (the buffers hold the full size anyway), so that the captured graphs change
+ * rarely.  *h2d_bytes / *d2h_bytes (may be NULL) = bytes copied each way by this call.  All four buffers hold
+ * bbb_engine_hosted_ragged_bytes() bytes.  The wait is bbb_engine_step_hosted_wait. */
+int64_t bbb_engine_hosted_ragged_bytes(bbb_engine *e);
+int bbb_engine_pack_states_ragged(bbb_engine *e, void *image, void *stream);
+int bbb_engine_step_hosted_ragged(bbb_engine *e, const void *host_in, void *host_out, void *dev_stage, void *dev_out,
+                                  int64_t *h2d_bytes, int64_t *d2h_bytes, void *stream);
 /* d_pred of the CURRENT states of one target, [n_data][C] (the "{target}.dpred" cache entry,
  * likelihood/_log_likelihood.py:311-320). */
 int bbb_engine_dpred(bbb_engine *e, int target, double *dpred_out, void *stream);

@@ -183,7 +183,8 @@ def misfit_and_logdet(dpred, dobs, std=None, cov_inv=None, corr=None):
     (likelihood/_target.py:172-208)."""
     r = dpred - dobs
     if cov_inv is not None:
-        misfit = float(r @ (cov_inv * r))
+        # `covariance_mat_inv @ vector` for a 2-D array, `covariance_mat_inv * vector` otherwise (_target.py:146-152)
+        misfit = float(r @ (cov_inv @ r)) if np.ndim(cov_inv) == 2 else float(r @ (cov_inv * r))
         return misfit, 0.0
     n = dobs.size
     if corr is None:

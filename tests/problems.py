@@ -170,9 +170,38 @@ def tomo_scalar_prior_birth():
     return spec
 
 
+def _spd_inverse_covariance(n, scale, seed):
+    """A dense symmetric positive-definite inverse covariance [n][n]: exponentially decaying correlations between
+    neighbouring data (full matrix, `covariance_mat_inv.ndim == 2`, likelihood/_target.py:150-151)."""
+    rng = np.random.default_rng(seed)
+    i = np.arange(n)
+    cov = np.exp(-np.abs(i[:, None] - i[None, :]) / 2.5) * np.outer(s := rng.uniform(0.8, 1.25, n), s)
+    return np.linalg.inv(cov) * scale
+
+
+def joint_matrix_cov():
+    """joint_small with FULL inverse covariance matrices on the weighted linear target and on the 1-D lookup target."""
+    spec = joint_small()
+    for t, scale, seed in ((1, 0.0025, 11), (2, 0.04, 12)):
+        tg = spec["targets"][t]
+        tg.update(hierarchical=False, cov_inv=_spd_inverse_covariance(tg["dobs"].size, scale, seed))
+    return spec
+
+
+def tomo_matrix_cov():
+    """Ray tomography with a FULL inverse covariance matrix on the travel times (runs the full-SpMM step: the misfit is
+    reduced from the materialised residual vector)."""
+    ing = synthetic.tomography_2d(nx=16, ny=12, n_sources_per_side=3, n_receivers=6, kmin=2, kmax=30)
+    spec = spec_from_ingredients(ing)
+    tg = spec["targets"][0]
+    tg.update(hierarchical=False, cov_inv=_spd_inverse_covariance(np.asarray(tg["dobs"]).size, 2.5e5, 13))
+    return spec
+
+
 # oracle-vs-device cases without a reference replay fixture
 SPECS = {"joint_small": joint_small, "tomo_joint_small": tomo_joint_small, "tomo_weighted_fixed": tomo_weighted_fixed,
-         "tomo_scalar_prior_birth": tomo_scalar_prior_birth}
+         "tomo_scalar_prior_birth": tomo_scalar_prior_birth, "joint_matrix_cov": joint_matrix_cov,
+         "tomo_matrix_cov": tomo_matrix_cov}
 EXTRA = {
     "tomo_small_corr": lambda: synthetic.tomography_2d(nx=12, ny=10, n_sources_per_side=3, n_receivers=5, kmin=4,
                                                        kmax=20, correlated=True),

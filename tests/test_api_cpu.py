@@ -146,6 +146,10 @@ def test_things_that_cannot_run_on_the_device_raise():
         bb.BaseBayesianInversion([None], [lambda s: (s, 0)], n_chains=1)
     with pytest.raises(ValueError):
         bb.likelihood.Target("d", np.zeros(3), noise_is_correlated=True, covariance_mat_inv=2.0)
+    # scalar, diagonal and full inverse covariances are all accepted (likelihood/_target.py:146-152)
+    assert not bb.likelihood.Target("d", np.zeros(3), covariance_mat_inv=np.eye(3)).is_hierarchical
+    with pytest.raises(ValueError):
+        bb.likelihood.Target("d", np.zeros(3), covariance_mat_inv=np.zeros((3, 3, 3)))
     with pytest.raises(DeviceUnsupported):  # N-D position grids (LinearNDInterpolator) are not on the device
         bb.prior.UniformPrior("v", vmin=[0, 1], vmax=[1, 2], perturb_std=0.1, position=[[0, 0], [1, 1]])
     pd = bb.prior.UniformPrior("v", vmin=[0, 1], vmax=[1, 2], perturb_std=0.1, position=[0, 1])

@@ -498,3 +498,38 @@ def test_set_perturbation_funcs_custom_weights():
     np.testing.assert_allclose(p2[:4] / p2[:4].sum(), [1 / 6, 1 / 6, 3 / 6, 1 / 6], atol=0.012)
     with pytest.raises(TypeError):
         inv2.set_perturbation_funcs([lambda state: (state, 0.0)])
+
+
+def test_full_matrix_inverse_covariance_through_the_api():
+    """`Target(covariance_mat_inv=<2-D array>)` (likelihood/_target.py:146-152: `covariance_mat_inv @ vector`): the
+    engine's misfit of every chain equals residual @ M @ residual of the d_pred it reports, the sampler moves towards
+    the data, and a diagonal matrix gives the misfit of the same values passed as a per-datum vector."""
+    ing = synthetic.partition_1d()
+    n = ing["d_obs"].size
+    i = np.arange(n)
+    cov = 4.0 * np.exp(-np.abs(i[:, None] - i[None, :]) / 3.0)
+    M = np.linalg.inv(cov)
+    ing = dict(ing, target=dict(name=ing["target"]["name"], covariance_mat_inv=M))
+    inv = make_inversion(ing, 16, seed=5)
+    eng = inv.batch.engine
+
+    def host_misfit():
+        dp = eng.dpred(0).cpu().numpy()  # [n_data][C]
+        r = dp - ing["d_obs"][:, None]
+        return np.einsum("ic,ij,jc->c", r, M, r)
+
+    m0 = eng.misfit_logdet()[0].cpu().numpy()
+    np.testing.assert_allclose(m0, host_misfit(), rtol=1e-12)
+    inv.run(n_iterations=1500, burnin_iterations=500, save_every=100, verbose=False)
+    m1, ld = (v.cpu().numpy() for v in eng.misfit_logdet())
+    np.testing.assert_allclose(m1, host_misfit(), rtol=1e-12)
+    assert (ld == 0).all() and np.median(m1) < 0.5 * np.median(m0)
+    res = inv.get_results()
+    assert len(res["voronoi.n_dimensions"]) == 16 * 10 and len(res[f"{ing['target']['name']}.dpred"][0]) == n
+    # diagonal matrix == per-datum vector (same residuals, so the misfits agree to rounding)
+    w = np.random.default_rng(1).uniform(0.1, 0.5, n)
+    mis = []
+    for c_inv in (np.diag(w), w):
+        ing2 = dict(ing, target=dict(name=ing["target"]["name"], covariance_mat_inv=c_inv))
+        mis.append(make_inversion(ing2, 8, seed=9).batch.engine.misfit_logdet()[0].cpu().numpy())
+    np.testing.assert_allclose(mis[0], mis[1], rtol=1e-13)

@@ -228,7 +228,8 @@ def test_incremental_raster_equals_brute_force_at_scale():
 
 
 @pytest.mark.parametrize("name,n_chains,n_steps", [("joint_small", 80, 80), ("tomo_joint_small", 48, 60),
-                                                   ("tomo_weighted_fixed", 60, 80), ("tomo_scalar_prior_birth", 60, 80)])
+                                                   ("tomo_weighted_fixed", 60, 80), ("tomo_scalar_prior_birth", 60, 80),
+                                                   ("joint_matrix_cov", 64, 80), ("tomo_matrix_cov", 48, 60)])
 def test_multi_space_multi_target_against_oracle(name, n_chains, n_steps):
     """Several parameter spaces and targets (hierarchical, per-datum and scalar inverse covariance; linear,
     1-D lookup and ray forwards side by side): move ids, outer weights and the summed likelihood ratio
@@ -266,6 +267,10 @@ def test_multi_space_multi_target_against_oracle(name, n_chains, n_steps):
     assert in_step.mean() > 0.9
     if name.endswith("joint_small"):
         assert len(seen) >= 6  # moves of both spaces and the noise move all occurred
+    elif name == "joint_matrix_cov":
+        assert len(seen) >= 5
+    elif name == "tomo_matrix_cov":
+        assert not eng.chain_local and len(seen) >= 3  # full inverse covariance: the full-SpMM step
     else:
         assert eng.chain_local and len(seen) >= 2
     mis, ld = eng.misfit_logdet()
@@ -603,6 +608,104 @@ def test_hosted_step_equals_resident_step(monkeypatch, pipeline, graph):
     np.testing.assert_allclose(eng.res[0].cpu().numpy(), res_inc.cpu().numpy(), rtol=0, atol=1e-9)
     with pytest.raises(Exception):
         eng.step_hosted(kb2, dst, dst, stage, out)
+
+
+@pytest.mark.parametrize("pipeline,graph", [(1, 1), (2, 1), (4, 0)])
+def test_hosted_step_ragged_image(monkeypatch, pipeline, graph):
+    """bbb_engine_step_hosted_ragged: the hosted step on the RAGGED wire format (only the cells in use travel).
+    (a) The ragged image decodes to the chains' states; fast path bit-identical to resident stepping over 300
+    iterations (incl. a from-scratch re-evaluation), never redone, and fewer bytes than the kb-padded rows.
+    (b) An edited chain is detected, its part redone, every chain advances once.  (c) An invalid k is refused."""
+    from bayesbay_b200 import synthetic
+
+    monkeypatch.setenv("BBB_HOSTED_PARTS", str(pipeline))
+    monkeypatch.setenv("BBB_HOSTED_GRAPH", str(graph))
+    ing = synthetic.tomography_2d(nx=32, ny=32, n_sources_per_side=5, n_receivers=12, kmin=4, kmax=60)
+    spec = problems.spec_from_ingredients(ing)
+    n = 148 + 37
+    K = spec["spaces"][0]["kmax"]
+    ref, eng = _engine(spec, n, seed=5), _engine(spec, n, seed=5)
+    for e in (ref, eng):
+        e.init_states()
+        e.step(20)
+    cap = eng.hosted_ragged_words()
+    host = [torch.zeros((cap,), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    stage = torch.zeros((cap,), dtype=torch.int64, device="cuda")
+    out = torch.zeros((cap,), dtype=torch.int64, device="cuda")
+    host[0].copy_(eng.pack_states_ragged())
+    torch.cuda.synchronize()
+
+    def decode(e, image):
+        """per chain (k, cells [k][3], sigma, temperature, iteration) from a ragged image"""
+        chains = {}
+        for c0, c1, words in e.ragged_parts(image):
+            n_c = c1 - c0
+            k = words[:n_c].numpy()
+            sig, temp = words[n_c:2 * n_c].view(torch.float64).numpy(), words[2 * n_c:3 * n_c].view(torch.float64).numpy()
+            it = words[3 * n_c:4 * n_c].numpy()
+            cells = words[4 * n_c:].view(torch.float64).numpy().reshape(-1, 3)
+            off = np.concatenate([[0], np.cumsum(k)])
+            assert off[-1] == cells.shape[0]
+            for lc in range(n_c):
+                chains[c0 + lc] = (int(k[lc]), cells[off[lc]:off[lc + 1]].copy(), float(sig[lc]), float(temp[lc]), int(it[lc]))
+        return chains
+
+    def check_against_engine(e, image):
+        got = decode(e, image)
+        k, sites, vals = (v.cpu().numpy() for v in e.gather_space(0))
+        sig, temp, it = e.sigma[0][0].cpu().numpy(), e.temperature.cpu().numpy(), e.iteration.cpu().numpy()
+        assert sorted(got) == list(range(n))
+        for c, (kc, cells, s_, t_, i_) in got.items():
+            assert kc == k[c] and s_ == sig[c] and t_ == temp[c] and i_ == it[c]
+            assert np.array_equal(cells[:, 0], sites[0, :kc, c]) and np.array_equal(cells[:, 1], sites[1, :kc, c])
+            assert np.array_equal(cells[:, 2], vals[0, :kc, c])
+
+    check_against_engine(eng, host[0])
+    n_steps = 300
+    moved = 0
+    for it in range(n_steps):
+        up, down = eng.step_hosted_ragged(host[it & 1], host[(it + 1) & 1], stage, out)
+        assert eng.step_hosted_wait() == 0
+        moved += up + down
+        ref.step(1)
+    last = host[n_steps & 1]
+    check_against_engine(eng, last)
+    ref_img = ref.pack_states_ragged().cpu()
+    for (c0, c1, a), (_, _, b) in zip(eng.ragged_parts(last), ref.ragged_parts(ref_img)):
+        assert torch.equal(a, b)
+    assert torch.equal(eng.res[0], ref.res[0]) and torch.equal(eng.idx_cm[0], ref.idx_cm[0])
+    assert torch.equal(eng.n_accepted, ref.n_accepted)
+    kb = int(eng.gather_space(0)[0].max().item())
+    assert moved / (2 * n_steps) < eng.state_image_bytes(kb)  # fewer bytes than the rows padded to the largest k
+
+    # (b) the caller edits the value of the first cell of a chain of the LAST part
+    parts = eng.ragged_parts(last)
+    c0, c1, words = parts[-1]
+    n_c = c1 - c0
+    lc = n_c - 3
+    pos = 4 * n_c + 3 * int(words[:lc].sum().item()) + 2
+    words[pos:pos + 1] = (words[pos:pos + 1].view(torch.float64) * 1.03125).view(torch.int64)  # (a view: edits `last`)
+    dst = host[(n_steps + 1) & 1]
+    eng.step_hosted_ragged(last, dst, stage, out)
+    assert eng.step_hosted_wait() == 1
+    assert (eng.iteration.cpu().numpy() == 20 + n_steps + 1).all()
+    check_against_engine(eng, dst)
+    ref.step(1)
+    got, want = decode(eng, dst), decode(ref, ref.pack_states_ragged().cpu())
+    for c in range(n):
+        if c != c0 + lc:
+            assert got[c][0] == want[c][0] and np.array_equal(got[c][1], want[c][1]) and got[c][2:] == want[c][2:]
+    eng.step(10)
+    res_inc = eng.res[0].clone()
+    eng.resync()
+    np.testing.assert_allclose(eng.res[0].cpu().numpy(), res_inc.cpu().numpy(), rtol=0, atol=1e-9)
+    # (c) a k outside [0, kmax] in the uploaded header is refused before anything is enqueued
+    bad = dst.clone().pin_memory()
+    bad[0] = K + 1
+    with pytest.raises(Exception):
+        eng.step_hosted_ragged(bad, host[n_steps & 1], stage, out)
+    with pytest.raises(Exception):
+        eng.step_hosted_ragged(dst, dst, stage, out)
 
 
 def test_exception_counters():

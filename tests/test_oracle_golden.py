@@ -92,6 +92,19 @@ def test_misfit_logdet_ratio(kg):
     np.testing.assert_allclose(OK.misfit_and_logdet(kg["ll_dp_old"], dobs, cov_inv=kg["ll_w"]), kg["ll_fixed_v"], rtol=RTOL)
 
 
+def test_full_matrix_inverse_covariance(golden_dir):
+    """`covariance_mat_inv @ residual` for a 2-D inverse covariance (likelihood/_target.py:150-151) against values
+    recorded from the unmodified reference (tests/golden/make_cov_matrix.py)."""
+    g = np.load(os.path.join(golden_dir, "cov_matrix.npz"))
+    for case in range(int(g["n_cases"])):
+        cov, dobs, dp = g[f"c{case}_cov_inv"], g[f"c{case}_dobs"], g[f"c{case}_dpred"]
+        got = [OK.misfit_and_logdet(dp[i], dobs, cov_inv=cov) for i in range(2)]
+        np.testing.assert_allclose([v[0] for v in got], g[f"c{case}_misfit"], rtol=RTOL)
+        np.testing.assert_array_equal([v[1] for v in got], g[f"c{case}_logdet"])
+        np.testing.assert_allclose(OK.log_like_ratio(got[0][0], got[0][1], got[1][0], got[1][1], 1.7),
+                                   float(g[f"c{case}_ratio_T1p7"]), rtol=1e-11, atol=1e-13)
+
+
 def test_tomography_forward(kg):
     spec = problems.spec_from_ingredients(problems.tomo_small())
     dpred, _ = OK.tomography_forward(spec["targets"][0]["forward"], kg["fw_sites"], kg["fw_vel"])
