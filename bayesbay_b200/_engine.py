@@ -642,6 +642,71 @@ class Engine:
         self._steps_since_sync += 1
         return int(up.value), int(down.value)
 
+    # ---- mapped hosted step: fixed-stride records in pinned host memory, moved by the chain kernel itself
+    def hosted_record_words(self) -> int:
+        n = int(self.lib.bbb_engine_hosted_record_words(self._handle))
+        if n < 0:
+            raise RuntimeError("bbb_engine_hosted_record_words failed")
+        return n
+
+    def pack_states_records(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Current states of all chains as records ``[C][hosted_record_words()]`` of int64 words (device tensor, or a
+        pinned host tensor the kernel writes directly; words behind a chain's cells in use are left as they are)."""
+        if out is None:
+            out = torch.zeros((self.C, self.hosted_record_words()), dtype=torch.int64, device=self.device)
+        L.check(self.lib.bbb_engine_pack_states_records(self._handle, C.c_void_p(out.data_ptr()), self._stream))
+        return out
+
+    def decode_records(self, image: torch.Tensor):
+        """Per chain ``dict(k=[..], cells=[array [k][ndim + n_params] per space], header=int64 words)`` from a record
+        image on the host (what a caller holding the chains reads)."""
+        rw = self.hosted_record_words()
+        img = image.view(self.C, rw)
+        n_sp = len(self.spec["spaces"])
+        n_noise = sum((2 if tg.get("correlated") else 1) for tg in self.spec["targets"] if tg["hierarchical"])
+        hrw = n_sp + n_noise + 2
+        out, base = [], hrw
+        bases = []
+        for sp in self.spec["spaces"]:
+            bases.append(base)
+            base += sp["kmax"] * (sp["ndim"] + len(sp["params"]))
+        for c in range(self.C):
+            rec = img[c]
+            ks = [int(rec[s]) for s in range(n_sp)]
+            cells = []
+            for s, sp in enumerate(self.spec["spaces"]):
+                w = sp["ndim"] + len(sp["params"])
+                cells.append(rec[bases[s]: bases[s] + ks[s] * w].view(torch.float64).numpy().reshape(ks[s], w).copy())
+            out.append(dict(k=ks, cells=cells, header=rec[:hrw].clone()))
+        return out
+
+    def step_hosted_mapped(self, host_in: torch.Tensor, host_out: torch.Tensor):
+        """Enqueue ONE iteration on the chains whose records are in the pinned host tensor ``host_in``; the chain kernel
+        reads them from and writes the new records to host memory (``host_out``) itself."""
+        if not (host_in.is_pinned() and host_out.is_pinned()):
+            raise ValueError("hosted images must live in pinned host memory")
+        if min(host_in.numel(), host_out.numel()) < self.C * self.hosted_record_words():
+            raise ValueError("hosted image buffers too small")
+        if self._steps_since_sync >= self.K_BOUND_RESYNC_LOCAL:
+            self.sync_k_bound()
+        L.check(self.lib.bbb_engine_step_hosted_mapped(self._handle, C.c_void_p(host_in.data_ptr()), C.c_void_p(host_out.data_ptr()),
+                                                       self._stream))
+        self._steps_since_sync += 1
+
+    def step_hosted_mapped_wait(self) -> int:
+        """Block until the mapped hosted step is done; returns the number of chains that had to be redone (0: fast path)."""
+        n = C.c_int32(0)
+        L.check(self.lib.bbb_engine_step_hosted_mapped_wait(self._handle, C.byref(n), self._stream))
+        if n.value:
+            self._steps_since_sync = 1 << 30
+        return int(n.value)
+
+    def hosted_mapped_bytes(self):
+        """Bytes the mapped hosted steps have read from / written to host memory so far."""
+        up, down = C.c_int64(0), C.c_int64(0)
+        L.check(self.lib.bbb_engine_hosted_mapped_bytes(self._handle, C.byref(up), C.byref(down)))
+        return int(up.value), int(down.value)
+
     def step_hosted_wait(self) -> int:
         """Wait for the hosted step; returns the number of parts whose caches had to be re-derived (0: fast path)."""
         n = C.c_int32(0)

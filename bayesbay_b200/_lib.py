@@ -124,6 +124,11 @@ SYMBOLS = {
     "bbb_engine_step_hosted": (C.c_int, [_vp, C.POINTER(_i32), _vp, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
     "bbb_engine_step_hosted_wait": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
     "bbb_engine_hosted_ragged_bytes": (_i64, [_vp]),
+    "bbb_engine_hosted_record_words": (_i64, [_vp]),
+    "bbb_engine_pack_states_records": (C.c_int, [_vp, _vp, _vp]),
+    "bbb_engine_step_hosted_mapped": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bbb_engine_step_hosted_mapped_wait": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
+    "bbb_engine_hosted_mapped_bytes": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "bbb_engine_pack_states_ragged": (C.c_int, [_vp, _vp, _vp]),
     "bbb_engine_step_hosted_ragged": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "bbb_engine_dpred": (C.c_int, [_vp, C.c_int, _vp, _vp]),

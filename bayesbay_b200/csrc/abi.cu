@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 
+#include "hosted.cuh"
 #include "kernels.h"
 
 using namespace bbb;
@@ -112,6 +113,20 @@ struct bbb_engine {
     // parts of the hosted step (BBB_HOSTED_PARTS, default 2) and their streams
     int hosted_np;
     cudaStream_t hosted_stream[4];
+    // mapped hosted step (bbb_engine_step_hosted_mapped): per-chain mismatch flags and byte counters on the device, a
+    // mapped pinned word the kernel raises on a mismatch, the event the wait blocks on (recorded right behind the chain
+    // kernel: the proposal of the NEXT iteration and a periodic re-evaluation are enqueued behind it and overlap the
+    // host's turn-around).  spec_valid: the proposal of the next iteration has been drawn from the resident states and
+    // nothing has touched the engine since (every entry point clears it through NEED_BOUND).
+    int32_t *mapped_mismatch, *mapped_flag_host;
+    unsigned long long *mapped_moved;
+    cudaEvent_t ev_mapped_done;
+    bool spec_valid;
+    struct {
+        bool pending;
+        const void *host_in;
+        void *host_out;
+    } mapped;
 };
 
 // the cached graphs hold the engine parameters BY VALUE: whatever changes them drops the graphs
@@ -375,6 +390,12 @@ void bbb_engine_destroy(bbb_engine *e) {
     if (e->run_ctl) cudaFree(e->run_ctl);
     if (e->hosted_flag_dev) cudaFree(e->hosted_flag_dev);
     if (e->hosted_flag_host) cudaFreeHost(e->hosted_flag_host);
+    if (e->mapped_mismatch) {
+        cudaFree(e->mapped_mismatch);
+        cudaFree(e->mapped_moved);
+        cudaFreeHost(e->mapped_flag_host);
+        cudaEventDestroy(e->ev_mapped_done);
+    }
     cudaFree(e->dev);
     delete e;
 }
@@ -484,6 +505,7 @@ static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool wri
     do {                                                                               \
         if (!(e)) return fail(BBB_ERR_INVALID, "NULL engine");                         \
         if (!(e)->bound) return fail(BBB_ERR_SHAPE, "bbb_engine_bind_buffers not called"); \
+        (e)->spec_valid = false;                                                       \
         CU(cudaSetDevice((e)->device));                                                \
     } while (0)
 
@@ -1201,6 +1223,154 @@ int bbb_engine_step_hosted_wait(bbb_engine *e, int32_t *n_redone, void *stream) 
                            (size_t)sh.out_words[h] * 8, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
+    return BBB_OK;
+}
+
+// ---- mapped hosted step (hosted.cuh): records in pinned host memory, read and written by the chain kernel itself ----
+static HostedIO mapped_layout(const bbb_engine *e) {
+    const bbb_problem_spec &P = e->host.spec;
+    HostedIO io{};
+    io.hrw = ragged_header_rows(e->host);
+    long long off = io.hrw;
+    for (int s = 0; s < P.n_spaces; ++s) {
+        io.base[s] = (int)off;
+        off += (long long)P.spaces[s].kmax * (P.spaces[s].ndim + P.spaces[s].n_params);
+    }
+    io.stride = (off + 15) & ~15LL;  // records start on 128-byte lines
+    return io;
+}
+static int mapped_init(bbb_engine *e) {
+    if (e->mapped_mismatch != nullptr) return BBB_OK;
+    const long long C = e->host.buf.n_chains;
+    CU(cudaMalloc(&e->mapped_mismatch, (size_t)C * sizeof(int32_t)));
+    CU(cudaMemset(e->mapped_mismatch, 0, (size_t)C * sizeof(int32_t)));
+    CU(cudaMalloc(&e->mapped_moved, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(e->mapped_moved, 0, 2 * sizeof(unsigned long long)));
+    CU(cudaHostAlloc(&e->mapped_flag_host, 16 * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    e->mapped_flag_host[0] = 0;
+    CU(cudaEventCreateWithFlags(&e->ev_mapped_done, cudaEventDisableTiming));
+    return BBB_OK;
+}
+
+int64_t bbb_engine_hosted_record_words(bbb_engine *e) {
+    if (!e || !e->bound) return -1;
+    return mapped_layout(e).stride;
+}
+
+int bbb_engine_pack_states_records(bbb_engine *e, void *image, void *stream) {
+    NEED_BOUND(e);
+    if (!image) return fail(BBB_ERR_INVALID, "image is NULL");
+    HostedIO io = mapped_layout(e);
+    io.out = reinterpret_cast<unsigned long long *>(image);
+    CU(launch_hosted_pack(e->host, io, (cudaStream_t)stream));
+    return BBB_OK;
+}
+
+int bbb_engine_step_hosted_mapped(bbb_engine *e, const void *host_in, void *host_out, void *stream) {
+    const bool spec = e != nullptr && e->spec_valid;
+    NEED_BOUND(e);
+    if (!e->host.chain_local) return fail(BBB_ERR_UNSUPPORTED, "the hosted step needs a chain-local engine (2-D ray target)");
+    if (e->hosted.pending || e->mapped.pending) return fail(BBB_ERR_INVALID, "the previous hosted step was not waited for");
+    if (e->host.buf.tape != nullptr) return fail(BBB_ERR_UNSUPPORTED, "tape-driven engines use bbb_engine_step_hosted");
+    if (!host_in || !host_out) return fail(BBB_ERR_INVALID, "NULL argument");
+    if (host_in == host_out) return fail(BBB_ERR_INVALID, "in and out images must be different buffers");
+    // the kernel reaches the images through their device aliases (the same addresses under unified addressing)
+    const void *dev_alias[2] = {nullptr, nullptr};
+    {
+        const void *ptrs[2] = {host_in, host_out};
+        for (int i = 0; i < 2; ++i) {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) {
+                (void)cudaGetLastError();
+                return fail(BBB_ERR_INVALID, "hosted images must live in pinned (page-locked, device-mapped) host memory");
+            }
+            dev_alias[i] = at.devicePointer;
+        }
+    }
+    if (int rc = mapped_init(e)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_target_spec &T = P.targets[e->ray_t];
+    const long long C = e->host.buf.n_chains;
+    HostedIO io = mapped_layout(e);
+    io.in = reinterpret_cast<const unsigned long long *>(dev_alias[0]);
+    io.out = reinterpret_cast<unsigned long long *>(const_cast<void *>(dev_alias[1]));
+    io.mismatch = e->mapped_mismatch;
+    io.host_flag = e->mapped_flag_host;
+    io.moved = e->mapped_moved;
+    // the proposal of this iteration: drawn behind the previous hosted call (counter-based generators make it a pure
+    // function of the resident states), unless something touched the engine in between
+    if (!spec) CU(run_propose(e, st));
+    CU(launch_chain_step(e->host, 0, C, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax, idx_bytes_of(P, e->ray_t),
+                         e->order_pending[0] ? e->order_parity[0] * 4 : -1, !spec && e->dependent_launch >= 1, nullptr, st, &io));
+    CU(cudaEventRecord(e->ev_mapped_done, st));  // what the wait blocks on
+    if (e->order_pending[0]) { e->order_parity[0] ^= 1; e->order_pending[0] = false; }
+    bump_k_bound(e, 1);
+    ++e->steps_since_resync;
+    if (e->resync_every > 0 && e->steps_since_resync >= e->resync_every) CU(chain_local_from_scratch(e, false, st));
+    CU(run_propose(e, st));  // next iteration's proposal, behind the event: it overlaps the host's turn-around
+    e->spec_valid = true;
+    e->mapped.pending = true;
+    e->mapped.host_in = dev_alias[0];
+    e->mapped.host_out = const_cast<void *>(dev_alias[1]);
+    return BBB_OK;
+}
+
+int bbb_engine_step_hosted_mapped_wait(bbb_engine *e, int32_t *n_redone, void *stream) {
+    const bool spec = e != nullptr && e->spec_valid;
+    NEED_BOUND(e);
+    if (!e->mapped.pending) return fail(BBB_ERR_INVALID, "no mapped hosted step pending");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaEventSynchronize(e->ev_mapped_done));
+    e->mapped.pending = false;
+    e->spec_valid = spec;
+    if (n_redone) *n_redone = 0;
+    if (*reinterpret_cast<volatile int32_t *>(e->mapped_flag_host) == 0) return BBB_OK;
+    // Chains whose uploaded record differed from the resident state were left untouched: write their records into the
+    // engine, re-derive the caches of all chains (for the others this is the periodic from-scratch re-evaluation),
+    // advance exactly those chains (their new records go to the out image) and draw the next proposals again.
+    e->mapped_flag_host[0] = 0;
+    const bbb_problem_spec &P = e->host.spec;
+    const bbb_target_spec &T = P.targets[e->ray_t];
+    const long long C = e->host.buf.n_chains;
+    CU(cudaStreamSynchronize(st));
+    if (n_redone) {
+        int32_t *flags = (int32_t *)malloc((size_t)C * sizeof(int32_t));
+        if (flags == nullptr) return fail(BBB_ERR_INVALID, "out of host memory");
+        const cudaError_t err = cudaMemcpy(flags, e->mapped_mismatch, (size_t)C * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        int n = 0;
+        for (long long c = 0; c < C && err == cudaSuccess; ++c) n += flags[c] != 0 ? 1 : 0;
+        free(flags);
+        CU(err);
+        *n_redone = n;
+    }
+    HostedIO io = mapped_layout(e);
+    io.in = reinterpret_cast<const unsigned long long *>(e->mapped.host_in);
+    io.out = reinterpret_cast<unsigned long long *>(e->mapped.host_out);
+    io.mismatch = e->mapped_mismatch;
+    io.host_flag = e->mapped_flag_host;
+    io.moved = e->mapped_moved;
+    io.only = e->mapped_mismatch;
+    CU(launch_hosted_unpack(e->host, io, st));
+    if (int rc = bbb_engine_refresh(e, stream)) return rc;
+    CU(launch_propose(e->host, 0, C, -1, nullptr, st));
+    // (the flags select the chains and are only raised by a chain whose record still differs -- which cannot happen now)
+    CU(launch_chain_step(e->host, 0, C, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax, idx_bytes_of(P, e->ray_t), -1, false,
+                         nullptr, st, &io));
+    CU(cudaMemsetAsync(e->mapped_mismatch, 0, (size_t)C * sizeof(int32_t), st));
+    CU(run_propose(e, st));
+    CU(cudaStreamSynchronize(st));
+    e->mapped_flag_host[0] = 0;
+    e->spec_valid = true;
+    return BBB_OK;
+}
+
+int bbb_engine_hosted_mapped_bytes(bbb_engine *e, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!e || !e->bound) return fail(BBB_ERR_INVALID, "NULL / unbound engine");
+    unsigned long long v[2] = {0, 0};
+    if (e->mapped_moved != nullptr) CU(cudaMemcpy(v, e->mapped_moved, sizeof(v), cudaMemcpyDeviceToHost));
+    if (h2d_bytes) *h2d_bytes = (int64_t)v[0];
+    if (d2h_bytes) *d2h_bytes = (int64_t)v[1];
     return BBB_OK;
 }
 

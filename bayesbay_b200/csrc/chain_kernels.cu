@@ -30,6 +30,7 @@
 #include <cstdlib>
 
 #include "finish.cuh"
+#include "hosted.cuh"
 #include "kernels.h"
 #include "propose.cuh"
 
@@ -232,9 +233,12 @@ __device__ __forceinline__ void fx_add4(unsigned lo_s, unsigned hi_s, const int 
 // FUSED: the body runs on the 480 workers of k_chain_run with the proposal handed over in shared memory (`rec`).
 // Returns what the accumulator planes hold afterwards: n >= 0 -- only the n rays listed in the touched-ray list (the
 // `prep` area) are non-zero; -1 -- anything; -2 -- untouched (still zero).
-template <typename IdxT, bool MULTI, bool FUSED>
+// HOSTED: the mapped hosted step (hosted.cuh) -- the chain's uploaded record is read from pinned host memory and
+// compared with the resident state before anything is committed (a chain that differs is flagged and left untouched),
+// and the new state is written to the chain's record of the out image.
+template <typename IdxT, bool MULTI, bool FUSED, bool HOSTED = false>
 __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, long long c, const int32_t *guard,
-                                               unsigned char *cs_smem, ItemRec *rec) {
+                                               unsigned char *cs_smem, ItemRec *rec, const HostedIO &io) {
     constexpr int NW = FUSED ? CS_MAIN_WARPS : CS_WARPS;  // warps in the body
     constexpr int NTH = NW * 32;
     const bbb_problem_spec &P = ep.spec;
@@ -276,7 +280,26 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
         k_old = cur ? k_slot1 : k_slot0; k_new = cur ? k_slot0 : k_slot1;
         // hosted step: stale caches (see k_propose) -- the whole launch is a no-op
         if (guard != nullptr && *guard != 0) return -2;
+        if constexpr (HOSTED) {
+            if (io.only != nullptr && io.only[c] == 0) return -2;  // redo pass: only the flagged chains
+        }
         if (!target_touched(P, move, lpr, t)) {  // noise move, other space, or rejected by the prior: no forward
+            if constexpr (HOSTED) {
+                const int words_in = hosted_words_in_use(ep, io, c);
+                if (__syncthreads_or(hosted_compare(ep, io, c, tid, CS_THREADS) ? 1 : 0)) {
+                    if (tid == 0) { io.mismatch[c] = 1; *io.host_flag = 1; }
+                    return -2;
+                }
+                if (tid == 0) {
+                    Rng rng;
+                    rng_begin(rng, ep, c, STREAM_STEP, true);
+                    finish_chain(ep, c, rng);
+                    rng_end(rng, ep, c);
+                }
+                __syncthreads();
+                hosted_write(ep, io, c, tid, CS_THREADS, words_in);
+                return -2;
+            }
             if (tid == 0) {
                 Rng rng;
                 rng_begin(rng, ep, c, STREAM_STEP, true);
@@ -287,6 +310,14 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
             return -2;
         }
         if (tid == CS_THREADS - 1) finish_gather(ep, c, s_fin);  // thread 0 decides from these after the forward
+    }
+    int h_words = 0;
+    if constexpr (HOSTED) {
+        // the uploaded record is requested now (one 128-byte line per thread, into the L2) and compared after the
+        // first rasterisation pass, so that the trip over the bus overlaps the pass
+        h_words = hosted_words_in_use(ep, io, c);
+        const unsigned long long *line = io.in + c * io.stride + 16 * tid;
+        if (16 * tid < io.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
     }
     const int prop = cur ^ 1;
     (void)move;
@@ -447,6 +478,8 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
         // queue item: group << 17 | reach << 16 | mask of the points that lost their owner
         if (scn || reach) queue_at(atomicAdd(&s_back, 1)) = ((unsigned)(g0 >> 4) << 17) | (reach ? 1u << 16 : 0u) | scn;
     }
+    bool h_bad = false;
+    if constexpr (HOSTED) h_bad = hosted_compare(ep, io, c, tid, CS_THREADS);
     CS_TL(10);
     cs_sync<FUSED>();
     CS_TL(2);
@@ -759,6 +792,13 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
     CS_TL(6);
 
     // ---- likelihood ratio, decision, statistics (thread 0), then the commit by the whole block ----------------
+    if constexpr (HOSTED) {
+        // the uploaded state differs from the one the caches belong to: nothing is decided, nothing committed
+        if (__syncthreads_or(h_bad ? 1 : 0)) {
+            if (tid == 0) { io.mismatch[c] = 1; *io.host_flag = 1; }
+            return -1;
+        }
+    }
     if (tid == 0) s_accept = finish_post(ep, c, fin, pre, t, finite ? fin.phi_old[t].s0 + dphi : NAN) ? 1 : 0;
     cs_sync<FUSED>();
     CS_TL(7);
@@ -770,7 +810,10 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
     }
     CS_TL_G(17);
     const int planes = MULTI ? -1 : n_touch;
-    if (!s_accept) return planes;
+    if (!s_accept) {
+        if constexpr (HOSTED) hosted_write(ep, io, c, tid, CS_THREADS, h_words);
+        return planes;
+    }
 
     if (!MULTI && n_touch >= 0) {
         for (int i = tid; i < n_touch; i += NTH) {
@@ -825,6 +868,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
         const IdxT owner = (IdxT)((pk & CS_BACK) ? (pk & CS_M_MASK) : (unsigned)ins);
         for (int q = 0; q < (1 << (2 * lvl)); ++q) row[g_first + q] = owner;
     }
+    if constexpr (HOSTED) hosted_write(ep, io, c, tid, CS_THREADS, h_words);
     CS_TL(8);
     CS_TL_G(17);
     return planes;
@@ -834,9 +878,10 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
 // counter (the 16th word of the launch's block-order class counts, zeroed by the proposal kernel) in longest-first
 // order; measured SLOWER than letting the hardware dispatch one block per chain (chain kernel 0.111 vs 0.103 ms: the
 // atomic, two more barriers per chain and the in-loop zeroing cost more than the block dispatch they replace).
-template <typename IdxT, bool MULTI>
+template <typename IdxT, bool MULTI, bool HOSTED>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
-                                                              int order_slot, const int32_t *guard, int n_launch) {
+                                                              int order_slot, const int32_t *guard, int n_launch,
+                                                              const __grid_constant__ HostedIO io) {
     const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
     const int tid = threadIdx.x;
@@ -891,7 +936,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             for (int i = 1; i < BBB_ORDER_BUCKETS; ++i) cls += b >= s_cum[i] ? 1 : 0;
             c = B.block_order[(long long)cls * C + c_first + (b - s_cum[cls])];
         }
-        chain_step_body<IdxT, MULTI, false>(ep, t, c, guard, cs_smem, nullptr);
+        chain_step_body<IdxT, MULTI, false, HOSTED>(ep, t, c, guard, cs_smem, nullptr, io);
         if (persistent) __syncthreads();
     }
 }
@@ -1146,7 +1191,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_run(const __grid_consta
                 cs_sync<true>();  // (everyone has read the position before its next use)
                 continue;
             }
-            const int planes = chain_step_body<IdxT, MULTI, true>(ep, t, c, nullptr, cs_smem, rec);
+            const int planes = chain_step_body<IdxT, MULTI, true>(ep, t, c, nullptr, cs_smem, rec, HostedIO{});
             const long long t2 = RS_CLK();
             // leave the planes zero for the next item: only the words this item touched, when the body listed them
             if (planes >= 0) {
@@ -1226,7 +1271,7 @@ extern "C" int bbb_debug_timeline_clear() {
 #endif
 
 int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, long long n_data, int K,
-                      int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard, cudaStream_t st) {
+                      int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard, cudaStream_t st, const HostedIO *hosted) {
     if (dev.buf.block_order == nullptr) order_slot = -1;
     // programmatic dependent launch behind the proposal kernel of the same stream (see the kernel's prologue)
     cudaLaunchAttribute attr[1];
@@ -1253,11 +1298,14 @@ int launch_chain_step(const EngineParams &dev, long long c_first, long long c_en
     auto launch = [&](auto kernel) -> int {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        return (int)cudaLaunchKernelEx(&cfg, kernel, dev, t, c_first, order_slot, guard, (int)n_launch);
+        return (int)cudaLaunchKernelEx(&cfg, kernel, dev, t, c_first, order_slot, guard, (int)n_launch, hosted != nullptr ? *hosted : HostedIO{});
     };
     int rc;
-    if (idx_bytes == 1) rc = multi ? launch(k_chain_step<uint8_t, true>) : launch(k_chain_step<uint8_t, false>);
-    else rc = multi ? launch(k_chain_step<uint16_t, true>) : launch(k_chain_step<uint16_t, false>);
+    if (hosted != nullptr) {
+        if (idx_bytes == 1) rc = multi ? launch(k_chain_step<uint8_t, true, true>) : launch(k_chain_step<uint8_t, false, true>);
+        else rc = multi ? launch(k_chain_step<uint16_t, true, true>) : launch(k_chain_step<uint16_t, false, true>);
+    } else if (idx_bytes == 1) rc = multi ? launch(k_chain_step<uint8_t, true, false>) : launch(k_chain_step<uint8_t, false, false>);
+    else rc = multi ? launch(k_chain_step<uint16_t, true, false>) : launch(k_chain_step<uint16_t, false, false>);
     if (rc != 0) return rc;
     return (int)cudaGetLastError();
 }

@@ -64,9 +64,10 @@ int spmm_ray_groups(int R, long long C, int K, int idx_bytes, int n_sm);
 
 // chain_kernels.cu
 long long chain_local_tile_rays(long long n_data, int kmax, long long n_points);
+struct HostedIO;  // hosted.cuh: the mapped hosted step (records in pinned host memory read / written by the kernel)
 int launch_chain_step(const EngineParams &host_params, long long c_first, long long c_end, int target, int tile_rays,
                       long long n_data, int K, int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const HostedIO *hosted = nullptr);
 long long chain_run_ctl_words(long long n_chains_engine);
 // the fused persistent run (k_chain_run): n_iters iterations of the chains [c_first, c_end) in one launch of n_blocks
 // blocks; ctl = chain_run_ctl_words(n_chains of the engine) int32 control words, zero before the launch (left zero by it)
@@ -100,6 +101,9 @@ int launch_state_image(const EngineParams &host_params, int mode, const int32_t 
 int ragged_header_rows(const EngineParams &host_params);
 int launch_state_image_ragged(const EngineParams &host_params, int mode, void *image, int32_t *differ, long long c_first,
                               long long c_end, cudaStream_t stream);
+// records of the mapped hosted step (hosted.cuh): all chains -> io.out; flagged chains of io.in -> engine slot 0
+int launch_hosted_pack(const EngineParams &host_params, const HostedIO &io, cudaStream_t stream);
+int launch_hosted_unpack(const EngineParams &host_params, const HostedIO &io, cudaStream_t stream);
 // save point: states + noise + temperature sections of the chain-major image (step_kernels.cu), d_pred of a chain-local
 // ray target from its resident residuals
 long long save_point_state_words(const EngineParams &host_params, const int32_t *kb);

@@ -2,6 +2,7 @@
 // thread-evaluable forwards, initialisation (I1), result gathering (O1), parallel-tempering swap
 // round (T1) and the small stand-alone parity kernels (F3, F4, L1-L3).
 #include "finish.cuh"
+#include "hosted.cuh"
 #include "kernels.h"
 #include "propose.cuh"
 
@@ -829,6 +830,65 @@ int launch_state_image(const EngineParams &p, int mode, const int32_t *kb, void 
     if (mode == 0) k_state_image<0><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
     else if (mode == 1) k_state_image<1><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
     else k_state_image<2><<<grid, 128, 0, st>>>(p, ir, img, differ, c_first, n_c);
+    return (int)cudaGetLastError();
+}
+// Records of the mapped hosted step (hosted.cuh): one warp per chain.  k_hosted_pack writes the CURRENT state of every
+// chain into its record of io.out; k_hosted_unpack writes the records of io.in whose chain is flagged in io.only into
+// slot 0 of the engine (the caller then re-derives the caches).
+__global__ void __launch_bounds__(256) k_hosted_pack(const __grid_constant__ EngineParams ep, const __grid_constant__ HostedIO io) {
+    const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= ep.buf.n_chains) return;
+    hosted_write(ep, io, c, threadIdx.x & 31, 32, 0);
+}
+__global__ void __launch_bounds__(256) k_hosted_unpack(const __grid_constant__ EngineParams ep, const __grid_constant__ HostedIO io) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    const long long C = B.n_chains;
+    const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= C || (io.only != nullptr && io.only[c] == 0)) return;
+    const unsigned long long *rec = io.in + c * io.stride;
+    for (int s = 0; s < P.n_spaces; ++s) {
+        const bbb_space_spec &S = P.spaces[s];
+        long long kv = (long long)rec[s];
+        kv = kv < S.kmin ? S.kmin : (kv > S.kmax ? S.kmax : kv);  // (a record the host filled with nonsense cannot index outside the arrays)
+        const int w = S.ndim + S.n_params;
+        for (int i = lane; i < (int)kv * w; i += 32) {
+            const int j = i / w, q = i - j * w;
+            const double v = __longlong_as_double((long long)rec[io.base[s] + i]);
+            if (q < S.ndim) site_ref(B, S, s, 0, q, j, c) = v;
+            else value_ref(B, S, s, 0, q - S.ndim, j, c) = v;
+        }
+        if (lane == 0) {
+            k_ref(B, s, 0, c) = (int)kv;
+            k_ref(B, s, 1, c) = (int)kv;
+            B.sel[s][c] = 0;
+        }
+    }
+    if (lane == 0) {
+        int i = P.n_spaces;
+        for (int t = 0; t < P.n_targets; ++t) {
+            const bbb_target_spec &T = P.targets[t];
+            if (T.cov_kind != BBB_COV_HIERARCHICAL) continue;
+            const double sg = __longlong_as_double((long long)rec[i++]);
+            B.sigma[t][c] = sg;
+            B.sigma[t][C + c] = sg;
+            if (T.correlated) {
+                const double rho = __longlong_as_double((long long)rec[i++]);
+                B.corr[t][c] = rho;
+                B.corr[t][C + c] = rho;
+            }
+        }
+        B.temperature[c] = __longlong_as_double((long long)rec[i++]);
+        B.iteration[c] = (int64_t)rec[i];
+    }
+}
+int launch_hosted_pack(const EngineParams &p, const HostedIO &io, cudaStream_t st) {
+    k_hosted_pack<<<blocks_for(p.buf.n_chains, 8), 256, 0, st>>>(p, io);
+    return (int)cudaGetLastError();
+}
+int launch_hosted_unpack(const EngineParams &p, const HostedIO &io, cudaStream_t st) {
+    k_hosted_unpack<<<blocks_for(p.buf.n_chains, 8), 256, 0, st>>>(p, io);
     return (int)cudaGetLastError();
 }
 int ragged_header_rows(const EngineParams &p) {

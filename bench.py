@@ -340,6 +340,7 @@ def cuda_arm(args):
 
     # ---- end to end through the plugin call with HOST buffers ----------------------------------------------
     e2e = e2e_run(eng, args.steps, device, world, dist if world > 1 else None)
+    e2e_copy = e2e_copy_engine_run(eng, args.steps, device) if world == 1 else None
 
     # ---- the other BASELINE configurations (every N; weak scaling: the per-GPU work is fixed) ---------------
     configs = other_configs(ctx, args)
@@ -384,6 +385,7 @@ def cuda_arm(args):
         "step_ms_min_median_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
         "clocks": {k: clk[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clk else None,
         "e2e": e2e,
+        **({"e2e_copy_engine": e2e_copy} if e2e_copy is not None else {}),
         "gpu_launches": (2 if eng.chain_local else 6) * args.steps + (3 * n_swaps if tempered_main else 0),
         "step_kind": "chain-local (k_propose, k_chain_step)" if eng.chain_local
         else "full SpMM (k_propose, k_idx_commit_copy, k_raster2d_inc, k_raster2d_rescan, k_ray_spmm, k_finish)",
@@ -527,41 +529,37 @@ def api_run(par, ll, bb, n_chains, n_iterations=2000, save_every=100):
 
 
 def e2e_run(eng, steps, device, world, dist):
-    """The plugin call with HOST buffers, one iteration per call (bbb_engine_step_hosted_ragged + _wait): the chains' states
-    (k, sites, values, noise sigma, temperature, iteration) go pinned host -> device, the chains advance one
-    iteration, the updated states come back device -> host and the host waits for them.  The chain set travels in
-    parts on the engine's internal streams, so one part's copies overlap the other parts' kernels.  The derived
-    per-chain caches (nearest-site index, residuals, misfit) stay resident on the device between calls and are used
-    only after the uploaded states were compared, on the device, with the states the caches belong to
-    (bit-identical -> the part's kernels run; else they are no-ops and the wait re-derives the caches with
-    bbb_engine_refresh and advances the part) -- the analogue of the d_pred / KD-tree caches the reference pickles
-    along with every chain."""
+    """The plugin call with HOST buffers, one iteration per call (bbb_engine_step_hosted_mapped + _wait): the chains'
+    states (k, sites, values, noise sigma, temperature, iteration) live in pinned host memory as fixed-stride records;
+    every chain's block of the chain kernel reads its record straight from host memory (host -> device over the bus),
+    compares it with the resident state its caches belong to, advances the chain one iteration and writes the new
+    record back to host memory (device -> host); the host waits for the step before the next call.  The derived
+    per-chain caches (nearest-site index, residuals, misfit) stay resident on the device between calls and are only
+    used for a chain whose uploaded record is bit-identical to the state they belong to (else the chain is left
+    untouched and the wait re-derives the caches with bbb_engine_refresh and advances it) -- the analogue of the
+    d_pred / KD-tree caches the reference pickles along with every chain.  Bytes per step are counted by the kernel
+    (header + the k cells in use of every chain, each way)."""
     import torch
 
-    cap = eng.hosted_ragged_words()
-    host = [torch.zeros((cap,), dtype=torch.int64, pin_memory=True) for _ in range(2)]  # the caller's chains, in / out
-    stage = torch.zeros((cap,), dtype=torch.int64, device=device)     # upload buffer
-    out = torch.zeros((cap,), dtype=torch.int64, device=device)       # download buffer
+    rw = eng.hosted_record_words()
+    host = [torch.zeros((eng.C, rw), dtype=torch.int64).pin_memory() for _ in range(2)]  # the caller's chains, in / out
     refreshed = [0]
-    moved = [0, 0]
 
-    host[0].copy_(eng.pack_states_ragged())
+    eng.pack_states_records(host[0])
     torch.cuda.synchronize(device)
     cur = 0
     kb = None
 
     def call(_, cur):
-        up, down = eng.step_hosted_ragged(host[cur], host[cur ^ 1], stage, out)
-        refreshed[0] += eng.step_hosted_wait()  # the host reads the step's result before the next call
-        moved[0] += up
-        moved[1] += down
+        eng.step_hosted_mapped(host[cur], host[cur ^ 1])
+        refreshed[0] += eng.step_hosted_mapped_wait()  # the host has the step's result before the next call
         return None
 
     for _ in range(3):
         kb = call(kb, cur)
         cur ^= 1
-    moved[0] = moved[1] = 0
     refreshed[0] = 0
+    moved0 = eng.hosted_mapped_bytes()
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -574,20 +572,51 @@ def e2e_run(eng, steps, device, world, dist):
     torch.cuda.synchronize(device)
     wall_ms = (time.perf_counter() - t0) * 1e3
     ms = e0.elapsed_time(e1)
+    moved = [b - a for a, b in zip(moved0, eng.hosted_mapped_bytes())]
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return {"value": world * eng.C * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": moved[0] // steps,
             "d2h_bytes_per_step": moved[1] // steps, "ms_per_step": ms / steps, "host_wall_ms_per_step": wall_ms / steps,
-            "cache_refreshes": refreshed[0], "parts": len(eng.hosted_parts()) - 1,
+            "cache_refreshes": refreshed[0],
             "k_mean": float(eng.gather_space(0)[0].double().mean().item()),
-            "what": "per call (bbb_engine_step_hosted_ragged + bbb_engine_step_hosted_wait): RAGGED packed image of the chains' "
-                    "states in pinned host memory (k; sites and values of the k cells in use; sigma, temperature, iteration; "
-                    "copy sizes rounded up to 32 KiB) -> device, "
-                    "compared on the device with the resident states the caches belong to, one iteration, packed image -> "
-                    "pinned host memory, host waits; the chain set travels in parts on internal streams (copies of one part "
-                    "overlap the kernels of the others)"}
+            "what": "per call (bbb_engine_step_hosted_mapped + _wait): the chains' records (k; sites and values of the k cells "
+                    "in use; sigma, temperature, iteration) in pinned host memory are read by the chain kernel over the bus, "
+                    "compared with the resident states the caches belong to, advanced one iteration and written back to "
+                    "pinned host memory by the same kernel; the host waits for the step's result before the next call"}
+
+
+def e2e_copy_engine_run(eng, steps, device):
+    """The same round trip with copy-engine transfers (bbb_engine_step_hosted_ragged): ragged packed image pinned host ->
+    staging buffer, compared, proposal + chain kernel, packed, staging buffer -> pinned host, in parts on internal
+    streams.  For information (`e2e_copy_engine`)."""
+    import torch
+
+    cap = eng.hosted_ragged_words()
+    host = [torch.zeros((cap,), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    stage = torch.zeros((cap,), dtype=torch.int64, device=device)
+    out = torch.zeros((cap,), dtype=torch.int64, device=device)
+    host[0].copy_(eng.pack_states_ragged())
+    torch.cuda.synchronize(device)
+    moved, redone, cur = [0, 0], 0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(steps + 3):
+        if it == 3:
+            moved = [0, 0]
+            e0.record()
+        up, down = eng.step_hosted_ragged(host[cur], host[cur ^ 1], stage, out)
+        redone += eng.step_hosted_wait()
+        moved[0] += up
+        moved[1] += down
+        cur ^= 1
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    return {"value": eng.C * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "h2d_bytes_per_step": moved[0] // steps,
+            "d2h_bytes_per_step": moved[1] // steps, "cache_refreshes": redone, "parts": len(eng.hosted_parts()) - 1,
+            "what": "bbb_engine_step_hosted_ragged + _wait: copy-engine transfers of a ragged packed image through staging "
+                    "buffers, compare / proposal / chain / pack kernels per part on internal streams, replayed from CUDA graphs"}
 
 
 # --------------------------------------------------------------------------- #

@@ -325,6 +325,28 @@ int bbb_engine_step_hosted_wait(bbb_engine *e, int32_t *n_redone, void *stream);
  * rarely.  *h2d_bytes / *d2h_bytes (may be NULL) = bytes copied each way by this call.  All four buffers hold
  * bbb_engine_hosted_ragged_bytes() bytes.  The wait is bbb_engine_step_hosted_wait. */
 int64_t bbb_engine_hosted_ragged_bytes(bbb_engine *e);
+/* MAPPED hosted step: the same round trip with the chain kernel itself moving the states over the bus.  The caller's
+ * chains live in pinned (page-locked, device-mapped) host memory as fixed-stride RECORDS, chain c at word
+ * c * bbb_engine_hosted_record_words():
+ *   header: k of every space (int64) | sigma (and correlation) per hierarchical target | temperature | iteration (int64);
+ *   then per space s (room for kmax cells; only the k in use are read / written, so only they cross the bus):
+ *   cell j at (ndim + n_params) * j words into the space's block: site coordinates, then parameter values.
+ * bbb_engine_step_hosted_mapped: every chain's block reads its record of host_in straight from host memory (requested
+ * when the block starts, compared with the resident state the caches belong to before anything is decided), advances
+ * the chain one iteration and writes the new record to host_out -- no staging buffers, no copy-engine transfers, the
+ * traffic overlaps the step.  The proposal of the NEXT iteration is drawn behind the call (counter-based generators:
+ * a pure function of the resident state), so it overlaps the host's turn-around; any other call on the engine
+ * invalidates it and the next hosted call draws it again.  A chain whose record is not bit-identical to the resident
+ * state is left untouched and flagged; bbb_engine_step_hosted_mapped_wait (which blocks until the step is done) then
+ * writes those records into the engine, re-derives the caches (bbb_engine_refresh), advances exactly those chains and
+ * reports their number in *n_redone (0 on the fast path).  bbb_engine_pack_states_records writes the current states as
+ * records (image: device or mapped host memory of n_chains records).  bbb_engine_hosted_mapped_bytes: bytes the
+ * kernels have read from / written to host memory so far.  Not for tape-driven engines. */
+int64_t bbb_engine_hosted_record_words(bbb_engine *e);
+int bbb_engine_pack_states_records(bbb_engine *e, void *image, void *stream);
+int bbb_engine_step_hosted_mapped(bbb_engine *e, const void *host_in, void *host_out, void *stream);
+int bbb_engine_step_hosted_mapped_wait(bbb_engine *e, int32_t *n_redone, void *stream);
+int bbb_engine_hosted_mapped_bytes(bbb_engine *e, int64_t *h2d_bytes, int64_t *d2h_bytes);
 int bbb_engine_pack_states_ragged(bbb_engine *e, void *image, void *stream);
 int bbb_engine_step_hosted_ragged(bbb_engine *e, const void *host_in, void *host_out, void *dev_stage, void *dev_out,
                                   int64_t *h2d_bytes, int64_t *d2h_bytes, void *stream);

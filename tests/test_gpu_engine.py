@@ -708,6 +708,104 @@ def test_hosted_step_ragged_image(monkeypatch, pipeline, graph):
         eng.step_hosted_ragged(dst, dst, stage, out)
 
 
+def test_hosted_step_mapped_records(monkeypatch):
+    """bbb_engine_step_hosted_mapped: the chains live in pinned host memory as fixed-stride records which the chain
+    kernel reads and writes itself.  (a) The records decode to the chains' states; the fast path is bit-identical to
+    resident stepping over 300 iterations (incl. a from-scratch re-evaluation) and never redone; only the cells in use
+    cross the bus.  (b) Other engine calls between hosted calls (resident steps) are allowed.  (c) Edited chains are
+    detected, exactly they are redone, every chain advances once.  (d) Bad arguments are refused."""
+    from bayesbay_b200 import synthetic
+
+    ing = synthetic.tomography_2d(nx=32, ny=32, n_sources_per_side=5, n_receivers=12, kmin=4, kmax=60)
+    spec = problems.spec_from_ingredients(ing)
+    n = 148 + 37
+    ref, eng = _engine(spec, n, seed=5), _engine(spec, n, seed=5)
+    for e in (ref, eng):
+        e.init_states()
+        e.step(20)
+    rw = eng.hosted_record_words()
+    host = [torch.zeros((n, rw), dtype=torch.int64).pin_memory() for _ in range(2)]
+    eng.pack_states_records(host[0])  # (the kernel writes the pinned tensor directly)
+    torch.cuda.synchronize()
+    assert torch.equal(host[0].cpu(), _records_in_use(eng, eng.pack_states_records().cpu(), host[0]))
+
+    def check_against_engine(e, image):
+        got = e.decode_records(image)
+        k, sites, vals = (v.cpu().numpy() for v in e.gather_space(0))
+        sig, temp, it = e.sigma[0][0].cpu().numpy(), e.temperature.cpu().numpy(), e.iteration.cpu().numpy()
+        for c, d in enumerate(got):
+            kc, cells, h = d["k"][0], d["cells"][0], d["header"]
+            assert kc == k[c] and h[1:2].view(torch.float64).item() == sig[c] and h[2:3].view(torch.float64).item() == temp[c]
+            assert int(h[3]) == it[c]
+            assert np.array_equal(cells[:, 0], sites[0, :kc, c]) and np.array_equal(cells[:, 1], sites[1, :kc, c])
+            assert np.array_equal(cells[:, 2], vals[0, :kc, c])
+
+    check_against_engine(eng, host[0])
+    n_steps = 300
+    for it in range(n_steps):
+        eng.step_hosted_mapped(host[it & 1], host[(it + 1) & 1])
+        assert eng.step_hosted_mapped_wait() == 0
+        ref.step(1)
+    last = host[n_steps & 1]
+    check_against_engine(eng, last)
+    assert torch.equal(eng.res[0], ref.res[0]) and torch.equal(eng.idx_cm[0], ref.idx_cm[0])
+    assert torch.equal(eng.n_accepted, ref.n_accepted) and torch.equal(eng.pack_states(60), ref.pack_states(60))
+    up, down = eng.hosted_mapped_bytes()
+    assert 0 < up < n_steps * n * rw * 8 and 0 < down < n_steps * n * rw * 8  # only the cells in use travel
+
+    # (b) resident steps in between (they invalidate the proposal drawn ahead; the next hosted call draws it again)
+    eng.step(3)
+    ref.step(3)
+    eng.pack_states_records(last)
+    torch.cuda.synchronize()
+    eng.step_hosted_mapped(last, host[(n_steps + 1) & 1])
+    assert eng.step_hosted_mapped_wait() == 0
+    ref.step(1)
+    assert torch.equal(eng.pack_states(60), ref.pack_states(60)) and torch.equal(eng.res[0], ref.res[0])
+    cur = host[(n_steps + 1) & 1]
+    check_against_engine(eng, cur)
+
+    # (c) the caller edits the value of the first cell of two chains
+    base = 4  # header words: k, sigma, temperature, iteration
+    edited = [5, n - 3]
+    for c in edited:
+        cur[c, base + 2:base + 3] = (cur[c, base + 2:base + 3].view(torch.float64) * 1.03125).view(torch.int64)
+    nxt = host[n_steps & 1]
+    eng.step_hosted_mapped(cur, nxt)
+    assert eng.step_hosted_mapped_wait() == len(edited)
+    assert (eng.iteration.cpu().numpy() == 20 + n_steps + 3 + 2).all()
+    check_against_engine(eng, nxt)
+    ref.step(1)
+    got, want = eng.decode_records(nxt), ref.decode_records(ref.pack_states_records().cpu())
+    for c in range(n):
+        if c not in edited:
+            assert got[c]["k"] == want[c]["k"] and np.array_equal(got[c]["cells"][0], want[c]["cells"][0])
+            assert torch.equal(got[c]["header"], want[c]["header"])
+    # the engine carries on from the edited states, caches consistent
+    eng.step_hosted_mapped(nxt, cur)
+    assert eng.step_hosted_mapped_wait() == 0
+    eng.step(10)
+    res_inc = eng.res[0].clone()
+    eng.resync()
+    np.testing.assert_allclose(eng.res[0].cpu().numpy(), res_inc.cpu().numpy(), rtol=0, atol=1e-9)
+    # (d) refused: same buffer twice, pageable memory
+    with pytest.raises(Exception):
+        eng.step_hosted_mapped(cur, cur)
+    with pytest.raises(Exception):
+        eng.step_hosted_mapped(cur, torch.zeros((n, rw), dtype=torch.int64))
+
+
+def _records_in_use(eng, records, like):
+    """`records` with the words behind every chain's cells in use taken from `like` (a pack leaves them untouched)."""
+    out = like.clone()
+    rw = eng.hosted_record_words()
+    k = records[:, 0]
+    for c in range(records.shape[0]):
+        n = 4 + 3 * int(k[c])
+        out[c, :n] = records[c, :n]
+    return out.view(-1, rw)
+
+
 def test_exception_counters():
     """What the reference reports under statistics["exceptions"] (src/bayesbay/_markov_chain.py:205-247) has a device
     analogue: proposals with a non-finite likelihood ratio are rejected and counted; rejection-sampling loops that give
