@@ -644,9 +644,12 @@ class Engine:
 
     # ---- mapped hosted step: fixed-stride records in pinned host memory, moved by the chain kernel itself
     def hosted_record_words(self) -> int:
-        n = int(self.lib.bbb_engine_hosted_record_words(self._handle))
-        if n < 0:
-            raise RuntimeError("bbb_engine_hosted_record_words failed")
+        n = getattr(self, "_record_words", None)
+        if n is None:
+            n = int(self.lib.bbb_engine_hosted_record_words(self._handle))
+            if n < 0:
+                raise RuntimeError("bbb_engine_hosted_record_words failed")
+            self._record_words = n
         return n
 
     def pack_states_records(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -683,14 +686,17 @@ class Engine:
     def step_hosted_mapped(self, host_in: torch.Tensor, host_out: torch.Tensor):
         """Enqueue ONE iteration on the chains whose records are in the pinned host tensor ``host_in``; the chain kernel
         reads them from and writes the new records to host memory (``host_out``) itself."""
-        if not (host_in.is_pinned() and host_out.is_pinned()):
-            raise ValueError("hosted images must live in pinned host memory")
-        if min(host_in.numel(), host_out.numel()) < self.C * self.hosted_record_words():
-            raise ValueError("hosted image buffers too small")
+        a, b = host_in.data_ptr(), host_out.data_ptr()
+        checked = self.__dict__.setdefault("_mapped_checked", set())
+        if (a, b) not in checked:  # (buffers seen before were checked then; the library checks the pointers on every call)
+            if not (host_in.is_pinned() and host_out.is_pinned()):
+                raise ValueError("hosted images must live in pinned host memory")
+            if min(host_in.numel(), host_out.numel()) < self.C * self.hosted_record_words():
+                raise ValueError("hosted image buffers too small")
+            checked.add((a, b))
         if self._steps_since_sync >= self.K_BOUND_RESYNC_LOCAL:
             self.sync_k_bound()
-        L.check(self.lib.bbb_engine_step_hosted_mapped(self._handle, C.c_void_p(host_in.data_ptr()), C.c_void_p(host_out.data_ptr()),
-                                                       self._stream))
+        L.check(self.lib.bbb_engine_step_hosted_mapped(self._handle, a, b, self._stream))
         self._steps_since_sync += 1
 
     def step_hosted_mapped_wait(self) -> int:

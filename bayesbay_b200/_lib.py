@@ -14,7 +14,7 @@ MAX_PARAMS = 8
 MAX_TARGETS = 4
 MAX_LINEAR_PARAMS = 16
 CSC_LEVELS = 3
-ABI_VERSION = 5
+ABI_VERSION = 6
 ORDER_BUCKETS = 10
 
 SPACE_PLAIN, SPACE_VORONOI1D, SPACE_VORONOI2D = 0, 1, 2

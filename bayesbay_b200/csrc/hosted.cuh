@@ -20,6 +20,11 @@ struct HostedIO {
     int32_t *host_flag;            // mapped pinned word: set when some chain mismatched
     const int32_t *only;           // device [C] or nullptr: only chains with a non-zero word run (the redo pass)
     unsigned long long *moved;     // device [2]: bytes read from / written to host memory (statistics)
+    // developer switch BBB_MAPPED_PDL=1 (measured slower, see abi.cu): chain_done[c] = seq once chain c's new STATE is
+    // complete -- what the next proposal's warp for chain c then waits for, the proposal kernel being launched as this
+    // kernel's programmatic dependent
+    int32_t *chain_done;           // device [C] or nullptr
+    int seq;
     long long stride;              // words per record
     int hrw;                       // header words
     int base[BBB_MAX_SPACES];      // first cell word of each space
@@ -47,10 +52,11 @@ __device__ __forceinline__ unsigned long long hosted_cell_word(const bbb_buffers
 }
 
 // This thread's share (words tid, tid + nth, ...) of "uploaded record == resident current state"; true on a mismatch.
-__device__ __forceinline__ bool hosted_compare(const EngineParams &ep, const HostedIO &io, long long c, int tid, int nth) {
+// `rec`: the chain's uploaded record -- in host memory (io.in + c * io.stride) or its staged copy in shared memory.
+__device__ __forceinline__ bool hosted_compare(const EngineParams &ep, const HostedIO &io, const unsigned long long *rec, long long c, int tid,
+                                               int nth) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
-    const unsigned long long *rec = io.in + c * io.stride;
     bool bad = false;
     for (int i = tid; i < io.hrw; i += nth) bad |= rec[i] != hosted_header_word(P, B, c, i);
     for (int s = 0; s < P.n_spaces; ++s) {
@@ -78,6 +84,13 @@ __device__ __forceinline__ void hosted_write(const EngineParams &ep, const Hoste
         atomicAdd(io.moved, 8ull * (unsigned long long)words_in);
         atomicAdd(io.moved + 1, 8ull * (unsigned long long)words);
     }
+}
+// Completion signal of chain c's step (thread 0 of its block, right after the decision's last write of the chain's
+// STATE): released at device scope for the next iteration's proposal warp of the chain (k_propose, step_kernels.cu).
+__device__ __forceinline__ void hosted_signal_done(const HostedIO &io, long long c) {
+    if (io.chain_done == nullptr) return;
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(io.chain_done + c), "r"(io.seq) : "memory");
 }
 // words of chain c's record that are in use (header + the cells of every space), from the resident state
 __device__ __forceinline__ int hosted_words_in_use(const EngineParams &ep, const HostedIO &io, long long c) {

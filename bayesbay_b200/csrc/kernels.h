@@ -83,8 +83,10 @@ int launch_residual_transpose(const double *dpred, double *res, long long R, lon
 // problem spec and every buffer pointer is then a constant-bank read instead of a dependent global load)
 // order_slot = parity * 4 + part of the block-order class counts (common.cuh), -1: no block order
 // guard (device, may be NULL): a non-zero word makes the launch a no-op (hosted step, abi.cu)
+// wait_done != NULL: launched as the programmatic dependent of the hosted chain kernel in front of it; the warp of chain c
+// waits (bounded; *wait_failed is raised otherwise) until wait_done[c] == wait_seq
 int launch_propose(const EngineParams &host_params, long long c_first, long long c_end, int order_slot, const int32_t *guard,
-                   cudaStream_t stream);
+                   cudaStream_t stream, const int32_t *wait_done = nullptr, int wait_seq = 0, int32_t *wait_failed = nullptr);
 int launch_finish(const EngineParams &host_params, long long C, cudaStream_t stream);
 int launch_corr_sums(const EngineParams *dev_params, long long C, int target, int proposal, cudaStream_t stream);
 int launch_fused_steps(const EngineParams &host_params, long long C, long long n_steps, cudaStream_t stream);

@@ -38,7 +38,8 @@ __device__ __forceinline__ int block_cost_class(const EngineParams &ep, long lon
 }
 
 __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep, long long c_first, long long c_end,
-                                                                int order_slot, const int32_t *guard) {
+                                                                int order_slot, const int32_t *guard, const int32_t *wait_done, int wait_seq,
+                                                                int32_t *wait_failed) {
     // the chain kernel behind this launch may become resident now (it waits for this grid before it reads a proposal)
     asm volatile("griddepcontrol.launch_dependents;");
     // work counter of the (persistent) chain kernel behind this launch: the 16th word of the launch's class counts
@@ -49,6 +50,22 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_con
     // hosted step (bbb_engine_step_hosted): the uploaded states of this part differ from the resident ones, so the
     // caches are stale and nothing may be drawn or stepped until the host has re-derived them
     if (guard != nullptr && *guard != 0) return;
+    // Launched as the programmatic dependent of a hosted chain kernel (chain_kernels.cu): this warp may run while that
+    // grid's last blocks are still stepping, and waits for ITS chain's completion signal (released by the chain's block
+    // after the step's last write).  Bounded: a signal that never comes is reported, not waited for forever.
+    if (wait_done != nullptr) {
+        const int32_t *flag = wait_done + c;
+        int v = 0;
+        for (long long spin = 0; spin < (1LL << 24); ++spin) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == wait_seq) break;
+            __nanosleep(64);
+        }
+        if (v != wait_seq) {
+            if ((threadIdx.x & 31) == 0) *reinterpret_cast<volatile int32_t *>(wait_failed) = 1;
+            return;
+        }
+    }
     // the warp's generator: the first 32 draws of the (chain, iteration) computed by the lanes at once into shared memory
     __shared__ double s_draw[PROPOSE_WARPS][2][32];
     const bbb_buffers &B = ep.buf;
@@ -771,10 +788,25 @@ __global__ void k_phi_from_partial(const double *partial, int n_tiles, long long
 // ------------------------------------------------------------------------------------------------
 static inline int blocks_for(long long C, int threads) { return (int)((C + threads - 1) / threads); }
 
-int launch_propose(const EngineParams &p, long long c_first, long long c_end, int order_slot, const int32_t *guard, cudaStream_t st) {
+int launch_propose(const EngineParams &p, long long c_first, long long c_end, int order_slot, const int32_t *guard, cudaStream_t st,
+                   const int32_t *wait_done, int wait_seq, int32_t *wait_failed) {
     if (!p.chain_local || p.buf.block_order == nullptr) order_slot = -1;
-    k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end, order_slot, guard);
-    return (int)cudaGetLastError();
+    if (wait_done == nullptr) {
+        k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end, order_slot, guard, nullptr, 0, nullptr);
+        return (int)cudaGetLastError();
+    }
+    // programmatic dependent of the hosted chain kernel in front of it in `st` (per-chain completion signals)
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks_for(c_end - c_first, PROPOSE_WARPS));
+    cfg.blockDim = dim3(PROPOSE_WARPS * 32);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int rc = (int)cudaLaunchKernelEx(&cfg, k_propose, p, c_first, c_end, order_slot, guard, wait_done, wait_seq, wait_failed);
+    return rc != 0 ? rc : (int)cudaGetLastError();
 }
 int launch_corr_sums(const EngineParams *p, long long C, int target, int proposal, cudaStream_t st) {
     k_corr_sums<<<blocks_for(C, 128), 128, 0, st>>>(p, target, proposal);

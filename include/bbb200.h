@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BBB_ABI_VERSION 5
+#define BBB_ABI_VERSION 6
 #define BBB_ORDER_BUCKETS 10
 
 #define BBB_MAX_SPACES 4

@@ -708,15 +708,21 @@ def test_hosted_step_ragged_image(monkeypatch, pipeline, graph):
         eng.step_hosted_ragged(dst, dst, stage, out)
 
 
-def test_hosted_step_mapped_records(monkeypatch):
+@pytest.mark.parametrize("variant", ["one_tile_u8", "ray_tiles_u16"])
+def test_hosted_step_mapped_records(monkeypatch, variant):
     """bbb_engine_step_hosted_mapped: the chains live in pinned host memory as fixed-stride records which the chain
     kernel reads and writes itself.  (a) The records decode to the chains' states; the fast path is bit-identical to
     resident stepping over 300 iterations (incl. a from-scratch re-evaluation) and never redone; only the cells in use
     cross the bus.  (b) Other engine calls between hosted calls (resident steps) are allowed.  (c) Edited chains are
-    detected, exactly they are redone, every chain advances once.  (d) Bad arguments are refused."""
+    detected, exactly they are redone, every chain advances once.  (d) Bad arguments are refused.
+    Variants: one ray tile with a 1-byte nearest-site index; several ray tiles with a 2-byte index (n_dimensions_max > 256)."""
     from bayesbay_b200 import synthetic
 
-    ing = synthetic.tomography_2d(nx=32, ny=32, n_sources_per_side=5, n_receivers=12, kmin=4, kmax=60)
+    kmax = 60
+    if variant == "ray_tiles_u16":
+        monkeypatch.setenv("BBB_CHAIN_TILE_RAYS", "96")
+        kmax = 300
+    ing = synthetic.tomography_2d(nx=32, ny=32, n_sources_per_side=5, n_receivers=12, kmin=4, kmax=kmax)
     spec = problems.spec_from_ingredients(ing)
     n = 148 + 37
     ref, eng = _engine(spec, n, seed=5), _engine(spec, n, seed=5)
@@ -741,6 +747,7 @@ def test_hosted_step_mapped_records(monkeypatch):
             assert np.array_equal(cells[:, 2], vals[0, :kc, c])
 
     check_against_engine(eng, host[0])
+    assert eng.ray_tiles(0) == (1 if variant == "one_tile_u8" else 3) and eng.idx_cm[0].element_size() == (1 if kmax <= 256 else 2)
     n_steps = 300
     for it in range(n_steps):
         eng.step_hosted_mapped(host[it & 1], host[(it + 1) & 1])
@@ -749,7 +756,7 @@ def test_hosted_step_mapped_records(monkeypatch):
     last = host[n_steps & 1]
     check_against_engine(eng, last)
     assert torch.equal(eng.res[0], ref.res[0]) and torch.equal(eng.idx_cm[0], ref.idx_cm[0])
-    assert torch.equal(eng.n_accepted, ref.n_accepted) and torch.equal(eng.pack_states(60), ref.pack_states(60))
+    assert torch.equal(eng.n_accepted, ref.n_accepted) and torch.equal(eng.pack_states(kmax), ref.pack_states(kmax))
     up, down = eng.hosted_mapped_bytes()
     assert 0 < up < n_steps * n * rw * 8 and 0 < down < n_steps * n * rw * 8  # only the cells in use travel
 
@@ -761,7 +768,7 @@ def test_hosted_step_mapped_records(monkeypatch):
     eng.step_hosted_mapped(last, host[(n_steps + 1) & 1])
     assert eng.step_hosted_mapped_wait() == 0
     ref.step(1)
-    assert torch.equal(eng.pack_states(60), ref.pack_states(60)) and torch.equal(eng.res[0], ref.res[0])
+    assert torch.equal(eng.pack_states(kmax), ref.pack_states(kmax)) and torch.equal(eng.res[0], ref.res[0])
     cur = host[(n_steps + 1) & 1]
     check_against_engine(eng, cur)
 
