@@ -25,7 +25,7 @@ marks = {"tables: proposed": "tables", "change-local rasterisation: which": "ras
          "One block per chain.": "kernel entry (zeroing, dependency wait, block order)"}
 bounds, kstart = [], None
 for i, ln in enumerate(open(cu), 1):
-    if "void chain_step_body(const EngineParams &ep" in ln: kstart = i
+    if "chain_step_body(const EngineParams &ep" in ln and kstart is None: kstart = i
     for k, v in marks.items():
         if k in ln: bounds.append((i, v))
 bounds = [(kstart, "entry / gather")] + bounds
