@@ -371,11 +371,7 @@ class Engine:
         self._steps_since_sync = 0
         if not self._has_ray:
             return
-        for s, sp in enumerate(self.spec["spaces"]):
-            if sp["trans_d"]:
-                sel = self.sel[s].long()
-                kcur = torch.where(sel == 0, self.k[s][0], self.k[s][1])
-                L.check(self.lib.bbb_engine_set_k_bound(self._handle, s, int(kcur.max().item())))
+        L.check(self.lib.bbb_engine_sync_k_bound(self._handle, None, self._stream))  # (one reduction kernel + a 16-byte read-back)
 
     def stage(self, stage: int):
         """One stage of one step (0 propose, 1 raster, 2 ray forward + misfit, 3 accept)."""

@@ -123,6 +123,7 @@ SYMBOLS = {
     "bbb_engine_hosted_parts": (C.c_int, [_vp, C.POINTER(_i64)]),
     "bbb_engine_step_hosted": (C.c_int, [_vp, C.POINTER(_i32), _vp, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
     "bbb_engine_step_hosted_wait": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
+    "bbb_engine_sync_k_bound": (C.c_int, [_vp, C.POINTER(_i32), _vp]),
     "bbb_engine_hosted_ragged_bytes": (_i64, [_vp]),
     "bbb_engine_hosted_record_words": (_i64, [_vp]),
     "bbb_engine_pack_states_records": (C.c_int, [_vp, _vp, _vp]),

@@ -134,6 +134,18 @@ struct bbb_engine {
 };
 
 // the cached graphs hold the engine parameters BY VALUE: whatever changes them drops the graphs
+// resources of the mapped hosted step (sized by the bound chain count: dropped when buffers are bound again)
+static void mapped_drop(bbb_engine *e) {
+    if (e->mapped_mismatch == nullptr) return;
+    cudaFree(e->mapped_mismatch);
+    cudaFree(e->mapped_moved);
+    cudaFreeHost(e->mapped_flag_host);
+    cudaFree(e->mapped_chain_done);
+    cudaEventDestroy(e->ev_mapped_done);
+    e->mapped_mismatch = nullptr;
+    e->spec_valid = false;
+}
+
 static void hosted_graphs_drop(bbb_engine *e) {
     for (auto &row : e->step_graph)
         for (auto &g : row)
@@ -332,6 +344,7 @@ int bbb_engine_bind_buffers(bbb_engine *e, const bbb_buffers *b) {
     if (b->tape && b->tape_stride < 1) return fail(BBB_ERR_SHAPE, "tape_stride < 1");
     e->host.buf = *b;
     hosted_graphs_drop(e);
+    mapped_drop(e);
     for (int t = 0; t < P.n_targets; ++t) {
         e->host.n_partial[t] = 0;
         if (P.targets[t].fwd_kind != BBB_FWD_RAY2D) continue;
@@ -394,13 +407,7 @@ void bbb_engine_destroy(bbb_engine *e) {
     if (e->run_ctl) cudaFree(e->run_ctl);
     if (e->hosted_flag_dev) cudaFree(e->hosted_flag_dev);
     if (e->hosted_flag_host) cudaFreeHost(e->hosted_flag_host);
-    if (e->mapped_mismatch) {
-        cudaFree(e->mapped_mismatch);
-        cudaFree(e->mapped_moved);
-        cudaFreeHost(e->mapped_flag_host);
-        cudaFree(e->mapped_chain_done);
-        cudaEventDestroy(e->ev_mapped_done);
-    }
+    mapped_drop(e);
     cudaFree(e->dev);
     delete e;
 }
@@ -704,12 +711,47 @@ int bbb_engine_init_states(bbb_engine *e, void *stream) {
     return rc;
 }
 
+// true maximum of k over the resident chains of every space (device reduction, blocking read-back)
+static int measure_k_max(bbb_engine *e, int32_t *out, cudaStream_t st) {
+    int32_t *dev = nullptr;
+    CU(cudaMalloc(&dev, BBB_MAX_SPACES * sizeof(int32_t)));
+    int rc = (int)cudaMemsetAsync(dev, 0, BBB_MAX_SPACES * sizeof(int32_t), st);
+    if (rc == 0) rc = launch_max_k(e->dev, e->host.buf.n_chains, dev, st);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(out, dev, BBB_MAX_SPACES * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (rc != 0) return fail(BBB_ERR_CUDA, "measuring the largest k: %s", cudaGetErrorString((cudaError_t)rc));
+    return BBB_OK;
+}
+
 int bbb_engine_set_k_bound(bbb_engine *e, int space, int32_t bound) {
     if (!e) return fail(BBB_ERR_INVALID, "NULL engine");
     if (space < 0 || space >= e->host.spec.n_spaces) return fail(BBB_ERR_INVALID, "space index");
     const bbb_space_spec &S = e->host.spec.spaces[space];
     if (bound < S.kmin || bound > S.kmax) return fail(BBB_ERR_INVALID, "bound outside [kmin, kmax]");
+    if (e->bound) {  // a bound below the true maximum would let the ray kernel index outside its value table: refused
+        CU(cudaSetDevice(e->device));
+        int32_t kmax_now[BBB_MAX_SPACES] = {0};
+        if (int rc = measure_k_max(e, kmax_now, 0)) return rc;
+        if (bound < kmax_now[space])
+            return fail(BBB_ERR_INVALID, "space %d: bound %d is below the largest k of the resident chains (%d)", space, bound, kmax_now[space]);
+    }
     e->k_bound[space] = bound;
+    return BBB_OK;
+}
+
+int bbb_engine_sync_k_bound(bbb_engine *e, int32_t *bounds_out, void *stream) {
+    if (!e) return fail(BBB_ERR_INVALID, "NULL engine");
+    if (!e->bound) return fail(BBB_ERR_SHAPE, "bbb_engine_bind_buffers not called");
+    CU(cudaSetDevice(e->device));
+    int32_t kmax_now[BBB_MAX_SPACES] = {0};
+    if (int rc = measure_k_max(e, kmax_now, (cudaStream_t)stream)) return rc;
+    for (int s = 0; s < e->host.spec.n_spaces; ++s) {
+        const bbb_space_spec &S = e->host.spec.spaces[s];
+        int32_t b = kmax_now[s] < S.kmin ? S.kmin : (kmax_now[s] > S.kmax ? S.kmax : kmax_now[s]);
+        if (S.trans_d) e->k_bound[s] = b;
+        if (bounds_out) bounds_out[s] = e->k_bound[s];
+    }
     return BBB_OK;
 }
 
@@ -1317,7 +1359,9 @@ int bbb_engine_step_hosted_mapped(bbb_engine *e, const void *host_in, void *host
     // the chain kernel's programmatic dependent, every warp waiting for its own chain's completion signal
     // (BBB_MAPPED_PDL=1), 0.141 ms -- the waiting warps cost the chain kernel's tail more than the overlap gains; the
     // host polling a pinned word written by the kernel's last block behind system-wide fences instead of an event,
-    // 0.154 ms -- a system-wide fence per block waits for the block's writes over the bus.
+    // 0.154 ms -- a system-wide fence per block waits for the block's writes over the bus; comparing the upload with a
+    // device-side shadow of the records last written (two contiguous reads instead of scattered reads of the resident
+    // arrays), 0.130 ms -- no gain: what the comparison costs is the read over the bus, not the resident side.
     const int seq = ++e->mapped_seq;
     io.chain_done = e->mapped_pdl ? e->mapped_chain_done : nullptr;
     io.seq = seq;

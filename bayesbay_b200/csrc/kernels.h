@@ -106,6 +106,7 @@ int launch_state_image_ragged(const EngineParams &host_params, int mode, void *i
 // records of the mapped hosted step (hosted.cuh): all chains -> io.out; flagged chains of io.in -> engine slot 0
 int launch_hosted_pack(const EngineParams &host_params, const HostedIO &io, cudaStream_t stream);
 int launch_hosted_unpack(const EngineParams &host_params, const HostedIO &io, cudaStream_t stream);
+int launch_max_k(const EngineParams *dev_params, long long C, int32_t *out /* device [n_spaces], zeroed */, cudaStream_t stream);
 // save point: states + noise + temperature sections of the chain-major image (step_kernels.cu), d_pred of a chain-local
 // ray target from its resident residuals
 long long save_point_state_words(const EngineParams &host_params, const int32_t *kb);

@@ -923,6 +923,21 @@ int launch_hosted_unpack(const EngineParams &p, const HostedIO &io, cudaStream_t
     k_hosted_unpack<<<blocks_for(p.buf.n_chains, 8), 256, 0, st>>>(p, io);
     return (int)cudaGetLastError();
 }
+// largest current k of every space over the resident chains (out[s], zeroed by the caller)
+__global__ void k_max_k(const EngineParams *epp, int32_t *out) {
+    const EngineParams &ep = *epp;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int s = 0; s < ep.spec.n_spaces; ++s) {
+        int k = c < ep.buf.n_chains ? k_ref(ep.buf, s, (int)ep.buf.sel[s][c], c) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, o));
+        if ((threadIdx.x & 31) == 0 && k > 0) atomicMax(out + s, k);
+    }
+}
+int launch_max_k(const EngineParams *p, long long C, int32_t *out, cudaStream_t st) {
+    k_max_k<<<blocks_for(C, 256), 256, 0, st>>>(p, out);
+    return (int)cudaGetLastError();
+}
 int ragged_header_rows(const EngineParams &p) {
     int rows = p.spec.n_spaces + 2;  // k per space, temperature, iteration
     for (int t = 0; t < p.spec.n_targets; ++t)

@@ -231,9 +231,12 @@ int bbb_engine_init_states(bbb_engine *e, void *stream);
 int bbb_engine_refresh(bbb_engine *e, void *stream);
 /* Performance hint: an upper bound of the current number of cells over all resident chains of `space`
  * (kmin <= bound <= kmax).  The engine sizes shared-memory staging by it and raises it by one per step on its
- * own; callers may tighten it with the true maximum of k at a synchronisation point.  A bound BELOW the
- * true maximum is an error the engine cannot detect. */
+ * own; callers may tighten it at a synchronisation point.  A bound BELOW the true maximum of the resident chains
+ * (measured on the device by the call; it blocks) is refused with BBB_ERR_INVALID.
+ * bbb_engine_sync_k_bound measures the true maximum of every trans-dimensional space on the device (one kernel, blocks
+ * on `stream`), sets the bounds to it and reports them in bounds_out[n_spaces] (may be NULL). */
 int bbb_engine_set_k_bound(bbb_engine *e, int space, int32_t bound);
+int bbb_engine_sync_k_bound(bbb_engine *e, int32_t *bounds_out, void *stream);
 /* Advance every chain n_steps iterations: `BaseMarkovChain.advance_chain`
  * (src/bayesbay/_markov_chain.py:249-297) for all chains at once. */
 int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream);

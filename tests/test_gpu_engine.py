@@ -813,6 +813,27 @@ def _records_in_use(eng, records, like):
     return out.view(-1, rw)
 
 
+def test_k_bound_is_checked_on_the_device():
+    """bbb_engine_set_k_bound refuses a bound below the largest k of the resident chains (it would let the ray kernel index
+    outside its value table); bbb_engine_sync_k_bound measures that maximum on the device."""
+    import ctypes as C
+
+    from bayesbay_b200 import _lib as L
+
+    spec = problems.spec_from_ingredients(problems.tomo_small())
+    eng = _engine(spec, 64, seed=3)
+    eng.init_states()
+    eng.step(40)
+    k_true = int(eng.gather_space(0)[0].max().item())
+    out = (C.c_int32 * len(spec["spaces"]))()
+    L.check(eng.lib.bbb_engine_sync_k_bound(eng._handle, out, eng._stream))
+    assert out[0] == k_true
+    L.check(eng.lib.bbb_engine_set_k_bound(eng._handle, 0, k_true))
+    with pytest.raises(ValueError, match="below the largest k"):
+        L.check(eng.lib.bbb_engine_set_k_bound(eng._handle, 0, k_true - 1))
+    eng.step(5)  # (the engine goes on with the bound it has)
+
+
 def test_exception_counters():
     """What the reference reports under statistics["exceptions"] (src/bayesbay/_markov_chain.py:205-247) has a device
     analogue: proposals with a non-finite likelihood ratio are rejected and counted; rejection-sampling loops that give
