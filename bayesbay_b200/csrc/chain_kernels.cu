@@ -313,14 +313,17 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
         if (tid == CS_THREADS - 1) finish_gather(ep, c, s_fin);  // thread 0 decides from these after the forward
     }
     int h_words = 0;
+    unsigned long long h_pref = 0;
     if constexpr (HOSTED) {
-        // The uploaded record is requested now (one 128-byte line per thread, into the L2) and compared after the first
-        // rasterisation pass, so that the trip over the bus overlaps the pass.  (Measured alternatives, both slower on
-        // B200: asynchronous copies of the record into a shared-memory staging area with the resident cells captured
-        // next to it in the tables phase, 0.142 against 0.131 ms per call; comparing right here, 0.137.)
+        // The uploaded record is requested now (one word per thread, held in a register) and compared after the first
+        // rasterisation pass, so that the trip over the bus overlaps the tables and the pass: 0.125 ms per call.  (Measured
+        // alternatives, all slower on B200: an L2 prefetch of the record's lines instead of the register, 0.131 ms;
+        // comparing after the second pass, 0.132; comparing right here, 0.137; asynchronous copies of the record into a
+        // shared-memory staging area with the resident cells captured next to it in the tables phase, 0.142.)
         h_words = hosted_words_in_use(ep, io, c);
-        const unsigned long long *line = io.in + c * io.stride + 16 * tid;
-        if (16 * tid < io.stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+        // (space 0's cells follow the header: one contiguous run of the record, thread tid requests word tid of it now)
+        const int run = io.hrw + k_ref(B, 0, (int)B.sel[0][c], c) * (P.spaces[0].ndim + P.spaces[0].n_params);
+        if (tid < run) h_pref = io.in[c * io.stride + tid];
     }
     const int prop = cur ^ 1;
     (void)move;
@@ -482,7 +485,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
         if (scn || reach) queue_at(atomicAdd(&s_back, 1)) = ((unsigned)(g0 >> 4) << 17) | (reach ? 1u << 16 : 0u) | scn;
     }
     bool h_bad = false;
-    if constexpr (HOSTED) h_bad = hosted_compare(ep, io, io.in + c * io.stride, c, tid, CS_THREADS);
+    if constexpr (HOSTED) h_bad = hosted_compare_prefetched(ep, io, io.in + c * io.stride, c, tid, CS_THREADS, h_pref);
     CS_TL(10);
     cs_sync<FUSED>();
     CS_TL(2);

@@ -66,6 +66,30 @@ __device__ __forceinline__ bool hosted_compare(const EngineParams &ep, const Hos
     }
     return bad;
 }
+// The same with this thread's FIRST word of the record (word `tid` of the contiguous run header + cells of space 0) already
+// in a register: the chain kernel requests it when the block starts, so that the trip over the bus overlaps the tables
+// and the first rasterisation pass.  `pref` is rec[tid] when tid < hrw + (cells of space 0 in use) words.
+__device__ __forceinline__ bool hosted_compare_prefetched(const EngineParams &ep, const HostedIO &io, const unsigned long long *rec, long long c,
+                                                          int tid, int nth, unsigned long long pref) {
+    const bbb_problem_spec &P = ep.spec;
+    const bbb_buffers &B = ep.buf;
+    bool bad = false;
+    {
+        const bbb_space_spec &S = P.spaces[0];
+        const int slot = (int)B.sel[0][c], n = io.hrw + k_ref(B, 0, slot, c) * (S.ndim + S.n_params);
+        for (int j = tid; j < n; j += nth) {
+            const unsigned long long up = j == tid ? pref : rec[j];
+            const unsigned long long here = j < io.hrw ? hosted_header_word(P, B, c, j) : hosted_cell_word(B, S, 0, slot, c, j - io.hrw);
+            bad |= up != here;
+        }
+    }
+    for (int s = 1; s < P.n_spaces; ++s) {
+        const bbb_space_spec &S = P.spaces[s];
+        const int slot = (int)B.sel[s][c], n = k_ref(B, s, slot, c) * (S.ndim + S.n_params);
+        for (int i = tid; i < n; i += nth) bad |= rec[io.base[s] + i] != hosted_cell_word(B, S, s, slot, c, i);
+    }
+    return bad;
+}
 // The CURRENT state of chain c into its record of the out image (all threads of the group; the caller has made the
 // decision's writes visible with a barrier).  Thread 0 also counts the bytes of the exchange.
 __device__ __forceinline__ void hosted_write(const EngineParams &ep, const HostedIO &io, long long c, int tid, int nth, int words_in) {
