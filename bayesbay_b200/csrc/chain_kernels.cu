@@ -822,7 +822,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
     CS_TL_G(17);
     const int planes = MULTI ? -1 : n_touch;
     if (!s_accept) {
-        if constexpr (HOSTED) hosted_write(ep, io, c, tid, CS_THREADS, h_words);
+        if constexpr (HOSTED) hosted_write(ep, io, c, tid, CS_THREADS, h_words, s, cur, k_old);
         return planes;
     }
 
@@ -879,7 +879,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
         const IdxT owner = (IdxT)((pk & CS_BACK) ? (pk & CS_M_MASK) : (unsigned)ins);
         for (int q = 0; q < (1 << (2 * lvl)); ++q) row[g_first + q] = owner;
     }
-    if constexpr (HOSTED) hosted_write(ep, io, c, tid, CS_THREADS, h_words);
+    if constexpr (HOSTED) hosted_write(ep, io, c, tid, CS_THREADS, h_words, s, prop, k_new);
     CS_TL(8);
     CS_TL_G(17);
     return planes;

@@ -92,15 +92,20 @@ __device__ __forceinline__ bool hosted_compare_prefetched(const EngineParams &ep
 }
 // The CURRENT state of chain c into its record of the out image (all threads of the group; the caller has made the
 // decision's writes visible with a barrier).  Thread 0 also counts the bytes of the exchange.
-__device__ __forceinline__ void hosted_write(const EngineParams &ep, const HostedIO &io, long long c, int tid, int nth, int words_in) {
+// (s_known >= 0: the caller knows the current slot and k of that space -- the chain kernel after its decision -- which
+// saves the two dependent loads in front of the cells' loads)
+__device__ __forceinline__ void hosted_write(const EngineParams &ep, const HostedIO &io, long long c, int tid, int nth, int words_in,
+                                             int s_known = -1, int slot_known = 0, int k_known = 0) {
     const bbb_problem_spec &P = ep.spec;
     const bbb_buffers &B = ep.buf;
     unsigned long long *rec = io.out + c * io.stride;
-    for (int i = tid; i < io.hrw; i += nth) rec[i] = hosted_header_word(P, B, c, i);
+    for (int i = tid; i < io.hrw; i += nth)
+        rec[i] = i == s_known ? (unsigned long long)(long long)k_known : hosted_header_word(P, B, c, i);
     int words = io.hrw;
     for (int s = 0; s < P.n_spaces; ++s) {
         const bbb_space_spec &S = P.spaces[s];
-        const int slot = (int)B.sel[s][c], n = k_ref(B, s, slot, c) * (S.ndim + S.n_params);
+        const int slot = s == s_known ? slot_known : (int)B.sel[s][c];
+        const int n = (s == s_known ? k_known : k_ref(B, s, slot, c)) * (S.ndim + S.n_params);
         for (int i = tid; i < n; i += nth) rec[io.base[s] + i] = hosted_cell_word(B, S, s, slot, c, i);
         words += n;
     }
