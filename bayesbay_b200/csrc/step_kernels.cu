@@ -12,7 +12,10 @@ constexpr int STEP_THREADS = 64;  // 2 warps per block: spreads C = 1024 chains 
 
 // One WARP per chain: lane 0 owns the generator (every draw is broadcast), the O(k) nearest-site searches of
 // birth/death-from-neighbour run with lanes = sites, and the lanes write the proposed slot (lanes = cells).
-constexpr int PROPOSE_WARPS = 4;
+#ifndef PROPOSE_WARPS_N
+#define PROPOSE_WARPS_N 4
+#endif
+constexpr int PROPOSE_WARPS = PROPOSE_WARPS_N;
 // Cost class of chain c's block in the chain kernel, 0 = longest.  est = a[move] + b[move] * (points per cell): block
 // times measured on the C3 shape with the two-pass rasterisation (tools/timeline.py: birth 20.1 + 2.49 x, death
 // 18.8 + 2.72 x, values 14.5 + 2.11 x, sites 21.0 + 0.96 x microseconds, x = G / (100 k)).  Only the ORDER of the
