@@ -122,6 +122,7 @@ struct bbb_engine {
     // signal (BBB_MAPPED_PDL=1 only).
     int32_t *mapped_mismatch, *mapped_flag_host, *mapped_chain_done;
     unsigned long long *mapped_moved;
+    bool proposer_finished;  // the pending proposal kernel (run_propose) has decided the chains that need no forward
     int mapped_seq;
     int mapped_pdl;  // developer switch BBB_MAPPED_PDL (default 0, see bbb_engine_step_hosted_mapped)
     cudaEvent_t ev_mapped_done;
@@ -455,12 +456,13 @@ static int run_raster(bbb_engine *e, int t, bool proposal, cudaStream_t st) {
 }
 
 // proposal + parallel write of the proposed slots
-static int run_propose(bbb_engine *e, cudaStream_t st) {
-    const bbb_problem_spec &P = e->host.spec;
+// (decide_no_forward: resident stepping of a chain-local engine -- chains whose proposal needs no forward are decided by
+// the proposal kernel and skipped by the chain kernel; never for a proposal drawn ahead of a hosted step)
+static int run_propose(bbb_engine *e, cudaStream_t st, bool decide_no_forward = false) {
     const long long C = e->host.buf.n_chains;
-    (void)P;
     e->order_pending[0] = true;
-    return launch_propose(e->host, 0, C, e->order_parity[0] * 4, nullptr, st);  // the proposal warps also write the proposed slots
+    e->proposer_finished = decide_no_forward && e->host.chain_local;
+    return launch_propose(e->host, 0, C, e->order_parity[0] * 4, nullptr, st, nullptr, 0, nullptr, e->proposer_finished);
 }
 
 static int run_spmm(bbb_engine *e, int t, bool proposal, double *dpred, bool write_partial, cudaStream_t st) {
@@ -597,7 +599,9 @@ static int run_chain_step(bbb_engine *e, cudaStream_t st) {
     const bbb_problem_spec &P = e->host.spec;
     const bbb_target_spec &T = P.targets[e->ray_t];
     int rc = launch_chain_step(e->host, 0, e->host.buf.n_chains, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
-                               idx_bytes_of(P, e->ray_t), e->order_pending[0] ? e->order_parity[0] * 4 : -1, e->dependent_launch >= 1, nullptr, st);
+                               idx_bytes_of(P, e->ray_t), e->order_pending[0] ? e->order_parity[0] * 4 : -1, e->dependent_launch >= 1, nullptr, st,
+                               nullptr, e->proposer_finished);
+    e->proposer_finished = false;
     if (rc != 0) return rc;
     if (e->order_pending[0]) { e->order_parity[0] ^= 1; e->order_pending[0] = false; }
     bump_k_bound(e, 1);
@@ -641,10 +645,11 @@ static int run_chain_steps_direct(bbb_engine *e, long long n, cudaStream_t st) {
         for (int h = 0; h < NP && rc == 0; ++h) {
             const long long c0 = h * part < C ? h * part : C, c1 = (h + 1) * part < C ? (h + 1) * part : C;
             if (c0 >= c1) continue;
-            rc = launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, nullptr, e->half_stream[h]);
+            rc = launch_propose(e->host, c0, c1, e->order_parity[h] * 4 + h, nullptr, e->half_stream[h], nullptr, 0, nullptr, true);
             if (rc == 0)
                 rc = launch_chain_step(e->host, c0, c1, e->ray_t, T.csc_tile_rays, T.n_data, P.spaces[T.space].kmax,
-                                       idx_bytes_of(P, e->ray_t), e->order_parity[h] * 4 + h, e->dependent_launch >= 2, nullptr, e->half_stream[h]);
+                                       idx_bytes_of(P, e->ray_t), e->order_parity[h] * 4 + h, e->dependent_launch >= 2, nullptr, e->half_stream[h],
+                                       nullptr, true);
             e->order_parity[h] ^= 1;
         }
     }
@@ -799,7 +804,7 @@ int bbb_engine_step(bbb_engine *e, int64_t n_steps, void *stream) {
         return BBB_OK;
     }
     for (int64_t it = 0; it < n_steps; ++it) {
-        CU(run_propose(e, st));
+        CU(run_propose(e, st, true));
         if (e->host.chain_local) {
             CU(run_chain_step(e, st));
         } else {
@@ -822,7 +827,7 @@ int bbb_engine_stage(bbb_engine *e, int stage, void *stream) {
     const long long C = e->host.buf.n_chains;
     if (!e->has_ray) return fail(BBB_ERR_UNSUPPORTED, "staged stepping needs a ray target (other problems run the fused kernel)");
     switch (stage) {
-        case 0: CU(run_propose(e, st)); break;
+        case 0: CU(run_propose(e, st, true)); break;
         case 1:
             if (e->host.chain_local) break;
             for (int t = 0; t < P.n_targets; ++t)

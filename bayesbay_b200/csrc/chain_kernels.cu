@@ -238,7 +238,7 @@ __device__ __forceinline__ void fx_add4(unsigned lo_s, unsigned hi_s, const int 
 // and the new state is written to the chain's record of the out image.
 template <typename IdxT, bool MULTI, bool FUSED, bool HOSTED = false>
 __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, long long c, const int32_t *guard,
-                                               unsigned char *cs_smem, ItemRec *rec, const HostedIO &io) {
+                                               unsigned char *cs_smem, ItemRec *rec, const HostedIO &io, int proposer_finished = 0) {
     constexpr int NW = FUSED ? CS_MAIN_WARPS : CS_WARPS;  // warps in the body
     constexpr int NTH = NW * 32;
     const bbb_problem_spec &P = ep.spec;
@@ -301,7 +301,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
                 hosted_write(ep, io, c, tid, CS_THREADS, words_in);
                 return -2;
             }
-            if (tid == 0) {
+            if (tid == 0 && !proposer_finished) {  // (else: decided by the warp that drew the proposal, k_propose)
                 Rng rng;
                 rng_begin(rng, ep, c, STREAM_STEP, true);
                 finish_chain(ep, c, rng);
@@ -892,7 +892,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
 template <typename IdxT, bool MULTI, bool HOSTED>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
                                                               int order_slot, const int32_t *guard, int n_launch,
-                                                              const __grid_constant__ HostedIO io) {
+                                                              const __grid_constant__ HostedIO io, int proposer_finished) {
     const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
     const int tid = threadIdx.x;
@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             for (int i = 1; i < BBB_ORDER_BUCKETS; ++i) cls += b >= s_cum[i] ? 1 : 0;
             c = B.block_order[(long long)cls * C + c_first + (b - s_cum[cls])];
         }
-        chain_step_body<IdxT, MULTI, false, HOSTED>(ep, t, c, guard, cs_smem, nullptr, io);
+        chain_step_body<IdxT, MULTI, false, HOSTED>(ep, t, c, guard, cs_smem, nullptr, io, proposer_finished);
         if (persistent) __syncthreads();
     }
 }
@@ -1288,7 +1288,8 @@ extern "C" int bbb_debug_timeline_clear() {
 #endif
 
 int launch_chain_step(const EngineParams &dev, long long c_first, long long c_end, int t, int tile_rays, long long n_data, int K,
-                      int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard, cudaStream_t st, const HostedIO *hosted) {
+                      int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard, cudaStream_t st, const HostedIO *hosted,
+                      bool proposer_finished) {
     if (dev.buf.block_order == nullptr) order_slot = -1;
     // programmatic dependent launch behind the proposal kernel of the same stream (see the kernel's prologue)
     cudaLaunchAttribute attr[1];
@@ -1316,7 +1317,7 @@ int launch_chain_step(const EngineParams &dev, long long c_first, long long c_en
     auto launch = [&](auto kernel) -> int {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        return (int)cudaLaunchKernelEx(&cfg, kernel, dev, t, c_first, order_slot, guard, (int)n_launch, hio);
+        return (int)cudaLaunchKernelEx(&cfg, kernel, dev, t, c_first, order_slot, guard, (int)n_launch, hio, proposer_finished ? 1 : 0);
     };
     int rc;
     if (hosted != nullptr) {

@@ -67,7 +67,7 @@ long long chain_local_tile_rays(long long n_data, int kmax, long long n_points);
 struct HostedIO;  // hosted.cuh: the mapped hosted step (records in pinned host memory read / written by the kernel)
 int launch_chain_step(const EngineParams &host_params, long long c_first, long long c_end, int target, int tile_rays,
                       long long n_data, int K, int idx_bytes, int order_slot, bool dependent_launch, const int32_t *guard,
-                      cudaStream_t stream, const HostedIO *hosted = nullptr);
+                      cudaStream_t stream, const HostedIO *hosted = nullptr, bool proposer_finished = false);
 long long chain_run_ctl_words(long long n_chains_engine);
 // the fused persistent run (k_chain_run): n_iters iterations of the chains [c_first, c_end) in one launch of n_blocks
 // blocks; ctl = chain_run_ctl_words(n_chains of the engine) int32 control words, zero before the launch (left zero by it)
@@ -85,8 +85,11 @@ int launch_residual_transpose(const double *dpred, double *res, long long R, lon
 // guard (device, may be NULL): a non-zero word makes the launch a no-op (hosted step, abi.cu)
 // wait_done != NULL: launched as the programmatic dependent of the hosted chain kernel in front of it; the warp of chain c
 // waits (bounded; *wait_failed is raised otherwise) until wait_done[c] == wait_seq
+// finish_no_forward (chain-local engines): chains whose proposal needs no forward are decided by the proposal kernel
+// itself; the chain kernel behind it must then be launched with proposer_finished = true
 int launch_propose(const EngineParams &host_params, long long c_first, long long c_end, int order_slot, const int32_t *guard,
-                   cudaStream_t stream, const int32_t *wait_done = nullptr, int wait_seq = 0, int32_t *wait_failed = nullptr);
+                   cudaStream_t stream, const int32_t *wait_done = nullptr, int wait_seq = 0, int32_t *wait_failed = nullptr,
+                   bool finish_no_forward = false);
 int launch_finish(const EngineParams &host_params, long long C, cudaStream_t stream);
 int launch_corr_sums(const EngineParams *dev_params, long long C, int target, int proposal, cudaStream_t stream);
 int launch_fused_steps(const EngineParams &host_params, long long C, long long n_steps, cudaStream_t stream);

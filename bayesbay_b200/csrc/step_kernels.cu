@@ -42,7 +42,7 @@ __device__ __forceinline__ int block_cost_class(const EngineParams &ep, long lon
 
 __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_constant__ EngineParams ep, long long c_first, long long c_end,
                                                                 int order_slot, const int32_t *guard, const int32_t *wait_done, int wait_seq,
-                                                                int32_t *wait_failed) {
+                                                                int32_t *wait_failed, int finish_no_forward) {
     // the chain kernel behind this launch may become resident now (it waits for this grid before it reads a proposal)
     asm volatile("griddepcontrol.launch_dependents;");
     // work counter of the (persistent) chain kernel behind this launch: the 16th word of the launch's class counts
@@ -77,8 +77,35 @@ __global__ void __launch_bounds__(PROPOSE_WARPS * 32) k_propose(const __grid_con
     rng.begin(s_draw[w][0], s_draw[w][1], B.tape != nullptr ? B.tape + c * B.tape_stride : nullptr,
               B.tape != nullptr ? B.tape_cursor[c] : 0, B.tape_stride, ep.spec.seed, (uint64_t)(B.chain_id0 + c), (uint64_t)B.iteration[c],
               STREAM_STEP);
-    propose_chain(ep.spec, ep.buf, c, rng, false);
-    if ((threadIdx.x & 31) == 0) B.tape_cursor[c] = rng.after();
+    __shared__ Edit s_edit[PROPOSE_WARPS];
+    Edit &ed = s_edit[w];
+    propose_chain(ep.spec, ep.buf, c, rng, false, ed);
+    const long long cursor = rng.after();
+    if ((threadIdx.x & 31) == 0) B.tape_cursor[c] = cursor;
+    // Chain-local engines, resident stepping: a proposal that needs no forward (noise move, move in another space,
+    // rejected by the prior) is DECIDED here, by the warp that drew it -- same expressions, same generator positions as
+    // the chain kernel's own path for such chains (finish.cuh) -- and the chain's block of the chain kernel exits at
+    // once.  (Not when the proposal is drawn ahead of a hosted step: nothing may be decided before the uploaded state
+    // has been compared.)
+    if (finish_no_forward) {
+        __syncwarp();
+        const int move = ed.move;
+        const double lpr = ed.lpr;
+        if (!target_touched(ep.spec, move, lpr, ep.ray_t) && (threadIdx.x & 31) == 0) {
+            __shared__ FinishIn s_fin[PROPOSE_WARPS];
+            __shared__ FinishPre s_pre[PROPOSE_WARPS];
+            FinishIn &fin = s_fin[w];
+            fin.move = move;
+            fin.lpr = lpr;
+            fin.cursor = cursor;
+            finish_gather_rest(ep, c, fin);
+            Rng r2;
+            rng_resume(r2, ep, c, fin);
+            finish_pre(ep, c, fin, r2, -1, s_pre[w]);
+            rng_end(r2, ep, c);
+            finish_post(ep, c, fin, s_pre[w], -1, 0.0);
+        }
+    }
     if (order_slot >= 0) {  // file the chain for the longest-first block order of the chain kernel
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
@@ -792,10 +819,12 @@ __global__ void k_phi_from_partial(const double *partial, int n_tiles, long long
 static inline int blocks_for(long long C, int threads) { return (int)((C + threads - 1) / threads); }
 
 int launch_propose(const EngineParams &p, long long c_first, long long c_end, int order_slot, const int32_t *guard, cudaStream_t st,
-                   const int32_t *wait_done, int wait_seq, int32_t *wait_failed) {
+                   const int32_t *wait_done, int wait_seq, int32_t *wait_failed, bool finish_no_forward) {
     if (!p.chain_local || p.buf.block_order == nullptr) order_slot = -1;
+    if (!p.chain_local) finish_no_forward = false;  // (the full-SpMM step decides every chain in k_finish)
     if (wait_done == nullptr) {
-        k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end, order_slot, guard, nullptr, 0, nullptr);
+        k_propose<<<blocks_for(c_end - c_first, PROPOSE_WARPS), PROPOSE_WARPS * 32, 0, st>>>(p, c_first, c_end, order_slot, guard, nullptr, 0, nullptr,
+                                                                                             finish_no_forward ? 1 : 0);
         return (int)cudaGetLastError();
     }
     // programmatic dependent of the hosted chain kernel in front of it in `st` (per-chain completion signals)
@@ -808,7 +837,7 @@ int launch_propose(const EngineParams &p, long long c_first, long long c_end, in
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const int rc = (int)cudaLaunchKernelEx(&cfg, k_propose, p, c_first, c_end, order_slot, guard, wait_done, wait_seq, wait_failed);
+    const int rc = (int)cudaLaunchKernelEx(&cfg, k_propose, p, c_first, c_end, order_slot, guard, wait_done, wait_seq, wait_failed, 0);
     return rc != 0 ? rc : (int)cudaGetLastError();
 }
 int launch_corr_sums(const EngineParams *p, long long C, int target, int proposal, cudaStream_t st) {
