@@ -42,6 +42,7 @@ namespace bbb {
 #ifndef CS_AB_LIST
 #define CS_AB_LIST 1
 #endif
+
 constexpr int CS_THREADS = 512;
 constexpr int CS_WARPS = CS_THREADS / 32;
 constexpr int CS_CHUNK = CS_THREADS;       // change-list entries prepared per round
@@ -643,6 +644,14 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
     unsigned short *touch = reinterpret_cast<unsigned short *>(prep);
     int n_touch = -1;  // >= 0: `touch` lists the touched rays of the (only) tile
     for (int tile = 0; tile < NT; ++tile) {
+        if (MULTI) {
+            // The parking pass below reads the residual of every touched ray of this tile.  A good part of the rays are
+            // touched and 16 rays share a 128-byte line, so practically every line of the tile's stretch of the row is read
+            // anyway: all of them are requested now, one prefetch per line, and the reads find them in the L2 instead of
+            // waiting for DRAM (C5: 0.800 -> 0.791 ms per iteration; no effect on single-tile problems, where it is off).
+            const int pr0 = tile * RT, pnr = min(RT, R - pr0);
+            for (int i = tid; 16 * i < pnr; i += NTH) asm volatile("prefetch.global.L2 [%0];" ::"l"(res + pr0 + 16 * i));
+        }
         if (tile > 0) zero_acc();
         accumulate(tile);
         CS_TL(5);
