@@ -802,6 +802,56 @@ def test_hosted_step_mapped_records(monkeypatch, variant):
         eng.step_hosted_mapped(cur, torch.zeros((n, rw), dtype=torch.int64))
 
 
+def test_hosted_step_mapped_with_several_spaces():
+    """The mapped hosted step on a problem with two parameter spaces and two targets (ray tomography + a plain space
+    read by a linear target): records hold both spaces' cells, moves of the plain space need no ray forward (decided in
+    the block's short path), fast path bit-identical to resident stepping, an edit in the SECOND space is detected."""
+    spec = problems.SPECS["tomo_joint_small"]()
+    n = 96
+    ref, eng = _engine(spec, n, seed=21), _engine(spec, n, seed=21)
+    for e in (ref, eng):
+        e.init_states()
+        e.step(10)
+    assert eng.chain_local and len(spec["spaces"]) == 2
+    rw = eng.hosted_record_words()
+    host = [torch.zeros((n, rw), dtype=torch.int64).pin_memory() for _ in range(2)]
+    eng.pack_states_records(host[0])
+    torch.cuda.synchronize()
+    kb = [sp["kmax"] for sp in spec["spaces"]]
+    n_steps = 120
+    for it in range(n_steps):
+        eng.step_hosted_mapped(host[it & 1], host[(it + 1) & 1])
+        assert eng.step_hosted_mapped_wait() == 0
+        ref.step(1)
+    assert torch.equal(eng.pack_states(kb), ref.pack_states(kb)) and torch.equal(eng.res[0], ref.res[0])
+    assert torch.equal(eng.n_accepted, ref.n_accepted) and torch.equal(eng.n_proposed, ref.n_proposed)
+    last = host[n_steps & 1]
+    got = eng.decode_records(last)
+    for s_ in range(2):
+        k, sites, vals = (None if v is None else v.cpu().numpy() for v in eng.gather_space(s_))
+        nd = spec["spaces"][s_]["ndim"]
+        for c in range(n):
+            kc = got[c]["k"][s_]
+            assert kc == k[c]
+            cells = got[c]["cells"][s_]
+            for d in range(nd):
+                assert np.array_equal(cells[:, d], sites[d, :kc, c])
+            for p_ in range(vals.shape[0]):
+                assert np.array_equal(cells[:, nd + p_], vals[p_, :kc, c])
+    # edit a value of the plain (second) space of one chain
+    hrw = int(got[0]["header"].numel())
+    base1 = hrw + spec["spaces"][0]["kmax"] * (spec["spaces"][0]["ndim"] + len(spec["spaces"][0]["params"]))
+    c_edit = 17
+    last[c_edit, base1:base1 + 1] = (last[c_edit, base1:base1 + 1].view(torch.float64) + 0.125).view(torch.int64)
+    eng.step_hosted_mapped(last, host[(n_steps + 1) & 1])
+    assert eng.step_hosted_mapped_wait() == 1
+    assert (eng.iteration.cpu().numpy() == 10 + n_steps + 1).all()
+    ref.step(1)
+    a, b = eng.pack_states(kb).view(-1, n), ref.pack_states(kb).view(-1, n)
+    keep = [c for c in range(n) if c != c_edit]
+    assert torch.equal(a[:, keep], b[:, keep])
+
+
 def _records_in_use(eng, records, like):
     """`records` with the words behind every chain's cells in use taken from `like` (a pack leaves them untouched)."""
     out = like.clone()
