@@ -399,6 +399,9 @@ def cuda_arm(args):
     }
     if world == 1:
         out["api_run"] = api_run(par, ll, bb, C)
+        plug = plugin_run(ing, C)
+        if plug is not None:
+            out["plugin_run"] = plug
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(ing, spec, args.cpu_seconds)
     emit(out)
@@ -526,6 +529,51 @@ def api_run(par, ll, bb, n_chains, n_iterations=2000, save_every=100):
             "what": f"BayesianInversion.run(n_iterations={n_iterations}, save_every={save_every}) + get_results() on the same "
                     f"problem and chain count, host wall clock: the saved samples ({n_samples} states with d_pred, the "
                     "reference's defaults) are in host memory when run() returns and in the reference's result lists at the end"}
+
+
+def plugin_run(ing, n_chains, n_iterations=2000, save_every=100):
+    """The drop-in seam itself: the UNMODIFIED reference's `BayesianInversion.run(sampler=...)` (baseline/_ref, when it is
+    installed) with the plug-in sampler of bayesbay_b200/plugin.py, which runs the reference's own chain objects on the CUDA
+    engine.  Host wall clock of the second run (the first one also creates the engine); for information."""
+    import torch
+
+    try:
+        import importlib
+
+        from bayesbay_b200 import synthetic
+        from bayesbay_b200.plugin import cuda_samplers
+
+        ref_dir = os.path.join(REPO, "baseline", "_ref")
+        if not os.path.isdir(os.path.join(ref_dir, "bayesbay")):
+            return None
+        for mod in ("matplotlib", "shapely"):  # hard imports of the reference used for plotting / polygons only
+            try:
+                importlib.import_module(mod)
+            except ImportError:
+                stubs = os.path.join(ref_dir, "_stubs")
+                if stubs not in sys.path:
+                    sys.path.append(stubs)
+        if ref_dir not in sys.path:
+            sys.path.insert(0, ref_dir)
+        bayesbay = importlib.import_module("bayesbay")
+        par, ll = synthetic.build_problem(ing, bayesbay, synthetic.forward_operator)
+        inv = bayesbay.BayesianInversion(par, ll, n_chains=n_chains)
+        CudaVanillaSampler, _ = cuda_samplers(bayesbay, seed=3)
+        walls = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            inv.run(sampler=CudaVanillaSampler(), n_iterations=n_iterations, burnin_iterations=0, save_every=save_every, verbose=False)
+            torch.cuda.synchronize()
+            res = inv.get_results()
+            walls.append(time.perf_counter() - t0)
+        return {"value": n_chains * n_iterations / walls[1], "unit": UNIT, "wall_s": walls[1], "wall_s_first_run": walls[0],
+                "n_samples": len(res["voronoi.n_dimensions"]),
+                "what": f"bayesbay (unmodified, baseline/_ref) BayesianInversion.run(sampler=CudaVanillaSampler(), n_iterations="
+                        f"{n_iterations}, save_every={save_every}) + get_results() on {n_chains} chains the reference initialised itself: "
+                        "host wall clock of the second run (the first also builds the engine)"}
+    except Exception as e:  # pragma: no cover  (informational leg: never fails the bench)
+        log("plugin_run skipped:", repr(e))
+        return None
 
 
 def e2e_run(eng, steps, device, world, dist):

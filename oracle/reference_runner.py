@@ -46,8 +46,12 @@ def import_reference():
         bayesbay = sys.modules["bayesbay"]
         root = os.path.dirname(os.path.dirname(os.path.abspath(bayesbay.__file__)))
         env = os.environ.get("PYTHONPATH", "")
-        if root not in env.split(os.pathsep):
-            os.environ["PYTHONPATH"] = os.pathsep.join([root, REPO] + ([env] if env else []))
+        # (stub packages that stand in for matplotlib / shapely in this process must reach the workers too)
+        stubbed = any((getattr(sys.modules.get(m), "__file__", None) or "").startswith(STUB_DIR) for m in ("matplotlib", "shapely"))
+        want = [root] + ([STUB_DIR] if stubbed else []) + [REPO]
+        have = env.split(os.pathsep)
+        if any(p not in have for p in want):
+            os.environ["PYTHONPATH"] = os.pathsep.join(want + ([env] if env else []))
         return bayesbay
     if not available():
         raise ImportError("the reference is not installed under baseline/_ref (run __graft_entry__.build() where "
