@@ -703,6 +703,10 @@ __global__ void __launch_bounds__(SWAP_WAVE_THREADS) k_pt_swap_waves(double *gat
     if (tid == 0) s_acc = 0;
     __syncthreads();
     int n_acc = 0;
+    // Stamps carry the wave they were written in, counted DOWN, above the attempt's index: a stamp of a later wave is
+    // smaller than any stamp of an earlier one, so atomicMin overrides stale stamps and nothing has to be reset between
+    // waves (two barriers per wave instead of three).
+    int wave_key = 0x7fffffff >> 10;
     for (long long w0 = 0; w0 < n_total; w0 += SWAP_WAVE_THREADS) {
         const long long i = w0 + tid;
         bool pending = i < n_total;
@@ -724,14 +728,14 @@ __global__ void __launch_bounds__(SWAP_WAVE_THREADS) k_pt_swap_waves(double *gat
                     gathered[3 * (long long)b + 0]) / 2.0;
         }
         for (;;) {
+            --wave_key;
+            const int key = (wave_key << 10) | tid;
             if (pending) {
-                atomicMin(&stamp[a], tid);
-                atomicMin(&stamp[b], tid);
+                atomicMin(&stamp[a], key);
+                atomicMin(&stamp[b], key);
             }
             __syncthreads();
-            const bool ready = pending && stamp[a] == tid && stamp[b] == tid;
-            __syncthreads();
-            if (pending) { stamp[a] = 0x7fffffff; stamp[b] = 0x7fffffff; }
+            const bool ready = pending && stamp[a] == key && stamp[b] == key;
             if (ready) {
                 const double t1 = temps[a], t2 = temps[b], i1 = itemps[a], i2 = itemps[b];
                 const double llr = core / t1;
