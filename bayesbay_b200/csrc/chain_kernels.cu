@@ -53,7 +53,8 @@ constexpr unsigned CS_BACK = 1u << 31;     // entry of a point that LOST its own
 constexpr unsigned CS_G_MASK = (1u << CS_G_BITS) - 1u, CS_M_MASK = (1u << CS_M_BITS) - 1u;
 constexpr int CS_PTS = 16;                 // grid points per thread and pass = the largest merged group
 constexpr int CS_SMEM_BLOCK = 112 * 1024;  // two resident blocks per SM
-constexpr int CS_LIST_SMEM = 1024;         // change-list entries kept in shared memory (the rest spill to the global list)
+constexpr int CS_LIST_SMEM = 1024;         // change-list entries kept in shared memory at most (the rest spill to the global list;
+                                           // the launch may choose fewer, see fit_list_cap)
 // The misfit phases (touched-ray scan, residual arithmetic, block sum) are mapped onto the first CS_MAIN_WARPS warps in
 // EVERY variant of the kernel: the order of the floating-point misfit sum then does not depend on whether the block's
 // last warp is a worker (k_chain_step) or the proposer of the fused kernel (k_chain_run), and the variants stay
@@ -109,10 +110,32 @@ struct IdxVec {
 };
 
 // multi-tile problems also keep a bitmap of the touched rays (one bit per ray of the target)
-__host__ __device__ inline size_t chain_step_smem(int tile_rays, int K, long long n_data = 0) {
+__host__ __device__ inline size_t chain_step_smem(int tile_rays, int K, long long n_data = 0, int list_cap = CS_LIST_SMEM) {
     const bool multi = n_data > tile_rays;
-    return (size_t)tile_rays * 8 + (size_t)K * 4 * 8 + (size_t)CS_CHUNK * sizeof(PrepEntry) + (size_t)CS_LIST_SMEM * 4 +
+    return (size_t)tile_rays * 8 + (size_t)K * 4 * 8 + (size_t)CS_CHUNK * sizeof(PrepEntry) + (size_t)list_cap * 4 +
            (multi ? (size_t)((n_data + 31) / 32) * 4 : 0);
+}
+
+// An SM divides 256 KB between its L1 cache and shared memory in steps (shared-memory carve-outs of 100, 132, 164, 196,
+// 228 KB, ...), and every resident block costs 1 KB on top of what it asks for.  Two blocks that need a few bytes more
+// than a step are given the next one and lose 32 KB of L1: BASELINE configs[2] (10 000 rays, K = 200) sat 144 bytes above
+// the 196 KB step, and trimming the shared-memory head of the change list by 64 entries took the chain kernel from 0.0928 to
+// 0.0880 ms (back to back 0.085 -> 0.080 ms per iteration).  Single-tile problems therefore shrink that head (it only
+// decides how many entries spill to the global list) when that brings two blocks under a step.
+static int fit_list_cap(size_t smem_without_list, size_t static_smem) {
+    const size_t per_block_extra = static_smem + 1024;
+    const size_t steps_kb[] = {100, 132, 164, 196};
+    const size_t full = smem_without_list + (size_t)CS_LIST_SMEM * 4 + per_block_extra;
+    for (size_t kb : steps_kb) {
+        const size_t budget = kb * 1024 / 2;  // two blocks per SM
+        if (full <= budget) return CS_LIST_SMEM;  // fits this step as it is
+        const size_t floor_need = smem_without_list + 256 * 4 + per_block_extra;
+        if (floor_need <= budget) {
+            const size_t cap = (budget - smem_without_list - per_block_extra) / 4;
+            return (int)(cap & ~(size_t)63);
+        }
+    }
+    return CS_LIST_SMEM;
 }
 
 long long chain_local_tile_rays(long long n_data, int kmax, long long n_points) {
@@ -239,7 +262,8 @@ __device__ __forceinline__ void fx_add4(unsigned lo_s, unsigned hi_s, const int 
 // and the new state is written to the chain's record of the out image.
 template <typename IdxT, bool MULTI, bool FUSED, bool HOSTED = false>
 __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, long long c, const int32_t *guard,
-                                               unsigned char *cs_smem, ItemRec *rec, const HostedIO &io, int proposer_finished = 0) {
+                                               unsigned char *cs_smem, ItemRec *rec, const HostedIO &io, int proposer_finished = 0,
+                                               int list_cap = CS_LIST_SMEM) {
     constexpr int NW = FUSED ? CS_MAIN_WARPS : CS_WARPS;  // warps in the body
     constexpr int NTH = NW * 32;
     const bbb_problem_spec &P = ep.spec;
@@ -340,7 +364,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
     unsigned *s_list = reinterpret_cast<unsigned *>(prep + CS_CHUNK);
     unsigned *s_queue = reinterpret_cast<unsigned *>(prep);
     constexpr int CS_QUEUE_SMEM = CS_CHUNK * (int)sizeof(PrepEntry) / 4;
-    unsigned *s_touch = s_list + CS_LIST_SMEM;  // multi-tile: bitmap of the touched rays
+    unsigned *s_touch = s_list + list_cap;  // multi-tile: bitmap of the touched rays
 
     const int inner = move & 3;
     const bool recip = T.transform == BBB_TRANSFORM_RECIPROCAL;
@@ -348,7 +372,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
     // change list [0, G) and, behind it, the queue of 16-point groups with points to re-derive
     unsigned *list = B.change_list[t] + c * (long long)(G + (G + 15) / 16);
     unsigned *queue = list + G;
-    auto list_at = [&](int pos) -> unsigned & { return pos < (CS_AB_LIST ? CS_LIST_SMEM : 0) ? s_list[pos] : list[pos]; };
+    auto list_at = [&](int pos) -> unsigned & { return pos < (CS_AB_LIST ? list_cap : 0) ? s_list[pos] : list[pos]; };
     auto queue_at = [&](int pos) -> unsigned & { return pos < (CS_AB_LIST ? CS_QUEUE_SMEM : 0) ? s_queue[pos] : queue[pos]; };
     const int n_levels = T.csc_n_levels;
     IdxVec<IdxT> wv_next;
@@ -901,7 +925,7 @@ __device__ __forceinline__ int chain_step_body(const EngineParams &ep, int t, lo
 template <typename IdxT, bool MULTI, bool HOSTED>
 __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_constant__ EngineParams ep, int t, long long c_first,
                                                               int order_slot, const int32_t *guard, int n_launch,
-                                                              const __grid_constant__ HostedIO io, int proposer_finished) {
+                                                              const __grid_constant__ HostedIO io, int proposer_finished, int list_cap) {
     const bbb_buffers &B = ep.buf;
     const long long C = B.n_chains;
     const int tid = threadIdx.x;
@@ -962,7 +986,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) k_chain_step(const __grid_const
             for (int i = 1; i < BBB_ORDER_BUCKETS; ++i) cls += b >= s_cum[i] ? 1 : 0;
             c = B.block_order[(long long)cls * C + c_first + (b - s_cum[cls])];
         }
-        chain_step_body<IdxT, MULTI, false, HOSTED>(ep, t, c, guard, cs_smem, nullptr, io, proposer_finished);
+        chain_step_body<IdxT, MULTI, false, HOSTED>(ep, t, c, guard, cs_smem, nullptr, io, proposer_finished, list_cap);
         if (persistent) __syncthreads();
     }
 }
@@ -1319,14 +1343,26 @@ int launch_chain_step(const EngineParams &dev, long long c_first, long long c_en
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = dependent_launch ? 1 : 0;
-    const size_t smem = chain_step_smem(tile_rays, K, n_data);
     const bool multi = n_data > tile_rays;
     const HostedIO hio = hosted != nullptr ? *hosted : HostedIO{};
-    cfg.dynamicSmemBytes = smem;
     auto launch = [&](auto kernel) -> int {
+        // (multi-tile problems size their ray tiles to fill the block's budget: nothing to trim there)
+        int list_cap = CS_LIST_SMEM;
+        if (!multi) {
+            static size_t static_smem = (size_t)-1;  // (one per kernel instantiation: the lambda is generic)
+            if (static_smem == (size_t)-1) {
+                cudaFuncAttributes fa{};
+                cudaError_t e0 = cudaFuncGetAttributes(&fa, kernel);
+                if (e0 != cudaSuccess) return (int)e0;
+                static_smem = fa.sharedSizeBytes;
+            }
+            list_cap = fit_list_cap(chain_step_smem(tile_rays, K, n_data, 0), static_smem);
+        }
+        const size_t smem = chain_step_smem(tile_rays, K, n_data, list_cap);
+        cfg.dynamicSmemBytes = smem;
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        return (int)cudaLaunchKernelEx(&cfg, kernel, dev, t, c_first, order_slot, guard, (int)n_launch, hio, proposer_finished ? 1 : 0);
+        return (int)cudaLaunchKernelEx(&cfg, kernel, dev, t, c_first, order_slot, guard, (int)n_launch, hio, proposer_finished ? 1 : 0, list_cap);
     };
     int rc;
     if (hosted != nullptr) {
