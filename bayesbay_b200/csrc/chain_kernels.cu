@@ -123,6 +123,10 @@ __host__ __device__ inline size_t chain_step_smem(int tile_rays, int K, long lon
 // 0.0880 ms (back to back 0.085 -> 0.080 ms per iteration).  Single-tile problems therefore shrink that head (it only
 // decides how many entries spill to the global list) when that brings two blocks under a step.
 static int fit_list_cap(size_t smem_without_list, size_t static_smem) {
+    if (const char *cap = getenv("BBB_CHAIN_LIST_CAP")) {  // tests: force the spill to the global list
+        const long v = atol(cap);
+        return (int)(v < 0 ? 0 : (v > CS_LIST_SMEM ? CS_LIST_SMEM : v));
+    }
     const size_t per_block_extra = static_smem + 1024;
     const size_t steps_kb[] = {100, 132, 164, 196};
     const size_t full = smem_without_list + (size_t)CS_LIST_SMEM * 4 + per_block_extra;

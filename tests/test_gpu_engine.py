@@ -436,6 +436,35 @@ def test_chain_local_step_equals_full_forward(monkeypatch, name, n_chains, n_ste
     np.testing.assert_allclose((local.res[0].t() + dobs[:, None]).cpu().numpy(), dp.cpu().numpy(), rtol=1e-12)
 
 
+@pytest.mark.parametrize("tile_cap", [None, 200])
+def test_change_list_spill_to_global_memory_is_bit_identical(monkeypatch, tile_cap):
+    """The shared-memory head of the change list only decides how many entries spill to the chain's global list (the
+    launch trims it to fit the SM's shared-memory carve-out steps): a head of 8 entries (nearly everything spills) gives
+    bit-identical trajectories, index and residuals to the default head, single- and multi-tile."""
+    from bayesbay_b200 import synthetic
+
+    ing = synthetic.tomography_2d(nx=64, ny=48, n_sources_per_side=6, n_receivers=20, kmin=3, kmax=300)
+    spec = problems.spec_from_ingredients(ing)
+    if tile_cap is not None:
+        monkeypatch.setenv("BBB_CHAIN_TILE_RAYS", str(tile_cap))
+    out = []
+    for cap in (None, 8):
+        if cap is None:
+            monkeypatch.delenv("BBB_CHAIN_LIST_CAP", raising=False)
+        else:
+            monkeypatch.setenv("BBB_CHAIN_LIST_CAP", str(cap))
+        eng = _engine(spec, 80, seed=9)
+        eng.init_states()
+        for _ in range(30):
+            eng.step(1)
+        eng.step(40)
+        assert eng.chain_local and eng.ray_tiles(0) == (1 if tile_cap is None else eng.ray_tiles(0)) and (tile_cap is None or eng.ray_tiles(0) > 1)
+        out.append((eng.pack_states(300).clone(), eng.res[0].clone(), eng.idx_cm[0].clone(), eng.n_accepted.clone()))
+    monkeypatch.delenv("BBB_CHAIN_LIST_CAP", raising=False)
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+
+
 def test_chain_local_step_is_bit_reproducible_and_shard_independent():
     """The ray accumulators are fixed point, so neither the thread timing of a launch nor the way chains are
     sharded over engines may change a single bit of the trajectories."""
